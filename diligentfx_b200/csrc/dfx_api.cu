@@ -1,0 +1,164 @@
+// dfx_api.cu — status / error plumbing, attribute defaults, host-side helpers and device-plane utilities of the C-ABI.
+#include "dfx_common.cuh"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+namespace dfx
+{
+static thread_local char          g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+dfx_status set_error(dfx_status st, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return st;
+}
+dfx_status check_cuda(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return DFX_OK;
+    return set_error(DFX_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+__global__ void fill_kernel(float* p, int pitch_f, int wf, int h, int ch, float4 v)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= wf || y >= h) return;
+    int   c = x % ch;
+    float s = c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+    p[(size_t)y * pitch_f + x] = s;
+}
+} // namespace dfx
+
+using namespace dfx;
+
+extern "C"
+{
+const char* dfx_last_error(void) { return g_err; }
+int         dfx_version(void) { return 100; } // 0.1.0
+uint64_t    dfx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void dfx_ssao_attribs_default(dfx_ssao_attribs* a)
+{
+    // ScreenSpaceAmbientOcclusionStructures.fxh:64-98
+    *a = dfx_ssao_attribs{1.0f, 0.615f, 1.457f, 3.3f, 0.9f, 4.0f, 0, 1.0f, 0.5f, DFX_SSAO_ALGORITHM_GTAO, 0.0f, 0.0f};
+}
+void dfx_ssr_attribs_default(dfx_ssr_attribs* a)
+{
+    // ScreenSpaceReflectionStructures.fxh:43-80
+    *a = dfx_ssr_attribs{0.025f, 0.2f, 0u, 1, 0u, 128u, 0.3f, 4.0f, 1.0f, 0.9f, 0.9f, 1.0f};
+}
+void dfx_bloom_attribs_default(dfx_bloom_attribs* a)
+{
+    // BloomStructures.fxh:12-34
+    *a = dfx_bloom_attribs{0.15f, 1.0f, 0.125f, 0.75f, 1.0f, 0.0f, 0.0f, 0.0f};
+}
+void dfx_taa_attribs_default(dfx_taa_attribs* a)
+{
+    // TemporalAntiAliasingStructures.fxh:35-46
+    *a = dfx_taa_attribs{0.9375f, 0, 0, 0.0f};
+}
+void dfx_tonemap_attribs_default(dfx_tonemap_attribs* a)
+{
+    // ToneMappingStructures.fxh:24-52
+    *a = dfx_tonemap_attribs{DFX_TONE_MAPPING_MODE_UNCHARTED2, 1, 0.18f, 1, 3.0f, 1.0f, 0u, 0u, 1.0f, 1.0f, 1.0f, 0.0f};
+}
+
+// TemporalAntiAliasing.cpp:43-54
+static float halton_sequence(uint32_t Base, uint32_t Index)
+{
+    float Result = 0.0f, F = 1.0f;
+    while (Index > 0)
+    {
+        F      = F / static_cast<float>(Base);
+        Result = Result + F * static_cast<float>(Index % Base);
+        Index  = static_cast<uint32_t>(floorf(static_cast<float>(Index) / static_cast<float>(Base)));
+    }
+    return Result;
+}
+// TemporalAntiAliasing.cpp:63-78
+void dfx_taa_jitter_offset(uint32_t frame_index, uint32_t width, uint32_t height, float out[2])
+{
+    const uint32_t SampleCount = 16u;
+    out[0] = (halton_sequence(2u, (frame_index % SampleCount) + 1) - 0.5f) / (0.5f * static_cast<float>(width));
+    out[1] = (halton_sequence(3u, (frame_index % SampleCount) + 1) - 0.5f) / (0.5f * static_cast<float>(height));
+}
+// Bloom.cpp:152-156 with DiligentCore's ComputeMipLevelsCount (levels down to 1 of the larger dimension)
+int32_t dfx_bloom_mip_count(uint32_t width, uint32_t height, float radius)
+{
+    uint32_t m = width > height ? width : height, n = 0;
+    while (m > 0) ++n, m >>= 1;
+    return static_cast<int32_t>(radius * static_cast<float>(n));
+}
+
+static size_t bytes_per_texel(int fmt)
+{
+    switch (fmt)
+    {
+        case DFX_FORMAT_R32F: return 4;
+        case DFX_FORMAT_RG32F: return 8;
+        case DFX_FORMAT_RGBA32F: return 16;
+        case DFX_FORMAT_R8U: return 1;
+        default: return 0;
+    }
+}
+
+dfx_status dfx_plane_alloc(int32_t width, int32_t height, int32_t format, dfx_plane* out)
+{
+    DFX_REQUIRE(out != nullptr, "out must not be null");
+    size_t bpt = bytes_per_texel(format);
+    DFX_REQUIRE(bpt != 0 && width > 0 && height > 0, "bad plane description %dx%d fmt %d", width, height, format);
+    // rows padded to 128 B so every row start is a full-line boundary (coalesced 128-bit access, TMA-compatible pitch)
+    size_t pitch = ((size_t)width * bpt + 127) / 128 * 128;
+    void*  p     = nullptr;
+    DFX_CUDA(cudaMalloc(&p, pitch * (size_t)height));
+    out->ptr = p, out->pitch_bytes = pitch, out->width = width, out->height = height, out->format = format, out->reserved = 0;
+    return DFX_OK;
+}
+void dfx_plane_free(dfx_plane* p)
+{
+    if (p && p->ptr) cudaFree(p->ptr), p->ptr = nullptr;
+}
+dfx_status dfx_plane_upload(void* stream, const dfx_plane* dst, const void* host_src, size_t host_pitch)
+{
+    DFX_REQUIRE(dst && dst->ptr && host_src, "null argument");
+    size_t row = (size_t)dst->width * bytes_per_texel(dst->format);
+    DFX_CUDA(cudaMemcpy2DAsync(dst->ptr, dst->pitch_bytes, host_src, host_pitch ? host_pitch : row, row, dst->height, cudaMemcpyHostToDevice, as_stream(stream)));
+    return DFX_OK;
+}
+dfx_status dfx_plane_download(void* stream, const dfx_plane* src, void* host_dst, size_t host_pitch)
+{
+    DFX_REQUIRE(src && src->ptr && host_dst, "null argument");
+    size_t row = (size_t)src->width * bytes_per_texel(src->format);
+    DFX_CUDA(cudaMemcpy2DAsync(host_dst, host_pitch ? host_pitch : row, src->ptr, src->pitch_bytes, row, src->height, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return DFX_OK;
+}
+dfx_status dfx_plane_fill(void* stream, const dfx_plane* dst, const float value[4])
+{
+    DFX_REQUIRE(dst && dst->ptr && value, "null argument");
+    if (dst->format == DFX_FORMAT_R8U)
+    {
+        DFX_CUDA(cudaMemset2DAsync(dst->ptr, dst->pitch_bytes, value[0] != 0.0f ? 1 : 0, dst->width, dst->height, as_stream(stream)));
+        return DFX_OK;
+    }
+    int ch = dst->format == DFX_FORMAT_R32F ? 1 : dst->format == DFX_FORMAT_RG32F ? 2 : 4;
+    int wf = dst->width * ch;
+    dim3 grid(div_up(wf, 256), dst->height);
+    fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<float*>(dst->ptr), int(dst->pitch_bytes / 4), wf, dst->height, ch,
+                                                     make_float4(value[0], value[1], value[2], value[3]));
+    DFX_LAUNCHED("fill_kernel");
+    return DFX_OK;
+}
+dfx_status dfx_stream_synchronize(void* stream)
+{
+    DFX_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return DFX_OK;
+}
+} // extern "C"

@@ -1,0 +1,296 @@
+// dfx_common.cuh — device-side vocabulary shared by all kernels of libdfx_b200.so (sm_100a only).
+//
+// Conventions (the DiligentCore macros the reference shaders rely on, D3D/Vulkan flavour):
+//   pixel centre = (x + 0.5, y + 0.5), y down; UV = pos / size; NDC y up, NDC z == depth in [0,1];
+//   matrices are row-major and multiply row vectors: clip = float4(p, 1) * M.
+// Planes are pitched fp32 arrays in HBM; all global loads of read-only planes go through the non-coherent path
+// (ld.global.nc) and are 64/128-bit wide where the element type allows.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dfx_b200.h"
+
+namespace dfx
+{
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: status handling and launch accounting
+// ---------------------------------------------------------------------------------------------------------------------
+dfx_status set_error(dfx_status st, const char* fmt, ...);
+dfx_status check_cuda(cudaError_t e, const char* what);
+void       count_launch(int n = 1);
+
+#define DFX_REQUIRE(cond, ...)                                       \
+    do {                                                             \
+        if (!(cond)) return ::dfx::set_error(DFX_ERR_INVALID_ARG, __VA_ARGS__); \
+    } while (0)
+
+#define DFX_CUDA(call)                                               \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return ::dfx::check_cuda(e__, #call); \
+    } while (0)
+
+// after a kernel launch
+#define DFX_LAUNCHED(name)                                           \
+    do {                                                             \
+        ::dfx::count_launch();                                       \
+        cudaError_t e__ = cudaGetLastError();                        \
+        if (e__ != cudaSuccess) return ::dfx::check_cuda(e__, name); \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+inline int          div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// plane views
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+struct View
+{
+    T*  p;
+    int pitch; // in elements of T
+    int w, h;
+    __device__ __forceinline__ T&       at(int x, int y) const { return p[(size_t)y * pitch + x]; }
+    __device__ __forceinline__ const T* row(int y) const { return p + (size_t)y * pitch; }
+};
+
+template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+// Texture.Load semantics: out of bounds -> 0
+__device__ __forceinline__ float load0(const View<const float>& v, int x, int y)
+{
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (size_t)y * v.pitch + x) : 0.0f;
+}
+__device__ __forceinline__ float2 load0(const View<const float2>& v, int x, int y)
+{
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (size_t)y * v.pitch + x) : make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ float4 load0(const View<const float4>& v, int x, int y)
+{
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (size_t)y * v.pitch + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <class T>
+__device__ __forceinline__ T loadc(const View<const T>& v, int x, int y) // clamp addressing
+{
+    x = min(max(x, 0), v.w - 1);
+    y = min(max(y, 0), v.h - 1);
+    return __ldg(v.p + (size_t)y * v.pitch + x);
+}
+
+template <class T>
+inline bool make_view(const dfx_plane* pl, int fmt, View<T>& v)
+{
+    if (!pl || !pl->ptr || pl->format != fmt || pl->width <= 0 || pl->height <= 0) return false;
+    if (pl->pitch_bytes % sizeof(T) != 0 || pl->pitch_bytes < (size_t)pl->width * sizeof(T)) return false;
+    if (reinterpret_cast<uintptr_t>(pl->ptr) % sizeof(T) != 0) return false;
+    v.p     = static_cast<T*>(pl->ptr);
+    v.pitch = int(pl->pitch_bytes / sizeof(T));
+    v.w     = pl->width;
+    v.h     = pl->height;
+    return true;
+}
+#define DFX_VIEW(T, name, plane, fmt)                                                                   \
+    ::dfx::View<T> name;                                                                                \
+    if (!::dfx::make_view<T>(plane, fmt, name)) return ::dfx::set_error(DFX_ERR_INVALID_ARG, "bad plane '%s' (null, wrong format, pitch or alignment)", #plane)
+
+#define DFX_SAME_SIZE(a, b) DFX_REQUIRE((a).w == (b).w && (a).h == (b).h, "plane size mismatch: %s vs %s", #a, #b)
+
+inline bool rows_ok(dfx_rows r, int h) { return r.y0 >= 0 && r.y1 <= h && r.y0 <= r.y1; }
+
+struct PyrView
+{
+    View<const float> lv[DFX_MAX_MIPS];
+    int               levels;
+};
+struct PyrViewRW
+{
+    View<float> lv[DFX_MAX_MIPS];
+    int         levels;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small vector helpers (CUDA has the types but no operators)
+// ---------------------------------------------------------------------------------------------------------------------
+#define DFX_HD __device__ __forceinline__
+DFX_HD float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DFX_HD float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DFX_HD float2 operator*(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+DFX_HD float2 operator*(float2 a, float b) { return make_float2(a.x * b, a.y * b); }
+DFX_HD float2 operator*(float a, float2 b) { return make_float2(a * b.x, a * b.y); }
+DFX_HD float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+DFX_HD float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+DFX_HD float3 operator*(float3 a, float3 b) { return make_float3(a.x * b.x, a.y * b.y, a.z * b.z); }
+DFX_HD float3 operator*(float3 a, float b) { return make_float3(a.x * b, a.y * b, a.z * b); }
+DFX_HD float3 operator*(float a, float3 b) { return make_float3(a * b.x, a * b.y, a * b.z); }
+DFX_HD float3 operator/(float3 a, float b) { return make_float3(a.x / b, a.y / b, a.z / b); }
+DFX_HD float3 operator-(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
+DFX_HD float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+DFX_HD float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+DFX_HD float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+DFX_HD float4 operator*(float4 a, float b) { return make_float4(a.x * b, a.y * b, a.z * b, a.w * b); }
+DFX_HD float4 operator*(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
+DFX_HD float4 operator/(float4 a, float b) { return make_float4(a.x / b, a.y / b, a.z / b, a.w / b); }
+DFX_HD float  dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
+DFX_HD float  dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+DFX_HD float  dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+DFX_HD float3 cross(float3 a, float3 b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+DFX_HD float  length(float2 a) { return sqrtf(dot(a, a)); }
+DFX_HD float  length(float3 a) { return sqrtf(dot(a, a)); }
+DFX_HD float3 normalize(float3 a) { return a / length(a); }
+DFX_HD float3 xyz(float4 a) { return make_float3(a.x, a.y, a.z); }
+DFX_HD float4 f4(float3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
+DFX_HD float  saturate(float v) { return __saturatef(v); } // NaN -> 0, same as fmin(fmax(v,0),1)
+DFX_HD float  lerpf(float a, float b, float t) { return a + t * (b - a); }
+DFX_HD float3 lerp3(float3 a, float3 b, float t) { return a + t * (b - a); }
+DFX_HD float4 lerp4(float4 a, float4 b, float t) { return a + t * (b - a); }
+DFX_HD float  fracf(float v) { return v - floorf(v); }
+DFX_HD float  signf(float v) { return float((v > 0.0f) - (v < 0.0f)); }
+DFX_HD float  luminance(float3 c) { return dot(c, make_float3(0.299f, 0.587f, 0.114f)); }
+DFX_HD float  smoothstepf(float a, float b, float x)
+{
+    float t = saturate((x - a) / (b - a));
+    return t * t * (3.0f - 2.0f * t);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// camera block: the fields the kernels use, staged once per CTA into shared memory from dfx_camera_attribs[2] in HBM
+// ---------------------------------------------------------------------------------------------------------------------
+struct Mat4
+{
+    float m[4][4];
+};
+struct CamS
+{
+    float    vw, vh, ivw, ivh; // f4ViewportSize
+    float    px, py, pz;       // f4Position.xyz
+    uint32_t frame_index;
+    float    jx, jy;
+    // projection terms used by depth<->cameraZ and ScreenXYDepthToViewSpace
+    float m00, m11, m22, m32, m23, m33;
+};
+
+__device__ __forceinline__ void load_cam(CamS& c, const dfx_camera_attribs* a)
+{
+    c.vw = a->f4ViewportSize[0], c.vh = a->f4ViewportSize[1], c.ivw = a->f4ViewportSize[2], c.ivh = a->f4ViewportSize[3];
+    c.px = a->f4Position[0], c.py = a->f4Position[1], c.pz = a->f4Position[2];
+    c.frame_index = a->uiFrameIndex;
+    c.jx = a->f2Jitter[0], c.jy = a->f2Jitter[1];
+    c.m00 = a->mProj.m[0][0], c.m11 = a->mProj.m[1][1], c.m22 = a->mProj.m[2][2], c.m32 = a->mProj.m[3][2];
+    c.m23 = a->mProj.m[2][3], c.m33 = a->mProj.m[3][3];
+}
+__device__ __forceinline__ void load_mat(Mat4& d, const dfx_float4x4& s)
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d.m[r][c] = s.m[r][c];
+}
+
+// DepthToCameraZ / CameraZToDepth (ShaderUtilities.fxh:5-39): z = (m32 - d*m33) / (d*m23 - m22)
+DFX_HD float depth_to_camz(float d, const CamS& c) { return (c.m32 - d * c.m33) / (d * c.m23 - c.m22); }
+DFX_HD float camz_to_depth(float z, const CamS& c) { return (c.m22 * z + c.m32) / (c.m23 * z + c.m33); }
+// ScreenXYDepthToViewSpace (PostFX_Common.fxh:107-111) with TexUVToNormalizedDeviceXY(uv) = (uv - 0.5) * (2, -2)
+DFX_HD float3 screen_to_view(float u, float v, float depth, const CamS& c)
+{
+    float z  = depth_to_camz(depth, c);
+    float nx = (u - 0.5f) * 2.0f, ny = (v - 0.5f) * -2.0f;
+    return make_float3(z * nx / c.m00, z * ny / c.m11, z);
+}
+// float4(v,1) * M
+DFX_HD float4 mul_point(float3 v, const Mat4& M)
+{
+    return make_float4(v.x * M.m[0][0] + v.y * M.m[1][0] + v.z * M.m[2][0] + M.m[3][0],
+                       v.x * M.m[0][1] + v.y * M.m[1][1] + v.z * M.m[2][1] + M.m[3][1],
+                       v.x * M.m[0][2] + v.y * M.m[1][2] + v.z * M.m[2][2] + M.m[3][2],
+                       v.x * M.m[0][3] + v.y * M.m[1][3] + v.z * M.m[2][3] + M.m[3][3]);
+}
+// float4(v,0) * M (xyz)
+DFX_HD float3 mul_dir(float3 v, const Mat4& M)
+{
+    return make_float3(v.x * M.m[0][0] + v.y * M.m[1][0] + v.z * M.m[2][0], v.x * M.m[0][1] + v.y * M.m[1][1] + v.z * M.m[2][1],
+                       v.x * M.m[0][2] + v.y * M.m[1][2] + v.z * M.m[2][2]);
+}
+// ProjectPosition (PostFX_Common.fxh:85-92): world/view -> (u, v, depth)
+DFX_HD float3 project_position(float3 p, const Mat4& M)
+{
+    float4 c = mul_point(p, M);
+    float  x = c.x / c.w, y = c.y / c.w, z = c.z / c.w;
+    return make_float3(0.5f + 0.5f * x, 0.5f - 0.5f * y, z);
+}
+// InvProjectPosition (PostFX_Common.fxh:99-105): (u, v, depth) -> position
+DFX_HD float3 inv_project_position(float u, float v, float depth, const Mat4& M)
+{
+    float4 c = mul_point(make_float3((u - 0.5f) * 2.0f, (v - 0.5f) * -2.0f, depth), M);
+    return make_float3(c.x / c.w, c.y / c.w, c.z / c.w);
+}
+
+// Bayer4x4 (PostFX_Common.fxh:57-65)
+DFX_HD float bayer4x4(uint32_t x, uint32_t y, uint32_t frame)
+{
+    uint32_t wx = x & 3u, wy = y & 3u;
+    uint32_t A  = 2068378560u * (1u - (wx >> 1u)) + 1500172770u * (wx >> 1u);
+    uint32_t B  = (wy + ((wx & 1u) << 2u)) << 2u;
+    return float(((A >> B) + frame) & 0xFu) * (1.0f / 16.0f);
+}
+
+// GetBilinearSamplingInfoUC (ShaderUtilities.fxh:126-142)
+struct Bilin
+{
+    int   x0, y0, x1, y1;
+    float w00, w10, w01, w11;
+};
+DFX_HD Bilin bilinear_uc(float lx, float ly, int w, int h)
+{
+    lx -= 0.5f, ly -= 0.5f;
+    float fx0 = floorf(lx), fy0 = floorf(ly);
+    Bilin b;
+    int   x0 = (int)fx0, y0 = (int)fy0;
+    b.x0 = min(max(x0, 0), w - 1), b.y0 = min(max(y0, 0), h - 1);
+    b.x1 = min(max(x0 + 1, 0), w - 1), b.y1 = min(max(y0 + 1, 0), h - 1);
+    float x = lx - fx0, y = ly - fy0;
+    b.w00 = (1.0f - x) * (1.0f - y), b.w10 = x * (1.0f - y), b.w01 = (1.0f - x) * y, b.w11 = x * y;
+    return b;
+}
+
+// bilinear SampleLevel at normalised uv, clamp addressing
+template <class T>
+__device__ __forceinline__ T sample_linear_clamp(const View<const T>& t, float u, float v)
+{
+    float px = u * float(t.w) - 0.5f, py = v * float(t.h) - 0.5f;
+    float fx0 = floorf(px), fy0 = floorf(py);
+    int   x0 = (int)fx0, y0 = (int)fy0;
+    float fx = px - fx0, fy = py - fy0;
+    T     a = loadc(t, x0, y0), b = loadc(t, x0 + 1, y0), c = loadc(t, x0, y0 + 1), d = loadc(t, x0 + 1, y0 + 1);
+    return a * ((1.0f - fx) * (1.0f - fy)) + b * (fx * (1.0f - fy)) + c * ((1.0f - fx) * fy) + d * (fx * fy);
+}
+template <class T>
+__device__ __forceinline__ T sample_linear_border(const View<const T>& t, float u, float v)
+{
+    float px = u * float(t.w) - 0.5f, py = v * float(t.h) - 0.5f;
+    float fx0 = floorf(px), fy0 = floorf(py);
+    int   x0 = (int)fx0, y0 = (int)fy0;
+    float fx = px - fx0, fy = py - fy0;
+    T     a = load0(t, x0, y0), b = load0(t, x0 + 1, y0), c = load0(t, x0, y0 + 1), d = load0(t, x0 + 1, y0 + 1);
+    return a * ((1.0f - fx) * (1.0f - fy)) + b * (fx * (1.0f - fy)) + c * ((1.0f - fx) * fy) + d * (fx * fy);
+}
+// point SampleLevel at normalised uv, clamp addressing
+template <class T>
+__device__ __forceinline__ T sample_point_clamp(const View<const T>& t, float u, float v)
+{
+    return loadc(t, (int)floorf(u * float(t.w)), (int)floorf(v * float(t.h)));
+}
+
+// streaming stores for write-once outputs (do not pollute L1)
+DFX_HD void st_cs(float* p, float v) { __stcs(p, v); }
+DFX_HD void st_cs(float2* p, float2 v) { __stcs(p, v); }
+DFX_HD void st_cs(float4* p, float4 v) { __stcs(p, v); }
+
+constexpr float kPi     = 3.14159265358979f;
+constexpr float kHalfPi = 1.57079632679490f;
+constexpr float kFltEps = 5.960464478e-8f;
+constexpr float kFltMax = 3.402823466e+38f;
+
+DFX_HD bool is_background(float d) { return d >= (1.0f - 1e-6f); }
+
+} // namespace dfx

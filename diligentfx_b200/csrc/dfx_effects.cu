@@ -1,0 +1,591 @@
+// dfx_effects.cu — effect-level objects of the C-ABI: they own the internal planes (pyramids, history ping-pong) and
+// sequence the pass-level entries exactly like the reference classes sequence their draws:
+//   PostFXContext::Execute                 PostProcess/Common/src/PostFXContext.cpp:287-338
+//   ScreenSpaceAmbientOcclusion::Execute   …/ScreenSpaceAmbientOcclusion.cpp:348-387 (+ UpdateConstantBuffer :790-816)
+//   ScreenSpaceReflection::Execute         …/ScreenSpaceReflection.cpp:300-341
+//   Bloom::Execute                         …/Bloom.cpp:407-436
+//   TemporalAntiAliasing::Execute          …/TemporalAntiAliasing.cpp:169-201 (+ UpdateConstantBuffer :123-141)
+#include "dfx_common.cuh"
+#include <chrono>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "_gen/blue_noise_tables.inc" // static const unsigned char kBlueNoiseTables[131328] (generated at build time from data/blue_noise_tables.bin)
+
+using namespace dfx;
+
+namespace
+{
+using Clock = std::chrono::steady_clock;
+
+struct PlaneOwner
+{
+    dfx_plane p{};
+    ~PlaneOwner() { dfx_plane_free(&p); }
+    dfx_status alloc(int w, int h, int fmt)
+    {
+        dfx_plane_free(&p);
+        return dfx_plane_alloc(w, h, fmt, &p);
+    }
+};
+
+dfx_status clear_plane(cudaStream_t s, const dfx_plane& p, float v)
+{
+    const float c[4] = {v, v, v, v};
+    return dfx_plane_fill(s, &p, c);
+}
+
+// AlphaInterpolation = clamp(seconds since the effect became ready, 0, 1) unless pinned
+struct AlphaTimer
+{
+    float             pinned = 1.0f; // < 0 -> wall clock
+    bool              started = false;
+    Clock::time_point t0;
+    float             value()
+    {
+        if (pinned >= 0.0f) return pinned;
+        if (!started) started = true, t0 = Clock::now();
+        float s = std::chrono::duration<float>(Clock::now() - t0).count();
+        return s < 0.0f ? 0.0f : (s > 1.0f ? 1.0f : s);
+    }
+};
+} // namespace
+
+// =====================================================================================================================
+// PostFXContext
+// =====================================================================================================================
+struct dfx_postfx
+{
+    dfx_frame_desc      desc{};
+    uint32_t            flags    = 0;
+    bool                prepared = false, executed = false;
+    uint8_t*            tables_dev = nullptr;
+    dfx_camera_attribs* cams_dev   = nullptr;
+    PlaneOwner          bn_xy, bn_zw, reproj, prev_depth, closest;
+    int                 w = 0, h = 0;
+    ~dfx_postfx()
+    {
+        cudaFree(tables_dev);
+        cudaFree(cams_dev);
+    }
+};
+
+extern "C" dfx_status dfx_postfx_create(dfx_postfx** out)
+{
+    DFX_REQUIRE(out, "out must not be null");
+    dfx_postfx* c = new (std::nothrow) dfx_postfx;
+    DFX_REQUIRE(c, "out of memory");
+    cudaError_t e = cudaMalloc((void**)&c->tables_dev, sizeof(kBlueNoiseTables));
+    if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, kBlueNoiseTables, sizeof(kBlueNoiseTables), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->cams_dev, 2 * sizeof(dfx_camera_attribs));
+    dfx_status st = DFX_OK;
+    if (e != cudaSuccess) st = check_cuda(e, "dfx_postfx_create");
+    if (st == DFX_OK) st = c->bn_xy.alloc(128, 128, DFX_FORMAT_RG32F);
+    if (st == DFX_OK) st = c->bn_zw.alloc(128, 128, DFX_FORMAT_RG32F);
+    if (st != DFX_OK)
+    {
+        delete c;
+        return st;
+    }
+    *out = c;
+    return DFX_OK;
+}
+extern "C" void dfx_postfx_destroy(dfx_postfx* c) { delete c; }
+
+extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* desc, uint32_t flags)
+{
+    DFX_REQUIRE(c && desc, "null argument");
+    if (flags != DFX_POSTFX_FEATURE_FLAG_NONE) return set_error(DFX_ERR_UNSUPPORTED, "PostFX feature flags 0x%x are not implemented (fp32, non-reversed depth only)", flags);
+    DFX_REQUIRE(desc->Width > 0 && desc->Height > 0, "empty frame");
+    c->desc  = *desc;
+    c->flags = flags;
+    if (c->w != (int)desc->Width || c->h != (int)desc->Height)
+    {
+        c->w = desc->Width, c->h = desc->Height;
+        dfx_status st;
+        if ((st = c->reproj.alloc(c->w, c->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = c->prev_depth.alloc(c->w, c->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = c->closest.alloc(c->w, c->h, DFX_FORMAT_RG32F)) != DFX_OK) return st;
+    }
+    c->prepared = true;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_postfx_execute(dfx_postfx* c, const dfx_postfx_render_attribs* a)
+{
+    DFX_REQUIRE(c && a, "null argument");
+    if (!c->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_postfx_prepare was not called");
+    DFX_REQUIRE(a->curr_depth && a->prev_depth && a->motion_vectors, "depth / motion planes must not be null");
+    DFX_REQUIRE(a->curr_camera && a->prev_camera, "camera attribs must not be null");
+    cudaStream_t s = as_stream(a->stream);
+    // upload {curr, prev} like the map-discard of PostFXContext.cpp:310-318 (pageable source: staged before returning)
+    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[0], a->curr_camera, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
+    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[1], a->prev_camera, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
+    dfx_status st;
+    if ((st = dfx_pass_blue_noise(s, c->tables_dev, c->desc.Index, &c->bn_xy.p, &c->bn_zw.p)) != DFX_OK) return st;
+    dfx_rows all{0, c->h};
+    if ((st = dfx_pass_postfx_prepare(s, c->cams_dev, a->curr_depth, a->prev_depth, a->motion_vectors, &c->reproj.p, &c->closest.p, &c->prev_depth.p, all)) != DFX_OK)
+        return st;
+    c->executed = true;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_postfx_get_plane(const dfx_postfx* c, int32_t id, dfx_plane* out)
+{
+    DFX_REQUIRE(c && out, "null argument");
+    switch (id)
+    {
+        case DFX_POSTFX_PLANE_BLUE_NOISE_XY: *out = c->bn_xy.p; break;
+        case DFX_POSTFX_PLANE_BLUE_NOISE_ZW: *out = c->bn_zw.p; break;
+        case DFX_POSTFX_PLANE_REPROJECTED_DEPTH: *out = c->reproj.p; break;
+        case DFX_POSTFX_PLANE_PREVIOUS_DEPTH: *out = c->prev_depth.p; break;
+        case DFX_POSTFX_PLANE_CLOSEST_MOTION: *out = c->closest.p; break;
+        default: return set_error(DFX_ERR_INVALID_ARG, "unknown PostFX plane id %d", id);
+    }
+    DFX_REQUIRE(out->ptr != nullptr, "plane %d is not allocated yet (prepare first)", id);
+    return DFX_OK;
+}
+extern "C" dfx_status dfx_postfx_get_frame_desc(const dfx_postfx* c, dfx_frame_desc* out)
+{
+    DFX_REQUIRE(c && out, "null argument");
+    *out = c->desc;
+    return DFX_OK;
+}
+extern "C" const dfx_camera_attribs* dfx_postfx_get_camera_attribs_dev(const dfx_postfx* c) { return c ? c->cams_dev : nullptr; }
+
+// =====================================================================================================================
+// ScreenSpaceAmbientOcclusion
+// =====================================================================================================================
+struct dfx_ssao
+{
+    int        w = 0, h = 0, levels = 0;
+    uint32_t   flags = 0, last_frame = ~0u, curr_frame = 0;
+    bool       prepared = false;
+    AlphaTimer alpha;
+    PlaneOwner pre[5];      // [0] unused: level 0 aliases the input depth
+    PlaneOwner conv_occ[5]; // [0] = accumulated AO (A5 output)
+    PlaneOwner conv_depth[5]; // [0] unused: aliases the input depth
+    PlaneOwner occ, resampled, hist[2], histlen[2];
+    dfx_plane  last_depth{}; // input depth of the last Execute (for get_plane of the aliased levels)
+};
+
+extern "C" dfx_status dfx_ssao_create(dfx_ssao** out)
+{
+    DFX_REQUIRE(out, "out must not be null");
+    *out = new (std::nothrow) dfx_ssao;
+    DFX_REQUIRE(*out, "out of memory");
+    return DFX_OK;
+}
+extern "C" void dfx_ssao_destroy(dfx_ssao* fx) { delete fx; }
+extern "C" dfx_status dfx_ssao_set_alpha_interpolation(dfx_ssao* fx, float alpha)
+{
+    DFX_REQUIRE(fx, "null argument");
+    fx->alpha.pinned  = alpha;
+    fx->alpha.started = false;
+    return DFX_OK;
+}
+
+static int mip_levels_count(int w, int h)
+{
+    int m = w > h ? w : h, n = 0;
+    while (m > 0) ++n, m >>= 1;
+    return n;
+}
+
+extern "C" dfx_status dfx_ssao_prepare(dfx_ssao* fx, dfx_postfx* postfx, uint32_t flags)
+{
+    DFX_REQUIRE(fx && postfx, "null argument");
+    if (flags != DFX_SSAO_FEATURE_FLAG_NONE) return set_error(DFX_ERR_UNSUPPORTED, "SSAO feature flags 0x%x are not implemented (full resolution, fp32 depth only)", flags);
+    if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
+    fx->curr_frame = postfx->desc.Index;
+    fx->flags      = flags;
+    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared) return DFX_OK;
+    fx->w = postfx->w, fx->h = postfx->h;
+    fx->levels = std::min(mip_levels_count(fx->w, fx->h), 5);
+    dfx_status st;
+    for (int i = 1; i < fx->levels; ++i)
+    {
+        const int mw = std::max(fx->w >> i, 1), mh = std::max(fx->h >> i, 1);
+        if ((st = fx->pre[i].alloc(mw, mh, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = fx->conv_occ[i].alloc(mw, mh, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = fx->conv_depth[i].alloc(mw, mh, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    }
+    if ((st = fx->conv_occ[0].alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    if ((st = fx->occ.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    if ((st = fx->resampled.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    for (int i = 0; i < 2; ++i)
+    {
+        if ((st = fx->hist[i].alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = fx->histlen[i].alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        // cleared to 1.0 at creation (…SSAO.cpp:304-305, :320-321)
+        if ((st = clear_plane(nullptr, fx->hist[i].p, 1.0f)) != DFX_OK) return st;
+        if ((st = clear_plane(nullptr, fx->histlen[i].p, 1.0f)) != DFX_OK) return st;
+    }
+    DFX_CUDA(cudaStreamSynchronize(nullptr));
+    fx->last_frame = ~0u;
+    fx->prepared   = true;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attribs* a)
+{
+    DFX_REQUIRE(fx && a, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_ssao_prepare was not called");
+    DFX_REQUIRE(a->postfx && a->depth && a->normal && a->attribs, "postfx / depth / normal / attribs must not be null");
+    dfx_postfx* pfx = a->postfx;
+    if (!pfx->executed) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext::Execute must run before SSAO");
+    DFX_REQUIRE(a->depth->width == fx->w && a->depth->height == fx->h, "depth size does not match the prepared frame size");
+    cudaStream_t s = as_stream(a->stream);
+
+    // UpdateConstantBuffer (…SSAO.cpp:790-816)
+    dfx_ssao_attribs A = *a->attribs;
+    const bool reset   = fx->last_frame == ~0u || fx->curr_frame != fx->last_frame + 1u || a->attribs->ResetAccumulation != 0;
+    A.ResetAccumulation  = reset ? 1 : 0;
+    A.AlphaInterpolation = fx->alpha.value();
+    fx->last_frame       = fx->curr_frame;
+
+    const uint32_t cur = fx->curr_frame & 1u, prv = (fx->curr_frame + 1u) & 1u;
+    const dfx_rows all{0, fx->h};
+    fx->last_depth = *a->depth;
+
+    dfx_pyramid pre{}, cocc{}, cdep{};
+    pre.levels = cocc.levels = cdep.levels = fx->levels;
+    pre.level[0] = *a->depth, cocc.level[0] = fx->conv_occ[0].p, cdep.level[0] = *a->depth;
+    for (int i = 1; i < fx->levels; ++i) pre.level[i] = fx->pre[i].p, cocc.level[i] = fx->conv_occ[i].p, cdep.level[i] = fx->conv_depth[i].p;
+
+    dfx_status st;
+    if ((st = dfx_pass_ssao_prefilter_depth(s, pfx->cams_dev, &A, &pre, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_ambient_occlusion(s, pfx->cams_dev, &A, &pre, a->normal, &pfx->bn_zw.p, &fx->occ.p, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_temporal(s, pfx->cams_dev, &A, &fx->occ.p, &fx->hist[prv].p, &fx->histlen[prv].p, &pfx->reproj.p, &pfx->prev_depth.p,
+                                     &pfx->closest.p, &fx->conv_occ[0].p, &fx->histlen[cur].p, all)) != DFX_OK)
+        return st;
+    if ((st = dfx_pass_ssao_convolute(s, &cocc, &cdep, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_resample(s, pfx->cams_dev, &cocc, &cdep, &fx->histlen[cur].p, a->normal, &fx->resampled.p, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_spatial(s, pfx->cams_dev, &A, &fx->resampled.p, &fx->histlen[cur].p, a->depth, a->normal, &fx->hist[cur].p, all)) != DFX_OK) return st;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_ssao_get_plane(const dfx_ssao* fx, int32_t id, dfx_plane* out)
+{
+    DFX_REQUIRE(fx && out, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_ssao_prepare was not called");
+    const uint32_t cur = fx->curr_frame & 1u;
+    if (id == DFX_SSAO_PLANE_OUTPUT) *out = fx->hist[cur].p;
+    else if (id == DFX_SSAO_PLANE_OCCLUSION) *out = fx->occ.p;
+    else if (id == DFX_SSAO_PLANE_ACCUMULATED) *out = fx->conv_occ[0].p;
+    else if (id == DFX_SSAO_PLANE_HISTORY_LENGTH) *out = fx->histlen[cur].p;
+    else if (id == DFX_SSAO_PLANE_RESAMPLED) *out = fx->resampled.p;
+    else if (id >= DFX_SSAO_PLANE_PREFILTERED_MIP0 && id < DFX_SSAO_PLANE_PREFILTERED_MIP0 + fx->levels)
+        *out = id == DFX_SSAO_PLANE_PREFILTERED_MIP0 ? fx->last_depth : fx->pre[id - DFX_SSAO_PLANE_PREFILTERED_MIP0].p;
+    else if (id >= DFX_SSAO_PLANE_CONV_AO_MIP0 && id < DFX_SSAO_PLANE_CONV_AO_MIP0 + fx->levels) *out = fx->conv_occ[id - DFX_SSAO_PLANE_CONV_AO_MIP0].p;
+    else if (id >= DFX_SSAO_PLANE_CONV_DEPTH_MIP0 && id < DFX_SSAO_PLANE_CONV_DEPTH_MIP0 + fx->levels)
+        *out = id == DFX_SSAO_PLANE_CONV_DEPTH_MIP0 ? fx->last_depth : fx->conv_depth[id - DFX_SSAO_PLANE_CONV_DEPTH_MIP0].p;
+    else
+        return set_error(DFX_ERR_INVALID_ARG, "unknown SSAO plane id %d", id);
+    DFX_REQUIRE(out->ptr != nullptr, "plane %d is not available yet", id);
+    return DFX_OK;
+}
+
+// =====================================================================================================================
+// ScreenSpaceReflection
+// =====================================================================================================================
+struct dfx_ssr
+{
+    int        w = 0, h = 0, levels = 0;
+    uint32_t   flags = 0, curr_frame = 0;
+    bool       prepared = false;
+    AlphaTimer alpha;
+    PlaneOwner hiz[7]; // [0] unused: aliases the input depth
+    PlaneOwner roughness, mask, radiance, raydir, res_rad, res_var, res_depth, radhist[2], varhist[2], out;
+    dfx_plane  last_depth{};
+};
+
+extern "C" dfx_status dfx_ssr_create(dfx_ssr** out)
+{
+    DFX_REQUIRE(out, "out must not be null");
+    *out = new (std::nothrow) dfx_ssr;
+    DFX_REQUIRE(*out, "out of memory");
+    return DFX_OK;
+}
+extern "C" void dfx_ssr_destroy(dfx_ssr* fx) { delete fx; }
+extern "C" dfx_status dfx_ssr_set_alpha_interpolation(dfx_ssr* fx, float alpha)
+{
+    DFX_REQUIRE(fx, "null argument");
+    fx->alpha.pinned  = alpha;
+    fx->alpha.started = false;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_ssr_prepare(dfx_ssr* fx, dfx_postfx* postfx, uint32_t flags)
+{
+    DFX_REQUIRE(fx && postfx, "null argument");
+    if (flags & ~DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) return set_error(DFX_ERR_UNSUPPORTED, "SSR feature flags 0x%x are not implemented (full resolution only)", flags);
+    if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
+    fx->curr_frame = postfx->desc.Index;
+    fx->flags      = flags;
+    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared) return DFX_OK;
+    fx->w = postfx->w, fx->h = postfx->h;
+    fx->levels = std::min(mip_levels_count(fx->w, fx->h), 7);
+    dfx_status st;
+    for (int i = 1; i < fx->levels; ++i)
+        if ((st = fx->hiz[i].alloc(std::max(fx->w >> i, 1), std::max(fx->h >> i, 1), DFX_FORMAT_R32F)) != DFX_OK) return st;
+    struct { PlaneOwner* p; int fmt; } planes[] = {
+        {&fx->roughness, DFX_FORMAT_R32F}, {&fx->mask, DFX_FORMAT_R8U}, {&fx->radiance, DFX_FORMAT_RGBA32F}, {&fx->raydir, DFX_FORMAT_RGBA32F},
+        {&fx->res_rad, DFX_FORMAT_RGBA32F}, {&fx->res_var, DFX_FORMAT_R32F}, {&fx->res_depth, DFX_FORMAT_R32F},
+        {&fx->radhist[0], DFX_FORMAT_RGBA32F}, {&fx->radhist[1], DFX_FORMAT_RGBA32F}, {&fx->varhist[0], DFX_FORMAT_R32F}, {&fx->varhist[1], DFX_FORMAT_R32F},
+        {&fx->out, DFX_FORMAT_RGBA32F}};
+    for (auto& pl : planes)
+    {
+        if ((st = pl.p->alloc(fx->w, fx->h, pl.fmt)) != DFX_OK) return st;
+        // history / output are cleared to 0 at creation (ScreenSpaceReflection.cpp:263-264, :279-280, :294-295); the targets the
+        // reference never clears (roughness, resolved *) start from zeroed memory here so runs are deterministic.
+        DFX_CUDA(cudaMemset2D(pl.p->p.ptr, pl.p->p.pitch_bytes, 0, pl.p->p.pitch_bytes, fx->h));
+    }
+    fx->prepared = true;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_ssr_execute(dfx_ssr* fx, const dfx_ssr_render_attribs* a)
+{
+    DFX_REQUIRE(fx && a, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_ssr_prepare was not called");
+    DFX_REQUIRE(a->postfx && a->color && a->depth && a->normal && a->material && a->motion && a->attribs, "all SSR inputs must not be null");
+    dfx_postfx* pfx = a->postfx;
+    if (!pfx->executed) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext::Execute must run before SSR");
+    DFX_REQUIRE(a->depth->width == fx->w && a->depth->height == fx->h, "depth size does not match the prepared frame size");
+    cudaStream_t s = as_stream(a->stream);
+
+    dfx_ssr_attribs A    = *a->attribs; // UpdateConstantBuffer (…cpp:755-776)
+    A.AlphaInterpolation = fx->alpha.value();
+    const uint32_t cur = fx->curr_frame & 1u, prv = (fx->curr_frame + 1u) & 1u;
+    const dfx_rows all{0, fx->h};
+    fx->last_depth = *a->depth;
+
+    dfx_pyramid hz{};
+    hz.levels   = fx->levels;
+    hz.level[0] = *a->depth;
+    for (int i = 1; i < fx->levels; ++i) hz.level[i] = fx->hiz[i].p;
+
+    dfx_status st;
+    if ((st = dfx_pass_ssr_hiz(s, &hz, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssr_mask_roughness(s, &A, a->material, a->depth, &fx->roughness.p, &fx->mask.p, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssr_intersect(s, pfx->cams_dev, &A, fx->flags, a->color, a->normal, &fx->roughness.p, &fx->mask.p, &pfx->bn_xy.p, &hz, a->motion,
+                                     &fx->radiance.p, &fx->raydir.p, all)) != DFX_OK)
+        return st;
+    if ((st = dfx_pass_ssr_spatial(s, pfx->cams_dev, &A, &fx->roughness.p, &fx->mask.p, a->normal, a->depth, &fx->raydir.p, &fx->radiance.p, &fx->res_rad.p,
+                                   &fx->res_var.p, &fx->res_depth.p, all)) != DFX_OK)
+        return st;
+    if ((st = dfx_pass_ssr_temporal(s, pfx->cams_dev, &A, &fx->mask.p, a->motion, &fx->res_depth.p, &pfx->reproj.p, &fx->res_rad.p, &fx->res_var.p,
+                                    &pfx->prev_depth.p, &fx->radhist[prv].p, &fx->varhist[prv].p, &fx->radhist[cur].p, &fx->varhist[cur].p, all)) != DFX_OK)
+        return st;
+    if ((st = dfx_pass_ssr_bilateral(s, pfx->cams_dev, &A, &fx->mask.p, a->depth, a->normal, &fx->roughness.p, &fx->radhist[cur].p, &fx->varhist[cur].p,
+                                     &fx->out.p, all)) != DFX_OK)
+        return st;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_ssr_get_plane(const dfx_ssr* fx, int32_t id, dfx_plane* out)
+{
+    DFX_REQUIRE(fx && out, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_ssr_prepare was not called");
+    const uint32_t cur = fx->curr_frame & 1u;
+    switch (id)
+    {
+        case DFX_SSR_PLANE_OUTPUT: *out = fx->out.p; break;
+        case DFX_SSR_PLANE_ROUGHNESS: *out = fx->roughness.p; break;
+        case DFX_SSR_PLANE_MASK: *out = fx->mask.p; break;
+        case DFX_SSR_PLANE_RADIANCE: *out = fx->radiance.p; break;
+        case DFX_SSR_PLANE_RAYDIR_PDF: *out = fx->raydir.p; break;
+        case DFX_SSR_PLANE_RESOLVED_RADIANCE: *out = fx->res_rad.p; break;
+        case DFX_SSR_PLANE_RESOLVED_VARIANCE: *out = fx->res_var.p; break;
+        case DFX_SSR_PLANE_RESOLVED_DEPTH: *out = fx->res_depth.p; break;
+        case DFX_SSR_PLANE_RADIANCE_HISTORY: *out = fx->radhist[cur].p; break;
+        case DFX_SSR_PLANE_VARIANCE_HISTORY: *out = fx->varhist[cur].p; break;
+        default:
+            if (id >= DFX_SSR_PLANE_HIZ_MIP0 && id < DFX_SSR_PLANE_HIZ_MIP0 + fx->levels)
+                *out = id == DFX_SSR_PLANE_HIZ_MIP0 ? fx->last_depth : fx->hiz[id - DFX_SSR_PLANE_HIZ_MIP0].p;
+            else
+                return set_error(DFX_ERR_INVALID_ARG, "unknown SSR plane id %d", id);
+    }
+    DFX_REQUIRE(out->ptr != nullptr, "plane %d is not available yet", id);
+    return DFX_OK;
+}
+
+// =====================================================================================================================
+// Bloom
+// =====================================================================================================================
+struct dfx_bloom
+{
+    int                     w = 0, h = 0;
+    bool                    prepared = false;
+    AlphaTimer              alpha;
+    std::vector<PlaneOwner> down, up;
+    PlaneOwner              out;
+};
+
+extern "C" dfx_status dfx_bloom_create(dfx_bloom** out)
+{
+    DFX_REQUIRE(out, "out must not be null");
+    *out = new (std::nothrow) dfx_bloom;
+    DFX_REQUIRE(*out, "out of memory");
+    return DFX_OK;
+}
+extern "C" void dfx_bloom_destroy(dfx_bloom* fx) { delete fx; }
+extern "C" dfx_status dfx_bloom_set_alpha_interpolation(dfx_bloom* fx, float alpha)
+{
+    DFX_REQUIRE(fx, "null argument");
+    fx->alpha.pinned  = alpha;
+    fx->alpha.started = false;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_bloom_prepare(dfx_bloom* fx, dfx_postfx* postfx, uint32_t flags)
+{
+    DFX_REQUIRE(fx && postfx, "null argument");
+    if (flags != DFX_BLOOM_FEATURE_FLAG_NONE) return set_error(DFX_ERR_UNSUPPORTED, "unknown Bloom feature flags 0x%x", flags);
+    if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
+    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared) return DFX_OK;
+    fx->w = postfx->w, fx->h = postfx->h;
+    // Bloom.cpp:96-128: TextureCount = ComputeMipLevelsCount(W/2, H/2), level i = max(half >> i, 1)
+    const int hw = std::max(fx->w / 2, 1), hh = std::max(fx->h / 2, 1);
+    const int count = mip_levels_count(hw, hh);
+    fx->down = std::vector<PlaneOwner>(count);
+    fx->up   = std::vector<PlaneOwner>(count);
+    dfx_status st;
+    for (int i = 0; i < count; ++i)
+    {
+        if ((st = fx->down[i].alloc(std::max(hw >> i, 1), std::max(hh >> i, 1), DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+        if ((st = fx->up[i].alloc(std::max(hw >> i, 1), std::max(hh >> i, 1), DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+    }
+    if ((st = fx->out.alloc(fx->w, fx->h, DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+    fx->prepared = true;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_bloom_execute(dfx_bloom* fx, const dfx_bloom_render_attribs* a)
+{
+    DFX_REQUIRE(fx && a, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_bloom_prepare was not called");
+    DFX_REQUIRE(a->color && a->attribs, "color / attribs must not be null");
+    DFX_REQUIRE(a->color->width == fx->w && a->color->height == fx->h, "color size does not match the prepared frame size");
+    cudaStream_t      s = as_stream(a->stream);
+    dfx_bloom_attribs A = *a->attribs; // UpdateConstantBuffer (Bloom.cpp:270-286)
+    A.AlphaInterpolation = fx->alpha.value();
+
+    const int mips = std::min<int>(dfx_bloom_mip_count(fx->down[0].p.width, fx->down[0].p.height, A.Radius), (int)fx->down.size());
+    DFX_REQUIRE(mips >= 2, "Bloom radius %.3f leaves fewer than two pyramid levels", A.Radius);
+    auto rows = [](const dfx_plane& p) { return dfx_rows{0, p.height}; };
+    dfx_status st;
+    if ((st = dfx_pass_bloom_prefilter(s, &A, a->color, &fx->down[0].p, rows(fx->down[0].p))) != DFX_OK) return st;
+    for (int i = 1; i < mips; ++i)
+        if ((st = dfx_pass_bloom_downsample(s, &fx->down[i - 1].p, &fx->down[i].p, rows(fx->down[i].p))) != DFX_OK) return st;
+    const int top = mips - 1;
+    for (int i = top; i > 0; --i)
+        if ((st = dfx_pass_bloom_upsample(s, &fx->down[i - 1].p, i != top ? &fx->up[i].p : &fx->down[i].p, &fx->up[i - 1].p, rows(fx->up[i - 1].p))) != DFX_OK)
+            return st;
+    return dfx_pass_bloom_composite(s, &A, a->color, &fx->up[0].p, &fx->out.p, rows(fx->out.p));
+}
+
+extern "C" dfx_status dfx_bloom_get_plane(const dfx_bloom* fx, int32_t id, dfx_plane* out)
+{
+    DFX_REQUIRE(fx && out, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_bloom_prepare was not called");
+    const int n = (int)fx->down.size();
+    if (id == DFX_BLOOM_PLANE_OUTPUT) *out = fx->out.p;
+    else if (id >= DFX_BLOOM_PLANE_DOWN0 && id < DFX_BLOOM_PLANE_DOWN0 + n) *out = fx->down[id - DFX_BLOOM_PLANE_DOWN0].p;
+    else if (id >= DFX_BLOOM_PLANE_UP0 && id < DFX_BLOOM_PLANE_UP0 + n) *out = fx->up[id - DFX_BLOOM_PLANE_UP0].p;
+    else
+        return set_error(DFX_ERR_INVALID_ARG, "unknown Bloom plane id %d", id);
+    return DFX_OK;
+}
+
+// =====================================================================================================================
+// TemporalAntiAliasing
+// =====================================================================================================================
+struct TaaBuffer
+{
+    int        w = 0, h = 0;
+    uint32_t   flags = 0, last_frame = ~0u, curr_frame = 0;
+    PlaneOwner accum[2];
+};
+struct dfx_taa
+{
+    std::map<uint32_t, TaaBuffer> buffers;
+};
+
+extern "C" dfx_status dfx_taa_create(dfx_taa** out)
+{
+    DFX_REQUIRE(out, "out must not be null");
+    *out = new (std::nothrow) dfx_taa;
+    DFX_REQUIRE(*out, "out of memory");
+    return DFX_OK;
+}
+extern "C" void dfx_taa_destroy(dfx_taa* fx) { delete fx; }
+
+extern "C" dfx_status dfx_taa_prepare(dfx_taa* fx, dfx_postfx* postfx, uint32_t flags, uint32_t idx)
+{
+    DFX_REQUIRE(fx && postfx, "null argument");
+    if (flags & ~7u) return set_error(DFX_ERR_UNSUPPORTED, "unknown TAA feature flags 0x%x", flags);
+    if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
+    TaaBuffer& b = fx->buffers[idx];
+    b.flags      = flags;
+    b.curr_frame = postfx->desc.Index;
+    if (b.w == postfx->w && b.h == postfx->h) return DFX_OK;
+    b.w = postfx->w, b.h = postfx->h;
+    dfx_status st;
+    for (int i = 0; i < 2; ++i)
+    {
+        if ((st = b.accum[i].alloc(b.w, b.h, DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+        DFX_CUDA(cudaMemset2D(b.accum[i].p.ptr, b.accum[i].p.pitch_bytes, 0, b.accum[i].p.pitch_bytes, b.h)); // cleared to 0 (TemporalAntiAliasing.cpp:112-116)
+    }
+    b.last_frame = ~0u;
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_taa_execute(dfx_taa* fx, const dfx_taa_render_attribs* a)
+{
+    DFX_REQUIRE(fx && a, "null argument");
+    DFX_REQUIRE(a->postfx && a->color && a->attribs, "postfx / color / attribs must not be null");
+    auto it = fx->buffers.find(a->accumulation_buffer_idx);
+    if (it == fx->buffers.end())
+        return set_error(DFX_ERR_NOT_PREPARED, "Accumulation buffer with index %u is not found, which indicates that PrepareResources() method was not called.",
+                         a->accumulation_buffer_idx);
+    TaaBuffer&  b   = it->second;
+    dfx_postfx* pfx = a->postfx;
+    if (!pfx->executed) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext::Execute must run before TAA");
+    DFX_REQUIRE(a->color->width == b.w && a->color->height == b.h, "color size does not match the prepared frame size");
+
+    // AccumulationBufferInfo::UpdateConstantBuffer (TemporalAntiAliasing.cpp:123-141)
+    dfx_taa_attribs A  = *a->attribs;
+    const bool reset   = b.last_frame == ~0u || b.curr_frame != b.last_frame + 1u || a->attribs->ResetAccumulation != 0;
+    A.ResetAccumulation = reset ? 1 : 0;
+    b.last_frame        = b.curr_frame;
+    const uint32_t cur = b.curr_frame & 1u, prv = (b.curr_frame + 1u) & 1u;
+    return dfx_pass_taa(as_stream(a->stream), pfx->cams_dev, &A, b.flags, a->color, &b.accum[prv].p, &pfx->closest.p, &pfx->reproj.p, &pfx->prev_depth.p,
+                        &b.accum[cur].p, dfx_rows{0, b.h});
+}
+
+extern "C" dfx_status dfx_taa_get_plane(const dfx_taa* fx, int32_t id, uint32_t idx, dfx_plane* out)
+{
+    DFX_REQUIRE(fx && out, "null argument");
+    auto it = fx->buffers.find(idx);
+    if (it == fx->buffers.end()) return set_error(DFX_ERR_NOT_PREPARED, "Accumulation buffer with index %u is not found.", idx);
+    const TaaBuffer& b = it->second;
+    // GetAccumulatedFrameSRV (TemporalAntiAliasing.cpp:203-214)
+    if (id == DFX_TAA_PLANE_ACCUMULATED_CURR) *out = b.accum[b.curr_frame & 1u].p;
+    else if (id == DFX_TAA_PLANE_ACCUMULATED_PREV) *out = b.accum[(b.curr_frame + 1u) & 1u].p;
+    else
+        return set_error(DFX_ERR_INVALID_ARG, "unknown TAA plane id %d", id);
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_taa_get_jitter_offset(const dfx_taa* fx, uint32_t idx, float out[2])
+{
+    DFX_REQUIRE(fx && out, "null argument");
+    out[0] = out[1] = 0.0f;
+    auto it = fx->buffers.find(idx);
+    if (it == fx->buffers.end() || it->second.w == 0 || it->second.h == 0) return DFX_OK; // TemporalAntiAliasing.cpp:65-72
+    dfx_taa_jitter_offset(it->second.curr_frame, it->second.w, it->second.h, out);
+    return DFX_OK;
+}

@@ -1,0 +1,605 @@
+// dfx_ssao.cu — ScreenSpaceAmbientOcclusion passes A1-A8 as sm_100a kernels.
+// Reference host code: PostProcess/ScreenSpaceAmbientOcclusion/src/ScreenSpaceAmbientOcclusion.cpp:818-1329;
+// shaders: Shaders/PostProcess/ScreenSpaceAmbientOcclusion/private/SSAO_*.fx (cited per kernel).
+// Layout: depth / AO / history-length planes are fp32, normals float4 (xyz used); see DESIGN.md.
+#include "dfx_common.cuh"
+
+namespace dfx
+{
+
+struct SsaoCam
+{
+    CamS c;
+    Mat4 view;
+};
+__device__ __forceinline__ void stage_cam(SsaoCam& s, const dfx_camera_attribs* cams)
+{
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+    {
+        load_cam(s.c, &cams[0]);
+        load_mat(s.view, cams[0].mView);
+    }
+    __syncthreads();
+}
+
+// level-m row range of a full-resolution strip [y0, y1)
+__host__ __device__ inline int mip_row(int y, int m, int full_h, int mip_h) { return y >= full_h ? mip_h : (y >> m); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A2: prefiltered depth mip m from mip m-1 (SSAO_ComputePrefilteredDepthBuffer.fx:79-122).
+// 2x2 footprint (+1 column / row when the source dimension is odd), taps converted to view-space Z, weighted average
+// that favours the closest tap within the falloff range, converted back to depth and saturated.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssao_prefilter_level_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
+                                                                   View<const float> src, View<float> dst, int r0, int r1)
+{
+    __shared__ CamS cam;
+    if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(cam, &cams[0]);
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dst.w || y >= r1) return;
+
+    const bool wodd = src.w & 1, hodd = src.h & 1;
+    float      z[9];
+    int        n = 0;
+    const int  rx = 2 * x, ry = 2 * y;
+    auto       tap = [&](int ox, int oy) { z[n++] = depth_to_camz(loadc(src, rx + ox, ry + oy), cam); };
+    tap(0, 0), tap(0, 1), tap(1, 0), tap(1, 1);
+    if (wodd) tap(2, 0), tap(2, 1);
+    if (hodd) tap(0, 2), tap(1, 2);
+    if (wodd && hodd) tap(2, 2);
+
+    float zmin = z[0];
+    for (int i = 1; i < n; ++i) zmin = fminf(zmin, z[i]);
+
+    const float radius       = 0.75f * A.EffectRadius * A.RadiusMultiplier;
+    const float falloffRange = A.EffectFalloffRange * radius;
+    const float falloffFrom  = radius - falloffRange;
+    const float falloffMul   = -1.0f / falloffRange;
+    const float falloffAdd   = falloffFrom / falloffRange + 1.0f;
+
+    float zsum = 0.0f, wsum = 0.0f;
+    for (int i = 0; i < n; ++i)
+    {
+        float w = saturate(fabsf(zmin - z[i]) * falloffMul + falloffAdd);
+        zsum += w * z[i];
+        wsum += w;
+    }
+    dst.at(x, y) = saturate(camz_to_depth(zsum / wsum, cam));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A3: ambient occlusion (SSAO_ComputeAmbientOcclusion.fx:132-231). One thread per pixel; the 18 depth taps per pixel are
+// point-sampled from the prefiltered pyramid at mip = round(clamp(log2(|offset_px|) - DepthMIPSamplingOffset, 0, 4)).
+// Background pixels keep the clear value 1.0 (the clear + discard of the reference are folded into the store).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_acos(float v) // :47-53
+{
+    float a = fabsf(v);
+    float r = (-0.156583f * a + kHalfPi) * sqrtf(1.0f - a);
+    return v >= 0.0f ? r : kPi - r;
+}
+
+__device__ __forceinline__ uint32_t occluded_sectors(float minH, float maxH, uint32_t bits) // :77-99
+{
+    minH = saturate(minH), maxH = saturate(maxH);
+    if (maxH > minH)
+    {
+        uint32_t start = min((uint32_t)(minH * 32.0f), 31u);
+        uint32_t end   = min((uint32_t)ceilf(maxH * 32.0f), 32u);
+        if (end > start)
+        {
+            uint32_t n    = end - start;
+            uint32_t mask = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+            bits |= mask << start;
+        }
+    }
+    return bits;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
+                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1)
+{
+    __shared__ SsaoCam S;
+    stage_cam(S, cams);
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+
+    const float u = (float(x) + 0.5f) * cam.ivw, v = (float(y) + 0.5f) * cam.ivh;
+    const float depth = sample_point_clamp(pyr.lv[0], u, v);
+    if (is_background(depth))
+    {
+        st_cs(&out.at(x, y), 1.0f);
+        return;
+    }
+    const float3 nvs = mul_dir(xyz(sample_point_clamp(normal, u, v)), S.view);
+    float3       pvs = screen_to_view(u, v, depth, cam);
+    pvs              = pvs + nvs * (0.00001f * pvs.z);
+    const float3 view = -normalize(pvs);
+    const float2 xi   = __ldg(&noise.at(x & 127, y & 127));
+
+    const float effectRadius = A.EffectRadius * A.RadiusMultiplier;
+    const float falloffRange = A.EffectFalloffRange * effectRadius;
+    const float falloffFrom  = effectRadius - falloffRange;
+    const float falloffMul   = -1.0f / falloffRange;
+    const float falloffAdd   = falloffFrom / falloffRange + 1.0f;
+    float       sampleRadius = 0.5f * effectRadius * cam.m00;
+    if (cam.m33 == 0.0f) sampleRadius /= pvs.z; // perspective
+
+    float visibility = 0.0f;
+#pragma unroll
+    for (int slice = 0; slice < 3; ++slice)
+    {
+        const float phi = (xi.x + float(slice) / 3.0f) * kPi;
+        float       so, co;
+        sincosf(phi, &so, &co);
+        const float3 sliceDir   = make_float3(co, so, 0.0f);
+        const float3 orthoSlice = sliceDir - dot(sliceDir, view) * view;
+        const float3 axis       = normalize(cross(sliceDir, view));
+        const float3 projN      = nvs - axis * dot(nvs, axis);
+        const float  projNLen   = length(projN);
+        const float  cosNorm    = saturate(dot(projN / projNLen, view));
+        const float  N          = signf(dot(orthoSlice, projN)) * fast_acos(cosNorm);
+
+        uint32_t bits = 0u;
+        float    minCos0 = cosf(N + kHalfPi), minCos1 = cosf(N - kHalfPi);
+        float    maxCos0 = minCos0, maxCos1 = minCos1;
+
+        float sdx = co * 0.5f * sampleRadius, sdy = so * -0.5f * sampleRadius;
+        sdx *= cam.vh * cam.ivw; // aspect-ratio correction
+
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+        {
+            const float noiseS = fracf(xi.y + float(slice + s * 3) * 0.6180339887498948482f);
+            const float smp    = (float(s) + noiseS) / 3.0f;
+            const float offx = smp * smp * sdx, offy = smp * smp * sdy;
+            const float lod  = fminf(fmaxf(log2f(length(make_float2(offx * cam.vw, offy * cam.vh))) - A.DepthMIPSamplingOffset, 0.0f), 4.0f);
+            const int   mip  = min((int)floorf(lod + 0.5f), pyr.levels - 1);
+            const View<const float>& lv = pyr.lv[mip];
+            const float u0 = u + offx, v0 = v + offy, u1 = u - offx, v1 = v - offy;
+            const float3 p0 = screen_to_view(u0, v0, sample_point_clamp(lv, u0, v0), cam);
+            const float3 p1 = screen_to_view(u1, v1, sample_point_clamp(lv, u1, v1), cam);
+            const float3 d0 = p0 - pvs, d1 = p1 - pvs;
+            if (ALGO == DFX_SSAO_ALGORITHM_VBAO)
+            {
+                // ComputeSampleOcclusion :101-119
+                const float3 thick = view * A.BitmaskThickness;
+                const float  w0 = saturate(length(d0) * falloffMul + falloffAdd), w1 = saturate(length(d1) * falloffMul + falloffAdd);
+                float f0 = fast_acos(dot(normalize(d0), view)), b0 = fast_acos(dot(normalize(d0 - thick), view));
+                float f1 = fast_acos(dot(normalize(d1), view)), b1 = fast_acos(dot(normalize(d1 - thick), view));
+                const float nb = -N;
+                f0 = saturate((-f0 - nb + kHalfPi) / kPi), b0 = saturate((-b0 - nb + kHalfPi) / kPi);
+                f1 = saturate((f1 - nb + kHalfPi) / kPi), b1 = saturate((b1 - nb + kHalfPi) / kPi);
+                if (w0 > 0.0f) bits = occluded_sectors(b0, f0, bits);
+                if (w1 > 0.0f) bits = occluded_sectors(f1, b1, bits);
+            }
+            else
+            {
+                // ComputeSampleHorizons :121-130
+                const float l0 = length(d0), l1 = length(d1);
+                const float c0 = dot(d0 / l0, view), c1 = dot(d1 / l1, view);
+                const float w0 = saturate(l0 * falloffMul + falloffAdd), w1 = saturate(l1 * falloffMul + falloffAdd);
+                maxCos0 = fmaxf(maxCos0, lerpf(minCos0, c0, w0));
+                maxCos1 = fmaxf(maxCos1, lerpf(minCos1, c1, w1));
+            }
+        }
+
+        if (ALGO == DFX_SSAO_ALGORITHM_VBAO)
+        {
+            visibility += 1.0f - float(__popc(bits)) / 32.0f;
+        }
+        else
+        {
+            const float h0 = fast_acos(maxCos0), h1 = -fast_acos(maxCos1);
+            if (ALGO == DFX_SSAO_ALGORITHM_HBAO)
+                visibility += 0.5f * ((1.0f - cosf(h0)) + (1.0f - cosf(h1))); // IntegrateArcUniform :55-58
+            else
+            {
+                // IntegrateArcCosWeighted :60-66
+                const float H1 = h0 * 2.0f, H2 = h1 * 2.0f, sinN = sinf(N);
+                visibility += projNLen * 0.25f * ((-cosf(H1 - N) + cosNorm + H1 * sinN) + (-cosf(H2 - N) + cosNorm + H2 * sinN));
+            }
+        }
+    }
+    st_cs(&out.at(x, y), visibility / 3.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A5: temporal accumulation (SSAO_ComputeTemporalAccumulation.fx:151-182). Background keeps the clear value (1, 1).
+// ---------------------------------------------------------------------------------------------------------------------
+struct TemporalCam
+{
+    CamS c, p;
+};
+__global__ void __launch_bounds__(256) ssao_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
+                                                            View<const float> curr_occ, View<const float> prev_occ,
+                                                            View<const float> prev_hist, View<const float> curr_depth,
+                                                            View<const float> prev_depth, View<const float2> motion, View<float> out_occ,
+                                                            View<float> out_hist, int y0, int y1)
+{
+    __shared__ TemporalCam S;
+    if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_cam(S.p, &cams[1]);
+    __syncthreads();
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_occ.w || y >= y1) return;
+
+    const float depth = __ldg(&curr_depth.at(x, y));
+    if (is_background(depth))
+    {
+        st_cs(&out_occ.at(x, y), 1.0f);
+        st_cs(&out_hist.at(x, y), 1.0f);
+        return;
+    }
+    const int    W = (int)cam.vw, H = (int)cam.vh;
+    float2       mv = __ldg(&motion.at(x, y));
+    mv.x *= 0.5f, mv.y *= -0.5f; // F3NDC_XYZ_TO_UVD_SCALE.xy
+    const float plx = (float(x) + 0.5f) - mv.x * cam.vw, ply = (float(y) + 0.5f) - mv.y * cam.vh;
+
+    // ComputeReprojection :105-149
+    const float currZ = depth_to_camz(depth, cam);
+    const Bilin b     = bilinear_uc(plx, ply, W, H);
+    auto  similar = [&](int sx, int sy) {
+        float pz = depth_to_camz(load0(prev_depth, sx, sy), S.p);
+        return fabsf(1.0f - currZ / pz) < 0.01f ? 1.0f : 0.0f;
+    };
+    const float w00 = b.w00 * similar(b.x0, b.y0), w10 = b.w10 * similar(b.x1, b.y0);
+    const float w01 = b.w01 * similar(b.x0, b.y1), w11 = b.w11 * similar(b.x1, b.y1);
+    const float total = w00 * 1.0f + w10 * 1.0f + w01 * 1.0f + w11 * 1.0f;
+
+    float rOcc = 1.0f, rHist = 1.0f;
+    const bool ok = total > 0.01f && !A.ResetAccumulation;
+    const float currOcc = __ldg(&curr_occ.at(x, y));
+    if (ok)
+    {
+        const float o00 = load0(prev_occ, b.x0, b.y0), o10 = load0(prev_occ, b.x1, b.y0), o01 = load0(prev_occ, b.x0, b.y1), o11 = load0(prev_occ, b.x1, b.y1);
+        const float h00 = fminf(load0(prev_hist, b.x0, b.y0) + 1.0f, 16.0f), h10 = fminf(load0(prev_hist, b.x1, b.y0) + 1.0f, 16.0f);
+        const float h01 = fminf(load0(prev_hist, b.x0, b.y1) + 1.0f, 16.0f), h11 = fminf(load0(prev_hist, b.x1, b.y1) + 1.0f, 16.0f);
+        rOcc  = (o00 * w00 + o10 * w10 + o01 * w01 + o11 * w11) / total;
+        rHist = (h00 * w00 + h10 * w10 + h01 * w01 + h11 * w11) / total;
+
+        // ComputePixelStatistic :81-103
+        float m1 = 0.0f, m2 = 0.0f;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+            {
+                float s = __ldg(&curr_occ.at(min(max(x + dx, 0), W - 1), min(max(y + dy, 0), H - 1)));
+                m1 += s;
+                m2 += s * s;
+            }
+        const float mean = m1 / 9.0f;
+        const float var  = (m2 / 9.0f) - (mean * mean);
+        const float sd   = sqrtf(fmaxf(var, 0.0f));
+
+        const float aspect = cam.vw * cam.ivh;
+        const float mf     = saturate(1.025f - length(make_float2(mv.x * aspect, mv.y)) * 128.0f);
+        const float gamma  = lerpf(0.5f, 2.5f, mf * mf);
+        const float lo = mean - gamma * sd, hi = mean + gamma * sd;
+        const bool  inside = lo < rOcc && rOcc < hi;
+        rHist = inside ? rHist : fmaxf(1.0f, mf * rHist);
+    }
+    const float alpha = 1.0f / rHist;
+    st_cs(&out_occ.at(x, y), lerpf(rOcc, currOcc, alpha));
+    st_cs(&out_hist.at(x, y), rHist);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A6: convoluted history / depth pyramids, level m from m-1, plain averages (SSAO_ComputeConvolutedDepthHistory.fx:93-109)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float footprint_average(const View<const float>& src, int rx, int ry)
+{
+    const bool wodd = src.w & 1, hodd = src.h & 1;
+    // accumulation order of the reference's ArrayAppend sequence
+    float r = loadc(src, rx, ry);
+    r += loadc(src, rx, ry + 1);
+    r += loadc(src, rx + 1, ry);
+    r += loadc(src, rx + 1, ry + 1);
+    int n = 4;
+    if (wodd) r += loadc(src, rx + 2, ry), r += loadc(src, rx + 2, ry + 1), n += 2;
+    if (hodd) r += loadc(src, rx, ry + 2), r += loadc(src, rx + 1, ry + 2), n += 2;
+    if (wodd && hodd) r += loadc(src, rx + 2, ry + 2), n += 1;
+    return r / float(n);
+}
+__global__ void __launch_bounds__(256) ssao_convolute_level_kernel(View<const float> occ_src, View<const float> depth_src, View<float> occ_dst,
+                                                                   View<float> depth_dst, int r0, int r1)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= occ_dst.w || y >= r1) return;
+    occ_dst.at(x, y)   = footprint_average(occ_src, 2 * x, 2 * y);
+    depth_dst.at(x, y) = footprint_average(depth_src, 2 * x, 2 * y);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A7: resampled history (SSAO_ComputeResampledHistory.fx:56-115)
+// ---------------------------------------------------------------------------------------------------------------------
+DFX_HD float geometry_weight(float3 center, float3 tap, float3 n, float planeNorm) // SSAO_Common.fxh:25-28
+{
+    return saturate(1.0f - fabsf(dot(tap - center, n)) * planeNorm);
+}
+
+__global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_attribs* __restrict__ cams, PyrView occ, PyrView dep,
+                                                            View<const float> history, View<const float4> normal, View<float> out, int y0, int y1)
+{
+    __shared__ SsaoCam S;
+    stage_cam(S, cams);
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+
+    const float depth = __ldg(&dep.lv[0].at(x, y));
+    const float hist  = __ldg(&history.at(x, y));
+    const float acc   = (hist - 1.0f) / 4.0f;
+    if (is_background(depth) || acc >= 1.0f)
+    {
+        st_cs(&out.at(x, y), __ldg(&occ.lv[0].at(x, y)));
+        return;
+    }
+    int          mip = min((int)(4.0f * (1.0f - saturate(acc))), occ.levels - 1);
+    const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
+    const float3 pvs  = screen_to_view(posx * cam.ivw, posy * cam.ivh, depth, cam);
+    const float3 nvs  = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    const float  planeNorm = 10.0f / (1.0f + depth_to_camz(depth, cam));
+
+    float osum = 0.0f, wsum = 0.0f;
+    while (mip >= 0 && wsum < 0.995f)
+    {
+        const float inv = 1.0f / float(1u << (unsigned)mip);
+        const float rx = cam.vw * inv, ry = cam.vh * inv; // GetMipResolution: float, not the integer mip size
+        const float lx = posx * inv, ly = posy * inv;
+        const int   ix = (int)(lx - 0.5f), iy = (int)(ly - 0.5f);
+        const float fx = fracf(lx + 0.5f), fy = fracf(ly + 0.5f);
+        const float w[4] = {(1.0f - fx) * (1.0f - fy), fx * (1.0f - fy), (1.0f - fx) * fy, fx * fy};
+        osum = 0.0f, wsum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const int   tx = ix + (i & 1), ty = iy + (i >> 1);
+            const float tu = (float(tx) + 0.5f) * (1.0f / rx), tv = (float(ty) + 0.5f) * (1.0f / ry);
+            const float sd = sample_linear_clamp(dep.lv[mip], tu, tv);
+            const float so = sample_point_clamp(occ.lv[mip], tu, tv);
+            const float3 svs = screen_to_view(tu, tv, sd, cam);
+            const float  wz  = geometry_weight(pvs, svs, nvs, planeNorm);
+            osum += so * w[i] * wz;
+            wsum += w[i] * wz;
+        }
+        --mip;
+    }
+    st_cs(&out.at(x, y), osum / wsum);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A8: spatial reconstruction, the "bilateral blur" (SSAO_ComputeSpatialReconstruction.fx:49-100): 8-tap Poisson disk
+// rotated per pixel by Bayer4x4(frame), Gaussian x plane-distance weights, radius shrinking with accumulated history.
+// ---------------------------------------------------------------------------------------------------------------------
+__constant__ float3 kPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f},
+                                    {-0.3487388f, +0.4037880f, +0.5335386f}, {+0.1023042f, +0.6439373f, +0.6520134f},
+                                    {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
+                                    {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+
+__global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
+                                                           View<const float> occlusion, View<const float> history, View<const float> depth,
+                                                           View<const float4> normal, View<float> out, int y0, int y1)
+{
+    __shared__ SsaoCam S;
+    stage_cam(S, cams);
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+
+    const float hist = __ldg(&history.at(x, y));
+    const float d    = __ldg(&depth.at(x, y));
+    const float occC = __ldg(&occlusion.at(x, y));
+    const float acc  = powf(fabsf((hist - 1.0f) / 8.0f), 0.2f);
+    if (is_background(d) || acc >= 1.0f)
+    {
+        st_cs(&out.at(x, y), lerpf(1.0f, occC, A.AlphaInterpolation));
+        return;
+    }
+    const int    W = (int)cam.vw, H = (int)cam.vh;
+    const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
+    const float3 pvs  = screen_to_view(posx * cam.ivw, posy * cam.ivh, d, cam);
+    const float3 nvs  = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    float        rs, rc;
+    sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
+    const float radius    = lerpf(0.0f, A.SpatialReconstructionRadius, 1.0f - saturate(acc));
+    const float planeNorm = 10.0f / (1.0f + depth_to_camz(d, cam));
+
+    float osum = 0.0f, wsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        const float3 P = kPoisson8[i];
+        // RotateVector(Rotator=(cos, sin, -sin, cos), v) = v.x*(cos, -sin) + v.y*(sin, cos)
+        const float xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
+        const int   sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
+        const float sd = __ldg(&depth.at(sx, sy)), so = __ldg(&occlusion.at(sx, sy));
+        const float3 svs = screen_to_view((float(sx) + 0.5f) * cam.ivw, (float(sy) + 0.5f) * cam.ivh, sd, cam);
+        const float  ws  = expf(-(P.z * P.z) / (2.0f * 0.9f * 0.9f));
+        const float  wz  = geometry_weight(pvs, svs, nvs, planeNorm);
+        osum += ws * wz * so;
+        wsum += ws * wz;
+    }
+    const float o = wsum > 0.0f ? osum / wsum : occC;
+    st_cs(&out.at(x, y), lerpf(1.0f, o, A.AlphaInterpolation));
+}
+
+static bool make_pyr(const dfx_pyramid* p, PyrView& v, int min_levels)
+{
+    if (!p || p->levels < min_levels || p->levels > DFX_MAX_MIPS) return false;
+    v.levels = p->levels;
+    for (int i = 0; i < p->levels; ++i)
+    {
+        if (!make_view<const float>(&p->level[i], DFX_FORMAT_R32F, v.lv[i])) return false;
+        if (i > 0 && (v.lv[i].w != max(v.lv[0].w >> i, 1) || v.lv[i].h != max(v.lv[0].h >> i, 1))) return false;
+    }
+    return true;
+}
+static bool make_pyr_rw(const dfx_pyramid* p, PyrViewRW& v, int min_levels)
+{
+    if (!p || p->levels < min_levels || p->levels > DFX_MAX_MIPS) return false;
+    v.levels = p->levels;
+    for (int i = 0; i < p->levels; ++i)
+    {
+        if (!make_view<float>(&p->level[i], DFX_FORMAT_R32F, v.lv[i])) return false;
+        if (i > 0 && (v.lv[i].w != max(v.lv[0].w >> i, 1) || v.lv[i].h != max(v.lv[0].h >> i, 1))) return false;
+    }
+    return true;
+}
+static View<const float> ro(const View<float>& v) { return View<const float>{v.p, v.pitch, v.w, v.h}; }
+
+} // namespace dfx
+
+using namespace dfx;
+
+#define DFX_ROWS_ALIGNED(rows, h) DFX_REQUIRE(rows_ok(rows, h) && (rows.y0 % 64 == 0) && (rows.y1 % 64 == 0 || rows.y1 == (h)), "pyramid passes need 64-row aligned strips")
+
+extern "C" dfx_status dfx_pass_ssao_prefilter_depth(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssao_attribs* attribs,
+                                                    const dfx_pyramid* pyr, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    PyrViewRW P;
+    DFX_REQUIRE(make_pyr_rw(pyr, P, 1), "bad prefiltered-depth pyramid");
+    const int H = P.lv[0].h;
+    DFX_ROWS_ALIGNED(rows, H);
+    for (int m = 1; m < P.levels && m <= 4; ++m)
+    {
+        const int r0 = mip_row(rows.y0, m, H, P.lv[m].h), r1 = mip_row(rows.y1, m, H, P.lv[m].h);
+        if (r1 <= r0) continue;
+        dim3 block(32, 8), grid(div_up(P.lv[m].w, 32), div_up(r1 - r0, 8));
+        ssao_prefilter_level_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, ro(P.lv[m - 1]), P.lv[m], r0, r1);
+        DFX_LAUNCHED("ssao_prefilter_level_kernel");
+    }
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssao_attribs* attribs,
+                                                      const dfx_pyramid* prefiltered_depth, const dfx_plane* normal,
+                                                      const dfx_plane* blue_noise_zw, const dfx_plane* occlusion, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    PyrView P;
+    DFX_REQUIRE(make_pyr(prefiltered_depth, P, 1), "bad prefiltered-depth pyramid");
+    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float2, bn, blue_noise_zw, DFX_FORMAT_RG32F);
+    DFX_VIEW(float, out, occlusion, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(P.lv[0], n);
+    DFX_SAME_SIZE(P.lv[0], out);
+    DFX_REQUIRE(bn.w == 128 && bn.h == 128, "blue noise must be 128x128");
+    DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
+    switch (attribs->Algorithm)
+    {
+        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1); break;
+        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1); break;
+        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1); break;
+        default: return set_error(DFX_ERR_INVALID_ARG, "unknown SSAO algorithm %u", attribs->Algorithm);
+    }
+    DFX_LAUNCHED("ssao_ao_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_temporal(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssao_attribs* attribs,
+                                             const dfx_plane* curr_occlusion, const dfx_plane* prev_occlusion,
+                                             const dfx_plane* prev_history_length, const dfx_plane* reprojected_depth,
+                                             const dfx_plane* previous_depth, const dfx_plane* closest_motion,
+                                             const dfx_plane* out_occlusion, const dfx_plane* out_history_length, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    DFX_VIEW(const float, co, curr_occlusion, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, po, prev_occlusion, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, ph, prev_history_length, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, cd, reprojected_depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, pd, previous_depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float2, mv, closest_motion, DFX_FORMAT_RG32F);
+    DFX_VIEW(float, oo, out_occlusion, DFX_FORMAT_R32F);
+    DFX_VIEW(float, oh, out_history_length, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(co, po);
+    DFX_SAME_SIZE(co, ph);
+    DFX_SAME_SIZE(co, cd);
+    DFX_SAME_SIZE(co, pd);
+    DFX_SAME_SIZE(co, mv);
+    DFX_SAME_SIZE(co, oo);
+    DFX_SAME_SIZE(co, oh);
+    DFX_REQUIRE(rows_ok(rows, co.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    dim3 block(32, 8), grid(div_up(co.w, 32), div_up(rows.y1 - rows.y0, 8));
+    ssao_temporal_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, co, po, ph, cd, pd, mv, oo, oh, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssao_temporal_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_convolute(void* stream, const dfx_pyramid* occlusion_pyr, const dfx_pyramid* depth_pyr, dfx_rows rows)
+{
+    PyrViewRW O, D;
+    DFX_REQUIRE(make_pyr_rw(occlusion_pyr, O, 1) && make_pyr_rw(depth_pyr, D, 1), "bad pyramid");
+    DFX_REQUIRE(O.levels == D.levels, "pyramid level mismatch");
+    DFX_SAME_SIZE(O.lv[0], D.lv[0]);
+    const int H = O.lv[0].h;
+    DFX_ROWS_ALIGNED(rows, H);
+    for (int m = 1; m < O.levels && m <= 4; ++m)
+    {
+        const int r0 = mip_row(rows.y0, m, H, O.lv[m].h), r1 = mip_row(rows.y1, m, H, O.lv[m].h);
+        if (r1 <= r0) continue;
+        dim3 block(32, 8), grid(div_up(O.lv[m].w, 32), div_up(r1 - r0, 8));
+        ssao_convolute_level_kernel<<<grid, block, 0, as_stream(stream)>>>(ro(O.lv[m - 1]), ro(D.lv[m - 1]), O.lv[m], D.lv[m], r0, r1);
+        DFX_LAUNCHED("ssao_convolute_level_kernel");
+    }
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_pyramid* occlusion_pyr,
+                                             const dfx_pyramid* depth_pyr, const dfx_plane* history_length, const dfx_plane* normal,
+                                             const dfx_plane* out_occlusion, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev, "null argument");
+    PyrView O, D;
+    DFX_REQUIRE(make_pyr(occlusion_pyr, O, 1) && make_pyr(depth_pyr, D, 1), "bad pyramid");
+    DFX_REQUIRE(O.levels == D.levels, "pyramid level mismatch");
+    DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float, out, out_occlusion, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(O.lv[0], D.lv[0]);
+    DFX_SAME_SIZE(O.lv[0], h);
+    DFX_SAME_SIZE(O.lv[0], n);
+    DFX_SAME_SIZE(O.lv[0], out);
+    DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
+    ssao_resample_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, O, D, h, n, out, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssao_resample_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssao_attribs* attribs,
+                                            const dfx_plane* occlusion, const dfx_plane* history_length, const dfx_plane* depth,
+                                            const dfx_plane* normal, const dfx_plane* out_occlusion, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    DFX_VIEW(const float, o, occlusion, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float, out, out_occlusion, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(o, h);
+    DFX_SAME_SIZE(o, d);
+    DFX_SAME_SIZE(o, n);
+    DFX_SAME_SIZE(o, out);
+    DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
+    ssao_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssao_spatial_kernel");
+    return DFX_OK;
+}

@@ -1,0 +1,735 @@
+// dfx_ssr.cu — ScreenSpaceReflection passes S1, S2, S4-S7 as sm_100a kernels.
+// Reference host code: PostProcess/ScreenSpaceReflection/src/ScreenSpaceReflection.cpp:777-1104;
+// shaders: Shaders/PostProcess/ScreenSpaceReflection/private/SSR_*.fx (cited per kernel).
+// The D16 stencil mask of the reference is an R8U plane here: 1 = reflection sample, 0 = masked out. Consumers that the
+// reference draws depth-tested against the mask simply skip masked pixels (their targets keep their previous content).
+#include "dfx_common.cuh"
+
+namespace dfx
+{
+
+DFX_HD bool is_reflection_sample(float rough, float depth, float thr) { return rough <= thr && !is_background(depth); } // SSR_Common.fxh:57-60
+
+__host__ __device__ inline int ssr_mip_row(int y, int m, int full_h, int mip_h) { return y >= full_h ? mip_h : (y >> m); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S1: Hi-Z level m from m-1: closest (min) depth of the 2x2 footprint (+ odd row/column) — SSR_ComputeHierarchicalDepthBuffer.fx:30-73
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssr_hiz_level_kernel(View<const float> src, View<float> dst, int r0, int r1)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dst.w || y >= r1) return;
+    const bool wodd = src.w & 1, hodd = src.h & 1;
+    const int  rx = 2 * x, ry = 2 * y;
+    float      m = 1.0f;
+    m = fminf(m, loadc(src, rx, ry)), m = fminf(m, loadc(src, rx, ry + 1));
+    m = fminf(m, loadc(src, rx + 1, ry)), m = fminf(m, loadc(src, rx + 1, ry + 1));
+    if (wodd) m = fminf(m, loadc(src, rx + 2, ry)), m = fminf(m, loadc(src, rx + 2, ry + 1));
+    if (hodd) m = fminf(m, loadc(src, rx, ry + 2)), m = fminf(m, loadc(src, rx + 1, ry + 2));
+    if (wodd && hodd) m = fminf(m, loadc(src, rx + 2, ry + 2));
+    dst.at(x, y) = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S2: reflection mask + roughness extraction — SSR_ComputeStencilMaskAndExtractRoughness.fx:13-40
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, View<const float4> material, View<const float> depth,
+                                                       View<float> roughness, View<uint8_t> mask, int y0, int y1)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= depth.w || y >= y1) return;
+    const float4 m = __ldg(&material.at(x, y));
+    float r = A.RoughnessChannel == 0u ? m.x : A.RoughnessChannel == 1u ? m.y : A.RoughnessChannel == 2u ? m.z : A.RoughnessChannel == 3u ? m.w : 0.0f;
+    if (!A.IsRoughnessPerceptual) r = sqrtf(r);
+    const bool pass = is_reflection_sample(r, __ldg(&depth.at(x, y)), A.RoughnessThreshold);
+    mask.at(x, y) = pass ? 1 : 0;
+    if (pass) roughness.at(x, y) = r; // masked-out texels keep their stale value, like the reference's un-cleared target
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S4: stochastic GGX ray + Hi-Z march + hit validation — SSR_ComputeIntersection.fx:281-325
+// ---------------------------------------------------------------------------------------------------------------------
+struct IntersectCam
+{
+    CamS c;
+    Mat4 view, view_inv, proj;
+};
+
+struct HizView
+{
+    View<const float> lv[DFX_MAX_MIPS];
+    int               levels;
+};
+
+__device__ __forceinline__ float hiz_load(const HizView& h, int x, int y, int mip)
+{
+    if (mip < 0 || mip >= h.levels) return 0.0f;
+    return load0(h.lv[mip], x, y);
+}
+
+// PBR_Common.fxh:181-195
+DFX_HD float ndf_ggx(float NdotH, float a)
+{
+    a         = fmaxf(a, 1e-3f);
+    float a2  = a * a;
+    float nh2 = NdotH * NdotH;
+    float f   = nh2 * a2 + (1.0f - nh2);
+    return a2 / fmaxf(3.141592653589793f * f * f, 1e-9f);
+}
+// PBR_Common.fxh:149-176
+DFX_HD float smith_ggx_masking(float NdotV, float a)
+{
+    float a2 = a * a;
+    float dn = NdotV + sqrtf(a2 + (1.0f - a2) * NdotV * NdotV);
+    return 2.0f * fmaxf(NdotV, 0.0f) / fmaxf(dn, 1e-6f);
+}
+// PBR_Common.fxh:107-124
+DFX_HD float smith_ggx_visibility_correlated(float NdotL, float NdotV, float a)
+{
+    float a2   = a * a;
+    float ggxv = NdotL * sqrtf(fmaxf(NdotV * NdotV * (1.0f - a2) + a2, 1e-7f));
+    float ggxl = NdotV * sqrtf(fmaxf(NdotL * NdotL * (1.0f - a2) + a2, 1e-7f));
+    return 0.5f / (ggxv + ggxl);
+}
+
+DFX_HD float edge_vignette(float hx, float hy, float sw, float sh) // :192-197
+{
+    float fx = 0.05f * (sh / sw), fy = 0.05f;
+    float bx = smoothstepf(0.0f, fx, hx) * (1.0f - smoothstepf(1.0f - fx, 1.0f, hx));
+    float by = smoothstepf(0.0f, fy, hy) * (1.0f - smoothstepf(1.0f - fy, 1.0f, hy));
+    return bx * by;
+}
+
+template <bool PREV_FRAME>
+__global__ void __launch_bounds__(256) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+                                                            View<const float4> color, View<const float4> normal, View<const float> roughness,
+                                                            View<const uint8_t> mask, View<const float2> noise, HizView hiz,
+                                                            View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1)
+{
+    __shared__ IntersectCam S;
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+    {
+        load_cam(S.c, &cams[0]);
+        load_mat(S.view, cams[0].mView);
+        load_mat(S.view_inv, cams[0].mViewInv);
+        load_mat(S.proj, cams[0].mProj);
+    }
+    __syncthreads();
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_rad.w || y >= y1) return;
+    if (!__ldg(&mask.at(x, y)))
+    {
+        // cleared targets (ScreenSpaceReflection.cpp:991-994)
+        st_cs(&out_rad.at(x, y), make_float4(0.f, 0.f, 0.f, 0.f));
+        st_cs(&out_dir.at(x, y), make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
+    const float sw = cam.vw, sh = cam.vh;
+    const float u = (float(x) + 0.5f) * cam.ivw, v = (float(y) + 0.5f) * cam.ivh;
+    const float3 nws = xyz(__ldg(&normal.at(x, y)));
+    const float3 nvs = mul_dir(nws, S.view);
+    const float  rough = __ldg(&roughness.at(x, y));
+
+    const bool  mirror  = rough < 0.01f;
+    const int   baseMip = mirror ? 0 : (int)A.MostDetailedMip;
+    const float inv0    = 1.0f / float(1 << baseMip);
+    const float mrx = sw * inv0, mry = sh * inv0;
+
+    const float  originD = hiz_load(hiz, (int)(u * mrx), (int)(v * mry), baseMip);
+    const float3 originVS = screen_to_view(u, v, originD, cam);
+
+    // SampleReflectionVector :254-278
+    float3 dirVS;
+    float  pdf;
+    {
+        const float3 V = -normalize(originVS);
+        const float  a = rough * rough;
+        const float3 N = nvs;
+        const float3 T = normalize(cross(N, fabsf(N.y) > 0.5f ? make_float3(1.f, 0.f, 0.f) : make_float3(0.f, 1.f, 0.f)));
+        const float3 B = cross(T, N);
+        float2       xi = __ldg(&noise.at(x & 127, y & 127));
+        xi.y            = lerpf(xi.y, 0.0f, A.GGXImportanceSampleBias);
+        const float3 Vts = make_float3(dot(T, V), dot(B, V), dot(N, V));
+        // SmithGGXSampleVisibleNormalSC (PBR_Common.fxh:278-296) with ax == ay == a
+        const float3 Vs  = normalize(make_float3(Vts.x * a, Vts.y * a, Vts.z));
+        const float  phi = 2.0f * 3.141592653589793f * xi.x;
+        const float  Z   = (1.0f - xi.y) * (1.0f + Vs.z) - Vs.z;
+        const float  st  = sqrtf(fminf(fmaxf(1.0f - Z * Z, 0.0f), 1.0f));
+        float        sp, cp;
+        sincosf(phi, &sp, &cp);
+        const float3 Hh = make_float3(st * cp, st * sp, Z) + Vs;
+        const float3 Hm = normalize(make_float3(a * Hh.x, a * Hh.y, Hh.z));
+        // reflect(-Vts, Hm) = -Vts - 2*dot(Hm, -Vts)*Hm
+        const float3 I  = -Vts;
+        const float3 Lts = I - 2.0f * dot(Hm, I) * Hm;
+        const float  D  = ndf_ggx(Hm.z, a);
+        const float  G1 = smith_ggx_masking(Vts.z, a);
+        pdf             = G1 * D / (4.0f * Vts.z + kFltEps);
+        dirVS           = Lts.x * T + Lts.y * B + Lts.z * N;
+    }
+    // ProjectDirection (PostFX_Common.fxh:94-97)
+    const float3 endSS = project_position(originVS + dirVS, S.proj);
+    const float3 O     = make_float3(u, v, originD);
+    const float3 Dr    = endSS - O;
+    const float3 dirWS = mul_dir(dirVS, S.view_inv);
+
+    // HierarchicalRaymarch :139-189
+    float3 pos;
+    bool   validHit;
+    {
+        const float3 invD = make_float3(Dr.x != 0.0f ? 1.0f / Dr.x : kFltMax, Dr.y != 0.0f ? 1.0f / Dr.y : kFltMax, Dr.z != 0.0f ? 1.0f / Dr.z : kFltMax);
+        int   mip = baseMip;
+        float resx = sw * inv0, resy = sh * inv0;
+        float irx = 1.0f / resx, iry = 1.0f / resy;
+        float uox = 0.005f * float(1 << baseMip) / sw, uoy = 0.005f * float(1 << baseMip) / sh;
+        uox = Dr.x < 0.0f ? -uox : uox, uoy = Dr.y < 0.0f ? -uoy : uoy;
+        const float fox = Dr.x < 0.0f ? 0.0f : 1.0f, foy = Dr.y < 0.0f ? 0.0f : 1.0f;
+
+        float t;
+        {
+            // InitialAdvanceRay :66-86
+            float px = (floorf(resx * O.x) + fox) * irx + uox, py = (floorf(resy * O.y) + foy) * iry + uoy;
+            float tx = px * invD.x - O.x * invD.x, ty = py * invD.y - O.y * invD.y;
+            t   = fminf(tx, ty);
+            pos = O + t * Dr;
+        }
+        uint32_t i = 0u;
+        while (i < A.MaxTraversalIntersections && mip >= baseMip)
+        {
+            const float mx = resx * pos.x, my = resy * pos.y;
+            const float surf = hiz_load(hiz, (int)mx, (int)my, mip);
+            // AdvanceRay :88-136
+            const float px = (floorf(mx) + fox) * irx + uox, py = (floorf(my) + foy) * iry + uoy;
+            const float tx = px * invD.x - O.x * invD.x, ty = py * invD.y - O.y * invD.y;
+            float       tz = surf * invD.z - O.z * invD.z;
+            tz             = Dr.z > 0.0f ? tz : kFltMax;
+            const float tmin  = fminf(fminf(tx, ty), tz);
+            const bool  above = surf > pos.z;
+            const bool  skipped = (__float_as_uint(tmin) != __float_as_uint(tz)) && above;
+            t   = above ? tmin : t;
+            pos = O + t * Dr;
+            const bool outOfRange = skipped && (mip >= 6);
+            if (!outOfRange)
+            {
+                mip += skipped ? 1 : -1;
+                const float s = skipped ? 0.5f : 2.0f, is = skipped ? 2.0f : 0.5f;
+                resx *= s, resy *= s, irx *= is, iry *= is;
+            }
+            ++i;
+        }
+        validHit = (i <= A.MaxTraversalIntersections);
+    }
+    const float3 hitVS = screen_to_view(pos.x, pos.y, pos.z, cam);
+
+    float hpx = pos.x, hpy = pos.y; // previous-frame hit position
+    if (PREV_FRAME)
+    {
+        float2 mv = load0(motion, (int)(sw * pos.x), (int)(sh * pos.y));
+        hpx = pos.x - mv.x * 0.5f, hpy = pos.y - mv.y * -0.5f;
+    }
+
+    // ValidateHit :201-242
+    float confidence = 0.0f;
+    if (validHit && !(pos.x < 0.0f || pos.y < 0.0f || pos.x > 1.0f || pos.y > 1.0f))
+    {
+        const float mdx = fabsf(pos.x - u), mdy = fabsf(pos.y - v);
+        if (!(mdx < (2.0f / sw) && mdy < (2.0f / sh)))
+        {
+            const int   tx = (int)(sw * pos.x), ty = (int)(sh * pos.y);
+            const float surfD = hiz_load(hiz, tx, ty, 0);
+            if (!is_background(surfD))
+            {
+                const float3 hitN = xyz(load0(normal, tx, ty));
+                if (!(dot(hitN, dirWS) > 0.0f))
+                {
+                    const float3 surfVS = screen_to_view(pos.x, pos.y, surfD, cam);
+                    const float3 dd     = surfVS - hitVS;
+                    const float  dist   = length(dd);
+                    float        vig    = edge_vignette(pos.x, pos.y, sw, sh);
+                    if (PREV_FRAME) vig = fminf(edge_vignette(hpx, hpy, sw, sh), vig);
+                    float c = 1.0f - smoothstepf(0.0f, A.DepthBufferThickness, dist * (1.0f / (surfVS.z + kFltEps)));
+                    c *= c;
+                    confidence = vig * c;
+                }
+            }
+        }
+    }
+    float3 radiance = make_float3(0.f, 0.f, 0.f);
+    if (confidence > 0.0f) radiance = xyz(load0(color, (int)(sw * hpx), (int)(sh * hpy)));
+    const float3 dv = hitVS - originVS;
+    st_cs(&out_rad.at(x, y), f4(radiance, confidence));
+    st_cs(&out_dir.at(x, y), f4(dirWS * length(dv), pdf));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S5: spatial reconstruction — SSR_ComputeSpatialReconstruction.fx:114-172
+// ---------------------------------------------------------------------------------------------------------------------
+__constant__ float3 kSsrPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f},
+                                       {-0.3487388f, +0.4037880f, +0.5335386f}, {+0.1023042f, +0.6439373f, +0.6520134f},
+                                       {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
+                                       {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+struct SpatialCam
+{
+    CamS c;
+    Mat4 vp_inv;
+};
+
+__global__ void __launch_bounds__(256) ssr_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+                                                          View<const float> roughness, View<const uint8_t> mask, View<const float4> normal,
+                                                          View<const float> depth, View<const float4> raydir, View<const float4> radiance,
+                                                          View<float4> out_rad, View<float> out_var, View<float> out_depth, int y0, int y1)
+{
+    __shared__ SpatialCam S;
+    if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_mat(S.vp_inv, cams[0].mViewProjInv);
+    __syncthreads();
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_rad.w || y >= y1) return;
+    if (!__ldg(&mask.at(x, y))) return;
+
+    const int    W = (int)cam.vw, H = (int)cam.vh;
+    const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
+    const float3 camPos = make_float3(cam.px, cam.py, cam.pz);
+    const float3 pws = inv_project_position(posx * cam.ivw, posy * cam.ivh, __ldg(&depth.at(x, y)), S.vp_inv);
+    const float3 nws = xyz(__ldg(&normal.at(x, y)));
+    const float3 vws = normalize(camPos - pws);
+    const float  NdotV = saturate(dot(nws, vws));
+    const float  rough = __ldg(&roughness.at(x, y));
+    const float  radius = lerpf(0.0f, A.SpatialReconstructionRadius, saturate(5.0f * rough));
+    float        rs, rc;
+    sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
+
+    float4 colorSum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float  wsum = 0.0f, variance = 0.0f, mean = 0.0f, nearest = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        const float3 P  = kSsrPoisson8[i];
+        const float  xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
+        const int    sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
+        const float  ws = expf(-(P.z * P.z) / (2.0f * 0.9f * 0.9f));
+        // ComputeWeightRayLength :60-86
+        float        weight, raylen;
+        const float4 rd = __ldg(&raydir.at(sx, sy));
+        const float  len = length(xyz(rd));
+        if (len < 1e-6f)
+        {
+            weight = 1e-6f, raylen = 1e-6f;
+        }
+        else
+        {
+            const float3 L  = xyz(rd) / len;
+            const float  a  = rough * rough;
+            const float3 Hh = normalize(L + vws);
+            const float  NdotH = saturate(dot(nws, Hh)), NdotL = saturate(dot(nws, L));
+            float        brdf  = smith_ggx_visibility_correlated(NdotL, NdotV, a) * ndf_ggx(NdotH, a) * NdotL;
+            brdf *= ws;
+            weight = fmaxf(brdf / fmaxf(rd.w, 1e-5f), 1e-6f);
+            raylen = len;
+        }
+        const float4 c = __ldg(&radiance.at(sx, sy));
+        // ComputeWeightedVariance :90-100
+        colorSum = colorSum + weight * c;
+        wsum += weight;
+        const float value = luminance(xyz(c)), prevMean = mean;
+        mean += weight * (1.0f / wsum) * (value - prevMean);
+        variance += weight * (value - prevMean) * (value - mean);
+        if (weight > 1.0e-6f) nearest = fmaxf(raylen, nearest);
+    }
+    const float den = fmaxf(wsum, 1e-6f);
+    out_rad.at(x, y) = colorSum / den;
+    out_var.at(x, y) = variance / den;
+    const float3 dd  = camPos - pws;
+    out_depth.at(x, y) = camz_to_depth(length(dd) + nearest, cam);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S6: temporal accumulation — SSR_ComputeTemporalAccumulation.fx:224-263
+// ---------------------------------------------------------------------------------------------------------------------
+struct SsrTemporalCam
+{
+    CamS c, p;
+    Mat4 curr_vp_inv, prev_vp;
+    float pjx, pjy;
+};
+
+DFX_HD float disocclusion(float cz, float pz) // :111-116
+{
+    cz = fabsf(cz), pz = fabsf(pz);
+    return expf(-fabsf(cz - pz) / fmaxf(fmaxf(cz, pz), 1e-6f));
+}
+
+__global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+                                                           View<const uint8_t> mask, View<const float2> motion, View<const float> hit_depth,
+                                                           View<const float> curr_depth, View<const float4> curr_rad, View<const float> curr_var,
+                                                           View<const float> prev_depth, View<const float4> prev_rad, View<const float> prev_var,
+                                                           View<float4> out_rad, View<float> out_var, int y0, int y1)
+{
+    __shared__ SsrTemporalCam S;
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+    {
+        load_cam(S.c, &cams[0]), load_cam(S.p, &cams[1]);
+        load_mat(S.curr_vp_inv, cams[0].mViewProjInv), load_mat(S.prev_vp, cams[1].mViewProj);
+        S.pjx = cams[1].f2Jitter[0], S.pjy = cams[1].f2Jitter[1];
+    }
+    __syncthreads();
+    const CamS& cam = S.c;
+    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_rad.w || y >= y1) return;
+    if (!__ldg(&mask.at(x, y))) return;
+
+    const int   W = (int)cam.vw, H = (int)cam.vh;
+    const float posx = float(x) + 0.5f, posy = float(y) + 0.5f;
+
+    // ComputePixelStatistic :119-145
+    float4 m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+        {
+            const float4 s = __ldg(&curr_rad.at(min(max(x + dx, 0), W - 1), min(max(y + dy, 0), H - 1)));
+            m1 = m1 + s, m2 = m2 + s * s;
+        }
+    const float4 mean = m1 / 9.0f;
+    const float4 var  = (m2 / 9.0f) - (mean * mean);
+    const float4 sd   = make_float4(sqrtf(fmaxf(var.x, 0.f)), sqrtf(fmaxf(var.y, 0.f)), sqrtf(fmaxf(var.z, 0.f)), sqrtf(fmaxf(var.w, 0.f)));
+
+    const float depth = __ldg(&curr_depth.at(x, y));
+    const float hitD  = __ldg(&hit_depth.at(x, y));
+    float2      mv    = __ldg(&motion.at(x, y));
+    mv.x *= 0.5f, mv.y *= -0.5f;
+
+    const float ipx = posx - mv.x * cam.vw, ipy = posy - mv.y * cam.vh; // PrevIncidentPoint
+    // ComputeReflectionHitPosition :102-108
+    float rhx, rhy;
+    {
+        const float  tu = posx * cam.ivw + 0.5f * cam.jx, tv = posy * cam.ivh + -0.5f * cam.jy;
+        const float3 pws = inv_project_position(tu, tv, hitD, S.curr_vp_inv);
+        const float3 puv = project_position(pws, S.prev_vp);
+        rhx = (puv.x - 0.5f * S.pjx) * cam.vw, rhy = (puv.y - -0.5f * S.pjy) * cam.vh;
+    }
+    const float4 cI = sample_linear_clamp(prev_rad, ipx * cam.ivw, ipy * cam.ivh);
+    const float4 cR = sample_linear_clamp(prev_rad, rhx * cam.ivw, rhy * cam.ivh);
+    const float  lm = luminance(xyz(mean));
+    const float  dI = fabsf(luminance(xyz(cI)) - lm), dR = fabsf(luminance(xyz(cR)) - lm);
+    const float  ppx = dI < dR ? ipx : rhx, ppy = dI < dR ? ipy : rhy;
+
+    // ComputeReprojection :147-221
+    const float currZ = depth_to_camz(depth, cam);
+    float4      rcol;
+    float       rpx = ppx, rpy = ppy;
+    bool        ok;
+    {
+        const float pz = depth_to_camz(load0(prev_depth, (int)ppx, (int)ppy), S.p);
+        rcol           = sample_linear_clamp(prev_rad, ppx * cam.ivw, ppy * cam.ivh);
+        ok             = disocclusion(currZ, pz) > 0.9f;
+    }
+    if (!ok)
+    {
+        float bw00 = 0.f, bw10 = 0.f, bw01 = 0.f, bw11 = 0.f, best = 0.0f;
+        int   bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
+        bool  done = false;
+        for (int dy = -1; dy <= 1 && !done; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+            {
+                const float lx = ppx + float(dx), ly = ppy + float(dy);
+                const Bilin b  = bilinear_uc(lx, ly, curr_depth.w, curr_depth.h);
+                auto pass = [&](int sx, int sy) { return disocclusion(currZ, depth_to_camz(load0(prev_depth, sx, sy), S.p)) > 0.45f ? 1.0f : 0.0f; };
+                const float w00 = b.w00 * pass(b.x0, b.y0), w10 = b.w10 * pass(b.x1, b.y0), w01 = b.w01 * pass(b.x0, b.y1), w11 = b.w11 * pass(b.x1, b.y1);
+                const float tot = w00 * 1.0f + w10 * 1.0f + w01 * 1.0f + w11 * 1.0f;
+                if (tot > best)
+                {
+                    best = tot, bw00 = w00, bw10 = w10, bw01 = w01, bw11 = w11;
+                    bx0 = b.x0, by0 = b.y0, bx1 = b.x1, by1 = b.y1;
+                    rpx = lx, rpy = ly;
+                    if (best > 0.9f)
+                    {
+                        done = true;
+                        break;
+                    }
+                }
+            }
+        ok = best > 0.1f;
+        if (ok)
+            rcol = (load0(prev_rad, bx0, by0) * bw00 + load0(prev_rad, bx1, by0) * bw10 + load0(prev_rad, bx0, by1) * bw01 + load0(prev_rad, bx1, by1) * bw11) / best;
+    }
+    ok = ok && (rpx >= 0.0f && rpy >= 0.0f && rpx < cam.vw && rpy < cam.vh);
+
+    const float4 cr = __ldg(&curr_rad.at(x, y));
+    if (ok)
+    {
+        const float4 lo = mean - 2.5f * sd, hi = mean + 2.5f * sd;
+        const float4 pr = make_float4(fminf(fmaxf(rcol.x, lo.x), hi.x), fminf(fmaxf(rcol.y, lo.y), hi.y), fminf(fmaxf(rcol.z, lo.z), hi.z),
+                                      fminf(fmaxf(rcol.w, lo.w), hi.w));
+        const float  pv = sample_linear_clamp(prev_var, rpx * cam.ivw, rpy * cam.ivh);
+        out_rad.at(x, y) = lerp4(cr, pr, A.TemporalRadianceStabilityFactor);
+        out_var.at(x, y) = lerpf(__ldg(&curr_var.at(x, y)), pv, A.TemporalVarianceStabilityFactor);
+    }
+    else
+    {
+        out_rad.at(x, y) = cr;
+        out_var.at(x, y) = 1.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S7: bilateral cleanup — SSR_ComputeBilateralCleanup.fx:49-97. ddx/ddy(CameraZ) are the 2x2 pixel-quad finite
+// differences v(x|1) - v(x&~1), v(y|1) - v(y&~1) (coordinates clamped at odd image edges).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+                                                            View<const uint8_t> mask, View<const float> depth, View<const float4> normal,
+                                                            View<const float> roughness, View<const float4> radiance, View<const float> variance,
+                                                            View<float4> out, int y0, int y1)
+{
+    __shared__ CamS cam;
+    if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(cam, &cams[0]);
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+    if (!__ldg(&mask.at(x, y)))
+    {
+        st_cs(&out.at(x, y), make_float4(0.f, 0.f, 0.f, 0.f)); // cleared target (…cpp:1097-1099)
+        return;
+    }
+    const int   W = (int)cam.vw, H = (int)cam.vh;
+    const float rough = __ldg(&roughness.at(x, y));
+    const float var   = __ldg(&variance.at(x, y));
+    const float3 nws  = xyz(__ldg(&normal.at(x, y)));
+    const float  camZ = depth_to_camz(__ldg(&depth.at(x, y)), cam);
+    auto         cz   = [&](int sx, int sy) { return depth_to_camz(loadc(depth, sx, sy), cam); };
+    const float  gx = cz(x | 1, y) - cz(x & ~1, y), gy = cz(x, y | 1) - cz(x, y & ~1);
+
+    const float target = saturate(8.0f * rough);
+    const float radius = lerpf(0.0f, var > 0.001f ? 2.0f : 0.0f, target);
+    const float sigma  = A.BilateralCleanupSpatialSigmaFactor;
+    const int   er     = (int)fminf(2.0f * sigma, radius);
+    float4      result = __ldg(&radiance.at(x, y));
+    if (var > 0.00005f && er > 0)
+    {
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+        float  wsum = 0.0f;
+        for (int dx = -er; dx <= er; ++dx)
+            for (int dy = -er; dy <= er; ++dy)
+            {
+                const int   sx = min(max(x + dx, 0), W - 1), sy = min(max(y + dy, 0), H - 1);
+                const float sd = __ldg(&depth.at(sx, sy)), sr = __ldg(&roughness.at(sx, sy));
+                if (is_reflection_sample(sr, sd, A.RoughnessThreshold))
+                {
+                    const float4 srad = __ldg(&radiance.at(sx, sy));
+                    const float3 sn   = xyz(__ldg(&normal.at(sx, sy)));
+                    const float  sz   = depth_to_camz(sd, cam);
+                    const float  fx = float(dx), fy = float(dy);
+                    const float  ws = expf(-0.5f * (fx * fx + fy * fy) / (sigma * sigma));
+                    const float  wz = expf(-fabsf(camZ - sz) / (1.0f * (fabsf(fx * gx + fy * gy) + 1e-6f)));
+                    const float  wn = powf(fmaxf(0.0f, dot(nws, sn)), 128.0f);
+                    const float  w  = ws * wn * wz;
+                    wsum += w;
+                    csum = csum + w * srad;
+                }
+            }
+        result = csum / fmaxf(wsum, 1.0e-6f);
+    }
+    st_cs(&out.at(x, y), make_float4(result.x, result.y, result.z, result.w * A.AlphaInterpolation));
+}
+
+static bool make_hiz(const dfx_pyramid* p, HizView& v)
+{
+    if (!p || p->levels < 1 || p->levels > DFX_MAX_MIPS) return false;
+    v.levels = p->levels;
+    for (int i = 0; i < p->levels; ++i)
+    {
+        if (!make_view<const float>(&p->level[i], DFX_FORMAT_R32F, v.lv[i])) return false;
+        if (i > 0 && (v.lv[i].w != max(v.lv[0].w >> i, 1) || v.lv[i].h != max(v.lv[0].h >> i, 1))) return false;
+    }
+    return true;
+}
+
+} // namespace dfx
+
+using namespace dfx;
+
+extern "C" dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx_rows rows)
+{
+    DFX_REQUIRE(pyr && pyr->levels >= 1 && pyr->levels <= DFX_MAX_MIPS, "bad Hi-Z pyramid");
+    View<float> lv[DFX_MAX_MIPS];
+    for (int i = 0; i < pyr->levels; ++i)
+    {
+        DFX_REQUIRE(make_view<float>(&pyr->level[i], DFX_FORMAT_R32F, lv[i]), "bad Hi-Z level %d", i);
+        DFX_REQUIRE(i == 0 || (lv[i].w == max(lv[0].w >> i, 1) && lv[i].h == max(lv[0].h >> i, 1)), "Hi-Z level %d has the wrong size", i);
+    }
+    const int H = lv[0].h;
+    DFX_REQUIRE(rows_ok(rows, H) && rows.y0 % 64 == 0 && (rows.y1 % 64 == 0 || rows.y1 == H), "pyramid passes need 64-row aligned strips");
+    for (int m = 1; m < pyr->levels && m <= 6; ++m)
+    {
+        const int r0 = ssr_mip_row(rows.y0, m, H, lv[m].h), r1 = ssr_mip_row(rows.y1, m, H, lv[m].h);
+        if (r1 <= r0) continue;
+        dim3 block(32, 8), grid(div_up(lv[m].w, 32), div_up(r1 - r0, 8));
+        View<const float> src{lv[m - 1].p, lv[m - 1].pitch, lv[m - 1].w, lv[m - 1].h};
+        ssr_hiz_level_kernel<<<grid, block, 0, as_stream(stream)>>>(src, lv[m], r0, r1);
+        DFX_LAUNCHED("ssr_hiz_level_kernel");
+    }
+    return DFX_OK;
+}
+
+#define DFX_GRID(w, rows) dim3 block(32, 8), grid(div_up(w, 32), div_up(rows.y1 - rows.y0, 8))
+
+extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_attribs* attribs, const dfx_plane* material, const dfx_plane* depth,
+                                                  const dfx_plane* roughness, const dfx_plane* mask, dfx_rows rows)
+{
+    DFX_REQUIRE(attribs, "null argument");
+    DFX_VIEW(const float4, m, material, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(float, r, roughness, DFX_FORMAT_R32F);
+    DFX_VIEW(uint8_t, k, mask, DFX_FORMAT_R8U);
+    DFX_SAME_SIZE(d, m);
+    DFX_SAME_SIZE(d, r);
+    DFX_SAME_SIZE(d, k);
+    DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    DFX_GRID(d.w, rows);
+    ssr_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssr_mask_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, uint32_t flags,
+                                             const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness, const dfx_plane* mask,
+                                             const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz, const dfx_plane* motion,
+                                             const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) == 0, "half-resolution SSR is not implemented");
+    DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
+    DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
+    DFX_VIEW(const float2, bn, blue_noise_xy, DFX_FORMAT_RG32F);
+    DFX_VIEW(float4, orad, out_radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float4, odir, out_raydir_pdf, DFX_FORMAT_RGBA32F);
+    HizView H;
+    DFX_REQUIRE(make_hiz(hiz, H), "bad Hi-Z pyramid");
+    DFX_SAME_SIZE(c, n);
+    DFX_SAME_SIZE(c, r);
+    DFX_SAME_SIZE(c, k);
+    DFX_SAME_SIZE(c, orad);
+    DFX_SAME_SIZE(c, odir);
+    DFX_SAME_SIZE(c, H.lv[0]);
+    DFX_REQUIRE(bn.w == 128 && bn.h == 128, "blue noise must be 128x128");
+    DFX_REQUIRE(rows_ok(rows, c.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    DFX_GRID(c.w, rows);
+    if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
+    {
+        DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
+        DFX_SAME_SIZE(c, mv);
+        ssr_intersect_kernel<true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1);
+    }
+    else
+    {
+        View<const float2> mv{nullptr, 0, 0, 0};
+        ssr_intersect_kernel<false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1);
+    }
+    DFX_LAUNCHED("ssr_intersect_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs,
+                                           const dfx_plane* roughness, const dfx_plane* mask, const dfx_plane* normal, const dfx_plane* depth,
+                                           const dfx_plane* raydir_pdf, const dfx_plane* radiance, const dfx_plane* out_resolved_radiance,
+                                           const dfx_plane* out_resolved_variance, const dfx_plane* out_resolved_depth, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
+    DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
+    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, rd, raydir_pdf, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float4, ra, radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float4, orad, out_resolved_radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float, ovar, out_resolved_variance, DFX_FORMAT_R32F);
+    DFX_VIEW(float, odep, out_resolved_depth, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(d, r);
+    DFX_SAME_SIZE(d, k);
+    DFX_SAME_SIZE(d, n);
+    DFX_SAME_SIZE(d, rd);
+    DFX_SAME_SIZE(d, ra);
+    DFX_SAME_SIZE(d, orad);
+    DFX_SAME_SIZE(d, ovar);
+    DFX_SAME_SIZE(d, odep);
+    DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    DFX_GRID(d.w, rows);
+    ssr_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, r, k, n, d, rd, ra, orad, ovar, odep, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssr_spatial_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_plane* mask,
+                                            const dfx_plane* motion, const dfx_plane* hit_depth, const dfx_plane* reprojected_depth,
+                                            const dfx_plane* curr_radiance, const dfx_plane* curr_variance, const dfx_plane* previous_depth,
+                                            const dfx_plane* prev_radiance, const dfx_plane* prev_variance, const dfx_plane* out_radiance,
+                                            const dfx_plane* out_variance, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
+    DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
+    DFX_VIEW(const float, hd, hit_depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, cd, reprojected_depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, cr, curr_radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, cv, curr_variance, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, pd, previous_depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, pr, prev_radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, pv, prev_variance, DFX_FORMAT_R32F);
+    DFX_VIEW(float4, orad, out_radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float, ovar, out_variance, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(cd, k);
+    DFX_SAME_SIZE(cd, mv);
+    DFX_SAME_SIZE(cd, hd);
+    DFX_SAME_SIZE(cd, cr);
+    DFX_SAME_SIZE(cd, cv);
+    DFX_SAME_SIZE(cd, pd);
+    DFX_SAME_SIZE(cd, pr);
+    DFX_SAME_SIZE(cd, pv);
+    DFX_SAME_SIZE(cd, orad);
+    DFX_SAME_SIZE(cd, ovar);
+    DFX_REQUIRE(rows_ok(rows, cd.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    DFX_GRID(cd.w, rows);
+    ssr_temporal_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssr_temporal_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_plane* mask,
+                                             const dfx_plane* depth, const dfx_plane* normal, const dfx_plane* roughness, const dfx_plane* radiance,
+                                             const dfx_plane* variance, const dfx_plane* out, dfx_rows rows)
+{
+    DFX_REQUIRE(cameras_dev && attribs, "null argument");
+    DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
+    DFX_VIEW(const float4, ra, radiance, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float, va, variance, DFX_FORMAT_R32F);
+    DFX_VIEW(float4, o, out, DFX_FORMAT_RGBA32F);
+    DFX_SAME_SIZE(d, k);
+    DFX_SAME_SIZE(d, n);
+    DFX_SAME_SIZE(d, r);
+    DFX_SAME_SIZE(d, ra);
+    DFX_SAME_SIZE(d, va);
+    DFX_SAME_SIZE(d, o);
+    DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    DFX_GRID(d.w, rows);
+    ssr_bilateral_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, d, n, r, ra, va, o, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssr_bilateral_kernel");
+    return DFX_OK;
+}

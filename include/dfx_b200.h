@@ -1,0 +1,524 @@
+/* dfx_b200.h — C-ABI of the B200-native DiligentFX PostProcess chain.
+ *
+ * This is the drop-in boundary: every entry point is `extern "C"`, takes plain pointers /
+ * sizes / POD structs, never throws and returns a dfx_status. It replaces, for the PostProcess hot path only,
+ * what the reference records through DiligentCore's IDeviceContext inside
+ *   PostFXContext::Execute                 (PostProcess/Common/src/PostFXContext.cpp:287-338)
+ *   ScreenSpaceAmbientOcclusion::Execute   (PostProcess/ScreenSpaceAmbientOcclusion/src/ScreenSpaceAmbientOcclusion.cpp:348-387)
+ *   ScreenSpaceReflection::Execute         (PostProcess/ScreenSpaceReflection/src/ScreenSpaceReflection.cpp:300-341)
+ *   Bloom::Execute                         (PostProcess/Bloom/src/Bloom.cpp:407-436)
+ *   TemporalAntiAliasing::Execute          (PostProcess/TemporalAntiAliasing/src/TemporalAntiAliasing.cpp:169-201)
+ *   ToneMap()                              (Shaders/PostProcess/ToneMapping/public/ToneMapping.fxh:87-226)
+ *
+ * Two layers:
+ *   1. pass level   `dfx_pass_*`  — one stateless call per reference render pass (or fused pass group); every
+ *                                   plane is passed explicitly. This is what the parity tests drive.
+ *   2. effect level `dfx_<effect>_{create,prepare,execute,get_plane,destroy}` — owns the effect's internal
+ *                                   planes (history ping-pong, pyramids) exactly like the reference classes own
+ *                                   their textures; the C++ headers under include/dfx/ wrap these in C++ classes with the
+ *                                   reference's own signatures.
+ *
+ * All device pointers are CUDA device pointers on the current device; `stream` is a cudaStream_t passed as void*.
+ * There is no CPU fallback: every entry fails with DFX_ERR_CUDA when no sm_100 device/driver is usable.
+ */
+#ifndef DFX_B200_H
+#define DFX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFX_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* status                                                                                                       */
+typedef enum dfx_status
+{
+    DFX_OK               = 0,
+    DFX_ERR_INVALID_ARG  = 1, /* null pointer, bad format, mismatched size (reference: DEV_CHECK_ERR)        */
+    DFX_ERR_CUDA         = 2, /* a CUDA runtime call or launch failed; see dfx_last_error()                   */
+    DFX_ERR_NOT_PREPARED = 3, /* execute before prepare (reference: TemporalAntiAliasing.cpp:178-183)         */
+    DFX_ERR_UNSUPPORTED  = 4  /* feature flag not implemented in this build (half-res / reversed depth …)   */
+} dfx_status;
+
+DFX_API const char* dfx_last_error(void);           /* thread-local message of the last non-OK status      */
+DFX_API int         dfx_version(void);              /* 10000*major + 100*minor + patch                     */
+DFX_API uint64_t    dfx_launch_count(void);         /* kernels launched by this library so far (process)   */
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* planes                                                                                                       */
+typedef enum dfx_format
+{
+    DFX_FORMAT_UNKNOWN = 0,
+    DFX_FORMAT_R32F    = 1, /* depth, AO, history length, variance, roughness …            4 B/texel */
+    DFX_FORMAT_RG32F   = 2, /* motion vectors, blue noise                                  8 B/texel */
+    DFX_FORMAT_RGBA32F = 3, /* colour, normal (xyz_), material, radiance, bloom levels    16 B/texel */
+    DFX_FORMAT_R8U     = 4  /* SSR reflection mask (stands in for the D16 stencil mask)    1 B/texel */
+} dfx_format;
+
+/* A pitched 2-D array in HBM: row y starts at (char*)ptr + y*pitch_bytes. Stands in for ITextureView. */
+typedef struct dfx_plane
+{
+    void*    ptr;
+    size_t   pitch_bytes;
+    int32_t  width;
+    int32_t  height;
+    int32_t  format; /* dfx_format */
+    int32_t  reserved;
+} dfx_plane;
+
+#define DFX_MAX_MIPS 8
+/* A mip chain of planes (level i is max(w>>i,1) x max(h>>i,1)). Stands in for a mip-mapped ITexture. */
+typedef struct dfx_pyramid
+{
+    dfx_plane level[DFX_MAX_MIPS];
+    int32_t   levels;
+    int32_t   reserved;
+} dfx_pyramid;
+
+/* Row range [y0, y1) of the full frame that a call computes. {0, height} = whole frame. Used by the row-strip
+ * multi-GPU path: every GPU holds full-size planes and computes only its strip; halo rows are
+ * exchanged between calls. For pyramid passes y0/y1 must be multiples of 64 (or y1 == height).               */
+typedef struct dfx_rows
+{
+    int32_t y0;
+    int32_t y1;
+} dfx_rows;
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* constant blocks — byte-identical to the reference's shared C++/HLSL structs                                  */
+
+typedef struct dfx_float4x4 { float m[4][4]; } dfx_float4x4; /* row-major, row-vector convention mul(v, M) */
+
+/* == HLSL::CameraAttribs, Shaders/Common/public/BasicStructures.fxh:84-149 (576 bytes) */
+typedef struct dfx_camera_attribs
+{
+    float f4Position[4];
+    float f4ViewportSize[4]; /* (width, height, 1/width, 1/height) */
+    float fNearPlaneZ, fFarPlaneZ, fNearPlaneDepth, fFarPlaneDepth;
+    float fSceneNearZ, fSceneFarZ, fSceneNearDepth, fSceneFarDepth;
+    float    fHandness;
+    uint32_t uiFrameIndex;
+    float    Padding0, Padding1;
+    float fFocusDistance, fFStop, fFocalLength, fSensorWidth;
+    float fSensorHeight, fExposure;
+    float f2Jitter[2];
+    dfx_float4x4 mView, mProj, mViewProj, mViewInv, mProjInv, mViewProjInv;
+    float f4ExtraData[5][4];
+} dfx_camera_attribs;
+
+/* == HLSL::ScreenSpaceAmbientOcclusionAttribs, …/ScreenSpaceAmbientOcclusionStructures.fxh:64-98 (48 bytes) */
+typedef struct dfx_ssao_attribs
+{
+    float    EffectRadius;                /* 1.0   */
+    float    EffectFalloffRange;          /* 0.615 */
+    float    RadiusMultiplier;            /* 1.457 */
+    float    DepthMIPSamplingOffset;      /* 3.3   */
+    float    TemporalStabilityFactor;     /* 0.9   */
+    float    SpatialReconstructionRadius; /* 4.0   */
+    int32_t  ResetAccumulation;           /* FALSE */
+    float    AlphaInterpolation;          /* 1.0   */
+    float    BitmaskThickness;            /* 0.5   */
+    uint32_t Algorithm;                   /* DFX_SSAO_ALGORITHM_GTAO */
+    float    Padding0, Padding1;
+} dfx_ssao_attribs;
+#define DFX_SSAO_ALGORITHM_GTAO 0
+#define DFX_SSAO_ALGORITHM_HBAO 1
+#define DFX_SSAO_ALGORITHM_VBAO 2
+
+/* == HLSL::ScreenSpaceReflectionAttribs, …/ScreenSpaceReflectionStructures.fxh:43-80 (48 bytes) */
+typedef struct dfx_ssr_attribs
+{
+    float    DepthBufferThickness;               /* 0.025 */
+    float    RoughnessThreshold;                 /* 0.2   */
+    uint32_t MostDetailedMip;                    /* 0     */
+    int32_t  IsRoughnessPerceptual;              /* TRUE  */
+    uint32_t RoughnessChannel;                   /* 0     */
+    uint32_t MaxTraversalIntersections;          /* 128   */
+    float    GGXImportanceSampleBias;            /* 0.3   */
+    float    SpatialReconstructionRadius;        /* 4.0   */
+    float    TemporalRadianceStabilityFactor;    /* 1.0   */
+    float    TemporalVarianceStabilityFactor;    /* 0.9   */
+    float    BilateralCleanupSpatialSigmaFactor; /* 0.9   */
+    float    AlphaInterpolation;                 /* 1.0   */
+} dfx_ssr_attribs;
+
+/* == HLSL::BloomAttribs, …/BloomStructures.fxh:12-34 (32 bytes) */
+typedef struct dfx_bloom_attribs
+{
+    float Intensity;          /* 0.15  */
+    float Threshold;          /* 1.0   */
+    float SoftTreshold;       /* 0.125 */
+    float Radius;             /* 0.75  */
+    float AlphaInterpolation; /* 1.0   */
+    float Padding0, Padding1, Padding2;
+} dfx_bloom_attribs;
+
+/* == HLSL::TemporalAntiAliasingAttribs, …/TemporalAntiAliasingStructures.fxh:35-46 (16 bytes) */
+typedef struct dfx_taa_attribs
+{
+    float   TemporalStabilityFactor; /* 0.9375 */
+    int32_t ResetAccumulation;       /* FALSE  */
+    int32_t SkipRejection;           /* FALSE  */
+    float   Padding0;
+} dfx_taa_attribs;
+
+/* == HLSL::ToneMappingAttribs (+AgXAttribs), …/ToneMappingStructures.fxh:24-52 (48 bytes) */
+typedef struct dfx_tonemap_attribs
+{
+    int32_t  iToneMappingMode;     /* DFX_TONE_MAPPING_MODE_UNCHARTED2 */
+    int32_t  bAutoExposure;        /* TRUE  */
+    float    fMiddleGray;          /* 0.18  */
+    int32_t  bLightAdaptation;     /* TRUE  */
+    float    fWhitePoint;          /* 3.0   */
+    float    fLuminanceSaturation; /* 1.0   */
+    uint32_t Padding0, Padding1;
+    float    AgXSaturation, AgXSlope, AgXPower, AgXOffset; /* 1,1,1,0 */
+} dfx_tonemap_attribs;
+#define DFX_TONE_MAPPING_MODE_NONE          0
+#define DFX_TONE_MAPPING_MODE_EXP           1
+#define DFX_TONE_MAPPING_MODE_REINHARD      2
+#define DFX_TONE_MAPPING_MODE_REINHARD_MOD  3
+#define DFX_TONE_MAPPING_MODE_UNCHARTED2    4
+#define DFX_TONE_MAPPING_MODE_FILMIC_ALU    5
+#define DFX_TONE_MAPPING_MODE_LOGARITHMIC   6
+#define DFX_TONE_MAPPING_MODE_ADAPTIVE_LOG  7
+#define DFX_TONE_MAPPING_MODE_AGX           8
+#define DFX_TONE_MAPPING_MODE_AGX_CUSTOM    9
+#define DFX_TONE_MAPPING_MODE_PBR_NEUTRAL  10
+#define DFX_TONE_MAPPING_MODE_COMMERCE     11
+
+/* Default-initialisers (the reference's DEFAULT_VALUE()s). */
+DFX_API void dfx_ssao_attribs_default(dfx_ssao_attribs* a);
+DFX_API void dfx_ssr_attribs_default(dfx_ssr_attribs* a);
+DFX_API void dfx_bloom_attribs_default(dfx_bloom_attribs* a);
+DFX_API void dfx_taa_attribs_default(dfx_taa_attribs* a);
+DFX_API void dfx_tonemap_attribs_default(dfx_tonemap_attribs* a);
+
+/* == PostFXContext::FrameDesc, PostProcess/Common/interface/PostFXContext.hpp:68-84 */
+typedef struct dfx_frame_desc
+{
+    uint32_t Index;
+    uint32_t Width;
+    uint32_t Height;
+    uint32_t OutputWidth;
+    uint32_t OutputHeight;
+} dfx_frame_desc;
+
+/* feature flags: numeric values of the reference enums */
+#define DFX_POSTFX_FEATURE_FLAG_NONE                 0u
+#define DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH       (1u << 0) /* unsupported in this build */
+#define DFX_POSTFX_FEATURE_FLAG_HALF_PRECISION_DEPTH (1u << 1) /* unsupported */
+#define DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING   (1u << 2) /* unsupported */
+#define DFX_SSAO_FEATURE_FLAG_NONE                   0u
+#define DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH   (1u << 0) /* unsupported */
+#define DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION        (1u << 1) /* unsupported */
+#define DFX_SSR_FEATURE_FLAG_NONE                    0u
+#define DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME          (1u << 0)
+#define DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION         (1u << 1) /* unsupported */
+#define DFX_BLOOM_FEATURE_FLAG_NONE                  0u
+#define DFX_TAA_FEATURE_FLAG_NONE                    0u
+#define DFX_TAA_FEATURE_FLAG_GAUSSIAN_WEIGHTING      (1u << 0)
+#define DFX_TAA_FEATURE_FLAG_BICUBIC_FILTER          (1u << 1)
+#define DFX_TAA_FEATURE_FLAG_YCOCG_COLOR_SPACE       (1u << 2)
+
+/* ============================================================================================================ */
+/* 1. pass level                                                                                                */
+/* ============================================================================================================ */
+
+/* P0 ComputeBlueNoiseTexture (PostFXContext.cpp:567-609; Shaders/Common/private/ComputeBlueNoiseTexture.fx:81-89).
+ * tables: device pointer to the 131,328-byte blob (Sobol_256d[256] ++ ScramblingTile[128*128*8]).
+ * xy, zw: 128x128 RG32F.                                                                                       */
+DFX_API dfx_status dfx_pass_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index,
+                                       const dfx_plane* xy, const dfx_plane* zw);
+
+/* P1+P2+P3 fused: ComputeReprojectedDepth (ComputeReprojectedDepth.fx:18-30), ComputeClosestMotion
+ * (ComputeClosestMotion.fx:24-55), ComputePreviousDepth (PostFXContext.cpp:657-676).
+ * cameras: device pointer to dfx_camera_attribs[2] = {curr, prev}.                                             */
+DFX_API dfx_status dfx_pass_postfx_prepare(void* stream, const dfx_camera_attribs* cameras_dev,
+                                           const dfx_plane* curr_depth, const dfx_plane* prev_depth_in,
+                                           const dfx_plane* motion,
+                                           const dfx_plane* reprojected_depth, const dfx_plane* closest_motion,
+                                           const dfx_plane* previous_depth, dfx_rows rows);
+
+/* A1+A2 ComputePrefilteredDepth (ScreenSpaceAmbientOcclusion.cpp:843-957; SSAO_ComputePrefilteredDepthBuffer.fx:79-122).
+ * pyr->level[0] aliases the input depth (the reference's CopyTextureDepth into mip 0 is elided); levels 1..4 written. */
+DFX_API dfx_status dfx_pass_ssao_prefilter_depth(void* stream, const dfx_camera_attribs* cameras_dev,
+                                                 const dfx_ssao_attribs* attribs, const dfx_pyramid* pyr, dfx_rows rows);
+
+/* A3 ComputeAmbientOcclusion (…cpp:961-990; SSAO_ComputeAmbientOcclusion.fx:132-231). Includes the clear to 1.0. */
+DFX_API dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_camera_attribs* cameras_dev,
+                                                   const dfx_ssao_attribs* attribs, const dfx_pyramid* prefiltered_depth,
+                                                   const dfx_plane* normal, const dfx_plane* blue_noise_zw,
+                                                   const dfx_plane* occlusion, dfx_rows rows);
+
+/* A5 ComputeTemporalAccumulation (…cpp:1032-1073; SSAO_ComputeTemporalAccumulation.fx:151-182). Includes the
+ * clears of both targets to 1.0 (background pixels keep 1.0).                                                  */
+DFX_API dfx_status dfx_pass_ssao_temporal(void* stream, const dfx_camera_attribs* cameras_dev,
+                                          const dfx_ssao_attribs* attribs,
+                                          const dfx_plane* curr_occlusion, const dfx_plane* prev_occlusion,
+                                          const dfx_plane* prev_history_length, const dfx_plane* reprojected_depth,
+                                          const dfx_plane* previous_depth, const dfx_plane* closest_motion,
+                                          const dfx_plane* out_occlusion, const dfx_plane* out_history_length,
+                                          dfx_rows rows);
+
+/* A6 ComputeConvolutedDepthHistory (…cpp:1075-1255; SSAO_ComputeConvolutedDepthHistory.fx:93-109).
+ * level[0] of both pyramids are inputs (accumulated AO, depth); levels 1..4 written.                           */
+DFX_API dfx_status dfx_pass_ssao_convolute(void* stream, const dfx_pyramid* occlusion_pyr, const dfx_pyramid* depth_pyr,
+                                           dfx_rows rows);
+
+/* A7 ComputeResampledHistory (…cpp:1257-1286; SSAO_ComputeResampledHistory.fx:56-115). */
+DFX_API dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attribs* cameras_dev,
+                                          const dfx_pyramid* occlusion_pyr, const dfx_pyramid* depth_pyr,
+                                          const dfx_plane* history_length, const dfx_plane* normal,
+                                          const dfx_plane* out_occlusion, dfx_rows rows);
+
+/* A8 ComputeSpatialReconstruction (…cpp:1288-1329; SSAO_ComputeSpatialReconstruction.fx:49-100). The reference's
+ * CopyTexture(resolved -> history[curr]) is elided: `out_occlusion` IS history[curr].                          */
+DFX_API dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attribs* cameras_dev,
+                                         const dfx_ssao_attribs* attribs,
+                                         const dfx_plane* occlusion, const dfx_plane* history_length,
+                                         const dfx_plane* depth, const dfx_plane* normal,
+                                         const dfx_plane* out_occlusion, dfx_rows rows);
+
+/* S1 ComputeHierarchicalDepthBuffer (ScreenSpaceReflection.cpp:777-902; SSR_ComputeHierarchicalDepthBuffer.fx:30-73).
+ * level[0] aliases the input depth; levels 1..6 written.                                                       */
+DFX_API dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx_rows rows);
+
+/* S2 ComputeStencilMaskAndExtractRoughness (…cpp:904-932; SSR_ComputeStencilMaskAndExtractRoughness.fx:13-40).
+ * mask (R8U): 1 where the pixel is a reflection sample, 0 elsewhere; roughness written only where mask==1.     */
+DFX_API dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_attribs* attribs,
+                                               const dfx_plane* material, const dfx_plane* depth,
+                                               const dfx_plane* roughness, const dfx_plane* mask, dfx_rows rows);
+
+/* S4 ComputeIntersection (…cpp:963-999; SSR_ComputeIntersection.fx:281-325). Includes both clears to 0.
+ * motion may be NULL unless DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME is set in `flags`.                             */
+DFX_API dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attribs* cameras_dev,
+                                          const dfx_ssr_attribs* attribs, uint32_t flags,
+                                          const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness,
+                                          const dfx_plane* mask, const dfx_plane* blue_noise_xy,
+                                          const dfx_pyramid* hiz, const dfx_plane* motion,
+                                          const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows);
+
+/* S5 ComputeSpatialReconstruction (…cpp:1001-1031; SSR_ComputeSpatialReconstruction.fx:114-172). Masked writes. */
+DFX_API dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attribs* cameras_dev,
+                                        const dfx_ssr_attribs* attribs,
+                                        const dfx_plane* roughness, const dfx_plane* mask, const dfx_plane* normal,
+                                        const dfx_plane* depth, const dfx_plane* raydir_pdf, const dfx_plane* radiance,
+                                        const dfx_plane* out_resolved_radiance, const dfx_plane* out_resolved_variance,
+                                        const dfx_plane* out_resolved_depth, dfx_rows rows);
+
+/* S6 ComputeTemporalAccumulation (…cpp:1033-1069; SSR_ComputeTemporalAccumulation.fx:224-263). Masked writes. */
+DFX_API dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attribs* cameras_dev,
+                                         const dfx_ssr_attribs* attribs, const dfx_plane* mask,
+                                         const dfx_plane* motion, const dfx_plane* hit_depth,
+                                         const dfx_plane* reprojected_depth, const dfx_plane* curr_radiance,
+                                         const dfx_plane* curr_variance, const dfx_plane* previous_depth,
+                                         const dfx_plane* prev_radiance, const dfx_plane* prev_variance,
+                                         const dfx_plane* out_radiance, const dfx_plane* out_variance, dfx_rows rows);
+
+/* S7 ComputeBilateralCleanup (…cpp:1071-1104; SSR_ComputeBilateralCleanup.fx:49-97). Includes the clear to 0. */
+DFX_API dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attribs* cameras_dev,
+                                          const dfx_ssr_attribs* attribs, const dfx_plane* mask,
+                                          const dfx_plane* depth, const dfx_plane* normal, const dfx_plane* roughness,
+                                          const dfx_plane* radiance, const dfx_plane* variance,
+                                          const dfx_plane* out, dfx_rows rows);
+
+/* B1 ComputePrefilteredTexture (Bloom.cpp:288-311; Bloom_ComputePrefilteredTexture.fx:37-83). */
+DFX_API dfx_status dfx_pass_bloom_prefilter(void* stream, const dfx_bloom_attribs* attribs,
+                                            const dfx_plane* color, const dfx_plane* out_level0, dfx_rows rows);
+/* B2 ComputeDownsampledTexture (Bloom.cpp:313-337; Bloom_ComputeDownsampledTexture.fx:11-41). */
+DFX_API dfx_status dfx_pass_bloom_downsample(void* stream, const dfx_plane* in, const dfx_plane* out, dfx_rows rows);
+/* B3 ComputeUpsampledTexture, uInstID==0 (Bloom.cpp:339-375; Bloom_ComputeUpsampledTexture.fx:20-54). */
+DFX_API dfx_status dfx_pass_bloom_upsample(void* stream, const dfx_plane* same_level_down, const dfx_plane* coarser,
+                                           const dfx_plane* out, dfx_rows rows);
+/* B4 final composite, uInstID!=0 (Bloom.cpp:373-393; Bloom_ComputeUpsampledTexture.fx:45-48). */
+DFX_API dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_attribs* attribs,
+                                            const dfx_plane* color, const dfx_plane* up0, const dfx_plane* out, dfx_rows rows);
+
+/* T1 ComputeTemporalAccumulation (TemporalAntiAliasing.cpp:260-289; TAA_ComputeTemporalAccumulation.fx:229-261). */
+DFX_API dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs,
+                                uint32_t flags, const dfx_plane* curr_color, const dfx_plane* prev_accum,
+                                const dfx_plane* closest_motion, const dfx_plane* reprojected_depth,
+                                const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows);
+
+/* Compose step between SSAO and TAA, reduced form (Hydrogent/shaders/HnPostProcess.psh:145-185):
+ *   rgb += ssr.rgb * ssr.a * ssr_scale;  rgb *= lerp(1, ao, ssao_scale);  alpha passes through.
+ * ssr / ao may be NULL (scale treated as 0).                                                                   */
+DFX_API dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao,
+                                    float ssr_scale, float ssao_scale, const dfx_plane* out, dfx_rows rows);
+
+/* M1+M2 ToneMap() (ToneMapping.fxh:87-226) + optional LinearToSRGB (SRGBUtilities.fxh:27-33), as used by
+ * Hydrogent/shaders/HnCopyFrame.psh:32-62. ave_log_lum is the already exposure-scaled fAveLogLum argument.     */
+DFX_API dfx_status dfx_pass_tonemap(void* stream, const dfx_tonemap_attribs* attribs, float ave_log_lum,
+                                    int32_t convert_to_srgb, const dfx_plane* color, const dfx_plane* out, dfx_rows rows);
+
+/* Host-side pieces that the reference computes on the CPU. */
+/* TemporalAntiAliasing::GetJitterOffset (TemporalAntiAliasing.cpp:63-78, Halton(2,3) x16). */
+DFX_API void dfx_taa_jitter_offset(uint32_t frame_index, uint32_t width, uint32_t height, float out_jitter[2]);
+/* Bloom::ComputeMipCount (Bloom.cpp:152-156) applied to the half-resolution level-0 size. */
+DFX_API int32_t dfx_bloom_mip_count(uint32_t width, uint32_t height, float radius);
+
+/* ============================================================================================================ */
+/* 2. effect level                                                                                              */
+/* ============================================================================================================ */
+
+typedef struct dfx_postfx dfx_postfx;
+typedef struct dfx_ssao   dfx_ssao;
+typedef struct dfx_ssr    dfx_ssr;
+typedef struct dfx_bloom  dfx_bloom;
+typedef struct dfx_taa    dfx_taa;
+
+/* plane ids for dfx_*_get_plane */
+enum
+{
+    DFX_POSTFX_PLANE_BLUE_NOISE_XY     = 0,
+    DFX_POSTFX_PLANE_BLUE_NOISE_ZW     = 1,
+    DFX_POSTFX_PLANE_REPROJECTED_DEPTH = 2,
+    DFX_POSTFX_PLANE_PREVIOUS_DEPTH    = 3,
+    DFX_POSTFX_PLANE_CLOSEST_MOTION    = 4
+};
+enum
+{
+    DFX_SSAO_PLANE_OUTPUT            = 0,  /* == GetAmbientOcclusionSRV()                       */
+    DFX_SSAO_PLANE_OCCLUSION         = 1,  /* raw AO (A3)                                       */
+    DFX_SSAO_PLANE_ACCUMULATED       = 2,  /* A5 output == convoluted-AO mip 0                  */
+    DFX_SSAO_PLANE_HISTORY_LENGTH    = 3,  /* A5 history length of the current frame            */
+    DFX_SSAO_PLANE_RESAMPLED         = 4,  /* A7                                                */
+    DFX_SSAO_PLANE_PREFILTERED_MIP0  = 10, /* +i : prefiltered depth mip i (0..4)               */
+    DFX_SSAO_PLANE_CONV_AO_MIP0      = 20, /* +i : convoluted AO mip i (0..4)                   */
+    DFX_SSAO_PLANE_CONV_DEPTH_MIP0   = 30  /* +i : convoluted depth mip i (0..4)                */
+};
+enum
+{
+    DFX_SSR_PLANE_OUTPUT            = 0,  /* == GetSSRRadianceSRV()                             */
+    DFX_SSR_PLANE_ROUGHNESS         = 1,
+    DFX_SSR_PLANE_MASK              = 2,
+    DFX_SSR_PLANE_RADIANCE          = 3,
+    DFX_SSR_PLANE_RAYDIR_PDF        = 4,
+    DFX_SSR_PLANE_RESOLVED_RADIANCE = 5,
+    DFX_SSR_PLANE_RESOLVED_VARIANCE = 6,
+    DFX_SSR_PLANE_RESOLVED_DEPTH    = 7,
+    DFX_SSR_PLANE_RADIANCE_HISTORY  = 8,  /* current frame's slot                               */
+    DFX_SSR_PLANE_VARIANCE_HISTORY  = 9,
+    DFX_SSR_PLANE_HIZ_MIP0          = 10  /* +i : Hi-Z mip i (0..6)                             */
+};
+enum
+{
+    DFX_BLOOM_PLANE_OUTPUT    = 0,   /* == GetBloomTextureSRV()                                 */
+    DFX_BLOOM_PLANE_DOWN0     = 10,  /* +i : downsampled level i                                */
+    DFX_BLOOM_PLANE_UP0       = 30   /* +i : upsampled level i                                  */
+};
+enum
+{
+    DFX_TAA_PLANE_ACCUMULATED_CURR = 0, /* == GetAccumulatedFrameSRV(false)                     */
+    DFX_TAA_PLANE_ACCUMULATED_PREV = 1  /* == GetAccumulatedFrameSRV(true)                      */
+};
+
+/* ---- PostFXContext (PostProcess/Common/interface/PostFXContext.hpp:51-172) ---- */
+typedef struct dfx_postfx_render_attribs
+{
+    void*                     stream;          /* stands in for pDeviceContext                   */
+    const dfx_plane*          curr_depth;      /* pCurrDepthBufferSRV  R32F                      */
+    const dfx_plane*          prev_depth;      /* pPrevDepthBufferSRV  R32F                      */
+    const dfx_plane*          motion_vectors;  /* pMotionVectorsSRV    RG32F                     */
+    const dfx_camera_attribs* curr_camera;     /* host pointers, uploaded like PostFXContext.cpp:302-319 */
+    const dfx_camera_attribs* prev_camera;
+} dfx_postfx_render_attribs;
+
+DFX_API dfx_status dfx_postfx_create(dfx_postfx** out);
+DFX_API void       dfx_postfx_destroy(dfx_postfx* ctx);
+DFX_API dfx_status dfx_postfx_prepare(dfx_postfx* ctx, const dfx_frame_desc* desc, uint32_t feature_flags);
+DFX_API dfx_status dfx_postfx_execute(dfx_postfx* ctx, const dfx_postfx_render_attribs* attribs);
+DFX_API dfx_status dfx_postfx_get_plane(const dfx_postfx* ctx, int32_t id, dfx_plane* out);
+DFX_API dfx_status dfx_postfx_get_frame_desc(const dfx_postfx* ctx, dfx_frame_desc* out);
+DFX_API const dfx_camera_attribs* dfx_postfx_get_camera_attribs_dev(const dfx_postfx* ctx); /* GetCameraAttribsCB */
+
+/* ---- ScreenSpaceAmbientOcclusion (…/ScreenSpaceAmbientOcclusion.hpp:59-136) ---- */
+typedef struct dfx_ssao_render_attribs
+{
+    void*                   stream;
+    dfx_postfx*             postfx;  /* pPostFXContext   */
+    const dfx_plane*        depth;   /* pDepthBufferSRV  R32F    */
+    const dfx_plane*        normal;  /* pNormalBufferSRV RGBA32F (xyz world-space normal) */
+    const dfx_ssao_attribs* attribs; /* pSSAOAttribs     */
+} dfx_ssao_render_attribs;
+
+DFX_API dfx_status dfx_ssao_create(dfx_ssao** out);
+DFX_API void       dfx_ssao_destroy(dfx_ssao* fx);
+DFX_API dfx_status dfx_ssao_prepare(dfx_ssao* fx, dfx_postfx* postfx, uint32_t feature_flags);
+/* The reference fades the effect in with wall-clock time (AlphaInterpolation, …cpp:793-795). `alpha < 0`
+ * restores that behaviour; parity runs pin it (default after create: pinned to 1.0).                            */
+DFX_API dfx_status dfx_ssao_set_alpha_interpolation(dfx_ssao* fx, float alpha);
+DFX_API dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attribs* attribs);
+DFX_API dfx_status dfx_ssao_get_plane(const dfx_ssao* fx, int32_t id, dfx_plane* out);
+
+/* ---- ScreenSpaceReflection (…/ScreenSpaceReflection.hpp:64-139) ---- */
+typedef struct dfx_ssr_render_attribs
+{
+    void*                  stream;
+    dfx_postfx*            postfx;
+    const dfx_plane*       color;     /* pColorBufferSRV    RGBA32F */
+    const dfx_plane*       depth;     /* pDepthBufferSRV    R32F    */
+    const dfx_plane*       normal;    /* pNormalBufferSRV   RGBA32F */
+    const dfx_plane*       material;  /* pMaterialBufferSRV RGBA32F */
+    const dfx_plane*       motion;    /* pMotionVectorsSRV  RG32F   */
+    const dfx_ssr_attribs* attribs;   /* pSSRAttribs        */
+} dfx_ssr_render_attribs;
+
+DFX_API dfx_status dfx_ssr_create(dfx_ssr** out);
+DFX_API void       dfx_ssr_destroy(dfx_ssr* fx);
+DFX_API dfx_status dfx_ssr_prepare(dfx_ssr* fx, dfx_postfx* postfx, uint32_t feature_flags);
+DFX_API dfx_status dfx_ssr_set_alpha_interpolation(dfx_ssr* fx, float alpha);
+DFX_API dfx_status dfx_ssr_execute(dfx_ssr* fx, const dfx_ssr_render_attribs* attribs);
+DFX_API dfx_status dfx_ssr_get_plane(const dfx_ssr* fx, int32_t id, dfx_plane* out);
+
+/* ---- Bloom (…/Bloom.hpp:60-114) ---- */
+typedef struct dfx_bloom_render_attribs
+{
+    void*                    stream;
+    dfx_postfx*              postfx;
+    const dfx_plane*         color;   /* pColorBufferSRV RGBA32F */
+    const dfx_bloom_attribs* attribs; /* pBloomAttribs   */
+} dfx_bloom_render_attribs;
+
+DFX_API dfx_status dfx_bloom_create(dfx_bloom** out);
+DFX_API void       dfx_bloom_destroy(dfx_bloom* fx);
+DFX_API dfx_status dfx_bloom_prepare(dfx_bloom* fx, dfx_postfx* postfx, uint32_t feature_flags);
+DFX_API dfx_status dfx_bloom_set_alpha_interpolation(dfx_bloom* fx, float alpha);
+DFX_API dfx_status dfx_bloom_execute(dfx_bloom* fx, const dfx_bloom_render_attribs* attribs);
+DFX_API dfx_status dfx_bloom_get_plane(const dfx_bloom* fx, int32_t id, dfx_plane* out);
+
+/* ---- TemporalAntiAliasing (…/TemporalAntiAliasing.hpp:62-156) ---- */
+typedef struct dfx_taa_render_attribs
+{
+    void*                  stream;
+    dfx_postfx*            postfx;
+    const dfx_plane*       color;   /* pColorBufferSRV RGBA32F */
+    const dfx_taa_attribs* attribs; /* pTAAAttribs     */
+    uint32_t               accumulation_buffer_idx;
+} dfx_taa_render_attribs;
+
+DFX_API dfx_status dfx_taa_create(dfx_taa** out);
+DFX_API void       dfx_taa_destroy(dfx_taa* fx);
+DFX_API dfx_status dfx_taa_prepare(dfx_taa* fx, dfx_postfx* postfx, uint32_t feature_flags, uint32_t accumulation_buffer_idx);
+DFX_API dfx_status dfx_taa_execute(dfx_taa* fx, const dfx_taa_render_attribs* attribs);
+DFX_API dfx_status dfx_taa_get_plane(const dfx_taa* fx, int32_t id, uint32_t accumulation_buffer_idx, dfx_plane* out);
+DFX_API dfx_status dfx_taa_get_jitter_offset(const dfx_taa* fx, uint32_t accumulation_buffer_idx, float out_jitter[2]);
+
+/* ============================================================================================================ */
+/* plane helpers (device memory owned by the library; used by the C++ shim and the tests)                       */
+DFX_API dfx_status dfx_plane_alloc(int32_t width, int32_t height, int32_t format, dfx_plane* out);
+DFX_API void       dfx_plane_free(dfx_plane* p);
+DFX_API dfx_status dfx_plane_upload(void* stream, const dfx_plane* dst, const void* host_src, size_t host_pitch_bytes);
+DFX_API dfx_status dfx_plane_download(void* stream, const dfx_plane* src, void* host_dst, size_t host_pitch_bytes);
+DFX_API dfx_status dfx_plane_fill(void* stream, const dfx_plane* dst, const float value[4]);
+DFX_API dfx_status dfx_stream_synchronize(void* stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* DFX_B200_H */

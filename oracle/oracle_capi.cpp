@@ -1,0 +1,359 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// C API (ctypes) over the oracle passes: a context of named fp32 planes + one "run" entry per reference pass and a
+// whole-frame driver that sequences them exactly as the reference's host code does
+// (Hydrogent/src/Tasks/HnPostProcessTask.cpp:743-947; per-effect Execute() methods).
+#include "oracle.h"
+#include <map>
+#include <string>
+#include <chrono>
+#include <cstdio>
+
+using namespace orc;
+
+namespace
+{
+struct Ctx
+{
+    int W = 0, H = 0, threads = 1;
+    std::map<std::string, TexF>          f1;
+    std::map<std::string, TexF2>         f2;
+    std::map<std::string, TexF4>         f4;
+    std::map<std::string, Tex<uint8_t>>  u8;
+    std::map<std::string, MipTex<float>> pyr;
+
+    std::vector<uint8_t> tables;
+    Camera               curr, prev;
+    dfx_ssao_attribs     ssao{};
+    dfx_ssr_attribs      ssr{};
+    dfx_bloom_attribs    bloom{};
+    dfx_taa_attribs      taa{};
+    dfx_tonemap_attribs  tm{};
+    float                ave_log_lum = 0.3f;
+    int                  to_srgb     = 1;
+    uint                 ssr_flags = 0, taa_flags = DFX_TAA_FEATURE_FLAG_BICUBIC_FILTER;
+    uint                 frame_index = 0;
+    float                ssr_scale = 1.0f, ssao_scale = 1.0f;
+    // reset logic of the effect classes (m_LastFrameIdx), ScreenSpaceAmbientOcclusion.cpp:797-800, TemporalAntiAliasing.cpp:125-128
+    uint   ssao_last = ~0u, taa_last = ~0u;
+    double last_ms = 0.0;
+    std::string err;
+};
+
+std::string slot(const char* base, uint idx) { return std::string(base) + char('0' + (idx & 1u)); }
+
+void ensure_persistent(Ctx& c)
+{
+    const int W = c.W, H = c.H;
+    auto mk1 = [&](const std::string& n, float v) { if (!c.f1.count(n)) c.f1[n] = TexF(W, H, v); };
+    auto mk4 = [&](const std::string& n) { if (!c.f4.count(n)) c.f4[n] = TexF4(W, H, float4()); };
+    // SSAO history: cleared to 1.0 at creation (…SSAO.cpp:304-305, :320-321)
+    mk1("ssao_hist0", 1.0f), mk1("ssao_hist1", 1.0f), mk1("ssao_histlen0", 1.0f), mk1("ssao_histlen1", 1.0f);
+    // SSR: history cleared to 0 at creation (ScreenSpaceReflection.cpp:263-264, :279-280); other targets start as zero memory
+    mk4("ssr_radhist0"), mk4("ssr_radhist1"), mk1("ssr_varhist0", 0.0f), mk1("ssr_varhist1", 0.0f);
+    mk1("ssr_roughness", 0.0f), mk4("ssr_resolved_rad"), mk1("ssr_resolved_var", 0.0f), mk1("ssr_resolved_depth", 0.0f);
+    // TAA accumulation: cleared to 0 at creation (TemporalAntiAliasing.cpp:101-119)
+    mk4("taa_accum0"), mk4("taa_accum1");
+}
+
+int run_pass(Ctx& c, const std::string& p)
+{
+    const int  T   = c.threads;
+    const uint cur = c.frame_index & 1u, prv = (c.frame_index + 1u) & 1u;
+    ensure_persistent(c);
+    if (p == "blue_noise")
+    {
+        if (c.tables.size() != 256 + 128 * 128 * 8) return c.err = "blue-noise tables not set", 1;
+        postfx_blue_noise(c.tables.data(), c.frame_index, c.f2["bn_xy"], c.f2["bn_zw"]);
+    }
+    else if (p == "reprojected_depth") postfx_reprojected_depth(c.curr, c.prev, c.f1["depth"], c.f1["reproj_depth"], T);
+    else if (p == "closest_motion") postfx_closest_motion(c.f1["depth"], c.f2["motion"], c.f2["closest_motion"], T);
+    else if (p == "previous_depth") c.f1["prev_depth"] = c.f1["prev_depth_in"];
+    else if (p == "ssao_prefilter") ssao_prefilter_depth(c.curr, c.ssao, c.f1["depth"], c.pyr["ssao_pre"], T);
+    else if (p == "ssao_ao") ssao_ambient_occlusion(c.curr, c.ssao, c.pyr["ssao_pre"], c.f4["normal"], c.f2["bn_zw"], c.f1["ssao_occ"], T);
+    else if (p == "ssao_temporal")
+        ssao_temporal(c.curr, c.prev, c.ssao, c.f1["ssao_occ"], c.f1[slot("ssao_hist", prv)], c.f1[slot("ssao_histlen", prv)], c.f1["reproj_depth"],
+                      c.f1["prev_depth"], c.f2["closest_motion"], c.f1["ssao_acc"], c.f1[slot("ssao_histlen", cur)], T);
+    else if (p == "ssao_convolute") ssao_convolute(c.f1["ssao_acc"], c.f1["depth"], c.pyr["ssao_conv_occ"], c.pyr["ssao_conv_depth"], T);
+    else if (p == "ssao_resample")
+        ssao_resample(c.curr, c.pyr["ssao_conv_occ"], c.pyr["ssao_conv_depth"], c.f1[slot("ssao_histlen", cur)], c.f4["normal"], c.f1["ssao_resampled"], T);
+    else if (p == "ssao_spatial")
+    {
+        // resolved output, then CopyTexture(resolved -> history[curr]) (…SSAO.cpp:1319-1328)
+        ssao_spatial(c.curr, c.ssao, c.f1["ssao_resampled"], c.f1[slot("ssao_histlen", cur)], c.f1["depth"], c.f4["normal"], c.f1["ssao_out"], T);
+        c.f1[slot("ssao_hist", cur)] = c.f1["ssao_out"];
+    }
+    else if (p == "ssr_hiz") ssr_hiz(c.f1["depth"], c.pyr["ssr_hiz"], T);
+    else if (p == "ssr_mask") ssr_mask_roughness(c.ssr, c.f4["material"], c.f1["depth"], c.f1["ssr_roughness"], c.u8["ssr_mask"], T);
+    else if (p == "ssr_intersect")
+        ssr_intersect(c.curr, c.ssr, c.ssr_flags, c.f4["color"], c.f4["normal"], c.f1["ssr_roughness"], c.u8["ssr_mask"], c.f2["bn_xy"], c.pyr["ssr_hiz"],
+                      &c.f2["motion"], c.f4["ssr_radiance"], c.f4["ssr_raydir"], T);
+    else if (p == "ssr_spatial")
+        ssr_spatial(c.curr, c.ssr, c.f1["ssr_roughness"], c.u8["ssr_mask"], c.f4["normal"], c.f1["depth"], c.f4["ssr_raydir"], c.f4["ssr_radiance"],
+                    c.f4["ssr_resolved_rad"], c.f1["ssr_resolved_var"], c.f1["ssr_resolved_depth"], T);
+    else if (p == "ssr_temporal")
+        ssr_temporal(c.curr, c.prev, c.ssr, c.u8["ssr_mask"], c.f2["motion"], c.f1["ssr_resolved_depth"], c.f1["reproj_depth"], c.f4["ssr_resolved_rad"],
+                     c.f1["ssr_resolved_var"], c.f1["prev_depth"], c.f4[slot("ssr_radhist", prv)], c.f1[slot("ssr_varhist", prv)],
+                     c.f4[slot("ssr_radhist", cur)], c.f1[slot("ssr_varhist", cur)], T);
+    else if (p == "ssr_bilateral")
+        ssr_bilateral(c.curr, c.ssr, c.u8["ssr_mask"], c.f1["depth"], c.f4["normal"], c.f1["ssr_roughness"], c.f4[slot("ssr_radhist", cur)],
+                      c.f1[slot("ssr_varhist", cur)], c.f4["ssr_out"], T);
+    else if (p == "compose") compose(c.f4["color"], &c.f4["ssr_out"], &c.f1["ssao_out"], c.ssr_scale, c.ssao_scale, c.f4["composed"], T);
+    else if (p == "taa")
+        taa_accumulate(c.curr, c.prev, c.taa, c.taa_flags, c.f4["taa_in"], c.f4[slot("taa_accum", prv)], c.f2["closest_motion"], c.f1["reproj_depth"],
+                       c.f1["prev_depth"], c.f4[slot("taa_accum", cur)], T);
+    else if (p == "bloom")
+    {
+        // Bloom::Execute (Bloom.cpp:407-436)
+        const TexF4& in   = c.f4["bloom_in"];
+        const int    mips = bloom_mip_count(std::max(in.w / 2, 1), std::max(in.h / 2, 1), c.bloom.Radius);
+        auto dn = [&](int i) -> TexF4& { return c.f4["bloom_down" + std::to_string(i)]; };
+        auto up = [&](int i) -> TexF4& { return c.f4["bloom_up" + std::to_string(i)]; };
+        bloom_prefilter(c.bloom, in, dn(0), T);
+        for (int i = 1; i < mips; ++i) bloom_downsample(dn(i - 1), dn(i), T);
+        const int top = mips - 1;
+        for (int i = top; i > 0; --i) bloom_upsample(dn(i - 1), i != top ? up(i) : dn(i), up(i - 1), T);
+        bloom_composite(c.bloom, in, up(0), c.f4["bloom_out"], T);
+    }
+    else if (p == "tonemap") tonemap_pass(c.tm, c.ave_log_lum, c.to_srgb != 0, c.f4["tonemap_in"], c.f4["ldr"], T);
+    else
+        return c.err = "unknown pass " + p, 1;
+    return 0;
+}
+} // namespace
+
+namespace orc { float oracle_fast_acos(float v); }
+
+extern "C"
+{
+#define ORC_API __attribute__((visibility("default")))
+
+ORC_API void* orc_create(int w, int h, int threads)
+{
+    Ctx* c     = new Ctx;
+    c->W       = w;
+    c->H       = h;
+    c->threads = threads < 1 ? 1 : threads;
+    dfx_ssao_attribs  s{1.0f, 0.615f, 1.457f, 3.3f, 0.9f, 4.0f, 0, 1.0f, 0.5f, 0u, 0.0f, 0.0f};
+    dfx_ssr_attribs   r{0.025f, 0.2f, 0u, 1, 0u, 128u, 0.3f, 4.0f, 1.0f, 0.9f, 0.9f, 1.0f};
+    dfx_bloom_attribs b{0.15f, 1.0f, 0.125f, 0.75f, 1.0f, 0, 0, 0};
+    dfx_taa_attribs   t{0.9375f, 0, 0, 0.0f};
+    dfx_tonemap_attribs m{DFX_TONE_MAPPING_MODE_UNCHARTED2, 1, 0.18f, 1, 3.0f, 1.0f, 0, 0, 1.0f, 1.0f, 1.0f, 0.0f};
+    c->ssao = s, c->ssr = r, c->bloom = b, c->taa = t, c->tm = m;
+    return c;
+}
+ORC_API void        orc_destroy(void* h) { delete static_cast<Ctx*>(h); }
+ORC_API const char* orc_last_error(void* h) { return static_cast<Ctx*>(h)->err.c_str(); }
+ORC_API double      orc_last_ms(void* h) { return static_cast<Ctx*>(h)->last_ms; }
+ORC_API void        orc_set_threads(void* h, int t) { static_cast<Ctx*>(h)->threads = t < 1 ? 1 : t; }
+
+ORC_API int orc_set_tables(void* h, const uint8_t* blob, int n)
+{
+    Ctx& c = *static_cast<Ctx*>(h);
+    if (n != 256 + 128 * 128 * 8) return c.err = "bad table size", 1;
+    c.tables.assign(blob, blob + n);
+    return 0;
+}
+
+// ch: 1, 2, 4 (fp32) ; name "x.N" addresses mip N of pyramid x ; u8 masks are exchanged as fp32 0/1 with ch == 1
+ORC_API int orc_set_plane(void* h, const char* name, const float* data, int w, int hgt, int ch)
+{
+    Ctx&        c = *static_cast<Ctx*>(h);
+    std::string n(name);
+    size_t      cnt = size_t(w) * size_t(hgt);
+    if (n == "ssr_mask")
+    {
+        Tex<uint8_t>& t = c.u8[n];
+        t.resize(w, hgt, 0);
+        for (size_t i = 0; i < cnt; ++i) t.d[i] = data[i] != 0.0f;
+        return 0;
+    }
+    auto dot_pos = n.find('.');
+    if (dot_pos != std::string::npos)
+    {
+        MipTex<float>& p  = c.pyr[n.substr(0, dot_pos)];
+        int            lv = std::stoi(n.substr(dot_pos + 1));
+        if (int(p.mip.size()) <= lv) p.mip.resize(lv + 1);
+        p.mip[lv].resize(w, hgt);
+        std::memcpy(p.mip[lv].d.data(), data, cnt * 4);
+        return 0;
+    }
+    if (ch == 1)
+    {
+        TexF& t = c.f1[n];
+        t.resize(w, hgt);
+        std::memcpy(t.d.data(), data, cnt * 4);
+    }
+    else if (ch == 2)
+    {
+        TexF2& t = c.f2[n];
+        t.resize(w, hgt);
+        std::memcpy((void*)t.d.data(), data, cnt * 8);
+    }
+    else if (ch == 4)
+    {
+        TexF4& t = c.f4[n];
+        t.resize(w, hgt);
+        std::memcpy((void*)t.d.data(), data, cnt * 16);
+    }
+    else
+        return c.err = "bad channel count", 1;
+    return 0;
+}
+
+// out == NULL: query only. Returns 0 and fills w/h/ch; 1 if the plane does not exist.
+ORC_API int orc_get_plane(void* h, const char* name, float* out, int* w, int* hgt, int* ch)
+{
+    Ctx&        c = *static_cast<Ctx*>(h);
+    std::string n(name);
+    auto        dot_pos = n.find('.');
+    if (n == "ssr_mask" && c.u8.count(n))
+    {
+        const Tex<uint8_t>& t = c.u8[n];
+        *w = t.w, *hgt = t.h, *ch = 1;
+        if (out)
+            for (size_t i = 0; i < t.d.size(); ++i) out[i] = float(t.d[i]);
+        return 0;
+    }
+    if (dot_pos != std::string::npos)
+    {
+        auto it = c.pyr.find(n.substr(0, dot_pos));
+        int  lv = std::stoi(n.substr(dot_pos + 1));
+        if (it == c.pyr.end() || lv >= it->second.levels()) return c.err = "no such plane " + n, 1;
+        const TexF& t = it->second.mip[lv];
+        *w = t.w, *hgt = t.h, *ch = 1;
+        if (out) std::memcpy(out, t.d.data(), t.d.size() * 4);
+        return 0;
+    }
+    if (c.f1.count(n))
+    {
+        const TexF& t = c.f1[n];
+        *w = t.w, *hgt = t.h, *ch = 1;
+        if (out) std::memcpy(out, t.d.data(), t.d.size() * 4);
+        return 0;
+    }
+    if (c.f2.count(n))
+    {
+        const TexF2& t = c.f2[n];
+        *w = t.w, *hgt = t.h, *ch = 2;
+        if (out) std::memcpy(out, (const void*)t.d.data(), t.d.size() * 8);
+        return 0;
+    }
+    if (c.f4.count(n))
+    {
+        const TexF4& t = c.f4[n];
+        *w = t.w, *hgt = t.h, *ch = 4;
+        if (out) std::memcpy(out, (const void*)t.d.data(), t.d.size() * 16);
+        return 0;
+    }
+    return c.err = "no such plane " + n, 1;
+}
+
+ORC_API void orc_set_cameras(void* h, const dfx_camera_attribs* curr, const dfx_camera_attribs* prev)
+{
+    Ctx& c = *static_cast<Ctx*>(h);
+    c.curr = to_camera(*curr);
+    c.prev = to_camera(*prev);
+}
+ORC_API void orc_set_frame_index(void* h, uint32_t idx) { static_cast<Ctx*>(h)->frame_index = idx; }
+ORC_API void orc_set_ssao_attribs(void* h, const dfx_ssao_attribs* a) { static_cast<Ctx*>(h)->ssao = *a; }
+ORC_API void orc_set_ssr_attribs(void* h, const dfx_ssr_attribs* a, uint32_t flags)
+{
+    static_cast<Ctx*>(h)->ssr       = *a;
+    static_cast<Ctx*>(h)->ssr_flags = flags;
+}
+ORC_API void orc_set_bloom_attribs(void* h, const dfx_bloom_attribs* a) { static_cast<Ctx*>(h)->bloom = *a; }
+ORC_API void orc_set_taa_attribs(void* h, const dfx_taa_attribs* a, uint32_t flags)
+{
+    static_cast<Ctx*>(h)->taa       = *a;
+    static_cast<Ctx*>(h)->taa_flags = flags;
+}
+ORC_API void orc_set_tonemap_attribs(void* h, const dfx_tonemap_attribs* a, float ave_log_lum, int to_srgb)
+{
+    Ctx& c        = *static_cast<Ctx*>(h);
+    c.tm          = *a;
+    c.ave_log_lum = ave_log_lum;
+    c.to_srgb     = to_srgb;
+}
+ORC_API void orc_set_compose_scales(void* h, float ssr_scale, float ssao_scale)
+{
+    static_cast<Ctx*>(h)->ssr_scale  = ssr_scale;
+    static_cast<Ctx*>(h)->ssao_scale = ssao_scale;
+}
+
+ORC_API int orc_run(void* h, const char* pass)
+{
+    Ctx& c  = *static_cast<Ctx*>(h);
+    auto t0 = std::chrono::steady_clock::now();
+    int  r  = run_pass(c, pass);
+    c.last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return r;
+}
+
+// Whole frame in the reference order (HnPostProcessTask.cpp:788-925): PostFX -> SSR -> SSAO -> compose -> TAA -> Bloom -> ToneMap(+sRGB).
+// `stages` bit mask: 1 postfx, 2 ssr, 4 ssao, 8 compose, 16 taa, 32 bloom, 64 tonemap.
+// Inputs: depth, prev_depth_in, motion, normal, color, material; cameras, frame index and attribs set beforehand.
+ORC_API int orc_frame(void* h, uint32_t stages)
+{
+    Ctx& c  = *static_cast<Ctx*>(h);
+    auto t0 = std::chrono::steady_clock::now();
+    int  r  = 0;
+    auto run = [&](const char* p) { if (!r) r = run_pass(c, p); };
+    if (stages & 1u) run("blue_noise"), run("reprojected_depth"), run("closest_motion"), run("previous_depth");
+    if (stages & 2u) run("ssr_hiz"), run("ssr_mask"), run("ssr_intersect"), run("ssr_spatial"), run("ssr_temporal"), run("ssr_bilateral");
+    if (stages & 4u)
+    {
+        // UpdateConstantBuffer reset rule (…SSAO.cpp:797-800)
+        dfx_ssao_attribs user = c.ssao;
+        bool reset = c.ssao_last == ~0u || c.frame_index != c.ssao_last + 1u || user.ResetAccumulation != 0;
+        c.ssao.ResetAccumulation = reset ? 1 : 0;
+        run("ssao_prefilter"), run("ssao_ao"), run("ssao_temporal"), run("ssao_convolute"), run("ssao_resample"), run("ssao_spatial");
+        c.ssao      = user;
+        c.ssao_last = c.frame_index;
+    }
+    if (stages & 8u) run("compose");
+    if (stages & 16u)
+    {
+        dfx_taa_attribs user = c.taa;
+        bool reset = c.taa_last == ~0u || c.frame_index != c.taa_last + 1u || user.ResetAccumulation != 0;
+        c.taa.ResetAccumulation = reset ? 1 : 0;
+        c.f4["taa_in"] = (stages & 8u) ? c.f4["composed"] : c.f4["color"];
+        run("taa");
+        c.taa      = user;
+        c.taa_last = c.frame_index;
+    }
+    if (stages & 32u)
+    {
+        c.f4["bloom_in"] = (stages & 16u) ? c.f4[slot("taa_accum", c.frame_index & 1u)] : ((stages & 8u) ? c.f4["composed"] : c.f4["color"]);
+        run("bloom");
+    }
+    if (stages & 64u)
+    {
+        c.f4["tonemap_in"] = (stages & 32u) ? c.f4["bloom_out"] : c.f4["color"];
+        run("tonemap");
+    }
+    c.last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return r;
+}
+
+// scalar helpers exposed for the KATs
+ORC_API void  orc_tone_map(const dfx_tonemap_attribs* a, float ave_log_lum, const float* rgb_in, float* rgb_out, int n)
+{
+    for (int i = 0; i < n; ++i)
+    {
+        float3 o = tone_map(float3(rgb_in[3 * i], rgb_in[3 * i + 1], rgb_in[3 * i + 2]), *a, ave_log_lum);
+        rgb_out[3 * i] = o.x, rgb_out[3 * i + 1] = o.y, rgb_out[3 * i + 2] = o.z;
+    }
+}
+ORC_API uint32_t orc_pcg_hash(uint32_t s) { return PCGHash(s); }
+ORC_API float    orc_bayer4x4(uint32_t x, uint32_t y, uint32_t f) { return Bayer4x4(x, y, f); }
+ORC_API float    orc_halton(uint32_t base, uint32_t idx) { return halton_sequence(base, idx); }
+ORC_API void     orc_taa_jitter(uint32_t frame, uint32_t w, uint32_t hgt, float* out)
+{
+    float2 j = taa_jitter_offset(frame, w, hgt);
+    out[0] = j.x, out[1] = j.y;
+}
+ORC_API int orc_bloom_mip_count(int w, int hgt, float radius) { return bloom_mip_count(w, hgt, radius); }
+ORC_API float orc_fast_acos(float v) { return orc::oracle_fast_acos(v); }
+ORC_API float orc_depth_to_camera_z(float d, const dfx_float4x4* proj) { return DepthToCameraZ(d, to_mat(*proj)); }
+ORC_API float orc_camera_z_to_depth(float z, const dfx_float4x4* proj) { return CameraZToDepth(z, to_mat(*proj)); }
+}

@@ -1,0 +1,135 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+//
+// Texture model: what the HLSL relies on from the fixed-function units:
+//   * Texture.Load out of bounds returns 0 (D3D)                                            -> Tex::load
+//   * point / bilinear SampleLevel with clamp or border(0) addressing                      -> sample_*()
+//   * SampleLevel(point-mip sampler, fractional LOD) picks the nearest mip (round half up)  -> nearest_mip()
+//   * render-target storage: fp32 planes (the north-star layout); no UNORM/half/R11G11B10 quantisation.
+// Bilinear weights are exact fp32 (hardware uses ~8 fractional bits; budgeted in the PSNR tolerance).
+#pragma once
+#include "oracle_math.h"
+#include <vector>
+#include <thread>
+#include <functional>
+
+namespace orc
+{
+
+template <class T>
+struct Tex
+{
+    int            w = 0, h = 0;
+    std::vector<T> d;
+
+    Tex() = default;
+    Tex(int w_, int h_, T fill = T()) : w(w_), h(h_), d(size_t(w_) * size_t(h_), fill) {}
+    void resize(int w_, int h_, T fill = T())
+    {
+        w = w_;
+        h = h_;
+        d.assign(size_t(w_) * size_t(h_), fill);
+    }
+    void     fill(T v) { std::fill(d.begin(), d.end(), v); }
+    T&       at(int x, int y) { return d[size_t(y) * w + x]; }
+    const T& at(int x, int y) const { return d[size_t(y) * w + x]; }
+    // Texture.Load: out-of-bounds -> 0
+    T load(int x, int y) const
+    {
+        if (x < 0 || y < 0 || x >= w || y >= h) return T();
+        return d[size_t(y) * w + x];
+    }
+    T load(int2 p) const { return load(p.x, p.y); }
+    T load_clamped(int x, int y) const { return d[size_t(clampi(y, 0, h - 1)) * w + clampi(x, 0, w - 1)]; }
+};
+
+template <class T>
+struct MipTex
+{
+    std::vector<Tex<T>> mip;
+    void create(int w, int h, int levels, T fill = T())
+    {
+        mip.clear();
+        for (int i = 0; i < levels; ++i) mip.emplace_back(std::max(w >> i, 1), std::max(h >> i, 1), fill);
+    }
+    int levels() const { return int(mip.size()); }
+};
+
+// ComputeMipLevelsCount (DiligentCore GraphicsAccessories): number of mips down to 1x1 of the larger dimension.
+inline int compute_mip_levels_count(int w, int h)
+{
+    int m = std::max(w, h), n = 0;
+    while (m > 0)
+    {
+        ++n;
+        m >>= 1;
+    }
+    return n;
+}
+
+enum class Address
+{
+    Clamp,
+    Border
+};
+
+// Point sampling at normalised uv: texel = floor(uv * size), clamp addressing.
+template <class T>
+inline T sample_point_clamp(const Tex<T>& t, float2 uv)
+{
+    int x = int(std::floor(uv.x * float(t.w)));
+    int y = int(std::floor(uv.y * float(t.h)));
+    return t.load_clamped(x, y);
+}
+
+// Bilinear sampling at normalised uv.
+template <class T>
+inline T sample_linear(const Tex<T>& t, float2 uv, Address addr)
+{
+    float px = uv.x * float(t.w) - 0.5f;
+    float py = uv.y * float(t.h) - 0.5f;
+    float fx0 = std::floor(px), fy0 = std::floor(py);
+    int   x0 = int(fx0), y0 = int(fy0);
+    float fx = px - fx0, fy = py - fy0;
+    T     t00, t10, t01, t11;
+    if (addr == Address::Clamp)
+    {
+        t00 = t.load_clamped(x0, y0);
+        t10 = t.load_clamped(x0 + 1, y0);
+        t01 = t.load_clamped(x0, y0 + 1);
+        t11 = t.load_clamped(x0 + 1, y0 + 1);
+    }
+    else
+    {
+        t00 = t.load(x0, y0);
+        t10 = t.load(x0 + 1, y0);
+        t01 = t.load(x0, y0 + 1);
+        t11 = t.load(x0 + 1, y0 + 1);
+    }
+    float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
+    return t00 * w00 + t10 * w10 + t01 * w01 + t11 * w11;
+}
+
+// Nearest-mip selection for a point-mip sampler given a fractional LOD.
+inline int nearest_mip(float lod, int levels) { return clampi(int(std::floor(lod + 0.5f)), 0, levels - 1); }
+
+// Row-parallel helper: the oracle's "all host cores" mode for the cpu_baseline leg. threads<=1 -> serial.
+inline void parallel_rows(int y0, int y1, int threads, const std::function<void(int, int)>& fn)
+{
+    int rows = y1 - y0;
+    if (threads <= 1 || rows < 2 * threads)
+    {
+        fn(y0, y1);
+        return;
+    }
+    std::vector<std::thread> pool;
+    int                      chunk = (rows + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t)
+    {
+        int a = y0 + t * chunk, b = std::min(y1, a + chunk);
+        if (a >= b) break;
+        pool.emplace_back(fn, a, b);
+    }
+    for (auto& th : pool) th.join();
+}
+
+} // namespace orc
