@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""bench.py — Mpixels/s of the full PostProcess chain (PostFX prep -> SSR -> SSAO -> compose -> TAA -> Bloom -> ToneMap+sRGB)
+on a synthetic 3840x2160 G-buffer (BASELINE.json metric / configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--width 3840 --height 2160]
+
+One "step" = one frame of the chain. Rank r (one process per GPU; torchrun for N > 1) processes its own sequence of
+frames: frames of a batch are independent sequences (replicas, no data-path collective), so
+scaling is weak and `value` = pixels all ranks processed / max-over-ranks device time.
+
+Lines of the JSON record (one line on stdout, rank 0):
+  value         device-resident throughput: the G-buffers of the timed steps are already in HBM (4 distinct frames, 0.5 GB
+                each, cycled -> every step's inputs are cold in the 126 MB L2); timed with CUDA events, max over ranks.
+  e2e           the same K steps through the public API with HOST buffers: per step the frame's G-buffer is copied from
+                pinned host memory, the chain runs, and the LDR result is read back into pinned host memory.
+  roofline      dominant pass of the chain (largest share of the step): algorithmic bytes / CUDA-event time inside this run,
+                against MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s, B200_PROFILING.md). `passes` lists every pass.
+  cpu_baseline  the oracle (scalar C++ port of the Shaders/PostProcess math) on this box's host cores, bounded sample.
+  --impl reference: the same metric from the oracle alone (the reference has no CPU implementation and cannot be built
+                here: DiligentCore + HLSL compiler + graphics device are required — DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/sec full PostProcess chain @ 4K G-buffer"
+UNIT = "Mpix/s"
+
+# Algorithmic (compulsory) bytes per full-resolution pixel of each pass in this build's fp32 layout: every distinct plane the
+# pass reads or writes counted once at its full size, pyramids as geometric sums (derivation in DESIGN.md §4).
+PASS_BYTES_PER_PX = {
+    "blue_noise": 0.0,
+    "postfx_prepare": 32.0,
+    "ssr_hiz": 5.33, "ssr_mask_roughness": 25.0, "ssr_intersect": 74.33, "ssr_spatial": 81.0, "ssr_temporal": 81.0, "ssr_bilateral": 61.0,
+    "ssao_prefilter_depth": 5.33, "ssao_ambient_occlusion": 25.33, "ssao_temporal": 36.0, "ssao_convolute": 10.67, "ssao_resample": 16.0,
+    "ssao_spatial": 32.0,
+    "compose": 52.0, "taa": 64.0,
+    "bloom_prefilter": 20.0, "bloom_downsample": 6.67, "bloom_upsample": 12.0, "bloom_composite": 36.0,
+    "tonemap": 32.0,
+}
+
+
+def measured_hbm_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(width: int, height: int, frames: int, threads: int) -> dict:
+    """Oracle full chain on a bounded sample (test infrastructure used as the reported CPU baseline only)."""
+    from diligentfx_b200 import synth
+    from oracle import oracle_py as op
+    seq = synth.generate_sequence(width, height, frames)
+    o = op.Oracle(width, height, threads=threads)
+    times = []
+    for fr in seq:
+        o.set_inputs(fr)
+        times.append(o.frame())
+    steady = times[1:] if len(times) > 1 else times
+    mpix = width * height / 1e6 / (statistics.median(steady) / 1e3)
+    return {"value": round(mpix, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{len(steady)} consecutive {width}x{height} frames of the full chain (1/{(3840 * 2160) // (width * height)} of a 4K frame each), "
+                      f"median; scalar C++ oracle, row-parallel std::thread"}
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's own CPU path does not exist (HLSL pixel shaders only); the oracle port stands in."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from diligentfx_b200 import synth
+    from oracle import oracle_py as op
+    threads = os.cpu_count() or 1
+    w, h = args.ref_width, args.ref_height
+    seq = synth.generate_sequence(w, h, args.warmup + args.steps)
+    o = op.Oracle(w, h, threads=threads)
+    for fr in seq[:args.warmup]:
+        o.set_inputs(fr)
+        o.frame()
+    t = 0.0
+    for fr in seq[args.warmup:]:
+        o.set_inputs(fr)
+        t += o.frame()
+    ms = t / args.steps
+    value = w * h / 1e6 / (ms / 1e3)
+    sample = f"each step = one {w}x{h} frame of the full chain (1/{(args.width * args.height) // (w * h)} of the {args.width}x{args.height} workload)"
+    rec = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"full PostProcess chain, {args.width}x{args.height} synthetic G-buffer (bounded sample: {sample})"},
+           "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(rec), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--frames", type=int, default=4, help="distinct synthetic frames resident per rank (cycled)")
+    ap.add_argument("--ref-width", type=int, default=960)
+    ap.add_argument("--ref-height", type=int, default=540)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from diligentfx_b200 import capi, synth
+    from diligentfx_b200.chain import INPUT_SPECS, PostProcessChain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the chain has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, K, Wm = args.width, args.height, args.steps, args.warmup
+    lib = capi.load()
+
+    # ---- synthetic data: `frames` consecutive frames of one camera path per rank (rank-specific seed) ----
+    seq = synth.generate_sequence(W, H, args.frames, seed=7 + rank)
+    host = [{n: torch.from_numpy(np.ascontiguousarray(fr[n])).pin_memory() for n in INPUT_SPECS} for fr in seq]
+    resident = [{n: t.to(dev) for n, t in hf.items()} for hf in host]
+    cams = [(fr["curr_camera"], fr["prev_camera"]) for fr in seq]
+    h2d_bytes = sum(t.numel() * 4 for t in host[0].values())
+    chain = PostProcessChain(W, H, device=dev)
+    ldr_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    d2h_bytes = ldr_host.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_id = [0]
+
+    def next_frame():
+        # consecutive frame indices (histories stay valid); the resident G-buffers are cycled
+        i = step_id[0]
+        step_id[0] += 1
+        return i, i % len(seq)
+
+    def run_resident():
+        idx, slot = next_frame()
+        chain.execute(idx, cams[slot][0], cams[slot][1], resident[slot])
+
+    def run_e2e():
+        idx, slot = next_frame()
+        chain.upload(host[slot])
+        ldr = chain.execute(idx, cams[slot][0], cams[slot][1])
+        ldr_host.copy_(ldr, non_blocking=True)
+
+    def timed(fn, steps: int) -> float:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the timed device-resident region (clocks sampled during it) ----
+    for _ in range(Wm):
+        run_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.dfx_launch_count()
+    total_ms = timed(run_resident, K)
+    launches = lib.dfx_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / K
+    value = world * W * H / 1e6 / (ms_per_step / 1e3)
+
+    # ---- end to end through the public API with host buffers ----
+    for _ in range(2):
+        run_e2e()
+    e2e_ms = timed(run_e2e, K) / K
+    e2e_value = world * W * H / 1e6 / (e2e_ms / 1e3)
+
+    # ---- per-pass device times (CUDA events on the launching stream, same steps) ----
+    passes, roof = [], None
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        lib.dfx_profile_reset()
+        lib.dfx_profile_enable(1)
+        for _ in range(K):
+            run_resident()
+        torch.cuda.synchronize()
+        lib.dfx_profile_enable(0)
+        capi.check(lib.dfx_profile_collect())
+        name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
+        step_sum = 0.0
+        for i in range(lib.dfx_profile_count()):
+            capi.check(lib.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls)))
+            nm = name.value.decode()
+            ms = tot.value / K                                  # per step (a pass may launch several kernels / levels)
+            step_sum += ms
+            by = PASS_BYTES_PER_PX.get(nm, 0.0) * W * H
+            gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            passes.append({"pass": nm, "ms": round(ms, 4), "launch_groups_per_step": calls.value // K, "alg_bytes": int(by), "GBps": round(gbs, 1),
+                           "frac": round(gbs / peak, 4)})
+        for p in passes:
+            p["share"] = round(p["ms"] / step_sum, 4) if step_sum else 0.0
+        top = max(passes, key=lambda p: p["ms"])
+        roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": None,
+                "peak_source": peak_src, "share_of_step": top["share"],
+                "chain": {"alg_bytes_per_px": round(sum(PASS_BYTES_PER_PX.values()), 2),
+                          "achieved": round(sum(p["alg_bytes"] for p in passes) / (ms_per_step * 1e-3) / 1e9, 1)}}
+        roof["chain"]["frac"] = round(roof["chain"]["achieved"] / peak, 4)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.ref_width, args.ref_height, 3, os.cpu_count() or 1)
+
+    if rank == 0:
+        rec = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"full PostProcess chain (PostFX prep, SSR, SSAO, compose, TAA bicubic, Bloom {lib.dfx_bloom_mip_count(W // 2, H // 2, C.c_float(0.75))} levels, "
+                                   f"ToneMap Uncharted2 + sRGB) on a {W}x{H} synthetic G-buffer + history, consecutive frames, one sequence per GPU",
+                       "width": W, "height": H, "parallelism": f"replicas x{world} (independent frame sequences, no data-path collective)",
+                       "cache": f"{args.frames} distinct resident G-buffers of {h2d_bytes / 1e6:.0f} MB cycled: inputs larger than the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes)},
+            "roofline": roof, "cpu_baseline": cpu, "passes": passes,
+        }
+        print(json.dumps(rec), flush=True)
+    chain.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+"""Host-side driver of the full PostProcess chain over the effect-level C-ABI.
+
+Mirrors the reference integration `HnPostProcessTask` (Hydrogent/src/Tasks/HnPostProcessTask.cpp): Prepare (:591-683)
+creates / prepares PostFXContext, SSR, SSAO, TAA, Bloom every frame; Execute (:743-947) runs
+PostFX -> SSR -> SSAO -> compose -> TAA -> Bloom -> ToneMap(+sRGB). All arithmetic happens in libdfx_b200.so; this
+module only sequences calls and owns the input/output device planes (torch is used for device memory and streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import (BloomAttribs, BloomRenderAttribs, FrameDesc, Plane, PostFXRenderAttribs, Rows, SSAOAttribs, SSAORenderAttribs, SSRAttribs,
+                   SSRRenderAttribs, TAAAttribs, TAARenderAttribs, ToneMapAttribs, check, plane_of)
+
+STAGE_POSTFX, STAGE_SSR, STAGE_SSAO, STAGE_COMPOSE, STAGE_TAA, STAGE_BLOOM, STAGE_TONEMAP = 1, 2, 4, 8, 16, 32, 64
+STAGE_ALL = 127
+
+INPUT_SPECS = {  # name -> trailing channel count (0 = scalar plane)
+    "depth": 0, "prev_depth": 0, "motion": 2, "normal": 4, "color": 4, "material": 4,
+}
+
+
+@dataclass
+class ChainConfig:
+    ssao: SSAOAttribs = field(default_factory=SSAOAttribs.default)
+    ssr: SSRAttribs = field(default_factory=SSRAttribs.default)
+    bloom: BloomAttribs = field(default_factory=BloomAttribs.default)
+    taa: TAAAttribs = field(default_factory=TAAAttribs.default)
+    tonemap: ToneMapAttribs = field(default_factory=ToneMapAttribs.default)
+    ssr_flags: int = 0
+    taa_flags: int = capi.TAA_FLAG_BICUBIC                 # Hydrogent default (HnPostProcessTask.hpp:109)
+    ave_log_lum: float = 0.3                               # HnPostProcessTask.hpp:88, fExposure 0
+    to_srgb: bool = True
+    ssr_scale: float = 1.0
+    ssao_scale: float = 1.0
+    stages: int = STAGE_ALL
+
+
+class PostProcessChain:
+    """One view / one stream of consecutive frames on the current CUDA device."""
+
+    def __init__(self, width: int, height: int, config: ChainConfig | None = None, device: torch.device | None = None):
+        self.lib = capi.load()
+        self.w, self.h = width, height
+        self.cfg = config or ChainConfig()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        if not torch.cuda.is_available():
+            raise capi.DfxError("no CUDA device: the PostProcess chain has no CPU path")
+        L = self.lib
+        self.postfx, self.ssao, self.ssr, self.bloom, self.taa = (C.c_void_p() for _ in range(5))
+        check(L.dfx_postfx_create(C.byref(self.postfx)), "dfx_postfx_create")
+        check(L.dfx_ssao_create(C.byref(self.ssao)), "dfx_ssao_create")
+        check(L.dfx_ssr_create(C.byref(self.ssr)), "dfx_ssr_create")
+        check(L.dfx_bloom_create(C.byref(self.bloom)), "dfx_bloom_create")
+        check(L.dfx_taa_create(C.byref(self.taa)), "dfx_taa_create")
+        dev = self.device
+        # device-resident inputs (filled by upload()) and chain-owned intermediates
+        self.inputs = {n: torch.empty((height, width) + ((c,) if c else ()), dtype=torch.float32, device=dev) for n, c in INPUT_SPECS.items()}
+        self.composed = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
+        self.ldr = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
+        self.frame_index = None
+
+    def close(self):
+        L = self.lib
+        for h, fn in ((self.taa, L.dfx_taa_destroy), (self.bloom, L.dfx_bloom_destroy), (self.ssr, L.dfx_ssr_destroy), (self.ssao, L.dfx_ssao_destroy),
+                      (self.postfx, L.dfx_postfx_destroy)):
+            if h:
+                fn(h)
+        self.postfx = self.ssao = self.ssr = self.bloom = self.taa = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- input transfer -------------------------------------------------------------------------------------------
+    def upload(self, frame: dict, non_blocking: bool = True) -> int:
+        """Host (numpy or pinned torch) -> device copies of one frame's G-buffer. Returns bytes copied."""
+        n = 0
+        for name in INPUT_SPECS:
+            src = frame[name]
+            t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, np.float32))
+            self.inputs[name].copy_(t, non_blocking=non_blocking)
+            n += t.numel() * 4
+        return n
+
+    # ---- one frame ------------------------------------------------------------------------------------------------
+    def execute(self, frame_index: int, curr_camera, prev_camera, inputs: dict | None = None) -> torch.Tensor:
+        """Runs the chain on device-resident inputs (default: the planes filled by upload()); returns the final LDR plane
+        (device tensor, rgba)."""
+        L, cfg = self.lib, self.cfg
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        st = cfg.stages
+        P = {n: plane_of(t) for n, t in (inputs or self.inputs).items()}
+
+        # Prepare (HnPostProcessTask.cpp:671-683)
+        desc = FrameDesc(frame_index, self.w, self.h, self.w, self.h)
+        check(L.dfx_postfx_prepare(self.postfx, C.byref(desc), 0), "dfx_postfx_prepare")
+        if st & STAGE_SSAO:
+            check(L.dfx_ssao_prepare(self.ssao, self.postfx, 0), "dfx_ssao_prepare")
+        if st & STAGE_SSR:
+            check(L.dfx_ssr_prepare(self.ssr, self.postfx, cfg.ssr_flags), "dfx_ssr_prepare")
+        if st & STAGE_TAA:
+            check(L.dfx_taa_prepare(self.taa, self.postfx, cfg.taa_flags, 0), "dfx_taa_prepare")
+        if st & STAGE_BLOOM:
+            check(L.dfx_bloom_prepare(self.bloom, self.postfx, 0), "dfx_bloom_prepare")
+
+        # Execute (HnPostProcessTask.cpp:788-925)
+        if st & STAGE_POSTFX:
+            a = PostFXRenderAttribs(stream, C.pointer(P["depth"]), C.pointer(P["prev_depth"]), C.pointer(P["motion"]), C.pointer(curr_camera),
+                                    C.pointer(prev_camera))
+            check(L.dfx_postfx_execute(self.postfx, C.byref(a)), "dfx_postfx_execute")
+        if st & STAGE_SSR:
+            a = SSRRenderAttribs(stream, self.postfx, C.pointer(P["color"]), C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(P["material"]),
+                                 C.pointer(P["motion"]), C.pointer(cfg.ssr))
+            check(L.dfx_ssr_execute(self.ssr, C.byref(a)), "dfx_ssr_execute")
+        if st & STAGE_SSAO:
+            a = SSAORenderAttribs(stream, self.postfx, C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(cfg.ssao))
+            check(L.dfx_ssao_execute(self.ssao, C.byref(a)), "dfx_ssao_execute")
+
+        color = P["color"]
+        if st & STAGE_COMPOSE:
+            ssr_out, ao_out = Plane(), Plane()
+            pssr = pao = None
+            if st & STAGE_SSR:
+                check(L.dfx_ssr_get_plane(self.ssr, 0, C.byref(ssr_out)), "dfx_ssr_get_plane")
+                pssr = C.byref(ssr_out)
+            if st & STAGE_SSAO:
+                check(L.dfx_ssao_get_plane(self.ssao, 0, C.byref(ao_out)), "dfx_ssao_get_plane")
+                pao = C.byref(ao_out)
+            comp = plane_of(self.composed)
+            check(L.dfx_pass_compose(stream, C.byref(color), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale), C.byref(comp), Rows(0, self.h)),
+                  "dfx_pass_compose")
+            color = comp
+        if st & STAGE_TAA:
+            a = TAARenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.taa), 0)
+            check(L.dfx_taa_execute(self.taa, C.byref(a)), "dfx_taa_execute")
+            acc = Plane()
+            check(L.dfx_taa_get_plane(self.taa, 0, 0, C.byref(acc)), "dfx_taa_get_plane")
+            color = acc
+        if st & STAGE_BLOOM:
+            a = BloomRenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.bloom))
+            check(L.dfx_bloom_execute(self.bloom, C.byref(a)), "dfx_bloom_execute")
+            out = Plane()
+            check(L.dfx_bloom_get_plane(self.bloom, 0, C.byref(out)), "dfx_bloom_get_plane")
+            color = out
+        if st & STAGE_TONEMAP:
+            ldr = plane_of(self.ldr)
+            check(L.dfx_pass_tonemap(stream, C.byref(cfg.tonemap), C.c_float(cfg.ave_log_lum), int(cfg.to_srgb), C.byref(color), C.byref(ldr), Rows(0, self.h)),
+                  "dfx_pass_tonemap")
+        self.frame_index = frame_index
+        return self.ldr
+
+    def run_frame(self, frame: dict) -> torch.Tensor:
+        """Public one-call API: host G-buffer in, LDR device plane out (upload + execute)."""
+        self.upload(frame)
+        return self.execute(frame["frame"], frame["curr_camera"], frame["prev_camera"])
+
+    # ---- debug access to effect-owned planes (parity tests) --------------------------------------------------------
+    def fetch(self, effect: str, plane_id: int) -> np.ndarray:
+        L = self.lib
+        p = Plane()
+        if effect == "postfx":
+            check(L.dfx_postfx_get_plane(self.postfx, plane_id, C.byref(p)))
+        elif effect == "ssao":
+            check(L.dfx_ssao_get_plane(self.ssao, plane_id, C.byref(p)))
+        elif effect == "ssr":
+            check(L.dfx_ssr_get_plane(self.ssr, plane_id, C.byref(p)))
+        elif effect == "bloom":
+            check(L.dfx_bloom_get_plane(self.bloom, plane_id, C.byref(p)))
+        elif effect == "taa":
+            check(L.dfx_taa_get_plane(self.taa, plane_id, 0, C.byref(p)))
+        else:
+            raise KeyError(effect)
+        return download_plane(p)
+
+
+def download_plane(p: Plane) -> np.ndarray:
+    """Device plane -> numpy (H,W[,C]) float32 (uint8 masks are returned as float 0/1)."""
+    L = capi.load()
+    ch = {capi.FORMAT_R32F: 1, capi.FORMAT_RG32F: 2, capi.FORMAT_RGBA32F: 4, capi.FORMAT_R8U: 1}[p.format]
+    if p.format == capi.FORMAT_R8U:
+        out = np.empty((p.height, p.width), np.uint8)
+    else:
+        out = np.empty((p.height, p.width) if ch == 1 else (p.height, p.width, ch), np.float32)
+    check(L.dfx_stream_synchronize(None))
+    check(L.dfx_plane_download(None, C.byref(p), out.ctypes.data_as(C.c_void_p), 0), "dfx_plane_download")
+    check(L.dfx_stream_synchronize(None))
+    return out.astype(np.float32)

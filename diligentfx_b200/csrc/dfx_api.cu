@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <string>
+#include <vector>
 
 namespace dfx
 {
@@ -25,6 +27,49 @@ dfx_status check_cuda(cudaError_t e, const char* what)
     return set_error(DFX_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- optional per-pass device timing -------------------------------------------------------------------------------
+struct ProfileRecord
+{
+    const char* name;
+    cudaEvent_t a, b;
+};
+static bool                        g_profile_on = false;
+static std::vector<ProfileRecord>  g_records;
+static std::vector<cudaEvent_t>    g_event_pool;
+struct ProfileEntry
+{
+    std::string name;
+    double      total_ms;
+    int         calls;
+};
+static std::vector<ProfileEntry> g_entries;
+
+static cudaEvent_t take_event()
+{
+    if (!g_event_pool.empty())
+    {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfileScope::ProfileScope(void* stream, const char* name) : s(static_cast<cudaStream_t>(stream)), slot(-1)
+{
+    if (!g_profile_on) return;
+    ProfileRecord r{name, take_event(), take_event()};
+    cudaEventRecord(r.a, s);
+    slot = (int)g_records.size();
+    g_records.push_back(r);
+}
+ProfileScope::~ProfileScope()
+{
+    if (slot >= 0) cudaEventRecord(g_records[slot].b, s);
+}
 
 __global__ void fill_kernel(float* p, int pitch_f, int wf, int h, int ch, float4 v)
 {
@@ -159,6 +204,39 @@ dfx_status dfx_plane_fill(void* stream, const dfx_plane* dst, const float value[
 dfx_status dfx_stream_synchronize(void* stream)
 {
     DFX_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return DFX_OK;
+}
+
+void dfx_profile_enable(int32_t on) { g_profile_on = on != 0; }
+
+dfx_status dfx_profile_collect(void)
+{
+    // waits for the recorded events and folds them into per-pass totals (first-seen order)
+    for (const ProfileRecord& r : g_records)
+    {
+        DFX_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.0f;
+        DFX_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        size_t i = 0;
+        for (; i < g_entries.size(); ++i)
+            if (g_entries[i].name == r.name) break;
+        if (i == g_entries.size()) g_entries.push_back(ProfileEntry{r.name, 0.0, 0});
+        g_entries[i].total_ms += ms;
+        g_entries[i].calls += 1;
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_records.clear();
+    return DFX_OK;
+}
+void    dfx_profile_reset(void) { dfx_profile_collect(), g_entries.clear(); }
+int32_t dfx_profile_count(void) { return (int32_t)g_entries.size(); }
+dfx_status dfx_profile_entry(int32_t i, char* name, int32_t name_cap, double* total_ms, int32_t* calls)
+{
+    DFX_REQUIRE(i >= 0 && i < (int32_t)g_entries.size() && name && name_cap > 0 && total_ms && calls, "bad profile entry query");
+    snprintf(name, (size_t)name_cap, "%s", g_entries[i].name.c_str());
+    *total_ms = g_entries[i].total_ms;
+    *calls    = g_entries[i].calls;
     return DFX_OK;
 }
 } // extern "C"

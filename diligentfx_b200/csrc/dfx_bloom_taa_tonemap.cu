@@ -465,6 +465,7 @@ static inline dfx_rows scale_rows(dfx_rows r, int full_h, int h)
 
 extern "C" dfx_status dfx_pass_bloom_prefilter(void* stream, const dfx_bloom_attribs* attribs, const dfx_plane* color, const dfx_plane* out_level0, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "bloom_prefilter");
     DFX_REQUIRE(attribs, "null argument");
     DFX_VIEW(const float4, in, color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(float4, out, out_level0, DFX_FORMAT_RGBA32F);
@@ -479,6 +480,7 @@ extern "C" dfx_status dfx_pass_bloom_prefilter(void* stream, const dfx_bloom_att
 
 extern "C" dfx_status dfx_pass_bloom_downsample(void* stream, const dfx_plane* in_, const dfx_plane* out_, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "bloom_downsample");
     DFX_VIEW(const float4, in, in_, DFX_FORMAT_RGBA32F);
     DFX_VIEW(float4, out, out_, DFX_FORMAT_RGBA32F);
     DFX_REQUIRE(out.w == max(in.w / 2, 1) && out.h == max(in.h / 2, 1), "output must be half the input size");
@@ -492,6 +494,7 @@ extern "C" dfx_status dfx_pass_bloom_downsample(void* stream, const dfx_plane* i
 
 extern "C" dfx_status dfx_pass_bloom_upsample(void* stream, const dfx_plane* same_level_down, const dfx_plane* coarser, const dfx_plane* out_, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "bloom_upsample");
     DFX_VIEW(const float4, same, same_level_down, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float4, lo, coarser, DFX_FORMAT_RGBA32F);
     DFX_VIEW(float4, out, out_, DFX_FORMAT_RGBA32F);
@@ -507,6 +510,7 @@ extern "C" dfx_status dfx_pass_bloom_upsample(void* stream, const dfx_plane* sam
 extern "C" dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_attribs* attribs, const dfx_plane* color, const dfx_plane* up0,
                                                const dfx_plane* out_, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "bloom_composite");
     DFX_REQUIRE(attribs, "null argument");
     DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float4, u, up0, DFX_FORMAT_RGBA32F);
@@ -524,6 +528,7 @@ extern "C" dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* camer
                                    const dfx_plane* curr_color, const dfx_plane* prev_accum, const dfx_plane* closest_motion,
                                    const dfx_plane* reprojected_depth, const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "taa");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const float4, cc, curr_color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float4, pa, prev_accum, DFX_FORMAT_RGBA32F);
@@ -560,6 +565,7 @@ extern "C" dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* camer
 extern "C" dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale,
                                        float ssao_scale, const dfx_plane* out_, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "compose");
     DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(float4, out, out_, DFX_FORMAT_RGBA32F);
     DFX_SAME_SIZE(c, out);
@@ -584,6 +590,7 @@ extern "C" dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, con
 extern "C" dfx_status dfx_pass_tonemap(void* stream, const dfx_tonemap_attribs* attribs, float ave_log_lum, int32_t convert_to_srgb,
                                        const dfx_plane* color, const dfx_plane* out_, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "tonemap");
     DFX_REQUIRE(attribs, "null argument");
     DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(float4, out, out_, DFX_FORMAT_RGBA32F);

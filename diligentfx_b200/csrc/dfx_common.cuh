@@ -39,6 +39,17 @@ void       count_launch(int n = 1);
         if (e__ != cudaSuccess) return ::dfx::check_cuda(e__, name); \
     } while (0)
 
+// Optional per-pass device timing (dfx_profile_* in the C-ABI): when enabled, every dfx_pass_* call brackets its launches
+// with a pair of CUDA events on the launching stream.
+struct ProfileScope
+{
+    cudaStream_t s;
+    int          slot;
+    ProfileScope(void* stream, const char* name);
+    ~ProfileScope();
+};
+#define DFX_PROFILE(stream, name) ::dfx::ProfileScope profile_scope__(stream, name)
+
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 inline int          div_up(int a, int b) { return (a + b - 1) / b; }
 

@@ -108,6 +108,7 @@ using namespace dfx;
 
 extern "C" dfx_status dfx_pass_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const dfx_plane* xy, const dfx_plane* zw)
 {
+    DFX_PROFILE(stream, "blue_noise");
     DFX_REQUIRE(tables != nullptr, "tables must not be null");
     DFX_VIEW(float2, vxy, xy, DFX_FORMAT_RG32F);
     DFX_VIEW(float2, vzw, zw, DFX_FORMAT_RG32F);
@@ -121,6 +122,7 @@ extern "C" dfx_status dfx_pass_postfx_prepare(void* stream, const dfx_camera_att
                                               const dfx_plane* prev_depth_in, const dfx_plane* motion, const dfx_plane* reprojected_depth,
                                               const dfx_plane* closest_motion, const dfx_plane* previous_depth, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "postfx_prepare");
     DFX_REQUIRE(cameras_dev != nullptr, "cameras_dev must not be null");
     DFX_VIEW(const float, d, curr_depth, DFX_FORMAT_R32F);
     DFX_VIEW(const float, pin, prev_depth_in, DFX_FORMAT_R32F);

@@ -467,6 +467,7 @@ using namespace dfx;
 extern "C" dfx_status dfx_pass_ssao_prefilter_depth(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssao_attribs* attribs,
                                                     const dfx_pyramid* pyr, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssao_prefilter_depth");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     PyrViewRW P;
     DFX_REQUIRE(make_pyr_rw(pyr, P, 1), "bad prefiltered-depth pyramid");
@@ -487,6 +488,7 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
                                                       const dfx_pyramid* prefiltered_depth, const dfx_plane* normal,
                                                       const dfx_plane* blue_noise_zw, const dfx_plane* occlusion, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssao_ambient_occlusion");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     PyrView P;
     DFX_REQUIRE(make_pyr(prefiltered_depth, P, 1), "bad prefiltered-depth pyramid");
@@ -516,6 +518,7 @@ extern "C" dfx_status dfx_pass_ssao_temporal(void* stream, const dfx_camera_attr
                                              const dfx_plane* previous_depth, const dfx_plane* closest_motion,
                                              const dfx_plane* out_occlusion, const dfx_plane* out_history_length, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssao_temporal");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const float, co, curr_occlusion, DFX_FORMAT_R32F);
     DFX_VIEW(const float, po, prev_occlusion, DFX_FORMAT_R32F);
@@ -542,6 +545,7 @@ extern "C" dfx_status dfx_pass_ssao_temporal(void* stream, const dfx_camera_attr
 
 extern "C" dfx_status dfx_pass_ssao_convolute(void* stream, const dfx_pyramid* occlusion_pyr, const dfx_pyramid* depth_pyr, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssao_convolute");
     PyrViewRW O, D;
     DFX_REQUIRE(make_pyr_rw(occlusion_pyr, O, 1) && make_pyr_rw(depth_pyr, D, 1), "bad pyramid");
     DFX_REQUIRE(O.levels == D.levels, "pyramid level mismatch");
@@ -563,6 +567,7 @@ extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attr
                                              const dfx_pyramid* depth_pyr, const dfx_plane* history_length, const dfx_plane* normal,
                                              const dfx_plane* out_occlusion, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssao_resample");
     DFX_REQUIRE(cameras_dev, "null argument");
     PyrView O, D;
     DFX_REQUIRE(make_pyr(occlusion_pyr, O, 1) && make_pyr(depth_pyr, D, 1), "bad pyramid");
@@ -586,6 +591,7 @@ extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attri
                                             const dfx_plane* occlusion, const dfx_plane* history_length, const dfx_plane* depth,
                                             const dfx_plane* normal, const dfx_plane* out_occlusion, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssao_spatial");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const float, o, occlusion, DFX_FORMAT_R32F);
     DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);

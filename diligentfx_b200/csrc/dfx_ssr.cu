@@ -558,6 +558,7 @@ using namespace dfx;
 
 extern "C" dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssr_hiz");
     DFX_REQUIRE(pyr && pyr->levels >= 1 && pyr->levels <= DFX_MAX_MIPS, "bad Hi-Z pyramid");
     View<float> lv[DFX_MAX_MIPS];
     for (int i = 0; i < pyr->levels; ++i)
@@ -584,6 +585,7 @@ extern "C" dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx
 extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_attribs* attribs, const dfx_plane* material, const dfx_plane* depth,
                                                   const dfx_plane* roughness, const dfx_plane* mask, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssr_mask_roughness");
     DFX_REQUIRE(attribs, "null argument");
     DFX_VIEW(const float4, m, material, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
@@ -605,6 +607,7 @@ extern "C" dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attr
                                              const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz, const dfx_plane* motion,
                                              const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssr_intersect");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) == 0, "half-resolution SSR is not implemented");
     DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
@@ -646,6 +649,7 @@ extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attrib
                                            const dfx_plane* raydir_pdf, const dfx_plane* radiance, const dfx_plane* out_resolved_radiance,
                                            const dfx_plane* out_resolved_variance, const dfx_plane* out_resolved_depth, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssr_spatial");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
@@ -678,6 +682,7 @@ extern "C" dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attri
                                             const dfx_plane* prev_radiance, const dfx_plane* prev_variance, const dfx_plane* out_radiance,
                                             const dfx_plane* out_variance, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssr_temporal");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
     DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
@@ -712,6 +717,7 @@ extern "C" dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attr
                                              const dfx_plane* depth, const dfx_plane* normal, const dfx_plane* roughness, const dfx_plane* radiance,
                                              const dfx_plane* variance, const dfx_plane* out, dfx_rows rows)
 {
+    DFX_PROFILE(stream, "ssr_bilateral");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);

@@ -518,6 +518,14 @@ DFX_API dfx_status dfx_plane_download(void* stream, const dfx_plane* src, void* 
 DFX_API dfx_status dfx_plane_fill(void* stream, const dfx_plane* dst, const float value[4]);
 DFX_API dfx_status dfx_stream_synchronize(void* stream);
 
+/* Optional per-pass device timing (stands in for the reference's ScopedDebugGroup markers, e.g. ScreenSpaceAmbientOcclusion.cpp:363):
+ * while enabled every dfx_pass_* call is bracketed by two CUDA events on its stream. Not thread-safe; one stream at a time. */
+DFX_API void       dfx_profile_enable(int32_t on);
+DFX_API dfx_status dfx_profile_collect(void);                 /* waits for the recorded events, folds them into per-pass totals */
+DFX_API void       dfx_profile_reset(void);
+DFX_API int32_t    dfx_profile_count(void);
+DFX_API dfx_status dfx_profile_entry(int32_t i, char* name, int32_t name_cap, double* total_ms, int32_t* calls);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -1,0 +1,354 @@
+"""GPU parity tests: every CUDA pass against the CPU oracle on identical seeded inputs, through the C-ABI.
+
+Two layers:
+  * isolated passes — the oracle runs 4 consecutive frames; at the last frame each CUDA pass is fed the ORACLE's own
+    input planes, so a difference is attributable to that pass alone;
+  * whole chain — the effect-level objects run the same 4 frames end to end and every stage output is compared.
+
+Tolerances (fp32 arithmetic on both sides; the GPU contracts a*b+c into FMA and uses CUDA's libm, so results differ in
+the last bits; a handful of pixels may flip a discrete decision — nearest-mip rounding, a clamp, a Hi-Z cell step):
+per plane an absolute tolerance, a maximum fraction of outlier pixels, and a PSNR floor. HDR planes are compared after
+Reinhard c/(1+c) with peak 1. The north-star floor for the final LDR frame is 49 dB.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from diligentfx_b200 import capi, synth
+from helpers import Dev, assert_close, psnr, reinhard, rows
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(333, 187), (256, 144)]
+
+
+def _oracle_run(seq, threads=8):
+    from oracle import oracle_py as op
+    w, h = seq[0]["depth"].shape[1], seq[0]["depth"].shape[0]
+    o = op.Oracle(w, h, threads=threads)
+    for fr in seq:
+        o.set_inputs(fr)
+        o.frame()
+    return o
+
+
+@pytest.fixture(scope="module", params=SIZES, ids=lambda s: f"{s[0]}x{s[1]}")
+def ctx(request, built):
+    w, h = request.param
+    seq = synth.generate_sequence(w, h, 4)
+    o = _oracle_run(seq)
+    return dict(w=w, h=h, seq=seq, fr=seq[-1], o=o, f=seq[-1]["frame"])
+
+
+def _slots(f):
+    return f & 1, (f + 1) & 1
+
+
+# =====================================================================================================================
+# isolated passes
+# =====================================================================================================================
+def test_postfx_blue_noise(ctx):
+    d, o = Dev(), ctx["o"]
+    blob = np.frombuffer(open(capi.REPO_ROOT + "/diligentfx_b200/data/blue_noise_tables.bin", "rb").read(), np.uint8)
+    tables = d.torch.from_numpy(blob.copy()).cuda()
+    xy, zw = d.empty(128, 128, 2), d.empty(128, 128, 2)
+    for frame in (ctx["f"], 0, 200, 1000):
+        capi.check(d.lib.dfx_pass_blue_noise(None, C.c_void_p(tables.data_ptr()), frame, C.byref(d.plane(xy)), C.byref(d.plane(zw))))
+        o.set_frame_index(frame)
+        o.run("blue_noise")
+        # integer table lookups are exact; the golden-ratio shifts are fp32 and may differ by an ulp, and frac() can wrap
+        for name, got in (("bn_xy", d.host(xy)), ("bn_zw", d.host(zw))):
+            want = o.get(name)
+            diff = np.abs(got - want)
+            diff = np.minimum(diff, 1.0 - diff)
+            assert diff.max() < 1e-4, (name, frame, diff.max())
+    o.set_frame_index(ctx["f"])
+    o.run("blue_noise")
+
+
+def test_postfx_prepare(ctx):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+    depth, prev_in, motion = d.up(fr["depth"]), d.up(fr["prev_depth"]), d.up(fr["motion"])
+    rp, cm, pd = d.empty(h, w), d.empty(h, w, 2), d.empty(h, w)
+    capi.check(d.lib.dfx_pass_postfx_prepare(None, cams, C.byref(d.plane(depth)), C.byref(d.plane(prev_in)), C.byref(d.plane(motion)), C.byref(d.plane(rp)),
+                                             C.byref(d.plane(cm)), C.byref(d.plane(pd)), rows(h)))
+    assert_close("reprojected_depth", d.host(rp), o.get("reproj_depth"), tol=2e-6)
+    assert np.array_equal(d.host(cm), o.get("closest_motion"))
+    assert np.array_equal(d.host(pd), o.get("prev_depth"))
+
+
+def _pyr_names(o, base, n):
+    return [o.get(f"{base}.{i}") for i in range(n)]
+
+
+def test_ssao_prefilter(ctx):
+    d, o, fr, h = Dev(), ctx["o"], ctx["fr"], ctx["h"]
+    cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+    want = _pyr_names(o, "ssao_pre", 5)
+    lv = [d.up(fr["depth"])] + [d.empty(m.shape[0], m.shape[1]) for m in want[1:]]
+    a = capi.SSAOAttribs.default()
+    capi.check(d.lib.dfx_pass_ssao_prefilter_depth(None, cams, C.byref(a), C.byref(d.pyr(lv)), rows(h)))
+    for i in range(1, 5):
+        # depth near 1.0: fp32 resolution 6e-8; the weighted view-space average amplifies rounding through 1/z
+        assert_close(f"prefiltered mip {i}", d.host(lv[i]), want[i], tol=2e-6, max_outliers=1e-3, min_psnr=100.0)
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2], ids=["GTAO", "HBAO", "VBAO"])
+def test_ssao_ambient_occlusion(ctx, algo):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+    a = capi.SSAOAttribs.default()
+    a.Algorithm = algo
+    o.set_ssao(a)
+    o.run("ssao_ao")
+    want = o.get("ssao_occ")
+    lv = [d.up(m) for m in _pyr_names(o, "ssao_pre", 5)]
+    normal, bn, out = d.up(fr["normal"]), d.up(o.get("bn_zw")), d.empty(h, w)
+    capi.check(d.lib.dfx_pass_ssao_ambient_occlusion(None, cams, C.byref(a), C.byref(d.pyr(lv)), C.byref(d.plane(normal)), C.byref(d.plane(bn)),
+                                                     C.byref(d.plane(out)), rows(h)))
+    got = d.host(out)
+    # a tap whose LOD sits on x.5 or whose UV sits on a texel edge may pick the neighbouring texel/mip: rare, bounded
+    msg = assert_close(f"AO algo {algo}", got, want, tol=2e-3, max_outliers=(5e-3 if algo != 2 else 3e-2), min_psnr=(55.0 if algo != 2 else 40.0))
+    print(msg)
+    assert np.array_equal(got == 1.0, want == 1.0) or (np.abs((got == 1.0).astype(int) - (want == 1.0).astype(int)).mean() < 1e-3)
+    o.set_ssao(capi.SSAOAttribs.default())
+    o.run("ssao_ao")
+
+
+def test_ssao_temporal(ctx):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    cur, prv = _slots(ctx["f"])
+    cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+    a = capi.SSAOAttribs.default()
+    ins = [d.up(o.get(n)) for n in ("ssao_occ", f"ssao_hist{prv}", f"ssao_histlen{prv}", "reproj_depth", "prev_depth")]
+    mv = d.up(o.get("closest_motion"))
+    oo, oh = d.empty(h, w), d.empty(h, w)
+    capi.check(d.lib.dfx_pass_ssao_temporal(None, cams, C.byref(a), *[C.byref(d.plane(t)) for t in ins], C.byref(d.plane(mv)), C.byref(d.plane(oo)),
+                                            C.byref(d.plane(oh)), rows(h)))
+    # the 1 % depth-similarity test and the variance-clamp comparison are discrete decisions
+    print(assert_close("ssao accumulated", d.host(oo), o.get("ssao_acc"), tol=1e-4, max_outliers=2e-3, min_psnr=60.0))
+    print(assert_close("ssao history length", d.host(oh) / 16.0, o.get(f"ssao_histlen{cur}") / 16.0, tol=1e-4, max_outliers=2e-3, min_psnr=50.0))
+
+
+def test_ssao_convolute_resample_spatial(ctx):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    cur, _ = _slots(ctx["f"])
+    cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+    a = capi.SSAOAttribs.default()
+    wocc, wdep = _pyr_names(o, "ssao_conv_occ", 5), _pyr_names(o, "ssao_conv_depth", 5)
+    occ = [d.up(wocc[0])] + [d.empty(*m.shape) for m in wocc[1:]]
+    dep = [d.up(wdep[0])] + [d.empty(*m.shape) for m in wdep[1:]]
+    capi.check(d.lib.dfx_pass_ssao_convolute(None, C.byref(d.pyr(occ)), C.byref(d.pyr(dep)), rows(h)))
+    for i in range(1, 5):
+        assert_close(f"conv occ mip {i}", d.host(occ[i]), wocc[i], tol=1e-6)
+        assert_close(f"conv depth mip {i}", d.host(dep[i]), wdep[i], tol=1e-6)
+    # A7 on the oracle's pyramids
+    occ = [d.up(m) for m in wocc]
+    dep = [d.up(m) for m in wdep]
+    hist, normal = d.up(o.get(f"ssao_histlen{cur}")), d.up(fr["normal"])
+    res = d.empty(h, w)
+    capi.check(d.lib.dfx_pass_ssao_resample(None, cams, C.byref(d.pyr(occ)), C.byref(d.pyr(dep)), C.byref(d.plane(hist)), C.byref(d.plane(normal)),
+                                            C.byref(d.plane(res)), rows(h)))
+    print(assert_close("ssao resampled", d.host(res), o.get("ssao_resampled"), tol=2e-4, max_outliers=2e-3, min_psnr=60.0))
+    # A8 on the oracle's resampled plane
+    ins = [d.up(o.get("ssao_resampled")), hist, d.up(fr["depth"]), normal]
+    out = d.empty(h, w)
+    capi.check(d.lib.dfx_pass_ssao_spatial(None, cams, C.byref(a), *[C.byref(d.plane(t)) for t in ins], C.byref(d.plane(out)), rows(h)))
+    print(assert_close("ssao spatial (output)", d.host(out), o.get("ssao_out"), tol=2e-4, max_outliers=2e-3, min_psnr=60.0))
+
+
+def test_ssr_hiz_and_mask(ctx):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    want = _pyr_names(o, "ssr_hiz", 7)
+    lv = [d.up(fr["depth"])] + [d.empty(*m.shape) for m in want[1:]]
+    capi.check(d.lib.dfx_pass_ssr_hiz(None, C.byref(d.pyr(lv)), rows(h)))
+    for i in range(1, 7):
+        assert np.array_equal(d.host(lv[i]), want[i]), f"Hi-Z mip {i} must be bit-exact (min reduction)"
+    a = capi.SSRAttribs.default()
+    rough, mask = d.empty(h, w, fill=0.0), d.empty(h, w, dtype=d.torch.uint8, fill=7)
+    capi.check(d.lib.dfx_pass_ssr_mask_roughness(None, C.byref(a), C.byref(d.plane(d.up(fr["material"]))), C.byref(d.plane(d.up(fr["depth"]))),
+                                                 C.byref(d.plane(rough)), C.byref(d.plane(mask)), rows(h)))
+    wmask = o.get("ssr_mask")
+    assert np.array_equal(d.host(mask), wmask)
+    got_r, want_r = d.host(rough), o.get("ssr_roughness")
+    assert np.array_equal(got_r[wmask > 0], want_r[wmask > 0])
+
+
+def _ssr_common(ctx, d):
+    o, fr = ctx["o"], ctx["fr"]
+    return dict(cams=d.cameras(fr["curr_camera"], fr["prev_camera"]), a=capi.SSRAttribs.default(), rough=d.up(o.get("ssr_roughness")), mask=d.mask(o.get("ssr_mask")),
+                normal=d.up(fr["normal"]), depth=d.up(fr["depth"]), wmask=o.get("ssr_mask") > 0)
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["current", "previous_frame"])
+def test_ssr_intersect(ctx, flags):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    c = _ssr_common(ctx, d)
+    o.set_ssr(c["a"], flags)
+    o.run("ssr_intersect")
+    hiz = [d.up(m) for m in _pyr_names(o, "ssr_hiz", 7)]
+    rad, rdir = d.empty(h, w, 4, fill=-1.0), d.empty(h, w, 4, fill=-1.0)
+    capi.check(d.lib.dfx_pass_ssr_intersect(None, c["cams"], C.byref(c["a"]), flags, C.byref(d.plane(d.up(fr["color"]))), C.byref(d.plane(c["normal"])),
+                                            C.byref(d.plane(c["rough"])), C.byref(d.plane(c["mask"])), C.byref(d.plane(d.up(o.get("bn_xy")))), C.byref(d.pyr(hiz)),
+                                            C.byref(d.plane(d.up(fr["motion"]))), C.byref(d.plane(rad)), C.byref(d.plane(rdir)), rows(h)))
+    grad, wrad, gdir, wdir = d.host(rad), o.get("ssr_radiance"), d.host(rdir), o.get("ssr_raydir")
+    m = c["wmask"]
+    assert np.all(grad[~m] == 0.0) and np.all(gdir[~m] == 0.0), "masked-out pixels keep the clear value"
+    # The Hi-Z march is a chaotic integer walk: an ulp in the ray set-up can move a hit by a cell. Compare statistically:
+    # the hit decision (confidence > 0) must agree on >= 99 % of the rays, and rays that agree must agree closely.
+    ghit, whit = grad[..., 3] > 0, wrad[..., 3] > 0
+    agree = (ghit == whit)[m].mean()
+    both = m & ghit & whit
+    dlen = np.abs(np.linalg.norm(gdir[..., :3], axis=-1) - np.linalg.norm(wdir[..., :3], axis=-1))
+    same = both & (dlen < 1e-2 * (1.0 + np.linalg.norm(wdir[..., :3], axis=-1)))
+    print(f"ssr_intersect flags={flags}: rays={m.sum()} hit agreement={agree:.4%} same-hit among both-hit={same.sum() / max(both.sum(), 1):.4%}")
+    assert agree >= 0.99
+    assert same.sum() >= 0.98 * both.sum()
+    assert_close("ssr pdf", gdir[..., 3], wdir[..., 3], tol=1e-3 * max(1.0, float(np.abs(wdir[..., 3]).max())), max_outliers=5e-3, mask=m)
+    assert_close("ssr radiance (same hit)", grad, wrad, tol=5e-3, max_outliers=5e-3, hdr=True, mask=same)
+    o.set_ssr(c["a"], 0)
+    o.run("ssr_intersect")
+
+
+def test_ssr_spatial_temporal_bilateral(ctx):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    cur, prv = _slots(ctx["f"])
+    c = _ssr_common(ctx, d)
+    m = c["wmask"]
+    # S5
+    orad, ovar, odep = d.empty(h, w, 4, fill=0.0), d.empty(h, w, fill=0.0), d.empty(h, w, fill=0.0)
+    capi.check(d.lib.dfx_pass_ssr_spatial(None, c["cams"], C.byref(c["a"]), C.byref(d.plane(c["rough"])), C.byref(d.plane(c["mask"])), C.byref(d.plane(c["normal"])),
+                                          C.byref(d.plane(c["depth"])), C.byref(d.plane(d.up(o.get("ssr_raydir")))), C.byref(d.plane(d.up(o.get("ssr_radiance")))),
+                                          C.byref(d.plane(orad)), C.byref(d.plane(ovar)), C.byref(d.plane(odep)), rows(h)))
+    print(assert_close("ssr resolved radiance", d.host(orad), o.get("ssr_resolved_rad"), tol=2e-3, max_outliers=3e-3, min_psnr=55.0, hdr=True, mask=m))
+    print(assert_close("ssr resolved variance", d.host(ovar), o.get("ssr_resolved_var"), tol=2e-3, max_outliers=3e-3, hdr=True, mask=m))
+    print(assert_close("ssr resolved depth", d.host(odep), o.get("ssr_resolved_depth"), tol=2e-6, max_outliers=3e-3, mask=m))
+    assert np.all(d.host(orad)[~m] == 0.0), "masked-out pixels are not written"
+    # S6 (prev slots hold frame f-1 history, curr slots hold frame f-2 data that must survive where masked)
+    names = ("ssr_resolved_depth", "reproj_depth", "ssr_resolved_rad", "ssr_resolved_var", "prev_depth", f"ssr_radhist{prv}", f"ssr_varhist{prv}")
+    ins = [d.up(o.get(n)) for n in names]
+    want_rad, want_var = o.get(f"ssr_radhist{cur}"), o.get(f"ssr_varhist{cur}")
+    out_rad, out_var = d.empty(h, w, 4, fill=123.0), d.empty(h, w, fill=123.0)
+    capi.check(d.lib.dfx_pass_ssr_temporal(None, c["cams"], C.byref(c["a"]), C.byref(d.plane(c["mask"])), C.byref(d.plane(d.up(fr["motion"]))),
+                                           *[C.byref(d.plane(t)) for t in ins], C.byref(d.plane(out_rad)), C.byref(d.plane(out_var)), rows(h)))
+    assert np.all(d.host(out_rad)[~m] == 123.0) and np.all(d.host(out_var)[~m] == 123.0), "masked-out pixels are not written"
+    print(assert_close("ssr radiance history", d.host(out_rad), want_rad, tol=2e-3, max_outliers=5e-3, min_psnr=50.0, hdr=True, mask=m))
+    print(assert_close("ssr variance history", d.host(out_var), want_var, tol=2e-3, max_outliers=5e-3, hdr=True, mask=m))
+    # S7
+    out = d.empty(h, w, 4, fill=5.0)
+    capi.check(d.lib.dfx_pass_ssr_bilateral(None, c["cams"], C.byref(c["a"]), C.byref(d.plane(c["mask"])), C.byref(d.plane(c["depth"])), C.byref(d.plane(c["normal"])),
+                                            C.byref(d.plane(c["rough"])), C.byref(d.plane(d.up(want_rad))), C.byref(d.plane(d.up(want_var))), C.byref(d.plane(out)),
+                                            rows(h)))
+    got = d.host(out)
+    assert np.all(got[~m] == 0.0), "masked-out pixels hold the clear value"
+    print(assert_close("ssr output", got, o.get("ssr_out"), tol=2e-3, max_outliers=3e-3, min_psnr=55.0, hdr=True))
+
+
+def test_bloom_passes(ctx):
+    d, o = Dev(), ctx["o"]
+    a = capi.BloomAttribs.default()
+    src = o.get("bloom_in")
+    h, w = src.shape[:2]
+    mips = d.lib.dfx_bloom_mip_count(max(w // 2, 1), max(h // 2, 1), C.c_float(a.Radius))
+    want_d = [o.get(f"bloom_down{i}") for i in range(mips)]
+    want_u = [o.get(f"bloom_up{i}") for i in range(mips - 1)]
+    # B1
+    t_in, d0 = d.up(src), d.empty(*want_d[0].shape[:2], 4)
+    capi.check(d.lib.dfx_pass_bloom_prefilter(None, C.byref(a), C.byref(d.plane(t_in)), C.byref(d.plane(d0)), rows(want_d[0].shape[0])))
+    print(assert_close("bloom prefilter", d.host(d0), want_d[0], tol=1e-4, max_outliers=1e-4, min_psnr=90.0, hdr=True))
+    # B2 on the oracle's levels
+    for i in range(1, mips):
+        out = d.empty(*want_d[i].shape[:2], 4)
+        capi.check(d.lib.dfx_pass_bloom_downsample(None, C.byref(d.plane(d.up(want_d[i - 1]))), C.byref(d.plane(out)), rows(want_d[i].shape[0])))
+        assert_close(f"bloom down {i}", d.host(out), want_d[i], tol=1e-5, min_psnr=100.0, hdr=True)
+    # B3
+    top = mips - 1
+    for i in range(top, 0, -1):
+        coarser = want_u[i] if i != top else want_d[i]
+        out = d.empty(*want_u[i - 1].shape[:2], 4)
+        capi.check(d.lib.dfx_pass_bloom_upsample(None, C.byref(d.plane(d.up(want_d[i - 1]))), C.byref(d.plane(d.up(coarser))), C.byref(d.plane(out)),
+                                                 rows(want_u[i - 1].shape[0])))
+        assert_close(f"bloom up {i - 1}", d.host(out), want_u[i - 1], tol=1e-5, min_psnr=100.0, hdr=True)
+    # B4
+    out = d.empty(h, w, 4)
+    capi.check(d.lib.dfx_pass_bloom_composite(None, C.byref(a), C.byref(d.plane(t_in)), C.byref(d.plane(d.up(want_u[0]))), C.byref(d.plane(out)), rows(h)))
+    print(assert_close("bloom output", d.host(out), o.get("bloom_out"), tol=1e-5, min_psnr=100.0, hdr=True))
+
+
+@pytest.mark.parametrize("flags", [2, 0, 7], ids=["bicubic", "bilinear", "bicubic+ycocg+gauss"])
+def test_taa(ctx, flags):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    cur, prv = _slots(ctx["f"])
+    cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+    a = capi.TAAAttribs.default()
+    o.set_taa(a, flags)
+    o.run("taa")
+    want = o.get(f"taa_accum{cur}")
+    ins = [d.up(o.get(n)) for n in ("taa_in", f"taa_accum{prv}", "closest_motion", "reproj_depth", "prev_depth")]
+    out = d.empty(h, w, 4)
+    capi.check(d.lib.dfx_pass_taa(None, cams, C.byref(a), flags, *[C.byref(d.plane(t)) for t in ins], C.byref(d.plane(out)), rows(h)))
+    got = d.host(out)
+    print(assert_close(f"taa rgb flags={flags}", got[..., :3], want[..., :3], tol=1e-4, max_outliers=1e-3, min_psnr=70.0, hdr=True))
+    print(assert_close(f"taa alpha flags={flags}", got[..., 3], want[..., 3], tol=1e-4, max_outliers=1e-3))
+    o.set_taa(a, 2)
+    o.run("taa")
+
+
+def test_compose_and_tonemap(ctx):
+    d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
+    out = d.empty(h, w, 4)
+    capi.check(d.lib.dfx_pass_compose(None, C.byref(d.plane(d.up(fr["color"]))), C.byref(d.plane(d.up(o.get("ssr_out")))), C.byref(d.plane(d.up(o.get("ssao_out")))),
+                                      C.c_float(1.0), C.c_float(1.0), C.byref(d.plane(out)), rows(h)))
+    assert_close("composed", d.host(out), o.get("composed"), tol=1e-5, hdr=True)
+    rng = np.random.default_rng(1)
+    hdr = np.zeros((64, 256, 4), np.float32)
+    hdr[..., :3] = np.exp2(rng.uniform(-8, 6, (64, 256, 3)))
+    hdr[..., 3] = rng.uniform(size=(64, 256))
+    from oracle import oracle_py as op
+    for mode in range(12):
+        for srgb in (0, 1):
+            a = capi.ToneMapAttribs.default()
+            a.iToneMappingMode = mode
+            o2 = op.Oracle(256, 64, threads=2)
+            o2.set("tonemap_in", hdr)
+            o2.set_tonemap(a, 0.3, bool(srgb))
+            o2.run("tonemap")
+            got = d.empty(64, 256, 4)
+            capi.check(d.lib.dfx_pass_tonemap(None, C.byref(a), C.c_float(0.3), srgb, C.byref(d.plane(d.up(hdr))), C.byref(d.plane(got)), rows(64)))
+            want = o2.get("ldr")
+            g = d.host(got)
+            assert np.array_equal(g[..., 3], want[..., 3])
+            scale = max(1.0, float(np.abs(want[..., :3]).max()))
+            assert np.abs(g[..., :3] - want[..., :3]).max() <= 2e-5 * scale, (mode, srgb, np.abs(g[..., :3] - want[..., :3]).max())
+
+
+# =====================================================================================================================
+# whole chain through the effect-level objects
+# =====================================================================================================================
+def test_full_chain_four_frames(ctx):
+    from diligentfx_b200.chain import PostProcessChain
+    o, seq, h, w = ctx["o"], ctx["seq"], ctx["h"], ctx["w"]
+    chain = PostProcessChain(w, h)
+    launches0 = chain.lib.dfx_launch_count()
+    for fr in seq:
+        ldr = chain.run_frame(fr)
+    got = ldr.cpu().numpy()
+    assert chain.lib.dfx_launch_count() - launches0 >= 4 * 20, "the chain must launch this library's kernels"
+    cur = ctx["f"] & 1
+    checks = [
+        ("postfx reprojected depth", chain.fetch("postfx", 2), o.get("reproj_depth"), dict(tol=2e-6)),
+        ("ssao output", chain.fetch("ssao", 0), o.get("ssao_out"), dict(tol=2e-3, max_outliers=1e-2, min_psnr=50.0)),
+        ("ssao history length", chain.fetch("ssao", 3) / 16.0, o.get(f"ssao_histlen{cur}") / 16.0, dict(tol=2e-3, max_outliers=1e-2)),
+        ("ssr output", chain.fetch("ssr", 0), o.get("ssr_out"), dict(tol=1e-2, max_outliers=3e-2, min_psnr=40.0, hdr=True)),
+        ("taa accumulation", chain.fetch("taa", 0), o.get(f"taa_accum{cur}"), dict(tol=5e-3, max_outliers=2e-2, min_psnr=45.0, hdr=True)),
+        ("bloom output", chain.fetch("bloom", 0), o.get("bloom_out"), dict(tol=5e-3, max_outliers=2e-2, min_psnr=45.0, hdr=True)),
+    ]
+    for name, g, wnt, kw in checks:
+        print(assert_close(name, g, wnt, **kw))
+    want = o.get("ldr")
+    p = psnr(np.clip(got[..., :3], 0, 1), np.clip(want[..., :3], 0, 1))
+    print(f"full chain LDR PSNR after 4 frames at {w}x{h}: {p:.2f} dB")
+    assert p >= 49.0, "north-star floor: full-chain output within 1 dB of 50 dB PSNR"
+    chain.close()
