@@ -145,10 +145,10 @@ DFX_HD float3 ycocg_to_rgb(float3 c)
     float tmp = c.x - 0.5f * c.z, g = c.z + tmp, b = tmp - 0.5f * c.y, r = b + c.y;
     return make_float3(r, g, b);
 }
-DFX_HD float3 hdr_to_sdr(float3 c) { return make_float3(c.x * (1.0f / (1.0f + c.x)), c.y * (1.0f / (1.0f + c.y)), c.z * (1.0f / (1.0f + c.z))); }
+DFX_HD float3 hdr_to_sdr(float3 c) { return make_float3(c.x * frcp(1.0f + c.x), c.y * frcp(1.0f + c.y), c.z * frcp(1.0f + c.z)); }
 DFX_HD float3 sdr_to_hdr(float3 c)
 {
-    return make_float3(c.x * (1.0f / (1.0f - c.x + kFltEps)), c.y * (1.0f / (1.0f - c.y + kFltEps)), c.z * (1.0f / (1.0f - c.z + kFltEps)));
+    return make_float3(c.x * frcp(1.0f - c.x + kFltEps), c.y * frcp(1.0f - c.y + kFltEps), c.z * frcp(1.0f - c.z + kFltEps));
 }
 DFX_HD float3 max0(float3 c) { return make_float3(fmaxf(c.x, 0.f), fmaxf(c.y, 0.f), fmaxf(c.z, 0.f)); }
 DFX_HD float4 max0(float4 c) { return make_float4(fmaxf(c.x, 0.f), fmaxf(c.y, 0.f), fmaxf(c.z, 0.f), fmaxf(c.w, 0.f)); }
@@ -158,9 +158,9 @@ DFX_HD float3 clip_to_aabb(float3 prev, float3 curr, float3 centre, float3 ext)
 {
     const float  maxT = 10.0f;
     const float3 dir  = curr - prev;
-    const float  ix = ((centre.x - signf(dir.x) * ext.x) - prev.x) / dir.x;
-    const float  iy = ((centre.y - signf(dir.y) * ext.y) - prev.y) / dir.y;
-    const float  iz = ((centre.z - signf(dir.z) * ext.z) - prev.z) / dir.z;
+    const float  ix = fdiv((centre.x - signf(dir.x) * ext.x) - prev.x, dir.x); // x/0 -> +-inf, 0/0 -> NaN as in IEEE division
+    const float  iy = fdiv((centre.y - signf(dir.y) * ext.y) - prev.y, dir.y);
+    const float  iz = fdiv((centre.z - signf(dir.z) * ext.z) - prev.z, dir.z);
     const float  px = lerpf(maxT + 1.0f, ix, ix >= 0.0f ? 1.0f : 0.0f);
     const float  py = lerpf(maxT + 1.0f, iy, iy >= 0.0f ? 1.0f : 0.0f);
     const float  pz = lerpf(maxT + 1.0f, iz, iz >= 0.0f ? 1.0f : 0.0f);
@@ -179,14 +179,26 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
                                                   View<const float4> prev_accum, View<const float2> motion, View<const float> curr_depth,
                                                   View<const float> prev_depth, View<float4> out, int y0, int y1)
 {
+    // 32x8 pixel tile + 1-pixel halo of the current colour, converted ONCE per texel to the clipping space (Reinhard SDR,
+    // optionally YCoCg) and shared through smem: the 3x3 statistics then cost 9 LDS instead of 9 LDG + 9 conversions.
     __shared__ TaaCam S;
+    __shared__ float4 tile[10][34];
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_cam(S.p, &cams[1]);
+    {
+        const int tx0 = blockIdx.x * 32 - 1, ty0 = y0 + blockIdx.y * 8 - 1;
+        for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256)
+        {
+            const int    ly = i / 34, lx = i - ly * 34;
+            const int    gx = min(max(tx0 + lx, 0), curr_color.w - 1), gy = min(max(ty0 + ly, 0), curr_color.h - 1); // ClampScreenCoord
+            const float3 sdr = rgb_to_ycocg<YCOCG>(hdr_to_sdr(max0(xyz(__ldg(&curr_color.at(gx, gy))))));
+            tile[ly][lx]     = f4(sdr, 0.0f);
+        }
+    }
     __syncthreads();
     const CamS& cam = S.c;
     const int   x = blockIdx.x * blockDim.x + threadIdx.x;
     const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out.w || y >= y1) return;
-    const int W = (int)cam.vw, H = (int)cam.vh;
 
     const float posx = float(x) + 0.5f, posy = float(y) + 0.5f;
     float2      mv   = __ldg(&motion.at(x, y));
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
         return;
     }
     const float aspect = cam.vw * cam.ivh;
-    const float mf     = saturate(1.0f - length(make_float2(mv.x * aspect, mv.y)) * 256.0f);
+    const float mf     = saturate(1.0f - fsqrt((mv.x * aspect) * (mv.x * aspect) + mv.y * mv.y) * 256.0f);
 
     // ComputeDepthDisocclusion :117-136 (unclamped loads)
     float depthFactor;
@@ -208,17 +220,18 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
         const int   pix = (int)ppx, piy = (int)ppy;
         const float cd  = __ldg(&curr_depth.at(x, y));
         const float lc  = fabsf(depth_to_camz(cd, cam));
-        float       dis = 0.0f;
+        // max_i exp(-r_i) > 0.9  <=>  min_i r_i < -ln(0.9): the predicate is evaluated without the nine exp()
+        float rmin = kFltMax;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx)
             {
-                const float lp = fabsf(depth_to_camz(load0(prev_depth, pix + dx, piy + dy), S.p));
-                const float w  = expf(-fabsf(lc - lp) / fmaxf(fmaxf(lc, lp), 1e-6f));
-                dis            = fmaxf(dis, w);
+                const float pd = load0(prev_depth, pix + dx, piy + dy);
+                const float lp = fabsf(fdiv(S.p.m32 - pd * S.p.m33, pd * S.p.m23 - S.p.m22));
+                rmin           = fminf(rmin, fdiv(fabsf(lc - lp), fmaxf(fmaxf(lc, lp), 1e-6f)));
             }
-        depthFactor = dis > 0.9f ? 1.0f : 0.0f;
+        depthFactor = rmin < 0.105360516f ? 1.0f : 0.0f;
     }
 
     float4 prevHDR;
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
         const float w12x = w1x + w2x, w12y = w1y + w2y;
         const float t0x = (cx - 1.0f) * cam.ivw, t0y = (cy - 1.0f) * cam.ivh;
         const float t3x = (cx + 2.0f) * cam.ivw, t3y = (cy + 2.0f) * cam.ivh;
-        const float t12x = (cx + w2x / w12x) * cam.ivw, t12y = (cy + w2y / w12y) * cam.ivh;
+        const float t12x = (cx + fdiv(w2x, w12x)) * cam.ivw, t12y = (cy + fdiv(w2y, w12y)) * cam.ivh;
         const float p0 = w12x * w0y, p1 = w0x * w12y, p2 = w12x * w12y, p3 = w3x * w12y, p4 = w12x * w3y;
         float4      r  = make_float4(0.f, 0.f, 0.f, 0.f);
         r = r + sample_linear_clamp(prev_accum, t12x, t0y) * p0;
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
         r = r + sample_linear_clamp(prev_accum, t12x, t12y) * p2;
         r = r + sample_linear_clamp(prev_accum, t3x, t12y) * p3;
         r = r + sample_linear_clamp(prev_accum, t12x, t3y) * p4;
-        prevHDR = max0(r * (1.0f / (p0 + p1 + p2 + p3 + p4)));
+        prevHDR = max0(r * frcp(p0 + p1 + p2 + p3 + p4));
     }
     else
     {
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
 
     const float3 currSDR = rgb_to_ycocg<YCOCG>(hdr_to_sdr(currHDR));
     const float3 prevSDR = rgb_to_ycocg<YCOCG>(hdr_to_sdr(xyz(prevHDR)));
-    auto corrected_alpha = [&](float a) { return fminf(A.TemporalStabilityFactor, saturate(1.0f / (2.0f - a))); };
+    auto corrected_alpha = [&](float a) { return fminf(A.TemporalStabilityFactor, saturate(frcp(2.0f - a))); };
 
     if (A.SkipRejection)
     {
@@ -270,15 +283,15 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
         {
-            const float3 hdr = max0(xyz(__ldg(&curr_color.at(min(max(x + dx, 0), W - 1), min(max(y + dy, 0), H - 1)))));
-            const float3 sdr = rgb_to_ycocg<YCOCG>(hdr_to_sdr(hdr));
-            const float  w   = GAUSS ? expf(-3.0f * float(dx * dx + dy * dy) / ((1.0f + 1.0f) * (1.0f + 1.0f))) : 1.0f;
+            const float3 sdr = xyz(tile[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx]);
+            // exp(-3 r^2 / 4), r^2 in {0, 1, 2}: compile-time constants after unrolling
+            const float  w   = GAUSS ? ((dx * dx + dy * dy) == 0 ? 1.0f : (dx * dx + dy * dy) == 1 ? 0.472366553f : 0.223130160f) : 1.0f;
             m1 = m1 + sdr * w, m2 = m2 + sdr * sdr * w;
             wsum += w;
         }
-    const float3 mean = m1 / wsum;
-    const float3 var  = m2 / wsum - (mean * mean);
-    const float3 sd   = make_float3(sqrtf(fmaxf(var.x, 0.f)), sqrtf(fmaxf(var.y, 0.f)), sqrtf(fmaxf(var.z, 0.f)));
+    const float3 mean = m1 * frcp(wsum);
+    const float3 var  = m2 * frcp(wsum) - (mean * mean);
+    const float3 sd   = make_float3(fsqrt(fmaxf(var.x, 0.f)), fsqrt(fmaxf(var.y, 0.f)), fsqrt(fmaxf(var.z, 0.f)));
     const float3 clipped = clip_to_aabb(prevSDR, currSDR, mean, gamma * sd);
     const float  alpha   = prevHDR.w * mf * depthFactor;
     const float3 o       = sdr_to_hdr(ycocg_to_rgb<YCOCG>(lerp3(currSDR, clipped, alpha)));

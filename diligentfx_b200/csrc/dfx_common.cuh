@@ -199,14 +199,16 @@ __device__ __forceinline__ void load_mat(Mat4& d, const dfx_float4x4& s)
 }
 
 // DepthToCameraZ / CameraZToDepth (ShaderUtilities.fxh:5-39): z = (m32 - d*m33) / (d*m23 - m22)
-DFX_HD float depth_to_camz(float d, const CamS& c) { return (c.m32 - d * c.m33) / (d * c.m23 - c.m22); }
-DFX_HD float camz_to_depth(float z, const CamS& c) { return (c.m22 * z + c.m32) / (c.m23 * z + c.m33); }
+// (MUFU reciprocal + multiply, <= 2 ulp: every pass is issue-bound, and a correctly-rounded division costs ~8x as much)
+DFX_HD float fdiv_(float a, float b) { return __fdividef(a, b); }
+DFX_HD float depth_to_camz(float d, const CamS& c) { return fdiv_(c.m32 - d * c.m33, d * c.m23 - c.m22); }
+DFX_HD float camz_to_depth(float z, const CamS& c) { return fdiv_(c.m22 * z + c.m32, c.m23 * z + c.m33); }
 // ScreenXYDepthToViewSpace (PostFX_Common.fxh:107-111) with TexUVToNormalizedDeviceXY(uv) = (uv - 0.5) * (2, -2)
 DFX_HD float3 screen_to_view(float u, float v, float depth, const CamS& c)
 {
     float z  = depth_to_camz(depth, c);
     float nx = (u - 0.5f) * 2.0f, ny = (v - 0.5f) * -2.0f;
-    return make_float3(z * nx / c.m00, z * ny / c.m11, z);
+    return make_float3(fdiv_(z * nx, c.m00), fdiv_(z * ny, c.m11), z);
 }
 // float4(v,1) * M
 DFX_HD float4 mul_point(float3 v, const Mat4& M)
@@ -226,14 +228,16 @@ DFX_HD float3 mul_dir(float3 v, const Mat4& M)
 DFX_HD float3 project_position(float3 p, const Mat4& M)
 {
     float4 c = mul_point(p, M);
-    float  x = c.x / c.w, y = c.y / c.w, z = c.z / c.w;
+    float  iw = fdiv_(1.0f, c.w);
+    float  x = c.x * iw, y = c.y * iw, z = c.z * iw;
     return make_float3(0.5f + 0.5f * x, 0.5f - 0.5f * y, z);
 }
 // InvProjectPosition (PostFX_Common.fxh:99-105): (u, v, depth) -> position
 DFX_HD float3 inv_project_position(float u, float v, float depth, const Mat4& M)
 {
     float4 c = mul_point(make_float3((u - 0.5f) * 2.0f, (v - 0.5f) * -2.0f, depth), M);
-    return make_float3(c.x / c.w, c.y / c.w, c.z / c.w);
+    float iw = fdiv_(1.0f, c.w);
+    return make_float3(c.x * iw, c.y * iw, c.z * iw);
 }
 
 // Bayer4x4 (PostFX_Common.fxh:57-65)
@@ -264,11 +268,25 @@ DFX_HD Bilin bilinear_uc(float lx, float ly, int w, int h)
     return b;
 }
 
+// Fast (approximate, <= 2 ulp) arithmetic for the issue-bound kernels; used only where the parity budget allows.
+DFX_HD float fdiv(float a, float b) { return __fdividef(a, b); }
+DFX_HD float frcp(float a) { return __fdividef(1.0f, a); }
+DFX_HD float fsqrt(float a)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+DFX_HD float3 fnormalize(float3 a) { return a * rsqrtf(dot(a, a)); }
+
+// The fixed-function sampler resolves the sample position to 8 fractional bits: snap to the nearest 1/256 texel.
+DFX_HD float snap8(float p) { return floorf(p * 256.0f + 0.5f) * (1.0f / 256.0f); }
+
 // bilinear SampleLevel at normalised uv, clamp addressing
 template <class T>
 __device__ __forceinline__ T sample_linear_clamp(const View<const T>& t, float u, float v)
 {
-    float px = u * float(t.w) - 0.5f, py = v * float(t.h) - 0.5f;
+    float px = snap8(u * float(t.w) - 0.5f), py = snap8(v * float(t.h) - 0.5f);
     float fx0 = floorf(px), fy0 = floorf(py);
     int   x0 = (int)fx0, y0 = (int)fy0;
     float fx = px - fx0, fy = py - fy0;
@@ -278,7 +296,7 @@ __device__ __forceinline__ T sample_linear_clamp(const View<const T>& t, float u
 template <class T>
 __device__ __forceinline__ T sample_linear_border(const View<const T>& t, float u, float v)
 {
-    float px = u * float(t.w) - 0.5f, py = v * float(t.h) - 0.5f;
+    float px = snap8(u * float(t.w) - 0.5f), py = snap8(v * float(t.h) - 0.5f);
     float fx0 = floorf(px), fy0 = floorf(py);
     int   x0 = (int)fx0, y0 = (int)fy0;
     float fx = px - fx0, fy = py - fy0;

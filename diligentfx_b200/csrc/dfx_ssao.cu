@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) ssao_prefilter_level_kernel(const dfx_cam
 __device__ __forceinline__ float fast_acos(float v) // :47-53
 {
     float a = fabsf(v);
-    float r = (-0.156583f * a + kHalfPi) * sqrtf(1.0f - a);
+    float r = (-0.156583f * a + kHalfPi) * fsqrt(1.0f - a);
     return v >= 0.0f ? r : kPi - r;
 }
 
@@ -109,17 +109,26 @@ __global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* 
     const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out.w || y >= y1) return;
 
+    // The kernel is issue-bound (18 taps x view-space reconstruction per pixel), not bandwidth-bound, so the arithmetic is
+    // written for instruction count: MUFU reciprocals / rsqrt / sincos, no precise-division or libm slow paths, and the
+    // mip LOD log2() replaced by four squared-length threshold compares (floor(clamp(log2(l) - o, 0, 4) + 0.5) counts the
+    // k in 1..4 with l >= 2^(o + k - 0.5)).
     const float u = (float(x) + 0.5f) * cam.ivw, v = (float(y) + 0.5f) * cam.ivh;
-    const float depth = sample_point_clamp(pyr.lv[0], u, v);
+    const float depth = __ldg(&pyr.lv[0].at(x, y)); // point sample at the pixel centre == Load(x, y)
     if (is_background(depth))
     {
         st_cs(&out.at(x, y), 1.0f);
         return;
     }
-    const float3 nvs = mul_dir(xyz(sample_point_clamp(normal, u, v)), S.view);
-    float3       pvs = screen_to_view(u, v, depth, cam);
+    const float kx = 2.0f * frcp(cam.m00), ky = -2.0f * frcp(cam.m11); // view.xy = z * (uv - 0.5) * (kx, ky)
+    auto to_view = [&](float su, float sv, float d) {
+        const float z = fdiv(cam.m32 - d * cam.m33, d * cam.m23 - cam.m22);
+        return make_float3(z * (su - 0.5f) * kx, z * (sv - 0.5f) * ky, z);
+    };
+    const float3 nvs = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    float3       pvs = to_view(u, v, depth);
     pvs              = pvs + nvs * (0.00001f * pvs.z);
-    const float3 view = -normalize(pvs);
+    const float3 view = -fnormalize(pvs);
     const float2 xi   = __ldg(&noise.at(x & 127, y & 127));
 
     const float effectRadius = A.EffectRadius * A.RadiusMultiplier;
@@ -128,7 +137,16 @@ __global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* 
     const float falloffMul   = -1.0f / falloffRange;
     const float falloffAdd   = falloffFrom / falloffRange + 1.0f;
     float       sampleRadius = 0.5f * effectRadius * cam.m00;
-    if (cam.m33 == 0.0f) sampleRadius /= pvs.z; // perspective
+    if (cam.m33 == 0.0f) sampleRadius = fdiv(sampleRadius, pvs.z); // perspective
+    // squared pixel-length thresholds of mips 1..4
+    float thr2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const float t = exp2f(A.DepthMIPSamplingOffset + float(k + 1) - 0.5f);
+        thr2[k]       = t * t;
+    }
+    const int maxMip = pyr.levels - 1;
 
     float visibility = 0.0f;
 #pragma unroll
@@ -136,18 +154,24 @@ __global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* 
     {
         const float phi = (xi.x + float(slice) / 3.0f) * kPi;
         float       so, co;
-        sincosf(phi, &so, &co);
-        const float3 sliceDir   = make_float3(co, so, 0.0f);
-        const float3 orthoSlice = sliceDir - dot(sliceDir, view) * view;
-        const float3 axis       = normalize(cross(sliceDir, view));
+        __sincosf(phi, &so, &co);
+        // sliceDir = (co, so, 0)
+        const float  sdv        = co * view.x + so * view.y;
+        const float3 orthoSlice = make_float3(co - sdv * view.x, so - sdv * view.y, -sdv * view.z);
+        const float3 axis       = fnormalize(make_float3(so * view.z, -co * view.z, co * view.y - so * view.x)); // cross(sliceDir, view)
         const float3 projN      = nvs - axis * dot(nvs, axis);
-        const float  projNLen   = length(projN);
-        const float  cosNorm    = saturate(dot(projN / projNLen, view));
+        const float  projN2     = dot(projN, projN);
+        const float  invLen     = rsqrtf(projN2);
+        const float  projNLen   = projN2 * invLen;
+        const float  cosNorm    = saturate(dot(projN, view) * invLen);
         const float  N          = signf(dot(orthoSlice, projN)) * fast_acos(cosNorm);
+        float        sinN, cosN;
+        __sincosf(N, &sinN, &cosN);
 
         uint32_t bits = 0u;
-        float    minCos0 = cosf(N + kHalfPi), minCos1 = cosf(N - kHalfPi);
-        float    maxCos0 = minCos0, maxCos1 = minCos1;
+        // cos(N + pi/2) = -sin N ; cos(N - pi/2) = sin N
+        const float minCos0 = -sinN, minCos1 = sinN;
+        float       maxCos0 = minCos0, maxCos1 = minCos1;
 
         float sdx = co * 0.5f * sampleRadius, sdy = so * -0.5f * sampleRadius;
         sdx *= cam.vh * cam.ivw; // aspect-ratio correction
@@ -156,34 +180,38 @@ __global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* 
         for (int s = 0; s < 3; ++s)
         {
             const float noiseS = fracf(xi.y + float(slice + s * 3) * 0.6180339887498948482f);
-            const float smp    = (float(s) + noiseS) / 3.0f;
+            const float smp    = (float(s) + noiseS) * (1.0f / 3.0f);
             const float offx = smp * smp * sdx, offy = smp * smp * sdy;
-            const float lod  = fminf(fmaxf(log2f(length(make_float2(offx * cam.vw, offy * cam.vh))) - A.DepthMIPSamplingOffset, 0.0f), 4.0f);
-            const int   mip  = min((int)floorf(lod + 0.5f), pyr.levels - 1);
+            const float lx = offx * cam.vw, ly = offy * cam.vh, l2 = lx * lx + ly * ly;
+            int         mip = (l2 >= thr2[0]) + (l2 >= thr2[1]) + (l2 >= thr2[2]) + (l2 >= thr2[3]);
+            mip             = min(mip, maxMip);
             const View<const float>& lv = pyr.lv[mip];
+            const float fw = float(lv.w), fh = float(lv.h);
             const float u0 = u + offx, v0 = v + offy, u1 = u - offx, v1 = v - offy;
-            const float3 p0 = screen_to_view(u0, v0, sample_point_clamp(lv, u0, v0), cam);
-            const float3 p1 = screen_to_view(u1, v1, sample_point_clamp(lv, u1, v1), cam);
-            const float3 d0 = p0 - pvs, d1 = p1 - pvs;
+            const int   ax = min(max(__float2int_rd(u0 * fw), 0), lv.w - 1), ay = min(max(__float2int_rd(v0 * fh), 0), lv.h - 1);
+            const int   bx = min(max(__float2int_rd(u1 * fw), 0), lv.w - 1), by = min(max(__float2int_rd(v1 * fh), 0), lv.h - 1);
+            const float da = __ldg(lv.p + (size_t)ay * lv.pitch + ax), db = __ldg(lv.p + (size_t)by * lv.pitch + bx);
+            const float3 d0 = to_view(u0, v0, da) - pvs, d1 = to_view(u1, v1, db) - pvs;
+            const float  q0 = dot(d0, d0), q1 = dot(d1, d1);
+            const float  r0 = rsqrtf(q0), r1 = rsqrtf(q1);
+            const float  l0 = q0 * r0, l1 = q1 * r1; // lengths
+            const float  w0 = saturate(l0 * falloffMul + falloffAdd), w1 = saturate(l1 * falloffMul + falloffAdd);
             if (ALGO == DFX_SSAO_ALGORITHM_VBAO)
             {
                 // ComputeSampleOcclusion :101-119
                 const float3 thick = view * A.BitmaskThickness;
-                const float  w0 = saturate(length(d0) * falloffMul + falloffAdd), w1 = saturate(length(d1) * falloffMul + falloffAdd);
-                float f0 = fast_acos(dot(normalize(d0), view)), b0 = fast_acos(dot(normalize(d0 - thick), view));
-                float f1 = fast_acos(dot(normalize(d1), view)), b1 = fast_acos(dot(normalize(d1 - thick), view));
-                const float nb = -N;
-                f0 = saturate((-f0 - nb + kHalfPi) / kPi), b0 = saturate((-b0 - nb + kHalfPi) / kPi);
-                f1 = saturate((f1 - nb + kHalfPi) / kPi), b1 = saturate((b1 - nb + kHalfPi) / kPi);
+                float f0 = fast_acos(dot(d0, view) * r0), b0 = fast_acos(dot(fnormalize(d0 - thick), view));
+                float f1 = fast_acos(dot(d1, view) * r1), b1 = fast_acos(dot(fnormalize(d1 - thick), view));
+                const float nb = -N, ipi = 1.0f / kPi;
+                f0 = saturate((-f0 - nb + kHalfPi) * ipi), b0 = saturate((-b0 - nb + kHalfPi) * ipi);
+                f1 = saturate((f1 - nb + kHalfPi) * ipi), b1 = saturate((b1 - nb + kHalfPi) * ipi);
                 if (w0 > 0.0f) bits = occluded_sectors(b0, f0, bits);
                 if (w1 > 0.0f) bits = occluded_sectors(f1, b1, bits);
             }
             else
             {
                 // ComputeSampleHorizons :121-130
-                const float l0 = length(d0), l1 = length(d1);
-                const float c0 = dot(d0 / l0, view), c1 = dot(d1 / l1, view);
-                const float w0 = saturate(l0 * falloffMul + falloffAdd), w1 = saturate(l1 * falloffMul + falloffAdd);
+                const float c0 = dot(d0, view) * r0, c1 = dot(d1, view) * r1;
                 maxCos0 = fmaxf(maxCos0, lerpf(minCos0, c0, w0));
                 maxCos1 = fmaxf(maxCos1, lerpf(minCos1, c1, w1));
             }
@@ -191,22 +219,22 @@ __global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* 
 
         if (ALGO == DFX_SSAO_ALGORITHM_VBAO)
         {
-            visibility += 1.0f - float(__popc(bits)) / 32.0f;
+            visibility += 1.0f - float(__popc(bits)) * (1.0f / 32.0f);
         }
         else
         {
             const float h0 = fast_acos(maxCos0), h1 = -fast_acos(maxCos1);
             if (ALGO == DFX_SSAO_ALGORITHM_HBAO)
-                visibility += 0.5f * ((1.0f - cosf(h0)) + (1.0f - cosf(h1))); // IntegrateArcUniform :55-58
+                visibility += 0.5f * ((1.0f - __cosf(h0)) + (1.0f - __cosf(h1))); // IntegrateArcUniform :55-58
             else
             {
                 // IntegrateArcCosWeighted :60-66
-                const float H1 = h0 * 2.0f, H2 = h1 * 2.0f, sinN = sinf(N);
-                visibility += projNLen * 0.25f * ((-cosf(H1 - N) + cosNorm + H1 * sinN) + (-cosf(H2 - N) + cosNorm + H2 * sinN));
+                const float H1 = h0 * 2.0f, H2 = h1 * 2.0f;
+                visibility += projNLen * 0.25f * ((-__cosf(H1 - N) + cosNorm + H1 * sinN) + (-__cosf(H2 - N) + cosNorm + H2 * sinN));
             }
         }
     }
-    st_cs(&out.at(x, y), visibility / 3.0f);
+    st_cs(&out.at(x, y), visibility * (1.0f / 3.0f));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -275,9 +303,9 @@ __global__ void __launch_bounds__(256) ssao_temporal_kernel(const dfx_camera_att
                 m1 += s;
                 m2 += s * s;
             }
-        const float mean = m1 / 9.0f;
-        const float var  = (m2 / 9.0f) - (mean * mean);
-        const float sd   = sqrtf(fmaxf(var, 0.0f));
+        const float mean = m1 * (1.0f / 9.0f);
+        const float var  = (m2 * (1.0f / 9.0f)) - (mean * mean);
+        const float sd   = fsqrt(fmaxf(var, 0.0f));
 
         const float aspect = cam.vw * cam.ivh;
         const float mf     = saturate(1.025f - length(make_float2(mv.x * aspect, mv.y)) * 128.0f);
@@ -386,6 +414,9 @@ __constant__ float3 kPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0
                                     {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
                                     {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
 
+// exp(-z^2 / (2 * 0.9^2)) for the eight disk samples (the shader evaluates this constant expression per tap)
+__constant__ float kPoisson8Weight[8] = {0.77283178f, 0.570022457f, 0.838854363f, 0.769187387f, 0.758268871f, 0.940613337f, 0.613583686f, 0.650469323f};
+
 __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
                                                            View<const float> occlusion, View<const float> history, View<const float> depth,
                                                            View<const float4> normal, View<float> out, int y0, int y1)
@@ -400,20 +431,27 @@ __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attr
     const float hist = __ldg(&history.at(x, y));
     const float d    = __ldg(&depth.at(x, y));
     const float occC = __ldg(&occlusion.at(x, y));
-    const float acc  = powf(fabsf((hist - 1.0f) / 8.0f), 0.2f);
-    if (is_background(d) || acc >= 1.0f)
+    // acc = |(hist-1)/8|^0.2 >= 1  <=>  |hist-1| >= 8: decide the early-out without the pow
+    const float hq = fabsf((hist - 1.0f) / 8.0f);
+    if (is_background(d) || hq >= 1.0f)
     {
         st_cs(&out.at(x, y), lerpf(1.0f, occC, A.AlphaInterpolation));
         return;
     }
+    const float  acc = __powf(hq, 0.2f);
     const int    W = (int)cam.vw, H = (int)cam.vh;
     const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
-    const float3 pvs  = screen_to_view(posx * cam.ivw, posy * cam.ivh, d, cam);
+    const float  kx = 2.0f * frcp(cam.m00), ky = -2.0f * frcp(cam.m11);
+    auto to_view = [&](float su, float sv, float dd) {
+        const float z = fdiv(cam.m32 - dd * cam.m33, dd * cam.m23 - cam.m22);
+        return make_float3(z * (su - 0.5f) * kx, z * (sv - 0.5f) * ky, z);
+    };
+    const float3 pvs  = to_view(posx * cam.ivw, posy * cam.ivh, d);
     const float3 nvs  = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
     float        rs, rc;
-    sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
+    __sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
     const float radius    = lerpf(0.0f, A.SpatialReconstructionRadius, 1.0f - saturate(acc));
-    const float planeNorm = 10.0f / (1.0f + depth_to_camz(d, cam));
+    const float planeNorm = fdiv(10.0f, 1.0f + pvs.z);
 
     float osum = 0.0f, wsum = 0.0f;
 #pragma unroll
@@ -424,8 +462,8 @@ __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attr
         const float xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
         const int   sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
         const float sd = __ldg(&depth.at(sx, sy)), so = __ldg(&occlusion.at(sx, sy));
-        const float3 svs = screen_to_view((float(sx) + 0.5f) * cam.ivw, (float(sy) + 0.5f) * cam.ivh, sd, cam);
-        const float  ws  = expf(-(P.z * P.z) / (2.0f * 0.9f * 0.9f));
+        const float3 svs = to_view((float(sx) + 0.5f) * cam.ivw, (float(sy) + 0.5f) * cam.ivh, sd);
+        const float  ws  = kPoisson8Weight[i]; // exp(-z^2 / (2 * 0.9^2)), ComputeSpatialWeight with SSAO_SPATIAL_RECONSTRUCTION_SIGMA
         const float  wz  = geometry_weight(pvs, svs, nvs, planeNorm);
         osum += ws * wz * so;
         wsum += ws * wz;

@@ -272,6 +272,7 @@ __constant__ float3 kSsrPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, 
                                        {-0.3487388f, +0.4037880f, +0.5335386f}, {+0.1023042f, +0.6439373f, +0.6520134f},
                                        {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
                                        {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+__constant__ float kSsrPoisson8Weight[8] = {0.77283178f, 0.570022457f, 0.838854363f, 0.769187387f, 0.758268871f, 0.940613337f, 0.613583686f, 0.650469323f};
 struct SpatialCam
 {
     CamS c;
@@ -297,12 +298,18 @@ __global__ void __launch_bounds__(256) ssr_spatial_kernel(const dfx_camera_attri
     const float3 camPos = make_float3(cam.px, cam.py, cam.pz);
     const float3 pws = inv_project_position(posx * cam.ivw, posy * cam.ivh, __ldg(&depth.at(x, y)), S.vp_inv);
     const float3 nws = xyz(__ldg(&normal.at(x, y)));
-    const float3 vws = normalize(camPos - pws);
+    const float3 toCam = camPos - pws;
+    const float  camDist2 = dot(toCam, toCam), invCamDist = rsqrtf(camDist2);
+    const float3 vws = toCam * invCamDist;
     const float  NdotV = saturate(dot(nws, vws));
     const float  rough = __ldg(&roughness.at(x, y));
     const float  radius = lerpf(0.0f, A.SpatialReconstructionRadius, saturate(5.0f * rough));
     float        rs, rc;
-    sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
+    __sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
+    // per-pixel invariants of SmithGGXVisibilityCorrelated / NormalDistribution_GGX (PBR_Common.fxh:107-124, :181-195)
+    const float a    = rough * rough, a2 = a * a;
+    const float ad   = fmaxf(a, 1e-3f), ad2 = ad * ad;
+    const float visV = NdotV * NdotV * (1.0f - a2) + a2; // under the sqrt of GGXV
 
     float4 colorSum = make_float4(0.f, 0.f, 0.f, 0.f);
     float  wsum = 0.0f, variance = 0.0f, mean = 0.0f, nearest = 0.0f;
@@ -312,24 +319,27 @@ __global__ void __launch_bounds__(256) ssr_spatial_kernel(const dfx_camera_attri
         const float3 P  = kSsrPoisson8[i];
         const float  xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
         const int    sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
-        const float  ws = expf(-(P.z * P.z) / (2.0f * 0.9f * 0.9f));
+        const float  ws = kSsrPoisson8Weight[i]; // exp(-z^2 / (2 * 0.9^2)), a constant per disk sample
         // ComputeWeightRayLength :60-86
         float        weight, raylen;
         const float4 rd = __ldg(&raydir.at(sx, sy));
-        const float  len = length(xyz(rd));
-        if (len < 1e-6f)
+        const float  len2 = dot(xyz(rd), xyz(rd)), invLen = rsqrtf(len2), len = len2 * invLen;
+        if (!(len >= 1e-6f)) // also catches len2 == 0 (0 * inf = NaN)
         {
             weight = 1e-6f, raylen = 1e-6f;
         }
         else
         {
-            const float3 L  = xyz(rd) / len;
-            const float  a  = rough * rough;
-            const float3 Hh = normalize(L + vws);
+            const float3 L  = xyz(rd) * invLen;
+            const float3 Hh = fnormalize(L + vws);
             const float  NdotH = saturate(dot(nws, Hh)), NdotL = saturate(dot(nws, L));
-            float        brdf  = smith_ggx_visibility_correlated(NdotL, NdotV, a) * ndf_ggx(NdotH, a) * NdotL;
-            brdf *= ws;
-            weight = fmaxf(brdf / fmaxf(rd.w, 1e-5f), 1e-6f);
+            const float  ggxv = NdotL * fsqrt(fmaxf(visV, 1e-7f));
+            const float  ggxl = NdotV * fsqrt(fmaxf(NdotL * NdotL * (1.0f - a2) + a2, 1e-7f));
+            const float  f    = NdotH * NdotH * ad2 + (1.0f - NdotH * NdotH);
+            // Vis * D * NdotL * ws / max(pdf, 1e-5)
+            const float  num = 0.5f * ad2 * NdotL * ws;
+            const float  den = (ggxv + ggxl) * fmaxf(3.141592653589793f * f * f, 1e-9f) * fmaxf(rd.w, 1e-5f);
+            weight = fmaxf(fdiv(num, den), 1e-6f);
             raylen = len;
         }
         const float4 c = __ldg(&radiance.at(sx, sy));
@@ -337,15 +347,14 @@ __global__ void __launch_bounds__(256) ssr_spatial_kernel(const dfx_camera_attri
         colorSum = colorSum + weight * c;
         wsum += weight;
         const float value = luminance(xyz(c)), prevMean = mean;
-        mean += weight * (1.0f / wsum) * (value - prevMean);
+        mean += weight * frcp(wsum) * (value - prevMean);
         variance += weight * (value - prevMean) * (value - mean);
         if (weight > 1.0e-6f) nearest = fmaxf(raylen, nearest);
     }
-    const float den = fmaxf(wsum, 1e-6f);
-    out_rad.at(x, y) = colorSum / den;
-    out_var.at(x, y) = variance / den;
-    const float3 dd  = camPos - pws;
-    out_depth.at(x, y) = camz_to_depth(length(dd) + nearest, cam);
+    const float iden = frcp(fmaxf(wsum, 1e-6f));
+    out_rad.at(x, y) = colorSum * iden;
+    out_var.at(x, y) = variance * iden;
+    out_depth.at(x, y) = camz_to_depth(camDist2 * invCamDist + nearest, cam);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -358,11 +367,15 @@ struct SsrTemporalCam
     float pjx, pjy;
 };
 
-DFX_HD float disocclusion(float cz, float pz) // :111-116
+// ComputeDisocclusion :111-116 is exp(-r) with r = |cz - pz| / max(|cz|, |pz|, 1e-6); it is only ever compared with a
+// threshold T, and exp(-r) > T  <=>  r < -ln(T), so the kernels evaluate r and compare against -ln(T).
+DFX_HD float disocclusion_ratio(float cz, float pz)
 {
     cz = fabsf(cz), pz = fabsf(pz);
-    return expf(-fabsf(cz - pz) / fmaxf(fmaxf(cz, pz), 1e-6f));
+    return fdiv(fabsf(cz - pz), fmaxf(fmaxf(cz, pz), 1e-6f));
 }
+constexpr float kNegLn090 = 0.105360516f; // -ln(SSR_DISOCCLUSION_THRESHOLD)
+constexpr float kNegLn045 = 0.798507696f; // -ln(SSR_DISOCCLUSION_THRESHOLD / 2)
 
 __global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                            View<const uint8_t> mask, View<const float2> motion, View<const float> hit_depth,
@@ -397,9 +410,9 @@ __global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attr
             const float4 s = __ldg(&curr_rad.at(min(max(x + dx, 0), W - 1), min(max(y + dy, 0), H - 1)));
             m1 = m1 + s, m2 = m2 + s * s;
         }
-    const float4 mean = m1 / 9.0f;
-    const float4 var  = (m2 / 9.0f) - (mean * mean);
-    const float4 sd   = make_float4(sqrtf(fmaxf(var.x, 0.f)), sqrtf(fmaxf(var.y, 0.f)), sqrtf(fmaxf(var.z, 0.f)), sqrtf(fmaxf(var.w, 0.f)));
+    const float4 mean = m1 * (1.0f / 9.0f);
+    const float4 var  = (m2 * (1.0f / 9.0f)) - (mean * mean);
+    const float4 sd   = make_float4(fsqrt(fmaxf(var.x, 0.f)), fsqrt(fmaxf(var.y, 0.f)), fsqrt(fmaxf(var.z, 0.f)), fsqrt(fmaxf(var.w, 0.f)));
 
     const float depth = __ldg(&curr_depth.at(x, y));
     const float hitD  = __ldg(&hit_depth.at(x, y));
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attr
     {
         const float pz = depth_to_camz(load0(prev_depth, (int)ppx, (int)ppy), S.p);
         rcol           = sample_linear_clamp(prev_rad, ppx * cam.ivw, ppy * cam.ivh);
-        ok             = disocclusion(currZ, pz) > 0.9f;
+        ok             = disocclusion_ratio(currZ, pz) < kNegLn090;
     }
     if (!ok)
     {
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attr
             {
                 const float lx = ppx + float(dx), ly = ppy + float(dy);
                 const Bilin b  = bilinear_uc(lx, ly, curr_depth.w, curr_depth.h);
-                auto pass = [&](int sx, int sy) { return disocclusion(currZ, depth_to_camz(load0(prev_depth, sx, sy), S.p)) > 0.45f ? 1.0f : 0.0f; };
+                auto pass = [&](int sx, int sy) { return disocclusion_ratio(currZ, depth_to_camz(load0(prev_depth, sx, sy), S.p)) < kNegLn045 ? 1.0f : 0.0f; };
                 const float w00 = b.w00 * pass(b.x0, b.y0), w10 = b.w10 * pass(b.x1, b.y0), w01 = b.w01 * pass(b.x0, b.y1), w11 = b.w11 * pass(b.x1, b.y1);
                 const float tot = w00 * 1.0f + w10 * 1.0f + w01 * 1.0f + w11 * 1.0f;
                 if (tot > best)
@@ -503,8 +516,11 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     const float rough = __ldg(&roughness.at(x, y));
     const float var   = __ldg(&variance.at(x, y));
     const float3 nws  = xyz(__ldg(&normal.at(x, y)));
-    const float  camZ = depth_to_camz(__ldg(&depth.at(x, y)), cam);
-    auto         cz   = [&](int sx, int sy) { return depth_to_camz(loadc(depth, sx, sy), cam); };
+    // The depth edge-stopping weight exp(-|dz| / (|grad . d| + 1e-6)) divides by a quantity that is ~0 on flat surfaces, so it
+    // amplifies the last bits of the camera-space Z: this pass keeps the correctly-rounded division for Z.
+    auto         camz_precise = [&](float dpt) { return (cam.m32 - dpt * cam.m33) / (dpt * cam.m23 - cam.m22); };
+    const float  camZ = camz_precise(__ldg(&depth.at(x, y)));
+    auto         cz   = [&](int sx, int sy) { return camz_precise(loadc(depth, sx, sy)); };
     const float  gx = cz(x | 1, y) - cz(x & ~1, y), gy = cz(x, y | 1) - cz(x, y & ~1);
 
     const float target = saturate(8.0f * rough);
@@ -516,6 +532,7 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     {
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         float  wsum = 0.0f;
+        const float inv_sigma2 = frcp(sigma * sigma);
         for (int dx = -er; dx <= er; ++dx)
             for (int dy = -er; dy <= er; ++dy)
             {
@@ -525,11 +542,13 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
                 {
                     const float4 srad = __ldg(&radiance.at(sx, sy));
                     const float3 sn   = xyz(__ldg(&normal.at(sx, sy)));
-                    const float  sz   = depth_to_camz(sd, cam);
+                    const float  sz   = camz_precise(sd);
                     const float  fx = float(dx), fy = float(dy);
-                    const float  ws = expf(-0.5f * (fx * fx + fy * fy) / (sigma * sigma));
-                    const float  wz = expf(-fabsf(camZ - sz) / (1.0f * (fabsf(fx * gx + fy * gy) + 1e-6f)));
-                    const float  wn = powf(fmaxf(0.0f, dot(nws, sn)), 128.0f);
+                    const float  ws = __expf(-0.5f * (fx * fx + fy * fy) * inv_sigma2);
+                    const float  wz = __expf(-fabsf(camZ - sz) / (fabsf(fx * gx + fy * gy) + 1e-6f));
+                    // x^128 by seven squarings (exact to a few ulp, no log/exp round trip)
+                    float        wn = fmaxf(0.0f, dot(nws, sn));
+                    wn *= wn, wn *= wn, wn *= wn, wn *= wn, wn *= wn, wn *= wn, wn *= wn;
                     const float  w  = ws * wn * wz;
                     wsum += w;
                     csum = csum + w * srad;

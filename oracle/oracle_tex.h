@@ -5,7 +5,9 @@
 //   * point / bilinear SampleLevel with clamp or border(0) addressing                      -> sample_*()
 //   * SampleLevel(point-mip sampler, fractional LOD) picks the nearest mip (round half up)  -> nearest_mip()
 //   * render-target storage: fp32 planes (the north-star layout); no UNORM/half/R11G11B10 quantisation.
-// Bilinear weights are exact fp32 (hardware uses ~8 fractional bits; budgeted in the PSNR tolerance).
+// Bilinear SampleLevel positions are snapped to 1/256 texel (8-bit sub-texel precision of the fixed-function sampler);
+// the weights derived from the snapped position are then exact in fp32. Shader-side bilinear arithmetic
+// (GetBilinearSamplingInfoUC) is NOT snapped — it is ordinary fp32 shader math.
 #pragma once
 #include "oracle_math.h"
 #include <vector>
@@ -87,6 +89,11 @@ inline T sample_linear(const Tex<T>& t, float2 uv, Address addr)
 {
     float px = uv.x * float(t.w) - 0.5f;
     float py = uv.y * float(t.h) - 0.5f;
+    // fixed-function samplers resolve the sample position to 8 fractional bits (D3D11 functional spec, texture
+    // coordinate / filter-weight precision): snap to the nearest 1/256 texel. Taps aimed at texel centres or texel
+    // corners therefore get exact weights (1, or 1/2-1/2), as they do on the reference's GPUs.
+    px = std::floor(px * 256.0f + 0.5f) * (1.0f / 256.0f);
+    py = std::floor(py * 256.0f + 0.5f) * (1.0f / 256.0f);
     float fx0 = std::floor(px), fy0 = std::floor(py);
     int   x0 = int(fx0), y0 = int(fy0);
     float fx = px - fx0, fy = py - fy0;
