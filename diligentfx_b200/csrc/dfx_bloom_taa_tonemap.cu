@@ -44,8 +44,8 @@ DFX_HD Taps13 taps13(const View<const float4>& in, float u, float v)
 // B1: Bloom_ComputePrefilteredTexture.fx:37-83 — 13 taps in 5 Karis-weighted groups, soft-knee threshold
 __global__ void __launch_bounds__(256) bloom_prefilter_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
     const float  u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
     const Taps13 t = taps13(in, u, v);
@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(256) bloom_prefilter_kernel(dfx_bloom_attribs 
 // B2: Bloom_ComputeDownsampledTexture.fx:11-41 — 13-tap downsample, weights 1/32, 1/16, 1/8
 __global__ void __launch_bounds__(256) bloom_downsample_kernel(View<const float4> in, View<float4> out, int y0, int y1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
     const float  u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
     const Taps13 t = taps13(in, u, v);
@@ -106,8 +106,8 @@ DFX_HD float3 tent9(const View<const float4>& lo, float u, float v)
 // B3: Bloom_ComputeUpsampledTexture.fx:20-54 (uInstID == 0): same-level downsample + 3x3 tent of the coarser level
 __global__ void __launch_bounds__(256) bloom_upsample_kernel(View<const float4> same, View<const float4> coarser, View<float4> out, int y0, int y1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
     const float  u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
     const float3 s = tent9(coarser, u, v);
@@ -119,13 +119,132 @@ __global__ void __launch_bounds__(256) bloom_upsample_kernel(View<const float4> 
 __global__ void __launch_bounds__(256) bloom_composite_kernel(dfx_bloom_attribs A, View<const float4> color, View<const float4> up0,
                                                               View<float4> out, int y0, int y1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
     const float  u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
     const float3 s = tent9(up0, u, v);
     const float3 c = tap3<false>(color, u, v);
     st_cs(&out.at(x, y), f4(lerp3(c, c + A.Intensity * s, A.AlphaInterpolation), 0.0f));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact-2:1 fast paths. When the finer plane is exactly twice the coarser one in both dimensions (every large level of the
+// pyramid: 3840x2160 -> 1920x1080 -> 960x540 -> 480x270 -> 240x135), all sample positions fall on texel corners
+// (down-sampling) or on quarter-texel offsets (up-sampling), exactly representable in the sampler's 8 sub-texel bits. The
+// bilinear weights are then the constants 1/4 (corner average) resp. {1/4, 3/4}, so the taps can be evaluated from a
+// shared-memory tile of the source with fixed weights instead of 13x4 / 9x4 gathered texels per pixel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDnTileW = 68, kDnTileH = 20; // source texels staged for a 32x8 output tile of B1/B2: (2*32 + 4) x (2*8 + 4)
+constexpr int kDnCornW = 67, kDnCornH = 19; // texel corners inside that tile
+
+// B1 / B2 on an exact 2:1 level. Stage 1: the CTA stages the 68x20 source tile (out-of-range texels = 0: border addressing).
+// Stage 2: the 67x19 corner averages (each bilinear tap of the shader IS one corner average). Stage 3: 13 taps per output.
+template <bool PREFILTER>
+__global__ void __launch_bounds__(256) bloom_down2x_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1)
+{
+    __shared__ float4 tile[kDnTileH][kDnTileW];
+    __shared__ float4 corner[kDnCornH][kDnCornW];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int ox0 = blockIdx.x * 32, oy0 = y0 + blockIdx.y * 8;
+    const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;
+    for (int i = tid; i < kDnTileW * kDnTileH; i += 256)
+    {
+        const int ly = i / kDnTileW, lx = i - ly * kDnTileW;
+        tile[ly][lx] = load0(in, sx0 + lx, sy0 + ly);
+    }
+    __syncthreads();
+    for (int i = tid; i < kDnCornW * kDnCornH; i += 256)
+    {
+        const int    ly = i / kDnCornW, lx = i - ly * kDnCornW;
+        const float4 a = tile[ly][lx], b = tile[ly][lx + 1], c = tile[ly + 1][lx], d = tile[ly + 1][lx + 1];
+        corner[ly][lx] = (a * 0.25f + b * 0.25f) + (c * 0.25f + d * 0.25f);
+    }
+    __syncthreads();
+    const int x = ox0 + threadIdx.x, y = oy0 + threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+    // output centre = corner (2*lx + 2, 2*ly + 2) of the tile; tap offset (i, j) texels -> corner (cx + i, cy + j)
+    const int cx = 2 * threadIdx.x + 2, cy = 2 * threadIdx.y + 2;
+    auto      T  = [&](int i, int j) { return xyz(corner[cy + j][cx + i]); };
+    const float3 tA = T(-2, +2), tB = T(0, +2), tC = T(+2, +2), tD = T(-2, 0), tE = T(0, 0), tF = T(+2, 0), tG = T(-2, -2), tH = T(0, -2), tI = T(+2, -2);
+    const float3 tJ = T(-1, +1), tK = T(+1, +1), tL = T(-1, -1), tM = T(+1, -1);
+    if (!PREFILTER)
+    {
+        float3 o = make_float3(0.f, 0.f, 0.f);
+        o = o + (tA + tC + tG + tI) * 0.03125f;
+        o = o + (tB + tD + tF + tH) * 0.0625f;
+        o = o + (tE + tJ + tK + tL + tM) * 0.125f;
+        out.at(x, y) = f4(o, 0.0f);
+        return;
+    }
+    float3 g[5];
+    g[0] = (tA + tB + tD + tE) * 0.25f;
+    g[1] = (tB + tC + tE + tF) * 0.25f;
+    g[2] = (tD + tE + tG + tH) * 0.25f;
+    g[3] = (tE + tF + tH + tI) * 0.25f;
+    g[4] = (tJ + tK + tL + tM) * 0.25f;
+    float3 csum = make_float3(0.f, 0.f, 0.f);
+    float  wsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+    {
+        const float w = (i == 4 ? 0.5f : 0.125f) * frcp(1.0f + luminance(g[i]));
+        csum = csum + g[i] * w;
+        wsum += w;
+    }
+    const float3 c = csum * frcp(wsum + 1.0e-5f);
+    const float brightness = fmaxf(c.x, fmaxf(c.y, c.z));
+    const float knee       = A.Threshold * A.SoftTreshold;
+    float       soft       = fminf(fmaxf(brightness - A.Threshold + knee, 0.0f), 2.0f * knee);
+    soft                   = soft * soft * 0.25f * frcp(knee + 1.0e-5f);
+    const float contribution = fmaxf(soft, brightness - A.Threshold) * frcp(fmaxf(brightness, 1.0e-5f));
+    out.at(x, y) = f4(c * contribution, 0.0f);
+}
+
+// B3 / B4 on an exact 1:2 level: the 3x3 tent of bilinear taps of the coarser level collapses to a separable 4-tap filter
+// whose weights depend only on the parity of the output coordinate:
+//   even x = 2k : texels k-2..k+1 weigh (1, 5, 7, 3)/16      odd x = 2k+1 : texels k-1..k+2 weigh (3, 7, 5, 1)/16
+// (position x/2 - 1/4 resp. + 1/4 -> bilinear {1/4, 3/4}, convolved with the tent {1/4, 1/2, 1/4}). Clamp addressing is
+// applied when the 20x8 coarse tile is staged. COMPOSITE selects B4 (lerp with Intensity) instead of B3 (plain add).
+template <bool COMPOSITE>
+__global__ void __launch_bounds__(256) bloom_up2x_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out, int y0, int y1)
+{
+    // A CTA of 256 threads produces 64x16 outputs; every thread a 2x2 block that shares one 5x5 coarse footprint, so the
+    // shared-memory traffic is 25 LDS.128 per four outputs (the kernel would otherwise be bound by smem bandwidth, not HBM).
+    __shared__ float4 tile[12][36];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int ox0 = blockIdx.x * 64, oy0 = y0 + blockIdx.y * 16; // y0 is even for whole-level launches (checked by the caller)
+    const int cx0 = (ox0 >> 1) - 2, cy0 = (oy0 >> 1) - 2;
+    for (int i = tid; i < 12 * 36; i += 256)
+    {
+        const int ly = i / 36, lx = i - ly * 36;
+        tile[ly][lx] = loadc(coarser, cx0 + lx, cy0 + ly);
+    }
+    __syncthreads();
+    const int x = ox0 + 2 * threadIdx.x, y = oy0 + 2 * threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+    float3 E[5], O[5]; // per coarse row: the horizontal 4-tap result for the even / odd output column
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+    {
+        const float3 c0 = xyz(tile[threadIdx.y + j][threadIdx.x]), c1 = xyz(tile[threadIdx.y + j][threadIdx.x + 1]), c2 = xyz(tile[threadIdx.y + j][threadIdx.x + 2]);
+        const float3 c3 = xyz(tile[threadIdx.y + j][threadIdx.x + 3]), c4 = xyz(tile[threadIdx.y + j][threadIdx.x + 4]);
+        E[j] = c0 * (1.f / 16) + c1 * (5.f / 16) + c2 * (7.f / 16) + c3 * (3.f / 16);
+        O[j] = c1 * (3.f / 16) + c2 * (7.f / 16) + c3 * (5.f / 16) + c4 * (1.f / 16);
+    }
+    const float3 s00 = E[0] * (1.f / 16) + E[1] * (5.f / 16) + E[2] * (7.f / 16) + E[3] * (3.f / 16);
+    const float3 s10 = O[0] * (1.f / 16) + O[1] * (5.f / 16) + O[2] * (7.f / 16) + O[3] * (3.f / 16);
+    const float3 s01 = E[1] * (3.f / 16) + E[2] * (7.f / 16) + E[3] * (5.f / 16) + E[4] * (1.f / 16);
+    const float3 s11 = O[1] * (3.f / 16) + O[2] * (7.f / 16) + O[3] * (5.f / 16) + O[4] * (1.f / 16);
+    auto emit = [&](int px, int py, float3 s) {
+        if (px >= out.w || py >= y1) return;
+        const float3 c = xyz(__ldg(&fine.at(px, py))); // linear sampler at the texel centre == the texel
+        if (COMPOSITE)
+            st_cs(&out.at(px, py), f4(lerp3(c, c + A.Intensity * s, A.AlphaInterpolation), 0.0f));
+        else
+            out.at(px, py) = f4(c + s, 0.0f);
+    };
+    emit(x, y, s00), emit(x + 1, y, s10), emit(x, y + 1, s01), emit(x + 1, y + 1, s11);
 }
 
 // =====================================================================================================================
@@ -250,12 +369,26 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
         const float t3x = (cx + 2.0f) * cam.ivw, t3y = (cy + 2.0f) * cam.ivh;
         const float t12x = (cx + fdiv(w2x, w12x)) * cam.ivw, t12y = (cy + fdiv(w2y, w12y)) * cam.ivh;
         const float p0 = w12x * w0y, p1 = w0x * w12y, p2 = w12x * w12y, p3 = w3x * w12y, p4 = w12x * w3y;
-        float4      r  = make_float4(0.f, 0.f, 0.f, 0.f);
-        r = r + sample_linear_clamp(prev_accum, t12x, t0y) * p0;
-        r = r + sample_linear_clamp(prev_accum, t0x, t12y) * p1;
-        r = r + sample_linear_clamp(prev_accum, t12x, t12y) * p2;
-        r = r + sample_linear_clamp(prev_accum, t3x, t12y) * p3;
-        r = r + sample_linear_clamp(prev_accum, t12x, t3y) * p4;
+        // The five bilinear taps touch 12 texels, not 20: the "0" and "3" coordinates are exact texel centres (after the
+        // sampler's 1/256 snap their second bilinear weight is exactly 0), only the "12" coordinate blends two texels.
+        const int   PW = prev_accum.w, PH = prev_accum.h;
+        const float fpw = float(PW), fph = float(PH);
+        const float sx12 = snap8(t12x * fpw - 0.5f), sy12 = snap8(t12y * fph - 0.5f);
+        const float bx = floorf(sx12), by = floorf(sy12);
+        const float qx = sx12 - bx, qy = sy12 - by; // weights of the right / lower texel of the "12" pair
+        auto cxi = [&](int v) { return min(max(v, 0), PW - 1); };
+        auto cyi = [&](int v) { return min(max(v, 0), PH - 1); };
+        const int xa = cxi((int)bx), xb = cxi((int)bx + 1), ya = cyi((int)by), yb = cyi((int)by + 1);
+        const int x0 = cxi((int)rintf(snap8(t0x * fpw - 0.5f))), x3 = cxi((int)rintf(snap8(t3x * fpw - 0.5f)));
+        const int y0i = cyi((int)rintf(snap8(t0y * fph - 0.5f))), y3i = cyi((int)rintf(snap8(t3y * fph - 0.5f)));
+        auto ld = [&](int tx, int ty) { return __ldg(&prev_accum.at(tx, ty)); };
+        auto mixx = [&](int ty) { return ld(xa, ty) * (1.0f - qx) + ld(xb, ty) * qx; };
+        const float4 rowa = mixx(ya), rowb = mixx(yb);
+        float4       r    = mixx(y0i) * p0;                                        // (12, 0)
+        r = r + (ld(x0, ya) * (1.0f - qy) + ld(x0, yb) * qy) * p1;                 // (0, 12)
+        r = r + (rowa * (1.0f - qy) + rowb * qy) * p2;                             // (12, 12)
+        r = r + (ld(x3, ya) * (1.0f - qy) + ld(x3, yb) * qy) * p3;                 // (3, 12)
+        r = r + mixx(y3i) * p4;                                                    // (12, 3)
         prevHDR = max0(r * frcp(p0 + p1 + p2 + p3 + p4));
     }
     else
@@ -304,8 +437,8 @@ __global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __re
 __global__ void __launch_bounds__(256) compose_kernel(View<const float4> color, View<const float4> ssr, View<const float> ao, float ssr_scale,
                                                       float ssao_scale, View<float4> out, int y0, int y1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
     const float4 C = __ldg(&color.at(x, y));
     float3       c = xyz(C);
@@ -486,7 +619,10 @@ extern "C" dfx_status dfx_pass_bloom_prefilter(void* stream, const dfx_bloom_att
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range (rows are in output-plane coordinates)");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
-    bloom_prefilter_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, in, out, rows.y0, rows.y1);
+    if (in.w == 2 * out.w && in.h == 2 * out.h)
+        bloom_down2x_kernel<true><<<grid, block, 0, as_stream(stream)>>>(*attribs, in, out, rows.y0, rows.y1);
+    else
+        bloom_prefilter_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, in, out, rows.y0, rows.y1);
     DFX_LAUNCHED("bloom_prefilter_kernel");
     return DFX_OK;
 }
@@ -500,7 +636,10 @@ extern "C" dfx_status dfx_pass_bloom_downsample(void* stream, const dfx_plane* i
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range (rows are in output-plane coordinates)");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
-    bloom_downsample_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows.y0, rows.y1);
+    if (in.w == 2 * out.w && in.h == 2 * out.h)
+        bloom_down2x_kernel<false><<<grid, block, 0, as_stream(stream)>>>(dfx_bloom_attribs{}, in, out, rows.y0, rows.y1);
+    else
+        bloom_downsample_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows.y0, rows.y1);
     DFX_LAUNCHED("bloom_downsample_kernel");
     return DFX_OK;
 }
@@ -515,7 +654,10 @@ extern "C" dfx_status dfx_pass_bloom_upsample(void* stream, const dfx_plane* sam
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range (rows are in output-plane coordinates)");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
-    bloom_upsample_kernel<<<grid, block, 0, as_stream(stream)>>>(same, lo, out, rows.y0, rows.y1);
+    if (out.w == 2 * lo.w && out.h == 2 * lo.h && (rows.y0 & 1) == 0)
+        bloom_up2x_kernel<false><<<dim3(div_up(out.w, 64), div_up(rows.y1 - rows.y0, 16)), block, 0, as_stream(stream)>>>(dfx_bloom_attribs{}, same, lo, out, rows.y0, rows.y1);
+    else
+        bloom_upsample_kernel<<<grid, block, 0, as_stream(stream)>>>(same, lo, out, rows.y0, rows.y1);
     DFX_LAUNCHED("bloom_upsample_kernel");
     return DFX_OK;
 }
@@ -532,7 +674,10 @@ extern "C" dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_att
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
-    bloom_composite_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, c, u, out, rows.y0, rows.y1);
+    if (out.w == 2 * u.w && out.h == 2 * u.h && (rows.y0 & 1) == 0)
+        bloom_up2x_kernel<true><<<dim3(div_up(out.w, 64), div_up(rows.y1 - rows.y0, 16)), block, 0, as_stream(stream)>>>(*attribs, c, u, out, rows.y0, rows.y1);
+    else
+        bloom_composite_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, c, u, out, rows.y0, rows.y1);
     DFX_LAUNCHED("bloom_composite_kernel");
     return DFX_OK;
 }

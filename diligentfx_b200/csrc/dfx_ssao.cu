@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* 
     __shared__ SsaoCam S;
     stage_cam(S, cams);
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
 
     // The kernel is issue-bound (18 taps x view-space reconstruction per pixel), not bandwidth-bound, so the arithmetic is
@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(256) ssao_temporal_kernel(const dfx_camera_att
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_cam(S.p, &cams[1]);
     __syncthreads();
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out_occ.w || y >= y1) return;
 
     const float depth = __ldg(&curr_depth.at(x, y));
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_att
     __shared__ SsaoCam S;
     stage_cam(S, cams);
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
 
     const float depth = __ldg(&dep.lv[0].at(x, y));
@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attr
     __shared__ SsaoCam S;
     stage_cam(S, cams);
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
 
     const float hist = __ldg(&history.at(x, y));

@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(256) ssr_hiz_level_kernel(View<const float> sr
 __global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, View<const float4> material, View<const float> depth,
                                                        View<float> roughness, View<uint8_t> mask, int y0, int y1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= depth.w || y >= y1) return;
     const float4 m = __ldg(&material.at(x, y));
     float r = A.RoughnessChannel == 0u ? m.x : A.RoughnessChannel == 1u ? m.y : A.RoughnessChannel == 2u ? m.z : A.RoughnessChannel == 3u ? m.w : 0.0f;
@@ -67,6 +67,18 @@ __device__ __forceinline__ float hiz_load(const HizView& h, int x, int y, int mi
 {
     if (mip < 0 || mip >= h.levels) return 0.0f;
     return load0(h.lv[mip], x, y);
+}
+struct __align__(16) HizLevel
+{
+    const float* p;
+    int          pitch;
+    int          wh; // width | height << 16  (0 for a level the pyramid does not have: every Load returns 0)
+};
+__device__ __forceinline__ float hiz_load(const HizLevel* lvl, int x, int y, int mip)
+{
+    const HizLevel L = lvl[mip & (DFX_MAX_MIPS - 1)];
+    const unsigned w = (unsigned)L.wh & 0xFFFFu, hgt = (unsigned)L.wh >> 16;
+    return ((unsigned)x < w && (unsigned)y < hgt) ? __ldg(L.p + (size_t)y * L.pitch + x) : 0.0f;
 }
 
 // PBR_Common.fxh:181-195
@@ -109,6 +121,9 @@ __global__ void __launch_bounds__(256) ssr_intersect_kernel(const dfx_camera_att
                                                             View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1)
 {
     __shared__ IntersectCam S;
+    // Hi-Z level table in shared memory: the march picks a level per iteration, and one 16-byte LDS (pointer, pitch, packed
+    // size) is cheaper than four register-indexed constant-bank loads of the kernel-parameter struct.
+    __shared__ HizLevel lvl[DFX_MAX_MIPS];
     if (threadIdx.x == 0 && threadIdx.y == 0)
     {
         load_cam(S.c, &cams[0]);
@@ -116,10 +131,15 @@ __global__ void __launch_bounds__(256) ssr_intersect_kernel(const dfx_camera_att
         load_mat(S.view_inv, cams[0].mViewInv);
         load_mat(S.proj, cams[0].mProj);
     }
+    if (threadIdx.y == 1 && threadIdx.x < DFX_MAX_MIPS)
+    {
+        const int i = threadIdx.x;
+        lvl[i]      = i < hiz.levels ? HizLevel{hiz.lv[i].p, hiz.lv[i].pitch, hiz.lv[i].w | (hiz.lv[i].h << 16)} : HizLevel{nullptr, 0, 0};
+    }
     __syncthreads();
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out_rad.w || y >= y1) return;
     if (!__ldg(&mask.at(x, y)))
     {
@@ -146,23 +166,23 @@ __global__ void __launch_bounds__(256) ssr_intersect_kernel(const dfx_camera_att
     float3 dirVS;
     float  pdf;
     {
-        const float3 V = -normalize(originVS);
+        const float3 V = -fnormalize(originVS);
         const float  a = rough * rough;
         const float3 N = nvs;
-        const float3 T = normalize(cross(N, fabsf(N.y) > 0.5f ? make_float3(1.f, 0.f, 0.f) : make_float3(0.f, 1.f, 0.f)));
+        const float3 T = fnormalize(cross(N, fabsf(N.y) > 0.5f ? make_float3(1.f, 0.f, 0.f) : make_float3(0.f, 1.f, 0.f)));
         const float3 B = cross(T, N);
         float2       xi = __ldg(&noise.at(x & 127, y & 127));
         xi.y            = lerpf(xi.y, 0.0f, A.GGXImportanceSampleBias);
         const float3 Vts = make_float3(dot(T, V), dot(B, V), dot(N, V));
         // SmithGGXSampleVisibleNormalSC (PBR_Common.fxh:278-296) with ax == ay == a
-        const float3 Vs  = normalize(make_float3(Vts.x * a, Vts.y * a, Vts.z));
+        const float3 Vs  = fnormalize(make_float3(Vts.x * a, Vts.y * a, Vts.z));
         const float  phi = 2.0f * 3.141592653589793f * xi.x;
         const float  Z   = (1.0f - xi.y) * (1.0f + Vs.z) - Vs.z;
-        const float  st  = sqrtf(fminf(fmaxf(1.0f - Z * Z, 0.0f), 1.0f));
+        const float  st  = fsqrt(fminf(fmaxf(1.0f - Z * Z, 0.0f), 1.0f));
         float        sp, cp;
-        sincosf(phi, &sp, &cp);
+        __sincosf(phi, &sp, &cp);
         const float3 Hh = make_float3(st * cp, st * sp, Z) + Vs;
-        const float3 Hm = normalize(make_float3(a * Hh.x, a * Hh.y, Hh.z));
+        const float3 Hm = fnormalize(make_float3(a * Hh.x, a * Hh.y, Hh.z));
         // reflect(-Vts, Hm) = -Vts - 2*dot(Hm, -Vts)*Hm
         const float3 I  = -Vts;
         const float3 Lts = I - 2.0f * dot(Hm, I) * Hm;
@@ -201,7 +221,7 @@ __global__ void __launch_bounds__(256) ssr_intersect_kernel(const dfx_camera_att
         while (i < A.MaxTraversalIntersections && mip >= baseMip)
         {
             const float mx = resx * pos.x, my = resy * pos.y;
-            const float surf = hiz_load(hiz, (int)mx, (int)my, mip);
+            const float surf = hiz_load(lvl, (int)mx, (int)my, mip);
             // AdvanceRay :88-136
             const float px = (floorf(mx) + fox) * irx + uox, py = (floorf(my) + foy) * iry + uoy;
             const float tx = px * invD.x - O.x * invD.x, ty = py * invD.y - O.y * invD.y;
@@ -288,8 +308,8 @@ __global__ void __launch_bounds__(256) ssr_spatial_kernel(const dfx_camera_attri
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_mat(S.vp_inv, cams[0].mViewProjInv);
     __syncthreads();
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out_rad.w || y >= y1) return;
     if (!__ldg(&mask.at(x, y))) return;
 
@@ -392,8 +412,8 @@ __global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attr
     }
     __syncthreads();
     const CamS& cam = S.c;
-    const int   x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int   y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out_rad.w || y >= y1) return;
     if (!__ldg(&mask.at(x, y))) return;
 
@@ -504,8 +524,8 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     __shared__ CamS cam;
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(cam, &cams[0]);
     __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
     if (!__ldg(&mask.at(x, y)))
     {
@@ -519,10 +539,6 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     // The depth edge-stopping weight exp(-|dz| / (|grad . d| + 1e-6)) divides by a quantity that is ~0 on flat surfaces, so it
     // amplifies the last bits of the camera-space Z: this pass keeps the correctly-rounded division for Z.
     auto         camz_precise = [&](float dpt) { return (cam.m32 - dpt * cam.m33) / (dpt * cam.m23 - cam.m22); };
-    const float  camZ = camz_precise(__ldg(&depth.at(x, y)));
-    auto         cz   = [&](int sx, int sy) { return camz_precise(loadc(depth, sx, sy)); };
-    const float  gx = cz(x | 1, y) - cz(x & ~1, y), gy = cz(x, y | 1) - cz(x, y & ~1);
-
     const float target = saturate(8.0f * rough);
     const float radius = lerpf(0.0f, var > 0.001f ? 2.0f : 0.0f, target);
     const float sigma  = A.BilateralCleanupSpatialSigmaFactor;
@@ -530,6 +546,10 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     float4      result = __ldg(&radiance.at(x, y));
     if (var > 0.00005f && er > 0)
     {
+        // camera Z and its quad derivatives are only needed by the filter branch
+        const float  camZ = camz_precise(__ldg(&depth.at(x, y)));
+        auto         cz   = [&](int sx, int sy) { return camz_precise(loadc(depth, sx, sy)); };
+        const float  gx = cz(x | 1, y) - cz(x & ~1, y), gy = cz(x, y | 1) - cz(x, y & ~1);
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         float  wsum = 0.0f;
         const float inv_sigma2 = frcp(sigma * sigma);

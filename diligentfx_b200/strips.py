@@ -1,0 +1,191 @@
+"""Row-strip sharding of one frame across the GPUs of a box (BASELINE.json config 4).
+
+Every rank holds FULL-SIZE planes and owns the rows `[y0, y1)` of every plane; the pass-level C-ABI computes only the owned
+rows (`dfx_rows`). Between passes the host exchanges exactly the rows the next pass reads outside its strip:
+
+* bounded reach  -> `exchange_halo`: grouped NCCL send/recv (`torch.distributed.batch_isend_irecv`) of `halo` rows with the
+  upper and lower neighbour, written in place into the receiver's full-size plane;
+* unbounded reach (SSR rays may cross the whole screen and fetch colour / normal at the hit; AO taps scale with 1/z)
+  -> `gather_rows`: every rank sends its strip to every other rank (strips are 64-row aligned, hence unequal, so this is a
+  grouped send/recv too rather than an equal-chunk all-gather).
+
+Because every kernel addresses pixels by their global coordinates in full-size planes, a sharded run reads exactly the
+values a single-GPU run reads: outputs are bit-identical (checked by tests/test_strips_gpu.py on 2 GPUs). The exchange
+helpers are backend-agnostic (`gloo` on CPU tensors in tests/test_strips_cpu.py, `nccl` on device planes in production).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+STRIP_ALIGN = 64  # 2^SSR_DEPTH_HIERARCHY_MAX_MIP: pyramid passes then need no halo (SURVEY.md §8e "Partitioning")
+
+
+def strip_bounds(height: int, world: int, align: int = STRIP_ALIGN) -> list[tuple[int, int]]:
+    """Rows [y0, y1) per rank: boundaries are multiples of `align`, sizes differ by at most `align`; the last strip ends at height."""
+    blocks = -(-height // align)
+    base, extra = divmod(blocks, world)
+    bounds, y = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        y1 = min(height, y + n * align)
+        bounds.append((y, y1))
+        y = y1
+    assert bounds[-1][1] == height
+    return bounds
+
+
+def exchange_halo(planes: list[torch.Tensor], bounds: list[tuple[int, int]], halo: int, group=None) -> None:
+    """In place: after the call rows [y0 - halo, y0) and [y1, y1 + halo) of every plane hold the neighbours' owned rows.
+
+    `planes` are full-size (H, W[, C]) tensors; this rank owns bounds[rank]. Ranks with an empty strip take no part.
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1 or halo <= 0:
+        return
+    y0, y1 = bounds[rank]
+    if y1 <= y0:
+        return
+    ops = []
+    up = next((r for r in range(rank - 1, -1, -1) if bounds[r][1] > bounds[r][0]), None)
+    down = next((r for r in range(rank + 1, world) if bounds[r][1] > bounds[r][0]), None)
+    H = planes[0].shape[0]
+    for p in planes:
+        if up is not None:
+            n_send = min(halo, y1 - y0)
+            n_recv = min(halo, bounds[up][1] - bounds[up][0])
+            ops.append(dist.P2POp(dist.isend, p[y0:y0 + n_send], up, group))
+            ops.append(dist.P2POp(dist.irecv, p[y0 - n_recv:y0], up, group))
+        if down is not None:
+            n_send = min(halo, y1 - y0)
+            n_recv = min(halo, bounds[down][1] - bounds[down][0], H - y1)
+            ops.append(dist.P2POp(dist.isend, p[y1 - n_send:y1], down, group))
+            ops.append(dist.P2POp(dist.irecv, p[y1:y1 + n_recv], down, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def gather_rows(planes: list[torch.Tensor], bounds: list[tuple[int, int]], group=None, row_shift: int = 0) -> None:
+    """In place: after the call every plane is complete on every rank (each rank contributed its owned rows).
+
+    `row_shift` = k gathers level k of a pyramid whose level-0 strips are `bounds` (rows y >> k; the last strip ends at the
+    level's height).
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return
+    ops = []
+    for p in planes:
+        h = p.shape[0]
+
+        def rows_of(r: int) -> tuple[int, int]:
+            a, b = bounds[r]
+            lo = a >> row_shift
+            hi = h if r == world - 1 or bounds[r][1] >= bounds[-1][1] else (b >> row_shift)
+            return lo, max(lo, min(hi, h))
+
+        my = rows_of(rank)
+        for r in range(world):
+            if r == rank:
+                continue
+            theirs = rows_of(r)
+            if my[1] > my[0]:
+                ops.append(dist.P2POp(dist.isend, p[my[0]:my[1]], r, group))
+            if theirs[1] > theirs[0]:
+                ops.append(dist.P2POp(dist.irecv, p[theirs[0]:theirs[1]], r, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class SsrStripRunner:
+    """ScreenSpaceReflection (S1-S7) + the PostFX planes it needs, one frame split into row strips over the ranks of `group`.
+
+    Reach of every pass: P1-P3 +-1 row of depth / motion; S1, S2 none (64-row aligned strips); S4 unbounded
+    (Hi-Z, colour, normal gathered); S5 +-4 rows of the intersect outputs; S6 previous-frame planes at the reprojected
+    position (|motion| is capped at MAX_MOTION_ROWS by the caller) plus +-1 row of the resolved radiance; S7 +-2 rows.
+    """
+
+    MAX_MOTION_ROWS = 24  # reprojection reach (motion + 3x3 search + bilinear footprint) the temporal pass is given
+
+    def __init__(self, width: int, height: int, group=None, device: torch.device | None = None):
+        from . import capi
+        self.capi = capi
+        self.lib = capi.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.w, self.h = width, height
+        self.bounds = strip_bounds(height, self.world)
+        self.rows = capi.Rows(*self.bounds[self.rank])
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        H, W = height, width
+        self.hiz = [None] + [f(max(H >> i, 1), max(W >> i, 1)) for i in range(1, 7)]
+        self.roughness, self.mask = f(H, W), torch.zeros((H, W), dtype=torch.uint8, device=dev)
+        self.radiance, self.raydir = f(H, W, 4), f(H, W, 4)
+        self.res_rad, self.res_var, self.res_depth = f(H, W, 4), f(H, W), f(H, W)
+        self.radhist, self.varhist = [f(H, W, 4), f(H, W, 4)], [f(H, W), f(H, W)]
+        self.out = f(H, W, 4)
+        self.reproj, self.closest, self.prev_depth = f(H, W), f(H, W, 2), f(H, W)
+        self.bn_xy, self.bn_zw = f(128, 128, 2), f(128, 128, 2)
+        blob = open(capi.REPO_ROOT + "/diligentfx_b200/data/blue_noise_tables.bin", "rb").read()
+        self.tables = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        self.cams = torch.zeros(2 * 576, dtype=torch.uint8, device=dev)
+        self.comm_bytes = 0
+
+    def _count(self, planes, rows: int):
+        self.comm_bytes += sum(rows * p[0].numel() * p.element_size() for p in planes)
+
+    def execute(self, frame_index: int, inputs: dict, curr_camera, prev_camera, attribs=None, flags: int = 0) -> torch.Tensor:
+        """`inputs`: full-size device planes depth, prev_depth, motion, normal, color, material of which this rank's strip is
+        valid (everything else is filled in by the exchanges). Returns the SSR output plane (valid on the owned rows)."""
+        capi, L, B, R, g = self.capi, self.lib, self.bounds, self.rows, self.group
+        P = capi.plane_of
+        a = attribs or capi.SSRAttribs.default()
+        s = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        cur, prv = frame_index & 1, (frame_index + 1) & 1
+        self.cams.copy_(torch.frombuffer(bytearray(bytes(curr_camera) + bytes(prev_camera)), dtype=torch.uint8), non_blocking=False)
+        cams = C.c_void_p(self.cams.data_ptr())
+        ck = capi.check
+        depth, motion, normal, color = inputs["depth"], inputs["motion"], inputs["normal"], inputs["color"]
+
+        # PostFX prep: 3x3 closest-depth search -> +-1 row of depth and motion; previous depth: reprojection reach
+        exchange_halo([depth, motion], B, 1, g)
+        exchange_halo([inputs["prev_depth"]], B, self.MAX_MOTION_ROWS, g)
+        ck(L.dfx_pass_blue_noise(s, C.c_void_p(self.tables.data_ptr()), frame_index, C.byref(P(self.bn_xy)), C.byref(P(self.bn_zw))))
+        # the copy of the previous depth has to cover the halo rows the temporal pass will read: widen the row range
+        y0w, y1w = max(R.y0 - self.MAX_MOTION_ROWS, 0), min(R.y1 + self.MAX_MOTION_ROWS, self.h)
+        ck(L.dfx_pass_postfx_prepare(s, cams, C.byref(P(depth)), C.byref(P(inputs["prev_depth"])), C.byref(P(motion)), C.byref(P(self.reproj)),
+                                     C.byref(P(self.closest)), C.byref(P(self.prev_depth)), R))
+        self.prev_depth[y0w:R.y0].copy_(inputs["prev_depth"][y0w:R.y0])
+        self.prev_depth[R.y1:y1w].copy_(inputs["prev_depth"][R.y1:y1w])
+
+        # S1 + S2 on the owned rows, then make Hi-Z / colour / normal complete everywhere for the ray march
+        pyr = capi.pyramid_of([depth] + self.hiz[1:])
+        ck(L.dfx_pass_ssr_hiz(s, C.byref(pyr), R))
+        ck(L.dfx_pass_ssr_mask_roughness(s, C.byref(a), C.byref(P(inputs["material"])), C.byref(P(depth)), C.byref(P(self.roughness)), C.byref(P(self.mask)), R))
+        gather_rows([depth, color, normal] + ([motion] if flags & capi.SSR_FLAG_PREVIOUS_FRAME else []), B, g)
+        for k in range(1, 7):
+            gather_rows([self.hiz[k]], B, g, row_shift=k)
+        # S4
+        ck(L.dfx_pass_ssr_intersect(s, cams, C.byref(a), flags, C.byref(P(color)), C.byref(P(normal)), C.byref(P(self.roughness)), C.byref(P(self.mask)),
+                                    C.byref(P(self.bn_xy)), C.byref(pyr), C.byref(P(motion)), C.byref(P(self.radiance)), C.byref(P(self.raydir)), R))
+        # S5: 8-tap disk of radius <= 4 px
+        exchange_halo([self.radiance, self.raydir], B, 4, g)
+        ck(L.dfx_pass_ssr_spatial(s, cams, C.byref(a), C.byref(P(self.roughness)), C.byref(P(self.mask)), C.byref(P(normal)), C.byref(P(depth)),
+                                  C.byref(P(self.raydir)), C.byref(P(self.radiance)), C.byref(P(self.res_rad)), C.byref(P(self.res_var)),
+                                  C.byref(P(self.res_depth)), R))
+        # S6: 3x3 statistics of the resolved radiance; history of the previous frame at the reprojected position
+        exchange_halo([self.res_rad], B, 1, g)
+        exchange_halo([self.radhist[prv], self.varhist[prv]], B, self.MAX_MOTION_ROWS, g)
+        ck(L.dfx_pass_ssr_temporal(s, cams, C.byref(a), C.byref(P(self.mask)), C.byref(P(motion)), C.byref(P(self.res_depth)), C.byref(P(self.reproj)),
+                                   C.byref(P(self.res_rad)), C.byref(P(self.res_var)), C.byref(P(self.prev_depth)), C.byref(P(self.radhist[prv])),
+                                   C.byref(P(self.varhist[prv])), C.byref(P(self.radhist[cur])), C.byref(P(self.varhist[cur])), R))
+        # S7: (2r+1)^2 window, r <= 2, reads roughness / radiance of the neighbours (normal and depth are already complete)
+        exchange_halo([self.radhist[cur], self.roughness], B, 2, g)
+        ck(L.dfx_pass_ssr_bilateral(s, cams, C.byref(a), C.byref(P(self.mask)), C.byref(P(depth)), C.byref(P(normal)), C.byref(P(self.roughness)),
+                                    C.byref(P(self.radhist[cur])), C.byref(P(self.varhist[cur])), C.byref(P(self.out)), R))
+        return self.out
