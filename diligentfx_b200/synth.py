@@ -203,20 +203,29 @@ def generate_frame(scene: Scene, frame: int, width: int, height: int, prev_depth
                    use_jitter: bool = True, chunk_rows: int = 256) -> dict:
     """Returns dict(depth (H,W) f32, normal (H,W,4), color (H,W,4), material (H,W,4), motion (H,W,2), prev_depth (H,W),
     curr_camera, prev_camera (CameraAttribs))."""
+    return generate_rows(scene, frame, width, height, 0, height, prev_depth, use_jitter, chunk_rows)
+
+
+def generate_rows(scene: Scene, frame: int, width: int, height: int, row0: int, row1: int, prev_depth: np.ndarray | None = None,
+                  use_jitter: bool = True, chunk_rows: int = 256) -> dict:
+    """Rows [row0, row1) of frame `frame` of the full width x height image (arrays have row1 - row0 rows). When `prev_depth`
+    is None the previous frame's depth of the same rows is ray-cast too (frame 0: a copy of the current depth)."""
     cam = make_camera(frame, width, height, use_jitter)
     prev = make_camera(max(frame - 1, 0), width, height, use_jitter)
-    depth = np.empty((height, width), np.float32)
-    normal = np.zeros((height, width, 4), np.float32)
-    color = np.zeros((height, width, 4), np.float32)
-    material = np.zeros((height, width, 4), np.float32)
-    motion = np.empty((height, width, 2), np.float32)
+    nrows = row1 - row0
+    depth = np.empty((nrows, width), np.float32)
+    normal = np.zeros((nrows, width, 4), np.float32)
+    color = np.zeros((nrows, width, 4), np.float32)
+    material = np.zeros((nrows, width, 4), np.float32)
+    motion = np.empty((nrows, width, 2), np.float32)
     light = np.array([0.4, 0.8, -0.45])
     light = light / np.linalg.norm(light)
     nobj = len(scene.radii)
     pvp = prev.view @ prev.proj
-    for y0 in range(0, height, chunk_rows):
-        rows = slice(y0, min(y0 + chunk_rows, height))
-        rc = _raycast(scene, cam, width, height, rows)
+    for g0 in range(row0, row1, chunk_rows):
+        grows = slice(g0, min(g0 + chunk_rows, row1))
+        rows = slice(g0 - row0, grows.stop - row0)
+        rc = _raycast(scene, cam, width, height, grows)
         z = rc["t"]
         p = cam.proj
         d = (z * p[2, 2] + p[3, 2]) / z
@@ -256,7 +265,15 @@ def generate_frame(scene: Scene, frame: int, width: int, height: int, prev_depth
         material[rows, :, 0] = np.where(rc["is_bg"], 1.0, scene.rough[oid]).astype(np.float32)
         material[rows, :, 1] = np.where(obj == nobj, 0.0, 0.5).astype(np.float32)
     if prev_depth is None:
-        prev_depth = depth.copy()
+        if frame == 0:
+            prev_depth = depth.copy()
+        else:
+            prev_depth = np.empty_like(depth)
+            for g0 in range(row0, row1, chunk_rows):
+                grows = slice(g0, min(g0 + chunk_rows, row1))
+                rc = _raycast(scene, prev, width, height, grows)
+                z = rc["t"]
+                prev_depth[g0 - row0:grows.stop - row0] = np.where(rc["is_bg"], 1.0, (z * prev.proj[2, 2] + prev.proj[3, 2]) / z).astype(np.float32)
     return dict(depth=depth, normal=normal, color=color, material=material, motion=motion, prev_depth=prev_depth,
                 curr_camera=cam.attribs, prev_camera=prev.attribs, frame=frame)
 
