@@ -91,9 +91,15 @@ class PostProcessChain:
         return n
 
     # ---- one frame ------------------------------------------------------------------------------------------------
-    def execute(self, frame_index: int, curr_camera, prev_camera, inputs: dict | None = None) -> torch.Tensor:
+    def execute(self, frame_index: int, curr_camera, prev_camera, inputs: dict | None = None, ldr_out: torch.Tensor | None = None) -> torch.Tensor:
         """Runs the chain on device-resident inputs (default: the planes filled by upload()); returns the final LDR plane
-        (device tensor, rgba)."""
+        (device tensor, rgba; `ldr_out` if given)."""
+        if ldr_out is not None:
+            self.ldr, saved = ldr_out, self.ldr
+            try:
+                return self.execute(frame_index, curr_camera, prev_camera, inputs)
+            finally:
+                self.ldr = saved
         L, cfg = self.lib, self.cfg
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         st = cfg.stages
@@ -161,6 +167,49 @@ class PostProcessChain:
         """Public one-call API: host G-buffer in, LDR device plane out (upload + execute)."""
         self.upload(frame)
         return self.execute(frame["frame"], frame["curr_camera"], frame["prev_camera"])
+
+    def stream_frames(self, frames, ldr_host: list | None = None) -> int:
+        """Offline throughput path (BASELINE.json config 5: batches of frames): a double-buffered pipeline over three CUDA
+        streams. While frame k runs on the compute stream, frame k+1's G-buffer is copied from (pinned) host memory on a
+        copy stream and frame k-1's LDR result is copied back on a read-back stream; PCIe is full duplex, so the two copy
+        directions overlap as well.
+
+        `frames`: iterable of frame dicts (host planes + cameras + "frame" index). `ldr_host`: optional list of pinned
+        (H, W, 4) float32 host tensors that receive the results (reused round-robin). Returns the number of frames run.
+        """
+        dev = self.device
+        if not hasattr(self, "_pipe"):
+            mk = lambda: {n: torch.empty_like(t) for n, t in self.inputs.items()}  # noqa: E731
+            self._pipe = dict(inputs=[mk(), mk()], ldr=[torch.empty_like(self.ldr), torch.empty_like(self.ldr)], h2d=torch.cuda.Stream(dev),
+                              d2h=torch.cuda.Stream(dev), h2d_done=[torch.cuda.Event(), torch.cuda.Event()],
+                              compute_done=[torch.cuda.Event(), torch.cuda.Event()], d2h_done=[torch.cuda.Event(), torch.cuda.Event()])
+            for e in self._pipe["compute_done"] + self._pipe["d2h_done"]:
+                e.record(torch.cuda.current_stream(dev))
+        P = self._pipe
+        main = torch.cuda.current_stream(dev)
+        n = 0
+        for k, fr in enumerate(frames):
+            s = k & 1
+            with torch.cuda.stream(P["h2d"]):
+                P["h2d"].wait_event(P["compute_done"][s])          # frame k-2 no longer reads this input set
+                for name in INPUT_SPECS:
+                    src = fr[name]
+                    t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, np.float32))
+                    P["inputs"][s][name].copy_(t, non_blocking=True)
+                P["h2d_done"][s].record(P["h2d"])
+            main.wait_event(P["h2d_done"][s])
+            main.wait_event(P["d2h_done"][s])                        # frame k-2's result has left this LDR buffer
+            self.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], P["inputs"][s], ldr_out=P["ldr"][s])
+            P["compute_done"][s].record(main)
+            if ldr_host:
+                with torch.cuda.stream(P["d2h"]):
+                    P["d2h"].wait_event(P["compute_done"][s])
+                    ldr_host[k % len(ldr_host)].copy_(P["ldr"][s], non_blocking=True)
+                    P["d2h_done"][s].record(P["d2h"])
+            n += 1
+        main.wait_event(P["d2h_done"][0])
+        main.wait_event(P["d2h_done"][1])
+        return n
 
     # ---- debug access to effect-owned planes (parity tests) --------------------------------------------------------
     def fetch(self, effect: str, plane_id: int) -> np.ndarray:

@@ -294,7 +294,7 @@ struct TaaCam
 };
 
 template <bool BICUBIC, bool YCOCG, bool GAUSS>
-__global__ void __launch_bounds__(256) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, View<const float4> curr_color,
+__global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, View<const float4> curr_color,
                                                   View<const float4> prev_accum, View<const float2> motion, View<const float> curr_depth,
                                                   View<const float> prev_depth, View<float4> out, int y0, int y1)
 {

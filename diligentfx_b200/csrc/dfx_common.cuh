@@ -10,6 +10,24 @@
 #include <stdint.h>
 #include "../../include/dfx_b200.h"
 
+// Minimum resident CTAs per SM requested from ptxas for the latency-bound gather kernels (register budget = 65536 /
+// (256 * N)); the values are the measured optimum of round 1 (profiles/r1f_occupancy_sweep.md). Overridable with -D.
+#ifndef DFX_OCC_INTERSECT
+#    define DFX_OCC_INTERSECT 5
+#endif
+#ifndef DFX_OCC_SSR_SPATIAL
+#    define DFX_OCC_SSR_SPATIAL 5
+#endif
+#ifndef DFX_OCC_SSR_TEMPORAL
+#    define DFX_OCC_SSR_TEMPORAL 6
+#endif
+#ifndef DFX_OCC_AO
+#    define DFX_OCC_AO 4
+#endif
+#ifndef DFX_OCC_TAA
+#    define DFX_OCC_TAA 5
+#endif
+
 namespace dfx
 {
 

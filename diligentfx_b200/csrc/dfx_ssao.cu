@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t occluded_sectors(float minH, float maxH, uin
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(256) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
+__global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
                                                       View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1)
 {
     __shared__ SsaoCam S;

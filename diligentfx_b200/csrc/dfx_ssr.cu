@@ -115,7 +115,7 @@ DFX_HD float edge_vignette(float hx, float hy, float sw, float sh) // :192-197
 }
 
 template <bool PREV_FRAME>
-__global__ void __launch_bounds__(256) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+__global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                             View<const float4> color, View<const float4> normal, View<const float> roughness,
                                                             View<const uint8_t> mask, View<const float2> noise, HizView hiz,
                                                             View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1)
@@ -299,7 +299,7 @@ struct SpatialCam
     Mat4 vp_inv;
 };
 
-__global__ void __launch_bounds__(256) ssr_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+__global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                           View<const float> roughness, View<const uint8_t> mask, View<const float4> normal,
                                                           View<const float> depth, View<const float4> raydir, View<const float4> radiance,
                                                           View<float4> out_rad, View<float> out_var, View<float> out_depth, int y0, int y1)
@@ -397,7 +397,7 @@ DFX_HD float disocclusion_ratio(float cz, float pz)
 constexpr float kNegLn090 = 0.105360516f; // -ln(SSR_DISOCCLUSION_THRESHOLD)
 constexpr float kNegLn045 = 0.798507696f; // -ln(SSR_DISOCCLUSION_THRESHOLD / 2)
 
-__global__ void __launch_bounds__(256) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
+__global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                            View<const uint8_t> mask, View<const float2> motion, View<const float> hit_depth,
                                                            View<const float> curr_depth, View<const float4> curr_rad, View<const float> curr_var,
                                                            View<const float> prev_depth, View<const float4> prev_rad, View<const float> prev_var,

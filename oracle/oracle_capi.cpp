@@ -7,6 +7,7 @@
 #include <string>
 #include <chrono>
 #include <cstdio>
+#include <atomic>
 
 using namespace orc;
 
@@ -121,7 +122,11 @@ int run_pass(Ctx& c, const std::string& p)
 }
 } // namespace
 
-namespace orc { float oracle_fast_acos(float v); }
+namespace orc
+{
+float oracle_fast_acos(float v);
+extern std::atomic<unsigned long long> g_march_rays, g_march_iterations;
+} // namespace orc
 
 extern "C"
 {
@@ -351,6 +356,12 @@ ORC_API void     orc_taa_jitter(uint32_t frame, uint32_t w, uint32_t hgt, float*
 {
     float2 j = taa_jitter_offset(frame, w, hgt);
     out[0] = j.x, out[1] = j.y;
+}
+ORC_API void orc_march_stats(unsigned long long* rays, unsigned long long* iterations, int reset)
+{
+    *rays       = orc::g_march_rays.load();
+    *iterations = orc::g_march_iterations.load();
+    if (reset) orc::g_march_rays = 0, orc::g_march_iterations = 0;
 }
 ORC_API int orc_bloom_mip_count(int w, int hgt, float radius) { return bloom_mip_count(w, hgt, radius); }
 ORC_API float orc_fast_acos(float v) { return orc::oracle_fast_acos(v); }

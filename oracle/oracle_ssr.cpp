@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
 // SSR passes S1, S2, S4-S7 restated from Shaders/PostProcess/ScreenSpaceReflection/private/*.fx (file:line per function).
 #include "oracle.h"
+#include <atomic>
 
 namespace orc
 {
@@ -75,12 +76,11 @@ void ssr_mask_roughness(const dfx_ssr_attribs& A, const TexF4& material, const T
 
 // ---------------------------------------------------------------------------------------------------------------------
 // S4  SSR_ComputeIntersection.fx
+// workload statistics of the Hi-Z march (rays traced, loop iterations), for DESIGN.md / the bench report
+std::atomic<unsigned long long> g_march_rays{0}, g_march_iterations{0};
+
 namespace
 {
-struct RayCtx
-{
-    const MipTex<float>* hiz;
-};
 
 inline float LoadDepthHierarchy(const MipTex<float>& hiz, int x, int y, int mip)
 {
@@ -149,6 +149,8 @@ inline float3 HierarchicalRaymarch(const MipTex<float>& hiz, float3 Origin, floa
         ++Idx;
     }
     ValidHit = (Idx <= MaxTraversalIntersections);
+    g_march_rays.fetch_add(1, std::memory_order_relaxed);
+    g_march_iterations.fetch_add(Idx, std::memory_order_relaxed);
     return Position;
 }
 

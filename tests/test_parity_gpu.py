@@ -325,6 +325,22 @@ def test_compose_and_tonemap(ctx):
             assert np.abs(g[..., :3] - want[..., :3]).max() <= 2e-5 * scale, (mode, srgb, np.abs(g[..., :3] - want[..., :3]).max())
 
 
+def test_streaming_pipeline_equals_frame_by_frame(ctx):
+    """The double-buffered three-stream pipeline (copy-in / compute / copy-out overlapped) must return exactly what the
+    one-frame-at-a-time API returns."""
+    import torch
+    from diligentfx_b200.chain import PostProcessChain
+    seq, h, w = ctx["seq"], ctx["h"], ctx["w"]
+    a, b = PostProcessChain(w, h), PostProcessChain(w, h)
+    want = [a.run_frame(fr).cpu().numpy().copy() for fr in seq]
+    hosts = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in seq]
+    assert b.stream_frames(iter(seq), hosts) == len(seq)
+    torch.cuda.synchronize()
+    for k, wnt in enumerate(want):
+        assert np.array_equal(hosts[k].numpy(), wnt), f"frame {k}"
+    a.close(), b.close()
+
+
 # =====================================================================================================================
 # whole chain through the effect-level objects
 # =====================================================================================================================
