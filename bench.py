@@ -46,6 +46,8 @@ PASS_BYTES_PER_PX = {
     "ssao_prefilter_depth": 5.33, "ssao_ambient_occlusion": 25.33, "ssao_temporal": 36.0, "ssao_convolute": 10.67, "ssao_resample": 16.0,
     "ssao_spatial": 32.0,
     "compose": 52.0, "taa": 64.0,
+    "compose_taa": 84.0,                 # fused: colour 16 + ssr 16 + ao 4 + history 16 + motion 8 + depths 8 in, accumulation 16 out
+    "bloom_composite_tonemap": 36.0,     # fused: colour 16 + up[0] 4 in, LDR 16 out
     "bloom_prefilter": 20.0, "bloom_downsample": 6.67, "bloom_upsample": 12.0, "bloom_composite": 36.0,
     "tonemap": 32.0,
 }
@@ -281,7 +283,7 @@ def main() -> None:
         top = max(passes, key=lambda p: p["ms"])
         roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": None,
                 "peak_source": peak_src, "share_of_step": top["share"],
-                "chain": {"alg_bytes_per_px": round(sum(PASS_BYTES_PER_PX.values()), 2),
+                "chain": {"alg_bytes_per_px": round(sum(PASS_BYTES_PER_PX.get(p["pass"], 0.0) for p in passes), 2),
                           "achieved": round(sum(p["alg_bytes"] for p in passes) / (ms_per_step * 1e-3) / 1e9, 1)}}
         roof["chain"]["frac"] = round(roof["chain"]["achieved"] / peak, 4)
 

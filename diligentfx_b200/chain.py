@@ -39,6 +39,7 @@ class ChainConfig:
     ssr_scale: float = 1.0
     ssao_scale: float = 1.0
     stages: int = STAGE_ALL
+    fuse: bool = True          # compose inside TAA, ToneMap inside the Bloom composite (same per-pixel arithmetic, two HBM round trips fewer)
 
 
 class PostProcessChain:
@@ -131,32 +132,43 @@ class PostProcessChain:
             check(L.dfx_ssao_execute(self.ssao, C.byref(a)), "dfx_ssao_execute")
 
         color = P["color"]
+        fuse_compose = cfg.fuse and (st & STAGE_COMPOSE) and (st & STAGE_TAA)      # compose evaluated inside the TAA kernel
+        fuse_tonemap = cfg.fuse and (st & STAGE_BLOOM) and (st & STAGE_TONEMAP)    # tone map evaluated inside the Bloom composite
+        ssr_out, ao_out = Plane(), Plane()
+        pssr = pao = None
         if st & STAGE_COMPOSE:
-            ssr_out, ao_out = Plane(), Plane()
-            pssr = pao = None
             if st & STAGE_SSR:
                 check(L.dfx_ssr_get_plane(self.ssr, 0, C.byref(ssr_out)), "dfx_ssr_get_plane")
                 pssr = C.byref(ssr_out)
             if st & STAGE_SSAO:
                 check(L.dfx_ssao_get_plane(self.ssao, 0, C.byref(ao_out)), "dfx_ssao_get_plane")
                 pao = C.byref(ao_out)
-            comp = plane_of(self.composed)
-            check(L.dfx_pass_compose(stream, C.byref(color), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale), C.byref(comp), Rows(0, self.h)),
-                  "dfx_pass_compose")
-            color = comp
+            if not fuse_compose:
+                comp = plane_of(self.composed)
+                check(L.dfx_pass_compose(stream, C.byref(color), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale), C.byref(comp),
+                                         Rows(0, self.h)), "dfx_pass_compose")
+                color = comp
         if st & STAGE_TAA:
             a = TAARenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.taa), 0)
-            check(L.dfx_taa_execute(self.taa, C.byref(a)), "dfx_taa_execute")
+            if fuse_compose:
+                check(L.dfx_taa_execute_composed(self.taa, C.byref(a), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale)), "dfx_taa_execute_composed")
+            else:
+                check(L.dfx_taa_execute(self.taa, C.byref(a)), "dfx_taa_execute")
             acc = Plane()
             check(L.dfx_taa_get_plane(self.taa, 0, 0, C.byref(acc)), "dfx_taa_get_plane")
             color = acc
         if st & STAGE_BLOOM:
             a = BloomRenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.bloom))
-            check(L.dfx_bloom_execute(self.bloom, C.byref(a)), "dfx_bloom_execute")
-            out = Plane()
-            check(L.dfx_bloom_get_plane(self.bloom, 0, C.byref(out)), "dfx_bloom_get_plane")
-            color = out
-        if st & STAGE_TONEMAP:
+            if fuse_tonemap:
+                ldr = plane_of(self.ldr)
+                check(L.dfx_bloom_execute_tonemapped(self.bloom, C.byref(a), C.byref(cfg.tonemap), C.c_float(cfg.ave_log_lum), int(cfg.to_srgb), C.byref(ldr)),
+                      "dfx_bloom_execute_tonemapped")
+            else:
+                check(L.dfx_bloom_execute(self.bloom, C.byref(a)), "dfx_bloom_execute")
+                out = Plane()
+                check(L.dfx_bloom_get_plane(self.bloom, 0, C.byref(out)), "dfx_bloom_get_plane")
+                color = out
+        if (st & STAGE_TONEMAP) and not fuse_tonemap:
             ldr = plane_of(self.ldr)
             check(L.dfx_pass_tonemap(stream, C.byref(cfg.tonemap), C.c_float(cfg.ave_log_lum), int(cfg.to_srgb), C.byref(color), C.byref(ldr), Rows(0, self.h)),
                   "dfx_pass_tonemap")

@@ -206,8 +206,18 @@ __global__ void __launch_bounds__(256) bloom_down2x_kernel(dfx_bloom_attribs A, 
 //   even x = 2k : texels k-2..k+1 weigh (1, 5, 7, 3)/16      odd x = 2k+1 : texels k-1..k+2 weigh (3, 7, 5, 1)/16
 // (position x/2 - 1/4 resp. + 1/4 -> bilinear {1/4, 3/4}, convolved with the tent {1/4, 1/2, 1/4}). Clamp addressing is
 // applied when the 20x8 coarse tile is staged. COMPOSITE selects B4 (lerp with Intensity) instead of B3 (plain add).
-template <bool COMPOSITE>
-__global__ void __launch_bounds__(256) bloom_up2x_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out, int y0, int y1)
+DFX_HD float3 tone_map_rt(int mode, float3 color, const dfx_tonemap_attribs& A, float aveLogLum);
+DFX_HD float3 linear_to_srgb(float3 c);
+struct ToneMapIn // only read by the TONEMAP variant: the final ToneMap(+sRGB) pass fused into the Bloom composite
+{
+    dfx_tonemap_attribs attribs;
+    float               ave_log_lum;
+    int                 to_srgb;
+};
+
+template <bool COMPOSITE, bool TONEMAP = false>
+__global__ void __launch_bounds__(256) bloom_up2x_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out, int y0, int y1,
+                                                         ToneMapIn tm = ToneMapIn{})
 {
     // A CTA of 256 threads produces 64x16 outputs; every thread a 2x2 block that shares one 5x5 coarse footprint, so the
     // shared-memory traffic is 25 LDS.128 per four outputs (the kernel would otherwise be bound by smem bandwidth, not HBM).
@@ -240,7 +250,15 @@ __global__ void __launch_bounds__(256) bloom_up2x_kernel(dfx_bloom_attribs A, Vi
         if (px >= out.w || py >= y1) return;
         const float3 c = xyz(__ldg(&fine.at(px, py))); // linear sampler at the texel centre == the texel
         if (COMPOSITE)
-            st_cs(&out.at(px, py), f4(lerp3(c, c + A.Intensity * s, A.AlphaInterpolation), 0.0f));
+        {
+            float3 o = lerp3(c, c + A.Intensity * s, A.AlphaInterpolation);
+            if (TONEMAP)
+            {
+                o = tone_map_rt(tm.attribs.iToneMappingMode, o, tm.attribs, tm.ave_log_lum);
+                if (tm.to_srgb) o = linear_to_srgb(o);
+            }
+            st_cs(&out.at(px, py), f4(o, 0.0f));
+        }
         else
             out.at(px, py) = f4(c + s, 0.0f);
     };
@@ -293,9 +311,33 @@ struct TaaCam
     CamS c, p;
 };
 
-template <bool BICUBIC, bool YCOCG, bool GAUSS>
+// The compose step (rgb += ssr.rgb * ssr.a * scale; rgb *= lerp(1, ao, scale)) evaluated where the composed colour is
+// consumed, so that the composed frame never makes a round trip through HBM (same arithmetic as compose_kernel).
+struct ComposeIn
+{
+    View<const float4> ssr;
+    View<const float>  ao;
+    float              ssr_scale, ssao_scale;
+};
+template <bool COMPOSE>
+DFX_HD float3 load_scene_colour(const View<const float4>& color, const ComposeIn& ci, int gx, int gy)
+{
+    float3 c = xyz(__ldg(&color.at(gx, gy)));
+    if (COMPOSE)
+    {
+        if (ci.ssr.p && ci.ssr_scale > 0.0f)
+        {
+            const float4 s = __ldg(&ci.ssr.at(gx, gy));
+            c              = c + xyz(s) * s.w * ci.ssr_scale;
+        }
+        if (ci.ao.p && ci.ssao_scale > 0.0f) c = c * lerpf(1.0f, __ldg(&ci.ao.at(gx, gy)), ci.ssao_scale);
+    }
+    return c;
+}
+
+template <bool BICUBIC, bool YCOCG, bool GAUSS, bool COMPOSE>
 __global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, View<const float4> curr_color,
-                                                  View<const float4> prev_accum, View<const float2> motion, View<const float> curr_depth,
+                                                  ComposeIn ci, View<const float4> prev_accum, View<const float2> motion, View<const float> curr_depth,
                                                   View<const float> prev_depth, View<float4> out, int y0, int y1)
 {
     // 32x8 pixel tile + 1-pixel halo of the current colour, converted ONCE per texel to the clipping space (Reinhard SDR,
@@ -309,7 +351,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_
         {
             const int    ly = i / 34, lx = i - ly * 34;
             const int    gx = min(max(tx0 + lx, 0), curr_color.w - 1), gy = min(max(ty0 + ly, 0), curr_color.h - 1); // ClampScreenCoord
-            const float3 sdr = rgb_to_ycocg<YCOCG>(hdr_to_sdr(max0(xyz(__ldg(&curr_color.at(gx, gy))))));
+            const float3 sdr = rgb_to_ycocg<YCOCG>(hdr_to_sdr(max0(load_scene_colour<COMPOSE>(curr_color, ci, gx, gy))));
             tile[ly][lx]     = f4(sdr, 0.0f);
         }
     }
@@ -323,7 +365,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_
     float2      mv   = __ldg(&motion.at(x, y));
     mv.x *= 0.5f, mv.y *= -0.5f;
     const float ppx = posx - mv.x * cam.vw, ppy = posy - mv.y * cam.vh;
-    const float3 currHDR = max0(xyz(__ldg(&curr_color.at(x, y))));
+    const float3 currHDR = max0(load_scene_colour<COMPOSE>(curr_color, ci, x, y));
 
     if (!(ppx >= 0.0f && ppy >= 0.0f && ppx < cam.vw && ppy < cam.vh) || A.ResetAccumulation)
     {
@@ -457,14 +499,17 @@ __global__ void __launch_bounds__(256) compose_kernel(View<const float4> color, 
 DFX_HD float3 uncharted2(float3 x) // :8-19
 {
     const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-    auto        f = [&](float v) { return ((v * (A * v + C * B) + D * E) / (v * (A * v + B) + D * F)) - E / F; };
+    auto        f = [&](float v) { return fdiv(v * (A * v + C * B) + D * E, v * (A * v + B) + D * F) - E / F; };
     return make_float3(f(x.x), f(x.y), f(x.z));
 }
-DFX_HD float3 pow3(float3 v, float e) { return make_float3(powf(v.x, e), powf(v.y, e), powf(v.z, e)); }
+// pow via MUFU lg2/ex2 (relative error ~1e-6 at these exponents): the tone map is a full-screen element-wise pass that
+// the correctly-rounded powf() would make ALU-bound instead of HBM-bound
+DFX_HD float fpow(float v, float e) { return __powf(v, e); }
+DFX_HD float3 pow3(float3 v, float e) { return make_float3(fpow(v.x, e), fpow(v.y, e), fpow(v.z, e)); }
 DFX_HD float3 srgb_to_linear(float3 s)
 {
     auto f = [](float v) {
-        float hi = powf(saturate((v + 0.055f) / 1.055f), 2.4f);
+        float hi = fpow(saturate((v + 0.055f) * (1.0f / 1.055f)), 2.4f);
         return lerpf(v / 12.92f, hi, v >= 0.04045f ? 1.0f : 0.0f);
     };
     return make_float3(f(s.x), f(s.y), f(s.z));
@@ -472,7 +517,7 @@ DFX_HD float3 srgb_to_linear(float3 s)
 DFX_HD float3 linear_to_srgb(float3 c)
 {
     auto f = [](float v) {
-        float hi = powf(v, 1.0f / 2.4f) * 1.055f - 0.055f;
+        float hi = fpow(v, 1.0f / 2.4f) * 1.055f - 0.055f;
         return lerpf(v * 12.92f, hi, v >= 0.0031308f ? 1.0f : 0.0f);
     };
     return make_float3(f(c.x), f(c.y), f(c.z));
@@ -516,7 +561,7 @@ DFX_HD float3 tone_map(float3 color, const dfx_tonemap_attribs& A, float aveLogL
     {
         const float3 curr = uncharted2(2.0f * cS);
         const float3 w    = uncharted2(make_float3(wp, wp, wp));
-        return curr * make_float3(1.0f / w.x, 1.0f / w.y, 1.0f / w.z);
+        return curr * make_float3(frcp(w.x), frcp(w.y), frcp(w.z));
     }
     if (MODE == DFX_TONE_MAPPING_MODE_FILMIC_ALU)
     {
@@ -576,6 +621,25 @@ DFX_HD float3 tone_map(float3 color, const dfx_tonemap_attribs& A, float aveLogL
         return c;
     }
     return color;
+}
+
+DFX_HD float3 tone_map_rt(int mode, float3 color, const dfx_tonemap_attribs& A, float aveLogLum)
+{
+    switch (mode) // warp-uniform
+    {
+        case DFX_TONE_MAPPING_MODE_EXP: return tone_map<DFX_TONE_MAPPING_MODE_EXP>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_REINHARD: return tone_map<DFX_TONE_MAPPING_MODE_REINHARD>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_REINHARD_MOD: return tone_map<DFX_TONE_MAPPING_MODE_REINHARD_MOD>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_UNCHARTED2: return tone_map<DFX_TONE_MAPPING_MODE_UNCHARTED2>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_FILMIC_ALU: return tone_map<DFX_TONE_MAPPING_MODE_FILMIC_ALU>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_LOGARITHMIC: return tone_map<DFX_TONE_MAPPING_MODE_LOGARITHMIC>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_ADAPTIVE_LOG: return tone_map<DFX_TONE_MAPPING_MODE_ADAPTIVE_LOG>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_AGX: return tone_map<DFX_TONE_MAPPING_MODE_AGX>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_AGX_CUSTOM: return tone_map<DFX_TONE_MAPPING_MODE_AGX_CUSTOM>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_PBR_NEUTRAL: return tone_map<DFX_TONE_MAPPING_MODE_PBR_NEUTRAL>(color, A, aveLogLum);
+        case DFX_TONE_MAPPING_MODE_COMMERCE: return tone_map<DFX_TONE_MAPPING_MODE_COMMERCE>(color, A, aveLogLum);
+        default: return tone_map<DFX_TONE_MAPPING_MODE_NONE>(color, A, aveLogLum);
+    }
 }
 
 template <int MODE>
@@ -682,11 +746,31 @@ extern "C" dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_att
     return DFX_OK;
 }
 
-extern "C" dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs, uint32_t flags,
-                                   const dfx_plane* curr_color, const dfx_plane* prev_accum, const dfx_plane* closest_motion,
-                                   const dfx_plane* reprojected_depth, const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows)
+// B4 + M1/M2 in one kernel (only on exact 2:1 levels: the caller falls back to the two separate passes otherwise).
+extern "C" dfx_status dfx_pass_bloom_composite_tonemap(void* stream, const dfx_bloom_attribs* attribs, const dfx_tonemap_attribs* tonemap, float ave_log_lum,
+                                                       int32_t convert_to_srgb, const dfx_plane* color, const dfx_plane* up0, const dfx_plane* ldr_out, dfx_rows rows)
 {
-    DFX_PROFILE(stream, "taa");
+    DFX_PROFILE(stream, "bloom_composite_tonemap");
+    DFX_REQUIRE(attribs && tonemap, "null argument");
+    DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(const float4, u, up0, DFX_FORMAT_RGBA32F);
+    DFX_VIEW(float4, out, ldr_out, DFX_FORMAT_RGBA32F);
+    DFX_SAME_SIZE(c, out);
+    DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
+    if (!(out.w == 2 * u.w && out.h == 2 * u.h && (rows.y0 & 1) == 0)) return set_error(DFX_ERR_UNSUPPORTED, "fused composite+tonemap needs an exact 2:1 level");
+    DFX_REQUIRE(tonemap->iToneMappingMode >= 0 && tonemap->iToneMappingMode <= DFX_TONE_MAPPING_MODE_COMMERCE, "unknown tone mapping mode %d", tonemap->iToneMappingMode);
+    if (rows.y1 == rows.y0) return DFX_OK;
+    bloom_up2x_kernel<true, true><<<dim3(div_up(out.w, 64), div_up(rows.y1 - rows.y0, 16)), dim3(32, 8), 0, as_stream(stream)>>>(
+        *attribs, c, u, out, rows.y0, rows.y1, ToneMapIn{*tonemap, ave_log_lum, convert_to_srgb});
+    DFX_LAUNCHED("bloom_up2x_kernel<composite, tonemap>");
+    return DFX_OK;
+}
+
+static dfx_status launch_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs, uint32_t flags, bool compose,
+                             const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale, float ssao_scale, const dfx_plane* curr_color,
+                             const dfx_plane* prev_accum, const dfx_plane* closest_motion, const dfx_plane* reprojected_depth,
+                             const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows)
+{
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const float4, cc, curr_color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float4, pa, prev_accum, DFX_FORMAT_RGBA32F);
@@ -701,9 +785,18 @@ extern "C" dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* camer
     DFX_SAME_SIZE(cc, out);
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
+    ComposeIn ci{View<const float4>{nullptr, 0, 0, 0}, View<const float>{nullptr, 0, 0, 0}, ssr_scale, ssao_scale};
+    if (compose && ssr) DFX_REQUIRE(make_view<const float4>(ssr, DFX_FORMAT_RGBA32F, ci.ssr) && ci.ssr.w == cc.w && ci.ssr.h == cc.h, "bad ssr plane");
+    if (compose && ao) DFX_REQUIRE(make_view<const float>(ao, DFX_FORMAT_R32F, ci.ao) && ci.ao.w == cc.w && ci.ao.h == cc.h, "bad ao plane");
     DFX_GRID(out.w, rows);
     cudaStream_t s = as_stream(stream);
-#define TAA_LAUNCH(B, Y, G) taa_kernel<B, Y, G><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, pa, mv, cd, pd, out, rows.y0, rows.y1)
+#define TAA_LAUNCH(B, Y, G)                                                                                                            \
+    do {                                                                                                                               \
+        if (compose)                                                                                                                   \
+            taa_kernel<B, Y, G, true><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, ci, pa, mv, cd, pd, out, rows.y0, rows.y1);    \
+        else                                                                                                                           \
+            taa_kernel<B, Y, G, false><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, ci, pa, mv, cd, pd, out, rows.y0, rows.y1);   \
+    } while (0)
     switch (flags & 7u)
     {
         case 0: TAA_LAUNCH(false, false, false); break;
@@ -718,6 +811,25 @@ extern "C" dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* camer
 #undef TAA_LAUNCH
     DFX_LAUNCHED("taa_kernel");
     return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs, uint32_t flags,
+                                   const dfx_plane* curr_color, const dfx_plane* prev_accum, const dfx_plane* closest_motion,
+                                   const dfx_plane* reprojected_depth, const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "taa");
+    return launch_taa(stream, cameras_dev, attribs, flags, false, nullptr, nullptr, 0.0f, 0.0f, curr_color, prev_accum, closest_motion, reprojected_depth,
+                      previous_depth, out_accum, rows);
+}
+
+extern "C" dfx_status dfx_pass_compose_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs, uint32_t flags,
+                                           const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale, float ssao_scale,
+                                           const dfx_plane* prev_accum, const dfx_plane* closest_motion, const dfx_plane* reprojected_depth,
+                                           const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "compose_taa");
+    return launch_taa(stream, cameras_dev, attribs, flags, true, ssr, ao, ssr_scale, ssao_scale, color, prev_accum, closest_motion, reprojected_depth,
+                      previous_depth, out_accum, rows);
 }
 
 extern "C" dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale,

@@ -463,7 +463,22 @@ extern "C" dfx_status dfx_bloom_prepare(dfx_bloom* fx, dfx_postfx* postfx, uint3
     return DFX_OK;
 }
 
-extern "C" dfx_status dfx_bloom_execute(dfx_bloom* fx, const dfx_bloom_render_attribs* a)
+static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attribs* a, const dfx_tonemap_attribs* tonemap, float ave_log_lum,
+                                     int32_t to_srgb, const dfx_plane* ldr_out);
+
+extern "C" dfx_status dfx_bloom_execute(dfx_bloom* fx, const dfx_bloom_render_attribs* a) { return bloom_execute_impl(fx, a, nullptr, 0.0f, 0, nullptr); }
+
+// Bloom followed by the final ToneMap(+sRGB) (HnPostProcessTask.cpp:911-925) with the composite and the tone map fused into
+// one kernel: the HDR bloom output never touches HBM (GetBloomTextureSRV() is NOT updated by this call).
+extern "C" dfx_status dfx_bloom_execute_tonemapped(dfx_bloom* fx, const dfx_bloom_render_attribs* a, const dfx_tonemap_attribs* tonemap, float ave_log_lum,
+                                                   int32_t convert_to_srgb, const dfx_plane* ldr_out)
+{
+    DFX_REQUIRE(tonemap && ldr_out, "tonemap attribs / output plane must not be null");
+    return bloom_execute_impl(fx, a, tonemap, ave_log_lum, convert_to_srgb, ldr_out);
+}
+
+static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attribs* a, const dfx_tonemap_attribs* tonemap, float ave_log_lum,
+                                     int32_t to_srgb, const dfx_plane* ldr_out)
 {
     DFX_REQUIRE(fx && a, "null argument");
     if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_bloom_prepare was not called");
@@ -484,6 +499,14 @@ extern "C" dfx_status dfx_bloom_execute(dfx_bloom* fx, const dfx_bloom_render_at
     for (int i = top; i > 0; --i)
         if ((st = dfx_pass_bloom_upsample(s, &fx->down[i - 1].p, i != top ? &fx->up[i].p : &fx->down[i].p, &fx->up[i - 1].p, rows(fx->up[i - 1].p))) != DFX_OK)
             return st;
+    if (tonemap)
+    {
+        const dfx_plane& u0 = fx->up[0].p;
+        if (fx->w == 2 * u0.width && fx->h == 2 * u0.height)
+            return dfx_pass_bloom_composite_tonemap(s, &A, tonemap, ave_log_lum, to_srgb, a->color, &u0, ldr_out, rows(fx->out.p));
+        if ((st = dfx_pass_bloom_composite(s, &A, a->color, &u0, &fx->out.p, rows(fx->out.p))) != DFX_OK) return st;
+        return dfx_pass_tonemap(s, tonemap, ave_log_lum, to_srgb, &fx->out.p, ldr_out, rows(fx->out.p));
+    }
     return dfx_pass_bloom_composite(s, &A, a->color, &fx->up[0].p, &fx->out.p, rows(fx->out.p));
 }
 
@@ -543,7 +566,20 @@ extern "C" dfx_status dfx_taa_prepare(dfx_taa* fx, dfx_postfx* postfx, uint32_t 
     return DFX_OK;
 }
 
-extern "C" dfx_status dfx_taa_execute(dfx_taa* fx, const dfx_taa_render_attribs* a)
+static dfx_status taa_execute_impl(dfx_taa* fx, const dfx_taa_render_attribs* a, bool compose, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale,
+                                   float ssao_scale);
+
+extern "C" dfx_status dfx_taa_execute(dfx_taa* fx, const dfx_taa_render_attribs* a) { return taa_execute_impl(fx, a, false, nullptr, nullptr, 0.0f, 0.0f); }
+
+// TAA with the compose step (HnPostProcessTask.cpp:834-895) evaluated on the fly: attribs->color is the UN-composed scene colour.
+extern "C" dfx_status dfx_taa_execute_composed(dfx_taa* fx, const dfx_taa_render_attribs* a, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale,
+                                               float ssao_scale)
+{
+    return taa_execute_impl(fx, a, true, ssr, ao, ssr_scale, ssao_scale);
+}
+
+static dfx_status taa_execute_impl(dfx_taa* fx, const dfx_taa_render_attribs* a, bool compose, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale,
+                                   float ssao_scale)
 {
     DFX_REQUIRE(fx && a, "null argument");
     DFX_REQUIRE(a->postfx && a->color && a->attribs, "postfx / color / attribs must not be null");
@@ -562,6 +598,9 @@ extern "C" dfx_status dfx_taa_execute(dfx_taa* fx, const dfx_taa_render_attribs*
     A.ResetAccumulation = reset ? 1 : 0;
     b.last_frame        = b.curr_frame;
     const uint32_t cur = b.curr_frame & 1u, prv = (b.curr_frame + 1u) & 1u;
+    if (compose)
+        return dfx_pass_compose_taa(as_stream(a->stream), pfx->cams_dev, &A, b.flags, a->color, ssr, ao, ssr_scale, ssao_scale, &b.accum[prv].p, &pfx->closest.p,
+                                    &pfx->reproj.p, &pfx->prev_depth.p, &b.accum[cur].p, dfx_rows{0, b.h});
     return dfx_pass_taa(as_stream(a->stream), pfx->cams_dev, &A, b.flags, a->color, &b.accum[prv].p, &pfx->closest.p, &pfx->reproj.p, &pfx->prev_depth.p,
                         &b.accum[cur].p, dfx_rows{0, b.h});
 }

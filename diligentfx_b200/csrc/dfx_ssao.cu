@@ -98,11 +98,26 @@ __device__ __forceinline__ uint32_t occluded_sectors(float minH, float maxH, uin
     return bits;
 }
 
+// one prefiltered-depth level, laid out for two 16-byte shared-memory loads
+struct __align__(16) AoLevel
+{
+    const float* p;
+    int          pitch, w;
+    float        fw, fh;
+    int          h, pad0;
+};
+
 template <int ALGO>
 __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
                                                       View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1)
 {
     __shared__ SsaoCam S;
+    __shared__ AoLevel lvl[DFX_MAX_MIPS];
+    if (threadIdx.y == 1 && threadIdx.x < DFX_MAX_MIPS)
+    {
+        const int i = min((int)threadIdx.x, pyr.levels - 1);
+        lvl[threadIdx.x] = AoLevel{pyr.lv[i].p, pyr.lv[i].pitch, pyr.lv[i].w, float(pyr.lv[i].w), float(pyr.lv[i].h), pyr.lv[i].h, 0};
+    }
     stage_cam(S, cams);
     const CamS& cam = S.c;
     const PixelXY pix = cta_pixel(y0);
@@ -130,6 +145,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
     pvs              = pvs + nvs * (0.00001f * pvs.z);
     const float3 view = -fnormalize(pvs);
     const float2 xi   = __ldg(&noise.at(x & 127, y & 127));
+    const float  cxk = (u - 0.5f) * kx, cyk = (v - 0.5f) * ky;
 
     const float effectRadius = A.EffectRadius * A.RadiusMultiplier;
     const float falloffRange = A.EffectFalloffRange * effectRadius;
@@ -175,6 +191,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
 
         float sdx = co * 0.5f * sampleRadius, sdy = so * -0.5f * sampleRadius;
         sdx *= cam.vh * cam.ivw; // aspect-ratio correction
+        const float sdkx = sdx * kx, sdky = sdy * ky;
 
 #pragma unroll
         for (int s = 0; s < 3; ++s)
@@ -185,13 +202,16 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
             const float lx = offx * cam.vw, ly = offy * cam.vh, l2 = lx * lx + ly * ly;
             int         mip = (l2 >= thr2[0]) + (l2 >= thr2[1]) + (l2 >= thr2[2]) + (l2 >= thr2[3]);
             mip             = min(mip, maxMip);
-            const View<const float>& lv = pyr.lv[mip];
-            const float fw = float(lv.w), fh = float(lv.h);
+            const AoLevel lv = lvl[mip]; // two 16-byte LDS: pointer, pitch, size as int and as float
             const float u0 = u + offx, v0 = v + offy, u1 = u - offx, v1 = v - offy;
-            const int   ax = min(max(__float2int_rd(u0 * fw), 0), lv.w - 1), ay = min(max(__float2int_rd(v0 * fh), 0), lv.h - 1);
-            const int   bx = min(max(__float2int_rd(u1 * fw), 0), lv.w - 1), by = min(max(__float2int_rd(v1 * fh), 0), lv.h - 1);
+            const int   ax = min(max(__float2int_rd(u0 * lv.fw), 0), lv.w - 1), ay = min(max(__float2int_rd(v0 * lv.fh), 0), lv.h - 1);
+            const int   bx = min(max(__float2int_rd(u1 * lv.fw), 0), lv.w - 1), by = min(max(__float2int_rd(v1 * lv.fh), 0), lv.h - 1);
             const float da = __ldg(lv.p + (size_t)ay * lv.pitch + ax), db = __ldg(lv.p + (size_t)by * lv.pitch + bx);
-            const float3 d0 = to_view(u0, v0, da) - pvs, d1 = to_view(u1, v1, db) - pvs;
+            // view.xy = z * ((uv - 0.5) * k) with (uv - 0.5) * k = (centre - 0.5) * k +- smp^2 * (slice direction * k)
+            const float za = fdiv(cam.m32 - da * cam.m33, da * cam.m23 - cam.m22), zb = fdiv(cam.m32 - db * cam.m33, db * cam.m23 - cam.m22);
+            const float ox = smp * smp * sdkx, oy = smp * smp * sdky;
+            const float3 d0 = make_float3(za * (cxk + ox), za * (cyk + oy), za) - pvs;
+            const float3 d1 = make_float3(zb * (cxk - ox), zb * (cyk - oy), zb) - pvs;
             const float  q0 = dot(d0, d0), q1 = dot(d1, d1);
             const float  r0 = rsqrtf(q0), r1 = rsqrtf(q1);
             const float  l0 = q0 * r0, l1 = q1 * r1; // lengths

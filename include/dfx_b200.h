@@ -356,6 +356,18 @@ DFX_API dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, const 
 DFX_API dfx_status dfx_pass_tonemap(void* stream, const dfx_tonemap_attribs* attribs, float ave_log_lum,
                                     int32_t convert_to_srgb, const dfx_plane* color, const dfx_plane* out, dfx_rows rows);
 
+/* Fused variants (B200-first: an element-wise pass is evaluated inside the kernel that consumes / produces its plane, so the
+ * intermediate frame never makes a round trip through HBM). Same arithmetic per pixel as the separate passes.
+ *   compose + T1 : `color` is the un-composed scene colour; the composed colour is computed on the fly.
+ *   B4 + M1/M2   : writes the tone-mapped LDR frame directly; only for exact 2:1 levels (DFX_ERR_UNSUPPORTED otherwise). */
+DFX_API dfx_status dfx_pass_compose_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs, uint32_t flags,
+                                        const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao, float ssr_scale, float ssao_scale,
+                                        const dfx_plane* prev_accum, const dfx_plane* closest_motion, const dfx_plane* reprojected_depth,
+                                        const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows);
+DFX_API dfx_status dfx_pass_bloom_composite_tonemap(void* stream, const dfx_bloom_attribs* attribs, const dfx_tonemap_attribs* tonemap, float ave_log_lum,
+                                                    int32_t convert_to_srgb, const dfx_plane* color, const dfx_plane* up0, const dfx_plane* ldr_out,
+                                                    dfx_rows rows);
+
 /* Host-side pieces that the reference computes on the CPU. */
 /* TemporalAntiAliasing::GetJitterOffset (TemporalAntiAliasing.cpp:63-78, Halton(2,3) x16). */
 DFX_API void dfx_taa_jitter_offset(uint32_t frame_index, uint32_t width, uint32_t height, float out_jitter[2]);
@@ -491,6 +503,9 @@ DFX_API dfx_status dfx_bloom_prepare(dfx_bloom* fx, dfx_postfx* postfx, uint32_t
 DFX_API dfx_status dfx_bloom_set_alpha_interpolation(dfx_bloom* fx, float alpha);
 DFX_API dfx_status dfx_bloom_execute(dfx_bloom* fx, const dfx_bloom_render_attribs* attribs);
 DFX_API dfx_status dfx_bloom_get_plane(const dfx_bloom* fx, int32_t id, dfx_plane* out);
+/* Bloom + final ToneMap(+sRGB) with the last two kernels fused; writes `ldr_out`, does not update the bloom output plane. */
+DFX_API dfx_status dfx_bloom_execute_tonemapped(dfx_bloom* fx, const dfx_bloom_render_attribs* attribs, const dfx_tonemap_attribs* tonemap,
+                                                float ave_log_lum, int32_t convert_to_srgb, const dfx_plane* ldr_out);
 
 /* ---- TemporalAntiAliasing (…/TemporalAntiAliasing.hpp:62-156) ---- */
 typedef struct dfx_taa_render_attribs
@@ -506,6 +521,9 @@ DFX_API dfx_status dfx_taa_create(dfx_taa** out);
 DFX_API void       dfx_taa_destroy(dfx_taa* fx);
 DFX_API dfx_status dfx_taa_prepare(dfx_taa* fx, dfx_postfx* postfx, uint32_t feature_flags, uint32_t accumulation_buffer_idx);
 DFX_API dfx_status dfx_taa_execute(dfx_taa* fx, const dfx_taa_render_attribs* attribs);
+/* TAA with the compose step evaluated on the fly (attribs->color = un-composed scene colour; ssr / ao may be NULL). */
+DFX_API dfx_status dfx_taa_execute_composed(dfx_taa* fx, const dfx_taa_render_attribs* attribs, const dfx_plane* ssr, const dfx_plane* ao,
+                                            float ssr_scale, float ssao_scale);
 DFX_API dfx_status dfx_taa_get_plane(const dfx_taa* fx, int32_t id, uint32_t accumulation_buffer_idx, dfx_plane* out);
 DFX_API dfx_status dfx_taa_get_jitter_offset(const dfx_taa* fx, uint32_t accumulation_buffer_idx, float out_jitter[2]);
 

@@ -344,10 +344,22 @@ def test_streaming_pipeline_equals_frame_by_frame(ctx):
 # =====================================================================================================================
 # whole chain through the effect-level objects
 # =====================================================================================================================
+def test_fused_chain_equals_unfused(ctx):
+    """compose-inside-TAA and ToneMap-inside-Bloom-composite perform the same arithmetic per pixel as the separate passes:
+    the LDR frames must be bit-identical (both the exact-2:1 fused kernel and, at odd sizes, the fallback sequence)."""
+    from diligentfx_b200.chain import ChainConfig, PostProcessChain
+    seq, h, w = ctx["seq"], ctx["h"], ctx["w"]
+    a, b = PostProcessChain(w, h, ChainConfig(fuse=True)), PostProcessChain(w, h, ChainConfig(fuse=False))
+    for k, fr in enumerate(seq):
+        la, lb = a.run_frame(fr).cpu().numpy(), b.run_frame(fr).cpu().numpy()
+        assert np.array_equal(la, lb), f"frame {k}: max abs diff {np.abs(la - lb).max()}"
+    a.close(), b.close()
+
+
 def test_full_chain_four_frames(ctx):
-    from diligentfx_b200.chain import PostProcessChain
+    from diligentfx_b200.chain import ChainConfig, PostProcessChain
     o, seq, h, w = ctx["o"], ctx["seq"], ctx["h"], ctx["w"]
-    chain = PostProcessChain(w, h)
+    chain = PostProcessChain(w, h, ChainConfig(fuse=False))  # stage outputs are inspected below: keep every pass separate
     launches0 = chain.lib.dfx_launch_count()
     for fr in seq:
         ldr = chain.run_frame(fr)
