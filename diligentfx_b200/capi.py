@@ -111,6 +111,15 @@ class Rows(C.Structure):
     _fields_ = [("y0", C.c_int32), ("y1", C.c_int32)]
 
 
+MAX_PEERS = 8
+
+
+class PeerSet(C.Structure):
+    """dfx_peer_set (include/dfx_b200.h): base pointers of the row-strip-sharded planes per owning rank."""
+    _fields_ = [("count", C.c_int32), ("row_begin", C.c_int32 * (MAX_PEERS + 1)), ("color", C.c_void_p * MAX_PEERS),
+                ("normal", C.c_void_p * MAX_PEERS), ("hiz", (C.c_void_p * MAX_PEERS) * MAX_MIPS)]
+
+
 class PostFXRenderAttribs(C.Structure):
     _fields_ = [("stream", C.c_void_p), ("curr_depth", C.POINTER(Plane)), ("prev_depth", C.POINTER(Plane)),
                 ("motion_vectors", C.POINTER(Plane)), ("curr_camera", C.POINTER(CameraAttribs)),

@@ -207,6 +207,60 @@ dfx_status dfx_stream_synchronize(void* stream)
     return DFX_OK;
 }
 
+dfx_status dfx_enable_peer_access(int32_t peer_device)
+{
+    int dev = -1, can = 0;
+    DFX_CUDA(cudaGetDevice(&dev));
+    if (dev == peer_device) return DFX_OK;
+    DFX_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return dfx::set_error(DFX_ERR_UNSUPPORTED, "device %d has no peer path to device %d", dev, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled)
+    {
+        (void)cudaGetLastError();
+        return DFX_OK;
+    }
+    DFX_CUDA(e);
+    return DFX_OK;
+}
+
+dfx_status dfx_ipc_alloc(size_t bytes, void** out_ptr, uint8_t handle[DFX_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == DFX_IPC_HANDLE_BYTES, "IPC handle size");
+    DFX_REQUIRE(out_ptr && handle && bytes > 0, "null argument");
+    void* p = nullptr;
+    DFX_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t  e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess)
+    {
+        cudaFree(p);
+        DFX_CUDA(e);
+    }
+    memcpy(handle, &h, sizeof(h));
+    *out_ptr = p;
+    return DFX_OK;
+}
+dfx_status dfx_ipc_free(void* ptr)
+{
+    if (ptr) DFX_CUDA(cudaFree(ptr));
+    return DFX_OK;
+}
+dfx_status dfx_ipc_open(const uint8_t handle[DFX_IPC_HANDLE_BYTES], void** out_ptr)
+{
+    DFX_REQUIRE(out_ptr && handle, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    // mapped into the CURRENT device's address space; peer access to the owning device is enabled as needed
+    DFX_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DFX_OK;
+}
+dfx_status dfx_ipc_close(void* mapped)
+{
+    if (mapped) DFX_CUDA(cudaIpcCloseMemHandle(mapped));
+    return DFX_OK;
+}
+
 void dfx_profile_enable(int32_t on) { g_profile_on = on != 0; }
 
 dfx_status dfx_profile_collect(void)

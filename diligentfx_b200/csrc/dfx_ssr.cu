@@ -114,16 +114,59 @@ DFX_HD float edge_vignette(float hx, float hy, float sw, float sh) // :192-197
     return bx * by;
 }
 
-template <bool PREV_FRAME>
+// Frame split into row strips over several GPUs (dfx_pass_ssr_intersect_peer): base pointers of the planes the march reads
+// beyond its own strip, per owning rank. Rank r owns the full-res rows [row_begin[r], row_begin[r+1]); boundaries are
+// multiples of 64 so row y of level k is owned by the owner of full-res row y << k.
+constexpr int kPeerBlockShift = 6;
+constexpr int kPeerMaxBlocks  = 256; // 64-row blocks: heights up to 16384
+struct PeerArgs
+{
+    const float*  hiz[DFX_MAX_MIPS][DFX_MAX_PEERS];
+    const float4* color[DFX_MAX_PEERS];
+    const float4* normal[DFX_MAX_PEERS];
+    int           row_begin[DFX_MAX_PEERS + 1];
+    int           count;
+};
+struct PeerTables
+{
+    const float*  hiz[DFX_MAX_MIPS * DFX_MAX_PEERS];
+    const float4* color[DFX_MAX_PEERS];
+    const float4* normal[DFX_MAX_PEERS];
+    uint8_t       owner[kPeerMaxBlocks];
+};
+struct NoPeerTables
+{
+};
+__device__ __forceinline__ float hiz_load(const HizLevel* lvl, const PeerTables& P, int x, int y, int mip)
+{
+    const HizLevel L = lvl[mip & (DFX_MAX_MIPS - 1)];
+    const unsigned w = (unsigned)L.wh & 0xFFFFu, hgt = (unsigned)L.wh >> 16;
+    if (!((unsigned)x < w && (unsigned)y < hgt)) return 0.0f;
+    const float* p = P.hiz[(mip & (DFX_MAX_MIPS - 1)) * DFX_MAX_PEERS + P.owner[(y << mip) >> kPeerBlockShift]];
+    return __ldg(p + (size_t)y * L.pitch + x);
+}
+__device__ __forceinline__ float hiz_load(const HizLevel* lvl, const NoPeerTables&, int x, int y, int mip) { return hiz_load(lvl, x, y, mip); }
+// Load of a full-res RGBA plane at the hit texel (0 out of bounds): from the owner of row y.
+template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const PeerTables& P, int x, int y)
+{
+    if (!((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* base = (NORMAL ? P.normal : P.color)[P.owner[y >> kPeerBlockShift]];
+    return __ldg(base + (size_t)y * v.pitch + x);
+}
+template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
+
+template <bool PREV_FRAME, bool PEER>
 __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                             View<const float4> color, View<const float4> normal, View<const float> roughness,
                                                             View<const uint8_t> mask, View<const float2> noise, HizView hiz,
-                                                            View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1)
+                                                            View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1,
+                                                            const __grid_constant__ typename std::conditional<PEER, PeerArgs, NoPeerTables>::type peer_args)
 {
     __shared__ IntersectCam S;
     // Hi-Z level table in shared memory: the march picks a level per iteration, and one 16-byte LDS (pointer, pitch, packed
     // size) is cheaper than four register-indexed constant-bank loads of the kernel-parameter struct.
     __shared__ HizLevel lvl[DFX_MAX_MIPS];
+    __shared__ typename std::conditional<PEER, PeerTables, NoPeerTables>::type PT;
     if (threadIdx.x == 0 && threadIdx.y == 0)
     {
         load_cam(S.c, &cams[0]);
@@ -135,6 +178,18 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
     {
         const int i = threadIdx.x;
         lvl[i]      = i < hiz.levels ? HizLevel{hiz.lv[i].p, hiz.lv[i].pitch, hiz.lv[i].w | (hiz.lv[i].h << 16)} : HizLevel{nullptr, 0, 0};
+    }
+    if constexpr (PEER)
+    {
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x; // 256 threads
+        if (tid < DFX_MAX_MIPS * DFX_MAX_PEERS) PT.hiz[tid] = peer_args.hiz[tid / DFX_MAX_PEERS][tid % DFX_MAX_PEERS];
+        if (tid < DFX_MAX_PEERS) PT.color[tid] = peer_args.color[tid], PT.normal[tid] = peer_args.normal[tid];
+        {
+            const int row = tid << kPeerBlockShift;
+            int       o   = 0;
+            for (int r = 1; r < peer_args.count; ++r) o = row >= peer_args.row_begin[r] ? r : o;
+            PT.owner[tid] = (uint8_t)o;
+        }
     }
     __syncthreads();
     const CamS& cam = S.c;
@@ -221,7 +276,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         while (i < A.MaxTraversalIntersections && mip >= baseMip)
         {
             const float mx = resx * pos.x, my = resy * pos.y;
-            const float surf = hiz_load(lvl, (int)mx, (int)my, mip);
+            const float surf = hiz_load(lvl, PT, (int)mx, (int)my, mip);
             // AdvanceRay :88-136
             const float px = (floorf(mx) + fox) * irx + uox, py = (floorf(my) + foy) * iry + uoy;
             const float tx = px * invD.x - O.x * invD.x, ty = py * invD.y - O.y * invD.y;
@@ -260,10 +315,10 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         if (!(mdx < (2.0f / sw) && mdy < (2.0f / sh)))
         {
             const int   tx = (int)(sw * pos.x), ty = (int)(sh * pos.y);
-            const float surfD = hiz_load(hiz, tx, ty, 0);
+            const float surfD = hiz_load(lvl, PT, tx, ty, 0);
             if (!is_background(surfD))
             {
-                const float3 hitN = xyz(load0(normal, tx, ty));
+                const float3 hitN = xyz(hit_load0<true>(normal, PT, tx, ty));
                 if (!(dot(hitN, dirWS) > 0.0f))
                 {
                     const float3 surfVS = screen_to_view(pos.x, pos.y, surfD, cam);
@@ -279,7 +334,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         }
     }
     float3 radiance = make_float3(0.f, 0.f, 0.f);
-    if (confidence > 0.0f) radiance = xyz(load0(color, (int)(sw * hpx), (int)(sh * hpy)));
+    if (confidence > 0.0f) radiance = xyz(hit_load0<false>(color, PT, (int)(sw * hpx), (int)(sh * hpy)));
     const float3 dv = hitVS - originVS;
     st_cs(&out_rad.at(x, y), f4(radiance, confidence));
     st_cs(&out_dir.at(x, y), f4(dirWS * length(dv), pdf));
@@ -641,12 +696,11 @@ extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_at
     return DFX_OK;
 }
 
-extern "C" dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, uint32_t flags,
-                                             const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness, const dfx_plane* mask,
-                                             const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz, const dfx_plane* motion,
-                                             const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
+static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, uint32_t flags,
+                                     const dfx_peer_set* peers, const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness,
+                                     const dfx_plane* mask, const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz, const dfx_plane* motion,
+                                     const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
 {
-    DFX_PROFILE(stream, "ssr_intersect");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) == 0, "half-resolution SSR is not implemented");
     DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
@@ -668,19 +722,70 @@ extern "C" dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attr
     DFX_REQUIRE(rows_ok(rows, c.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(c.w, rows);
-    if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
+    if (peers)
+    {
+        DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) == 0, "previous-frame SSR is not supported on peer-sharded frames");
+        DFX_REQUIRE(peers->count >= 1 && peers->count <= DFX_MAX_PEERS, "peer count out of range");
+        DFX_REQUIRE(c.h <= (kPeerMaxBlocks << kPeerBlockShift), "frame too tall for the peer owner table");
+        PeerArgs pa{};
+        pa.count = peers->count;
+        DFX_REQUIRE(peers->row_begin[0] == 0 && peers->row_begin[peers->count] == c.h, "peer strips must cover rows [0, height)");
+        for (int i = 0; i <= peers->count; ++i)
+        {
+            const int b = peers->row_begin[i];
+            DFX_REQUIRE((i == 0 || b >= peers->row_begin[i - 1]) && (b == c.h || (b & ((1 << kPeerBlockShift) - 1)) == 0),
+                        "peer strip boundaries must be ascending multiples of 64");
+            pa.row_begin[i] = b;
+        }
+        for (int i = 0; i < peers->count; ++i)
+        {
+            const bool empty = peers->row_begin[i + 1] == peers->row_begin[i];
+            DFX_REQUIRE(empty || (peers->color[i] && peers->normal[i]), "null peer plane");
+            pa.color[i]  = static_cast<const float4*>(peers->color[i]);
+            pa.normal[i] = static_cast<const float4*>(peers->normal[i]);
+            for (int m = 0; m < H.levels; ++m)
+            {
+                DFX_REQUIRE(empty || peers->hiz[m][i], "null peer Hi-Z level");
+                pa.hiz[m][i] = static_cast<const float*>(peers->hiz[m][i]);
+            }
+        }
+        View<const float2> mv{nullptr, 0, 0, 0};
+        ssr_intersect_kernel<false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, pa);
+    }
+    else if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
     {
         DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
         DFX_SAME_SIZE(c, mv);
-        ssr_intersect_kernel<true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1);
+        ssr_intersect_kernel<true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
     }
     else
     {
         View<const float2> mv{nullptr, 0, 0, 0};
-        ssr_intersect_kernel<false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1);
+        ssr_intersect_kernel<false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
     }
     DFX_LAUNCHED("ssr_intersect_kernel");
     return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, uint32_t flags,
+                                             const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness, const dfx_plane* mask,
+                                             const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz, const dfx_plane* motion,
+                                             const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "ssr_intersect");
+    return ssr_intersect_impl(stream, cameras_dev, attribs, flags, nullptr, color, normal, roughness, mask, blue_noise_xy, hiz, motion, out_radiance,
+                              out_raydir_pdf, rows);
+}
+
+extern "C" dfx_status dfx_pass_ssr_intersect_peer(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, uint32_t flags,
+                                                  const dfx_peer_set* peers, const dfx_plane* color, const dfx_plane* normal,
+                                                  const dfx_plane* roughness, const dfx_plane* mask, const dfx_plane* blue_noise_xy,
+                                                  const dfx_pyramid* hiz, const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "ssr_intersect_peer");
+    DFX_REQUIRE(peers, "null argument");
+    return ssr_intersect_impl(stream, cameras_dev, attribs, flags, peers, color, normal, roughness, mask, blue_noise_xy, hiz, nullptr, out_radiance,
+                              out_raydir_pdf, rows);
 }
 
 extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs,

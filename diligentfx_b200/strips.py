@@ -100,6 +100,82 @@ def gather_rows(planes: list[torch.Tensor], bounds: list[tuple[int, int]], group
             req.wait()
 
 
+class _RawCuda:
+    """`__cuda_array_interface__` carrier: lets torch view device memory this package allocated itself."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerSlab:
+    """One device allocation per rank, laid out identically on every rank and mapped into every peer (CUDA IPC, one process
+    per GPU on one box), holding the planes other GPUs load from directly over NVLink.
+
+    `specs`: name -> (shape, torch dtype). `self.local[name]` is this rank's tensor; `self.ptr(name, r)` is the address of
+    rank r's copy as mapped into THIS process (usable by kernels launched on this rank's device). The mapping is opened
+    with the reading device current (dfx_ipc_open), which is what makes it kernel-addressable; a mapping opened on the
+    owner's device, as torch's tensor IPC does, serves copies but faults under direct kernel loads from another GPU.
+    """
+
+    ALIGN = 256
+
+    def __init__(self, specs: dict, group=None, device: torch.device | None = None, fill: float = 0.0):
+        from . import capi
+        self.capi, self.lib, self.group = capi, capi.load(), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.offsets, off = {}, 0
+        for name, (shape, dtype) in specs.items():
+            n = int(torch.tensor(shape).prod().item()) * torch.empty((), dtype=dtype).element_size()
+            self.offsets[name] = (off, n, tuple(shape), dtype)
+            off += -(-n // self.ALIGN) * self.ALIGN
+        self.nbytes = off
+        handle = (C.c_uint8 * 64)()
+        base = C.c_void_p()
+        with torch.cuda.device(self.dev):
+            capi.check(self.lib.dfx_ipc_alloc(C.c_size_t(self.nbytes), C.byref(base), handle), "dfx_ipc_alloc")
+            self.base = [0] * self.world
+            self.base[self.rank] = int(base.value)
+            handles: list = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self._mapped = []
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                ptr = C.c_void_p()
+                capi.check(self.lib.dfx_ipc_open((C.c_uint8 * 64).from_buffer_copy(handles[r]), C.byref(ptr)), "dfx_ipc_open")
+                self.base[r] = int(ptr.value)
+                self._mapped.append(int(ptr.value))
+        self._raw = _RawCuda(self.base[self.rank], self.nbytes)
+        self._bytes = torch.as_tensor(self._raw, device=self.dev)
+        assert self._bytes.data_ptr() == self.base[self.rank], "torch copied the slab instead of viewing it"
+        self.local = {}
+        for name, (o, n, shape, dtype) in self.offsets.items():
+            self.local[name] = self._bytes[o:o + n].view(dtype).view(shape)
+            self.local[name].fill_(fill)
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier(group)  # nobody reads a peer's slab before its owner has initialised it
+
+    def ptr(self, name: str, r: int) -> int:
+        return self.base[r] + self.offsets[name][0]
+
+    def close(self):
+        """Collective: unmap the peers' slabs, then free the own one once every peer has unmapped it."""
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.device(self.dev):
+            for p in self._mapped:
+                self.capi.check(self.lib.dfx_ipc_close(C.c_void_p(p)), "dfx_ipc_close")
+            if self.world > 1:
+                dist.barrier(self.group)
+            self.local, self._bytes, self._raw = {}, None, None
+            self.capi.check(self.lib.dfx_ipc_free(C.c_void_p(self.base[self.rank])), "dfx_ipc_free")
+        self.base = None
+
+
 class SsrStripRunner:
     """ScreenSpaceReflection (S1-S7) + the PostFX planes it needs, one frame split into row strips over the ranks of `group`.
 
@@ -110,7 +186,14 @@ class SsrStripRunner:
 
     MAX_MOTION_ROWS = 24  # reprojection reach (motion + 3x3 search + bilinear footprint) the temporal pass is given
 
-    def __init__(self, width: int, height: int, group=None, device: torch.device | None = None):
+    def __init__(self, width: int, height: int, group=None, device: torch.device | None = None, peer: bool = False, poison: bool = False,
+                 input_sets: int = 1):
+        """`peer=True`: no gather before the ray march — the intersect kernel loads Hi-Z / colour / normal texels straight from
+        the GPU that owns their row over NVLink (dfx_pass_ssr_intersect_peer). The runner then owns the depth / colour /
+        normal planes the peers read: `self.shared_sets[i]` for i < input_sets (a renderer that double-buffers its G-buffer
+        asks for 2). Fill a set directly and name it in execute(input_set=i), or pass other tensors to execute() and pay a
+        device copy of the strip. `poison=True` fills those planes with NaN first (tests: a texel read from a row nobody
+        wrote shows up in the output)."""
         from . import capi
         self.capi = capi
         self.lib = capi.load()
@@ -135,13 +218,50 @@ class SsrStripRunner:
         self.tables = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
         self.cams = torch.zeros(2 * 576, dtype=torch.uint8, device=dev)
         self.comm_bytes = 0
+        self.peer = bool(peer) and self.world > 1
+        if self.peer:
+            fill = float("nan") if poison else 0.0
+            specs = {f"hiz{k}": (tuple(self.hiz[k].shape), torch.float32) for k in range(1, 7)}
+            for i in range(max(1, input_sets)):
+                specs.update({f"depth{i}": ((H, W), torch.float32), f"color{i}": ((H, W, 4), torch.float32), f"normal{i}": ((H, W, 4), torch.float32)})
+            self.slab = PeerSlab(specs, group, dev, fill)
+            self.hiz = [None] + [self.slab.local[f"hiz{k}"] for k in range(1, 7)]
+            self.shared_sets = [{n: self.slab.local[f"{n}{i}"] for n in ("depth", "color", "normal")} for i in range(max(1, input_sets))]
+            self.peer_sets = []
+            for i in range(len(self.shared_sets)):
+                ps = capi.PeerSet()
+                ps.count = self.world
+                for r, (a, _) in enumerate(self.bounds):
+                    ps.row_begin[r] = a
+                ps.row_begin[self.world] = H
+                for r in range(self.world):
+                    ps.color[r], ps.normal[r] = self.slab.ptr(f"color{i}", r), self.slab.ptr(f"normal{i}", r)
+                    ps.hiz[0][r] = self.slab.ptr(f"depth{i}", r)
+                    for k in range(1, 7):
+                        ps.hiz[k][r] = self.slab.ptr(f"hiz{k}", r)
+                self.peer_sets.append(ps)
+            self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def close(self):
+        """Collective in peer mode (unmaps / frees the shared slab)."""
+        if self.peer:
+            self.slab.close()
+            self.peer = False
+
+    def _device_barrier(self):
+        """Stream-ordered barrier over the ranks (a 4-byte all-reduce): work enqueued after it on any rank starts only when
+        the work enqueued before it on every rank has finished. Does not block the host."""
+        dist.all_reduce(self.token, group=self.group)
 
     def _count(self, planes, rows: int):
         self.comm_bytes += sum(rows * p[0].numel() * p.element_size() for p in planes)
 
-    def execute(self, frame_index: int, inputs: dict, curr_camera, prev_camera, attribs=None, flags: int = 0) -> torch.Tensor:
+    def execute(self, frame_index: int, inputs: dict, curr_camera, prev_camera, attribs=None, flags: int = 0,
+                input_set: int = 0) -> torch.Tensor:
         """`inputs`: full-size device planes depth, prev_depth, motion, normal, color, material of which this rank's strip is
-        valid (everything else is filled in by the exchanges). Returns the SSR output plane (valid on the owned rows)."""
+        valid (everything else is filled in by the exchanges). Returns the SSR output plane (valid on the owned rows).
+        Peer mode: depth / color / normal are taken from `self.shared_sets[input_set]`; entries of `inputs` under those
+        names that are other tensors are first copied into the set (owned rows)."""
         capi, L, B, R, g = self.capi, self.lib, self.bounds, self.rows, self.group
         P = capi.plane_of
         a = attribs or capi.SSRAttribs.default()
@@ -150,10 +270,23 @@ class SsrStripRunner:
         self.cams.copy_(torch.frombuffer(bytearray(bytes(curr_camera) + bytes(prev_camera)), dtype=torch.uint8), non_blocking=False)
         cams = C.c_void_p(self.cams.data_ptr())
         ck = capi.check
-        depth, motion, normal, color = inputs["depth"], inputs["motion"], inputs["normal"], inputs["color"]
+        depth, motion, normal, color = inputs.get("depth"), inputs["motion"], inputs.get("normal"), inputs.get("color")
+        if self.peer:
+            if flags & capi.SSR_FLAG_PREVIOUS_FRAME:
+                raise capi.DfxError("previous-frame SSR is not supported on peer-sharded frames")
+            shared = self.shared_sets[input_set]
+            for name in ("depth", "color", "normal"):
+                if inputs.get(name) is not None and inputs[name] is not shared[name]:
+                    shared[name][R.y0:R.y1].copy_(inputs[name][R.y0:R.y1])
+            depth, normal, color = shared["depth"], shared["normal"], shared["color"]
 
         # PostFX prep: 3x3 closest-depth search -> +-1 row of depth and motion; previous depth: reprojection reach
-        exchange_halo([depth, motion], B, 1, g)
+        # (peer mode: S5 / S7 read depth and normal of up to 4 rows beyond the strip, which the gather would have provided)
+        if self.peer:
+            exchange_halo([depth, normal], B, 4, g)
+            exchange_halo([motion], B, 1, g)
+        else:
+            exchange_halo([depth, motion], B, 1, g)
         exchange_halo([inputs["prev_depth"]], B, self.MAX_MOTION_ROWS, g)
         ck(L.dfx_pass_blue_noise(s, C.c_void_p(self.tables.data_ptr()), frame_index, C.byref(P(self.bn_xy)), C.byref(P(self.bn_zw))))
         # the copy of the previous depth has to cover the halo rows the temporal pass will read: widen the row range
@@ -167,12 +300,21 @@ class SsrStripRunner:
         pyr = capi.pyramid_of([depth] + self.hiz[1:])
         ck(L.dfx_pass_ssr_hiz(s, C.byref(pyr), R))
         ck(L.dfx_pass_ssr_mask_roughness(s, C.byref(a), C.byref(P(inputs["material"])), C.byref(P(depth)), C.byref(P(self.roughness)), C.byref(P(self.mask)), R))
-        gather_rows([depth, color, normal] + ([motion] if flags & capi.SSR_FLAG_PREVIOUS_FRAME else []), B, g)
-        for k in range(1, 7):
-            gather_rows([self.hiz[k]], B, g, row_shift=k)
-        # S4
-        ck(L.dfx_pass_ssr_intersect(s, cams, C.byref(a), flags, C.byref(P(color)), C.byref(P(normal)), C.byref(P(self.roughness)), C.byref(P(self.mask)),
-                                    C.byref(P(self.bn_xy)), C.byref(pyr), C.byref(P(motion)), C.byref(P(self.radiance)), C.byref(P(self.raydir)), R))
+        if self.peer:
+            # S4 with peer loads: every rank's Hi-Z / colour / normal strips must be complete before anybody marches, and
+            # every march must be over before anybody overwrites them (next frame) -> one device barrier on either side
+            self._device_barrier()
+            ck(L.dfx_pass_ssr_intersect_peer(s, cams, C.byref(a), flags, C.byref(self.peer_sets[input_set]), C.byref(P(color)), C.byref(P(normal)),
+                                             C.byref(P(self.roughness)), C.byref(P(self.mask)), C.byref(P(self.bn_xy)), C.byref(pyr),
+                                             C.byref(P(self.radiance)), C.byref(P(self.raydir)), R))
+            self._device_barrier()
+        else:
+            gather_rows([depth, color, normal] + ([motion] if flags & capi.SSR_FLAG_PREVIOUS_FRAME else []), B, g)
+            for k in range(1, 7):
+                gather_rows([self.hiz[k]], B, g, row_shift=k)
+            # S4
+            ck(L.dfx_pass_ssr_intersect(s, cams, C.byref(a), flags, C.byref(P(color)), C.byref(P(normal)), C.byref(P(self.roughness)), C.byref(P(self.mask)),
+                                        C.byref(P(self.bn_xy)), C.byref(pyr), C.byref(P(motion)), C.byref(P(self.radiance)), C.byref(P(self.raydir)), R))
         # S5: 8-tap disk of radius <= 4 px
         exchange_halo([self.radiance, self.raydir], B, 4, g)
         ck(L.dfx_pass_ssr_spatial(s, cams, C.byref(a), C.byref(P(self.roughness)), C.byref(P(self.mask)), C.byref(P(normal)), C.byref(P(depth)),

@@ -303,6 +303,42 @@ DFX_API dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attribs
                                           const dfx_pyramid* hiz, const dfx_plane* motion,
                                           const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows);
 
+/* S4 for one frame split into row strips over several GPUs of an NVLink / NVSwitch box. The march of a ray
+ * may cross the whole screen, so instead of gathering Hi-Z / colour / normal onto every GPU before the pass, the kernel
+ * loads each texel straight from the GPU that OWNS its row (peer loads; every GPU holds full-size planes at the same pitch,
+ * valid on its own rows only). `color`, `normal`, `hiz` describe the local planes (sizes and pitches); `peers` gives, per
+ * rank, the base pointer of the same plane as mapped into this process (cudaIpcOpenMemHandle, or a plain pointer when one
+ * process drives all GPUs; base[own rank] = the local pointer). row_begin[r] .. row_begin[r+1] are the rows of full-res
+ * planes rank r owns; every boundary but the last is a multiple of 64 so that every Hi-Z level splits at a row boundary.
+ * Output is bit-identical to dfx_pass_ssr_intersect on complete planes. DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME is not
+ * supported. The caller orders the producers on all GPUs before this launch (stream-ordered barrier) and this launch
+ * before the next frame's writers. No reference counterpart: the reference renders a frame on one device.          */
+#define DFX_MAX_PEERS 8
+typedef struct dfx_peer_set {
+    int32_t     count;                                  /* GPUs sharing the frame, 1..DFX_MAX_PEERS                    */
+    int32_t     row_begin[DFX_MAX_PEERS + 1];
+    const void* color[DFX_MAX_PEERS];
+    const void* normal[DFX_MAX_PEERS];
+    const void* hiz[DFX_MAX_MIPS][DFX_MAX_PEERS];       /* level 0 = the depth plane                                   */
+} dfx_peer_set;
+DFX_API dfx_status dfx_pass_ssr_intersect_peer(void* stream, const dfx_camera_attribs* cameras_dev,
+                                               const dfx_ssr_attribs* attribs, uint32_t flags, const dfx_peer_set* peers,
+                                               const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness,
+                                               const dfx_plane* mask, const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz,
+                                               const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device; OK if already enabled, DFX_ERR_UNSUPPORTED if the
+ * two devices have no peer path.                                                                                   */
+DFX_API dfx_status dfx_enable_peer_access(int32_t peer_device);
+/* Device memory another process on the same box can map (one process per GPU): dfx_ipc_alloc = cudaMalloc +
+ * cudaIpcGetMemHandle on the current device; the 64-byte handle travels over any host channel; dfx_ipc_open maps it into
+ * the CURRENT device's address space (cudaIpcMemLazyEnablePeerAccess), so kernels of the opening process may load from
+ * it over NVLink. The owner keeps the allocation alive until every peer has called dfx_ipc_close.                  */
+#define DFX_IPC_HANDLE_BYTES 64
+DFX_API dfx_status dfx_ipc_alloc(size_t bytes, void** out_ptr, uint8_t handle[DFX_IPC_HANDLE_BYTES]);
+DFX_API dfx_status dfx_ipc_free(void* ptr);
+DFX_API dfx_status dfx_ipc_open(const uint8_t handle[DFX_IPC_HANDLE_BYTES], void** out_ptr);
+DFX_API dfx_status dfx_ipc_close(void* mapped);
+
 /* S5 ComputeSpatialReconstruction (…cpp:1001-1031; SSR_ComputeSpatialReconstruction.fx:114-172). Masked writes. */
 DFX_API dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attribs* cameras_dev,
                                         const dfx_ssr_attribs* attribs,

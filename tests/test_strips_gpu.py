@@ -17,7 +17,7 @@ def _free_port() -> int:
     return p
 
 
-def _worker(rank: int, world: int, port: int, w: int, h: int, frames: int, out_dir: str):
+def _worker(rank: int, world: int, port: int, w: int, h: int, frames: int, out_dir: str, peer: bool):
     import torch
     import torch.distributed as dist
 
@@ -31,7 +31,7 @@ def _worker(rank: int, world: int, port: int, w: int, h: int, frames: int, out_d
         seq = synth.generate_sequence(w, h, frames)
         bounds = strip_bounds(h, world)
         y0, y1 = bounds[rank]
-        runner = SsrStripRunner(w, h)
+        runner = SsrStripRunner(w, h, peer=peer, poison=True)
         ref = PostProcessChain(w, h, ChainConfig(stages=STAGE_POSTFX | STAGE_SSR)) if rank == 0 else None
         for fr in seq:
             inputs = {}
@@ -45,21 +45,25 @@ def _worker(rank: int, world: int, port: int, w: int, h: int, frames: int, out_d
                 ref.run_frame(fr)
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"strip_{rank}.npy"), out[y0:y1].cpu().numpy())
+        runner.close()
         if ref is not None:
             np.save(os.path.join(out_dir, "ref.npy"), ref.fetch("ssr", 0))
     finally:
         dist.destroy_process_group()
 
 
-def test_ssr_strips_bit_identical_on_two_gpus(built, tmp_path):
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl-gather", "nvlink-peer-loads"])
+def test_ssr_strips_bit_identical_on_two_gpus(built, tmp_path, peer):
     import torch
     import torch.multiprocessing as mp
 
     from diligentfx_b200.strips import strip_bounds
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    if peer and not torch.cuda.can_device_access_peer(0, 1):
+        pytest.skip("GPUs 0 and 1 have no peer path")
     w, h, world = 320, 256, 2
-    mp.spawn(_worker, args=(world, _free_port(), w, h, 3, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), w, h, 3, str(tmp_path), peer), nprocs=world, join=True)
     ref = np.load(tmp_path / "ref.npy")
     for r, (y0, y1) in enumerate(strip_bounds(h, world)):
         got = np.load(tmp_path / f"strip_{r}.npy")

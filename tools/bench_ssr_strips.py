@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--height", type=int, default=4320)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--peer", action="store_true", help="ray march with NVLink peer loads instead of gathering Hi-Z / colour / normal")
     a = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -51,11 +52,16 @@ def main():
         for n in INPUT_SPECS:
             full[n][y0:y1] = torch.from_numpy(fr[n]).to(dev)
         frames.append((full, cam.attribs, prev.attribs))
-    runner = strips.SsrStripRunner(W, H)
+    runner = strips.SsrStripRunner(W, H, peer=a.peer, input_sets=2)
+    if runner.peer:  # the G-buffer lives in the runner's exported planes (double-buffered), as a renderer would write it
+        for i, (full, _, _) in enumerate(frames):
+            for n in ("depth", "color", "normal"):
+                runner.shared_sets[i][n][y0:y1] = full[n][y0:y1]
+                del full[n]
 
     def step(i):
         full, c, p = frames[i & 1]
-        runner.execute(i, full, c, p)
+        runner.execute(i, full, c, p, input_set=i & 1)
 
     def barrier():
         if world > 1:
@@ -78,8 +84,10 @@ def main():
         t = float(ms.item())
         print(json.dumps({"metric": "Mpixels/sec ScreenSpaceReflection Hi-Z ray-march @ 8K G-buffer, row-strip shard", "value": round(W * H / 1e6 / (t / 1e3), 2),
                           "unit": "Mpix/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(t, 4), "scaling": "strong",
-                          "config": {"workload": f"SSR S1-S7 + PostFX prep, {W}x{H}, strips {bounds}", "exchange": "NCCL send/recv: halo rows (1/4/24/2) + gathered depth, colour, normal, Hi-Z"}}),
+                          "config": {"workload": f"SSR S1-S7 + PostFX prep, {W}x{H}, strips {bounds}", "exchange": ("NCCL send/recv of halo rows (4/1/24/4/1/24/2); ray march loads Hi-Z / colour / normal from the owning GPU over NVLink" if runner.peer
+                                                  else "NCCL send/recv: halo rows (1/4/24/2) + gathered depth, colour, normal, Hi-Z")}}),
               flush=True)
+    runner.close()
     dist.destroy_process_group()
 
 
