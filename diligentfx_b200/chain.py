@@ -40,6 +40,7 @@ class ChainConfig:
     ssao_scale: float = 1.0
     stages: int = STAGE_ALL
     fuse: bool = True          # compose inside TAA, ToneMap inside the Bloom composite (same per-pixel arithmetic, two HBM round trips fewer)
+    overlap: bool = True       # async compute: SSAO beside SSR on a second stream, Bloom + ToneMap beside the NEXT frame's front half on a third
 
 
 class PostProcessChain:
@@ -65,6 +66,18 @@ class PostProcessChain:
         self.composed = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
         self.ldr = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
         self.frame_index = None
+        # async-compute streams (cfg.overlap): the SSAO chain and the SSR chain only share read-only inputs, and Bloom + ToneMap
+        # of frame f only share the (ping-pong) TAA accumulator with frame f+1, so their small launches (pyramid levels) fill
+        # the gaps of the other branch instead of leaving the GPU idle.
+        self._ao_stream = torch.cuda.Stream(dev)
+        self._post_stream = torch.cuda.Stream(dev)
+        self._post_done: list = []   # events of the last two frames' Bloom + ToneMap (TAA of frame f+2 overwrites what Bloom of f read)
+
+    def join(self):
+        """Makes the current stream wait for everything execute(defer_post=True) left running on the side streams."""
+        main = torch.cuda.current_stream(self.device)
+        for e in self._post_done:
+            main.wait_event(e)
 
     def close(self):
         L = self.lib
@@ -92,18 +105,25 @@ class PostProcessChain:
         return n
 
     # ---- one frame ------------------------------------------------------------------------------------------------
-    def execute(self, frame_index: int, curr_camera, prev_camera, inputs: dict | None = None, ldr_out: torch.Tensor | None = None) -> torch.Tensor:
+    def execute(self, frame_index: int, curr_camera, prev_camera, inputs: dict | None = None, ldr_out: torch.Tensor | None = None,
+                defer_post: bool = False) -> torch.Tensor:
         """Runs the chain on device-resident inputs (default: the planes filled by upload()); returns the final LDR plane
-        (device tensor, rgba; `ldr_out` if given)."""
+        (device tensor, rgba; `ldr_out` if given). Everything is ordered after the work already on the current stream. With
+        cfg.overlap the LDR plane is produced on a side stream: by default the current stream waits for it before this call
+        returns; `defer_post=True` skips that wait so that the next frame's front half overlaps it (call join(), or wait
+        on `self.post_event`, before consuming the result)."""
         if ldr_out is not None:
             self.ldr, saved = ldr_out, self.ldr
             try:
-                return self.execute(frame_index, curr_camera, prev_camera, inputs)
+                return self.execute(frame_index, curr_camera, prev_camera, inputs, defer_post=defer_post)
             finally:
                 self.ldr = saved
         L, cfg = self.lib, self.cfg
-        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        main = torch.cuda.current_stream(self.device)
+        stream = C.c_void_p(main.cuda_stream)
         st = cfg.stages
+        side_ao = cfg.overlap and bool(st & STAGE_SSAO) and bool(st & STAGE_SSR)
+        side_post = self._side_post = cfg.overlap and bool(st & STAGE_BLOOM) and bool(st & STAGE_TAA)
         P = {n: plane_of(t) for n, t in (inputs or self.inputs).items()}
 
         # Prepare (HnPostProcessTask.cpp:671-683)
@@ -123,13 +143,18 @@ class PostProcessChain:
             a = PostFXRenderAttribs(stream, C.pointer(P["depth"]), C.pointer(P["prev_depth"]), C.pointer(P["motion"]), C.pointer(curr_camera),
                                     C.pointer(prev_camera))
             check(L.dfx_postfx_execute(self.postfx, C.byref(a)), "dfx_postfx_execute")
+        if side_ao:
+            self._ao_stream.wait_stream(main)  # PostFX planes (and whatever produced the inputs) are ready
         if st & STAGE_SSR:
             a = SSRRenderAttribs(stream, self.postfx, C.pointer(P["color"]), C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(P["material"]),
                                  C.pointer(P["motion"]), C.pointer(cfg.ssr))
             check(L.dfx_ssr_execute(self.ssr, C.byref(a)), "dfx_ssr_execute")
         if st & STAGE_SSAO:
-            a = SSAORenderAttribs(stream, self.postfx, C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(cfg.ssao))
+            ao_stream = C.c_void_p(self._ao_stream.cuda_stream) if side_ao else stream
+            a = SSAORenderAttribs(ao_stream, self.postfx, C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(cfg.ssao))
             check(L.dfx_ssao_execute(self.ssao, C.byref(a)), "dfx_ssao_execute")
+        if side_ao:
+            main.wait_stream(self._ao_stream)
 
         color = P["color"]
         fuse_compose = cfg.fuse and (st & STAGE_COMPOSE) and (st & STAGE_TAA)      # compose evaluated inside the TAA kernel
@@ -149,6 +174,8 @@ class PostProcessChain:
                                          Rows(0, self.h)), "dfx_pass_compose")
                 color = comp
         if st & STAGE_TAA:
+            while len(self._post_done) > 1:            # Bloom of frame f-2 read the accumulator this frame's TAA overwrites
+                main.wait_event(self._post_done.pop(0))
             a = TAARenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.taa), 0)
             if fuse_compose:
                 check(L.dfx_taa_execute_composed(self.taa, C.byref(a), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale)), "dfx_taa_execute_composed")
@@ -157,6 +184,9 @@ class PostProcessChain:
             acc = Plane()
             check(L.dfx_taa_get_plane(self.taa, 0, 0, C.byref(acc)), "dfx_taa_get_plane")
             color = acc
+        if side_post:
+            self._post_stream.wait_stream(main)
+            stream = C.c_void_p(self._post_stream.cuda_stream)
         if st & STAGE_BLOOM:
             a = BloomRenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.bloom))
             if fuse_tonemap:
@@ -172,6 +202,12 @@ class PostProcessChain:
             ldr = plane_of(self.ldr)
             check(L.dfx_pass_tonemap(stream, C.byref(cfg.tonemap), C.c_float(cfg.ave_log_lum), int(cfg.to_srgb), C.byref(color), C.byref(ldr), Rows(0, self.h)),
                   "dfx_pass_tonemap")
+        if side_post:
+            self.post_event = torch.cuda.Event()
+            self.post_event.record(self._post_stream)
+            self._post_done.append(self.post_event)
+            if not defer_post:
+                main.wait_event(self.post_event)
         self.frame_index = frame_index
         return self.ldr
 
@@ -211,14 +247,19 @@ class PostProcessChain:
                 P["h2d_done"][s].record(P["h2d"])
             main.wait_event(P["h2d_done"][s])
             main.wait_event(P["d2h_done"][s])                        # frame k-2's result has left this LDR buffer
-            self.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], P["inputs"][s], ldr_out=P["ldr"][s])
-            P["compute_done"][s].record(main)
+            self.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], P["inputs"][s], ldr_out=P["ldr"][s], defer_post=True)
+            # the frame is complete when its Bloom + ToneMap (side stream under cfg.overlap) is: the event goes on that stream
+            post = self._post_stream if self._side_post else main
+            if post is not main:
+                post.wait_stream(main)
+            P["compute_done"][s].record(post)
             if ldr_host:
                 with torch.cuda.stream(P["d2h"]):
                     P["d2h"].wait_event(P["compute_done"][s])
                     ldr_host[k % len(ldr_host)].copy_(P["ldr"][s], non_blocking=True)
                     P["d2h_done"][s].record(P["d2h"])
             n += 1
+        self.join()
         main.wait_event(P["d2h_done"][0])
         main.wait_event(P["d2h_done"][1])
         return n
@@ -239,6 +280,7 @@ class PostProcessChain:
             check(L.dfx_taa_get_plane(self.taa, plane_id, 0, C.byref(p)))
         else:
             raise KeyError(effect)
+        torch.cuda.synchronize(self.device)  # side streams included
         return download_plane(p)
 
 

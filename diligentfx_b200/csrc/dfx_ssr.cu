@@ -73,13 +73,18 @@ struct __align__(16) HizLevel
     const float* p;
     int          pitch;
     int          wh; // width | height << 16  (0 for a level the pyramid does not have: every Load returns 0)
+    // The march's per-level screen resolution and its reciprocal (SSR_ComputeIntersection.fx:150-152, 179-183 keep them as
+    // running products by 2 / 0.5; powers of two scale exactly, so sw * 2^-k and 1 / (sw * 2^-k) are the same floats).
+    float resx, resy, irx, iry;
 };
-__device__ __forceinline__ float hiz_load(const HizLevel* lvl, int x, int y, int mip)
+static_assert(sizeof(HizLevel) == 32, "two 128-bit shared loads per level");
+__device__ __forceinline__ float hiz_load(const HizLevel& L, int x, int y)
 {
-    const HizLevel L = lvl[mip & (DFX_MAX_MIPS - 1)];
     const unsigned w = (unsigned)L.wh & 0xFFFFu, hgt = (unsigned)L.wh >> 16;
-    return ((unsigned)x < w && (unsigned)y < hgt) ? __ldg(L.p + (size_t)y * L.pitch + x) : 0.0f;
+    // planes are < 2^31 texels: 32-bit index arithmetic (one IMAD + one IMAD.WIDE instead of the 64-bit expansion)
+    return ((unsigned)x < w && (unsigned)y < hgt) ? __ldg(L.p + (unsigned)(y * L.pitch + x)) : 0.0f;
 }
+__device__ __forceinline__ float hiz_load(const HizLevel* lvl, int x, int y, int mip) { return hiz_load(lvl[mip & (DFX_MAX_MIPS - 1)], x, y); }
 
 // PBR_Common.fxh:181-195
 DFX_HD float ndf_ggx(float NdotH, float a)
@@ -137,15 +142,14 @@ struct PeerTables
 struct NoPeerTables
 {
 };
-__device__ __forceinline__ float hiz_load(const HizLevel* lvl, const PeerTables& P, int x, int y, int mip)
+__device__ __forceinline__ float hiz_load(const HizLevel& L, const PeerTables& P, int x, int y, int mip)
 {
-    const HizLevel L = lvl[mip & (DFX_MAX_MIPS - 1)];
     const unsigned w = (unsigned)L.wh & 0xFFFFu, hgt = (unsigned)L.wh >> 16;
     if (!((unsigned)x < w && (unsigned)y < hgt)) return 0.0f;
     const float* p = P.hiz[(mip & (DFX_MAX_MIPS - 1)) * DFX_MAX_PEERS + P.owner[(y << mip) >> kPeerBlockShift]];
-    return __ldg(p + (size_t)y * L.pitch + x);
+    return __ldg(p + (unsigned)(y * L.pitch + x));
 }
-__device__ __forceinline__ float hiz_load(const HizLevel* lvl, const NoPeerTables&, int x, int y, int mip) { return hiz_load(lvl, x, y, mip); }
+__device__ __forceinline__ float hiz_load(const HizLevel& L, const NoPeerTables&, int x, int y, int) { return hiz_load(L, x, y); }
 // Load of a full-res RGBA plane at the hit texel (0 out of bounds): from the owner of row y.
 template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const PeerTables& P, int x, int y)
 {
@@ -177,7 +181,10 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
     if (threadIdx.y == 1 && threadIdx.x < DFX_MAX_MIPS)
     {
         const int i = threadIdx.x;
-        lvl[i]      = i < hiz.levels ? HizLevel{hiz.lv[i].p, hiz.lv[i].pitch, hiz.lv[i].w | (hiz.lv[i].h << 16)} : HizLevel{nullptr, 0, 0};
+        const float rx = cams[0].f4ViewportSize[0] * (1.0f / float(1 << i)), ry = cams[0].f4ViewportSize[1] * (1.0f / float(1 << i));
+        HizLevel    L  = i < hiz.levels ? HizLevel{hiz.lv[i].p, hiz.lv[i].pitch, hiz.lv[i].w | (hiz.lv[i].h << 16)} : HizLevel{nullptr, 0, 0};
+        L.resx = rx, L.resy = ry, L.irx = 1.0f / rx, L.iry = 1.0f / ry;
+        lvl[i] = L;
     }
     if constexpr (PEER)
     {
@@ -258,8 +265,8 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
     {
         const float3 invD = make_float3(Dr.x != 0.0f ? 1.0f / Dr.x : kFltMax, Dr.y != 0.0f ? 1.0f / Dr.y : kFltMax, Dr.z != 0.0f ? 1.0f / Dr.z : kFltMax);
         int   mip = baseMip;
-        float resx = sw * inv0, resy = sh * inv0;
-        float irx = 1.0f / resx, iry = 1.0f / resy;
+        const float resx = sw * inv0, resy = sh * inv0;
+        const float irx = 1.0f / resx, iry = 1.0f / resy;
         float uox = 0.005f * float(1 << baseMip) / sw, uoy = 0.005f * float(1 << baseMip) / sh;
         uox = Dr.x < 0.0f ? -uox : uox, uoy = Dr.y < 0.0f ? -uoy : uoy;
         const float fox = Dr.x < 0.0f ? 0.0f : 1.0f, foy = Dr.y < 0.0f ? 0.0f : 1.0f;
@@ -272,31 +279,28 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
             t   = fminf(tx, ty);
             pos = O + t * Dr;
         }
-        uint32_t i = 0u;
-        while (i < A.MaxTraversalIntersections && mip >= baseMip)
+        // The loop is issue-bound (one dependent Hi-Z load per iteration, ~36 iterations per ray): per-level constants come
+        // from one 32-byte shared-memory entry, the level update is branch-free, the trip counter counts down.
+        const float oxi = O.x * invD.x, oyi = O.y * invD.y, ozi = O.z * invD.z;
+        int         left = (int)min(A.MaxTraversalIntersections, 0x7fffffffu);
+        while (left > 0 && mip >= baseMip)
         {
-            const float mx = resx * pos.x, my = resy * pos.y;
-            const float surf = hiz_load(lvl, PT, (int)mx, (int)my, mip);
+            const HizLevel L  = lvl[mip];
+            const float    mx = L.resx * pos.x, my = L.resy * pos.y;
+            const float    surf = hiz_load(L, PT, (int)mx, (int)my, mip);
             // AdvanceRay :88-136
-            const float px = (floorf(mx) + fox) * irx + uox, py = (floorf(my) + foy) * iry + uoy;
-            const float tx = px * invD.x - O.x * invD.x, ty = py * invD.y - O.y * invD.y;
-            float       tz = surf * invD.z - O.z * invD.z;
-            tz             = Dr.z > 0.0f ? tz : kFltMax;
+            const float px = (floorf(mx) + fox) * L.irx + uox, py = (floorf(my) + foy) * L.iry + uoy;
+            const float tx = px * invD.x - oxi, ty = py * invD.y - oyi;
+            const float tz = Dr.z > 0.0f ? surf * invD.z - ozi : kFltMax;
             const float tmin  = fminf(fminf(tx, ty), tz);
             const bool  above = surf > pos.z;
             const bool  skipped = (__float_as_uint(tmin) != __float_as_uint(tz)) && above;
             t   = above ? tmin : t;
             pos = O + t * Dr;
-            const bool outOfRange = skipped && (mip >= 6);
-            if (!outOfRange)
-            {
-                mip += skipped ? 1 : -1;
-                const float s = skipped ? 0.5f : 2.0f, is = skipped ? 2.0f : 0.5f;
-                resx *= s, resy *= s, irx *= is, iry *= is;
-            }
-            ++i;
+            mip += skipped ? (mip >= 6 ? 0 : 1) : -1; // a skip at the coarsest level stays there (:179-183)
+            --left;
         }
-        validHit = (i <= A.MaxTraversalIntersections);
+        validHit = true; // i <= MaxTraversalIntersections always holds at loop exit (:187)
     }
     const float3 hitVS = screen_to_view(pos.x, pos.y, pos.z, cam);
 
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         if (!(mdx < (2.0f / sw) && mdy < (2.0f / sh)))
         {
             const int   tx = (int)(sw * pos.x), ty = (int)(sh * pos.y);
-            const float surfD = hiz_load(lvl, PT, tx, ty, 0);
+            const float surfD = hiz_load(lvl[0], PT, tx, ty, 0);
             if (!is_background(surfD))
             {
                 const float3 hitN = xyz(hit_load0<true>(normal, PT, tx, ty));

@@ -356,6 +356,32 @@ def test_fused_chain_equals_unfused(ctx):
     a.close(), b.close()
 
 
+def test_async_compute_equals_single_stream(ctx):
+    """SSAO beside SSR on a second stream and Bloom + ToneMap beside the next frame's front half on a third (ChainConfig.overlap)
+    only reorders independent work: every LDR frame must be bit-identical to the single-stream run, also when the caller
+    defers the join to the end of the sequence (a missing event would show up as a torn frame)."""
+    import torch
+
+    from diligentfx_b200.chain import ChainConfig, PostProcessChain
+    seq, h, w = ctx["seq"], ctx["h"], ctx["w"]
+    a, b, c = (PostProcessChain(w, h, ChainConfig(overlap=o)) for o in (True, False, True))
+    deferred = []
+    for rep in range(3):  # 12 frames: long enough for the ping-pong planes to be reused several times
+        for k, fr in enumerate(seq):
+            idx = rep * len(seq) + k
+            f2 = {**fr, "frame": idx}
+            la, lb = a.run_frame(f2).cpu().numpy(), b.run_frame(f2).cpu().numpy()
+            assert np.array_equal(la, lb), f"frame {idx}: max abs diff {np.abs(la - lb).max()}"
+            c.upload(f2)
+            out = torch.empty_like(c.ldr)
+            c.execute(idx, f2["curr_camera"], f2["prev_camera"], ldr_out=out, defer_post=True)
+            deferred.append((out, lb))
+    c.join()
+    for idx, (out, want) in enumerate(deferred):
+        assert np.array_equal(out.cpu().numpy(), want), f"deferred frame {idx} differs"
+    a.close(), b.close(), c.close()
+
+
 def test_full_chain_four_frames(ctx):
     from diligentfx_b200.chain import ChainConfig, PostProcessChain
     o, seq, h, w = ctx["o"], ctx["seq"], ctx["h"], ctx["w"]

@@ -22,6 +22,26 @@ def test_strip_bounds_are_aligned_and_cover():
     assert strip_bounds(4320, 8)[0] == (0, 576)  # ceil(67.5 blocks / 8): the first strips take 9 blocks of 64 rows
 
 
+def test_cost_balanced_strip_bounds():
+    from diligentfx_b200.strips import reflective_block_cost
+    # a frame whose lower 60 % is reflective: equal-height strips would give the last rank ~12x the work of the first
+    h = 4320
+    frac = [0.0] * 108 + [1.0] * 162  # per row of a 270-row preview
+    w = reflective_block_cost(frac, h)
+    assert len(w) == 68 and w[0] == 64.0 and abs(w[40] - 64 * 12.0) < 1e-9
+    for n in (2, 3, 4, 8):
+        b = strip_bounds(h, n, weights=w)
+        assert b[0][0] == 0 and b[-1][1] == h and len(b) == n
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(b, b[1:]))
+        assert all(y0 % 64 == 0 and y1 > y0 for y0, y1 in b)
+        cost = [sum(w[y0 // 64:-(-y1 // 64)]) for y0, y1 in b]
+        assert max(cost) <= 1.25 * sum(cost) / n, (n, b, cost)  # within a block's worth of the ideal share
+        equal = strip_bounds(h, n)
+        assert max(cost) < max(sum(w[y0 // 64:-(-y1 // 64)]) for y0, y1 in equal)
+    assert strip_bounds(128, 2, weights=[0.0, 5.0]) == [(0, 64), (64, 128)]  # nobody is left without a block
+    assert strip_bounds(64, 3, weights=[1.0])[-1][1] == 64  # fewer blocks than ranks: empty strips are allowed
+
+
 def _free_port() -> int:
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -29,9 +29,9 @@ def _worker(rank: int, world: int, port: int, w: int, h: int, frames: int, out_d
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         seq = synth.generate_sequence(w, h, frames)
-        bounds = strip_bounds(h, world)
+        bounds = strip_bounds(h, world, weights=[1.0, 3.0, 3.0, 3.0][:h // 64] if peer else None)  # peer run: unequal, cost-balanced strips
         y0, y1 = bounds[rank]
-        runner = SsrStripRunner(w, h, peer=peer, poison=True)
+        runner = SsrStripRunner(w, h, peer=peer, poison=True, bounds=bounds)
         ref = PostProcessChain(w, h, ChainConfig(stages=STAGE_POSTFX | STAGE_SSR)) if rank == 0 else None
         for fr in seq:
             inputs = {}
@@ -65,7 +65,7 @@ def test_ssr_strips_bit_identical_on_two_gpus(built, tmp_path, peer):
     w, h, world = 320, 256, 2
     mp.spawn(_worker, args=(world, _free_port(), w, h, 3, str(tmp_path), peer), nprocs=world, join=True)
     ref = np.load(tmp_path / "ref.npy")
-    for r, (y0, y1) in enumerate(strip_bounds(h, world)):
+    for r, (y0, y1) in enumerate(strip_bounds(h, world, weights=[1.0, 3.0, 3.0, 3.0] if peer else None)):
         got = np.load(tmp_path / f"strip_{r}.npy")
         assert np.isfinite(got).all(), "poison rows leaked into the owned strip: an exchange is missing"
         assert np.array_equal(got, ref[y0:y1]), f"strip {r} differs from the single-GPU result (max abs {np.abs(got - ref[y0:y1]).max()})"

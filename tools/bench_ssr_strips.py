@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--height", type=int, default=4320)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--balance", action="store_true", help="cost-balanced strip heights (reflective pixels weigh more) instead of equal ones")
     ap.add_argument("--peer", action="store_true", help="ray march with NVLink peer loads instead of gathering Hi-Z / colour / normal")
     a = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -40,7 +41,13 @@ def main():
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("gloo", rank=0, world_size=1)
     W, H = a.width, a.height
-    bounds = strips.strip_bounds(H, world)
+    weights = None
+    if a.balance and world > 1:
+        # cost-balanced strips: fraction of reflection samples per row of a small rendering of the same frame
+        small = synth.generate_frame(synth.make_scene(7), 0, 480, 270)
+        refl = (small["material"][..., 0] <= 0.2) & (small["depth"] < 1.0)  # SSR defaults: roughness in .x, threshold 0.2
+        weights = strips.reflective_block_cost(refl.mean(axis=1), H)
+    bounds = strips.strip_bounds(H, world, weights=weights)
     y0, y1 = bounds[rank]
     # two consecutive frames of the camera path; only this rank's rows (+1 so that chunked generation lines up) are ray-cast
     scene = synth.make_scene(7)
@@ -52,7 +59,7 @@ def main():
         for n in INPUT_SPECS:
             full[n][y0:y1] = torch.from_numpy(fr[n]).to(dev)
         frames.append((full, cam.attribs, prev.attribs))
-    runner = strips.SsrStripRunner(W, H, peer=a.peer, input_sets=2)
+    runner = strips.SsrStripRunner(W, H, peer=a.peer, input_sets=2, bounds=bounds)
     if runner.peer:  # the G-buffer lives in the runner's exported planes (double-buffered), as a renderer would write it
         for i, (full, _, _) in enumerate(frames):
             for n in ("depth", "color", "normal"):
