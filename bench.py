@@ -61,6 +61,20 @@ def measured_hbm_peak() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(pass_name: str, width: int, height: int):
+    """DRAM bytes per launch of the pass's kernel from the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json),
+    or None when the capture has no entry for it or was taken at another frame size (3840x2160)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        k = d["kernels"][d["pass_to_kernel"][pass_name]]
+    except (OSError, KeyError, ValueError):
+        return None, "no ncu capture for this kernel"
+    if (width, height) != (3840, 2160):
+        return None, "ncu capture is for 3840x2160"
+    return int(k["dram_bytes"]), "profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -285,8 +299,9 @@ def main() -> None:
         for p in passes:
             p["share"] = round(p["ms"] / step_sum, 4) if step_sum else 0.0
         top = max(passes, key=lambda p: p["ms"])
-        roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": None,
-                "peak_source": peak_src, "share_of_step": top["share"],
+        traffic, traffic_src = ncu_traffic(top["pass"], W, H)
+        roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
+                "traffic_source": traffic_src, "alg_bytes": top["alg_bytes"], "peak_source": peak_src, "share_of_step": top["share"],
                 "chain": {"alg_bytes_per_px": round(sum(PASS_BYTES_PER_PX.get(p["pass"], 0.0) for p in passes), 2),
                           "achieved": round(sum(p["alg_bytes"] for p in passes) / (ms_per_step * 1e-3) / 1e9, 1)}}
         roof["chain"]["frac"] = round(roof["chain"]["achieved"] / peak, 4)

@@ -80,8 +80,8 @@ struct View
     T*  p;
     int pitch; // in elements of T
     int w, h;
-    __device__ __forceinline__ T&       at(int x, int y) const { return p[(size_t)y * pitch + x]; }
-    __device__ __forceinline__ const T* row(int y) const { return p + (size_t)y * pitch; }
+    __device__ __forceinline__ T&       at(int x, int y) const { return p[(unsigned)(y * pitch + x)]; } // planes hold < 2^31 texels (host-checked): 32-bit index, one IMAD + one IMAD.WIDE
+    __device__ __forceinline__ const T* row(int y) const { return p + (unsigned)(y * pitch); }
 };
 
 template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
@@ -89,22 +89,22 @@ template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p
 // Texture.Load semantics: out of bounds -> 0
 __device__ __forceinline__ float load0(const View<const float>& v, int x, int y)
 {
-    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (size_t)y * v.pitch + x) : 0.0f;
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (unsigned)(y * v.pitch + x)) : 0.0f;
 }
 __device__ __forceinline__ float2 load0(const View<const float2>& v, int x, int y)
 {
-    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (size_t)y * v.pitch + x) : make_float2(0.f, 0.f);
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (unsigned)(y * v.pitch + x)) : make_float2(0.f, 0.f);
 }
 __device__ __forceinline__ float4 load0(const View<const float4>& v, int x, int y)
 {
-    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (size_t)y * v.pitch + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (unsigned)(y * v.pitch + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 template <class T>
 __device__ __forceinline__ T loadc(const View<const T>& v, int x, int y) // clamp addressing
 {
     x = min(max(x, 0), v.w - 1);
     y = min(max(y, 0), v.h - 1);
-    return __ldg(v.p + (size_t)y * v.pitch + x);
+    return __ldg(v.p + (unsigned)(y * v.pitch + x));
 }
 
 template <class T>
@@ -113,6 +113,7 @@ inline bool make_view(const dfx_plane* pl, int fmt, View<T>& v)
     if (!pl || !pl->ptr || pl->format != fmt || pl->width <= 0 || pl->height <= 0) return false;
     if (pl->pitch_bytes % sizeof(T) != 0 || pl->pitch_bytes < (size_t)pl->width * sizeof(T)) return false;
     if (reinterpret_cast<uintptr_t>(pl->ptr) % sizeof(T) != 0) return false;
+    if ((pl->pitch_bytes / sizeof(T)) * (size_t)pl->height >= (size_t(1) << 31)) return false; // kernels index texels with 32 bits
     v.p     = static_cast<T*>(pl->ptr);
     v.pitch = int(pl->pitch_bytes / sizeof(T));
     v.w     = pl->width;
@@ -287,15 +288,29 @@ DFX_HD Bilin bilinear_uc(float lx, float ly, int w, int h)
 }
 
 // Fast (approximate, <= 2 ulp) arithmetic for the issue-bound kernels; used only where the parity budget allows.
-DFX_HD float fdiv(float a, float b) { return __fdividef(a, b); }
-DFX_HD float frcp(float a) { return __fdividef(1.0f, a); }
+// The .ftz forms are ONE MUFU instruction each; the non-ftz forms (__fdividef, rsqrtf, sqrt.approx.f32) wrap it in a
+// denormal rescue (FSETP + 2-3 FMUL/FSEL) that cost 20 % of the TAA kernel's instructions. Denormal operands do not occur
+// in this path (depths, luminances and squared lengths are either 0 or far above 1e-38), and 0 behaves the same.
+DFX_HD float frcp(float a)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+DFX_HD float fdiv(float a, float b) { return a * frcp(b); }
 DFX_HD float fsqrt(float a)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r;
 }
-DFX_HD float3 fnormalize(float3 a) { return a * rsqrtf(dot(a, a)); }
+DFX_HD float frsqrt(float a)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+DFX_HD float3 fnormalize(float3 a) { return a * frsqrt(dot(a, a)); }
 
 // The fixed-function sampler resolves the sample position to 8 fractional bits: snap to the nearest 1/256 texel.
 DFX_HD float snap8(float p) { return floorf(p * 256.0f + 0.5f) * (1.0f / 256.0f); }

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
         const float3 axis       = fnormalize(make_float3(so * view.z, -co * view.z, co * view.y - so * view.x)); // cross(sliceDir, view)
         const float3 projN      = nvs - axis * dot(nvs, axis);
         const float  projN2     = dot(projN, projN);
-        const float  invLen     = rsqrtf(projN2);
+        const float  invLen     = frsqrt(projN2);
         const float  projNLen   = projN2 * invLen;
         const float  cosNorm    = saturate(dot(projN, view) * invLen);
         const float  N          = signf(dot(orthoSlice, projN)) * fast_acos(cosNorm);
@@ -206,14 +206,14 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
             const float u0 = u + offx, v0 = v + offy, u1 = u - offx, v1 = v - offy;
             const int   ax = min(max(__float2int_rd(u0 * lv.fw), 0), lv.w - 1), ay = min(max(__float2int_rd(v0 * lv.fh), 0), lv.h - 1);
             const int   bx = min(max(__float2int_rd(u1 * lv.fw), 0), lv.w - 1), by = min(max(__float2int_rd(v1 * lv.fh), 0), lv.h - 1);
-            const float da = __ldg(lv.p + (size_t)ay * lv.pitch + ax), db = __ldg(lv.p + (size_t)by * lv.pitch + bx);
+            const float da = __ldg(lv.p + (unsigned)(ay * lv.pitch + ax)), db = __ldg(lv.p + (unsigned)(by * lv.pitch + bx));
             // view.xy = z * ((uv - 0.5) * k) with (uv - 0.5) * k = (centre - 0.5) * k +- smp^2 * (slice direction * k)
             const float za = fdiv(cam.m32 - da * cam.m33, da * cam.m23 - cam.m22), zb = fdiv(cam.m32 - db * cam.m33, db * cam.m23 - cam.m22);
             const float ox = smp * smp * sdkx, oy = smp * smp * sdky;
             const float3 d0 = make_float3(za * (cxk + ox), za * (cyk + oy), za) - pvs;
             const float3 d1 = make_float3(zb * (cxk - ox), zb * (cyk - oy), zb) - pvs;
             const float  q0 = dot(d0, d0), q1 = dot(d1, d1);
-            const float  r0 = rsqrtf(q0), r1 = rsqrtf(q1);
+            const float  r0 = frsqrt(q0), r1 = frsqrt(q1);
             const float  l0 = q0 * r0, l1 = q1 * r1; // lengths
             const float  w0 = saturate(l0 * falloffMul + falloffAdd), w1 = saturate(l1 * falloffMul + falloffAdd);
             if (ALGO == DFX_SSAO_ALGORITHM_VBAO)

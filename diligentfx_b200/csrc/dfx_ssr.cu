@@ -155,7 +155,7 @@ template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<co
 {
     if (!((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* base = (NORMAL ? P.normal : P.color)[P.owner[y >> kPeerBlockShift]];
-    return __ldg(base + (size_t)y * v.pitch + x);
+    return __ldg(base + (unsigned)(y * v.pitch + x));
 }
 template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
 
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(c
     const float3 pws = inv_project_position(posx * cam.ivw, posy * cam.ivh, __ldg(&depth.at(x, y)), S.vp_inv);
     const float3 nws = xyz(__ldg(&normal.at(x, y)));
     const float3 toCam = camPos - pws;
-    const float  camDist2 = dot(toCam, toCam), invCamDist = rsqrtf(camDist2);
+    const float  camDist2 = dot(toCam, toCam), invCamDist = frsqrt(camDist2);
     const float3 vws = toCam * invCamDist;
     const float  NdotV = saturate(dot(nws, vws));
     const float  rough = __ldg(&roughness.at(x, y));
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(c
         // ComputeWeightRayLength :60-86
         float        weight, raylen;
         const float4 rd = __ldg(&raydir.at(sx, sy));
-        const float  len2 = dot(xyz(rd), xyz(rd)), invLen = rsqrtf(len2), len = len2 * invLen;
+        const float  len2 = dot(xyz(rd), xyz(rd)), invLen = frsqrt(len2), len = len2 * invLen;
         if (!(len >= 1e-6f)) // also catches len2 == 0 (0 * inf = NaN)
         {
             weight = 1e-6f, raylen = 1e-6f;
