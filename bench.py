@@ -184,7 +184,7 @@ def main() -> None:
     import torch.distributed as dist
 
     from diligentfx_b200 import capi, synth
-    from diligentfx_b200.chain import INPUT_SPECS, ChainConfig, PostProcessChain
+    from diligentfx_b200.chain import INPUT_SPECS, PACKED_SPECS, ChainConfig, PostProcessChain, pack_frame, widen_frame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,14 +200,22 @@ def main() -> None:
     lib = capi.load()
 
     # ---- synthetic data: `frames` consecutive frames of one camera path per rank (rank-specific seed) ----
+    # The renderer hands the G-buffer over in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8
+    # material, D32F depths: Hydrogent/src/Tasks/HnBeginFrameTask.cpp:63-69); the fp32 planes the passes read are the exact
+    # widening of those, on the device-resident arm as well, so both arms process the same values.
     seq = synth.generate_sequence(W, H, args.frames, seed=7 + rank)
+    packed = [pack_frame(fr, pin=True) for fr in seq]
+    seq = [widen_frame(p) for p in packed]
     host = [{n: torch.from_numpy(np.ascontiguousarray(fr[n])).pin_memory() for n in INPUT_SPECS} for fr in seq]
     resident = [{n: t.to(dev) for n, t in hf.items()} for hf in host]
     cams = [(fr["curr_camera"], fr["prev_camera"]) for fr in seq]
-    h2d_bytes = sum(t.numel() * 4 for t in host[0].values())
+    packed_keys = [s[0] for s in PACKED_SPECS.values()] + ["depth", "prev_depth"]
+    h2d_bytes = sum(packed[0][k].numel() * packed[0][k].element_size() for k in packed_keys)
+    h2d_bytes_fp32 = sum(t.numel() * 4 for t in host[0].values())
     chain = PostProcessChain(W, H, ChainConfig(overlap=not args.no_overlap), device=dev)
     ldr_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    d2h_bytes = ldr_host.numel() * 4
+    ldr8_hosts = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    d2h_bytes, d2h_bytes_fp32 = ldr8_hosts[0].numel(), ldr_host.numel() * 4
 
     def barrier():
         if world > 1:
@@ -228,14 +236,17 @@ def main() -> None:
 
     ldr_hosts = [ldr_host, torch.empty_like(ldr_host).pin_memory()]
 
-    def e2e_frames(steps: int):
+    def e2e_frames(steps: int, src):
         # host frame dicts for the public streaming API: pinned G-buffer planes + cameras + consecutive frame index
         for _ in range(steps):
             idx, slot = next_frame()
-            yield {**host[slot], "curr_camera": cams[slot][0], "prev_camera": cams[slot][1], "frame": idx}
+            yield {**src[slot], "curr_camera": cams[slot][0], "prev_camera": cams[slot][1], "frame": idx}
 
-    def run_e2e(steps: int):
-        chain.stream_frames(e2e_frames(steps), ldr_hosts)
+    def run_e2e(steps: int):      # the G-buffer crosses PCIe in its render-target formats, the frame comes back as RGBA8
+        chain.stream_frames(e2e_frames(steps, packed), ldr8_hosts, packed=True)
+
+    def run_e2e_fp32(steps: int):  # everything crosses PCIe as fp32 (64 B/px in, 16 B/px out)
+        chain.stream_frames(e2e_frames(steps, host), ldr_hosts)
 
     def timed(fn, steps: int, whole: bool = False) -> float:
         barrier()
@@ -271,6 +282,9 @@ def main() -> None:
     run_e2e(3)
     e2e_ms = timed(run_e2e, K, whole=True) / K
     e2e_value = world * W * H / 1e6 / (e2e_ms / 1e3)
+    run_e2e_fp32(3)
+    e2e32_ms = timed(run_e2e_fp32, max(K // 4, 4), whole=True) / max(K // 4, 4)
+    e2e32_value = world * W * H / 1e6 / (e2e32_ms / 1e3)
 
     # ---- per-pass device times (CUDA events on the launching stream, same steps) ----
     passes, roof = [], None
@@ -320,10 +334,15 @@ def main() -> None:
                        "width": W, "height": H, "parallelism": f"replicas x{world} (independent frame sequences, no data-path collective)",
                        "streams": ("3 per GPU: SSR chain + TAA | SSAO chain | Bloom + ToneMap (overlaps the next frame's front half); per-pass times in `passes` are "
                                    "measured serially on one stream" if chain.cfg.overlap else "1 per GPU"),
-                       "cache": f"{args.frames} distinct resident G-buffers of {h2d_bytes / 1e6:.0f} MB cycled: inputs larger than the 126 MB L2"},
+                       "cache": f"{args.frames} distinct resident G-buffers of {h2d_bytes_fp32 / 1e6:.0f} MB cycled: inputs larger than the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes)},
+                    "d2h_bytes_per_step": int(d2h_bytes),
+                    "formats": "host G-buffer in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8 material, fp32 depth + "
+                               "previous depth = 30 B/px), widened on the device; result read back as RGBA8 (4 B/px); PostProcessChain.stream_frames("
+                               "packed=True): copy-in / compute / copy-out pipelined on 3 streams",
+                    "fp32_transfers": {"value": round(e2e32_value, 2), "ms_per_step": round(e2e32_ms, 4), "h2d_bytes_per_step": int(h2d_bytes_fp32),
+                                       "d2h_bytes_per_step": int(d2h_bytes_fp32)}},
             "roofline": roof, "cpu_baseline": cpu, "passes": passes,
         }
         print(json.dumps(rec), flush=True)

@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(REPO_ROOT, "include", "dfx_b200.h")
 
 DFX_OK, DFX_ERR_INVALID_ARG, DFX_ERR_CUDA, DFX_ERR_NOT_PREPARED, DFX_ERR_UNSUPPORTED = range(5)
 FORMAT_R32F, FORMAT_RG32F, FORMAT_RGBA32F, FORMAT_R8U = 1, 2, 3, 4
+FORMAT_RGBA16F, FORMAT_RG16F, FORMAT_RG8U, FORMAT_RGBA8U = 5, 6, 7, 8   # transfer formats (unpack / pack only)
 MAX_MIPS = 8
 
 TAA_FLAG_GAUSSIAN, TAA_FLAG_BICUBIC, TAA_FLAG_YCOCG = 1, 2, 4
@@ -193,12 +194,15 @@ _FMT_OF = {(1,): FORMAT_R32F, (2,): FORMAT_RG32F, (4,): FORMAT_RGBA32F}
 
 
 def plane_of(t, fmt: int | None = None) -> Plane:
-    """Describe a contiguous torch CUDA tensor (H,W), (H,W,2) or (H,W,4) float32 / (H,W) uint8 as a dfx_plane."""
+    """Describe a contiguous torch CUDA tensor (H,W), (H,W,2) or (H,W,4) float32 / (H,W) uint8 as a dfx_plane; transfer
+    formats: (H,W,4) / (H,W,2) float16 and (H,W,2) / (H,W,4) uint8."""
     import torch
     assert t.is_cuda and t.is_contiguous(), "plane tensors must be contiguous CUDA tensors"
     h, w = int(t.shape[0]), int(t.shape[1])
     if t.dtype == torch.uint8:
-        f, bpp = FORMAT_R8U, 1
+        f, bpp = {2: (FORMAT_R8U, 1), 3: {2: (FORMAT_RG8U, 2), 4: (FORMAT_RGBA8U, 4)}.get(int(t.shape[-1]))}[t.dim()]
+    elif t.dtype == torch.float16:
+        f, bpp = {2: (FORMAT_RG16F, 4), 4: (FORMAT_RGBA16F, 8)}[int(t.shape[2])]
     else:
         assert t.dtype == torch.float32
         ch = 1 if t.dim() == 2 else int(t.shape[2])

@@ -23,6 +23,52 @@ STAGE_ALL = 127
 INPUT_SPECS = {  # name -> trailing channel count (0 = scalar plane)
     "depth": 0, "prev_depth": 0, "motion": 2, "normal": 4, "color": 4, "material": 4,
 }
+# Transfer formats of the G-buffer planes that are narrower than fp32 in the reference (Hydrogent/src/Tasks/HnBeginFrameTask.cpp:
+# 63-68): input name -> (key in a packed frame, dtype, channels). Depth (D32_FLOAT) and the previous depth travel as fp32.
+PACKED_SPECS = {
+    "color": ("color16", torch.float16, 4), "normal": ("normal16", torch.float16, 4), "motion": ("motion16", torch.float16, 2),
+    "material": ("material8", torch.uint8, 2),
+}
+
+
+def pack_frame(frame: dict, pin: bool = False) -> dict:
+    """Host-side: a frame dict with the G-buffer in the reference's render-target formats (what a renderer would hand over).
+    Colour is clamped to the half range; material keeps roughness (.x) and metallic (.y) as UNORM8."""
+    out = {k: v for k, v in frame.items() if k not in PACKED_SPECS}
+    for name, (key, dt, ch) in PACKED_SPECS.items():
+        a = np.asarray(frame[name], np.float32)[..., :ch]
+        if dt == torch.uint8:
+            t = torch.from_numpy(np.floor(np.clip(a, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8))
+        else:
+            t = torch.from_numpy(np.clip(a, -65504.0, 65504.0).astype(np.float16))
+        out[key] = t.contiguous().pin_memory() if pin else t.contiguous()
+    for name in ("depth", "prev_depth"):
+        t = frame[name] if isinstance(frame[name], torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frame[name], np.float32))
+        out[name] = t.pin_memory() if pin and not t.is_pinned() else t
+    return out
+
+
+def widen_frame(packed: dict) -> dict:
+    """The fp32 frame dict the device sees after dfx_pass_unpack_plane (exact widening; material z = w = 0)."""
+    out = {k: v for k, v in packed.items() if k not in {s[0] for s in PACKED_SPECS.values()}}
+    for name, (key, dt, ch) in PACKED_SPECS.items():
+        a = packed[key].numpy()
+        if dt == torch.uint8:
+            m = np.zeros(a.shape[:2] + (4,), np.float32)
+            m[..., :ch] = a.astype(np.float32) / np.float32(255.0)
+            out[name] = m
+        else:
+            out[name] = a.astype(np.float32)
+    for name in ("depth", "prev_depth"):
+        out[name] = packed[name].numpy() if isinstance(packed[name], torch.Tensor) else packed[name]
+    return out
+
+
+def pack_ldr8(ldr: np.ndarray) -> np.ndarray:
+    """Host restatement of dfx_pass_pack_ldr8 (D3D UNORM rule: saturate, * 255, + 0.5, truncate; NaN -> 0)."""
+    v = np.nan_to_num(np.asarray(ldr, np.float32), nan=0.0)
+    # the kernel evaluates x * 255 + 0.5 as one fused multiply-add: exact in float64, rounded once to float32
+    return (np.clip(v, 0.0, 1.0).astype(np.float64) * 255.0 + 0.5).astype(np.float32).astype(np.uint8)
 
 
 @dataclass
@@ -216,7 +262,7 @@ class PostProcessChain:
         self.upload(frame)
         return self.execute(frame["frame"], frame["curr_camera"], frame["prev_camera"])
 
-    def stream_frames(self, frames, ldr_host: list | None = None) -> int:
+    def stream_frames(self, frames, ldr_host: list | None = None, packed: bool = False) -> int:
         """Offline throughput path (BASELINE.json config 5: batches of frames): a double-buffered pipeline over three CUDA
         streams. While frame k runs on the compute stream, frame k+1's G-buffer is copied from (pinned) host memory on a
         copy stream and frame k-1's LDR result is copied back on a read-back stream; PCIe is full duplex, so the two copy
@@ -224,6 +270,11 @@ class PostProcessChain:
 
         `frames`: iterable of frame dicts (host planes + cameras + "frame" index). `ldr_host`: optional list of pinned
         (H, W, 4) float32 host tensors that receive the results (reused round-robin). Returns the number of frames run.
+
+        `packed=True`: the frames carry the G-buffer in the reference's render-target formats (`pack_frame`: colour and
+        normal RGBA16F, motion RG16F, material RG8; depths stay fp32) and `ldr_host` holds (H, W, 4) uint8 tensors: 30 B/px
+        cross PCIe instead of 64, 4 B/px come back instead of 16. The device widens them (dfx_pass_unpack_plane) into the
+        same fp32 planes, so the chain computes exactly what it computes on `widen_frame(packed_frame)`.
         """
         dev = self.device
         if not hasattr(self, "_pipe"):
@@ -234,29 +285,47 @@ class PostProcessChain:
             for e in self._pipe["compute_done"] + self._pipe["d2h_done"]:
                 e.record(torch.cuda.current_stream(dev))
         P = self._pipe
+        if packed and "staging" not in P:
+            mk16 = lambda: {n: torch.empty((self.h, self.w, c), dtype=dt, device=dev) for n, (_, dt, c) in PACKED_SPECS.items()}  # noqa: E731
+            P["staging"] = [mk16(), mk16()]
+            P["ldr8"] = [torch.empty((self.h, self.w, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
         main = torch.cuda.current_stream(dev)
+        L, full = self.lib, Rows(0, self.h)
         n = 0
         for k, fr in enumerate(frames):
             s = k & 1
             with torch.cuda.stream(P["h2d"]):
                 P["h2d"].wait_event(P["compute_done"][s])          # frame k-2 no longer reads this input set
                 for name in INPUT_SPECS:
+                    if packed and name in PACKED_SPECS:
+                        P["staging"][s][name].copy_(fr[PACKED_SPECS[name][0]], non_blocking=True)
+                        continue
                     src = fr[name]
                     t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, np.float32))
                     P["inputs"][s][name].copy_(t, non_blocking=True)
                 P["h2d_done"][s].record(P["h2d"])
             main.wait_event(P["h2d_done"][s])
             main.wait_event(P["d2h_done"][s])                        # frame k-2's result has left this LDR buffer
+            if packed:                                               # widen the transfer formats into the fp32 planes the passes read
+                stream = C.c_void_p(main.cuda_stream)
+                for name in PACKED_SPECS:
+                    src, dst = plane_of(P["staging"][s][name]), plane_of(P["inputs"][s][name])
+                    check(L.dfx_pass_unpack_plane(stream, C.byref(src), C.byref(dst), full), "dfx_pass_unpack_plane")
             self.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], P["inputs"][s], ldr_out=P["ldr"][s], defer_post=True)
             # the frame is complete when its Bloom + ToneMap (side stream under cfg.overlap) is: the event goes on that stream
             post = self._post_stream if self._side_post else main
             if post is not main:
                 post.wait_stream(main)
+            result = P["ldr"][s]
+            if packed:
+                src, dst = plane_of(P["ldr"][s]), plane_of(P["ldr8"][s])
+                check(L.dfx_pass_pack_ldr8(C.c_void_p(post.cuda_stream), C.byref(src), C.byref(dst), full), "dfx_pass_pack_ldr8")
+                result = P["ldr8"][s]
             P["compute_done"][s].record(post)
             if ldr_host:
                 with torch.cuda.stream(P["d2h"]):
                     P["d2h"].wait_event(P["compute_done"][s])
-                    ldr_host[k % len(ldr_host)].copy_(P["ldr"][s], non_blocking=True)
+                    ldr_host[k % len(ldr_host)].copy_(result, non_blocking=True)
                     P["d2h_done"][s].record(P["d2h"])
             n += 1
         self.join()

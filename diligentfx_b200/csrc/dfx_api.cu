@@ -151,6 +151,10 @@ static size_t bytes_per_texel(int fmt)
         case DFX_FORMAT_RG32F: return 8;
         case DFX_FORMAT_RGBA32F: return 16;
         case DFX_FORMAT_R8U: return 1;
+        case DFX_FORMAT_RGBA16F: return 8;
+        case DFX_FORMAT_RG16F: return 4;
+        case DFX_FORMAT_RG8U: return 2;
+        case DFX_FORMAT_RGBA8U: return 4;
         default: return 0;
     }
 }

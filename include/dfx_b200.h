@@ -56,7 +56,12 @@ typedef enum dfx_format
     DFX_FORMAT_R32F    = 1, /* depth, AO, history length, variance, roughness …            4 B/texel */
     DFX_FORMAT_RG32F   = 2, /* motion vectors, blue noise                                  8 B/texel */
     DFX_FORMAT_RGBA32F = 3, /* colour, normal (xyz_), material, radiance, bloom levels    16 B/texel */
-    DFX_FORMAT_R8U     = 4  /* SSR reflection mask (stands in for the D16 stencil mask)    1 B/texel */
+    DFX_FORMAT_R8U     = 4, /* SSR reflection mask (stands in for the D16 stencil mask)    1 B/texel */
+    /* transfer formats (dfx_pass_unpack_plane / dfx_pass_pack_ldr8 only; the passes compute on the fp32 formats above) */
+    DFX_FORMAT_RGBA16F = 5, /* scene colour, normal as the G-buffer stores them             8 B/texel */
+    DFX_FORMAT_RG16F   = 6, /* motion vectors                                               4 B/texel */
+    DFX_FORMAT_RG8U    = 7, /* material (roughness, metallic) UNORM                         2 B/texel */
+    DFX_FORMAT_RGBA8U  = 8  /* tone-mapped sRGB frame as a swap chain stores it             4 B/texel */
 } dfx_format;
 
 /* A pitched 2-D array in HBM: row y starts at (char*)ptr + y*pitch_bytes. Stands in for ITextureView. */
@@ -562,6 +567,16 @@ DFX_API dfx_status dfx_taa_execute_composed(dfx_taa* fx, const dfx_taa_render_at
                                             float ssr_scale, float ssao_scale);
 DFX_API dfx_status dfx_taa_get_plane(const dfx_taa* fx, int32_t id, uint32_t accumulation_buffer_idx, dfx_plane* out);
 DFX_API dfx_status dfx_taa_get_jitter_offset(const dfx_taa* fx, uint32_t accumulation_buffer_idx, float out_jitter[2]);
+
+/* ============================================================================================================ */
+/* Ingest / egress in the reference's render-target formats (Hydrogent/src/Tasks/HnBeginFrameTask.cpp:63-69: scene colour
+ * and normal RGBA16_FLOAT, motion RG16_FLOAT, material RG8_UNORM; the final target is an 8-bit sRGB swap chain). The
+ * passes keep fp32 planes in HBM; these two entries convert at the PCIe boundary so that the narrow formats are what
+ * travels (30 B/px in, 4 B/px out instead of 64 / 16). Widening is exact.
+ *   unpack: RGBA16F -> RGBA32F, RG16F -> RG32F, RG8U -> RGBA32F (x, y = c/255; z = w = 0)
+ *   pack  : RGBA32F -> RGBA8U, D3D UNORM rule: saturate, * 255, + 0.5, truncate (NaN -> 0)                        */
+DFX_API dfx_status dfx_pass_unpack_plane(void* stream, const dfx_plane* src, const dfx_plane* dst, dfx_rows rows);
+DFX_API dfx_status dfx_pass_pack_ldr8(void* stream, const dfx_plane* src_rgba32f, const dfx_plane* dst_rgba8u, dfx_rows rows);
 
 /* ============================================================================================================ */
 /* plane helpers (device memory owned by the library; used by the C++ shim and the tests)                       */

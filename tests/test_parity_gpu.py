@@ -341,6 +341,60 @@ def test_streaming_pipeline_equals_frame_by_frame(ctx):
     a.close(), b.close()
 
 
+def test_transfer_formats_unpack_pack(ctx):
+    """dfx_pass_unpack_plane widens RGBA16F / RG16F / RG8U exactly; dfx_pass_pack_ldr8 follows the D3D UNORM rule bit for bit
+    (edge values: negatives, > 1, NaN, exact .5 ties)."""
+    import ctypes as C
+
+    import torch
+    from diligentfx_b200 import capi
+    from diligentfx_b200.chain import pack_ldr8
+    L, h, w = capi.load(), 37, 53  # odd sizes: ragged last CTA
+    rng = np.random.default_rng(5)
+    full = capi.Rows(0, h)
+    for dt, ch, out_ch in ((torch.float16, 4, 4), (torch.float16, 2, 2), (torch.uint8, 2, 4)):
+        if dt == torch.uint8:
+            src = torch.from_numpy(rng.integers(0, 256, (h, w, ch), dtype=np.uint8))
+            want = np.zeros((h, w, 4), np.float32)
+            want[..., :2] = src.numpy().astype(np.float32) / np.float32(255.0)
+        else:
+            a = rng.standard_normal((h, w, ch)).astype(np.float32) * 100.0
+            a.flat[:6] = [0.0, -0.0, 65504.0, -65504.0, 6e-8, np.inf]  # zero signs, half max, a half denormal, inf
+            src = torch.from_numpy(a.astype(np.float16))
+            want = src.numpy().astype(np.float32)
+        d_src, d_dst = src.cuda(), torch.full((h, w, out_ch), -7.0, dtype=torch.float32, device="cuda")
+        capi.check(L.dfx_pass_unpack_plane(None, C.byref(capi.plane_of(d_src)), C.byref(capi.plane_of(d_dst)), full), "unpack")
+        torch.cuda.synchronize()
+        assert np.array_equal(d_dst.cpu().numpy(), want, equal_nan=True), (dt, ch)
+    ldr = rng.random((h, w, 4), dtype=np.float32) * 1.2 - 0.1
+    ldr.flat[:8] = [np.nan, -1.0, 2.0, 0.5 / 255.0, 1.5 / 255.0, 254.5 / 255.0, 1.0, 0.0]
+    d_src, d_dst = torch.from_numpy(ldr).cuda(), torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    capi.check(L.dfx_pass_pack_ldr8(None, C.byref(capi.plane_of(d_src)), C.byref(capi.plane_of(d_dst)), full), "pack")
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dst.cpu().numpy(), pack_ldr8(ldr))
+    # wrong pairing of formats is refused, not reinterpreted
+    bad = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    assert L.dfx_pass_unpack_plane(None, C.byref(capi.plane_of(d_src)), C.byref(capi.plane_of(bad)), full) == capi.DFX_ERR_INVALID_ARG
+
+
+def test_packed_streaming_equals_widened_frames(ctx):
+    """The G-buffer travels in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8 material) and
+    the result comes back as RGBA8: the chain must compute exactly what it computes on the widened fp32 planes, and the
+    8-bit frame must be the UNORM pack of that fp32 frame."""
+    import torch
+    from diligentfx_b200.chain import PostProcessChain, pack_frame, pack_ldr8, widen_frame
+    seq, h, w = ctx["seq"], ctx["h"], ctx["w"]
+    packed = [pack_frame(fr, pin=True) for fr in seq]
+    a, b = PostProcessChain(w, h), PostProcessChain(w, h)
+    want = [pack_ldr8(a.run_frame(widen_frame(p)).cpu().numpy()) for p in packed]
+    hosts = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in seq]
+    assert b.stream_frames(iter(packed), hosts, packed=True) == len(seq)
+    torch.cuda.synchronize()
+    for k, wnt in enumerate(want):
+        assert np.array_equal(hosts[k].numpy(), wnt), f"frame {k}: {np.count_nonzero(hosts[k].numpy() != wnt)} bytes differ"
+    a.close(), b.close()
+
+
 # =====================================================================================================================
 # whole chain through the effect-level objects
 # =====================================================================================================================
