@@ -194,6 +194,8 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one (JSON) line
         dist.init_process_group("nccl", device_id=dev)
 
     W, H, K, Wm = args.width, args.height, args.steps, args.warmup
@@ -209,7 +211,9 @@ def main() -> None:
     host = [{n: torch.from_numpy(np.ascontiguousarray(fr[n])).pin_memory() for n in INPUT_SPECS} for fr in seq]
     resident = [{n: t.to(dev) for n, t in hf.items()} for hf in host]
     cams = [(fr["curr_camera"], fr["prev_camera"]) for fr in seq]
-    packed_keys = [s[0] for s in PACKED_SPECS.values()] + ["depth", "prev_depth"]
+    # consecutive frames: the previous depth is the depth of the frame before and stays on the device (stream_frames docstring)
+    packed = [{k: v for k, v in p.items() if k != "prev_depth"} for p in packed]
+    packed_keys = [s[0] for s in PACKED_SPECS.values()] + ["depth"]
     h2d_bytes = sum(packed[0][k].numel() * packed[0][k].element_size() for k in packed_keys)
     h2d_bytes_fp32 = sum(t.numel() * 4 for t in host[0].values())
     chain = PostProcessChain(W, H, ChainConfig(overlap=not args.no_overlap), device=dev)
@@ -338,8 +342,8 @@ def main() -> None:
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes),
-                    "formats": "host G-buffer in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8 material, fp32 depth + "
-                               "previous depth = 30 B/px), widened on the device; result read back as RGBA8 (4 B/px); PostProcessChain.stream_frames("
+                    "formats": "host G-buffer in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8 material, fp32 depth = "
+                               "26 B/px; the previous depth is the depth of the frame before and stays on the device), widened on the device; result read back as RGBA8 (4 B/px); PostProcessChain.stream_frames("
                                "packed=True): copy-in / compute / copy-out pipelined on 3 streams",
                     "fp32_transfers": {"value": round(e2e32_value, 2), "ms_per_step": round(e2e32_ms, 4), "h2d_bytes_per_step": int(h2d_bytes_fp32),
                                        "d2h_bytes_per_step": int(d2h_bytes_fp32)}},

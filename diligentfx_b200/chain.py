@@ -262,7 +262,7 @@ class PostProcessChain:
         self.upload(frame)
         return self.execute(frame["frame"], frame["curr_camera"], frame["prev_camera"])
 
-    def stream_frames(self, frames, ldr_host: list | None = None, packed: bool = False) -> int:
+    def stream_frames(self, frames, ldr_host: list | None = None, packed: bool = False, new_sequence: bool = False) -> int:
         """Offline throughput path (BASELINE.json config 5: batches of frames): a double-buffered pipeline over three CUDA
         streams. While frame k runs on the compute stream, frame k+1's G-buffer is copied from (pinned) host memory on a
         copy stream and frame k-1's LDR result is copied back on a read-back stream; PCIe is full duplex, so the two copy
@@ -275,6 +275,11 @@ class PostProcessChain:
         normal RGBA16F, motion RG16F, material RG8; depths stay fp32) and `ldr_host` holds (H, W, 4) uint8 tensors: 30 B/px
         cross PCIe instead of 64, 4 B/px come back instead of 16. The device widens them (dfx_pass_unpack_plane) into the
         same fp32 planes, so the chain computes exactly what it computes on `widen_frame(packed_frame)`.
+
+        A frame without a "prev_depth" entry takes the depth of the frame streamed before it (its own depth if it is the
+        first one), which stays on the device: in the reference the previous depth is last frame's depth target, not
+        something the application uploads (HnPostProcessTask.cpp:788-832). Consecutive frames of one sequence then move 4 B/px less.
+        The "frame streamed before" carries over from one call to the next unless `new_sequence=True`.
         """
         dev = self.device
         if not hasattr(self, "_pipe"):
@@ -282,7 +287,8 @@ class PostProcessChain:
             self._pipe = dict(inputs=[mk(), mk()], ldr=[torch.empty_like(self.ldr), torch.empty_like(self.ldr)], h2d=torch.cuda.Stream(dev),
                               d2h=torch.cuda.Stream(dev), h2d_done=[torch.cuda.Event(), torch.cuda.Event()],
                               compute_done=[torch.cuda.Event(), torch.cuda.Event()], d2h_done=[torch.cuda.Event(), torch.cuda.Event()])
-            for e in self._pipe["compute_done"] + self._pipe["d2h_done"]:
+            self._pipe["depth_taken"] = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._pipe["compute_done"] + self._pipe["d2h_done"] + self._pipe["depth_taken"]:
                 e.record(torch.cuda.current_stream(dev))
         P = self._pipe
         if packed and "staging" not in P:
@@ -291,12 +297,19 @@ class PostProcessChain:
             P["ldr8"] = [torch.empty((self.h, self.w, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
         main = torch.cuda.current_stream(dev)
         L, full = self.lib, Rows(0, self.h)
+        if new_sequence:
+            P["last_slot"] = None
         n = 0
+        base = P.get("count", 0)                                     # slots keep alternating from one call to the next
         for k, fr in enumerate(frames):
-            s = k & 1
+            s = (base + k) & 1
+            keep_prev = "prev_depth" not in fr                       # the previous depth stays on the device (see docstring)
             with torch.cuda.stream(P["h2d"]):
                 P["h2d"].wait_event(P["compute_done"][s])          # frame k-2 no longer reads this input set
+                P["h2d"].wait_event(P["depth_taken"][s])           # ... and frame k-1 has taken its previous depth from it
                 for name in INPUT_SPECS:
+                    if keep_prev and name == "prev_depth":
+                        continue
                     if packed and name in PACKED_SPECS:
                         P["staging"][s][name].copy_(fr[PACKED_SPECS[name][0]], non_blocking=True)
                         continue
@@ -306,6 +319,12 @@ class PostProcessChain:
                 P["h2d_done"][s].record(P["h2d"])
             main.wait_event(P["h2d_done"][s])
             main.wait_event(P["d2h_done"][s])                        # frame k-2's result has left this LDR buffer
+            if keep_prev:
+                last = P.get("last_slot")
+                P["inputs"][s]["prev_depth"].copy_(P["inputs"][s if last is None else last]["depth"])
+                if last is not None:
+                    P["depth_taken"][last].record(main)
+            P["last_slot"] = s
             if packed:                                               # widen the transfer formats into the fp32 planes the passes read
                 stream = C.c_void_p(main.cuda_stream)
                 for name in PACKED_SPECS:
@@ -328,6 +347,7 @@ class PostProcessChain:
                     ldr_host[k % len(ldr_host)].copy_(result, non_blocking=True)
                     P["d2h_done"][s].record(P["d2h"])
             n += 1
+        P["count"] = base + n
         self.join()
         main.wait_event(P["d2h_done"][0])
         main.wait_event(P["d2h_done"][1])

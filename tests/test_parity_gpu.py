@@ -392,7 +392,17 @@ def test_packed_streaming_equals_widened_frames(ctx):
     torch.cuda.synchronize()
     for k, wnt in enumerate(want):
         assert np.array_equal(hosts[k].numpy(), wnt), f"frame {k}: {np.count_nonzero(hosts[k].numpy() != wnt)} bytes differ"
-    a.close(), b.close()
+    # the previous depth of a consecutive sequence need not travel: the device keeps the depth of the frame before
+    # (frame 0 of the synthetic sequence has prev_depth == depth). Two calls: the carry-over between calls is exercised too.
+    c = PostProcessChain(w, h)
+    lean = [{k: v for k, v in p.items() if k != "prev_depth"} for p in packed]
+    hosts2 = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in seq]
+    assert c.stream_frames(iter(lean[:1]), hosts2[:1], packed=True, new_sequence=True) == 1
+    assert c.stream_frames(iter(lean[1:]), hosts2[1:], packed=True) == len(seq) - 1
+    torch.cuda.synchronize()
+    for k, wnt in enumerate(want):
+        assert np.array_equal(hosts2[k].numpy(), wnt), f"device-kept previous depth, frame {k}"
+    a.close(), b.close(), c.close()
 
 
 # =====================================================================================================================
