@@ -11,10 +11,15 @@ scaling is weak and `value` = pixels all ranks processed / max-over-ranks device
 Lines of the JSON record (one line on stdout, rank 0):
   value         device-resident throughput: the G-buffers of the timed steps are already in HBM (4 distinct frames, 0.5 GB
                 each, cycled -> every step's inputs are cold in the 126 MB L2); timed with CUDA events, max over ranks.
-  e2e           the same K steps through the public API with HOST buffers: per step the frame's G-buffer is copied from
-                pinned host memory, the chain runs, and the LDR result is read back into pinned host memory.
-  roofline      dominant pass of the chain (largest share of the step): algorithmic bytes / CUDA-event time inside this run,
-                against MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s, B200_PROFILING.md). `passes` lists every pass.
+                Async compute on three streams (ChainConfig.overlap; --no-overlap runs everything on one stream).
+  e2e           the same K steps through the public streaming API (PostProcessChain.stream_frames) with HOST buffers: per
+                step the frame's G-buffer is copied from pinned host memory in the reference's render-target formats
+                (RGBA16F / RG16F / RG8 / D32F, widened on the device), the chain runs, and the frame is read back as RGBA8
+                into pinned host memory; copy-in, compute and copy-out of neighbouring frames overlap on three streams.
+                `e2e.fp32_transfers` is the same with every plane crossing PCIe as fp32.
+  roofline      dominant pass of the chain (largest share of the step): algorithmic bytes / CUDA-event time inside this run
+                (each pass alone on one stream), against MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s,
+                B200_PROFILING.md); `traffic` = DRAM bytes per launch from the committed ncu capture. `passes` lists every pass.
   cpu_baseline  the oracle (scalar C++ port of the Shaders/PostProcess math) on this box's host cores, bounded sample.
   --impl reference: the same metric from the oracle alone (the reference has no CPU implementation and cannot be built
                 here: DiligentCore + HLSL compiler + graphics device are required — DESIGN.md).
