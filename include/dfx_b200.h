@@ -368,7 +368,9 @@ DFX_API dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attribs
                                           const dfx_plane* radiance, const dfx_plane* variance,
                                           const dfx_plane* out, dfx_rows rows);
 
-/* B1 ComputePrefilteredTexture (Bloom.cpp:288-311; Bloom_ComputePrefilteredTexture.fx:37-83). */
+/* Bloom passes: `rows` is a row range of the OUTPUT plane of the call (the pyramid level being written), not of the
+ * full-resolution frame — the levels have their own heights.
+ * B1 ComputePrefilteredTexture (Bloom.cpp:288-311; Bloom_ComputePrefilteredTexture.fx:37-83). */
 DFX_API dfx_status dfx_pass_bloom_prefilter(void* stream, const dfx_bloom_attribs* attribs,
                                             const dfx_plane* color, const dfx_plane* out_level0, dfx_rows rows);
 /* B2 ComputeDownsampledTexture (Bloom.cpp:313-337; Bloom_ComputeDownsampledTexture.fx:11-41). */
