@@ -22,6 +22,7 @@ MAX_MIPS = 8
 
 TAA_FLAG_GAUSSIAN, TAA_FLAG_BICUBIC, TAA_FLAG_YCOCG = 1, 2, 4
 SSR_FLAG_PREVIOUS_FRAME = 1
+POSTFX_FLAG_REVERSED_DEPTH = 1
 
 
 class Float4x4(C.Structure):
@@ -101,7 +102,7 @@ class FrameDesc(C.Structure):
 
 class Plane(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("pitch_bytes", C.c_size_t), ("width", C.c_int32), ("height", C.c_int32),
-                ("format", C.c_int32), ("reserved", C.c_int32)]
+                ("format", C.c_int32), ("flags", C.c_int32)]
 
 
 class Pyramid(C.Structure):
@@ -193,7 +194,10 @@ def check(status: int, what: str = "") -> None:
 _FMT_OF = {(1,): FORMAT_R32F, (2,): FORMAT_RG32F, (4,): FORMAT_RGBA32F}
 
 
-def plane_of(t, fmt: int | None = None) -> Plane:
+PLANE_FLAG_REVERSED_DEPTH = 1
+
+
+def plane_of(t, fmt: int | None = None, flags: int = 0) -> Plane:
     """Describe a contiguous torch CUDA tensor (H,W), (H,W,2) or (H,W,4) float32 / (H,W) uint8 as a dfx_plane; transfer
     formats: (H,W,4) / (H,W,2) float16 and (H,W,2) / (H,W,4) uint8."""
     import torch
@@ -209,14 +213,15 @@ def plane_of(t, fmt: int | None = None) -> Plane:
         f, bpp = _FMT_OF[(ch,)], 4 * ch
     if fmt is not None:
         assert fmt == f
-    return Plane(t.data_ptr(), w * bpp, w, h, f, 0)
+    return Plane(t.data_ptr(), w * bpp, w, h, f, flags)
 
 
-def pyramid_of(tensors) -> Pyramid:
+def pyramid_of(tensors, flags: int = 0) -> Pyramid:
+    """`flags` go on level 0 (the depth buffer a depth pyramid is built from)."""
     p = Pyramid()
     p.levels = len(tensors)
     for i, t in enumerate(tensors):
-        p.level[i] = plane_of(t)
+        p.level[i] = plane_of(t, flags=flags if i == 0 else 0)
     return p
 
 

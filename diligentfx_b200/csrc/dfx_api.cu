@@ -168,7 +168,7 @@ dfx_status dfx_plane_alloc(int32_t width, int32_t height, int32_t format, dfx_pl
     size_t pitch = ((size_t)width * bpt + 127) / 128 * 128;
     void*  p     = nullptr;
     DFX_CUDA(cudaMalloc(&p, pitch * (size_t)height));
-    out->ptr = p, out->pitch_bytes = pitch, out->width = width, out->height = height, out->format = format, out->reserved = 0;
+    out->ptr = p, out->pitch_bytes = pitch, out->width = width, out->height = height, out->format = format, out->flags = 0;
     return DFX_OK;
 }
 void dfx_plane_free(dfx_plane* p)

@@ -367,6 +367,9 @@ constexpr float kHalfPi = 1.57079632679490f;
 constexpr float kFltEps = 5.960464478e-8f;
 constexpr float kFltMax = 3.402823466e+38f;
 
-DFX_HD bool is_background(float d) { return d >= (1.0f - 1e-6f); }
+// SSAO_Common.fxh:16-23 / SSR_Common.fxh:48-55. `rev` = the depth plane carries DFX_PLANE_FLAG_REVERSED_DEPTH (the reference
+// compiles *_OPTION_INVERTED_DEPTH shader variants; here it is a uniform kernel argument: one predicated compare).
+DFX_HD bool is_background(float d, int rev) { return rev ? d < 1e-6f : d >= (1.0f - 1e-6f); }
+inline int  reversed_depth(const dfx_plane* depth) { return depth && (depth->flags & DFX_PLANE_FLAG_REVERSED_DEPTH) ? 1 : 0; }
 
 } // namespace dfx

@@ -96,7 +96,8 @@ extern "C" void dfx_postfx_destroy(dfx_postfx* c) { delete c; }
 extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* desc, uint32_t flags)
 {
     DFX_REQUIRE(c && desc, "null argument");
-    if (flags != DFX_POSTFX_FEATURE_FLAG_NONE) return set_error(DFX_ERR_UNSUPPORTED, "PostFX feature flags 0x%x are not implemented (fp32, non-reversed depth only)", flags);
+    if (flags & ~DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH)
+        return set_error(DFX_ERR_UNSUPPORTED, "PostFX feature flags 0x%x are not implemented (fp32 depth, no temporal upscaling)", flags);
     DFX_REQUIRE(desc->Width > 0 && desc->Height > 0, "empty frame");
     c->desc  = *desc;
     c->flags = flags;
@@ -108,6 +109,8 @@ extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* de
         if ((st = c->prev_depth.alloc(c->w, c->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
         if ((st = c->closest.alloc(c->w, c->h, DFX_FORMAT_RG32F)) != DFX_OK) return st;
     }
+    // the context's own depth planes carry the encoding of the depth buffer they are derived from (PostFXContext.cpp:515)
+    c->reproj.p.flags = c->prev_depth.p.flags = (flags & DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH) ? DFX_PLANE_FLAG_REVERSED_DEPTH : 0;
     c->prepared = true;
     return DFX_OK;
 }
@@ -125,7 +128,9 @@ extern "C" dfx_status dfx_postfx_execute(dfx_postfx* c, const dfx_postfx_render_
     dfx_status st;
     if ((st = dfx_pass_blue_noise(s, c->tables_dev, c->desc.Index, &c->bn_xy.p, &c->bn_zw.p)) != DFX_OK) return st;
     dfx_rows all{0, c->h};
-    if ((st = dfx_pass_postfx_prepare(s, c->cams_dev, a->curr_depth, a->prev_depth, a->motion_vectors, &c->reproj.p, &c->closest.p, &c->prev_depth.p, all)) != DFX_OK)
+    dfx_plane depth = *a->curr_depth;
+    depth.flags |= c->reproj.p.flags;
+    if ((st = dfx_pass_postfx_prepare(s, c->cams_dev, &depth, a->prev_depth, a->motion_vectors, &c->reproj.p, &c->closest.p, &c->prev_depth.p, all)) != DFX_OK)
         return st;
     c->executed = true;
     return DFX_OK;
@@ -247,11 +252,13 @@ extern "C" dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attri
 
     const uint32_t cur = fx->curr_frame & 1u, prv = (fx->curr_frame + 1u) & 1u;
     const dfx_rows all{0, fx->h};
-    fx->last_depth = *a->depth;
+    dfx_plane depth = *a->depth; // SSAO_OPTION_INVERTED_DEPTH follows the PostFX feature flag (ScreenSpaceAmbientOcclusion.cpp:72, :471)
+    depth.flags |= pfx->reproj.p.flags;
+    fx->last_depth = depth;
 
     dfx_pyramid pre{}, cocc{}, cdep{};
     pre.levels = cocc.levels = cdep.levels = fx->levels;
-    pre.level[0] = *a->depth, cocc.level[0] = fx->conv_occ[0].p, cdep.level[0] = *a->depth;
+    pre.level[0] = depth, cocc.level[0] = fx->conv_occ[0].p, cdep.level[0] = depth;
     for (int i = 1; i < fx->levels; ++i) pre.level[i] = fx->pre[i].p, cocc.level[i] = fx->conv_occ[i].p, cdep.level[i] = fx->conv_depth[i].p;
 
     dfx_status st;
@@ -262,7 +269,7 @@ extern "C" dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attri
         return st;
     if ((st = dfx_pass_ssao_convolute(s, &cocc, &cdep, all)) != DFX_OK) return st;
     if ((st = dfx_pass_ssao_resample(s, pfx->cams_dev, &cocc, &cdep, &fx->histlen[cur].p, a->normal, &fx->resampled.p, all)) != DFX_OK) return st;
-    if ((st = dfx_pass_ssao_spatial(s, pfx->cams_dev, &A, &fx->resampled.p, &fx->histlen[cur].p, a->depth, a->normal, &fx->hist[cur].p, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_spatial(s, pfx->cams_dev, &A, &fx->resampled.p, &fx->histlen[cur].p, &depth, a->normal, &fx->hist[cur].p, all)) != DFX_OK) return st;
     return DFX_OK;
 }
 
@@ -360,26 +367,28 @@ extern "C" dfx_status dfx_ssr_execute(dfx_ssr* fx, const dfx_ssr_render_attribs*
     A.AlphaInterpolation = fx->alpha.value();
     const uint32_t cur = fx->curr_frame & 1u, prv = (fx->curr_frame + 1u) & 1u;
     const dfx_rows all{0, fx->h};
-    fx->last_depth = *a->depth;
+    dfx_plane depth = *a->depth; // SSR_OPTION_INVERTED_DEPTH follows the PostFX feature flag (ScreenSpaceReflection.cpp:73, :473)
+    depth.flags |= pfx->reproj.p.flags;
+    fx->last_depth = depth;
 
     dfx_pyramid hz{};
     hz.levels   = fx->levels;
-    hz.level[0] = *a->depth;
+    hz.level[0] = depth;
     for (int i = 1; i < fx->levels; ++i) hz.level[i] = fx->hiz[i].p;
 
     dfx_status st;
     if ((st = dfx_pass_ssr_hiz(s, &hz, all)) != DFX_OK) return st;
-    if ((st = dfx_pass_ssr_mask_roughness(s, &A, a->material, a->depth, &fx->roughness.p, &fx->mask.p, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssr_mask_roughness(s, &A, a->material, &depth, &fx->roughness.p, &fx->mask.p, all)) != DFX_OK) return st;
     if ((st = dfx_pass_ssr_intersect(s, pfx->cams_dev, &A, fx->flags, a->color, a->normal, &fx->roughness.p, &fx->mask.p, &pfx->bn_xy.p, &hz, a->motion,
                                      &fx->radiance.p, &fx->raydir.p, all)) != DFX_OK)
         return st;
-    if ((st = dfx_pass_ssr_spatial(s, pfx->cams_dev, &A, &fx->roughness.p, &fx->mask.p, a->normal, a->depth, &fx->raydir.p, &fx->radiance.p, &fx->res_rad.p,
+    if ((st = dfx_pass_ssr_spatial(s, pfx->cams_dev, &A, &fx->roughness.p, &fx->mask.p, a->normal, &depth, &fx->raydir.p, &fx->radiance.p, &fx->res_rad.p,
                                    &fx->res_var.p, &fx->res_depth.p, all)) != DFX_OK)
         return st;
     if ((st = dfx_pass_ssr_temporal(s, pfx->cams_dev, &A, &fx->mask.p, a->motion, &fx->res_depth.p, &pfx->reproj.p, &fx->res_rad.p, &fx->res_var.p,
                                     &pfx->prev_depth.p, &fx->radhist[prv].p, &fx->varhist[prv].p, &fx->radhist[cur].p, &fx->varhist[cur].p, all)) != DFX_OK)
         return st;
-    if ((st = dfx_pass_ssr_bilateral(s, pfx->cams_dev, &A, &fx->mask.p, a->depth, a->normal, &fx->roughness.p, &fx->radhist[cur].p, &fx->varhist[cur].p,
+    if ((st = dfx_pass_ssr_bilateral(s, pfx->cams_dev, &A, &fx->mask.p, &depth, a->normal, &fx->roughness.p, &fx->radhist[cur].p, &fx->varhist[cur].p,
                                      &fx->out.p, all)) != DFX_OK)
         return st;
     return DFX_OK;

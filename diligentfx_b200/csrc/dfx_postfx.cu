@@ -64,7 +64,7 @@ struct PrepCam
 
 __global__ void __launch_bounds__(256) postfx_prepare_kernel(const dfx_camera_attribs* __restrict__ cams, View<const float> depth,
                                                              View<const float> prev_in, View<const float2> motion, View<float> reproj,
-                                                             View<float2> closest, View<float> prev_out, int y0, int y1)
+                                                             View<float2> closest, View<float> prev_out, int y0, int y1, int rev)
 {
     __shared__ PrepCam cam;
     if (threadIdx.x == 0 && threadIdx.y == 0)
@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(256) postfx_prepare_kernel(const dfx_camera_at
     const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= depth.w || y >= y1) return;
 
-    // 3x3 closest depth; iteration order x outer, y inner, strict '<' (first minimum wins) as in the shader
-    float d_c = 0.0f, closest_d = 1.0f;
+    // 3x3 closest depth; iteration order x outer, y inner, strict '<' (first minimum wins) as in the shader; reversed depth:
+    // far plane 0 and strict '>' (ComputeClosestMotion.fx:5-9, 36-40)
+    float d_c = 0.0f, closest_d = rev ? 0.0f : 1.0f;
     int   ox = 0, oy = 0;
 #pragma unroll
     for (int dx = -1; dx <= 1; ++dx)
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) postfx_prepare_kernel(const dfx_camera_at
         {
             float nd = load0(depth, x + dx, y + dy);
             if (dx == 0 && dy == 0) d_c = nd;
-            if (nd < closest_d) closest_d = nd, ox = dx, oy = dy;
+            if (rev ? nd > closest_d : nd < closest_d) closest_d = nd, ox = dx, oy = dy;
         }
     st_cs(&closest.at(x, y), load0(motion, x + ox, y + oy));
 
@@ -138,7 +139,7 @@ extern "C" dfx_status dfx_pass_postfx_prepare(void* stream, const dfx_camera_att
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(d.w, 32), div_up(rows.y1 - rows.y0, 8));
-    postfx_prepare_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, d, pin, m, rp, cm, pout, rows.y0, rows.y1);
+    postfx_prepare_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, d, pin, m, rp, cm, pout, rows.y0, rows.y1, reversed_depth(curr_depth));
     DFX_LAUNCHED("postfx_prepare_kernel");
     return DFX_OK;
 }

@@ -109,7 +109,7 @@ struct __align__(16) AoLevel
 
 template <int ALGO>
 __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
-                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1)
+                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     __shared__ AoLevel lvl[DFX_MAX_MIPS];
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
     // k in 1..4 with l >= 2^(o + k - 0.5)).
     const float u = (float(x) + 0.5f) * cam.ivw, v = (float(y) + 0.5f) * cam.ivh;
     const float depth = __ldg(&pyr.lv[0].at(x, y)); // point sample at the pixel centre == Load(x, y)
-    if (is_background(depth))
+    if (is_background(depth, rev))
     {
         st_cs(&out.at(x, y), 1.0f);
         return;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) ssao_temporal_kernel(const dfx_camera_att
                                                             View<const float> curr_occ, View<const float> prev_occ,
                                                             View<const float> prev_hist, View<const float> curr_depth,
                                                             View<const float> prev_depth, View<const float2> motion, View<float> out_occ,
-                                                            View<float> out_hist, int y0, int y1)
+                                                            View<float> out_hist, int y0, int y1, int rev)
 {
     __shared__ TemporalCam S;
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_cam(S.p, &cams[1]);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) ssao_temporal_kernel(const dfx_camera_att
     if (x >= out_occ.w || y >= y1) return;
 
     const float depth = __ldg(&curr_depth.at(x, y));
-    if (is_background(depth))
+    if (is_background(depth, rev))
     {
         st_cs(&out_occ.at(x, y), 1.0f);
         st_cs(&out_hist.at(x, y), 1.0f);
@@ -375,7 +375,7 @@ DFX_HD float geometry_weight(float3 center, float3 tap, float3 n, float planeNor
 }
 
 __global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_attribs* __restrict__ cams, PyrView occ, PyrView dep,
-                                                            View<const float> history, View<const float4> normal, View<float> out, int y0, int y1)
+                                                            View<const float> history, View<const float4> normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     stage_cam(S, cams);
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_att
     const float depth = __ldg(&dep.lv[0].at(x, y));
     const float hist  = __ldg(&history.at(x, y));
     const float acc   = (hist - 1.0f) / 4.0f;
-    if (is_background(depth) || acc >= 1.0f)
+    if (is_background(depth, rev) || acc >= 1.0f)
     {
         st_cs(&out.at(x, y), __ldg(&occ.lv[0].at(x, y)));
         return;
@@ -439,7 +439,7 @@ __constant__ float kPoisson8Weight[8] = {0.77283178f, 0.570022457f, 0.838854363f
 
 __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
                                                            View<const float> occlusion, View<const float> history, View<const float> depth,
-                                                           View<const float4> normal, View<float> out, int y0, int y1)
+                                                           View<const float4> normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     stage_cam(S, cams);
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attr
     const float occC = __ldg(&occlusion.at(x, y));
     // acc = |(hist-1)/8|^0.2 >= 1  <=>  |hist-1| >= 8: decide the early-out without the pow
     const float hq = fabsf((hist - 1.0f) / 8.0f);
-    if (is_background(d) || hq >= 1.0f)
+    if (is_background(d, rev) || hq >= 1.0f)
     {
         st_cs(&out.at(x, y), lerpf(1.0f, occC, A.AlphaInterpolation));
         return;
@@ -550,6 +550,7 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     PyrView P;
     DFX_REQUIRE(make_pyr(prefiltered_depth, P, 1), "bad prefiltered-depth pyramid");
+    const int rev = reversed_depth(&prefiltered_depth->level[0]); // level 0 is the depth buffer
     DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float2, bn, blue_noise_zw, DFX_FORMAT_RG32F);
     DFX_VIEW(float, out, occlusion, DFX_FORMAT_R32F);
@@ -561,9 +562,9 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
     switch (attribs->Algorithm)
     {
-        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1); break;
-        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1); break;
-        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1); break;
+        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev); break;
+        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev); break;
+        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev); break;
         default: return set_error(DFX_ERR_INVALID_ARG, "unknown SSAO algorithm %u", attribs->Algorithm);
     }
     DFX_LAUNCHED("ssao_ao_kernel");
@@ -582,6 +583,7 @@ extern "C" dfx_status dfx_pass_ssao_temporal(void* stream, const dfx_camera_attr
     DFX_VIEW(const float, po, prev_occlusion, DFX_FORMAT_R32F);
     DFX_VIEW(const float, ph, prev_history_length, DFX_FORMAT_R32F);
     DFX_VIEW(const float, cd, reprojected_depth, DFX_FORMAT_R32F);
+    const int rev = reversed_depth(reprojected_depth);
     DFX_VIEW(const float, pd, previous_depth, DFX_FORMAT_R32F);
     DFX_VIEW(const float2, mv, closest_motion, DFX_FORMAT_RG32F);
     DFX_VIEW(float, oo, out_occlusion, DFX_FORMAT_R32F);
@@ -596,7 +598,7 @@ extern "C" dfx_status dfx_pass_ssao_temporal(void* stream, const dfx_camera_attr
     DFX_REQUIRE(rows_ok(rows, co.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(co.w, 32), div_up(rows.y1 - rows.y0, 8));
-    ssao_temporal_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, co, po, ph, cd, pd, mv, oo, oh, rows.y0, rows.y1);
+    ssao_temporal_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, co, po, ph, cd, pd, mv, oo, oh, rows.y0, rows.y1, rev);
     DFX_LAUNCHED("ssao_temporal_kernel");
     return DFX_OK;
 }
@@ -629,6 +631,7 @@ extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attr
     DFX_REQUIRE(cameras_dev, "null argument");
     PyrView O, D;
     DFX_REQUIRE(make_pyr(occlusion_pyr, O, 1) && make_pyr(depth_pyr, D, 1), "bad pyramid");
+    const int rev = reversed_depth(&depth_pyr->level[0]); // level 0 is the depth buffer
     DFX_REQUIRE(O.levels == D.levels, "pyramid level mismatch");
     DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);
     DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
@@ -640,7 +643,7 @@ extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attr
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
-    ssao_resample_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, O, D, h, n, out, rows.y0, rows.y1);
+    ssao_resample_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, O, D, h, n, out, rows.y0, rows.y1, rev);
     DFX_LAUNCHED("ssao_resample_kernel");
     return DFX_OK;
 }
@@ -654,6 +657,7 @@ extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attri
     DFX_VIEW(const float, o, occlusion, DFX_FORMAT_R32F);
     DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    const int rev = reversed_depth(depth);
     DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
     DFX_VIEW(float, out, out_occlusion, DFX_FORMAT_R32F);
     DFX_SAME_SIZE(o, h);
@@ -663,7 +667,7 @@ extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attri
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
-    ssao_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1);
+    ssao_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1, rev);
     DFX_LAUNCHED("ssao_spatial_kernel");
     return DFX_OK;
 }

@@ -8,26 +8,30 @@
 namespace dfx
 {
 
-DFX_HD bool is_reflection_sample(float rough, float depth, float thr) { return rough <= thr && !is_background(depth); } // SSR_Common.fxh:57-60
+DFX_HD bool is_reflection_sample(float rough, float depth, float thr, int rev) { return rough <= thr && !is_background(depth, rev); } // SSR_Common.fxh:57-60
 
 __host__ __device__ inline int ssr_mip_row(int y, int m, int full_h, int mip_h) { return y >= full_h ? mip_h : (y >> m); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // S1: Hi-Z level m from m-1: closest (min) depth of the 2x2 footprint (+ odd row/column) — SSR_ComputeHierarchicalDepthBuffer.fx:30-73
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ssr_hiz_level_kernel(View<const float> src, View<float> dst, int r0, int r1)
+__global__ void __launch_bounds__(256) ssr_hiz_level_kernel(View<const float> src, View<float> dst, int r0, int r1, int rev)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dst.w || y >= r1) return;
     const bool wodd = src.w & 1, hodd = src.h & 1;
     const int  rx = 2 * x, ry = 2 * y;
-    float      m = 1.0f;
-    m = fminf(m, loadc(src, rx, ry)), m = fminf(m, loadc(src, rx, ry + 1));
-    m = fminf(m, loadc(src, rx + 1, ry)), m = fminf(m, loadc(src, rx + 1, ry + 1));
-    if (wodd) m = fminf(m, loadc(src, rx + 2, ry)), m = fminf(m, loadc(src, rx + 2, ry + 1));
-    if (hodd) m = fminf(m, loadc(src, rx, ry + 2)), m = fminf(m, loadc(src, rx + 1, ry + 2));
-    if (wodd && hodd) m = fminf(m, loadc(src, rx + 2, ry + 2));
+    // ClosestDepth = min, DepthFarPlane = 1; reversed depth: max and 0 (SSR_Common.fxh:6-12)
+    float      m   = rev ? 0.0f : 1.0f;
+    const auto upd = [&](int ox, int oy) {
+        const float d = loadc(src, rx + ox, ry + oy);
+        m             = rev ? fmaxf(m, d) : fminf(m, d);
+    };
+    upd(0, 0), upd(0, 1), upd(1, 0), upd(1, 1);
+    if (wodd) upd(2, 0), upd(2, 1);
+    if (hodd) upd(0, 2), upd(1, 2);
+    if (wodd && hodd) upd(2, 2);
     dst.at(x, y) = m;
 }
 
@@ -35,7 +39,7 @@ __global__ void __launch_bounds__(256) ssr_hiz_level_kernel(View<const float> sr
 // S2: reflection mask + roughness extraction — SSR_ComputeStencilMaskAndExtractRoughness.fx:13-40
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, View<const float4> material, View<const float> depth,
-                                                       View<float> roughness, View<uint8_t> mask, int y0, int y1)
+                                                       View<float> roughness, View<uint8_t> mask, int y0, int y1, int rev)
 {
     const PixelXY pix = cta_pixel(y0);
     const int     x = pix.x, y = pix.y;
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, View<c
     const float4 m = __ldg(&material.at(x, y));
     float r = A.RoughnessChannel == 0u ? m.x : A.RoughnessChannel == 1u ? m.y : A.RoughnessChannel == 2u ? m.z : A.RoughnessChannel == 3u ? m.w : 0.0f;
     if (!A.IsRoughnessPerceptual) r = sqrtf(r);
-    const bool pass = is_reflection_sample(r, __ldg(&depth.at(x, y)), A.RoughnessThreshold);
+    const bool pass = is_reflection_sample(r, __ldg(&depth.at(x, y)), A.RoughnessThreshold, rev);
     mask.at(x, y) = pass ? 1 : 0;
     if (pass) roughness.at(x, y) = r; // masked-out texels keep their stale value, like the reference's un-cleared target
 }
@@ -159,7 +163,7 @@ template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<co
 }
 template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
 
-template <bool PREV_FRAME, bool PEER>
+template <bool PREV_FRAME, bool PEER, bool REV>
 __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                             View<const float4> color, View<const float4> normal, View<const float> roughness,
                                                             View<const uint8_t> mask, View<const float2> noise, HizView hiz,
@@ -291,9 +295,9 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
             // AdvanceRay :88-136
             const float px = (floorf(mx) + fox) * L.irx + uox, py = (floorf(my) + foy) * L.iry + uoy;
             const float tx = px * invD.x - oxi, ty = py * invD.y - oyi;
-            const float tz = Dr.z > 0.0f ? surf * invD.z - ozi : kFltMax;
+            const float tz = (REV ? Dr.z < 0.0f : Dr.z > 0.0f) ? surf * invD.z - ozi : kFltMax; // :109-113
             const float tmin  = fminf(fminf(tx, ty), tz);
-            const bool  above = surf > pos.z;
+            const bool  above = REV ? surf < pos.z : surf > pos.z;                             // :118-124
             const bool  skipped = (__float_as_uint(tmin) != __float_as_uint(tz)) && above;
             t   = above ? tmin : t;
             pos = O + t * Dr;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         {
             const int   tx = (int)(sw * pos.x), ty = (int)(sh * pos.y);
             const float surfD = hiz_load(lvl[0], PT, tx, ty, 0);
-            if (!is_background(surfD))
+            if (!is_background(surfD, REV))
             {
                 const float3 hitN = xyz(hit_load0<true>(normal, PT, tx, ty));
                 if (!(dot(hitN, dirWS) > 0.0f))
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel
 __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                             View<const uint8_t> mask, View<const float> depth, View<const float4> normal,
                                                             View<const float> roughness, View<const float4> radiance, View<const float> variance,
-                                                            View<float4> out, int y0, int y1)
+                                                            View<float4> out, int y0, int y1, int rev)
 {
     __shared__ CamS cam;
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(cam, &cams[0]);
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
             {
                 const int   sx = min(max(x + dx, 0), W - 1), sy = min(max(y + dy, 0), H - 1);
                 const float sd = __ldg(&depth.at(sx, sy)), sr = __ldg(&roughness.at(sx, sy));
-                if (is_reflection_sample(sr, sd, A.RoughnessThreshold))
+                if (is_reflection_sample(sr, sd, A.RoughnessThreshold, rev))
                 {
                     const float4 srad = __ldg(&radiance.at(sx, sy));
                     const float3 sn   = xyz(__ldg(&normal.at(sx, sy)));
@@ -672,7 +676,7 @@ extern "C" dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx
         if (r1 <= r0) continue;
         dim3 block(32, 8), grid(div_up(lv[m].w, 32), div_up(r1 - r0, 8));
         View<const float> src{lv[m - 1].p, lv[m - 1].pitch, lv[m - 1].w, lv[m - 1].h};
-        ssr_hiz_level_kernel<<<grid, block, 0, as_stream(stream)>>>(src, lv[m], r0, r1);
+        ssr_hiz_level_kernel<<<grid, block, 0, as_stream(stream)>>>(src, lv[m], r0, r1, reversed_depth(&pyr->level[0]));
         DFX_LAUNCHED("ssr_hiz_level_kernel");
     }
     return DFX_OK;
@@ -695,7 +699,7 @@ extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_at
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(d.w, rows);
-    ssr_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1);
+    ssr_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1, reversed_depth(depth));
     DFX_LAUNCHED("ssr_mask_kernel");
     return DFX_OK;
 }
@@ -716,6 +720,7 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
     DFX_VIEW(float4, odir, out_raydir_pdf, DFX_FORMAT_RGBA32F);
     HizView H;
     DFX_REQUIRE(make_hiz(hiz, H), "bad Hi-Z pyramid");
+    const bool rev = reversed_depth(&hiz->level[0]) != 0; // level 0 is the depth buffer
     DFX_SAME_SIZE(c, n);
     DFX_SAME_SIZE(c, r);
     DFX_SAME_SIZE(c, k);
@@ -754,18 +759,27 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
             }
         }
         View<const float2> mv{nullptr, 0, 0, 0};
-        ssr_intersect_kernel<false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, pa);
+        if (rev)
+            ssr_intersect_kernel<false, true, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, pa);
+        else
+            ssr_intersect_kernel<false, true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, pa);
     }
     else if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
     {
         DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
         DFX_SAME_SIZE(c, mv);
-        ssr_intersect_kernel<true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+        if (rev)
+            ssr_intersect_kernel<true, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+        else
+            ssr_intersect_kernel<true, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
     }
     else
     {
         View<const float2> mv{nullptr, 0, 0, 0};
-        ssr_intersect_kernel<false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+        if (rev)
+            ssr_intersect_kernel<false, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+        else
+            ssr_intersect_kernel<false, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
     }
     DFX_LAUNCHED("ssr_intersect_kernel");
     return DFX_OK;
@@ -883,7 +897,7 @@ extern "C" dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attr
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(d.w, rows);
-    ssr_bilateral_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, d, n, r, ra, va, o, rows.y0, rows.y1);
+    ssr_bilateral_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, d, n, r, ra, va, o, rows.y0, rows.y1, reversed_depth(depth));
     DFX_LAUNCHED("ssr_bilateral_kernel");
     return DFX_OK;
 }

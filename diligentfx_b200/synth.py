@@ -309,3 +309,36 @@ def noise_frame(width: int, height: int, seed: int = 3) -> dict:
     motion = (rng.uniform(-1, 1, (height, width, 2)) * 4.0 / np.array([width, height])).astype(np.float32)
     return dict(depth=depth, normal=normal, color=color, material=material, motion=motion, prev_depth=depth.copy(),
                 curr_camera=cam.attribs, prev_camera=cam.attribs, frame=0)
+
+
+def _reversed_camera(a: CameraAttribs) -> CameraAttribs:
+    """The same camera with a reversed-depth projection: depth' = 1 - depth, i.e. (row-vector convention, clip.z = z*m22 + m32,
+    clip.w = z) m22' = 1 - m22, m32' = -m32; the derived matrices are recomputed in float64 from the stored float32 ones."""
+    def get(m):
+        return np.array([[m.m[r][c] for c in range(4)] for r in range(4)], np.float64)
+
+    def put(dst, m):
+        m32 = np.asarray(m, np.float32)
+        for r in range(4):
+            for c in range(4):
+                dst.m[r][c] = float(m32[r, c])
+
+    out = CameraAttribs.from_buffer_copy(bytes(a))
+    view, proj = get(a.mView), get(a.mProj)
+    proj[2, 2], proj[3, 2] = 1.0 - proj[2, 2], -proj[3, 2]
+    vp = view @ proj
+    put(out.mProj, proj), put(out.mViewProj, vp)
+    put(out.mProjInv, np.linalg.inv(proj)), put(out.mViewProjInv, np.linalg.inv(vp))
+    out.fNearPlaneDepth, out.fFarPlaneDepth, out.fSceneNearDepth, out.fSceneFarDepth = 1.0, 0.0, 1.0, 0.0
+    return out
+
+
+def reverse_depth_frame(frame: dict) -> dict:
+    """The same frame as a renderer with a reversed depth buffer would produce it (PostFXContext::FEATURE_FLAG_REVERSED_DEPTH):
+    depth' = 1 - depth (exact in fp32 for depth >= 0.5, which is where this scene lives), background = 0, cameras with the
+    reversed projection. Everything else is unchanged."""
+    out = dict(frame)
+    for k in ("depth", "prev_depth"):
+        out[k] = (np.float32(1.0) - np.asarray(frame[k], np.float32)).astype(np.float32)
+    out["curr_camera"], out["prev_camera"] = _reversed_camera(frame["curr_camera"]), _reversed_camera(frame["prev_camera"])
+    return out

@@ -72,8 +72,15 @@ typedef struct dfx_plane
     int32_t  width;
     int32_t  height;
     int32_t  format; /* dfx_format */
-    int32_t  reserved;
+    int32_t  flags;  /* DFX_PLANE_FLAG_*; 0 for every plane but a reversed depth buffer */
 } dfx_plane;
+/* A DEPTH plane (or level 0 of a depth pyramid) that stores reversed depth: near = 1, far = 0. Stands in for
+ * PostFXContext::FEATURE_FLAG_REVERSED_DEPTH (PostFXContext.hpp:54) at the pass level, where the reference compiles the
+ * POSTFX/SSAO/SSR_OPTION_INVERTED_DEPTH shader variants (ComputeClosestMotion.fx:5-9,36-40; SSAO_Common.fxh:6-23;
+ * SSR_Common.fxh:6-12,48-55; SSR_ComputeIntersection.fx:109-124): the passes that read the plane take the closest depth
+ * as the maximum, the far plane as 0 and the background test as depth < 1e-6. The effect-level objects set it themselves
+ * from the PostFX feature flag.                                                                                  */
+#define DFX_PLANE_FLAG_REVERSED_DEPTH 1
 
 #define DFX_MAX_MIPS 8
 /* A mip chain of planes (level i is max(w>>i,1) x max(h>>i,1)). Stands in for a mip-mapped ITexture. */
@@ -215,7 +222,7 @@ typedef struct dfx_frame_desc
 
 /* feature flags: numeric values of the reference enums */
 #define DFX_POSTFX_FEATURE_FLAG_NONE                 0u
-#define DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH       (1u << 0) /* unsupported in this build */
+#define DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH       (1u << 0) /* depth: near = 1, far = 0 (see DFX_PLANE_FLAG_REVERSED_DEPTH) */
 #define DFX_POSTFX_FEATURE_FLAG_HALF_PRECISION_DEPTH (1u << 1) /* unsupported */
 #define DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING   (1u << 2) /* unsupported */
 #define DFX_SSAO_FEATURE_FLAG_NONE                   0u

@@ -126,6 +126,7 @@ namespace orc
 {
 float oracle_fast_acos(float v);
 extern std::atomic<unsigned long long> g_march_rays, g_march_iterations;
+bool g_reversed_depth = false;
 } // namespace orc
 
 extern "C"
@@ -357,6 +358,7 @@ ORC_API void     orc_taa_jitter(uint32_t frame, uint32_t w, uint32_t hgt, float*
     float2 j = taa_jitter_offset(frame, w, hgt);
     out[0] = j.x, out[1] = j.y;
 }
+ORC_API void orc_set_reversed_depth(int on) { orc::g_reversed_depth = on != 0; } // process-wide, like a shader macro
 ORC_API void orc_march_stats(unsigned long long* rays, unsigned long long* iterations, int reset)
 {
     *rays       = orc::g_march_rays.load();

@@ -14,6 +14,11 @@
 namespace orc
 {
 
+// PostFXContext::FEATURE_FLAG_REVERSED_DEPTH (PostFXContext.hpp:54): the reference compiles the *_OPTION_INVERTED_DEPTH variants
+// of its shaders; the oracle switches at run time (orc_set_reversed_depth). Defined in oracle_capi.cpp.
+extern bool g_reversed_depth;
+
+
 constexpr float M_PI_F       = 3.14159265358979f;   // PostFX_Common.fxh:6  M_PI
 constexpr float M_HALF_PI_F  = 1.57079632679490f;   // PostFX_Common.fxh:7
 constexpr float PBR_PI       = 3.141592653589793f;  // PBR_Common.fxh:5

@@ -97,13 +97,13 @@ void postfx_closest_motion(const TexF& depth, const TexF2& motion, TexF2& out, i
         for (int py = ya; py < yb; ++py)
             for (int px = 0; px < depth.w; ++px)
             {
-                float ClosestDepth = 1.0f; // DepthFarPlane
+                float ClosestDepth = g_reversed_depth ? 0.0f : 1.0f; // DepthFarPlane (ComputeClosestMotion.fx:5-9)
                 int2  ClosestOffset(0, 0);
                 for (int x = -1; x <= 1; x++)
                     for (int y = -1; y <= 1; y++)
                     {
                         float NeighborDepth = depth.load(px + x, py + y); // unclamped Load: OOB -> 0
-                        if (NeighborDepth < ClosestDepth)
+                        if (g_reversed_depth ? NeighborDepth > ClosestDepth : NeighborDepth < ClosestDepth) // :36-40
                         {
                             ClosestOffset = int2(x, y);
                             ClosestDepth  = NeighborDepth;
@@ -118,7 +118,7 @@ void postfx_closest_motion(const TexF& depth, const TexF2& motion, TexF2& out, i
 // SSAO
 // =====================================================================================================================
 
-static inline bool IsBackground(float Depth) { return Depth >= (1.0f - 1e-6f); } // SSAO_Common.fxh:16-23
+static inline bool IsBackground(float Depth) { return g_reversed_depth ? Depth < 1e-6f : Depth >= (1.0f - 1e-6f); } // SSAO_Common.fxh:16-23
 
 // SSAO_Common.fxh:25-28
 static inline float ComputeGeometryWeight(float3 CenterPos, float3 TapPos, float3 CenterNormal, float PlaneDistanceNorm)

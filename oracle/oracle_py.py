@@ -86,6 +86,10 @@ class Oracle:
     def set_frame_index(self, idx: int):
         self.L.orc_set_frame_index(self.h_, C.c_uint32(idx))
 
+    def set_reversed_depth(self, on: bool):
+        """PostFXContext::FEATURE_FLAG_REVERSED_DEPTH (process-wide switch, like the reference's shader macro)."""
+        self.L.orc_set_reversed_depth(int(bool(on)))
+
     def set_threads(self, t: int):
         self.L.orc_set_threads(self.h_, t)
 

@@ -6,7 +6,7 @@
 namespace orc
 {
 
-static inline bool IsBackground(float Depth) { return Depth >= (1.0f - 1e-6f); }                         // SSR_Common.fxh:48-55
+static inline bool IsBackground(float Depth) { return g_reversed_depth ? Depth < 1e-6f : Depth >= (1.0f - 1e-6f); } // SSR_Common.fxh:48-55
 static inline bool IsReflectionSample(float R, float D, float Thr) { return R <= Thr && !IsBackground(D); } // :57-60
 static inline bool IsMirrorReflection(float R) { return R < 0.01f; }                                     // :62-65
 
@@ -26,8 +26,11 @@ void ssr_hiz(const TexF& depth, MipTex<float>& pyr, int threads)
                 for (int x = 0; x < dst.w; ++x)
                 {
                     int   rx = 2 * x, ry = 2 * y;
-                    float MinDepth = 1.0f; // DepthFarPlane
-                    auto  upd      = [&](int ox, int oy) { MinDepth = hmin(MinDepth, last.load_clamped(rx + ox, ry + oy)); };
+                    float MinDepth = g_reversed_depth ? 0.0f : 1.0f; // DepthFarPlane; ClosestDepth = max when reversed (SSR_Common.fxh:6-12)
+                    auto  upd      = [&](int ox, int oy) {
+                        const float d = last.load_clamped(rx + ox, ry + oy);
+                        MinDepth      = g_reversed_depth ? hmax(MinDepth, d) : hmin(MinDepth, d);
+                    };
                     upd(0, 0);
                     upd(0, 1);
                     upd(1, 0);
@@ -96,9 +99,9 @@ inline bool AdvanceRay(float3 Origin, float3 Direction, float3 InvDirection, flo
     XYPlane        = XYPlane * InvCurrentMipResolution + UVOffset;
     float3 BoundaryPlanes(XYPlane, SurfaceDepth);
     float3 T = BoundaryPlanes * InvDirection - Origin * InvDirection;
-    T.z      = Direction.z > 0.0f ? T.z : FLT_MAX_F;
+    T.z      = (g_reversed_depth ? Direction.z < 0.0f : Direction.z > 0.0f) ? T.z : FLT_MAX_F; // :109-113
     float TMin = hmin(hmin(T.x, T.y), T.z);
-    bool  AboveSurface = SurfaceDepth > Position.z;
+    bool  AboveSurface = g_reversed_depth ? SurfaceDepth < Position.z : SurfaceDepth > Position.z; // :118-124
     bool  SkippedTile  = asuint(TMin) != asuint(T.z) && AboveSurface;
     CurrentT           = AboveSurface ? TMin : CurrentT;
     Position           = Origin + CurrentT * Direction;
