@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -206,6 +207,18 @@ def generate_frame(scene: Scene, frame: int, width: int, height: int, prev_depth
     return generate_rows(scene, frame, width, height, 0, height, prev_depth, use_jitter, chunk_rows)
 
 
+def _map_chunks(fn, starts) -> None:
+    starts = list(starts)
+    workers = min(len(starts), max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))))
+    if workers <= 1:
+        for g0 in starts:
+            fn(g0)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(fn, starts))
+
+
 def generate_rows(scene: Scene, frame: int, width: int, height: int, row0: int, row1: int, prev_depth: np.ndarray | None = None,
                   use_jitter: bool = True, chunk_rows: int = 256) -> dict:
     """Rows [row0, row1) of frame `frame` of the full width x height image (arrays have row1 - row0 rows). When `prev_depth`
@@ -222,7 +235,8 @@ def generate_rows(scene: Scene, frame: int, width: int, height: int, row0: int, 
     light = light / np.linalg.norm(light)
     nobj = len(scene.radii)
     pvp = prev.view @ prev.proj
-    for g0 in range(row0, row1, chunk_rows):
+
+    def chunk(g0: int) -> None:
         grows = slice(g0, min(g0 + chunk_rows, row1))
         rows = slice(g0 - row0, grows.stop - row0)
         rc = _raycast(scene, cam, width, height, grows)
@@ -264,16 +278,24 @@ def generate_rows(scene: Scene, frame: int, width: int, height: int, row0: int, 
         color[rows, :, 3] = 1.0
         material[rows, :, 0] = np.where(rc["is_bg"], 1.0, scene.rough[oid]).astype(np.float32)
         material[rows, :, 1] = np.where(obj == nobj, 0.0, 0.5).astype(np.float32)
+
+    # Chunks are independent (every value is a per-pixel function) and numpy releases the GIL inside its kernels, so they are
+    # ray-cast on a thread pool: same chunk size, same arithmetic, same bits as the sequential loop — only the wall time of
+    # a 4K frame changes (bench.py generates its inputs at start-up, also under torchrun where OMP_NUM_THREADS is 1).
+    _map_chunks(chunk, range(row0, row1, chunk_rows))
     if prev_depth is None:
         if frame == 0:
             prev_depth = depth.copy()
         else:
             prev_depth = np.empty_like(depth)
-            for g0 in range(row0, row1, chunk_rows):
+
+            def prev_chunk(g0: int) -> None:
                 grows = slice(g0, min(g0 + chunk_rows, row1))
                 rc = _raycast(scene, prev, width, height, grows)
                 z = rc["t"]
                 prev_depth[g0 - row0:grows.stop - row0] = np.where(rc["is_bg"], 1.0, (z * prev.proj[2, 2] + prev.proj[3, 2]) / z).astype(np.float32)
+
+            _map_chunks(prev_chunk, range(row0, row1, chunk_rows))
     return dict(depth=depth, normal=normal, color=color, material=material, motion=motion, prev_depth=prev_depth,
                 curr_camera=cam.attribs, prev_camera=prev.attribs, frame=frame)
 
