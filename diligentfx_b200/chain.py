@@ -79,6 +79,7 @@ class ChainConfig:
     taa: TAAAttribs = field(default_factory=TAAAttribs.default)
     tonemap: ToneMapAttribs = field(default_factory=ToneMapAttribs.default)
     postfx_flags: int = 0                                  # capi.POSTFX_FLAG_REVERSED_DEPTH: the depth planes hold near = 1, far = 0
+    ssao_flags: int = 0                                    # capi.SSAO_FLAG_HALF_RESOLUTION
     ssr_flags: int = 0
     taa_flags: int = capi.TAA_FLAG_BICUBIC                 # Hydrogent default (HnPostProcessTask.hpp:109)
     ave_log_lum: float = 0.3                               # HnPostProcessTask.hpp:88, fExposure 0
@@ -177,7 +178,7 @@ class PostProcessChain:
         desc = FrameDesc(frame_index, self.w, self.h, self.w, self.h)
         check(L.dfx_postfx_prepare(self.postfx, C.byref(desc), cfg.postfx_flags), "dfx_postfx_prepare")
         if st & STAGE_SSAO:
-            check(L.dfx_ssao_prepare(self.ssao, self.postfx, 0), "dfx_ssao_prepare")
+            check(L.dfx_ssao_prepare(self.ssao, self.postfx, cfg.ssao_flags), "dfx_ssao_prepare")
         if st & STAGE_SSR:
             check(L.dfx_ssr_prepare(self.ssr, self.postfx, cfg.ssr_flags), "dfx_ssr_prepare")
         if st & STAGE_TAA:

@@ -172,6 +172,7 @@ struct dfx_ssao
     PlaneOwner conv_occ[5]; // [0] = accumulated AO (A5 output)
     PlaneOwner conv_depth[5]; // [0] unused: aliases the input depth
     PlaneOwner occ, resampled, hist[2], histlen[2];
+    PlaneOwner checker, occ_up; // FEATURE_FLAG_HALF_RESOLUTION: A0 output (prefiltered level 0) and A4 output
     dfx_plane  last_depth{}; // input depth of the last Execute (for get_plane of the aliased levels)
 };
 
@@ -201,23 +202,33 @@ static int mip_levels_count(int w, int h)
 extern "C" dfx_status dfx_ssao_prepare(dfx_ssao* fx, dfx_postfx* postfx, uint32_t flags)
 {
     DFX_REQUIRE(fx && postfx, "null argument");
-    if (flags != DFX_SSAO_FEATURE_FLAG_NONE) return set_error(DFX_ERR_UNSUPPORTED, "SSAO feature flags 0x%x are not implemented (full resolution, fp32 depth only)", flags);
+    if (flags & ~DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION)
+        return set_error(DFX_ERR_UNSUPPORTED, "SSAO feature flags 0x%x are not implemented (fp32 depth only)", flags);
     if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
     fx->curr_frame = postfx->desc.Index;
-    fx->flags      = flags;
-    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared) return DFX_OK;
+    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared && fx->flags == flags) return DFX_OK;
+    // a change of the resolution mode resets the temporal state, like the reference's ResetStateFeatureMask (…cpp:453)
+    fx->flags = flags, fx->last_frame = ~0u;
     fx->w = postfx->w, fx->h = postfx->h;
     fx->levels = std::min(mip_levels_count(fx->w, fx->h), 5);
+    const bool half = (flags & DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION) != 0;
+    const int  pw = half ? fx->w / 2 : fx->w, ph = half ? fx->h / 2 : fx->h; // prefiltered depth / raw occlusion (…cpp:109-110, :273-274)
+    DFX_REQUIRE(pw > 0 && ph > 0, "frame too small for half-resolution SSAO");
     dfx_status st;
     for (int i = 1; i < fx->levels; ++i)
     {
         const int mw = std::max(fx->w >> i, 1), mh = std::max(fx->h >> i, 1);
-        if ((st = fx->pre[i].alloc(mw, mh, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = fx->pre[i].alloc(std::max(pw >> i, 1), std::max(ph >> i, 1), DFX_FORMAT_R32F)) != DFX_OK) return st;
         if ((st = fx->conv_occ[i].alloc(mw, mh, DFX_FORMAT_R32F)) != DFX_OK) return st;
         if ((st = fx->conv_depth[i].alloc(mw, mh, DFX_FORMAT_R32F)) != DFX_OK) return st;
     }
+    if (half)
+    {
+        if ((st = fx->checker.alloc(pw, ph, DFX_FORMAT_R32F)) != DFX_OK) return st;
+        if ((st = fx->occ_up.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    }
     if ((st = fx->conv_occ[0].alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
-    if ((st = fx->occ.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    if ((st = fx->occ.alloc(pw, ph, DFX_FORMAT_R32F)) != DFX_OK) return st;
     if ((st = fx->resampled.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
     for (int i = 0; i < 2; ++i)
     {
@@ -258,13 +269,24 @@ extern "C" dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attri
 
     dfx_pyramid pre{}, cocc{}, cdep{};
     pre.levels = cocc.levels = cdep.levels = fx->levels;
+    const bool half = (fx->flags & DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION) != 0;
     pre.level[0] = depth, cocc.level[0] = fx->conv_occ[0].p, cdep.level[0] = depth;
     for (int i = 1; i < fx->levels; ++i) pre.level[i] = fx->pre[i].p, cocc.level[i] = fx->conv_occ[i].p, cdep.level[i] = fx->conv_depth[i].p;
 
     dfx_status st;
-    if ((st = dfx_pass_ssao_prefilter_depth(s, pfx->cams_dev, &A, &pre, all)) != DFX_OK) return st;
-    if ((st = dfx_pass_ssao_ambient_occlusion(s, pfx->cams_dev, &A, &pre, a->normal, &pfx->bn_zw.p, &fx->occ.p, all)) != DFX_OK) return st;
-    if ((st = dfx_pass_ssao_temporal(s, pfx->cams_dev, &A, &fx->occ.p, &fx->hist[prv].p, &fx->histlen[prv].p, &pfx->reproj.p, &pfx->prev_depth.p,
+    dfx_rows   pre_rows = all;
+    if (half)
+    {
+        // A0, then A1-A3 on the half-size checkerboard (…cpp:818-857); the checkerboard keeps the depth buffer's encoding
+        pre_rows = dfx_rows{0, fx->h / 2};
+        fx->checker.p.flags = depth.flags;
+        if ((st = dfx_pass_ssao_downsample_depth(s, &depth, &fx->checker.p, pre_rows)) != DFX_OK) return st;
+        pre.level[0] = fx->checker.p;
+    }
+    if ((st = dfx_pass_ssao_prefilter_depth(s, pfx->cams_dev, &A, &pre, pre_rows)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_ambient_occlusion(s, pfx->cams_dev, &A, &pre, a->normal, &pfx->bn_zw.p, &fx->occ.p, pre_rows)) != DFX_OK) return st;
+    if (half && (st = dfx_pass_ssao_upsample(s, pfx->cams_dev, &depth, &fx->occ.p, &fx->occ_up.p, all)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssao_temporal(s, pfx->cams_dev, &A, half ? &fx->occ_up.p : &fx->occ.p, &fx->hist[prv].p, &fx->histlen[prv].p, &pfx->reproj.p, &pfx->prev_depth.p,
                                      &pfx->closest.p, &fx->conv_occ[0].p, &fx->histlen[cur].p, all)) != DFX_OK)
         return st;
     if ((st = dfx_pass_ssao_convolute(s, &cocc, &cdep, all)) != DFX_OK) return st;
@@ -283,8 +305,10 @@ extern "C" dfx_status dfx_ssao_get_plane(const dfx_ssao* fx, int32_t id, dfx_pla
     else if (id == DFX_SSAO_PLANE_ACCUMULATED) *out = fx->conv_occ[0].p;
     else if (id == DFX_SSAO_PLANE_HISTORY_LENGTH) *out = fx->histlen[cur].p;
     else if (id == DFX_SSAO_PLANE_RESAMPLED) *out = fx->resampled.p;
+    else if (id == DFX_SSAO_PLANE_UPSAMPLED) *out = fx->occ_up.p;
     else if (id >= DFX_SSAO_PLANE_PREFILTERED_MIP0 && id < DFX_SSAO_PLANE_PREFILTERED_MIP0 + fx->levels)
-        *out = id == DFX_SSAO_PLANE_PREFILTERED_MIP0 ? fx->last_depth : fx->pre[id - DFX_SSAO_PLANE_PREFILTERED_MIP0].p;
+        *out = id == DFX_SSAO_PLANE_PREFILTERED_MIP0 ? ((fx->flags & DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION) ? fx->checker.p : fx->last_depth)
+                                                     : fx->pre[id - DFX_SSAO_PLANE_PREFILTERED_MIP0].p;
     else if (id >= DFX_SSAO_PLANE_CONV_AO_MIP0 && id < DFX_SSAO_PLANE_CONV_AO_MIP0 + fx->levels) *out = fx->conv_occ[id - DFX_SSAO_PLANE_CONV_AO_MIP0].p;
     else if (id >= DFX_SSAO_PLANE_CONV_DEPTH_MIP0 && id < DFX_SSAO_PLANE_CONV_DEPTH_MIP0 + fx->levels)
         *out = id == DFX_SSAO_PLANE_CONV_DEPTH_MIP0 ? fx->last_depth : fx->conv_depth[id - DFX_SSAO_PLANE_CONV_DEPTH_MIP0].p;

@@ -109,7 +109,7 @@ struct __align__(16) AoLevel
 
 template <int ALGO>
 __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
-                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev)
+                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half)
 {
     __shared__ SsaoCam S;
     __shared__ AoLevel lvl[DFX_MAX_MIPS];
@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
     // written for instruction count: MUFU reciprocals / rsqrt / sincos, no precise-division or libm slow paths, and the
     // mip LOD log2() replaced by four squared-length threshold compares (floor(clamp(log2(l) - o, 0, 4) + 0.5) counts the
     // k in 1..4 with l >= 2^(o + k - 0.5)).
-    const float u = (float(x) + 0.5f) * cam.ivw, v = (float(y) + 0.5f) * cam.ivh;
+    // FEATURE_FLAG_HALF_RESOLUTION: the target (and the pyramid) is W/2 x H/2 and GetInvViewportSize() doubles (:68-75)
+    const float ivs = half ? 2.0f : 1.0f;
+    const float u = (float(x) + 0.5f) * (ivs * cam.ivw), v = (float(y) + 0.5f) * (ivs * cam.ivh);
     const float depth = __ldg(&pyr.lv[0].at(x, y)); // point sample at the pixel centre == Load(x, y)
     if (is_background(depth, rev))
     {
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
         const float z = fdiv(cam.m32 - d * cam.m33, d * cam.m23 - cam.m22);
         return make_float3(z * (su - 0.5f) * kx, z * (sv - 0.5f) * ky, z);
     };
-    const float3 nvs = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    const float3 nvs = mul_dir(xyz(half ? sample_point_clamp(normal, u, v) : __ldg(&normal.at(x, y))), S.view); // LoadNormalWS: point clamp
     float3       pvs = to_view(u, v, depth);
     pvs              = pvs + nvs * (0.00001f * pvs.z);
     const float3 view = -fnormalize(pvs);
@@ -255,6 +257,69 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
         }
     }
     st_cs(&out.at(x, y), visibility * (1.0f / 3.0f));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A0 (half resolution only): checkerboard of the 2x2 min / max depth — SSAO_ComputeDownsampledDepth.fx:8-29
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssao_downsample_depth_kernel(View<const float> depth, View<float> out, int y0, int y1)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out.w || y >= y1) return;
+    const float2 r0 = __ldg(reinterpret_cast<const float2*>(depth.row(2 * y)) + x);     // (2x, 2y), (2x+1, 2y): 8-byte aligned
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(depth.row(2 * y + 1)) + x);
+    const float  mn = fminf(fminf(r0.x, r1.x), fminf(r0.y, r1.y)), mx = fmaxf(fmaxf(r0.x, r1.x), fmaxf(r0.y, r1.y));
+    out.at(x, y)    = lerpf(mn, mx, float((x + y) & 1));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A4 (half resolution only): 3x3 joint-bilateral upsampling of the half-res occlusion — SSAO_ComputeBilateralUpsampling.fx:62-139
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssao_upsample_kernel(const dfx_camera_attribs* __restrict__ cams, View<const float> depth,
+                                                            View<const float> occ, View<float> out, int y0, int y1, int rev)
+{
+    __shared__ SsaoCam S;
+    stage_cam(S, cams);
+    const CamS&   cam = S.c;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
+    if (x >= out.w || y >= y1) return;
+    const float dc = __ldg(&depth.at(x, y));
+    if (is_background(dc, rev))
+    {
+        st_cs(&out.at(x, y), 1.0f);
+        return;
+    }
+    const int   cx = x >> 1, cy = y >> 1;                       // int2(0.5 * floor(Position))
+    const int   hw = (int)(0.5f * cam.vw), hh = (int)(0.5f * cam.vh);
+    // IEEE division here: the depth weight is exp(-alpha^2 / 1.1e-4), a relative camera-Z error of 1e-6 is visible in it
+    auto        depth_to_camz_precise = [&](float d, const CamS& c) { return (c.m32 - d * c.m33) / (d * c.m23 - c.m22); };
+    const float zc = depth_to_camz_precise(dc, cam), izc = 1.0f / fmaxf(zc, 1e-6f);
+    // ComputeSpatialWeight(d2, 0.9) = exp(-d2 / 1.62) for d2 = 0, 1, 2; depth weight exp(-alpha^2 / (2 * 0.0075^2))
+    const float ws[3] = {1.0f, 0.53940751f, 0.29096046f};
+    float       sum = 0.0f, wsum = 0.0f;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+        {
+            const int   lx = min(max(cx + dx, 0), hw - 1), ly = min(max(cy + dy, 0), hh - 1);
+            const float tu = 2.0f * (float(lx) + 0.5f) * cam.ivw, tv = 2.0f * (float(ly) + 0.5f) * cam.ivh;
+            const float sig = load0(occ, lx, ly);
+            const float gd  = sample_linear_clamp(depth, tu, tv);
+            const float zg  = depth_to_camz_precise(gd, cam);
+            const float a   = fabsf(zc - zg) * izc;
+            const float wz  = expf(-(a * a) / (2.0f * 0.0075f * 0.0075f));
+            const float w   = ws[dx * dx + dy * dy] * wz;
+            sum += w * sig;
+            wsum += w;
+        }
+    float r;
+    if (wsum > 0.0f)
+        r = sum / wsum;
+    else
+        r = sample_linear_clamp(occ, 2.0f * (float(cx) + 0.5f) * cam.ivw, 2.0f * (float(cy) + 0.5f) * cam.ivh);
+    st_cs(&out.at(x, y), r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -554,7 +619,9 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float2, bn, blue_noise_zw, DFX_FORMAT_RG32F);
     DFX_VIEW(float, out, occlusion, DFX_FORMAT_R32F);
-    DFX_SAME_SIZE(P.lv[0], n);
+    // A pyramid of half the normal plane's size means FEATURE_FLAG_HALF_RESOLUTION (the reference allocates W/2 x H/2, …cpp:109-110)
+    const int half = (P.lv[0].w != n.w || P.lv[0].h != n.h) ? 1 : 0;
+    DFX_REQUIRE(!half || (P.lv[0].w == n.w / 2 && P.lv[0].h == n.h / 2), "the prefiltered pyramid must have the size of the normal plane or half of it");
     DFX_SAME_SIZE(P.lv[0], out);
     DFX_REQUIRE(bn.w == 128 && bn.h == 128, "blue noise must be 128x128");
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
@@ -562,12 +629,45 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
     switch (attribs->Algorithm)
     {
-        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev); break;
-        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev); break;
-        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev); break;
+        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half); break;
+        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half); break;
+        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half); break;
         default: return set_error(DFX_ERR_INVALID_ARG, "unknown SSAO algorithm %u", attribs->Algorithm);
     }
     DFX_LAUNCHED("ssao_ao_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_downsample_depth(void* stream, const dfx_plane* depth, const dfx_plane* out_half, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "ssao_downsample_depth");
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(float, o, out_half, DFX_FORMAT_R32F);
+    DFX_REQUIRE(o.w == d.w / 2 && o.h == d.h / 2, "the checkerboard plane must be width/2 x height/2 of the depth plane");
+    DFX_REQUIRE(d.pitch % 2 == 0 && reinterpret_cast<uintptr_t>(d.p) % 8 == 0, "depth rows must be 8-byte aligned");
+    DFX_REQUIRE(rows_ok(rows, o.h), "bad row range (rows of the half-resolution plane)");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    dim3 block(32, 8), grid(div_up(o.w, 32), div_up(rows.y1 - rows.y0, 8));
+    ssao_downsample_depth_kernel<<<grid, block, 0, as_stream(stream)>>>(d, o, rows.y0, rows.y1);
+    DFX_LAUNCHED("ssao_downsample_depth_kernel");
+    return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssao_upsample(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_plane* depth,
+                                             const dfx_plane* occlusion_half, const dfx_plane* out_occlusion, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "ssao_upsample");
+    DFX_REQUIRE(cameras_dev, "null argument");
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, oh, occlusion_half, DFX_FORMAT_R32F);
+    DFX_VIEW(float, o, out_occlusion, DFX_FORMAT_R32F);
+    DFX_SAME_SIZE(d, o);
+    DFX_REQUIRE(oh.w == d.w / 2 && oh.h == d.h / 2, "the half-resolution occlusion must be width/2 x height/2 of the depth plane");
+    DFX_REQUIRE(rows_ok(rows, o.h), "bad row range");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    dim3 block(32, 8), grid(div_up(o.w, 32), div_up(rows.y1 - rows.y0, 8));
+    ssao_upsample_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, d, oh, o, rows.y0, rows.y1, reversed_depth(depth));
+    DFX_LAUNCHED("ssao_upsample_kernel");
     return DFX_OK;
 }
 

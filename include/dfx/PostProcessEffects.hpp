@@ -22,7 +22,7 @@ public:
     {
         FEATURE_FLAG_NONE                 = 0u,
         FEATURE_FLAG_HALF_PRECISION_DEPTH = 1u << 0u, // not implemented
-        FEATURE_FLAG_HALF_RESOLUTION      = 1u << 1u  // not implemented
+        FEATURE_FLAG_HALF_RESOLUTION      = 1u << 1u  // AO at half resolution + bilateral upsampling
     };
     enum ALGORITHM_TYPE : Uint32
     {

@@ -227,7 +227,7 @@ typedef struct dfx_frame_desc
 #define DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING   (1u << 2) /* unsupported */
 #define DFX_SSAO_FEATURE_FLAG_NONE                   0u
 #define DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH   (1u << 0) /* unsupported */
-#define DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION        (1u << 1) /* unsupported */
+#define DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION        (1u << 1) /* A0 + A1-A3 at width/2 x height/2 + A4 */
 #define DFX_SSR_FEATURE_FLAG_NONE                    0u
 #define DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME          (1u << 0)
 #define DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION         (1u << 1) /* unsupported */
@@ -260,6 +260,17 @@ DFX_API dfx_status dfx_pass_postfx_prepare(void* stream, const dfx_camera_attrib
  * pyr->level[0] aliases the input depth (the reference's CopyTextureDepth into mip 0 is elided); levels 1..4 written. */
 DFX_API dfx_status dfx_pass_ssao_prefilter_depth(void* stream, const dfx_camera_attribs* cameras_dev,
                                                  const dfx_ssao_attribs* attribs, const dfx_pyramid* pyr, dfx_rows rows);
+
+/* FEATURE_FLAG_HALF_RESOLUTION (ScreenSpaceAmbientOcclusion.hpp:59-82): A0 builds a width/2 x height/2 checkerboard of the 2x2
+ * min / max depth, A1-A3 run on it (the prefiltered pyramid, hence the occlusion target, is half size: A3 recognises the
+ * mode by a pyramid of half the normal plane's size and doubles GetInvViewportSize(), SSAO_ComputeAmbientOcclusion.fx:68-75),
+ * and A4 brings the occlusion back to full resolution for A5-A8.
+ * A0 ComputeDepthCheckerboard (…cpp:818-841; SSAO_ComputeDownsampledDepth.fx:8-29). `rows`: rows of the half-size plane. */
+DFX_API dfx_status dfx_pass_ssao_downsample_depth(void* stream, const dfx_plane* depth, const dfx_plane* out_half, dfx_rows rows);
+/* A4 ComputeBilateralUpsampling (…cpp:992-1020; SSAO_ComputeBilateralUpsampling.fx:62-139): 3x3 joint-bilateral filter of
+ * the half-size occlusion guided by the full-resolution depth; background pixels get 1.0.                        */
+DFX_API dfx_status dfx_pass_ssao_upsample(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_plane* depth,
+                                          const dfx_plane* occlusion_half, const dfx_plane* out_occlusion, dfx_rows rows);
 
 /* A3 ComputeAmbientOcclusion (…cpp:961-990; SSAO_ComputeAmbientOcclusion.fx:132-231). Includes the clear to 1.0. */
 DFX_API dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_camera_attribs* cameras_dev,
@@ -450,6 +461,7 @@ enum
     DFX_SSAO_PLANE_ACCUMULATED       = 2,  /* A5 output == convoluted-AO mip 0                  */
     DFX_SSAO_PLANE_HISTORY_LENGTH    = 3,  /* A5 history length of the current frame            */
     DFX_SSAO_PLANE_RESAMPLED         = 4,  /* A7                                                */
+    DFX_SSAO_PLANE_UPSAMPLED         = 5,  /* A4 (half resolution only); OCCLUSION is then width/2 x height/2 */
     DFX_SSAO_PLANE_PREFILTERED_MIP0  = 10, /* +i : prefiltered depth mip i (0..4)               */
     DFX_SSAO_PLANE_CONV_AO_MIP0      = 20, /* +i : convoluted AO mip i (0..4)                   */
     DFX_SSAO_PLANE_CONV_DEPTH_MIP0   = 30  /* +i : convoluted depth mip i (0..4)                */

@@ -23,8 +23,13 @@ void postfx_closest_motion(const TexF& depth, const TexF2& motion, TexF2& out, i
 // SSAO_ComputePrefilteredDepthBuffer.fx:79-122 ; mip 0 = copy of depth (ScreenSpaceAmbientOcclusion.cpp:858-865)
 void ssao_prefilter_depth(const Camera& cam, const dfx_ssao_attribs& a, const TexF& depth, MipTex<float>& pyr, int threads);
 // SSAO_ComputeAmbientOcclusion.fx:132-231 ; target cleared to 1.0 first (…cpp:982-985)
+// half_res (FEATURE_FLAG_HALF_RESOLUTION): the pyramid, hence the target, is W/2 x H/2 and GetInvViewportSize() doubles (:68-75)
 void ssao_ambient_occlusion(const Camera& cam, const dfx_ssao_attribs& a, const MipTex<float>& prefiltered,
-                            const TexF4& normal, const TexF2& blue_noise_zw, TexF& out, int threads);
+                            const TexF4& normal, const TexF2& blue_noise_zw, TexF& out, int threads, bool half_res = false);
+// A0 SSAO_ComputeDownsampledDepth.fx:8-29 : W/2 x H/2 checkerboard of the 2x2 min / max depth
+void ssao_downsample_depth(const TexF& depth, TexF& out, int threads);
+// A4 SSAO_ComputeBilateralUpsampling.fx:62-139 : 3x3 joint-bilateral upsampling of the half-res occlusion to W x H
+void ssao_bilateral_upsampling(const Camera& cam, const TexF& depth, const TexF& occlusion_half, TexF& out, int threads);
 // SSAO_ComputeTemporalAccumulation.fx:151-182 ; both targets cleared to 1.0 first (…cpp:1059-1068)
 void ssao_temporal(const Camera& curr, const Camera& prev, const dfx_ssao_attribs& a, const TexF& curr_occlusion,
                    const TexF& prev_occlusion, const TexF& prev_history, const TexF& reprojected_depth,

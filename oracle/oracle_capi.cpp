@@ -25,6 +25,7 @@ struct Ctx
     std::vector<uint8_t> tables;
     Camera               curr, prev;
     dfx_ssao_attribs     ssao{};
+    uint                 ssao_flags = 0; // DFX_SSAO_FEATURE_FLAG_*
     dfx_ssr_attribs      ssr{};
     dfx_bloom_attribs    bloom{};
     dfx_taa_attribs      taa{};
@@ -69,10 +70,14 @@ int run_pass(Ctx& c, const std::string& p)
     else if (p == "reprojected_depth") postfx_reprojected_depth(c.curr, c.prev, c.f1["depth"], c.f1["reproj_depth"], T);
     else if (p == "closest_motion") postfx_closest_motion(c.f1["depth"], c.f2["motion"], c.f2["closest_motion"], T);
     else if (p == "previous_depth") c.f1["prev_depth"] = c.f1["prev_depth_in"];
-    else if (p == "ssao_prefilter") ssao_prefilter_depth(c.curr, c.ssao, c.f1["depth"], c.pyr["ssao_pre"], T);
-    else if (p == "ssao_ao") ssao_ambient_occlusion(c.curr, c.ssao, c.pyr["ssao_pre"], c.f4["normal"], c.f2["bn_zw"], c.f1["ssao_occ"], T);
+    // FEATURE_FLAG_HALF_RESOLUTION (bit 1 of the SSAO flags): A0, then A1-A3 on W/2 x H/2, then A4 (…SSAO.cpp:818-857, :992-1049)
+    else if (p == "ssao_downsample") ssao_downsample_depth(c.f1["depth"], c.f1["ssao_checker"], T);
+    else if (p == "ssao_prefilter") ssao_prefilter_depth(c.curr, c.ssao, c.f1[(c.ssao_flags & 2u) ? "ssao_checker" : "depth"], c.pyr["ssao_pre"], T);
+    else if (p == "ssao_ao")
+        ssao_ambient_occlusion(c.curr, c.ssao, c.pyr["ssao_pre"], c.f4["normal"], c.f2["bn_zw"], c.f1["ssao_occ"], T, (c.ssao_flags & 2u) != 0);
+    else if (p == "ssao_upsample") ssao_bilateral_upsampling(c.curr, c.f1["depth"], c.f1["ssao_occ"], c.f1["ssao_occ_up"], T);
     else if (p == "ssao_temporal")
-        ssao_temporal(c.curr, c.prev, c.ssao, c.f1["ssao_occ"], c.f1[slot("ssao_hist", prv)], c.f1[slot("ssao_histlen", prv)], c.f1["reproj_depth"],
+        ssao_temporal(c.curr, c.prev, c.ssao, c.f1[(c.ssao_flags & 2u) ? "ssao_occ_up" : "ssao_occ"], c.f1[slot("ssao_hist", prv)], c.f1[slot("ssao_histlen", prv)], c.f1["reproj_depth"],
                       c.f1["prev_depth"], c.f2["closest_motion"], c.f1["ssao_acc"], c.f1[slot("ssao_histlen", cur)], T);
     else if (p == "ssao_convolute") ssao_convolute(c.f1["ssao_acc"], c.f1["depth"], c.pyr["ssao_conv_occ"], c.pyr["ssao_conv_depth"], T);
     else if (p == "ssao_resample")
@@ -262,6 +267,7 @@ ORC_API void orc_set_cameras(void* h, const dfx_camera_attribs* curr, const dfx_
 }
 ORC_API void orc_set_frame_index(void* h, uint32_t idx) { static_cast<Ctx*>(h)->frame_index = idx; }
 ORC_API void orc_set_ssao_attribs(void* h, const dfx_ssao_attribs* a) { static_cast<Ctx*>(h)->ssao = *a; }
+ORC_API void orc_set_ssao_flags(void* h, uint32_t flags) { static_cast<Ctx*>(h)->ssao_flags = flags; }
 ORC_API void orc_set_ssr_attribs(void* h, const dfx_ssr_attribs* a, uint32_t flags)
 {
     static_cast<Ctx*>(h)->ssr       = *a;
@@ -312,7 +318,10 @@ ORC_API int orc_frame(void* h, uint32_t stages)
         dfx_ssao_attribs user = c.ssao;
         bool reset = c.ssao_last == ~0u || c.frame_index != c.ssao_last + 1u || user.ResetAccumulation != 0;
         c.ssao.ResetAccumulation = reset ? 1 : 0;
-        run("ssao_prefilter"), run("ssao_ao"), run("ssao_temporal"), run("ssao_convolute"), run("ssao_resample"), run("ssao_spatial");
+        if (c.ssao_flags & 2u) run("ssao_downsample");
+        run("ssao_prefilter"), run("ssao_ao");
+        if (c.ssao_flags & 2u) run("ssao_upsample");
+        run("ssao_temporal"), run("ssao_convolute"), run("ssao_resample"), run("ssao_spatial");
         c.ssao      = user;
         c.ssao_last = c.frame_index;
     }

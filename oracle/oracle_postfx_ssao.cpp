@@ -266,12 +266,76 @@ static float2 ComputeSampleHorizons(float3 S0, float3 S1, float3 PositionVS, flo
     return float2(hmax(MaxCosHorizons.x, l.x), hmax(MaxCosHorizons.y, l.y));
 }
 
+// A0 SSAO_ComputeDownsampledDepth.fx:8-29
+void ssao_downsample_depth(const TexF& depth, TexF& out, int threads)
+{
+    const int W = depth.w / 2, H = depth.h / 2;
+    out.resize(W, H);
+    parallel_rows(0, H, threads, [&](int ya, int yb) {
+        for (int y = ya; y < yb; ++y)
+            for (int x = 0; x < W; ++x)
+            {
+                float Depth0 = depth.load(2 * x + 0, 2 * y + 0), Depth1 = depth.load(2 * x + 0, 2 * y + 1);
+                float Depth2 = depth.load(2 * x + 1, 2 * y + 0), Depth3 = depth.load(2 * x + 1, 2 * y + 1);
+                float MinDepth = hmin(hmin(Depth0, Depth1), hmin(Depth2, Depth3));
+                float MaxDepth = hmax(hmax(Depth0, Depth1), hmax(Depth2, Depth3));
+                int   Pattern  = ((x + y) & 1) & 1; // ComputeCheckerboardPattern :8-11
+                out.at(x, y)   = lerp(MinDepth, MaxDepth, float(Pattern));
+            }
+    });
+}
+
+// A4 SSAO_ComputeBilateralUpsampling.fx:62-139 (g_TextureDepth: linear clamp, g_TextureOcclusion: linear clamp, …cpp:614-615)
+void ssao_bilateral_upsampling(const Camera& cam, const TexF& depth, const TexF& occ, TexF& out, int threads)
+{
+    const int W = depth.w, H = depth.h;
+    out.resize(W, H);
+    const float2 InvViewport(cam.f4ViewportSize.z, cam.f4ViewportSize.w);
+    const int2   HalfDim(int(0.5f * cam.f4ViewportSize.x), int(0.5f * cam.f4ViewportSize.y));
+    const float  Sigma = 0.9f, DepthSigma = 0.0075f; // SSAO_BILATERAL_UPSAMPLING_SIGMA / _DEPTH_SIGMA (Structures.fxh:38,41)
+    auto ComputeDepthWeight = [&](float CenterDepth, float GuideDepth, float S) {
+        float LinearDepth0 = DepthToCameraZ(CenterDepth, cam.mProj);
+        float LinearDepth1 = DepthToCameraZ(GuideDepth, cam.mProj);
+        float Alpha        = std::fabs(LinearDepth0 - LinearDepth1) / hmax(LinearDepth0, 1e-6f);
+        return std::exp(-(Alpha * Alpha) / (2.0f * S * S));
+    };
+    parallel_rows(0, H, threads, [&](int ya, int yb) {
+        for (int py = ya; py < yb; ++py)
+            for (int px = 0; px < W; ++px)
+            {
+                float CenterDepth = depth.load(px, py);
+                if (IsBackground(CenterDepth))
+                {
+                    out.at(px, py) = 1.0f;
+                    continue;
+                }
+                int2  CenterLocation(int(0.5f * float(px)), int(0.5f * float(py))); // int2(0.5 * floor(Position.xy))
+                float OcclusionSum = 0.0f, WeightSum = 0.0f;
+                for (int x = -1; x <= 1; x++)
+                    for (int y = -1; y <= 1; y++)
+                    {
+                        int2   Location = ClampScreenCoord(int2(CenterLocation.x + x, CenterLocation.y + y), HalfDim);
+                        float2 Texcoord = float2(2.0f * (float(Location.x) + 0.5f), 2.0f * (float(Location.y) + 0.5f)) * InvViewport;
+                        float  SampledSignal = occ.load(Location.x, Location.y);
+                        float  SampledGuided = sample_linear(depth, Texcoord, Address::Clamp);
+                        float  WeightS       = ComputeSpatialWeight(float(x * x + y * y), Sigma);
+                        float  WeightZ       = ComputeDepthWeight(CenterDepth, SampledGuided, DepthSigma);
+                        OcclusionSum += WeightS * WeightZ * SampledSignal;
+                        WeightSum += WeightS * WeightZ;
+                    }
+                float2 CenterUV = float2(2.0f * (float(CenterLocation.x) + 0.5f), 2.0f * (float(CenterLocation.y) + 0.5f)) * InvViewport;
+                out.at(px, py)  = WeightSum > 0.0f ? OcclusionSum / WeightSum : sample_linear(occ, CenterUV, Address::Clamp);
+            }
+    });
+}
+
 void ssao_ambient_occlusion(const Camera& cam, const dfx_ssao_attribs& A, const MipTex<float>& pre, const TexF4& normal,
-                            const TexF2& blue_noise_zw, TexF& out, int threads)
+                            const TexF2& blue_noise_zw, TexF& out, int threads, bool half_res)
 {
     const int W = pre.mip[0].w, H = pre.mip[0].h;
     out.resize(W, H, 1.0f); // ClearRenderTarget 1.0
-    const float2 InvViewport(cam.f4ViewportSize.z, cam.f4ViewportSize.w);
+    const float  ivs = half_res ? 2.0f : 1.0f; // GetInvViewportSize() :68-75
+    const float2 InvViewport(ivs * cam.f4ViewportSize.z, ivs * cam.f4ViewportSize.w);
     const float2 Viewport(cam.f4ViewportSize.x, cam.f4ViewportSize.y);
 
     auto SamplePrefilteredDepth = [&](float2 uv, float MipLevel) {

@@ -96,6 +96,10 @@ class Oracle:
     def set_ssao(self, a):
         self.L.orc_set_ssao_attribs(self.h_, C.byref(a))
 
+    def set_ssao_flags(self, flags: int):
+        """DFX_SSAO_FEATURE_FLAG_* (bit 1 = HALF_RESOLUTION)."""
+        self.L.orc_set_ssao_flags(self.h_, C.c_uint32(flags))
+
     def set_ssr(self, a, flags: int = 0):
         self.L.orc_set_ssr_attribs(self.h_, C.byref(a), C.c_uint32(flags))
 
