@@ -24,6 +24,7 @@ TAA_FLAG_GAUSSIAN, TAA_FLAG_BICUBIC, TAA_FLAG_YCOCG = 1, 2, 4
 SSR_FLAG_PREVIOUS_FRAME = 1
 POSTFX_FLAG_REVERSED_DEPTH = 1
 SSAO_FLAG_HALF_RESOLUTION = 2
+SSR_FLAG_HALF_RESOLUTION = 2
 
 
 class Float4x4(C.Structure):

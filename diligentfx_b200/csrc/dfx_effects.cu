@@ -329,6 +329,7 @@ struct dfx_ssr
     AlphaTimer alpha;
     PlaneOwner hiz[7]; // [0] unused: aliases the input depth
     PlaneOwner roughness, mask, radiance, raydir, res_rad, res_var, res_depth, radhist[2], varhist[2], out;
+    PlaneOwner mask_half; // FEATURE_FLAG_HALF_RESOLUTION: S3 output; radiance / raydir are then width/2 x height/2
     dfx_plane  last_depth{};
 };
 
@@ -351,12 +352,17 @@ extern "C" dfx_status dfx_ssr_set_alpha_interpolation(dfx_ssr* fx, float alpha)
 extern "C" dfx_status dfx_ssr_prepare(dfx_ssr* fx, dfx_postfx* postfx, uint32_t flags)
 {
     DFX_REQUIRE(fx && postfx, "null argument");
-    if (flags & ~DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) return set_error(DFX_ERR_UNSUPPORTED, "SSR feature flags 0x%x are not implemented (full resolution only)", flags);
+    if (flags & ~(DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME | DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION))
+        return set_error(DFX_ERR_UNSUPPORTED, "unknown SSR feature flags 0x%x", flags);
     if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
     fx->curr_frame = postfx->desc.Index;
-    fx->flags      = flags;
-    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared) return DFX_OK;
+    const bool half = (flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) != 0;
+    const bool same_mode = ((fx->flags ^ flags) & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) == 0;
+    fx->flags = flags;
+    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared && same_mode) return DFX_OK;
     fx->w = postfx->w, fx->h = postfx->h;
+    const int pw = half ? fx->w / 2 : fx->w, ph = half ? fx->h / 2 : fx->h; // intersect targets (…cpp:201-213)
+    DFX_REQUIRE(pw > 0 && ph > 0, "frame too small for half-resolution SSR");
     fx->levels = std::min(mip_levels_count(fx->w, fx->h), 7);
     dfx_status st;
     for (int i = 1; i < fx->levels; ++i)
@@ -368,11 +374,13 @@ extern "C" dfx_status dfx_ssr_prepare(dfx_ssr* fx, dfx_postfx* postfx, uint32_t 
         {&fx->out, DFX_FORMAT_RGBA32F}};
     for (auto& pl : planes)
     {
-        if ((st = pl.p->alloc(fx->w, fx->h, pl.fmt)) != DFX_OK) return st;
+        const bool target = pl.p == &fx->radiance || pl.p == &fx->raydir;
+        if ((st = pl.p->alloc(target ? pw : fx->w, target ? ph : fx->h, pl.fmt)) != DFX_OK) return st;
         // history / output are cleared to 0 at creation (ScreenSpaceReflection.cpp:263-264, :279-280, :294-295); the targets the
         // reference never clears (roughness, resolved *) start from zeroed memory here so runs are deterministic.
-        DFX_CUDA(cudaMemset2D(pl.p->p.ptr, pl.p->p.pitch_bytes, 0, pl.p->p.pitch_bytes, fx->h));
+        DFX_CUDA(cudaMemset2D(pl.p->p.ptr, pl.p->p.pitch_bytes, 0, pl.p->p.pitch_bytes, pl.p->p.height));
     }
+    if (half && (st = fx->mask_half.alloc(pw, ph, DFX_FORMAT_R8U)) != DFX_OK) return st;
     fx->prepared = true;
     return DFX_OK;
 }
@@ -403,8 +411,11 @@ extern "C" dfx_status dfx_ssr_execute(dfx_ssr* fx, const dfx_ssr_render_attribs*
     dfx_status st;
     if ((st = dfx_pass_ssr_hiz(s, &hz, all)) != DFX_OK) return st;
     if ((st = dfx_pass_ssr_mask_roughness(s, &A, a->material, &depth, &fx->roughness.p, &fx->mask.p, all)) != DFX_OK) return st;
-    if ((st = dfx_pass_ssr_intersect(s, pfx->cams_dev, &A, fx->flags, a->color, a->normal, &fx->roughness.p, &fx->mask.p, &pfx->bn_xy.p, &hz, a->motion,
-                                     &fx->radiance.p, &fx->raydir.p, all)) != DFX_OK)
+    const bool half = (fx->flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) != 0;
+    const dfx_rows trows = half ? dfx_rows{0, fx->h / 2} : all;
+    if (half && (st = dfx_pass_ssr_downsample_mask(s, &A, &fx->roughness.p, &depth, &fx->mask_half.p, trows)) != DFX_OK) return st;
+    if ((st = dfx_pass_ssr_intersect(s, pfx->cams_dev, &A, fx->flags, a->color, a->normal, &fx->roughness.p, half ? &fx->mask_half.p : &fx->mask.p,
+                                     &pfx->bn_xy.p, &hz, a->motion, &fx->radiance.p, &fx->raydir.p, trows)) != DFX_OK)
         return st;
     if ((st = dfx_pass_ssr_spatial(s, pfx->cams_dev, &A, &fx->roughness.p, &fx->mask.p, a->normal, &depth, &fx->raydir.p, &fx->radiance.p, &fx->res_rad.p,
                                    &fx->res_var.p, &fx->res_depth.p, all)) != DFX_OK)
@@ -428,6 +439,7 @@ extern "C" dfx_status dfx_ssr_get_plane(const dfx_ssr* fx, int32_t id, dfx_plane
         case DFX_SSR_PLANE_OUTPUT: *out = fx->out.p; break;
         case DFX_SSR_PLANE_ROUGHNESS: *out = fx->roughness.p; break;
         case DFX_SSR_PLANE_MASK: *out = fx->mask.p; break;
+        case DFX_SSR_PLANE_MASK_HALF: *out = fx->mask_half.p; break;
         case DFX_SSR_PLANE_RADIANCE: *out = fx->radiance.p; break;
         case DFX_SSR_PLANE_RAYDIR_PDF: *out = fx->raydir.p; break;
         case DFX_SSR_PLANE_RESOLVED_RADIANCE: *out = fx->res_rad.p; break;

@@ -53,6 +53,29 @@ __global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, View<c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// S3 (half resolution only): downsampled mask — closest depth and largest roughness of the 2x2 (+ odd row / column)
+// footprint pass IsReflectionSample — SSR_ComputeDownsampledStencilMask.fx:13-61
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssr_downsample_mask_kernel(dfx_ssr_attribs A, View<const float> roughness, View<const float> depth,
+                                                                  View<uint8_t> mask, int y0, int y1, int rev)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= mask.w || y >= y1) return;
+    const bool wodd = depth.w & 1, hodd = depth.h & 1;
+    float      md = rev ? 0.0f : 1.0f, mr = 0.0f;
+    const auto upd = [&](int ox, int oy) {
+        const float d = loadc(depth, 2 * x + ox, 2 * y + oy);
+        md            = rev ? fmaxf(md, d) : fminf(md, d);
+        mr            = fmaxf(mr, loadc(roughness, 2 * x + ox, 2 * y + oy));
+    };
+    upd(0, 0), upd(1, 0), upd(0, 1), upd(1, 1);
+    if (wodd) upd(2, 0), upd(2, 1);
+    if (hodd) upd(0, 2), upd(1, 2);
+    if (wodd && hodd) upd(2, 2);
+    mask.at(x, y) = is_reflection_sample(mr, md, A.RoughnessThreshold, rev) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // S4: stochastic GGX ray + Hi-Z march + hit validation — SSR_ComputeIntersection.fx:281-325
 // ---------------------------------------------------------------------------------------------------------------------
 struct IntersectCam
@@ -167,7 +190,7 @@ template <bool PREV_FRAME, bool PEER, bool REV>
 __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                             View<const float4> color, View<const float4> normal, View<const float> roughness,
                                                             View<const uint8_t> mask, View<const float2> noise, HizView hiz,
-                                                            View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1,
+                                                            View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1, int half,
                                                             const __grid_constant__ typename std::conditional<PEER, PeerArgs, NoPeerTables>::type peer_args)
 {
     __shared__ IntersectCam S;
@@ -215,10 +238,18 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         return;
     }
     const float sw = cam.vw, sh = cam.vh;
-    const float u = (float(x) + 0.5f) * cam.ivw, v = (float(y) + 0.5f) * cam.ivh;
-    const float3 nws = xyz(__ldg(&normal.at(x, y)));
+    // FEATURE_FLAG_HALF_RESOLUTION: the targets are W/2 x H/2 and each target pixel traces the ray of one of its four
+    // full-resolution pixels, picked by a 4x4 pattern of 2-bit offsets (PostFX_Common.fxh:45-55; :283-288)
+    int px = x, py = y;
+    if (half)
+    {
+        const unsigned idx = (1320229860u >> ((((unsigned)x & 3u) << 3) + (((unsigned)y & 3u) << 1))) & 3u;
+        px = 2 * x + (int)(idx & 1u), py = 2 * y + (int)(idx >> 1);
+    }
+    const float u = (float(px) + 0.5f) * cam.ivw, v = (float(py) + 0.5f) * cam.ivh;
+    const float3 nws = xyz(__ldg(&normal.at(px, py)));
     const float3 nvs = mul_dir(nws, S.view);
-    const float  rough = __ldg(&roughness.at(x, y));
+    const float  rough = __ldg(&roughness.at(px, py));
 
     const bool  mirror  = rough < 0.01f;
     const int   baseMip = mirror ? 0 : (int)A.MostDetailedMip;
@@ -365,7 +396,7 @@ struct SpatialCam
 __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                           View<const float> roughness, View<const uint8_t> mask, View<const float4> normal,
                                                           View<const float> depth, View<const float4> raydir, View<const float4> radiance,
-                                                          View<float4> out_rad, View<float> out_var, View<float> out_depth, int y0, int y1)
+                                                          View<float4> out_rad, View<float> out_var, View<float> out_depth, int y0, int y1, int half)
 {
     __shared__ SpatialCam S;
     if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(S.c, &cams[0]), load_mat(S.vp_inv, cams[0].mViewProjInv);
@@ -401,7 +432,12 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(c
     {
         const float3 P  = kSsrPoisson8[i];
         const float  xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
-        const int    sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
+        int          sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
+        if (half) // the intersect targets are W/2 x H/2: int2(0.5 * (floor(Position) + Radius * Xi) + 0.5) (:153-157)
+        {
+            sx = min(max((int)(0.5f * (float(x) + radius * xi) + 0.5f), 0), (int)(0.5f * cam.vw) - 1);
+            sy = min(max((int)(0.5f * (float(y) + radius * yi) + 0.5f), 0), (int)(0.5f * cam.vh) - 1);
+        }
         const float  ws = kSsrPoisson8Weight[i]; // exp(-z^2 / (2 * 0.9^2)), a constant per disk sample
         // ComputeWeightRayLength :60-86
         float        weight, raylen;
@@ -704,13 +740,30 @@ extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_at
     return DFX_OK;
 }
 
+extern "C" dfx_status dfx_pass_ssr_downsample_mask(void* stream, const dfx_ssr_attribs* attribs, const dfx_plane* roughness, const dfx_plane* depth,
+                                                   const dfx_plane* mask_half, dfx_rows rows)
+{
+    DFX_PROFILE(stream, "ssr_downsample_mask");
+    DFX_REQUIRE(attribs, "null argument");
+    DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
+    DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
+    DFX_VIEW(uint8_t, k, mask_half, DFX_FORMAT_R8U);
+    DFX_SAME_SIZE(d, r);
+    DFX_REQUIRE(k.w == d.w / 2 && k.h == d.h / 2, "the downsampled mask must be width/2 x height/2 of the depth plane");
+    DFX_REQUIRE(rows_ok(rows, k.h), "bad row range (rows of the half-size mask)");
+    if (rows.y1 == rows.y0) return DFX_OK;
+    DFX_GRID(k.w, rows);
+    ssr_downsample_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, r, d, k, rows.y0, rows.y1, reversed_depth(depth));
+    DFX_LAUNCHED("ssr_downsample_mask_kernel");
+    return DFX_OK;
+}
+
 static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, uint32_t flags,
                                      const dfx_peer_set* peers, const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness,
                                      const dfx_plane* mask, const dfx_plane* blue_noise_xy, const dfx_pyramid* hiz, const dfx_plane* motion,
                                      const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
 {
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
-    DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) == 0, "half-resolution SSR is not implemented");
     DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
@@ -723,14 +776,18 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
     const bool rev = reversed_depth(&hiz->level[0]) != 0; // level 0 is the depth buffer
     DFX_SAME_SIZE(c, n);
     DFX_SAME_SIZE(c, r);
-    DFX_SAME_SIZE(c, k);
-    DFX_SAME_SIZE(c, orad);
-    DFX_SAME_SIZE(c, odir);
+    // Targets (and mask) of half the colour plane's size mean FEATURE_FLAG_HALF_RESOLUTION (…cpp:201-213: Radiance and
+    // RayDirectionPDF are W/2 x H/2; the mask is then the downsampled one of dfx_pass_ssr_downsample_mask)
+    const int half = (orad.w != c.w || orad.h != c.h) ? 1 : 0;
+    DFX_REQUIRE(!half || (orad.w == c.w / 2 && orad.h == c.h / 2), "the intersect targets must have the size of the colour plane or half of it");
+    DFX_REQUIRE(!half || !peers, "half-resolution SSR is not supported on peer-sharded frames");
+    DFX_SAME_SIZE(orad, k);
+    DFX_SAME_SIZE(orad, odir);
     DFX_SAME_SIZE(c, H.lv[0]);
     DFX_REQUIRE(bn.w == 128 && bn.h == 128, "blue noise must be 128x128");
-    DFX_REQUIRE(rows_ok(rows, c.h), "bad row range");
+    DFX_REQUIRE(rows_ok(rows, orad.h), "bad row range (rows of the intersect targets)");
     if (rows.y1 == rows.y0) return DFX_OK;
-    DFX_GRID(c.w, rows);
+    DFX_GRID(orad.w, rows);
     if (peers)
     {
         DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) == 0, "previous-frame SSR is not supported on peer-sharded frames");
@@ -760,26 +817,26 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
         }
         View<const float2> mv{nullptr, 0, 0, 0};
         if (rev)
-            ssr_intersect_kernel<false, true, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, pa);
+            ssr_intersect_kernel<false, true, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
         else
-            ssr_intersect_kernel<false, true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, pa);
+            ssr_intersect_kernel<false, true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
     }
     else if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
     {
         DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
         DFX_SAME_SIZE(c, mv);
         if (rev)
-            ssr_intersect_kernel<true, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+            ssr_intersect_kernel<true, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
         else
-            ssr_intersect_kernel<true, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+            ssr_intersect_kernel<true, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
     }
     else
     {
         View<const float2> mv{nullptr, 0, 0, 0};
         if (rev)
-            ssr_intersect_kernel<false, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+            ssr_intersect_kernel<false, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
         else
-            ssr_intersect_kernel<false, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, NoPeerTables{});
+            ssr_intersect_kernel<false, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
     }
     DFX_LAUNCHED("ssr_intersect_kernel");
     return DFX_OK;
@@ -825,15 +882,16 @@ extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attrib
     DFX_SAME_SIZE(d, r);
     DFX_SAME_SIZE(d, k);
     DFX_SAME_SIZE(d, n);
-    DFX_SAME_SIZE(d, rd);
-    DFX_SAME_SIZE(d, ra);
+    const int half = (rd.w != d.w || rd.h != d.h) ? 1 : 0; // half-size intersect targets = FEATURE_FLAG_HALF_RESOLUTION
+    DFX_REQUIRE(!half || (rd.w == d.w / 2 && rd.h == d.h / 2), "the intersect planes must have the size of the depth plane or half of it");
+    DFX_SAME_SIZE(rd, ra);
     DFX_SAME_SIZE(d, orad);
     DFX_SAME_SIZE(d, ovar);
     DFX_SAME_SIZE(d, odep);
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(d.w, rows);
-    ssr_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, r, k, n, d, rd, ra, orad, ovar, odep, rows.y0, rows.y1);
+    ssr_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, r, k, n, d, rd, ra, orad, ovar, odep, rows.y0, rows.y1, half);
     DFX_LAUNCHED("ssr_spatial_kernel");
     return DFX_OK;
 }

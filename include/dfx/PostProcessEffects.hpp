@@ -103,7 +103,7 @@ public:
     {
         FEATURE_FLAG_NONE            = 0u,
         FEATURE_FLAG_PREVIOUS_FRAME  = 1u << 0u,
-        FEATURE_FLAG_HALF_RESOLUTION = 1u << 1u // not implemented
+        FEATURE_FLAG_HALF_RESOLUTION = 1u << 1u // one ray per 2x2 block, half-size intersect targets
     };
     struct RenderAttributes
     {

@@ -230,7 +230,7 @@ typedef struct dfx_frame_desc
 #define DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION        (1u << 1) /* A0 + A1-A3 at width/2 x height/2 + A4 */
 #define DFX_SSR_FEATURE_FLAG_NONE                    0u
 #define DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME          (1u << 0)
-#define DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION         (1u << 1) /* unsupported */
+#define DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION         (1u << 1) /* S3 + S4 at width/2 x height/2 */
 #define DFX_BLOOM_FEATURE_FLAG_NONE                  0u
 #define DFX_TAA_FEATURE_FLAG_NONE                    0u
 #define DFX_TAA_FEATURE_FLAG_GAUSSIAN_WEIGHTING      (1u << 0)
@@ -316,6 +316,14 @@ DFX_API dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx_ro
 DFX_API dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_attribs* attribs,
                                                const dfx_plane* material, const dfx_plane* depth,
                                                const dfx_plane* roughness, const dfx_plane* mask, dfx_rows rows);
+
+/* FEATURE_FLAG_HALF_RESOLUTION (ScreenSpaceReflection.hpp:64-76): S3 downsamples the mask, S4 traces one ray per 2x2 block
+ * into width/2 x height/2 targets (which of the four pixels: a 4x4 pattern, PostFX_Common.fxh:45-55), S5 gathers from the
+ * half-size targets; S6 / S7 are unchanged. S4 and S5 recognise the mode by intersect planes of half the frame size.
+ * S3 ComputeDownsampledStencilMask (…cpp:934-961; SSR_ComputeDownsampledStencilMask.fx:13-61): 1 where the closest depth
+ * and the largest roughness of the 2x2 (+ odd row / column) footprint pass IsReflectionSample. `rows`: of the half-size mask. */
+DFX_API dfx_status dfx_pass_ssr_downsample_mask(void* stream, const dfx_ssr_attribs* attribs, const dfx_plane* roughness,
+                                                const dfx_plane* depth, const dfx_plane* mask_half, dfx_rows rows);
 
 /* S4 ComputeIntersection (…cpp:963-999; SSR_ComputeIntersection.fx:281-325). Includes both clears to 0.
  * motion may be NULL unless DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME is set in `flags`.                             */
@@ -478,7 +486,8 @@ enum
     DFX_SSR_PLANE_RESOLVED_DEPTH    = 7,
     DFX_SSR_PLANE_RADIANCE_HISTORY  = 8,  /* current frame's slot                               */
     DFX_SSR_PLANE_VARIANCE_HISTORY  = 9,
-    DFX_SSR_PLANE_HIZ_MIP0          = 10  /* +i : Hi-Z mip i (0..6)                             */
+    DFX_SSR_PLANE_HIZ_MIP0          = 10, /* +i : Hi-Z mip i (0..6)                             */
+    DFX_SSR_PLANE_MASK_HALF         = 20  /* S3 (half resolution only); RADIANCE / RAYDIR_PDF are then half size */
 };
 enum
 {

@@ -57,7 +57,9 @@ void ssr_intersect(const Camera& cam, const dfx_ssr_attribs& a, uint flags, cons
 // SSR_ComputeSpatialReconstruction.fx:114-172 ; masked, targets not cleared
 void ssr_spatial(const Camera& cam, const dfx_ssr_attribs& a, const TexF& roughness, const Tex<uint8_t>& mask,
                  const TexF4& normal, const TexF& depth, const TexF4& raydir_pdf, const TexF4& radiance,
-                 TexF4& out_radiance, TexF& out_variance, TexF& out_depth, int threads);
+                 TexF4& out_radiance, TexF& out_variance, TexF& out_depth, int threads, bool half_res = false);
+// S3 SSR_ComputeDownsampledStencilMask.fx:13-61 (half resolution only): W/2 x H/2 mask of the 2x2 closest depth / max roughness
+void ssr_downsample_mask(const dfx_ssr_attribs& a, const TexF& roughness, const TexF& depth, Tex<uint8_t>& mask_half, int threads);
 // SSR_ComputeTemporalAccumulation.fx:224-263 ; masked, targets not cleared
 void ssr_temporal(const Camera& curr, const Camera& prev, const dfx_ssr_attribs& a, const Tex<uint8_t>& mask,
                   const TexF2& motion, const TexF& hit_depth, const TexF& reprojected_depth, const TexF4& curr_radiance,

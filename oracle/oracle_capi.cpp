@@ -90,12 +90,14 @@ int run_pass(Ctx& c, const std::string& p)
     }
     else if (p == "ssr_hiz") ssr_hiz(c.f1["depth"], c.pyr["ssr_hiz"], T);
     else if (p == "ssr_mask") ssr_mask_roughness(c.ssr, c.f4["material"], c.f1["depth"], c.f1["ssr_roughness"], c.u8["ssr_mask"], T);
+    // FEATURE_FLAG_HALF_RESOLUTION (bit 1 of the SSR flags): S3, S4 on W/2 x H/2 with the downsampled mask, S5 gathers from the half-size targets
+    else if (p == "ssr_downsample_mask") ssr_downsample_mask(c.ssr, c.f1["ssr_roughness"], c.f1["depth"], c.u8["ssr_mask_half"], T);
     else if (p == "ssr_intersect")
-        ssr_intersect(c.curr, c.ssr, c.ssr_flags, c.f4["color"], c.f4["normal"], c.f1["ssr_roughness"], c.u8["ssr_mask"], c.f2["bn_xy"], c.pyr["ssr_hiz"],
+        ssr_intersect(c.curr, c.ssr, c.ssr_flags, c.f4["color"], c.f4["normal"], c.f1["ssr_roughness"], c.u8[(c.ssr_flags & 2u) ? "ssr_mask_half" : "ssr_mask"], c.f2["bn_xy"], c.pyr["ssr_hiz"],
                       &c.f2["motion"], c.f4["ssr_radiance"], c.f4["ssr_raydir"], T);
     else if (p == "ssr_spatial")
         ssr_spatial(c.curr, c.ssr, c.f1["ssr_roughness"], c.u8["ssr_mask"], c.f4["normal"], c.f1["depth"], c.f4["ssr_raydir"], c.f4["ssr_radiance"],
-                    c.f4["ssr_resolved_rad"], c.f1["ssr_resolved_var"], c.f1["ssr_resolved_depth"], T);
+                    c.f4["ssr_resolved_rad"], c.f1["ssr_resolved_var"], c.f1["ssr_resolved_depth"], T, (c.ssr_flags & 2u) != 0);
     else if (p == "ssr_temporal")
         ssr_temporal(c.curr, c.prev, c.ssr, c.u8["ssr_mask"], c.f2["motion"], c.f1["ssr_resolved_depth"], c.f1["reproj_depth"], c.f4["ssr_resolved_rad"],
                      c.f1["ssr_resolved_var"], c.f1["prev_depth"], c.f4[slot("ssr_radhist", prv)], c.f1[slot("ssr_varhist", prv)],
@@ -217,7 +219,7 @@ ORC_API int orc_get_plane(void* h, const char* name, float* out, int* w, int* hg
     Ctx&        c = *static_cast<Ctx*>(h);
     std::string n(name);
     auto        dot_pos = n.find('.');
-    if (n == "ssr_mask" && c.u8.count(n))
+    if ((n == "ssr_mask" || n == "ssr_mask_half") && c.u8.count(n))
     {
         const Tex<uint8_t>& t = c.u8[n];
         *w = t.w, *hgt = t.h, *ch = 1;
@@ -311,7 +313,12 @@ ORC_API int orc_frame(void* h, uint32_t stages)
     int  r  = 0;
     auto run = [&](const char* p) { if (!r) r = run_pass(c, p); };
     if (stages & 1u) run("blue_noise"), run("reprojected_depth"), run("closest_motion"), run("previous_depth");
-    if (stages & 2u) run("ssr_hiz"), run("ssr_mask"), run("ssr_intersect"), run("ssr_spatial"), run("ssr_temporal"), run("ssr_bilateral");
+    if (stages & 2u)
+    {
+        run("ssr_hiz"), run("ssr_mask");
+        if (c.ssr_flags & 2u) run("ssr_downsample_mask");
+        run("ssr_intersect"), run("ssr_spatial"), run("ssr_temporal"), run("ssr_bilateral");
+    }
     if (stages & 4u)
     {
         // UpdateConstantBuffer reset rule (…SSAO.cpp:797-800)

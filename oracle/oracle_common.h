@@ -167,6 +167,13 @@ inline bool IsInsideScreen(float2 PixelCoord, float2 Dimension)
     return PixelCoord.x >= 0.0f && PixelCoord.y >= 0.0f && PixelCoord.x < Dimension.x && PixelCoord.y < Dimension.y;
 }
 // :129-132
+// PostFX_Common.fxh:45-55
+inline uint ComputeHalfResolutionOffset(uint x, uint y)
+{
+    const uint PackedOffsets = 1320229860u; // 4x4 matrix of 2-bit offsets: 0 1 2 3 / 3 2 1 0 / 1 0 3 2 / 2 3 0 1
+    const uint Idx           = ((x & 0x3u) << 3u) + ((y & 0x3u) << 1u);
+    return (PackedOffsets >> Idx) & 0x3u;
+}
 inline int2 ClampScreenCoord(int2 PixelCoord, int2 Dimension) { return int2(clampi(PixelCoord.x, 0, Dimension.x - 1), clampi(PixelCoord.y, 0, Dimension.y - 1)); }
 // :134-137
 inline float ComputeSpatialWeight(float Distance, float Sigma) { return std::exp(-(Distance) / (2.0f * Sigma * Sigma)); }

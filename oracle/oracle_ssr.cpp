@@ -78,6 +78,32 @@ void ssr_mask_roughness(const dfx_ssr_attribs& A, const TexF4& material, const T
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// S3  SSR_ComputeDownsampledStencilMask.fx:13-61 ; host: ScreenSpaceReflection.cpp:934-961 (half resolution only)
+void ssr_downsample_mask(const dfx_ssr_attribs& A, const TexF& roughness, const TexF& depth, Tex<uint8_t>& mask_half, int threads)
+{
+    const int W = depth.w / 2, H = depth.h / 2;
+    mask_half.resize(W, H, 0); // ClearDepthStencil 0.0
+    const bool IsWidthOdd = (depth.w & 1) != 0, IsHeightOdd = (depth.h & 1) != 0;
+    parallel_rows(0, H, threads, [&](int ya, int yb) {
+        for (int y = ya; y < yb; ++y)
+            for (int x = 0; x < W; ++x)
+            {
+                float MinDepth = g_reversed_depth ? 0.0f : 1.0f, MaxRoughness = 0.0f; // DepthFarPlane
+                auto  upd      = [&](int ox, int oy) {
+                    const float d = depth.load_clamped(2 * x + ox, 2 * y + oy);
+                    MinDepth      = g_reversed_depth ? hmax(MinDepth, d) : hmin(MinDepth, d);
+                    MaxRoughness  = hmax(MaxRoughness, roughness.load_clamped(2 * x + ox, 2 * y + oy));
+                };
+                upd(0, 0), upd(1, 0), upd(0, 1), upd(1, 1);
+                if (IsWidthOdd) upd(2, 0), upd(2, 1);
+                if (IsHeightOdd) upd(0, 2), upd(1, 2);
+                if (IsWidthOdd && IsHeightOdd) upd(2, 2);
+                if (IsReflectionSample(MaxRoughness, MinDepth, A.RoughnessThreshold)) mask_half.at(x, y) = 1;
+            }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // S4  SSR_ComputeIntersection.fx
 // workload statistics of the Hi-Z march (rays traced, loop iterations), for DESIGN.md / the bench report
 std::atomic<unsigned long long> g_march_rays{0}, g_march_iterations{0};
@@ -171,7 +197,10 @@ void ssr_intersect(const Camera& cam, const dfx_ssr_attribs& A, uint flags, cons
                    const Tex<uint8_t>& mask, const TexF2& blue_noise_xy, const MipTex<float>& hiz, const TexF2* motion, TexF4& out_radiance,
                    TexF4& out_raydir_pdf, int threads)
 {
-    const int W = color.w, H = color.h;
+    // FEATURE_FLAG_HALF_RESOLUTION: targets and (downsampled) mask are W/2 x H/2; every target pixel traces the ray of ONE of
+    // its four full-resolution pixels, chosen by a 4x4 pattern (:283-288)
+    const bool HalfRes = (flags & DFX_SSR_FEATURE_FLAG_HALF_RESOLUTION) != 0;
+    const int  W = HalfRes ? color.w / 2 : color.w, H = HalfRes ? color.h / 2 : color.h;
     out_radiance.resize(W, H, float4());
     out_raydir_pdf.resize(W, H, float4());
     const bool   PreviousFrame = (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) != 0;
@@ -184,10 +213,16 @@ void ssr_intersect(const Camera& cam, const dfx_ssr_attribs& A, uint flags, cons
                 if (!mask.load(px, py)) continue; // depth test LESS vs mask (early depth-stencil)
 
                 float2 Position(float(px) + 0.5f, float(py) + 0.5f);
+                if (HalfRes)
+                {
+                    uint SampleIdx = ComputeHalfResolutionOffset(uint(px), uint(py));
+                    Position       = float2(2.0f * float(px) + float(SampleIdx & 0x01u) + 0.5f, 2.0f * float(py) + float(SampleIdx >> 1u) + 0.5f);
+                }
+                const int fx = ftoi(Position.x), fy = ftoi(Position.y); // int2(Position)
                 float2 ScreenCoordUV = Position * float2(cam.f4ViewportSize.z, cam.f4ViewportSize.w);
-                float3 NormalWS  = normal.load(px, py).xyz();
+                float3 NormalWS  = normal.load(fx, fy).xyz();
                 float3 NormalVS  = mul_dir(NormalWS, cam.mView);
-                float  Roughness = roughness.load(px, py);
+                float  Roughness = roughness.load(fx, fy);
 
                 bool   IsMirror        = IsMirrorReflection(Roughness);
                 int    MostDetailedMip = IsMirror ? 0 : int(A.MostDetailedMip);
@@ -277,7 +312,7 @@ void ssr_intersect(const Camera& cam, const dfx_ssr_attribs& A, uint flags, cons
 // S5  SSR_ComputeSpatialReconstruction.fx:114-172
 void ssr_spatial(const Camera& cam, const dfx_ssr_attribs& A, const TexF& roughness, const Tex<uint8_t>& mask, const TexF4& normal,
                  const TexF& depth, const TexF4& raydir_pdf, const TexF4& radiance, TexF4& out_radiance, TexF& out_variance, TexF& out_depth,
-                 int threads)
+                 int threads, bool half_res)
 {
     static const float3 Poisson[8] = {
         float3(-0.4706069f, -0.4427112f, +0.6461146f), float3(-0.9057375f, +0.3003471f, +0.9542373f),
@@ -317,6 +352,11 @@ void ssr_spatial(const Camera& cam, const dfx_ssr_attribs& A, const TexF& roughn
                     float2 Xi = RotateVector(Rotator, Poisson[i].xy());
                     float2 sp = Position + Radius * Xi;
                     int2   SampleCoord = ClampScreenCoord(int2(ftoi(sp.x), ftoi(sp.y)), Dim);
+                    if (half_res) // the intersect targets are W/2 x H/2 (:153-157)
+                    {
+                        float2 hp   = (float2(float(px), float(py)) + Radius * Xi) * 0.5f + float2(0.5f, 0.5f);
+                        SampleCoord = ClampScreenCoord(int2(ftoi(hp.x), ftoi(hp.y)), int2(int(0.5f * cam.f4ViewportSize.x), int(0.5f * cam.f4ViewportSize.y)));
+                    }
                     float  WeightS = ComputeSpatialWeight(Poisson[i].z * Poisson[i].z, 0.9f);
 
                     // ComputeWeightRayLength :60-86
