@@ -96,8 +96,10 @@ extern "C" void dfx_postfx_destroy(dfx_postfx* c) { delete c; }
 extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* desc, uint32_t flags)
 {
     DFX_REQUIRE(c && desc, "null argument");
-    if (flags & ~DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH)
-        return set_error(DFX_ERR_UNSUPPORTED, "PostFX feature flags 0x%x are not implemented (fp32 depth, no temporal upscaling)", flags);
+    if (flags & ~(DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH | DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING))
+        return set_error(DFX_ERR_UNSUPPORTED, "PostFX feature flags 0x%x are not implemented (fp32 depth only)", flags);
+    DFX_REQUIRE(!(flags & DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING) || (desc->OutputWidth > 0 && desc->OutputHeight > 0),
+                "temporal upscaling needs FrameDesc.OutputWidth / OutputHeight");
     DFX_REQUIRE(desc->Width > 0 && desc->Height > 0, "empty frame");
     c->desc  = *desc;
     c->flags = flags;
@@ -490,8 +492,11 @@ extern "C" dfx_status dfx_bloom_prepare(dfx_bloom* fx, dfx_postfx* postfx, uint3
     DFX_REQUIRE(fx && postfx, "null argument");
     if (flags != DFX_BLOOM_FEATURE_FLAG_NONE) return set_error(DFX_ERR_UNSUPPORTED, "unknown Bloom feature flags 0x%x", flags);
     if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
-    if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared) return DFX_OK;
-    fx->w = postfx->w, fx->h = postfx->h;
+    // Bloom runs after the temporal upscaler when there is one: on the OUTPUT resolution of the frame (Bloom.cpp:84-85)
+    const bool upscaled = (postfx->flags & DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING) != 0;
+    const int  bw = upscaled ? (int)postfx->desc.OutputWidth : postfx->w, bh = upscaled ? (int)postfx->desc.OutputHeight : postfx->h;
+    if (fx->w == bw && fx->h == bh && fx->prepared) return DFX_OK;
+    fx->w = bw, fx->h = bh;
     // Bloom.cpp:96-128: TextureCount = ComputeMipLevelsCount(W/2, H/2), level i = max(half >> i, 1)
     const int hw = std::max(fx->w / 2, 1), hh = std::max(fx->h / 2, 1);
     const int count = mip_levels_count(hw, hh);

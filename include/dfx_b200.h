@@ -224,7 +224,7 @@ typedef struct dfx_frame_desc
 #define DFX_POSTFX_FEATURE_FLAG_NONE                 0u
 #define DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH       (1u << 0) /* depth: near = 1, far = 0 (see DFX_PLANE_FLAG_REVERSED_DEPTH) */
 #define DFX_POSTFX_FEATURE_FLAG_HALF_PRECISION_DEPTH (1u << 1) /* unsupported */
-#define DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING   (1u << 2) /* unsupported */
+#define DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING   (1u << 2) /* Bloom runs at FrameDesc.OutputWidth x OutputHeight (Bloom.cpp:84-85) */
 #define DFX_SSAO_FEATURE_FLAG_NONE                   0u
 #define DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH   (1u << 0) /* unsupported */
 #define DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION        (1u << 1) /* A0 + A1-A3 at width/2 x height/2 + A4 */

@@ -106,3 +106,40 @@ def test_cuda_reversed_hiz_is_max_pyramid(built):
                 want[y, x] = max(0.0, max(prev[yy, xx] for yy in ys for xx in xs))
         assert np.array_equal(lv[i].cpu().numpy(), want), f"level {i}"
         prev = want
+
+
+@pytest.mark.gpu
+def test_temporal_upscaling_runs_bloom_at_output_resolution(built):
+    """PostFXContext::FEATURE_FLAG_TEMPORAL_UPSCALING: Bloom takes FrameDesc.OutputWidth x OutputHeight instead of the render
+    resolution (Bloom.cpp:84-85). Checked through the effect-level objects against the oracle's Bloom at that size."""
+    import ctypes as C
+
+    import torch
+    from diligentfx_b200 import capi
+    from diligentfx_b200.capi import BloomAttribs, BloomRenderAttribs, FrameDesc, Plane
+    from oracle import oracle_py as op
+    L = capi.load()
+    w, h, ow, oh = 96, 64, 144, 96  # 1.5x upscaling
+    rng = np.random.default_rng(3)
+    src = np.exp2(rng.uniform(-3, 5, (oh, ow, 4))).astype(np.float32)
+    o = op.Oracle(ow, oh, threads=2)
+    o.set_bloom(BloomAttribs.default())
+    o.set("bloom_in", src)
+    o.run("bloom")
+    postfx, bloom = C.c_void_p(), C.c_void_p()
+    capi.check(L.dfx_postfx_create(C.byref(postfx))), capi.check(L.dfx_bloom_create(C.byref(bloom)))
+    try:
+        assert L.dfx_postfx_prepare(postfx, C.byref(FrameDesc(0, w, h, 0, 0)), 4) == capi.DFX_ERR_INVALID_ARG  # needs the output size
+        capi.check(L.dfx_postfx_prepare(postfx, C.byref(FrameDesc(0, w, h, ow, oh)), 4), "postfx prepare")
+        capi.check(L.dfx_bloom_prepare(bloom, postfx, 0), "bloom prepare")
+        color = torch.from_numpy(src).cuda()
+        pc, a = capi.plane_of(color), BloomAttribs.default()
+        capi.check(L.dfx_bloom_execute(bloom, C.byref(BloomRenderAttribs(None, postfx, C.pointer(pc), C.pointer(a)))), "bloom execute")
+        out = Plane()
+        capi.check(L.dfx_bloom_get_plane(bloom, 0, C.byref(out)))
+        assert (out.width, out.height) == (ow, oh)
+        from diligentfx_b200.chain import download_plane
+        got = download_plane(out)
+        assert psnr(rein(got), rein(o.get("bloom_out"))) >= 90.0
+    finally:
+        L.dfx_bloom_destroy(bloom), L.dfx_postfx_destroy(postfx)
