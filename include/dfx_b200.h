@@ -420,6 +420,24 @@ DFX_API dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_
 DFX_API dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao,
                                     float ssr_scale, float ssao_scale, const dfx_plane* out, dfx_rows rows);
 
+/* Compose step, full form (Hydrogent/shaders/HnPostProcess.psh:145-185; host HnPostProcessTask.cpp:834-869). With
+ * Opacity = color.a:
+ *   rgb += (GetSpecularIBL_GGX(surface, view, ssr.rgb) - specular_ibl.rgb) * ssr.a * ssr_scale * Opacity
+ *   rgb *= lerp(1, ao, ssao_scale * Opacity);                       alpha passes through
+ * i.e. the reflection is re-weighted by the split-sum BRDF of the surface (metallic-roughness workflow, PBR_Shading.fxh:
+ * 220-302 with USE_IBL_MULTIPLE_SCATTERING = 1, :429-451; material.x = roughness, material.y = metallic) and exchanged for
+ * the image-based specular term the renderer had already added. `brdf_lut` = dfx_pass_precompute_brdf_lut (RG32F, sampled
+ * linear-clamp at (N.V, roughness)). ssr == NULL skips the first line (the five planes it needs may then be NULL too);
+ * ao == NULL skips the second.                                                                                     */
+DFX_API dfx_status dfx_pass_compose_ibl(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_plane* color,
+                                        const dfx_plane* ssr, const dfx_plane* ao, const dfx_plane* specular_ibl,
+                                        const dfx_plane* normal, const dfx_plane* base_color, const dfx_plane* material,
+                                        const dfx_plane* brdf_lut, float ssr_scale, float ssao_scale, const dfx_plane* out,
+                                        dfx_rows rows);
+/* Pre-integrated GGX table (Shaders/PBR/private/PrecomputeBRDF.psh:10-48; PBR_Renderer.cpp:548-625 builds it once at
+ * 512 x 512 with 512 samples): texel (x, y) = (scale, bias) of the split sum at N.V = (x + .5)/w, roughness = (y + .5)/h. */
+DFX_API dfx_status dfx_pass_precompute_brdf_lut(void* stream, uint32_t num_samples, const dfx_plane* out_lut);
+
 /* M1+M2 ToneMap() (ToneMapping.fxh:87-226) + optional LinearToSRGB (SRGBUtilities.fxh:27-33), as used by
  * Hydrogent/shaders/HnCopyFrame.psh:32-62. ave_log_lum is the already exposure-scaled fAveLogLum argument.     */
 DFX_API dfx_status dfx_pass_tonemap(void* stream, const dfx_tonemap_attribs* attribs, float ave_log_lum,

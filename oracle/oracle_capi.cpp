@@ -105,6 +105,9 @@ int run_pass(Ctx& c, const std::string& p)
     else if (p == "ssr_bilateral")
         ssr_bilateral(c.curr, c.ssr, c.u8["ssr_mask"], c.f1["depth"], c.f4["normal"], c.f1["ssr_roughness"], c.f4[slot("ssr_radhist", cur)],
                       c.f1[slot("ssr_varhist", cur)], c.f4["ssr_out"], T);
+    else if (p == "compose_ibl")
+        compose_ibl(c.curr, c.f4["color"], &c.f4["ssr_out"], &c.f1["ssao_out"], c.f4["specular_ibl"], c.f4["normal"], c.f4["base_color"], c.f4["material"],
+                    c.f2["brdf_lut"], c.ssr_scale, c.ssao_scale, c.f4["composed"], T);
     else if (p == "compose") compose(c.f4["color"], &c.f4["ssr_out"], &c.f1["ssao_out"], c.ssr_scale, c.ssao_scale, c.f4["composed"], T);
     else if (p == "taa")
         taa_accumulate(c.curr, c.prev, c.taa, c.taa_flags, c.f4["taa_in"], c.f4[slot("taa_accum", prv)], c.f2["closest_motion"], c.f1["reproj_depth"],
@@ -373,6 +376,11 @@ ORC_API void     orc_taa_jitter(uint32_t frame, uint32_t w, uint32_t hgt, float*
 {
     float2 j = taa_jitter_offset(frame, w, hgt);
     out[0] = j.x, out[1] = j.y;
+}
+ORC_API void orc_brdf_lut(void* h, int size, uint32_t num_samples)
+{
+    Ctx& c = *static_cast<Ctx*>(h);
+    orc::brdf_lut(size, num_samples, c.f2["brdf_lut"], c.threads);
 }
 ORC_API void orc_set_reversed_depth(int on) { orc::g_reversed_depth = on != 0; } // process-wide, like a shader macro
 ORC_API void orc_march_stats(unsigned long long* rays, unsigned long long* iterations, int reset)
