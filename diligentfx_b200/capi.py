@@ -77,6 +77,19 @@ class BloomAttribs(C.Structure):
         return BloomAttribs(0.15, 1.0, 0.125, 0.75, 1.0, 0.0, 0.0, 0.0)
 
 
+class DOFAttribs(C.Structure):
+    _fields_ = [("MaxCircleOfConfusion", C.c_float), ("TemporalStabilityFactor", C.c_float), ("BokehKernelRingCount", C.c_int32),
+                ("BokehKernelRingDensity", C.c_int32), ("AlphaInterpolation", C.c_float), ("Padding0", C.c_float), ("Padding1", C.c_float),
+                ("Padding2", C.c_float)]
+
+    @staticmethod
+    def default() -> "DOFAttribs":
+        return DOFAttribs(0.01, 0.9375, 5, 7, 1.0, 0.0, 0.0, 0.0)
+
+
+DOF_FLAG_TEMPORAL_SMOOTHING, DOF_FLAG_KARIS_INVERSE = 1, 2
+
+
 class TAAAttribs(C.Structure):
     _fields_ = [("TemporalStabilityFactor", C.c_float), ("ResetAccumulation", C.c_int32), ("SkipRejection", C.c_int32),
                 ("Padding0", C.c_float)]
@@ -150,6 +163,12 @@ class TAARenderAttribs(C.Structure):
                 ("accumulation_buffer_idx", C.c_uint32)]
 
 
+class DOFRenderAttribs(C.Structure):
+    _fields_ = [("stream", C.c_void_p), ("postfx", C.c_void_p), ("color", C.POINTER(Plane)), ("depth", C.POINTER(Plane)),
+                ("attribs", C.POINTER(DOFAttribs))]
+
+
+assert C.sizeof(DOFAttribs) == 32
 assert C.sizeof(CameraAttribs) == 576 and C.sizeof(SSAOAttribs) == 48 and C.sizeof(SSRAttribs) == 48
 assert C.sizeof(BloomAttribs) == 32 and C.sizeof(TAAAttribs) == 16 and C.sizeof(ToneMapAttribs) == 48
 

@@ -80,6 +80,8 @@ class ChainConfig:
     tonemap: ToneMapAttribs = field(default_factory=ToneMapAttribs.default)
     postfx_flags: int = 0                                  # capi.POSTFX_FLAG_REVERSED_DEPTH: the depth planes hold near = 1, far = 0
     ssao_flags: int = 0                                    # capi.SSAO_FLAG_HALF_RESOLUTION
+    dof: capi.DOFAttribs | None = None                     # DepthOfField between TAA and Bloom (HnPostProcessTask.cpp:899-909); None = off
+    dof_flags: int = 0                                     # capi.DOF_FLAG_TEMPORAL_SMOOTHING | capi.DOF_FLAG_KARIS_INVERSE
     ssr_flags: int = 0
     taa_flags: int = capi.TAA_FLAG_BICUBIC                 # Hydrogent default (HnPostProcessTask.hpp:109)
     ave_log_lum: float = 0.3                               # HnPostProcessTask.hpp:88, fExposure 0
@@ -102,12 +104,13 @@ class PostProcessChain:
         if not torch.cuda.is_available():
             raise capi.DfxError("no CUDA device: the PostProcess chain has no CPU path")
         L = self.lib
-        self.postfx, self.ssao, self.ssr, self.bloom, self.taa = (C.c_void_p() for _ in range(5))
+        self.postfx, self.ssao, self.ssr, self.bloom, self.taa, self.dof = (C.c_void_p() for _ in range(6))
         check(L.dfx_postfx_create(C.byref(self.postfx)), "dfx_postfx_create")
         check(L.dfx_ssao_create(C.byref(self.ssao)), "dfx_ssao_create")
         check(L.dfx_ssr_create(C.byref(self.ssr)), "dfx_ssr_create")
         check(L.dfx_bloom_create(C.byref(self.bloom)), "dfx_bloom_create")
         check(L.dfx_taa_create(C.byref(self.taa)), "dfx_taa_create")
+        check(L.dfx_dof_create(C.byref(self.dof)), "dfx_dof_create")
         dev = self.device
         # device-resident inputs (filled by upload()) and chain-owned intermediates
         self.inputs = {n: torch.empty((height, width) + ((c,) if c else ()), dtype=torch.float32, device=dev) for n, c in INPUT_SPECS.items()}
@@ -129,11 +132,11 @@ class PostProcessChain:
 
     def close(self):
         L = self.lib
-        for h, fn in ((self.taa, L.dfx_taa_destroy), (self.bloom, L.dfx_bloom_destroy), (self.ssr, L.dfx_ssr_destroy), (self.ssao, L.dfx_ssao_destroy),
+        for h, fn in ((self.dof, L.dfx_dof_destroy), (self.taa, L.dfx_taa_destroy), (self.bloom, L.dfx_bloom_destroy), (self.ssr, L.dfx_ssr_destroy), (self.ssao, L.dfx_ssao_destroy),
                       (self.postfx, L.dfx_postfx_destroy)):
             if h:
                 fn(h)
-        self.postfx = self.ssao = self.ssr = self.bloom = self.taa = None
+        self.postfx = self.ssao = self.ssr = self.bloom = self.taa = self.dof = None
 
     def __del__(self):
         try:
@@ -171,7 +174,7 @@ class PostProcessChain:
         stream = C.c_void_p(main.cuda_stream)
         st = cfg.stages
         side_ao = cfg.overlap and bool(st & STAGE_SSAO) and bool(st & STAGE_SSR)
-        side_post = self._side_post = cfg.overlap and bool(st & STAGE_BLOOM) and bool(st & STAGE_TAA)
+        side_post = self._side_post = cfg.overlap and bool(st & STAGE_BLOOM) and bool(st & STAGE_TAA) and cfg.dof is None
         P = {n: plane_of(t) for n, t in (inputs or self.inputs).items()}
 
         # Prepare (HnPostProcessTask.cpp:671-683)
@@ -185,6 +188,8 @@ class PostProcessChain:
             check(L.dfx_taa_prepare(self.taa, self.postfx, cfg.taa_flags, 0), "dfx_taa_prepare")
         if st & STAGE_BLOOM:
             check(L.dfx_bloom_prepare(self.bloom, self.postfx, 0), "dfx_bloom_prepare")
+        if cfg.dof is not None:
+            check(L.dfx_dof_prepare(self.dof, self.postfx, cfg.dof_flags), "dfx_dof_prepare")
 
         # Execute (HnPostProcessTask.cpp:788-925)
         if st & STAGE_POSTFX:
@@ -232,6 +237,13 @@ class PostProcessChain:
             acc = Plane()
             check(L.dfx_taa_get_plane(self.taa, 0, 0, C.byref(acc)), "dfx_taa_get_plane")
             color = acc
+        if cfg.dof is not None:
+            # on the main stream: it reads the PostFX planes of this frame and its output feeds Bloom, so Bloom stays here too
+            a = capi.DOFRenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(P["depth"]), C.pointer(cfg.dof))
+            check(L.dfx_dof_execute(self.dof, C.byref(a)), "dfx_dof_execute")
+            dof_out = Plane()
+            check(L.dfx_dof_get_plane(self.dof, 0, C.byref(dof_out)), "dfx_dof_get_plane")
+            color = dof_out
         if side_post:
             self._post_stream.wait_stream(main)
             stream = C.c_void_p(self._post_stream.cuda_stream)
@@ -369,6 +381,8 @@ class PostProcessChain:
             check(L.dfx_bloom_get_plane(self.bloom, plane_id, C.byref(p)))
         elif effect == "taa":
             check(L.dfx_taa_get_plane(self.taa, plane_id, 0, C.byref(p)))
+        elif effect == "dof":
+            check(L.dfx_dof_get_plane(self.dof, plane_id, C.byref(p)))
         else:
             raise KeyError(effect)
         torch.cuda.synchronize(self.device)  # side streams included

@@ -678,3 +678,121 @@ extern "C" dfx_status dfx_taa_get_jitter_offset(const dfx_taa* fx, uint32_t idx,
     dfx_taa_jitter_offset(it->second.curr_frame, it->second.w, it->second.h, out);
     return DFX_OK;
 }
+
+// =====================================================================================================================
+// DepthOfField (PostProcess/DepthOfField/src/DepthOfField.cpp; interface/DepthOfField.hpp:59-125)
+// =====================================================================================================================
+struct dfx_dof
+{
+    int        w = 0, h = 0;
+    uint32_t   flags = 0, curr_frame = 0;
+    bool       prepared = false;
+    AlphaTimer alpha;
+    PlaneOwner coc, coc_temporal[2], dilation[4], dilation_tmp, pre[2], bokeh[2], out;
+};
+
+extern "C" dfx_status dfx_dof_create(dfx_dof** out)
+{
+    DFX_REQUIRE(out, "out must not be null");
+    *out = new (std::nothrow) dfx_dof;
+    DFX_REQUIRE(*out, "out of memory");
+    return DFX_OK;
+}
+extern "C" void dfx_dof_destroy(dfx_dof* fx) { delete fx; }
+extern "C" dfx_status dfx_dof_set_alpha_interpolation(dfx_dof* fx, float alpha)
+{
+    DFX_REQUIRE(fx, "null argument");
+    fx->alpha.pinned  = alpha;
+    fx->alpha.started = false;
+    return DFX_OK;
+}
+
+// DepthOfField::PrepareResources (…cpp:152-290)
+extern "C" dfx_status dfx_dof_prepare(dfx_dof* fx, dfx_postfx* postfx, uint32_t flags)
+{
+    DFX_REQUIRE(fx && postfx, "null argument");
+    if (flags & ~(DFX_DOF_FEATURE_FLAG_ENABLE_TEMPORAL_SMOOTHING | DFX_DOF_FEATURE_FLAG_ENABLE_KARIS_INVERSE))
+        return set_error(DFX_ERR_UNSUPPORTED, "unknown DepthOfField feature flags 0x%x", flags);
+    if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
+    fx->curr_frame = postfx->desc.Index;
+    if (fx->w == postfx->w && fx->h == postfx->h && fx->flags == flags && fx->prepared) return DFX_OK;
+    fx->w = postfx->w, fx->h = postfx->h, fx->flags = flags;
+    DFX_REQUIRE((fx->w >> 3) > 0 && (fx->h >> 3) > 0, "frame too small for the dilation chain (needs width, height >= 8)");
+    dfx_status st;
+    if ((st = fx->coc.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    if (flags & DFX_DOF_FEATURE_FLAG_ENABLE_TEMPORAL_SMOOTHING)
+        for (auto& t : fx->coc_temporal)
+        {
+            if ((st = t.alloc(fx->w, fx->h, DFX_FORMAT_R32F)) != DFX_OK) return st;
+            if ((st = clear_plane(nullptr, t.p, 0.0f)) != DFX_OK) return st; // cleared to 0 at creation (…cpp:187-189)
+        }
+    for (int k = 0; k < 4; ++k)
+        if ((st = fx->dilation[k].alloc(fx->w >> k, fx->h >> k, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    if ((st = fx->dilation_tmp.alloc(fx->w >> 3, fx->h >> 3, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    for (int i = 0; i < 2; ++i)
+    {
+        if ((st = fx->pre[i].alloc(fx->w / 2, fx->h / 2, DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+        if ((st = fx->bokeh[i].alloc(fx->w / 2, fx->h / 2, DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+    }
+    if ((st = fx->out.alloc(fx->w, fx->h, DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+    DFX_CUDA(cudaStreamSynchronize(nullptr));
+    fx->prepared = true;
+    return DFX_OK;
+}
+
+// DepthOfField::Execute (…cpp:292-331)
+extern "C" dfx_status dfx_dof_execute(dfx_dof* fx, const dfx_dof_render_attribs* a)
+{
+    DFX_REQUIRE(fx && a, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_dof_prepare was not called");
+    DFX_REQUIRE(a->postfx && a->color && a->depth && a->attribs, "postfx / color / depth / attribs must not be null");
+    dfx_postfx* pfx = a->postfx;
+    if (!pfx->executed) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext::Execute must run before DepthOfField");
+    DFX_REQUIRE(a->color->width == fx->w && a->color->height == fx->h, "color size does not match the prepared frame size");
+    cudaStream_t    s = as_stream(a->stream);
+    dfx_dof_attribs A = *a->attribs; // UpdateConstantBuffers (…cpp:792-818)
+    A.AlphaInterpolation = fx->alpha.value();
+    const bool     temporal = (fx->flags & DFX_DOF_FEATURE_FLAG_ENABLE_TEMPORAL_SMOOTHING) != 0;
+    const uint32_t cur = fx->curr_frame & 1u, prv = (fx->curr_frame + 1u) & 1u;
+    const auto     rows = [](const dfx_plane& p) { return dfx_rows{0, p.height}; };
+    dfx_status     st;
+    if ((st = dfx_pass_dof_coc(s, pfx->cams_dev, &A, a->depth, &fx->coc.p, rows(fx->coc.p))) != DFX_OK) return st;
+    const dfx_plane* coc = &fx->coc.p;
+    if (temporal)
+    {
+        if ((st = dfx_pass_dof_temporal_coc(s, pfx->cams_dev, &A, &fx->coc.p, &fx->coc_temporal[prv].p, &pfx->closest.p, &fx->coc_temporal[cur].p,
+                                            rows(fx->coc.p))) != DFX_OK)
+            return st;
+        coc = &fx->coc_temporal[cur].p;
+    }
+    if ((st = dfx_pass_dof_separated_coc(s, coc, &fx->dilation[0].p, rows(fx->dilation[0].p))) != DFX_OK) return st;
+    for (int k = 1; k < 4; ++k)
+        if ((st = dfx_pass_dof_dilation(s, &fx->dilation[k - 1].p, &fx->dilation[k].p, rows(fx->dilation[k].p))) != DFX_OK) return st;
+    if ((st = dfx_pass_dof_blur_coc(s, &fx->dilation[3].p, 0, &fx->dilation_tmp.p, rows(fx->dilation_tmp.p))) != DFX_OK) return st;
+    if ((st = dfx_pass_dof_blur_coc(s, &fx->dilation_tmp.p, 1, &fx->dilation[3].p, rows(fx->dilation[3].p))) != DFX_OK) return st;
+    if ((st = dfx_pass_dof_prefilter(s, a->color, coc, &fx->dilation[3].p, &fx->pre[0].p, &fx->pre[1].p, rows(fx->pre[0].p))) != DFX_OK) return st;
+    if ((st = dfx_pass_dof_bokeh(s, pfx->cams_dev, &A, fx->flags, 0, &fx->pre[0].p, &fx->pre[1].p, a->color, &fx->bokeh[0].p, &fx->bokeh[1].p,
+                                 rows(fx->bokeh[0].p))) != DFX_OK)
+        return st;
+    if ((st = dfx_pass_dof_bokeh(s, pfx->cams_dev, &A, fx->flags, 1, &fx->bokeh[0].p, &fx->bokeh[1].p, nullptr, &fx->pre[0].p, &fx->pre[1].p,
+                                 rows(fx->pre[0].p))) != DFX_OK)
+        return st;
+    if ((st = dfx_pass_dof_postfilter(s, &fx->pre[0].p, &fx->pre[1].p, &fx->bokeh[0].p, &fx->bokeh[1].p, rows(fx->bokeh[0].p))) != DFX_OK) return st;
+    return dfx_pass_dof_combine(s, &A, a->color, &fx->bokeh[0].p, &fx->bokeh[1].p, &fx->out.p, rows(fx->out.p));
+}
+
+extern "C" dfx_status dfx_dof_get_plane(const dfx_dof* fx, int32_t id, dfx_plane* out)
+{
+    DFX_REQUIRE(fx && out, "null argument");
+    if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_dof_prepare was not called");
+    if (id == DFX_DOF_PLANE_OUTPUT) *out = fx->out.p;
+    else if (id == DFX_DOF_PLANE_COC) *out = fx->coc.p;
+    else if (id == DFX_DOF_PLANE_COC_TEMPORAL) *out = fx->coc_temporal[fx->curr_frame & 1u].p;
+    else if (id >= DFX_DOF_PLANE_DILATION_MIP0 && id < DFX_DOF_PLANE_DILATION_MIP0 + 4) *out = fx->dilation[id - DFX_DOF_PLANE_DILATION_MIP0].p;
+    else if (id >= DFX_DOF_PLANE_PREFILTERED0 && id < DFX_DOF_PLANE_PREFILTERED0 + 2) *out = fx->pre[id - DFX_DOF_PLANE_PREFILTERED0].p;
+    else if (id >= DFX_DOF_PLANE_BOKEH0 && id < DFX_DOF_PLANE_BOKEH0 + 2) *out = fx->bokeh[id - DFX_DOF_PLANE_BOKEH0].p;
+    else
+        return set_error(DFX_ERR_INVALID_ARG, "unknown DepthOfField plane id %d", id);
+    DFX_REQUIRE(out->ptr != nullptr, "plane %d is not available (temporal smoothing off?)", id);
+    return DFX_OK;
+}

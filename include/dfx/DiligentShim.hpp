@@ -174,6 +174,10 @@ struct ScreenSpaceReflectionAttribs : dfx_ssr_attribs
 {
     ScreenSpaceReflectionAttribs() { dfx_ssr_attribs_default(this); }
 };
+struct DepthOfFieldAttribs : dfx_dof_attribs // DepthOfFieldStructures.fxh:31-56
+{
+    DepthOfFieldAttribs() : dfx_dof_attribs{0.01f, 0.9375f, 5, 7, 1.0f, 0.0f, 0.0f, 0.0f} {}
+};
 struct BloomAttribs : dfx_bloom_attribs
 {
     BloomAttribs() { dfx_bloom_attribs_default(this); }

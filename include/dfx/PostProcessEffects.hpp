@@ -246,6 +246,80 @@ private:
 };
 
 // =====================================================================================================================
+// PostProcess/DepthOfField/interface/DepthOfField.hpp:59-125
+class DepthOfField
+{
+public:
+    enum FEATURE_FLAGS : Uint32
+    {
+        FEATURE_FLAG_NONE                      = 0u,
+        FEATURE_FLAG_ENABLE_TEMPORAL_SMOOTHING = 1u << 0u,
+        FEATURE_FLAG_ENABLE_KARIS_INVERSE      = 1u << 1u
+    };
+    struct RenderAttributes
+    {
+        IRenderDevice*                   pDevice         = nullptr;
+        IRenderStateCache*               pStateCache     = nullptr;
+        IDeviceContext*                  pDeviceContext  = nullptr;
+        PostFXContext*                   pPostFXContext  = nullptr;
+        ITextureView*                    pColorBufferSRV = nullptr; // RGBA32_FLOAT
+        ITextureView*                    pDepthBufferSRV = nullptr; // R32_FLOAT
+        const HLSL::DepthOfFieldAttribs* pDOFAttribs     = nullptr;
+    };
+    struct CreateInfo
+    {
+        bool EnableAsyncCreation = false;
+    };
+
+    DepthOfField(IRenderDevice* pDevice, const CreateInfo& CI)
+    {
+        (void)pDevice, (void)CI;
+        detail::Check(dfx_dof_create(&m_Fx), "dfx_dof_create");
+    }
+    ~DepthOfField() { dfx_dof_destroy(m_Fx); }
+    DepthOfField(const DepthOfField&)            = delete;
+    DepthOfField& operator=(const DepthOfField&) = delete;
+
+    void PrepareResources(IRenderDevice* pDevice, IDeviceContext* pDeviceContext, PostFXContext* pPostFXContext, FEATURE_FLAGS FeatureFlags)
+    {
+        (void)pDeviceContext;
+        DFX_DEV_CHECK_ERR(pDevice != nullptr, "pDevice must not be null");
+        DFX_DEV_CHECK_ERR(pPostFXContext != nullptr, "pPostFXContext must not be null");
+        if (pPostFXContext) detail::Check(dfx_dof_prepare(m_Fx, pPostFXContext->GetHandle(), static_cast<uint32_t>(FeatureFlags)), "DepthOfField::PrepareResources");
+    }
+    void Execute(const RenderAttributes& RenderAttribs)
+    {
+        DFX_DEV_CHECK_ERR(RenderAttribs.pDevice != nullptr, "RenderAttribs.pDevice must not be null");
+        DFX_DEV_CHECK_ERR(RenderAttribs.pDeviceContext != nullptr, "RenderAttribs.pDeviceContext must not be null");
+        DFX_DEV_CHECK_ERR(RenderAttribs.pPostFXContext != nullptr, "RenderAttribs.pPostFXContext must not be null");
+        DFX_DEV_CHECK_ERR(RenderAttribs.pColorBufferSRV != nullptr, "RenderAttribs.pColorBufferSRV must not be null");
+        DFX_DEV_CHECK_ERR(RenderAttribs.pDepthBufferSRV != nullptr, "RenderAttribs.pDepthBufferSRV must not be null");
+        DFX_DEV_CHECK_ERR(RenderAttribs.pDOFAttribs != nullptr, "RenderAttribs.pDOFAttribs must not be null");
+        dfx_dof_render_attribs a{};
+        a.stream  = detail::StreamOf(RenderAttribs.pDeviceContext);
+        a.postfx  = RenderAttribs.pPostFXContext ? RenderAttribs.pPostFXContext->GetHandle() : nullptr;
+        a.color   = RenderAttribs.pColorBufferSRV ? RenderAttribs.pColorBufferSRV->GetPlane() : nullptr;
+        a.depth   = RenderAttribs.pDepthBufferSRV ? RenderAttribs.pDepthBufferSRV->GetPlane() : nullptr;
+        a.attribs = RenderAttribs.pDOFAttribs;
+        detail::Check(dfx_dof_execute(m_Fx, &a), "DepthOfField::Execute");
+    }
+    static bool UpdateUI(HLSL::DepthOfFieldAttribs&, FEATURE_FLAGS&) { return false; }
+
+    ITextureView* GetDepthOfFieldTextureSRV() const
+    {
+        dfx_plane p{};
+        return dfx_dof_get_plane(m_Fx, DFX_DOF_PLANE_OUTPUT, &p) == DFX_OK ? m_Out.Update(p) : nullptr;
+    }
+    void     SetAlphaInterpolation(float Alpha) { dfx_dof_set_alpha_interpolation(m_Fx, Alpha); }
+    dfx_dof* GetHandle() const { return m_Fx; }
+
+private:
+    dfx_dof*                  m_Fx = nullptr;
+    mutable detail::PlaneView m_Out;
+};
+DEFINE_FLAG_ENUM_OPERATORS(DepthOfField::FEATURE_FLAGS)
+
+// =====================================================================================================================
 class TemporalAntiAliasing
 {
 public:

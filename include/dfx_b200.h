@@ -178,6 +178,20 @@ typedef struct dfx_taa_attribs
     float   Padding0;
 } dfx_taa_attribs;
 
+/* == HLSL::DepthOfFieldAttribs, Shaders/PostProcess/DepthOfField/public/DepthOfFieldStructures.fxh:31-56 (32 bytes) */
+typedef struct dfx_dof_attribs
+{
+    float   MaxCircleOfConfusion;    /* 0.01   : largest CoC in texture coordinates                    */
+    float   TemporalStabilityFactor; /* 0.9375                                                         */
+    int32_t BokehKernelRingCount;    /* 5      : rings of the Octaweb kernel (2..5)                    */
+    int32_t BokehKernelRingDensity;  /* 7      : samples per ring step (2..7)                          */
+    float   AlphaInterpolation;      /* 1.0                                                            */
+    float   Padding0, Padding1, Padding2;
+} dfx_dof_attribs;
+#define DFX_DOF_FEATURE_FLAG_NONE                      0u
+#define DFX_DOF_FEATURE_FLAG_ENABLE_TEMPORAL_SMOOTHING (1u << 0) /* D2 (DepthOfField.hpp:65) */
+#define DFX_DOF_FEATURE_FLAG_ENABLE_KARIS_INVERSE      (1u << 1) /* HDR-weighted gather in D8 (:67) */
+
 /* == HLSL::ToneMappingAttribs (+AgXAttribs), …/ToneMappingStructures.fxh:24-52 (48 bytes) */
 typedef struct dfx_tonemap_attribs
 {
@@ -420,6 +434,38 @@ DFX_API dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_
 DFX_API dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, const dfx_plane* ssr, const dfx_plane* ao,
                                     float ssr_scale, float ssao_scale, const dfx_plane* out, dfx_rows rows);
 
+/* DepthOfField (PostProcess/DepthOfField/src/DepthOfField.cpp:292-331; Shaders/PostProcess/DepthOfField/private/DOF_*.fx), the
+ * eleven passes in execution order. `rows` is always a row range of the OUTPUT plane of the call. Sizes: CoC planes
+ * W x H; dilation level k (W >> k) x (H >> k), k = 0..3; prefiltered / bokeh planes (W/2) x (H/2), alpha = CoC of the layer.
+ *   D1  coc            signed circle of confusion in [-1, 1] from depth and the lens fields of the camera (…CircleOfConfusion.fx:24-39)
+ *   D2  temporal_coc   history reprojected by the closest motion, clamped to mean +- 2.5 sigma (…TemporalCircleOfConfusion.fx:54-92)
+ *   D3  separated_coc  near field |CoC| (CoC < 0) -> dilation level 0 (…SeparatedCircleOfConfusion.fx:5-11)
+ *   D4  dilation       2x2 (+ odd row / column) maximum, called for levels 1..3 (…DilationCircleOfConfusion.fx:16-52)
+ *   D5/6 blur_coc      13-tap Gaussian (radius 6, sigma 5), horizontal into an intermediate plane, vertical back (…BlurredCoC.fx:8-28)
+ *   D7  prefilter      SDR-weighted 2x2 mean -> foreground (alpha: blurred dilation, linear) and background (alpha: max far CoC)
+ *   D8  bokeh, first   gather over the Octaweb kernel (rings, density from attribs), optional HDR ("Karis inverse") weights
+ *   D9  bokeh, second  flood fill with the small 3 x 5 kernel (component-wise maximum)
+ *   D10 postfilter     2x2 tent
+ *   D11 combine        far layer, then near layer over the full-resolution colour by smoothstep(0.1, 1, alpha)            */
+DFX_API dfx_status dfx_pass_dof_coc(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_dof_attribs* attribs,
+                                    const dfx_plane* depth, const dfx_plane* out_coc, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_temporal_coc(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_dof_attribs* attribs,
+                                             const dfx_plane* curr_coc, const dfx_plane* prev_coc, const dfx_plane* closest_motion,
+                                             const dfx_plane* out_coc, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_separated_coc(void* stream, const dfx_plane* coc, const dfx_plane* out, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_dilation(void* stream, const dfx_plane* last, const dfx_plane* out, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_blur_coc(void* stream, const dfx_plane* coc, int32_t vertical, const dfx_plane* out, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_prefilter(void* stream, const dfx_plane* color, const dfx_plane* coc, const dfx_plane* dilation,
+                                          const dfx_plane* out_fg, const dfx_plane* out_bg, dfx_rows rows);
+/* radiance (the full-resolution colour) is read only with DFX_DOF_FEATURE_FLAG_ENABLE_KARIS_INVERSE in `flags`; may be NULL otherwise */
+DFX_API dfx_status dfx_pass_dof_bokeh(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_dof_attribs* attribs, uint32_t flags,
+                                      int32_t second_pass, const dfx_plane* fg, const dfx_plane* bg, const dfx_plane* radiance,
+                                      const dfx_plane* out_fg, const dfx_plane* out_bg, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_postfilter(void* stream, const dfx_plane* fg, const dfx_plane* bg, const dfx_plane* out_fg,
+                                           const dfx_plane* out_bg, dfx_rows rows);
+DFX_API dfx_status dfx_pass_dof_combine(void* stream, const dfx_dof_attribs* attribs, const dfx_plane* color, const dfx_plane* dof_near,
+                                        const dfx_plane* dof_far, const dfx_plane* out, dfx_rows rows);
+
 /* Compose step, full form (Hydrogent/shaders/HnPostProcess.psh:145-185; host HnPostProcessTask.cpp:834-869). With
  * Opacity = color.a:
  *   rgb += (GetSpecularIBL_GGX(surface, view, ssr.rgb) - specular_ibl.rgb) * ssr.a * ssr_scale * Opacity
@@ -595,6 +641,32 @@ DFX_API dfx_status dfx_bloom_get_plane(const dfx_bloom* fx, int32_t id, dfx_plan
 /* Bloom + final ToneMap(+sRGB) with the last two kernels fused; writes `ldr_out`, does not update the bloom output plane. */
 DFX_API dfx_status dfx_bloom_execute_tonemapped(dfx_bloom* fx, const dfx_bloom_render_attribs* attribs, const dfx_tonemap_attribs* tonemap,
                                                 float ave_log_lum, int32_t convert_to_srgb, const dfx_plane* ldr_out);
+
+/* ---- DepthOfField (PostProcess/DepthOfField/interface/DepthOfField.hpp:59-125) ---- */
+typedef struct dfx_dof dfx_dof;
+typedef struct dfx_dof_render_attribs
+{
+    void*                  stream;
+    dfx_postfx*            postfx;  /* camera (lens fields included), frame index, closest motion */
+    const dfx_plane*       color;   /* pColorBufferSRV RGBA32F */
+    const dfx_plane*       depth;   /* pDepthBufferSRV R32F    */
+    const dfx_dof_attribs* attribs; /* pDOFAttribs             */
+} dfx_dof_render_attribs;
+typedef enum dfx_dof_plane_id
+{
+    DFX_DOF_PLANE_OUTPUT        = 0,  /* == GetDepthOfFieldTextureSRV(): combined colour, alpha of the input kept */
+    DFX_DOF_PLANE_COC           = 1,  /* D1                                                   */
+    DFX_DOF_PLANE_COC_TEMPORAL  = 2,  /* D2, current frame's slot (temporal smoothing only)   */
+    DFX_DOF_PLANE_DILATION_MIP0 = 10, /* +k : dilation level k (0..3); level 3 is blurred     */
+    DFX_DOF_PLANE_PREFILTERED0  = 20, /* +i : foreground (0) / background (1) after D9        */
+    DFX_DOF_PLANE_BOKEH0        = 22  /* +i : foreground (0) / background (1) after D10       */
+} dfx_dof_plane_id;
+DFX_API dfx_status dfx_dof_create(dfx_dof** out);
+DFX_API void       dfx_dof_destroy(dfx_dof* fx);
+DFX_API dfx_status dfx_dof_prepare(dfx_dof* fx, dfx_postfx* postfx, uint32_t feature_flags);
+DFX_API dfx_status dfx_dof_set_alpha_interpolation(dfx_dof* fx, float alpha);
+DFX_API dfx_status dfx_dof_execute(dfx_dof* fx, const dfx_dof_render_attribs* attribs);
+DFX_API dfx_status dfx_dof_get_plane(const dfx_dof* fx, int32_t id, dfx_plane* out);
 
 /* ---- TemporalAntiAliasing (…/TemporalAntiAliasing.hpp:62-156) ---- */
 typedef struct dfx_taa_render_attribs

@@ -3,6 +3,7 @@
 // same plane set and ordering as the reference host code; storage is fp32 (north-star layout).
 #pragma once
 #include "oracle_common.h"
+#include <vector>
 
 namespace orc
 {
@@ -92,6 +93,21 @@ void compose(const TexF4& color, const TexF4* ssr, const TexF* ao, float ssr_sca
 void brdf_lut(int size, uint num_samples, TexF2& lut, int threads);
 void compose_ibl(const Camera& cam, const TexF4& color, const TexF4* ssr, const TexF* ao, const TexF4& specular_ibl, const TexF4& normal,
                  const TexF4& base_color, const TexF4& material, const TexF2& lut, float ssr_scale, float ssao_scale, TexF4& out, int threads);
+
+// ---------------- DepthOfField (oracle_dof.cpp; DepthOfField.cpp:292-331 gives the order) ----------------
+std::vector<float2> dof_kernel_points(int ring_count, int ring_density);  // DepthOfField.cpp:49-73
+std::vector<float>  dof_gauss_kernel(int radius, float sigma);            // DepthOfField.cpp:75-91
+void dof_circle_of_confusion(const Camera& cam, const dfx_dof_attribs& a, const TexF& depth, TexF& coc, int threads);                       // D1
+void dof_temporal_coc(const Camera& cam, const dfx_dof_attribs& a, const TexF& curr, const TexF& prev, const TexF2& closest_motion, TexF& out, int threads); // D2
+void dof_separated_coc(const TexF& coc, TexF& out, int threads);                                                                            // D3
+void dof_dilation_level(const TexF& last, TexF& out, int threads);                                                                          // D4 (x3)
+void dof_blur_coc(const TexF& coc, bool vertical, TexF& out, int threads);                                                                  // D5, D6
+void dof_prefilter(const TexF4& color, const TexF& coc, const TexF& dilation, TexF4& out_fg, TexF4& out_bg, int threads);                   // D7
+void dof_bokeh_first(const Camera& cam, const dfx_dof_attribs& a, uint flags, const TexF4& fg, const TexF4& bg, const TexF4& radiance, TexF4& out_fg,
+                     TexF4& out_bg, int threads);                                                                                           // D8
+void dof_bokeh_second(const Camera& cam, const dfx_dof_attribs& a, const TexF4& fg, const TexF4& bg, TexF4& out_fg, TexF4& out_bg, int threads); // D9
+void dof_postfilter(const TexF4& fg, const TexF4& bg, TexF4& out_fg, TexF4& out_bg, int threads);                                           // D10
+void dof_combine(const dfx_dof_attribs& a, const TexF4& color, const TexF4& dof_near, const TexF4& dof_far, TexF4& out, int threads);       // D11
 
 // ---------------- ToneMapping ----------------
 float3 tone_map(float3 color, const dfx_tonemap_attribs& a, float ave_log_lum); // ToneMapping.fxh:87-226

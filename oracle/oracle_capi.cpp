@@ -24,6 +24,8 @@ struct Ctx
 
     std::vector<uint8_t> tables;
     Camera               curr, prev;
+    dfx_dof_attribs      dof{0.01f, 0.9375f, 5, 7, 1.0f, 0.0f, 0.0f, 0.0f};
+    uint                 dof_flags = 0; // DFX_DOF_FEATURE_FLAG_*
     dfx_ssao_attribs     ssao{};
     uint                 ssao_flags = 0; // DFX_SSAO_FEATURE_FLAG_*
     dfx_ssr_attribs      ssr{};
@@ -105,6 +107,28 @@ int run_pass(Ctx& c, const std::string& p)
     else if (p == "ssr_bilateral")
         ssr_bilateral(c.curr, c.ssr, c.u8["ssr_mask"], c.f1["depth"], c.f4["normal"], c.f1["ssr_roughness"], c.f4[slot("ssr_radhist", cur)],
                       c.f1[slot("ssr_varhist", cur)], c.f4["ssr_out"], T);
+    // DepthOfField, D1-D11 in the order of DepthOfField::Execute (DepthOfField.cpp:292-331). "dof_in" = the colour it blurs.
+    else if (p == "dof")
+    {
+        const bool  temporal = (c.dof_flags & 1u) != 0;
+        dof_circle_of_confusion(c.curr, c.dof, c.f1["depth"], c.f1["dof_coc"], T);
+        if (temporal)
+        {
+            TexF& prevc = c.f1[slot("dof_coc_temporal", prv)];
+            if (prevc.w != c.f1["dof_coc"].w || prevc.h != c.f1["dof_coc"].h) prevc.resize(c.f1["dof_coc"].w, c.f1["dof_coc"].h, 0.0f); // cleared to 0 at creation (:187-189)
+            dof_temporal_coc(c.curr, c.dof, c.f1["dof_coc"], prevc, c.f2["closest_motion"], c.f1[slot("dof_coc_temporal", cur)], T);
+        }
+        const TexF& coc = temporal ? c.f1[slot("dof_coc_temporal", cur)] : c.f1["dof_coc"];
+        dof_separated_coc(coc, c.f1["dof_dilation0"], T);
+        for (int i = 0; i < 3; ++i) dof_dilation_level(c.f1["dof_dilation" + std::to_string(i)], c.f1["dof_dilation" + std::to_string(i + 1)], T);
+        dof_blur_coc(c.f1["dof_dilation3"], false, c.f1["dof_dilation_tmp"], T);
+        dof_blur_coc(c.f1["dof_dilation_tmp"], true, c.f1["dof_dilation3"], T);
+        dof_prefilter(c.f4["dof_in"], coc, c.f1["dof_dilation3"], c.f4["dof_pre0"], c.f4["dof_pre1"], T);
+        dof_bokeh_first(c.curr, c.dof, c.dof_flags, c.f4["dof_pre0"], c.f4["dof_pre1"], c.f4["dof_in"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], T);
+        dof_bokeh_second(c.curr, c.dof, c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], c.f4["dof_pre0"], c.f4["dof_pre1"], T);
+        dof_postfilter(c.f4["dof_pre0"], c.f4["dof_pre1"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], T);
+        dof_combine(c.dof, c.f4["dof_in"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], c.f4["dof_out"], T);
+    }
     else if (p == "compose_ibl")
         compose_ibl(c.curr, c.f4["color"], &c.f4["ssr_out"], &c.f1["ssao_out"], c.f4["specular_ibl"], c.f4["normal"], c.f4["base_color"], c.f4["material"],
                     c.f2["brdf_lut"], c.ssr_scale, c.ssao_scale, c.f4["composed"], T);
@@ -278,6 +302,11 @@ ORC_API void orc_set_ssr_attribs(void* h, const dfx_ssr_attribs* a, uint32_t fla
     static_cast<Ctx*>(h)->ssr       = *a;
     static_cast<Ctx*>(h)->ssr_flags = flags;
 }
+ORC_API void orc_set_dof_attribs(void* h, const dfx_dof_attribs* a, uint32_t flags)
+{
+    static_cast<Ctx*>(h)->dof       = *a;
+    static_cast<Ctx*>(h)->dof_flags = flags;
+}
 ORC_API void orc_set_bloom_attribs(void* h, const dfx_bloom_attribs* a) { static_cast<Ctx*>(h)->bloom = *a; }
 ORC_API void orc_set_taa_attribs(void* h, const dfx_taa_attribs* a, uint32_t flags)
 {
@@ -346,9 +375,15 @@ ORC_API int orc_frame(void* h, uint32_t stages)
         c.taa      = user;
         c.taa_last = c.frame_index;
     }
+    if (stages & 128u) // DepthOfField sits between TAA and Bloom (HnPostProcessTask.cpp:899-909)
+    {
+        c.f4["dof_in"] = (stages & 16u) ? c.f4[slot("taa_accum", c.frame_index & 1u)] : ((stages & 8u) ? c.f4["composed"] : c.f4["color"]);
+        run("dof");
+    }
     if (stages & 32u)
     {
-        c.f4["bloom_in"] = (stages & 16u) ? c.f4[slot("taa_accum", c.frame_index & 1u)] : ((stages & 8u) ? c.f4["composed"] : c.f4["color"]);
+        c.f4["bloom_in"] = (stages & 128u) ? c.f4["dof_out"]
+                                           : ((stages & 16u) ? c.f4[slot("taa_accum", c.frame_index & 1u)] : ((stages & 8u) ? c.f4["composed"] : c.f4["color"]));
         run("bloom");
     }
     if (stages & 64u)

@@ -31,6 +31,7 @@ struct Camera
     float4   f4ViewportSize;
     uint     uiFrameIndex = 0;
     float2   f2Jitter;
+    float    fFocusDistance = 10.0f, fFStop = 5.6f, fFocalLength = 50.0f, fSensorWidth = 36.0f; // lens (BasicStructures.fxh:112-121), used by DepthOfField
     float4x4 mView, mProj, mViewProj, mViewInv, mProjInv, mViewProjInv;
 };
 
@@ -47,6 +48,7 @@ inline Camera to_camera(const dfx_camera_attribs& c)
     r.f4ViewportSize = {c.f4ViewportSize[0], c.f4ViewportSize[1], c.f4ViewportSize[2], c.f4ViewportSize[3]};
     r.uiFrameIndex   = c.uiFrameIndex;
     r.f2Jitter       = {c.f2Jitter[0], c.f2Jitter[1]};
+    r.fFocusDistance = c.fFocusDistance, r.fFStop = c.fFStop, r.fFocalLength = c.fFocalLength, r.fSensorWidth = c.fSensorWidth;
     r.mView          = to_mat(c.mView);
     r.mProj          = to_mat(c.mProj);
     r.mViewProj      = to_mat(c.mViewProj);

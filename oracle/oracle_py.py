@@ -16,6 +16,7 @@ TABLES = os.path.join(os.path.dirname(_HERE), "diligentfx_b200", "data", "blue_n
 
 STAGE_POSTFX, STAGE_SSR, STAGE_SSAO, STAGE_COMPOSE, STAGE_TAA, STAGE_BLOOM, STAGE_TONEMAP = 1, 2, 4, 8, 16, 32, 64
 STAGE_ALL = 127
+STAGE_DOF = 128   # DepthOfField between TAA and Bloom (not part of STAGE_ALL: the benchmarked chain of BASELINE.json has no DoF)
 
 
 def build(force: bool = False) -> str:
@@ -106,6 +107,9 @@ class Oracle:
 
     def set_ssr(self, a, flags: int = 0):
         self.L.orc_set_ssr_attribs(self.h_, C.byref(a), C.c_uint32(flags))
+
+    def set_dof(self, a, flags: int = 0):
+        self.L.orc_set_dof_attribs(self.h_, C.byref(a), C.c_uint32(flags))
 
     def set_bloom(self, a):
         self.L.orc_set_bloom_attribs(self.h_, C.byref(a))
