@@ -96,8 +96,11 @@ extern "C" void dfx_postfx_destroy(dfx_postfx* c) { delete c; }
 extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* desc, uint32_t flags)
 {
     DFX_REQUIRE(c && desc, "null argument");
-    if (flags & ~(DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH | DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING))
-        return set_error(DFX_ERR_UNSUPPORTED, "PostFX feature flags 0x%x are not implemented (fp32 depth only)", flags);
+    // HALF_PRECISION_DEPTH only selects R16_UNORM for the reprojected / previous depth textures (PostFXContext.cpp:259, :270); this
+    // library keeps every plane in fp32 and models none of the reference's narrow formats, so the flag is accepted
+    // and changes nothing here.
+    if (flags & ~(DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH | DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING | DFX_POSTFX_FEATURE_FLAG_HALF_PRECISION_DEPTH))
+        return set_error(DFX_ERR_UNSUPPORTED, "unknown PostFX feature flags 0x%x", flags);
     DFX_REQUIRE(!(flags & DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING) || (desc->OutputWidth > 0 && desc->OutputHeight > 0),
                 "temporal upscaling needs FrameDesc.OutputWidth / OutputHeight");
     DFX_REQUIRE(desc->Width > 0 && desc->Height > 0, "empty frame");
@@ -204,8 +207,8 @@ static int mip_levels_count(int w, int h)
 extern "C" dfx_status dfx_ssao_prepare(dfx_ssao* fx, dfx_postfx* postfx, uint32_t flags)
 {
     DFX_REQUIRE(fx && postfx, "null argument");
-    if (flags & ~DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION)
-        return set_error(DFX_ERR_UNSUPPORTED, "SSAO feature flags 0x%x are not implemented (fp32 depth only)", flags);
+    if (flags & ~(DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION | DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH))
+        return set_error(DFX_ERR_UNSUPPORTED, "unknown SSAO feature flags 0x%x", flags);
     if (!postfx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "PostFXContext is not prepared");
     fx->curr_frame = postfx->desc.Index;
     if (fx->w == postfx->w && fx->h == postfx->h && fx->prepared && fx->flags == flags) return DFX_OK;
@@ -272,6 +275,9 @@ extern "C" dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attri
     dfx_pyramid pre{}, cocc{}, cdep{};
     pre.levels = cocc.levels = cdep.levels = fx->levels;
     const bool half = (fx->flags & DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION) != 0;
+    // HALF_PRECISION_DEPTH: the pyramids stay fp32 (no narrow format is modelled); what the shaders see of the flag is the larger
+    // self-occlusion offset of the AO pass, keyed on the plane flag (SSAO_ComputeAmbientOcclusion.fx:145-150)
+    if (fx->flags & DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH) depth.flags |= DFX_PLANE_FLAG_HALF_PRECISION_DEPTH;
     pre.level[0] = depth, cocc.level[0] = fx->conv_occ[0].p, cdep.level[0] = depth;
     for (int i = 1; i < fx->levels; ++i) pre.level[i] = fx->pre[i].p, cocc.level[i] = fx->conv_occ[i].p, cdep.level[i] = fx->conv_depth[i].p;
 

@@ -109,7 +109,7 @@ struct __align__(16) AoLevel
 
 template <int ALGO>
 __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
-                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half)
+                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half, float self_offset)
 {
     __shared__ SsaoCam S;
     __shared__ AoLevel lvl[DFX_MAX_MIPS];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
     };
     const float3 nvs = mul_dir(xyz(half ? sample_point_clamp(normal, u, v) : __ldg(&normal.at(x, y))), S.view); // LoadNormalWS: point clamp
     float3       pvs = to_view(u, v, depth);
-    pvs              = pvs + nvs * (0.00001f * pvs.z);
+    pvs              = pvs + nvs * (self_offset * pvs.z); // 0.00001, or 0.005 with SSAO_OPTION_HALF_PRECISION_DEPTH (:145-150)
     const float3 view = -fnormalize(pvs);
     const float2 xi   = __ldg(&noise.at(x & 127, y & 127));
     const float  cxk = (u - 0.5f) * kx, cyk = (v - 0.5f) * ky;
@@ -615,7 +615,8 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     PyrView P;
     DFX_REQUIRE(make_pyr(prefiltered_depth, P, 1), "bad prefiltered-depth pyramid");
-    const int rev = reversed_depth(&prefiltered_depth->level[0]); // level 0 is the depth buffer
+    const int   rev = reversed_depth(&prefiltered_depth->level[0]); // level 0 is the depth buffer
+    const float self_offset = (prefiltered_depth->level[0].flags & DFX_PLANE_FLAG_HALF_PRECISION_DEPTH) ? 0.005f : 0.00001f;
     DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float2, bn, blue_noise_zw, DFX_FORMAT_RG32F);
     DFX_VIEW(float, out, occlusion, DFX_FORMAT_R32F);
@@ -629,9 +630,9 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
     switch (attribs->Algorithm)
     {
-        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half); break;
-        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half); break;
-        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half); break;
+        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset); break;
+        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset); break;
+        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset); break;
         default: return set_error(DFX_ERR_INVALID_ARG, "unknown SSAO algorithm %u", attribs->Algorithm);
     }
     DFX_LAUNCHED("ssao_ao_kernel");

@@ -13,7 +13,7 @@ public:
     {
         FEATURE_FLAG_NONE                 = 0u,
         FEATURE_FLAG_REVERSED_DEPTH       = 1u << 0u, // near = 1, far = 0
-        FEATURE_FLAG_HALF_PRECISION_DEPTH = 1u << 1u, // not implemented
+        FEATURE_FLAG_HALF_PRECISION_DEPTH = 1u << 1u, // accepted: a storage-format choice, planes stay fp32 here
         FEATURE_FLAG_TEMPORAL_UPSCALING   = 1u << 2u, // Bloom runs at the frame's output resolution
     };
 

@@ -21,7 +21,7 @@ public:
     enum FEATURE_FLAGS : Uint32
     {
         FEATURE_FLAG_NONE                 = 0u,
-        FEATURE_FLAG_HALF_PRECISION_DEPTH = 1u << 0u, // not implemented
+        FEATURE_FLAG_HALF_PRECISION_DEPTH = 1u << 0u, // AO self-occlusion offset 0.005; planes stay fp32 here
         FEATURE_FLAG_HALF_RESOLUTION      = 1u << 1u  // AO at half resolution + bilateral upsampling
     };
     enum ALGORITHM_TYPE : Uint32

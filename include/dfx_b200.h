@@ -41,7 +41,7 @@ typedef enum dfx_status
     DFX_ERR_INVALID_ARG  = 1, /* null pointer, bad format, mismatched size (reference: DEV_CHECK_ERR)        */
     DFX_ERR_CUDA         = 2, /* a CUDA runtime call or launch failed; see dfx_last_error()                   */
     DFX_ERR_NOT_PREPARED = 3, /* execute before prepare (reference: TemporalAntiAliasing.cpp:178-183)         */
-    DFX_ERR_UNSUPPORTED  = 4  /* feature flag not implemented in this build (half-res / reversed depth …)   */
+    DFX_ERR_UNSUPPORTED  = 4  /* unknown feature-flag bits, or a combination this build has no kernel for   */
 } dfx_status;
 
 DFX_API const char* dfx_last_error(void);           /* thread-local message of the last non-OK status      */
@@ -81,6 +81,11 @@ typedef struct dfx_plane
  * as the maximum, the far plane as 0 and the background test as depth < 1e-6. The effect-level objects set it themselves
  * from the PostFX feature flag.                                                                                  */
 #define DFX_PLANE_FLAG_REVERSED_DEPTH 1
+/* A depth plane (level 0 of the SSAO prefiltered-depth pyramid) that the reference would keep in R16_UNORM
+ * (ScreenSpaceAmbientOcclusion::FEATURE_FLAG_HALF_PRECISION_DEPTH, …cpp:96-97). The plane stays fp32 here — this library
+ * models none of the reference's narrow storage formats — but the AO pass uses the larger self-occlusion offset the
+ * reference compiles in for that mode (0.005 instead of 0.00001, SSAO_ComputeAmbientOcclusion.fx:145-150).          */
+#define DFX_PLANE_FLAG_HALF_PRECISION_DEPTH 2
 
 #define DFX_MAX_MIPS 8
 /* A mip chain of planes (level i is max(w>>i,1) x max(h>>i,1)). Stands in for a mip-mapped ITexture. */
@@ -237,10 +242,10 @@ typedef struct dfx_frame_desc
 /* feature flags: numeric values of the reference enums */
 #define DFX_POSTFX_FEATURE_FLAG_NONE                 0u
 #define DFX_POSTFX_FEATURE_FLAG_REVERSED_DEPTH       (1u << 0) /* depth: near = 1, far = 0 (see DFX_PLANE_FLAG_REVERSED_DEPTH) */
-#define DFX_POSTFX_FEATURE_FLAG_HALF_PRECISION_DEPTH (1u << 1) /* unsupported */
+#define DFX_POSTFX_FEATURE_FLAG_HALF_PRECISION_DEPTH (1u << 1) /* accepted; selects a storage format only, planes stay fp32 */
 #define DFX_POSTFX_FEATURE_FLAG_TEMPORAL_UPSCALING   (1u << 2) /* Bloom runs at FrameDesc.OutputWidth x OutputHeight (Bloom.cpp:84-85) */
 #define DFX_SSAO_FEATURE_FLAG_NONE                   0u
-#define DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH   (1u << 0) /* unsupported */
+#define DFX_SSAO_FEATURE_FLAG_HALF_PRECISION_DEPTH   (1u << 0) /* AO self-occlusion offset 0.005; planes stay fp32 */
 #define DFX_SSAO_FEATURE_FLAG_HALF_RESOLUTION        (1u << 1) /* A0 + A1-A3 at width/2 x height/2 + A4 */
 #define DFX_SSR_FEATURE_FLAG_NONE                    0u
 #define DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME          (1u << 0)

@@ -26,7 +26,8 @@ void ssao_prefilter_depth(const Camera& cam, const dfx_ssao_attribs& a, const Te
 // SSAO_ComputeAmbientOcclusion.fx:132-231 ; target cleared to 1.0 first (…cpp:982-985)
 // half_res (FEATURE_FLAG_HALF_RESOLUTION): the pyramid, hence the target, is W/2 x H/2 and GetInvViewportSize() doubles (:68-75)
 void ssao_ambient_occlusion(const Camera& cam, const dfx_ssao_attribs& a, const MipTex<float>& prefiltered,
-                            const TexF4& normal, const TexF2& blue_noise_zw, TexF& out, int threads, bool half_res = false);
+                            const TexF4& normal, const TexF2& blue_noise_zw, TexF& out, int threads, bool half_res = false,
+                            bool half_precision_depth = false); // the latter: self-occlusion offset 0.005 (:145-150); storage stays fp32
 // A0 SSAO_ComputeDownsampledDepth.fx:8-29 : W/2 x H/2 checkerboard of the 2x2 min / max depth
 void ssao_downsample_depth(const TexF& depth, TexF& out, int threads);
 // A4 SSAO_ComputeBilateralUpsampling.fx:62-139 : 3x3 joint-bilateral upsampling of the half-res occlusion to W x H

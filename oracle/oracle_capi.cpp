@@ -76,7 +76,7 @@ int run_pass(Ctx& c, const std::string& p)
     else if (p == "ssao_downsample") ssao_downsample_depth(c.f1["depth"], c.f1["ssao_checker"], T);
     else if (p == "ssao_prefilter") ssao_prefilter_depth(c.curr, c.ssao, c.f1[(c.ssao_flags & 2u) ? "ssao_checker" : "depth"], c.pyr["ssao_pre"], T);
     else if (p == "ssao_ao")
-        ssao_ambient_occlusion(c.curr, c.ssao, c.pyr["ssao_pre"], c.f4["normal"], c.f2["bn_zw"], c.f1["ssao_occ"], T, (c.ssao_flags & 2u) != 0);
+        ssao_ambient_occlusion(c.curr, c.ssao, c.pyr["ssao_pre"], c.f4["normal"], c.f2["bn_zw"], c.f1["ssao_occ"], T, (c.ssao_flags & 2u) != 0, (c.ssao_flags & 1u) != 0);
     else if (p == "ssao_upsample") ssao_bilateral_upsampling(c.curr, c.f1["depth"], c.f1["ssao_occ"], c.f1["ssao_occ_up"], T);
     else if (p == "ssao_temporal")
         ssao_temporal(c.curr, c.prev, c.ssao, c.f1[(c.ssao_flags & 2u) ? "ssao_occ_up" : "ssao_occ"], c.f1[slot("ssao_hist", prv)], c.f1[slot("ssao_histlen", prv)], c.f1["reproj_depth"],

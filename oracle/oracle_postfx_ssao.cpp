@@ -330,7 +330,7 @@ void ssao_bilateral_upsampling(const Camera& cam, const TexF& depth, const TexF&
 }
 
 void ssao_ambient_occlusion(const Camera& cam, const dfx_ssao_attribs& A, const MipTex<float>& pre, const TexF4& normal,
-                            const TexF2& blue_noise_zw, TexF& out, int threads, bool half_res)
+                            const TexF2& blue_noise_zw, TexF& out, int threads, bool half_res, bool half_precision_depth)
 {
     const int W = pre.mip[0].w, H = pre.mip[0].h;
     out.resize(W, H, 1.0f); // ClearRenderTarget 1.0
@@ -353,7 +353,7 @@ void ssao_ambient_occlusion(const Camera& cam, const dfx_ssao_attribs& A, const 
 
                 float3 NormalVS   = mul_dir(sample_point_clamp(normal, ScreenCoordUV).xyz(), cam.mView);
                 float3 PositionVS = ScreenXYDepthToViewSpace(PositionSS, cam.mProj);
-                float  Offset     = 0.00001f;
+                float  Offset     = half_precision_depth ? 0.005f : 0.00001f; // :145-150
                 PositionVS        = PositionVS + NormalVS * Offset * PositionVS.z;
 
                 float3 ViewVS = -normalize(PositionVS);

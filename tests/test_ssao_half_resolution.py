@@ -116,3 +116,35 @@ def test_cuda_half_resolution_chain(built):
     full = chain.run_frame({**seq[-1], "frame": seq[-1]["frame"] + 1}).cpu().numpy()
     assert chain.fetch("ssao", 1).shape == (H, W) and np.isfinite(full).all()
     chain.close()
+
+
+def test_oracle_half_precision_depth_offset(built):
+    """FEATURE_FLAG_HALF_PRECISION_DEPTH: what the shaders see of it is the self-occlusion offset 0.005 instead of 0.00001
+    (SSAO_ComputeAmbientOcclusion.fx:145-150): the centre point is pushed further off the surface, so the raw AO can only
+    get brighter on average; storage stays fp32."""
+    seq = synth.generate_sequence(W, H, 1)
+    outs = []
+    for flags in (0, 1):
+        o = _oracle()
+        o.set_ssao_flags(flags)
+        o.set_inputs(seq[0])
+        o.frame()
+        outs.append(o.get("ssao_occ"))
+    assert not np.array_equal(outs[0], outs[1]) and outs[1].mean() > outs[0].mean()
+
+
+@pytest.mark.gpu
+def test_cuda_half_precision_depth_flag(built):
+    from diligentfx_b200.chain import ChainConfig, PostProcessChain
+    seq = synth.generate_sequence(W, H, FRAMES)
+    o = _oracle()
+    o.set_ssao_flags(1)
+    chain = PostProcessChain(W, H, ChainConfig(ssao_flags=1, postfx_flags=2))  # SSAO + PostFX HALF_PRECISION_DEPTH
+    for fr in seq:
+        o.set_inputs(fr)
+        o.frame()
+        ldr = chain.run_frame(fr).cpu().numpy()
+    assert psnr(chain.fetch("ssao", 1), o.get("ssao_occ")) >= 50.0
+    assert psnr(chain.fetch("ssao", 0), o.get("ssao_out")) >= 50.0
+    assert psnr(np.clip(ldr[..., :3], 0, 1), np.clip(o.get("ldr")[..., :3], 0, 1)) >= 49.0
+    chain.close()
