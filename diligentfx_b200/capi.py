@@ -12,7 +12,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "lib", "libdfx_b200.so")
+LIB_PATH = os.environ.get("DFX_LIB") or os.path.join(_HERE, "lib", "libdfx_b200.so")  # DFX_LIB: another build of the same library (tuning sweeps)
 HEADER_PATH = os.path.join(REPO_ROOT, "include", "dfx_b200.h")
 
 DFX_OK, DFX_ERR_INVALID_ARG, DFX_ERR_CUDA, DFX_ERR_NOT_PREPARED, DFX_ERR_UNSUPPORTED = range(5)

@@ -11,21 +11,22 @@
 #include "../../include/dfx_b200.h"
 
 // Minimum resident CTAs per SM requested from ptxas for the latency-bound gather kernels (register budget = 65536 /
-// (256 * N)); the values are the measured optimum of round 1 (profiles/r1f_occupancy_sweep.md). Overridable with -D.
+// (256 * N)); the values are the measured optimum of round 1 (profiles/r1f_occupancy_sweep.md, re-measured after the
+// instruction diet of the kernels: profiles/r1n_occupancy_variants.txt). Overridable with -D.
 #ifndef DFX_OCC_INTERSECT
-#    define DFX_OCC_INTERSECT 5
+#    define DFX_OCC_INTERSECT 6
 #endif
 #ifndef DFX_OCC_SSR_SPATIAL
-#    define DFX_OCC_SSR_SPATIAL 5
+#    define DFX_OCC_SSR_SPATIAL 6
 #endif
 #ifndef DFX_OCC_SSR_TEMPORAL
 #    define DFX_OCC_SSR_TEMPORAL 6
 #endif
 #ifndef DFX_OCC_AO
-#    define DFX_OCC_AO 4
+#    define DFX_OCC_AO 5
 #endif
 #ifndef DFX_OCC_TAA
-#    define DFX_OCC_TAA 5
+#    define DFX_OCC_TAA 6
 #endif
 
 namespace dfx

@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(c
     const float ad   = fmaxf(a, 1e-3f), ad2 = ad * ad;
     const float visV = NdotV * NdotV * (1.0f - a2) + a2; // under the sqrt of GGXV
 
+    const float sscale = half ? 0.5f : 1.0f, sbias = half ? 0.5f : 0.0f, sbx = half ? float(x) : posx, sby = half ? float(y) : posy;
+    const int   smaxx = (half ? (int)(0.5f * cam.vw) : W) - 1, smaxy = (half ? (int)(0.5f * cam.vh) : H) - 1;
     float4 colorSum = make_float4(0.f, 0.f, 0.f, 0.f);
     float  wsum = 0.0f, variance = 0.0f, mean = 0.0f, nearest = 0.0f;
 #pragma unroll
@@ -432,12 +434,9 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(c
     {
         const float3 P  = kSsrPoisson8[i];
         const float  xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
-        int          sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
-        if (half) // the intersect targets are W/2 x H/2: int2(0.5 * (floor(Position) + Radius * Xi) + 0.5) (:153-157)
-        {
-            sx = min(max((int)(0.5f * (float(x) + radius * xi) + 0.5f), 0), (int)(0.5f * cam.vw) - 1);
-            sy = min(max((int)(0.5f * (float(y) + radius * yi) + 0.5f), 0), (int)(0.5f * cam.vh) - 1);
-        }
+        // full resolution: int2(Position + Radius * Xi); half-size intersect targets: int2(0.5 * (floor(Position) + Radius * Xi) + 0.5)
+        // (:153-157). One expression for both — the scale 1 and the bias 0 of the full-resolution case are exact.
+        const int sx = min(max((int)(sscale * (sbx + radius * xi) + sbias), 0), smaxx), sy = min(max((int)(sscale * (sby + radius * yi) + sbias), 0), smaxy);
         const float  ws = kSsrPoisson8Weight[i]; // exp(-z^2 / (2 * 0.9^2)), a constant per disk sample
         // ComputeWeightRayLength :60-86
         float        weight, raylen;
