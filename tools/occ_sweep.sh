@@ -6,6 +6,6 @@ for n in 3 4 5 6; do
 import json,sys
 r=json.loads(sys.stdin.read())
 p={x['pass']:x['ms'] for x in r['passes']}
-print('occ $n step %.3f ms | intersect %.4f spatial %.4f temporal %.4f ao %.4f taa %.4f' % (r['ms_per_step'], p['ssr_intersect'], p['ssr_spatial'], p['ssr_temporal'], p['ssao_ambient_occlusion'], p['taa']))"
+print('occ $n step %.3f ms | intersect %.4f spatial %.4f temporal %.4f ao %.4f taa %.4f' % (r['ms_per_step'], p['ssr_intersect'], p['ssr_spatial'], p['ssr_temporal'], p['ssao_ambient_occlusion'], p.get('taa', p.get('compose_taa', 0.0))))"
 done
 python -m diligentfx_b200.build --force > /dev/null 2>&1
