@@ -55,6 +55,9 @@ PASS_BYTES_PER_PX = {
     "bloom_composite_tonemap": 36.0,     # fused: colour 16 + up[0] 4 in, LDR 16 out
     "bloom_prefilter": 20.0, "bloom_downsample": 6.67, "bloom_upsample": 12.0, "bloom_composite": 36.0,
     "tonemap": 32.0,
+    # DepthOfField (--dof only): CoC planes 4 B/px, half-size colour planes 16 B per quarter pixel
+    "dof_coc": 8.0, "dof_temporal_coc": 20.0, "dof_separated_coc": 8.0, "dof_dilation": 6.6, "dof_blur_coc": 0.25, "dof_prefilter": 28.0,
+    "dof_bokeh_first": 16.0, "dof_bokeh_second": 16.0, "dof_postfilter": 16.0, "dof_combine": 40.0,
 }
 
 
@@ -177,6 +180,7 @@ def main() -> None:
     ap.add_argument("--ref-height", type=int, default=540)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run every pass on one stream (no async compute)")
+    ap.add_argument("--dof", action="store_true", help="add DepthOfField between TAA and Bloom (NOT the BASELINE.json workload; config.workload says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -221,7 +225,14 @@ def main() -> None:
     packed_keys = [s[0] for s in PACKED_SPECS.values()] + ["depth"]
     h2d_bytes = sum(packed[0][k].numel() * packed[0][k].element_size() for k in packed_keys)
     h2d_bytes_fp32 = sum(t.numel() * 4 for t in host[0].values())
-    chain = PostProcessChain(W, H, ChainConfig(overlap=not args.no_overlap), device=dev)
+    dof = None
+    if args.dof:  # not BASELINE.json's chain: Hydrogent's optional DepthOfField between TAA and Bloom, f/1.4 focused at 6 m
+        dof = capi.DOFAttribs.default()
+        dof.MaxCircleOfConfusion = 0.02
+        for cp in cams:
+            for c in cp:
+                c.fFocusDistance, c.fFStop = 6.0, 1.4
+    chain = PostProcessChain(W, H, ChainConfig(overlap=not args.no_overlap, dof=dof, dof_flags=capi.DOF_FLAG_TEMPORAL_SMOOTHING if dof else 0), device=dev)
     ldr_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     ldr8_hosts = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
     d2h_bytes, d2h_bytes_fp32 = ldr8_hosts[0].numel(), ldr_host.numel() * 4
@@ -338,7 +349,8 @@ def main() -> None:
         rec = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"full PostProcess chain (PostFX prep, SSR, SSAO, compose, TAA bicubic, Bloom {lib.dfx_bloom_mip_count(W // 2, H // 2, C.c_float(0.75))} levels, "
+            "config": {"workload": ("NOT the BASELINE.json workload (--dof): DepthOfField added between TAA and Bloom; " if args.dof else "") +
+                                   f"full PostProcess chain (PostFX prep, SSR, SSAO, compose, TAA bicubic, Bloom {lib.dfx_bloom_mip_count(W // 2, H // 2, C.c_float(0.75))} levels, "
                                    f"ToneMap Uncharted2 + sRGB) on a {W}x{H} synthetic G-buffer + history, consecutive frames, one sequence per GPU",
                        "width": W, "height": H, "parallelism": f"replicas x{world} (independent frame sequences, no data-path collective)",
                        "streams": ("3 per GPU: SSR chain + TAA | SSAO chain | Bloom + ToneMap (overlaps the next frame's front half); per-pass times in `passes` are "
