@@ -108,26 +108,41 @@ int run_pass(Ctx& c, const std::string& p)
         ssr_bilateral(c.curr, c.ssr, c.u8["ssr_mask"], c.f1["depth"], c.f4["normal"], c.f1["ssr_roughness"], c.f4[slot("ssr_radhist", cur)],
                       c.f1[slot("ssr_varhist", cur)], c.f4["ssr_out"], T);
     // DepthOfField, D1-D11 in the order of DepthOfField::Execute (DepthOfField.cpp:292-331). "dof_in" = the colour it blurs.
+    // Each step is also a pass of its own, so that tests can look at one at a time.
     else if (p == "dof")
     {
+        static const char* steps[] = {"dof_coc", "dof_temporal", "dof_separated", "dof_dilation", "dof_blur_x", "dof_blur_y", "dof_prefilter",
+                                      "dof_bokeh_first", "dof_bokeh_second", "dof_postfilter", "dof_combine"};
+        for (const char* st : steps)
+            if (int r = run_pass(c, st)) return r;
+    }
+    else if (p.rfind("dof_", 0) == 0)
+    {
         const bool  temporal = (c.dof_flags & 1u) != 0;
-        dof_circle_of_confusion(c.curr, c.dof, c.f1["depth"], c.f1["dof_coc"], T);
-        if (temporal)
+        const TexF& coc      = temporal ? c.f1[slot("dof_coc_temporal", cur)] : c.f1["dof_coc"];
+        if (p == "dof_coc") dof_circle_of_confusion(c.curr, c.dof, c.f1["depth"], c.f1["dof_coc"], T);
+        else if (p == "dof_temporal")
         {
-            TexF& prevc = c.f1[slot("dof_coc_temporal", prv)];
-            if (prevc.w != c.f1["dof_coc"].w || prevc.h != c.f1["dof_coc"].h) prevc.resize(c.f1["dof_coc"].w, c.f1["dof_coc"].h, 0.0f); // cleared to 0 at creation (:187-189)
-            dof_temporal_coc(c.curr, c.dof, c.f1["dof_coc"], prevc, c.f2["closest_motion"], c.f1[slot("dof_coc_temporal", cur)], T);
+            if (temporal)
+            {
+                TexF& prevc = c.f1[slot("dof_coc_temporal", prv)];
+                if (prevc.w != c.f1["dof_coc"].w || prevc.h != c.f1["dof_coc"].h) prevc.resize(c.f1["dof_coc"].w, c.f1["dof_coc"].h, 0.0f); // cleared to 0 at creation (:187-189)
+                dof_temporal_coc(c.curr, c.dof, c.f1["dof_coc"], prevc, c.f2["closest_motion"], c.f1[slot("dof_coc_temporal", cur)], T);
+            }
         }
-        const TexF& coc = temporal ? c.f1[slot("dof_coc_temporal", cur)] : c.f1["dof_coc"];
-        dof_separated_coc(coc, c.f1["dof_dilation0"], T);
-        for (int i = 0; i < 3; ++i) dof_dilation_level(c.f1["dof_dilation" + std::to_string(i)], c.f1["dof_dilation" + std::to_string(i + 1)], T);
-        dof_blur_coc(c.f1["dof_dilation3"], false, c.f1["dof_dilation_tmp"], T);
-        dof_blur_coc(c.f1["dof_dilation_tmp"], true, c.f1["dof_dilation3"], T);
-        dof_prefilter(c.f4["dof_in"], coc, c.f1["dof_dilation3"], c.f4["dof_pre0"], c.f4["dof_pre1"], T);
-        dof_bokeh_first(c.curr, c.dof, c.dof_flags, c.f4["dof_pre0"], c.f4["dof_pre1"], c.f4["dof_in"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], T);
-        dof_bokeh_second(c.curr, c.dof, c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], c.f4["dof_pre0"], c.f4["dof_pre1"], T);
-        dof_postfilter(c.f4["dof_pre0"], c.f4["dof_pre1"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], T);
-        dof_combine(c.dof, c.f4["dof_in"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], c.f4["dof_out"], T);
+        else if (p == "dof_separated") dof_separated_coc(coc, c.f1["dof_dilation0"], T);
+        else if (p == "dof_dilation")
+            for (int i = 0; i < 3; ++i) dof_dilation_level(c.f1["dof_dilation" + std::to_string(i)], c.f1["dof_dilation" + std::to_string(i + 1)], T);
+        else if (p == "dof_blur_x") dof_blur_coc(c.f1["dof_dilation3"], false, c.f1["dof_dilation_tmp"], T);
+        else if (p == "dof_blur_y") dof_blur_coc(c.f1["dof_dilation_tmp"], true, c.f1["dof_dilation3"], T);
+        else if (p == "dof_prefilter") dof_prefilter(c.f4["dof_in"], coc, c.f1["dof_dilation3"], c.f4["dof_pre0"], c.f4["dof_pre1"], T);
+        else if (p == "dof_bokeh_first")
+            dof_bokeh_first(c.curr, c.dof, c.dof_flags, c.f4["dof_pre0"], c.f4["dof_pre1"], c.f4["dof_in"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], T);
+        else if (p == "dof_bokeh_second") dof_bokeh_second(c.curr, c.dof, c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], c.f4["dof_pre0"], c.f4["dof_pre1"], T);
+        else if (p == "dof_postfilter") dof_postfilter(c.f4["dof_pre0"], c.f4["dof_pre1"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], T);
+        else if (p == "dof_combine") dof_combine(c.dof, c.f4["dof_in"], c.f4["dof_bokeh0"], c.f4["dof_bokeh1"], c.f4["dof_out"], T);
+        else
+            return c.err = "unknown pass " + p, 1;
     }
     else if (p == "compose_ibl")
         compose_ibl(c.curr, c.f4["color"], &c.f4["ssr_out"], &c.f1["ssao_out"], c.f4["specular_ibl"], c.f4["normal"], c.f4["base_color"], c.f4["material"],
@@ -423,6 +438,19 @@ ORC_API void orc_march_stats(unsigned long long* rays, unsigned long long* itera
     *rays       = orc::g_march_rays.load();
     *iterations = orc::g_march_iterations.load();
     if (reset) orc::g_march_rays = 0, orc::g_march_iterations = 0;
+}
+// kernel textures of DepthOfField (DepthOfField.cpp:49-91): points as x,y pairs; returns the count (writes at most max_count entries)
+ORC_API int orc_dof_kernel_points(int ring_count, int ring_density, float* out_xy, int max_count)
+{
+    const std::vector<float2> k = dof_kernel_points(ring_count, ring_density);
+    for (int i = 0; i < int(k.size()) && i < max_count; ++i) out_xy[2 * i] = k[i].x, out_xy[2 * i + 1] = k[i].y;
+    return int(k.size());
+}
+ORC_API int orc_dof_gauss_kernel(int radius, float sigma, float* out, int max_count)
+{
+    const std::vector<float> k = dof_gauss_kernel(radius, sigma);
+    for (int i = 0; i < int(k.size()) && i < max_count; ++i) out[i] = k[i];
+    return int(k.size());
 }
 ORC_API int orc_bloom_mip_count(int w, int hgt, float radius) { return bloom_mip_count(w, hgt, radius); }
 ORC_API float orc_fast_acos(float v) { return orc::oracle_fast_acos(v); }

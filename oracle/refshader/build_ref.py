@@ -87,7 +87,9 @@ def translation_unit(p: dict, idx: dict[str, str]) -> str:
     parts += [f"#define {k} {v}\n" for k, v in p.get("macros", {}).items()]
     parts.append(f"namespace {ns} {{\nusing namespace hlsl;\n")
     parts.append(open(os.path.join(HERE, "core_defs.inc")).read())
-    parts.append(flatten(p["shader"], idx, set()))
+    seen: set[str] = set()
+    for shader in ([p["shader"]] if isinstance(p["shader"], str) else p["shader"]):  # several files: a function library + what its harness needs
+        parts.append(flatten(shader, idx, seen))
     parts.append(open(os.path.join(HERE, "harness", "common.inc")).read())
     parts.append(f"#define REFSH_ENTRY refsh_{p['name']}\n")
     parts.append(open(os.path.join(HERE, "harness", p["harness"])).read())

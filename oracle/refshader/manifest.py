@@ -9,6 +9,9 @@ def _p(name, shader, harness=None, **macros):
     return {"name": name, "shader": shader, "harness": harness or (name.split("__")[0] + ".inc"), "macros": {"SUPPORTED_SHADER_SRV": 1, **macros}}
 
 
+_SSAO = dict(SSAO_OPTION_INVERTED_DEPTH=0, SSAO_OPTION_HALF_RESOLUTION=0, SSAO_OPTION_HALF_PRECISION_DEPTH=0)
+_SSAO_REV = dict(_SSAO, SSAO_OPTION_INVERTED_DEPTH=1)
+_SSAO_HALF = dict(_SSAO, SSAO_OPTION_HALF_RESOLUTION=1)
 _SSR = dict(SSR_OPTION_INVERTED_DEPTH=0, SSR_OPTION_PREVIOUS_FRAME=0, SSR_OPTION_HALF_RESOLUTION=0)
 _SSR_REV = dict(_SSR, SSR_OPTION_INVERTED_DEPTH=1)
 
@@ -35,4 +38,34 @@ PASSES = [
     _p("ssr_temporal__rev", "SSR_ComputeTemporalAccumulation.fx", **_SSR_REV),
     _p("ssr_bilateral", "SSR_ComputeBilateralCleanup.fx", **_SSR),
     _p("ssr_bilateral__rev", "SSR_ComputeBilateralCleanup.fx", **_SSR_REV),
+    # ScreenSpaceAmbientOcclusion (ScreenSpaceAmbientOcclusion.cpp:471-479); SSAO_ALGORITHM 0 GTAO, 1 HBAO, 2 VBAO
+    _p("ssao_downsample", "SSAO_ComputeDownsampledDepth.fx", **_SSAO_HALF),
+    _p("ssao_prefilter", "SSAO_ComputePrefilteredDepthBuffer.fx", **_SSAO),
+    _p("ssao_prefilter__rev", "SSAO_ComputePrefilteredDepthBuffer.fx", **_SSAO_REV),
+    _p("ssao_ao", "SSAO_ComputeAmbientOcclusion.fx", SSAO_ALGORITHM=0, **_SSAO),
+    _p("ssao_ao__hbao", "SSAO_ComputeAmbientOcclusion.fx", SSAO_ALGORITHM=1, **_SSAO),
+    _p("ssao_ao__vbao", "SSAO_ComputeAmbientOcclusion.fx", SSAO_ALGORITHM=2, **_SSAO),
+    _p("ssao_ao__rev", "SSAO_ComputeAmbientOcclusion.fx", SSAO_ALGORITHM=0, **_SSAO_REV),
+    _p("ssao_ao__half", "SSAO_ComputeAmbientOcclusion.fx", SSAO_ALGORITHM=0, **_SSAO_HALF),
+    _p("ssao_ao__halfprec", "SSAO_ComputeAmbientOcclusion.fx", SSAO_ALGORITHM=0, **dict(_SSAO, SSAO_OPTION_HALF_PRECISION_DEPTH=1)),
+    _p("ssao_upsample", "SSAO_ComputeBilateralUpsampling.fx", **_SSAO_HALF),
+    _p("ssao_temporal", "SSAO_ComputeTemporalAccumulation.fx", **_SSAO),
+    _p("ssao_temporal__rev", "SSAO_ComputeTemporalAccumulation.fx", **_SSAO_REV),
+    _p("ssao_convolute", "SSAO_ComputeConvolutedDepthHistory.fx", **_SSAO),
+    _p("ssao_resample", "SSAO_ComputeResampledHistory.fx", **_SSAO),
+    _p("ssao_resample__rev", "SSAO_ComputeResampledHistory.fx", **_SSAO_REV),
+    _p("ssao_spatial", "SSAO_ComputeSpatialReconstruction.fx", **_SSAO),
+    _p("ssao_spatial__rev", "SSAO_ComputeSpatialReconstruction.fx", **_SSAO_REV),
+    # Bloom
+    _p("bloom_prefilter", "Bloom_ComputePrefilteredTexture.fx"),
+    _p("bloom_downsample", "Bloom_ComputeDownsampledTexture.fx"),
+    _p("bloom_upsample", "Bloom_ComputeUpsampledTexture.fx"),
+    # TemporalAntiAliasing (TemporalAntiAliasing.cpp:237-239); variant suffix = g(aussian) b(icubic) y(CoCg) bits
+] + [
+    _p("taa" + ("__" + "".join(n for n, on in zip("gby", (g, b, y)) if on) if (g or b or y) else ""), "TAA_ComputeTemporalAccumulation.fx", "taa.inc",
+       TAA_OPTION_GAUSSIAN_WEIGHTING=g, TAA_OPTION_BICUBIC_FILTER=b, TAA_OPTION_YCOCG_COLOR_SPACE=y)
+    for g in (0, 1) for b in (0, 1) for y in (0, 1)
+] + [
+    # ToneMapping.fxh: the operator is a compile-time choice (TONE_MAPPING_MODE 1..11, ToneMappingStructures.fxh:11-22)
+    _p(f"tonemap__{m}", ["ToneMapping.fxh", "SRGBUtilities.fxh", "FullScreenTriangleVSOutput.fxh"], "tonemap.inc", TONE_MAPPING_MODE=m) for m in range(1, 12)
 ]
