@@ -237,7 +237,7 @@ inline float atan(float x) { return std::atan(x); }
 inline float atan2(float y, float x) { return std::atan2(y, x); }
 inline float pow(float x, float y) { return std::pow(x, y); }
 inline float fmod(float x, float y) { return std::fmod(x, y); }
-inline float saturate(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); } // NaN -> 0 as on D3D
+inline float saturate(float x) { return std::fmin(std::fmax(x, 0.0f), 1.0f); } // NaN -> 0 (Direct3D: min / max return the non-NaN operand)
 inline float sign(float x) { return float((x > 0.0f) - (x < 0.0f)); }
 inline float step(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
 inline float min(float a, float b) { return std::fmin(a, b); } // D3D min/max return the non-NaN operand

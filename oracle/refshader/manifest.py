@@ -68,4 +68,18 @@ PASSES = [
 ] + [
     # ToneMapping.fxh: the operator is a compile-time choice (TONE_MAPPING_MODE 1..11, ToneMappingStructures.fxh:11-22)
     _p(f"tonemap__{m}", ["ToneMapping.fxh", "SRGBUtilities.fxh", "FullScreenTriangleVSOutput.fxh"], "tonemap.inc", TONE_MAPPING_MODE=m) for m in range(1, 12)
+] + [
+    # DepthOfField (DepthOfField.cpp:529, :564, :635)
+    _p("dof_coc", "DOF_ComputeCircleOfConfusion.fx"),
+    _p("dof_temporal", "DOF_ComputeTemporalCircleOfConfusion.fx"),
+    _p("dof_separated", "DOF_ComputeSeparatedCircleOfConfusion.fx"),
+    _p("dof_dilation", "DOF_ComputeDilationCircleOfConfusion.fx"),
+    _p("dof_blur__x", "DOF_ComputeBlurredCircleOfConfusion.fx", "dof_blur.inc", DOF_CIRCLE_OF_CONFUSION_BLUR_TYPE=0),
+    _p("dof_blur__y", "DOF_ComputeBlurredCircleOfConfusion.fx", "dof_blur.inc", DOF_CIRCLE_OF_CONFUSION_BLUR_TYPE=1),
+    _p("dof_prefilter", "DOF_ComputePrefilteredTexture.fx"),
+    _p("dof_bokeh_first", "DOF_ComputeBokehFirstPass.fx", DOF_OPTION_KARIS_INVERSE=0),
+    _p("dof_bokeh_first__karis", "DOF_ComputeBokehFirstPass.fx", DOF_OPTION_KARIS_INVERSE=1),
+    _p("dof_bokeh_second", "DOF_ComputeBokehSecondPass.fx"),
+    _p("dof_postfilter", "DOF_ComputePostfilteredTexture.fx"),
+    _p("dof_combine", "DOF_ComputeCombinedTexture.fx"),
 ]

@@ -1,0 +1,131 @@
+"""Pins the oracle against the reference ITSELF: every pass of the oracle is compared with the reference's own HLSL pixel
+shader for that pass, compiled for the CPU by oracle/refshader (sources read in place from /root/reference, never copied) and
+run on the same inputs.
+
+Bar: BIT-EXACT. The shader runner and the oracle state the HLSL intrinsics and the fixed-function sampler the same way
+(fp32, no contraction, 1/256-texel bilinear snap), so any difference is a difference between the oracle's restatement and
+the reference's shader text. The one tolerated pass is the first bokeh gather of DepthOfField, whose 142 bilinear taps per
+pixel are aimed with a texture coordinate the shader derives from the interpolated NDC position (0.5 + 0.5 * ndc) while
+the oracle uses (x + 0.5) / W: the last-bit difference moves a few taps across a 1/256-texel snap boundary.
+
+Runs wherever oracle/_ref/librefshaders.so exists: here it is (re)built from /root/reference; on a box without the
+reference the prebuilt library that travelled with the snapshot is used; with neither the module is skipped and
+tests/test_reference_shader_golden.py still checks the committed outputs of these shaders.
+"""
+import numpy as np
+import pytest
+
+from diligentfx_b200 import capi, synth
+from oracle.refshader import refsh
+
+from refshader_driver import Variant, compare_frame, make_oracle
+
+W, H = 157, 89                                   # odd on both axes: the odd-size branches of every mip chain run
+TOLERATED = {"D8 dof_bokeh_first.near": (1e-3, 0.02), "D8 dof_bokeh_first.far": (1e-3, 0.02)}   # (max abs, max fraction of texels that differ)
+
+
+@pytest.fixture(scope="module")
+def shaders(built):
+    try:
+        refsh.build()
+    except Exception as e:                       # pragma: no cover - only where the reference is mounted but does not compile
+        pytest.fail(f"the reference shaders no longer compile for the CPU: {e}")
+    if not refsh.available():
+        pytest.skip("oracle/_ref/librefshaders.so is absent and /root/reference is not mounted")
+    return True
+
+
+def _run(v: Variant, frames=None, warm: int = 2):
+    seq = frames if frames is not None else synth.generate_sequence(W, H, warm + 1)
+    o = make_oracle(W, H, v)
+    o.set_reversed_depth(v.reversed_depth)
+    try:
+        for fr in seq[:warm]:
+            o.set_inputs(fr)
+            o.frame(v.stages())
+        return compare_frame(o, seq[warm], v)
+    finally:
+        o.set_reversed_depth(False)
+
+
+def _check(res):
+    bad = []
+    for label, (got, want) in res.items():
+        assert got.shape == want.shape, label
+        if label in TOLERATED:
+            tol, frac = TOLERATED[label]
+            d = np.abs(got.astype(np.float64) - want)
+            if d.max() > tol or (d > 0).mean() > frac:
+                bad.append(f"{label}: max abs {d.max():.3e}, differing texels {(d > 0).mean():.3%}")
+        elif not np.array_equal(got, want):
+            d = np.abs(got.astype(np.float64) - want)
+            bad.append(f"{label}: NOT bit-exact (max abs {d.max():.3e}, {(d > 0).mean():.3%} of values differ)")
+    assert not bad, "oracle differs from the reference's shaders:\n  " + "\n  ".join(bad)
+    return len(res)
+
+
+def test_default_chain_bit_exact(shaders):
+    """The benchmarked configuration: every pass of PostFX, SSR, SSAO, TAA, Bloom and ToneMap, third frame of a sequence."""
+    n = _check(_run(Variant()))
+    assert n >= 45
+
+
+def test_reversed_depth_bit_exact(shaders):
+    seq = [synth.reverse_depth_frame(f) for f in synth.generate_sequence(W, H, 3)]
+    _check(_run(Variant(reversed_depth=True), seq))
+
+
+def test_half_resolution_bit_exact(shaders):
+    _check(_run(Variant(ssr_flags=capi.SSR_FLAG_HALF_RESOLUTION, ssao_flags=capi.SSAO_FLAG_HALF_RESOLUTION)))
+
+
+def test_ssr_previous_frame_and_half_precision_depth_bit_exact(shaders):
+    _check(_run(Variant(ssr_flags=1, ssao_flags=1)))
+
+
+@pytest.mark.parametrize("algorithm", [1, 2], ids=["hbao", "vbao"])
+def test_ssao_algorithms_bit_exact(shaders, algorithm):
+    res = _run(Variant(ssao_algorithm=algorithm))
+    _check({k: v for k, v in res.items() if k.startswith("A")})
+
+
+@pytest.mark.parametrize("flags", [0, 1, 4, 5, 6, 7], ids=lambda f: f"taa_flags_{f}")
+def test_taa_variants_bit_exact(shaders, flags):
+    res = _run(Variant(taa_flags=flags))
+    _check({k: v for k, v in res.items() if k.startswith("T")})
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 5, 6, 7, 8, 9, 10, 11])
+def test_tone_map_operators_bit_exact(shaders, mode):
+    res = _run(Variant(tonemap_mode=mode, to_srgb=bool(mode & 1)), warm=0)
+    _check({k: v for k, v in res.items() if k.startswith("M")})
+
+
+def test_depth_of_field_bit_exact(shaders):
+    a = capi.DOFAttribs.default()
+    a.MaxCircleOfConfusion = 0.02
+    frames = []
+    for f in synth.generate_sequence(W, H, 3):
+        g = dict(f)
+        for k in ("curr_camera", "prev_camera"):
+            c = capi.CameraAttribs.from_buffer_copy(bytes(f[k]))
+            c.fFocusDistance, c.fFStop = 6.0, 1.4
+            g[k] = c
+        frames.append(g)
+    for flags in (capi.DOF_FLAG_TEMPORAL_SMOOTHING | capi.DOF_FLAG_KARIS_INVERSE, 0):
+        res = _run(Variant(dof=True, dof_flags=flags, dof_attribs=a), frames)
+        assert any(k.startswith("D11") for k in res)
+        _check({k: v for k, v in res.items() if k[0] in "DB"})
+
+
+def test_constant_buffer_layouts_match_the_reference_structures(shaders):
+    """Each harness memcpy's the C struct of include/dfx_b200.h into the structure the reference's .fxh declares and refuses
+    (error 2) when the sizes differ; feeding a short struct must therefore fail."""
+    import ctypes as C
+
+    class Short(C.Structure):
+        _fields_ = [("x", C.c_float * 3)]
+
+    d = np.zeros((8, 8), np.float32)
+    with pytest.raises(RuntimeError, match="failed with 2"):
+        refsh.run("postfx_reprojected_depth", [d], [d.copy()], cbs=[Short(), Short()])
