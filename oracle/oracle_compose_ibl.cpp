@@ -121,7 +121,7 @@ void compose_ibl(const Camera& cam, const TexF4& color, const TexF4* ssr, const 
                     float3 k_S = SchlickReflection(NdotV, Reflectance0, Reflectance90);
                     // GetSpecularIBL_GGX :293-302
                     float3 SSR = SSRRadiance.xyz() * (k_S * PreIntBRDF.x + float3(PreIntBRDF.y, PreIntBRDF.y, PreIntBRDF.y));
-                    float3 rgb = Color.xyz() + (SSR - SpecularIBL.xyz()) * (SSRRadiance.w * SSRScale);
+                    float3 rgb = Color.xyz() + (SSR - SpecularIBL.xyz()) * SSRRadiance.w * SSRScale; // left to right, as HnPostProcess.psh:170 writes it
                     Color      = float4(rgb, Color.w);
                 }
                 float SSAOScale = ssao_scale * Opacity;

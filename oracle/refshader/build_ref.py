@@ -31,6 +31,7 @@ ORACLE = os.path.dirname(HERE)
 OUT_DIR = os.path.join(ORACLE, "_ref")
 LIB = os.path.join(OUT_DIR, "librefshaders.so")
 REF_SHADERS = os.environ.get("DFX_REFERENCE_SHADERS", "/root/reference/Shaders")
+REF_EXTRA = [os.path.join(os.path.dirname(REF_SHADERS), "Hydrogent", "shaders")]  # HnPostProcess.psh (the compose step)
 CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-pthread", "-w", f"-I{HERE}",
             f"-I{os.path.join(os.path.dirname(ORACLE), 'include')}"]
 
@@ -40,9 +41,10 @@ _FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE]
 
 def _index() -> dict[str, str]:
     idx: dict[str, str] = {}
-    for root, _, files in os.walk(REF_SHADERS):
-        for f in files:
-            idx.setdefault(f, os.path.join(root, f))
+    for top in [REF_SHADERS, *REF_EXTRA]:
+        for root, _, files in os.walk(top):
+            for f in files:
+                idx.setdefault(f, os.path.join(root, f))
     return idx
 
 
@@ -56,7 +58,10 @@ def rewrite(text: str) -> str:
     text = re.sub(r"(?<=[(,])(\s*)(?:in\s+)?(?:inout|out)\s+((?:const\s+)?[A-Za-z_]\w*\s+\w+\s*\[)", r"\1\2", text)  # arrays are passed by reference in C++ already
     text = re.sub(r"(?<=[(,])(\s*)(?:in\s+)?(?:inout|out)\s+((?:const\s+)?[A-Za-z_]\w*(?:<\w+>)?)\s+(?=[A-Za-z_])", r"\1\2& ", text)
     text = re.sub(r"(?<=[(,])(\s*)in\s+(?=[A-Za-z_])", r"\1", text)
-    text = re.sub(r"\bTexture2D\s+(?=[A-Za-z_])", "Texture2D<float4> ", text)
+    # the same qualifiers on a parameter that starts its own line (after an #if / #endif inside the parameter list)
+    text = re.sub(r"(?m)^(\s*)(?:in\s+)?(?:inout|out)\s+((?:const\s+)?[A-Za-z_]\w*(?:<\w+>)?)\s+(?=[A-Za-z_]\w*\s*[,)])", r"\1\2& ", text)
+    text = re.sub(r"(?m)^(\s*)in\s+(?=(?:const\s+)?[A-Za-z_]\w*(?:<\w+>)?\s+[A-Za-z_]\w*\s*[,)])", r"\1", text)
+    text = re.sub(r"\b(Texture2D|TextureCube)\s+(?=[A-Za-z_])", r"\1<float4> ", text)
     text = text.replace("__cplusplus", "DFX_REFSH_HIDDEN_CPLUSPLUS")
     lines = []
     for line in text.split("\n"):
@@ -73,7 +78,7 @@ def flatten(name: str, idx: dict[str, str], seen: set[str]) -> str:
     path = idx.get(name)
     if path is None:
         raise FileNotFoundError(f"{name} not found under {REF_SHADERS}")
-    out = [f"// ---- begin {os.path.relpath(path, REF_SHADERS)}\n"]
+    out = [f"// ---- begin {os.path.relpath(path, os.path.dirname(REF_SHADERS))}\n"]
     for line in rewrite(open(path, encoding="utf-8", errors="replace").read()).split("\n"):
         m = re.match(r'\s*#\s*include\s+"([^"]+)"', line)
         out.append(flatten(os.path.basename(m.group(1)), idx, seen) if m else line + "\n")

@@ -455,8 +455,18 @@ template <class T = float4> struct Texture2D
         const float f  = l - float(m0);
         return sample_mip(s, uv, m0) * (1.0f - f) + sample_mip(s, uv, m1) * f;
     }
+    // Sample(): implicit-derivative LOD. Only single-mip look-up tables are sampled this way on this path -> mip 0.
+    T Sample(const SamplerState& s, const float2& uv) const { return sample_mip(s, uv, 0); }
     template <class U> void GetDimensions(U& W, U& H) const { W = U(w[0]), H = U(h[0]); }
     template <class U, class L> void GetDimensions(uint m, U& W, U& H, L& n) const { W = U(w[m]), H = U(h[m]), n = L(levels); }
+};
+
+// Cube maps are declared by PBR_Shading.fxh (environment lighting) but never sampled on the PostProcess path: the type
+// exists so that those helper functions compile; sampling one returns 0.
+template <class T = float4> struct TextureCube
+{
+    T SampleLevel(const SamplerState&, const float3&, float) const { return T(0.0f); }
+    T Sample(const SamplerState&, const float3&) const { return T(0.0f); }
 };
 
 // ---- the full-screen pass: one pixel-shader invocation per target pixel, rows split over host threads ----

@@ -118,6 +118,59 @@ def test_depth_of_field_bit_exact(shaders):
         _check({k: v for k, v in res.items() if k[0] in "DB"})
 
 
+def test_brdf_table_bit_exact(shaders):
+    """PrecomputeBRDF.psh against oracle_compose_ibl.cpp's brdf_lut(), at two sample counts."""
+    from oracle import oracle_py as op
+    o = op.Oracle(W, H)
+    for size, samples, name in ((64, 512, "brdf_lut"), (32, 64, "brdf_lut__64")):     # powers of two, like the reference's 512 x 512 table
+        o.brdf_lut(size, samples)
+        want = o.get("brdf_lut")
+        got = np.zeros_like(want)
+        refsh.run(name, [], [got])
+        _check({f"BRDF table {size} x {size}, {samples} samples": (got, want)})
+
+
+@pytest.mark.parametrize("size", [(128, 64), (157, 89)], ids=["128x64", "157x89"])
+def test_full_compose(shaders, size):
+    """Hydrogent's HnPostProcess.psh (SSR re-weighted by the split-sum BRDF and exchanged for the specular IBL, then SSAO)
+    against the oracle's compose_ibl, on planes that exercise opacity 0, out-of-range roughness and metals.
+
+    The shader builds the view direction from the interpolated NDC position of the pixel; the runner interpolates it as
+    -1 + 2 (x + 0.5) / W, the oracle as ((x + 0.5) / W - 0.5) / 0.5. For power-of-two sizes both are exact and the pass is
+    bit-exact; for other sizes the last bit of the NDC position differs and the result agrees to 1e-5 (relative to 1 + |c|)."""
+    from oracle import oracle_py as op
+    w, h = size
+    fr = synth.generate_sequence(w, h, 1)[0]
+    rng = np.random.default_rng(5)
+    color = fr["color"].copy()
+    color[..., 3] = rng.choice([0.0, 0.35, 1.0], (h, w), p=[0.1, 0.2, 0.7])
+    mat = fr["material"].copy()
+    mat[..., 1] = rng.choice([0.0, 0.5, 1.0], (h, w))
+    mat[..., 0] = np.where(rng.random((h, w)) < 0.05, 1.5, mat[..., 0])
+    base = np.concatenate([rng.uniform(0.02, 1.0, (h, w, 3)), np.ones((h, w, 1))], -1).astype(np.float32)
+    ibl = np.concatenate([np.exp2(rng.uniform(-4, 2, (h, w, 3))), np.ones((h, w, 1))], -1).astype(np.float32)
+    ssr = np.concatenate([np.exp2(rng.uniform(-4, 3, (h, w, 3))), rng.uniform(0, 1, (h, w, 1))], -1).astype(np.float32)
+    ao = rng.uniform(0.2, 1.0, (h, w)).astype(np.float32)
+    o = op.Oracle(w, h)
+    o.set_inputs(fr)
+    o.brdf_lut(64, 512)
+    lut = o.get("brdf_lut")
+    for k, v in dict(color=color, material=mat, base_color=base, specular_ibl=ibl, ssr_out=ssr, ssao_out=ao).items():
+        o.set(k, v)
+    bits = lambda f: int(np.float32(f).view(np.uint32))  # noqa: E731
+    for ssr_scale, ssao_scale in ((0.8, 0.6), (1.0, 0.0), (0.0, 1.0)):
+        o.set_compose_scales(ssr_scale, ssao_scale)
+        o.run("compose_ibl")
+        want = o.get("composed")
+        got = np.zeros_like(want)
+        refsh.run("compose_ibl", [color, ssr, ao, fr["normal"], ibl, mat, base, lut], [got], cbs=[fr["curr_camera"]], iparams=[bits(ssr_scale), bits(ssao_scale)])
+        if w & (w - 1) == 0 and h & (h - 1) == 0:
+            _check({f"compose (SSRScale {ssr_scale}, SSAOScale {ssao_scale})": (got, want)})
+        else:
+            rel = np.abs(got.astype(np.float64) - want) / (1.0 + np.abs(want))
+            assert rel.max() < 1e-5, rel.max()
+
+
 def test_constant_buffer_layouts_match_the_reference_structures(shaders):
     """Each harness memcpy's the C struct of include/dfx_b200.h into the structure the reference's .fxh declares and refuses
     (error 2) when the sizes differ; feeding a short struct must therefore fail."""
