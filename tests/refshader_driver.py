@@ -84,8 +84,10 @@ def dof_kernels(a: capi.DOFAttribs):
     return points(a.BokehKernelRingCount, a.BokehKernelRingDensity), points(3, 5), np.array(buf[:n], np.float32).reshape(1, n)
 
 
-def compare_frame(o: op.Oracle, fr: dict, v: Variant) -> dict[str, tuple[np.ndarray, np.ndarray]]:
-    """`o` holds the history of the frames before `fr` (run with o.frame()); `fr` must be the next frame of the sequence."""
+def compare_frame(o: op.Oracle, fr: dict, v: Variant, with_reference: bool = True) -> dict[str, tuple[np.ndarray, np.ndarray]]:
+    """`o` holds the history of the frames before `fr` (run with o.frame()); `fr` must be the next frame of the sequence.
+    with_reference=False steps the oracle alone (the first element of every pair is then the untouched target), for
+    comparing it with the committed outputs of the reference shaders where librefshaders.so is not available."""
     res: dict[str, tuple[np.ndarray, np.ndarray]] = {}
     rev = "__rev" if v.reversed_depth else ""
     cur, prv = fr["curr_camera"], fr["prev_camera"]
@@ -95,7 +97,8 @@ def compare_frame(o: op.Oracle, fr: dict, v: Variant) -> dict[str, tuple[np.ndar
     g = o.get
 
     def ref(name, ins, outs, **kw):
-        refsh.run(name, ins, outs, **kw)
+        if with_reference:
+            refsh.run(name, ins, outs, **kw)
         return outs
 
     # ---------------- PostFXContext ----------------
