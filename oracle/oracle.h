@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // Pass-by-pass CPU restatement of the DiligentFX PostProcess chain. One function per reference render pass,
 // same plane set and ordering as the reference host code; storage is fp32 (north-star layout).
 #pragma once

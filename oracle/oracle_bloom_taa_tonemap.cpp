@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // Bloom B1-B4, TAA T0/T1, compose (reduced form) and ToneMap M1/M2 restated from the reference HLSL / C++.
 #include "oracle.h"
 

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // C API (ctypes) over the oracle passes: a context of named fp32 planes + one "run" entry per reference pass and a
 // whole-frame driver that sequences them exactly as the reference's host code does
 // (Hydrogent/src/Tasks/HnPostProcessTask.cpp:743-947; per-effect Execute() methods).

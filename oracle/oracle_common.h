@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 //
 // Restatement of the shared shader helpers:
 //   Shaders/Common/public/PostFX_Common.fxh, ShaderUtilities.fxh, SRGBUtilities.fxh, PBR_Common.fxh (GGX subset)

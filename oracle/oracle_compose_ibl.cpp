@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // The full compose step of the reference integration: Hydrogent/shaders/HnPostProcess.psh:145-185 with
 // the split-sum helpers it calls (Shaders/PBR/public/PBR_Shading.fxh:220-302, :429-451; Shaders/Common/public/PBR_Common.fxh:8-11,
 // :86-95) and the pre-integrated GGX look-up table those helpers sample (Shaders/PBR/private/PrecomputeBRDF.psh:10-48,

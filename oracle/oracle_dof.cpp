@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // DepthOfField, eleven passes restated from Shaders/PostProcess/DepthOfField/private/DOF_*.fx (file:line per
 // function) in the order of DepthOfField::Execute (PostProcess/DepthOfField/src/DepthOfField.cpp:292-331). Storage is fp32 like
 // the rest of the oracle (the reference keeps CoC in R16_FLOAT / R16_UNORM and colour in RGBA16_FLOAT / R11G11B10_FLOAT).

@@ -1,10 +1,15 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Nothing under oracle/ is part of the product path.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may use it.
 //
-// Parity status: PARITY UNPINNED. The reference (DiligentFX) ships no golden vectors, KATs or numerical
-// tests for its PostProcess shaders and cannot be built or run here (needs DiligentCore,
-// an HLSL compiler and a graphics device). This oracle is a scalar C++ restatement of the HLSL, anchored on
-// the analytic known-answer tests the shaders imply (tests/test_oracle_kats.py).
+// Parity status: PINNED AGAINST THE REFERENCE'S OWN SHADERS, pass by pass. The reference (DiligentFX) ships no golden
+// vectors or numerical tests for its PostProcess shaders and its C++ cannot be built here (DiligentCore
+// is not vendored), but its pixel shaders can be run: oracle/refshader compiles the HLSL sources where they lie under
+// /root/reference for the CPU (oracle/_ref/librefshaders.so) and tests/test_reference_shaders.py holds every function of
+// this oracle to the shader it restates, BIT FOR BIT, on the same inputs, in every variant; tests/golden/
+// reference_shaders_49x27.npz carries those shader outputs to machines without the reference.
+// What that does not cover: the host-side sequencing (which plane feeds which pass, clears, ping-pong: restated from the
+// .cpp files, cited per function) and the fixed-function model both sides share (oracle_tex.h). The analytic known-answer
+// tests the shaders imply stay in tests/test_oracle_kats.py.
 //
 // HLSL scalar/vector vocabulary restated for plain C++ (no SIMD, no FMA contraction: build with
 // -ffp-contract=off). Conventions follow SURVEY.md Appendix B: row-vector mul(v, M), M[r][c],

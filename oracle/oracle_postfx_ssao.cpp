@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // PostFXContext passes P0-P2 and SSAO passes A1-A8, restated from the reference HLSL (file:line cited per function).
 #include "oracle.h"
 

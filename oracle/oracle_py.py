@@ -1,4 +1,4 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY. ctypes wrapper over oracle/_build/liboracle.so (parity unpinned, see oracle_math.h).
+"""ORACLE — TEST INFRASTRUCTURE ONLY. ctypes wrapper over oracle/_build/liboracle.so (pinned against the reference's shaders, see oracle_math.h).
 
 Importers: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline leg and --impl reference). Never the product path.
 """

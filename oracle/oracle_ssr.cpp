@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 // SSR passes S1, S2, S4-S7 restated from Shaders/PostProcess/ScreenSpaceReflection/private/*.fx (file:line per function).
 #include "oracle.h"
 #include <atomic>

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h). Pinned against the reference's own shaders (oracle/refshader, tests/test_reference_shaders.py).
 //
 // Texture model: what the HLSL relies on from the fixed-function units:
 //   * Texture.Load out of bounds returns 0 (D3D)                                            -> Tex::load

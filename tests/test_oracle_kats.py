@@ -1,6 +1,7 @@
 """Known-answer tests that pin the ORACLE (CPU, no GPU needed).
 
-The reference ships no golden vectors for this path ("parity unpinned"), so the oracle is anchored on
+The reference ships no golden vectors for this path. Besides the pass-by-pass comparison with the reference's
+own shaders (tests/test_reference_shaders.py), the oracle is anchored on
 the analytic properties the shaders imply — each test cites the shader lines that imply the expected value.
 """
 import ctypes as C
