@@ -118,6 +118,44 @@ def test_depth_of_field_bit_exact(shaders):
         _check({k: v for k, v in res.items() if k[0] in "DB"})
 
 
+@pytest.mark.parametrize("size", [(34, 18), (33, 17)], ids=["even", "odd"])
+def test_bilateral_quad_derivatives_everywhere(shaders, size):
+    """SSR_ComputeBilateralCleanup.fx takes ddx / ddy of the camera-space depth. With the filter branch live on EVERY pixel
+    (the sequence tests reach it only where the variance is high) the oracle's 2x2 differences equal the shader's quad
+    derivatives bit for bit - except, on odd-sized targets, in the last column / row, whose quad partner lies outside the
+    target: Direct3D runs it as a helper lane whose Load returns 0, the oracle (and dfx_ssr.cu) clamp the partner onto the
+    pixel itself. KNOWN DEVIATION, confined to that column / row of odd-sized targets."""
+    from oracle import oracle_py as op
+    w, h = size
+    fr = synth.generate_sequence(w, h, 1)[0]
+    rng = np.random.default_rng(1)
+    ssr = capi.SSRAttribs.default()
+    o = op.Oracle(w, h)
+    o.set_ssr(ssr, 0)
+    o.set_inputs(fr)
+    depth = rng.uniform(0.3, 0.9, (h, w)).astype(np.float32)
+    normal = np.zeros((h, w, 4), np.float32)
+    normal[..., 2] = 1.0
+    o.set("depth", depth), o.set("normal", normal), o.set("material", np.full((h, w, 4), 0.2, np.float32))
+    o.run("ssr_mask")
+    rough, mask = o.get("ssr_roughness"), o.get("ssr_mask")
+    assert mask.all() and rough.min() >= 0.125                            # every pixel traced, full filter radius
+    ci = fr["frame"] & 1
+    rad, var = rng.uniform(0, 4, (h, w, 4)).astype(np.float32), np.ones((h, w), np.float32)
+    o.set(f"ssr_radhist{ci}", rad), o.set(f"ssr_varhist{ci}", var)
+    o.run("ssr_bilateral")
+    want = o.get("ssr_out")
+    assert np.abs(want - rad).max() > 0.1                                  # the filter really ran
+    got = np.zeros_like(want)
+    refsh.run("ssr_bilateral", [depth, normal, rough, rad, var], [got], cbs=[fr["curr_camera"], ssr], mask=np.ones((h, w), np.uint8))
+    differ = (got != want).any(axis=2)
+    if w % 2 == 0 and h % 2 == 0:
+        assert not differ.any()
+    else:
+        ys, xs = np.nonzero(differ)
+        assert differ.any() and np.all((xs == w - 1) | (ys == h - 1)), "the deviation must stay in the last column / row"
+
+
 def test_brdf_table_bit_exact(shaders):
     """PrecomputeBRDF.psh against oracle_compose_ibl.cpp's brdf_lut(), at two sample counts."""
     from oracle import oracle_py as op
