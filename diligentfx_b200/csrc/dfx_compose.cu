@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) compose_ibl_kernel(const dfx_camera_attri
         const float  t = fminf(fmaxf(1.0f - ndv, 0.0f), 1.0f), t2 = t * t, t5 = t2 * t2 * t;
         const float3 ks = r0 + (r90 - r0) * t5; // SchlickReflection
         const float3 spec = xyz(r) * (ks * pre.x + make_float3(pre.y, pre.y, pre.y));
-        c = c + (spec - xyz(ibl)) * (r.w * s_ssr);
+        c = c + (spec - xyz(ibl)) * r.w * s_ssr; // left to right, as HnPostProcess.psh:170 multiplies
     }
     const float s_ao = ssao_scale * opacity;
     if (ao.p && s_ao > 0.0f) c = c * lerpf(1.0f, __ldg(&ao.at(x, y)), s_ao);

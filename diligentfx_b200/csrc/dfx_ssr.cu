@@ -644,9 +644,10 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     float4      result = __ldg(&radiance.at(x, y));
     if (var > 0.00005f && er > 0)
     {
-        // camera Z and its quad derivatives are only needed by the filter branch
+        // camera Z and its quad derivatives are only needed by the filter branch. On an odd-sized target the quad partner of
+        // the last column / row lies outside it: Direct3D shades it as a helper lane whose Load returns 0 (load0, not a clamp)
         const float  camZ = camz_precise(__ldg(&depth.at(x, y)));
-        auto         cz   = [&](int sx, int sy) { return camz_precise(loadc(depth, sx, sy)); };
+        auto         cz   = [&](int sx, int sy) { return camz_precise(load0(depth, sx, sy)); };
         const float  gx = cz(x | 1, y) - cz(x & ~1, y), gy = cz(x, y | 1) - cz(x, y & ~1);
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         float  wsum = 0.0f;

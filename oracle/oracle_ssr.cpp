@@ -550,7 +550,9 @@ void ssr_bilateral(const Camera& cam, const dfx_ssr_attribs& A, const Tex<uint8_
     const int W = depth.w, H = depth.h;
     out.resize(W, H, float4()); // ClearRenderTarget 0
     const int2 Dim(int(cam.f4ViewportSize.x), int(cam.f4ViewportSize.y));
-    auto CamZ = [&](int x, int y) { return DepthToCameraZ(depth.load_clamped(x, y), cam.mProj); };
+    // quad partner of ddx / ddy (:59): a partner beyond the right / bottom edge of an odd-sized target is a helper lane whose
+    // Load returns 0 - confirmed against the shader itself (tests/test_reference_shaders.py::test_bilateral_quad_derivatives_everywhere)
+    auto CamZ = [&](int x, int y) { return DepthToCameraZ(depth.load(x, y), cam.mProj); };
 
     parallel_rows(0, H, threads, [&](int ya, int yb) {
         for (int py = ya; py < yb; ++py)
