@@ -1,6 +1,6 @@
 """cuemu — DEVELOPMENT TOOL. Kernel-source checks that the standard parity tests do not reach, run on the host build:
 
-    python -m pytest -p tools.cuemu.plugin tools/cuemu/test_emu_extra.py -q
+    python -m pytest -p tools.cuemu.plugin tests/cuemu_extra_check.py -q   (not collected by a plain `pytest tests/`: the file name does not match test_*.py)
 """
 import ctypes as C
 
