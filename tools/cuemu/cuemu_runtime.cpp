@@ -1,9 +1,40 @@
 // cuemu — DEVELOPMENT TOOL (see include/cuda_runtime.h): the block scheduler.
 #include "include/cuda_runtime.h"
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
-#include <ucontext.h>
 #include <vector>
+
+// A context switch without the two sigprocmask system calls swapcontext() makes: callee-saved registers on the old stack,
+// switch stack pointers, restore from the new stack (System V x86-64).
+extern "C" void cuemu_switch(void** save_sp, void* load_sp);
+asm(R"(
+    .text
+    .globl cuemu_switch
+    .type cuemu_switch, @function
+cuemu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size cuemu_switch, .-cuemu_switch
+)");
+#if !defined(__x86_64__)
+#    error "cuemu's context switch is written for x86-64"
+#endif
 
 namespace cuemu
 {
@@ -12,8 +43,8 @@ namespace
 constexpr size_t kStack = 256 * 1024;
 struct Block
 {
-    ucontext_t                     sched;
-    std::vector<ucontext_t>        ctx;
+    void*                          sched_sp = nullptr;
+    std::vector<void*>             sp;
     std::vector<std::vector<char>> stack;
     std::vector<char>              done;
     int                            current = -1;
@@ -27,25 +58,32 @@ void thread_entry()
     Block&    b = t_block;
     const int i = b.current;
     (*b.body)();
-    b.done[size_t(i)] = 1; // returning activates uc_link == the scheduler
+    b.done[size_t(i)] = 1;
+    void* dead;
+    cuemu_switch(&dead, b.sched_sp); // back to the scheduler for good
+    __builtin_trap();
+}
+
+void* fresh_stack(std::vector<char>& mem)
+{
+    if (mem.empty()) mem.resize(kStack);
+    // top of stack: [r15 r14 r13 r12 rbx rbp][return address = thread_entry]; the return-address slot is 16-byte aligned so
+    // that thread_entry starts with the stack the ABI expects after a call
+    uintptr_t top = (reinterpret_cast<uintptr_t>(mem.data()) + kStack) & ~uintptr_t(15);
+    void**    p   = reinterpret_cast<void**>(top - 16);
+    p[0]          = reinterpret_cast<void*>(&thread_entry);
+    for (int k = 1; k <= 6; ++k) p[-k] = nullptr;
+    return p - 6;
 }
 
 void run_block(dim3 grid, dim3 block, uint3 bidx, const std::function<void()>& body)
 {
     Block&    b = t_block;
     const int n = int(block.x * block.y * block.z);
-    if (int(b.ctx.size()) < n) b.ctx.resize(size_t(n)), b.stack.resize(size_t(n));
+    if (int(b.sp.size()) < n) b.sp.resize(size_t(n)), b.stack.resize(size_t(n));
     b.done.assign(size_t(n), 0);
     b.body = &body;
-    for (int i = 0; i < n; ++i)
-    {
-        if (b.stack[size_t(i)].empty()) b.stack[size_t(i)].resize(kStack);
-        getcontext(&b.ctx[size_t(i)]);
-        b.ctx[size_t(i)].uc_stack.ss_sp   = b.stack[size_t(i)].data();
-        b.ctx[size_t(i)].uc_stack.ss_size = kStack;
-        b.ctx[size_t(i)].uc_link          = &b.sched;
-        makecontext(&b.ctx[size_t(i)], thread_entry, 0);
-    }
+    for (int i = 0; i < n; ++i) b.sp[size_t(i)] = fresh_stack(b.stack[size_t(i)]);
     for (bool running = true; running;)
     {
         running = false;
@@ -54,7 +92,7 @@ void run_block(dim3 grid, dim3 block, uint3 bidx, const std::function<void()>& b
             if (b.done[size_t(i)]) continue;
             b.current  = i;
             t_builtins = Builtins{uint3{unsigned(i) % block.x, (unsigned(i) / block.x) % block.y, unsigned(i) / (block.x * block.y)}, bidx, block, grid};
-            swapcontext(&b.sched, &b.ctx[size_t(i)]); // runs thread i up to its next __syncthreads(), or to its end
+            cuemu_switch(&b.sched_sp, b.sp[size_t(i)]); // runs thread i up to its next __syncthreads(), or to its end
             running = running || !b.done[size_t(i)];
         }
     }
@@ -68,20 +106,71 @@ void sync_threads()
 {
     Block& b = t_block;
     if (b.current < 0) return;
-    swapcontext(&b.ctx[size_t(b.current)], &b.sched); // every thread that has not finished reaches the same barrier before anyone continues
+    cuemu_switch(&b.sp[size_t(b.current)], b.sched_sp); // every thread that has not finished reaches the same barrier before anyone continues
 }
+
+// Persistent workers: the per-thread coroutine stacks (64 MB per worker) are allocated once, not per launch.
+namespace
+{
+struct Pool
+{
+    std::mutex               m;
+    std::condition_variable  cv_work, cv_done;
+    std::vector<std::thread> threads;
+    const std::function<void(unsigned)>* job = nullptr;
+    unsigned long long       generation = 0;
+    unsigned                 pending = 0, active = 0;
+
+    explicit Pool(unsigned n)
+    {
+        for (unsigned w = 0; w < n; ++w)
+            threads.emplace_back([this, w] {
+                unsigned long long seen = 0;
+                for (;;)
+                {
+                    const std::function<void(unsigned)>* j;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv_work.wait(lk, [&] { return generation != seen; });
+                        seen = generation;
+                        j    = job;
+                    }
+                    if (w < active) (*j)(w);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) cv_done.notify_one();
+                    }
+                }
+            });
+        for (auto& t : threads) t.detach();
+    }
+    void run(unsigned workers, const std::function<void(unsigned)>& fn)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        job = &fn, active = workers, pending = unsigned(threads.size()), ++generation;
+        cv_work.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+Pool& pool()
+{
+    const char*  env = std::getenv("CUEMU_THREADS");
+    static Pool* p   = new Pool(std::max(1u, env ? unsigned(std::atoi(env)) : std::max(1u, std::thread::hardware_concurrency())));
+    return *p;
+}
+std::mutex g_launch_mutex; // one grid at a time (the C-ABI may be called from several host threads)
+} // namespace
 
 void launch(dim3 grid, dim3 block, const std::function<void()>& body)
 {
+    std::lock_guard<std::mutex> one(g_launch_mutex);
     const unsigned total   = grid.x * grid.y * grid.z;
-    const char*    env     = std::getenv("CUEMU_THREADS");
-    const unsigned workers = std::max(1u, std::min(total, env ? unsigned(std::atoi(env)) : std::max(1u, std::thread::hardware_concurrency())));
-    auto           work    = [&](unsigned w) {
-        for (unsigned i = w; i < total; i += workers) run_block(grid, block, uint3{i % grid.x, (i / grid.x) % grid.y, i / (grid.x * grid.y)}, body);
-    };
-    if (workers == 1) return work(0);
-    std::vector<std::thread> pool;
-    for (unsigned w = 0; w < workers; ++w) pool.emplace_back(work, w);
-    for (auto& t : pool) t.join();
+    Pool&          p       = pool();
+    const unsigned workers = std::max(1u, std::min(total, unsigned(p.threads.size())));
+    std::atomic<unsigned> next{0};
+    p.run(workers, [&](unsigned) {
+        for (unsigned i = next.fetch_add(1); i < total; i = next.fetch_add(1))
+            run_block(grid, block, uint3{i % grid.x, (i / grid.x) % grid.y, i / (grid.x * grid.y)}, body);
+    });
 }
 } // namespace cuemu

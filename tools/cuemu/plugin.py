@@ -37,7 +37,82 @@ def pytest_configure(config):
     capi.pyramid_of.__globals__["plane_of"] = ns["plane_of"]
 
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()        # the few direct .cuda() calls in the pass-level tests
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    torch.Tensor.cpu = lambda self, *a, **k: self.clone()         # a device -> host copy is a copy: tests keep the result while the plane is reused
     torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.is_available = lambda: True
+
+    def _on_cpu(fn):                                              # factory calls written with device="cuda"
+        def wrapped(*a, **k):
+            dev = k.get("device")
+            if dev is not None and (str(dev).startswith("cuda")):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapped
+
+    for _name in ("empty", "zeros", "ones", "full", "tensor", "rand", "randn", "arange", "empty_like", "zeros_like", "full_like"):
+        setattr(torch, _name, _on_cpu(getattr(torch, _name)))
+    torch.cuda.current_device = lambda: 0
+
+    # The chain driver (diligentfx_b200/chain.py) sequences its passes over CUDA streams and events; the host build executes
+    # every call synchronously, so streams and events are inert objects and the chain's planes live on the CPU device.
+    class _Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a, **k):
+            pass
+
+        def wait(self, *a, **k):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def query(self):
+            return True
+
+        def elapsed_time(self, other):
+            return 0.0
+
+    class _Stream:
+        cuda_stream = 0
+
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_event(self, e):
+            pass
+
+        def wait_stream(self, s):
+            pass
+
+        def record_event(self, e=None):
+            return e or _Event()
+
+        def synchronize(self):
+            pass
+
+    class _StreamCtx:
+        def __init__(self, s):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    _main = _Stream()
+    torch.cuda.Event, torch.cuda.Stream, torch.cuda.stream = _Event, _Stream, _StreamCtx
+    torch.cuda.current_stream = lambda *a, **k: _main
+    from diligentfx_b200 import chain as chain_mod
+    _init = chain_mod.PostProcessChain.__init__
+
+    def _cpu_init(self, width, height, config=None, device=None, **kw):
+        _init(self, width, height, config, device=torch.device("cpu"), **kw)
+
+    chain_mod.PostProcessChain.__init__ = _cpu_init
 
     import helpers
 
