@@ -54,18 +54,31 @@ def pytest_configure(config):
             return fn(*a, **k)
         return wrapped
 
+    _to = torch.Tensor.to
+
+    def _to_cpu(self, *a, **k):                                   # .to(torch.device("cuda", n)): device memory is host memory here
+        a = tuple("cpu" if (isinstance(x, (str, torch.device)) and str(x).startswith("cuda")) else x for x in a)
+        if "device" in k and str(k["device"]).startswith("cuda"):
+            k["device"] = "cpu"
+        out = _to(self, *a, **k)
+        return out.clone() if out is self else out
+
+    torch.Tensor.to = _to_cpu
+
     for _name in ("empty", "zeros", "ones", "full", "tensor", "rand", "randn", "arange", "empty_like", "zeros_like", "full_like"):
         setattr(torch, _name, _on_cpu(getattr(torch, _name)))
     torch.cuda.current_device = lambda: 0
+    torch.cuda.set_device = lambda *a, **k: None
 
     # The chain driver (diligentfx_b200/chain.py) sequences its passes over CUDA streams and events; the host build executes
     # every call synchronously, so streams and events are inert objects and the chain's planes live on the CPU device.
     class _Event:
         def __init__(self, *a, **k):
-            pass
+            self._t = 0.0
 
         def record(self, *a, **k):
-            pass
+            import time
+            self._t = time.perf_counter()
 
         def wait(self, *a, **k):
             pass
@@ -77,7 +90,7 @@ def pytest_configure(config):
             return True
 
         def elapsed_time(self, other):
-            return 0.0
+            return max(1e-3, (other._t - self._t) * 1e3)          # host wall clock: enough for code that divides by it
 
     class _Stream:
         cuda_stream = 0
