@@ -82,7 +82,7 @@ def rewrite(text: str) -> str:
     return rewrite_launches(text)
 
 
-def build(defines: list[str] | None = None) -> str:
+def build(defines: list[str] | None = None, asan: bool = False) -> str:
     sys.path.insert(0, ROOT)
     from diligentfx_b200 import build as product_build
     product_build.build()                                        # generates csrc/_gen (the blue-noise tables) as a side effect
@@ -92,12 +92,14 @@ def build(defines: list[str] | None = None) -> str:
         if f.endswith((".cu", ".cuh")):
             open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w").write(rewrite(open(os.path.join(CSRC, f)).read()))
     srcs = [os.path.join(src_dir, f.replace(".cu", ".cpp")) for f in product_build.SOURCES]
-    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", f"-I{os.path.join(HERE, 'include')}",
-           *[f"-D{d}" for d in (defines or [])], *srcs, os.path.join(HERE, "cuemu_runtime.cpp"), "-o", LIB]
+    out = LIB.replace(".so", "_asan.so") if asan else LIB      # --asan: every plane access of every kernel checked by AddressSanitizer
+    cmd = ["g++", "-std=c++17", "-O1" if asan else "-O2", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", f"-I{os.path.join(HERE, 'include')}",
+           *(["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if asan else []),
+           *[f"-D{d}" for d in (defines or [])], *srcs, os.path.join(HERE, "cuemu_runtime.cpp"), "-o", out]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
-    print(build(defs))
+    print(build(defs, asan="--asan" in sys.argv[1:]))

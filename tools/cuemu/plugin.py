@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, "_build", "libdfx_b200_emu.so")
+LIB = os.path.join(HERE, "_build", "libdfx_b200_emu_asan.so" if os.environ.get("CUEMU_ASAN") else "libdfx_b200_emu.so")
 
 
 def pytest_configure(config):
