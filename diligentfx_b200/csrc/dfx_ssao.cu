@@ -262,12 +262,24 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
 // ---------------------------------------------------------------------------------------------------------------------
 // A0 (half resolution only): checkerboard of the 2x2 min / max depth — SSAO_ComputeDownsampledDepth.fx:8-29
 // ---------------------------------------------------------------------------------------------------------------------
+// VEC: the depth rows are 8-byte aligned (even pitch), one 64-bit load per row; otherwise (a caller's tightly pitched plane of odd
+// width) four 32-bit loads.
+template <bool VEC>
 __global__ void __launch_bounds__(256) ssao_downsample_depth_kernel(View<const float> depth, View<float> out, int y0, int y1)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out.w || y >= y1) return;
-    const float2 r0 = __ldg(reinterpret_cast<const float2*>(depth.row(2 * y)) + x);     // (2x, 2y), (2x+1, 2y): 8-byte aligned
-    const float2 r1 = __ldg(reinterpret_cast<const float2*>(depth.row(2 * y + 1)) + x);
+    float2 r0, r1;
+    if (VEC)
+    {
+        r0 = __ldg(reinterpret_cast<const float2*>(depth.row(2 * y)) + x); // (2x, 2y), (2x+1, 2y)
+        r1 = __ldg(reinterpret_cast<const float2*>(depth.row(2 * y + 1)) + x);
+    }
+    else
+    {
+        r0 = make_float2(__ldg(&depth.at(2 * x, 2 * y)), __ldg(&depth.at(2 * x + 1, 2 * y)));
+        r1 = make_float2(__ldg(&depth.at(2 * x, 2 * y + 1)), __ldg(&depth.at(2 * x + 1, 2 * y + 1)));
+    }
     const float  mn = fminf(fminf(r0.x, r1.x), fminf(r0.y, r1.y)), mx = fmaxf(fmaxf(r0.x, r1.x), fmaxf(r0.y, r1.y));
     out.at(x, y)    = lerpf(mn, mx, float((x + y) & 1));
 }
@@ -645,11 +657,13 @@ extern "C" dfx_status dfx_pass_ssao_downsample_depth(void* stream, const dfx_pla
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
     DFX_VIEW(float, o, out_half, DFX_FORMAT_R32F);
     DFX_REQUIRE(o.w == d.w / 2 && o.h == d.h / 2, "the checkerboard plane must be width/2 x height/2 of the depth plane");
-    DFX_REQUIRE(d.pitch % 2 == 0 && reinterpret_cast<uintptr_t>(d.p) % 8 == 0, "depth rows must be 8-byte aligned");
     DFX_REQUIRE(rows_ok(rows, o.h), "bad row range (rows of the half-resolution plane)");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(o.w, 32), div_up(rows.y1 - rows.y0, 8));
-    ssao_downsample_depth_kernel<<<grid, block, 0, as_stream(stream)>>>(d, o, rows.y0, rows.y1);
+    if (d.pitch % 2 == 0 && reinterpret_cast<uintptr_t>(d.p) % 8 == 0)
+        ssao_downsample_depth_kernel<true><<<grid, block, 0, as_stream(stream)>>>(d, o, rows.y0, rows.y1);
+    else
+        ssao_downsample_depth_kernel<false><<<grid, block, 0, as_stream(stream)>>>(d, o, rows.y0, rows.y1);
     DFX_LAUNCHED("ssao_downsample_depth_kernel");
     return DFX_OK;
 }

@@ -30,8 +30,9 @@ def pytest_configure(config):
     capi._lib = None
     capi.load(LIB)                                                # every capi user of this process now talks to the host build
     alias = os.path.join(HERE, "_build", "libdfx_b200.so")         # tests/test_cpp_shim.py links its C++ driver with -ldfx_b200 from dirname(capi.LIB_PATH)
-    if not os.path.exists(alias):
-        os.symlink(os.path.basename(LIB), alias)
+    if os.path.islink(alias) or os.path.exists(alias):
+        os.remove(alias)
+    os.symlink(os.path.basename(LIB), alias)
     capi.LIB_PATH = alias
     # capi.plane_of insists on CUDA tensors; in the emulator device memory IS host memory
     src = inspect.getsource(capi.plane_of).replace("assert t.is_cuda and t.is_contiguous()", "assert t.is_contiguous()")
