@@ -35,11 +35,24 @@ def pytest_configure(config):
     os.symlink(os.path.basename(LIB), alias)
     capi.LIB_PATH = alias
     # capi.plane_of insists on CUDA tensors; in the emulator device memory IS host memory
-    src = inspect.getsource(capi.plane_of).replace("assert t.is_cuda and t.is_contiguous()", "assert t.is_contiguous()")
+    # CUEMU_PITCH_PAD=N: the tests' planes get N extra (poisoned) texels per row, i.e. a row pitch larger than width * texel
+    # size, the way an application's own allocations may be laid out (the tests themselves only use tight planes)
+    pad = int(os.environ.get("CUEMU_PITCH_PAD", "0"))
+    src = inspect.getsource(capi.plane_of).replace("assert t.is_cuda and t.is_contiguous()", "assert t.stride(1) == (1 if t.dim() == 2 else t.shape[2])")
+    src = src.replace("return Plane(t.data_ptr(), w * bpp, w, h, f, flags)", "return Plane(t.data_ptr(), t.stride(0) * t.element_size(), w, h, f, flags)")
+    assert "t.stride(0) * t.element_size()" in src
     ns = dict(vars(capi))
     exec(src, ns)
     capi.plane_of = ns["plane_of"]
     capi.pyramid_of.__globals__["plane_of"] = ns["plane_of"]
+
+    def _padded(t):
+        if not pad:
+            return t
+        store = torch.full((t.shape[0], t.shape[1] + pad) + tuple(t.shape[2:]), 7 if t.dtype == torch.uint8 else 12345.0, dtype=t.dtype)
+        view = store[:, :t.shape[1]]
+        view.copy_(t)
+        return view
 
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()        # the few direct .cuda() calls in the pass-level tests
     torch.Tensor.pin_memory = lambda self, *a, **k: self
@@ -132,23 +145,45 @@ def pytest_configure(config):
 
     chain_mod.PostProcessChain.__init__ = _cpu_init
 
+    # CUEMU_SPLIT_ROWS=K: every pass-level call that takes a row range runs as two calls, [y0, K) and [K, y1) - what a
+    # row-strip decomposition does (K must be a multiple of 64, the strip granularity of DESIGN.md section 7)
+    split = int(os.environ.get("CUEMU_SPLIT_ROWS", "0"))
+    if split:
+        real = capi._lib
+
+        class _SplitRows:
+            def __getattr__(self, name):
+                fn = getattr(real, name)
+                if not name.startswith("dfx_pass_"):
+                    return fn
+
+                def call(*args):
+                    if args and isinstance(args[-1], capi.Rows) and args[-1].y0 < split < args[-1].y1:
+                        r = args[-1]
+                        st = fn(*args[:-1], capi.Rows(r.y0, split))
+                        return st if st != 0 else fn(*args[:-1], capi.Rows(split, r.y1))
+                    return fn(*args)
+                return call
+
+        capi._lib = _SplitRows()
+
     import helpers
 
     class HostDev(helpers.Dev):
         def up(self, a, dtype=None):
-            t = torch.from_numpy(np.ascontiguousarray(a, np.float32 if dtype is None else dtype)).clone()
+            t = _padded(torch.from_numpy(np.ascontiguousarray(a, np.float32 if dtype is None else dtype)).clone())
             self.keep.append(t)
             return t
 
         def mask(self, a):
-            t = torch.from_numpy(np.ascontiguousarray(a != 0, np.uint8)).clone()
+            t = _padded(torch.from_numpy(np.ascontiguousarray(a != 0, np.uint8)).clone())
             self.keep.append(t)
             return t
 
         def empty(self, h, w, ch=1, fill=None, dtype=None):
             shape = (h, w) if ch == 1 else (h, w, ch)
             dt = dtype or torch.float32
-            t = torch.zeros(shape, dtype=dt) if fill is None else torch.full(shape, fill, dtype=dt)
+            t = _padded(torch.zeros(shape, dtype=dt) if fill is None else torch.full(shape, fill, dtype=dt))
             self.keep.append(t)
             return t
 
