@@ -84,11 +84,27 @@ void run_block(dim3 grid, dim3 block, uint3 bidx, const std::function<void()>& b
     b.done.assign(size_t(n), 0);
     b.body = &body;
     for (int i = 0; i < n; ++i) b.sp[size_t(i)] = fresh_stack(b.stack[size_t(i)]);
+    // CUEMU_ORDER=reverse | shuffle: the order in which the threads of a block run between two barriers. Results must not
+    // depend on it; if they do, a __syncthreads() is missing (or shared memory is read before it is written).
+    static const int order = [] {
+        const char* e = std::getenv("CUEMU_ORDER");
+        return !e ? 0 : (e[0] == 'r' ? 1 : 2);
+    }();
+    unsigned         lcg = 12345u + bidx.x * 7919u + bidx.y * 104729u;
+    std::vector<int> perm(static_cast<size_t>(n), 0);
+    for (int k = 0; k < n; ++k) perm[size_t(k)] = order == 1 ? n - 1 - k : k;
     for (bool running = true; running;)
     {
         running = false;
-        for (int i = 0; i < n; ++i)
+        if (order == 2) // a fresh permutation every round (Fisher-Yates)
+            for (int k = n - 1; k > 0; --k)
+            {
+                lcg = lcg * 1664525u + 1013904223u;
+                std::swap(perm[size_t(k)], perm[size_t((lcg >> 8) % unsigned(k + 1))]);
+            }
+        for (int k = 0; k < n; ++k)
         {
+            const int i = perm[size_t(k)];
             if (b.done[size_t(i)]) continue;
             b.current  = i;
             t_builtins = Builtins{uint3{unsigned(i) % block.x, (unsigned(i) / block.x) % block.y, unsigned(i) / (block.x * block.y)}, bidx, block, grid};
