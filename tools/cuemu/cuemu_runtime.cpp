@@ -2,6 +2,12 @@
 #include "include/cuda_runtime.h"
 
 #include <atomic>
+#include <fcntl.h>
+#include <map>
+#include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -190,3 +196,70 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body)
     });
 }
 } // namespace cuemu
+
+// ---- device memory: heap, or (CUEMU_IPC=1) named shared-memory segments that another process can map ----
+namespace
+{
+struct Segment
+{
+    std::string name;
+    size_t      bytes;
+    bool        owner;
+};
+std::mutex                g_seg_mutex;
+std::map<void*, Segment>  g_segments;
+std::atomic<unsigned>     g_seg_counter{0};
+bool ipc_mode() { return std::getenv("CUEMU_IPC") != nullptr; }
+} // namespace
+
+cudaError_t cudaMalloc(void** p, size_t bytes)
+{
+    *p = nullptr;
+    if (!ipc_mode()) return posix_memalign(p, 256, bytes ? bytes : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
+    const std::string name = "/cuemu-" + std::to_string(getpid()) + "-" + std::to_string(g_seg_counter++);
+    const int         fd   = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return cudaErrorMemoryAllocation;
+    const size_t n = std::max<size_t>(bytes, 256);
+    if (ftruncate(fd, off_t(n)) != 0) return close(fd), shm_unlink(name.c_str()), cudaErrorMemoryAllocation;
+    void* m = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return shm_unlink(name.c_str()), cudaErrorMemoryAllocation;
+    std::lock_guard<std::mutex> lk(g_seg_mutex);
+    g_segments[m] = Segment{name, n, true};
+    return *p = m, cudaSuccess;
+}
+cudaError_t cudaFree(void* p)
+{
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_seg_mutex);
+    auto                        it = g_segments.find(p);
+    if (it == g_segments.end()) return free(p), cudaSuccess;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    g_segments.erase(it);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
+{
+    std::lock_guard<std::mutex> lk(g_seg_mutex);
+    auto                        it = g_segments.find(p);
+    if (it == g_segments.end() || it->second.name.size() >= sizeof(h->reserved)) return cudaErrorNotSupported;
+    std::memset(h->reserved, 0, sizeof(h->reserved));
+    std::memcpy(h->reserved, it->second.name.c_str(), it->second.name.size());
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
+{
+    h.reserved[sizeof(h.reserved) - 1] = 0;
+    const int fd = shm_open(h.reserved, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorNotSupported;
+    struct stat st;
+    if (fstat(fd, &st) != 0) return close(fd), cudaErrorNotSupported;
+    void* m = mmap(nullptr, size_t(st.st_size), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorNotSupported;
+    std::lock_guard<std::mutex> lk(g_seg_mutex);
+    g_segments[m] = Segment{h.reserved, size_t(st.st_size), false};
+    return *p = m, cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) { return cudaFree(p); }

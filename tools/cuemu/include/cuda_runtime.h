@@ -180,13 +180,11 @@ inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ?
 inline const char* cudaGetErrorName(cudaError_t e) { return e == cudaSuccess ? "cudaSuccess" : "cudaErrorNotSupported"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { return *d = 0, cudaSuccess; }
-inline cudaError_t cudaMalloc(void** p, size_t bytes)
-{
-    *p = nullptr;
-    return posix_memalign(p, 256, bytes ? bytes : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
-}
+// CUEMU_IPC=1: allocations are POSIX shared-memory segments, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle work between the
+// processes of a multi-rank run (cuemu_runtime.cpp); otherwise plain aligned heap memory (which AddressSanitizer can guard).
+cudaError_t cudaMalloc(void** p, size_t bytes);
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc(reinterpret_cast<void**>(p), bytes); }
-inline cudaError_t cudaFree(void* p) { return free(p), cudaSuccess; }
+cudaError_t cudaFree(void* p);
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { return std::memcpy(d, s, n), cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { return std::memcpy(d, s, n), cudaSuccess; }
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t row, size_t rows, cudaMemcpyKind, cudaStream_t = nullptr)
@@ -212,8 +210,8 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 {
     return *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(), cudaSuccess;
 }
-inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { return *can = 0, cudaSuccess; }
-inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { return *can = std::getenv("CUEMU_IPC") ? 1 : 0, cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return std::getenv("CUEMU_IPC") ? cudaSuccess : cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void* p);

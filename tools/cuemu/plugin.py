@@ -134,6 +134,29 @@ def pytest_configure(config):
         def __exit__(self, *a):
             return False
 
+    class _DeviceCtx:                                             # torch.cuda.device(dev)
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    torch.cuda.device = _DeviceCtx
+    torch.cuda.can_device_access_peer = lambda a, b: bool(os.environ.get("CUEMU_IPC"))
+    _as_tensor = torch.as_tensor
+
+    def _as_tensor_host(obj, *a, **k):                            # strips.PeerSlab views its own allocation through __cuda_array_interface__
+        iface = getattr(obj, "__cuda_array_interface__", None)
+        if iface is not None:
+            return torch.frombuffer((C.c_uint8 * iface["shape"][0]).from_address(iface["data"][0]), dtype=torch.uint8)
+        if "device" in k and str(k["device"]).startswith("cuda"):
+            k["device"] = "cpu"
+        return _as_tensor(obj, *a, **k)
+
+    torch.as_tensor = _as_tensor_host
     _main = _Stream()
     torch.cuda.Event, torch.cuda.Stream, torch.cuda.stream = _Event, _Stream, _StreamCtx
     torch.cuda.current_stream = lambda *a, **k: _main
