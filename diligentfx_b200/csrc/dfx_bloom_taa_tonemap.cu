@@ -3,6 +3,12 @@
 //            PostProcess/TemporalAntiAliasing/src/TemporalAntiAliasing.cpp:260-289 + TAA_ComputeTemporalAccumulation.fx;
 //            Shaders/PostProcess/ToneMapping/public/ToneMapping.fxh; Hydrogent/shaders/HnPostProcess.psh:145-185, HnCopyFrame.psh:32-62.
 #include "dfx_common.cuh"
+#ifndef DFX_BLOOM_TMA
+#    define DFX_BLOOM_TMA 0
+#endif
+#if DFX_BLOOM_TMA
+#    include "dfx_tma.cuh"
+#endif
 
 namespace dfx
 {
@@ -140,20 +146,12 @@ constexpr int kDnCornW = 67, kDnCornH = 19; // texel corners inside that tile
 
 // B1 / B2 on an exact 2:1 level. Stage 1: the CTA stages the 68x20 source tile (out-of-range texels = 0: border addressing).
 // Stage 2: the 67x19 corner averages (each bilinear tap of the shader IS one corner average). Stage 3: 13 taps per output.
+// stages 2 and 3, from a staged source tile
 template <bool PREFILTER>
-__global__ void __launch_bounds__(256) bloom_down2x_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1)
+__device__ __forceinline__ void bloom_down2x_from_tile(const dfx_bloom_attribs& A, const float4 (&tile)[kDnTileH][kDnTileW], float4 (&corner)[kDnCornH][kDnCornW],
+                                                       View<float4> out, int ox0, int oy0, int y1)
 {
-    __shared__ float4 tile[kDnTileH][kDnTileW];
-    __shared__ float4 corner[kDnCornH][kDnCornW];
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    const int ox0 = blockIdx.x * 32, oy0 = y0 + blockIdx.y * 8;
-    const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;
-    for (int i = tid; i < kDnTileW * kDnTileH; i += 256)
-    {
-        const int ly = i / kDnTileW, lx = i - ly * kDnTileW;
-        tile[ly][lx] = load0(in, sx0 + lx, sy0 + ly);
-    }
-    __syncthreads();
     for (int i = tid; i < kDnCornW * kDnCornH; i += 256)
     {
         const int    ly = i / kDnCornW, lx = i - ly * kDnCornW;
@@ -200,6 +198,48 @@ __global__ void __launch_bounds__(256) bloom_down2x_kernel(dfx_bloom_attribs A, 
     const float contribution = fmaxf(soft, brightness - A.Threshold) * frcp(fmaxf(brightness, 1.0e-5f));
     out.at(x, y) = f4(c * contribution, 0.0f);
 }
+
+template <bool PREFILTER>
+__global__ void __launch_bounds__(256) bloom_down2x_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1)
+{
+    __shared__ float4 tile[kDnTileH][kDnTileW];
+    __shared__ float4 corner[kDnCornH][kDnCornW];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int ox0 = blockIdx.x * 32, oy0 = y0 + blockIdx.y * 8;
+    const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;
+    for (int i = tid; i < kDnTileW * kDnTileH; i += 256)
+    {
+        const int ly = i / kDnTileW, lx = i - ly * kDnTileW;
+        tile[ly][lx] = load0(in, sx0 + lx, sy0 + ly);
+    }
+    __syncthreads();
+    bloom_down2x_from_tile<PREFILTER>(A, tile, corner, out, ox0, oy0, y1);
+}
+
+#if DFX_BLOOM_TMA
+// The same pass with the source tile staged by ONE TMA 2-D tile load instead of 1360 predicated 128-bit loads (the north
+// star's prescription for the Bloom pyramid). The box starts at texel (2*ox0 - 2, 2*oy0 - 2); the parts of it that lie outside
+// the plane arrive as zeros, which is the border(0) addressing of these taps. Everything after the staging is shared with
+// bloom_down2x_kernel, so the two produce identical planes. Opt-in build (-DDFX_BLOOM_TMA=1): not yet timed on the GPU.
+template <bool PREFILTER>
+__global__ void __launch_bounds__(256) bloom_down2x_tma_kernel(dfx_bloom_attribs A, const __grid_constant__ CUtensorMap in_map, View<float4> out, int y0, int y1)
+{
+    __shared__ __align__(128) float4 tile[kDnTileH][kDnTileW];
+    __shared__ float4                corner[kDnCornH][kDnCornW];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int ox0 = blockIdx.x * 32, oy0 = y0 + blockIdx.y * 8;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0)
+    {
+        mbar_arrive_expect_tx(&bar, uint32_t(sizeof(tile)));
+        tma_load_2d(&tile[0][0], &in_map, 2 * (2 * ox0 - 2), 2 * oy0 - 2, &bar); // x in 64-bit elements: two per texel
+    }
+    mbar_wait(&bar, 0);
+    bloom_down2x_from_tile<PREFILTER>(A, tile, corner, out, ox0, oy0, y1);
+}
+#endif
 
 // B3 / B4 on an exact 1:2 level: the 3x3 tent of bilinear taps of the coarser level collapses to a separable 4-tap filter
 // whose weights depend only on the parity of the output coordinate:
@@ -661,6 +701,25 @@ using namespace dfx;
 
 #define DFX_GRID(w, rows) dim3 block(32, 8), grid(div_up(w, 32), div_up(rows.y1 - rows.y0, 8))
 
+#if DFX_BLOOM_TMA
+#    include <map>
+#    include <mutex>
+#    include <tuple>
+// Tensor maps of the planes the TMA variant has read so far (encoding one costs a driver call; a pyramid has a dozen planes).
+static const CUtensorMap* bloom_source_map(const View<const float4>& in)
+{
+    static std::mutex                                                              m;
+    static std::map<std::tuple<const void*, int, int, int>, CUtensorMap>           cache;
+    std::lock_guard<std::mutex>                                                    lk(m);
+    const auto                                                                     key = std::make_tuple(static_cast<const void*>(in.p), in.w, in.h, in.pitch);
+    auto                                                                           it  = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    CUtensorMap map;
+    if (!make_tensor_map_rgba32f(&map, in.p, in.w, in.h, size_t(in.pitch) * sizeof(float4), kDnTileW, kDnTileH)) return nullptr;
+    return &cache.emplace(key, map).first->second;
+}
+#endif
+
 static inline dfx_rows scale_rows(dfx_rows r, int full_h, int h)
 {
     // rows of a plane of height h that correspond to the full-frame strip r (h = full_h >> k)
@@ -683,6 +742,11 @@ extern "C" dfx_status dfx_pass_bloom_prefilter(void* stream, const dfx_bloom_att
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range (rows are in output-plane coordinates)");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
+#if DFX_BLOOM_TMA
+    if (const CUtensorMap* map = (in.w == 2 * out.w && in.h == 2 * out.h) ? bloom_source_map(in) : nullptr)
+        bloom_down2x_tma_kernel<true><<<grid, block, 0, as_stream(stream)>>>(*attribs, *map, out, rows.y0, rows.y1);
+    else
+#endif
     if (in.w == 2 * out.w && in.h == 2 * out.h)
         bloom_down2x_kernel<true><<<grid, block, 0, as_stream(stream)>>>(*attribs, in, out, rows.y0, rows.y1);
     else
@@ -700,6 +764,11 @@ extern "C" dfx_status dfx_pass_bloom_downsample(void* stream, const dfx_plane* i
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range (rows are in output-plane coordinates)");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
+#if DFX_BLOOM_TMA
+    if (const CUtensorMap* map = (in.w == 2 * out.w && in.h == 2 * out.h) ? bloom_source_map(in) : nullptr)
+        bloom_down2x_tma_kernel<false><<<grid, block, 0, as_stream(stream)>>>(dfx_bloom_attribs{}, *map, out, rows.y0, rows.y1);
+    else
+#endif
     if (in.w == 2 * out.w && in.h == 2 * out.h)
         bloom_down2x_kernel<false><<<grid, block, 0, as_stream(stream)>>>(dfx_bloom_attribs{}, in, out, rows.y0, rows.y1);
     else

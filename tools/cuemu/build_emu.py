@@ -91,6 +91,8 @@ def build(defines: list[str] | None = None, asan: bool = False) -> str:
     for f in os.listdir(CSRC):
         if f.endswith((".cu", ".cuh")):
             open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w").write(rewrite(open(os.path.join(CSRC, f)).read()))
+    # the TMA / mbarrier primitives are inline PTX: the host build uses its own statement of what they do
+    open(os.path.join(src_dir, "dfx_tma.cuh"), "w").write(open(os.path.join(HERE, "include", "dfx_tma_emu.cuh")).read())
     srcs = [os.path.join(src_dir, f.replace(".cu", ".cpp")) for f in product_build.SOURCES]
     out = LIB.replace(".so", "_asan.so") if asan else LIB      # --asan: every plane access of every kernel checked by AddressSanitizer
     cmd = ["g++", "-std=c++17", "-O1" if asan else "-O2", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", f"-I{os.path.join(HERE, 'include')}",

@@ -54,6 +54,8 @@ struct Block
     std::vector<std::vector<char>> stack;
     std::vector<char>              done;
     int                            current = -1;
+    int                            alive = 0, arrived = 0; // __syncthreads(): threads still running / threads waiting at the barrier
+    unsigned                       generation = 0;         // bumped when a barrier releases
     const std::function<void()>*   body = nullptr;
 };
 thread_local Block    t_block;
@@ -65,6 +67,7 @@ void thread_entry()
     const int i = b.current;
     (*b.body)();
     b.done[size_t(i)] = 1;
+    if (--b.alive > 0 && b.arrived >= b.alive) b.arrived = 0, ++b.generation; // a thread that has exited no longer holds a barrier up
     void* dead;
     cuemu_switch(&dead, b.sched_sp); // back to the scheduler for good
     __builtin_trap();
@@ -89,6 +92,7 @@ void run_block(dim3 grid, dim3 block, uint3 bidx, const std::function<void()>& b
     if (int(b.sp.size()) < n) b.sp.resize(size_t(n)), b.stack.resize(size_t(n));
     b.done.assign(size_t(n), 0);
     b.body = &body;
+    b.alive = n, b.arrived = 0;
     for (int i = 0; i < n; ++i) b.sp[size_t(i)] = fresh_stack(b.stack[size_t(i)]);
     // CUEMU_ORDER=reverse | shuffle: the order in which the threads of a block run between two barriers. Results must not
     // depend on it; if they do, a __syncthreads() is missing (or shared memory is read before it is written).
@@ -124,11 +128,25 @@ void run_block(dim3 grid, dim3 block, uint3 bidx, const std::function<void()>& b
 
 Builtins& builtins() { return t_builtins; }
 
+void yield()
+{
+    Block& b = t_block;
+    if (b.current < 0) return;
+    cuemu_switch(&b.sp[size_t(b.current)], b.sched_sp); // the scheduler resumes this thread in its next round
+}
+
+// Counting barrier (threads may also yield elsewhere, e.g. while polling an mbarrier, so "everybody has yielded" is not enough)
 void sync_threads()
 {
     Block& b = t_block;
     if (b.current < 0) return;
-    cuemu_switch(&b.sp[size_t(b.current)], b.sched_sp); // every thread that has not finished reaches the same barrier before anyone continues
+    const unsigned g = b.generation;
+    if (++b.arrived >= b.alive)
+    {
+        b.arrived = 0, ++b.generation;
+        return;
+    }
+    while (b.generation == g) yield();
 }
 
 // Persistent workers: the per-thread coroutine stacks (64 MB per worker) are allocated once, not per launch.

@@ -28,7 +28,8 @@
 #define __grid_constant__
 #define __shared__ static thread_local
 #define __constant__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
+inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
 
 // ---- built-in vector types (aggregates, like CUDA's) ----
 struct float2 { float x, y; };
@@ -66,6 +67,7 @@ struct Builtins
 };
 Builtins& builtins();
 void      sync_threads();
+void      yield(); // give the other threads of the block a turn (used by polling waits)
 void      launch(dim3 grid, dim3 block, const std::function<void()>& thread_body);
 } // namespace cuemu
 #define threadIdx (::cuemu::builtins().threadIdx)
