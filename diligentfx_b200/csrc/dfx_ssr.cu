@@ -4,6 +4,9 @@
 // The D16 stencil mask of the reference is an R8U plane here: 1 = reflection sample, 0 = masked out. Consumers that the
 // reference draws depth-tested against the mask simply skip masked pixels (their targets keep their previous content).
 #include "dfx_common.cuh"
+#ifndef DFX_INTERSECT_V2
+#    define DFX_INTERSECT_V2 0
+#endif
 
 namespace dfx
 {
@@ -318,6 +321,29 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         // from one 32-byte shared-memory entry, the level update is branch-free, the trip counter counts down.
         const float oxi = O.x * invD.x, oyi = O.y * invD.y, ozi = O.z * invD.z;
         int         left = (int)min(A.MaxTraversalIntersections, 0x7fffffffu);
+#if DFX_INTERSECT_V2
+        // Opt-in (-DDFX_INTERSECT_V2=1), same ray paths bit for bit, fewer instructions per step: the depth-plane crossing is
+        // switched off through its loop-invariant coefficients (surf * 0 + FLT_MAX is FLT_MAX exactly) instead of a select
+        // per step, and the level moves by min(mip + 1, 6) / mip - 1.
+        const bool  zOn = REV ? Dr.z < 0.0f : Dr.z > 0.0f;
+        const float rz = zOn ? invD.z : 0.0f, oz = zOn ? ozi : -kFltMax;
+        while (left > 0 && mip >= baseMip)
+        {
+            const HizLevel L  = lvl[mip];
+            const float    mx = L.resx * pos.x, my = L.resy * pos.y;
+            const float    surf = hiz_load(L, PT, (int)mx, (int)my, mip);
+            const float px = (floorf(mx) + fox) * L.irx + uox, py = (floorf(my) + foy) * L.iry + uoy;
+            const float tx = px * invD.x - oxi, ty = py * invD.y - oyi;
+            const float tz = surf * rz - oz;
+            const float tmin  = fminf(fminf(tx, ty), tz);
+            const bool  above = REV ? surf < pos.z : surf > pos.z;
+            const bool  skipped = (__float_as_uint(tmin) != __float_as_uint(tz)) && above;
+            t   = above ? tmin : t;
+            pos = O + t * Dr;
+            mip = skipped ? min(mip + 1, 6) : mip - 1;
+            --left;
+        }
+#else
         while (left > 0 && mip >= baseMip)
         {
             const HizLevel L  = lvl[mip];
@@ -335,6 +361,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
             mip += skipped ? (mip >= 6 ? 0 : 1) : -1; // a skip at the coarsest level stays there (:179-183)
             --left;
         }
+#endif
         validHit = true; // i <= MaxTraversalIntersections always holds at loop exit (:187)
     }
     const float3 hitVS = screen_to_view(pos.x, pos.y, pos.z, cam);
