@@ -143,7 +143,8 @@ def cpu_baseline(width: int, height: int, frames: int, threads: int) -> dict:
     mpix = width * height / 1e6 / (statistics.median(steady) / 1e3)
     return {"value": round(mpix, 3), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{len(steady)} consecutive {width}x{height} frames of the full chain (1/{(3840 * 2160) // (width * height)} of a 4K frame each), "
-                      f"median; scalar C++ oracle, row-parallel std::thread"}
+                      f"median; scalar C++ oracle (each pass bit-exact against the reference's own HLSL shader run on the CPU, "
+                      f"tests/test_reference_shaders.py), row-parallel std::thread"}
 
 
 def run_reference(args) -> None:
@@ -169,7 +170,9 @@ def run_reference(args) -> None:
             t += dt
     ms = t / args.steps
     value = w * h / 1e6 / (ms / 1e3)
-    sample = f"each step = one {w}x{h} frame of the full chain (1/{(args.width * args.height) // (w * h)} of the {args.width}x{args.height} workload)"
+    sample = (f"each step = one {w}x{h} frame of the full chain (1/{(args.width * args.height) // (w * h)} of the {args.width}x{args.height} workload); "
+              f"the oracle port, each pass bit-exact against the reference's own HLSL shader run on the CPU (tests/test_reference_shaders.py) - "
+              f"the shader runner itself (oracle/_ref) is a checker, several times slower, and is not what is timed")
     rec = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"full PostProcess chain, {args.width}x{args.height} synthetic G-buffer (bounded sample: {sample})"},
