@@ -172,7 +172,7 @@ def run_reference(args) -> None:
     value = w * h / 1e6 / (ms / 1e3)
     sample = (f"each step = one {w}x{h} frame of the full chain (1/{(args.width * args.height) // (w * h)} of the {args.width}x{args.height} workload); "
               f"the oracle port, each pass bit-exact against the reference's own HLSL shader run on the CPU (tests/test_reference_shaders.py) - "
-              f"the shader runner itself (oracle/_ref) is a checker, several times slower, and is not what is timed")
+              f"the shader runner itself (oracle/_ref) is a checker with about half the port's throughput and is not what is timed")
     rec = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"full PostProcess chain, {args.width}x{args.height} synthetic G-buffer (bounded sample: {sample})"},
