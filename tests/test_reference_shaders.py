@@ -37,7 +37,8 @@ def shaders(built):
 
 def _run(v: Variant, frames=None, warm: int = 2):
     seq = frames if frames is not None else synth.generate_sequence(W, H, warm + 1)
-    o = make_oracle(W, H, v)
+    h, w = seq[0]["depth"].shape
+    o = make_oracle(w, h, v)
     o.set_reversed_depth(v.reversed_depth)
     try:
         for fr in seq[:warm]:
@@ -57,7 +58,7 @@ def _check(res):
             d = np.abs(got.astype(np.float64) - want)
             if d.max() > tol or (d > 0).mean() > frac:
                 bad.append(f"{label}: max abs {d.max():.3e}, differing texels {(d > 0).mean():.3%}")
-        elif not np.array_equal(got, want):
+        elif not np.array_equal(np.ascontiguousarray(got).view(np.uint32), np.ascontiguousarray(want).view(np.uint32)):  # bit patterns: NaN == NaN
             d = np.abs(got.astype(np.float64) - want)
             bad.append(f"{label}: NOT bit-exact (max abs {d.max():.3e}, {(d > 0).mean():.3%} of values differ)")
     assert not bad, "oracle differs from the reference's shaders:\n  " + "\n  ".join(bad)
@@ -149,6 +150,41 @@ def test_bilateral_quad_derivatives_everywhere(shaders, size):
     got = np.zeros_like(want)
     refsh.run("ssr_bilateral", [depth, normal, rough, rad, var], [got], cbs=[fr["curr_camera"], ssr], mask=np.ones((h, w), np.uint8))
     assert np.array_equal(got, want), f"{(got != want).any(axis=2).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_random_configurations_bit_exact(shaders, trial):
+    """Random frame size, scene seed, feature flags, tone-map operator and attribute values (seeded): every pass of the third frame
+    must still equal its shader bit for bit."""
+    rng = np.random.default_rng(2024 + trial)
+    w, h = int(rng.integers(40, 220)), int(rng.integers(30, 130))
+    v = Variant(ssr_flags=int(rng.integers(0, 4)), ssao_flags=int(rng.integers(0, 4)), ssao_algorithm=int(rng.integers(0, 3)), taa_flags=int(rng.integers(0, 8)),
+                tonemap_mode=int(rng.integers(1, 12)), to_srgb=bool(rng.integers(0, 2)), dof=bool(rng.integers(0, 2)), dof_flags=int(rng.integers(0, 4)))
+    if v.ssr_flags == 3:
+        v.ssr_flags = 2                                   # the manifest builds previous-frame and half-resolution intersect separately
+    if v.ssao_algorithm:
+        v.ssao_flags = 0                                  # HBAO / VBAO are built for the full-resolution, full-precision path
+    if v.ssao_flags == 3:
+        v.ssao_flags = 2
+    v.ssr.MostDetailedMip, v.ssr.MaxTraversalIntersections = int(rng.integers(0, 3)), int(rng.integers(8, 200))
+    v.ssr.RoughnessThreshold, v.ssr.GGXImportanceSampleBias = float(rng.uniform(0.05, 0.6)), float(rng.uniform(0, 1))
+    v.ssr.SpatialReconstructionRadius, v.ssao.SpatialReconstructionRadius = float(rng.uniform(0, 6)), float(rng.uniform(0, 6))
+    v.ssao.EffectRadius, v.ssao.TemporalStabilityFactor = float(rng.uniform(0.2, 3)), float(rng.uniform(0, 1))
+    v.bloom.Threshold, v.bloom.Intensity, v.bloom.Radius = float(rng.uniform(0, 2)), float(rng.uniform(0, 1)), float(rng.uniform(0.5, 1.0))
+    v.taa.TemporalStabilityFactor, v.dof_attribs.MaxCircleOfConfusion = float(rng.uniform(0, 1)), float(rng.uniform(0.005, 0.03))
+    seq = synth.generate_sequence(w, h, 3, seed=int(rng.integers(1, 1000)))
+    if v.dof:
+        focus, fstop = float(rng.uniform(2, 12)), float(rng.uniform(1.2, 8))
+        lens = []
+        for f in seq:
+            g = dict(f)
+            for k in ("curr_camera", "prev_camera"):
+                c = capi.CameraAttribs.from_buffer_copy(bytes(f[k]))
+                c.fFocusDistance, c.fFStop = focus, fstop
+                g[k] = c
+            lens.append(g)
+        seq = lens
+    assert _check(_run(v, seq)) >= 40
 
 
 def test_brdf_table_bit_exact(shaders):
