@@ -1,5 +1,6 @@
 """Steps one frame through the oracle pass by pass and, beside every pass, runs the reference's own shader for that pass
-(oracle/refshader, the reference HLSL compiled for the CPU) on the SAME inputs. Test infrastructure only.
+(oracle/refshader, the reference HLSL compiled for the CPU) on the SAME inputs. Test infrastructure only: imported by tests/,
+tests/golden/make_reference_shader_golden.py and bench.py's `--impl reference` arm (which times the shader calls).
 
 compare_frame() returns an ordered {label: (reference_shader_output, oracle_output)}; the host-side sequencing (which plane
 feeds which pass, clears, history ping-pong, per-mip draws) is the oracle's restatement of the reference's .cpp files — what

@@ -25,7 +25,7 @@ OUT = os.path.join(HERE, "reference_shaders_49x27.npz")
 
 def configs():
     """(prefix, variant, frames): the benchmarked chain, and the chain with DepthOfField between TAA and Bloom."""
-    from refshader_driver import Variant
+    from oracle.refshader.driver import Variant
     seq = synth.generate_sequence(W, H, WARM + 1)
     a = capi.DOFAttribs.default()
     a.MaxCircleOfConfusion = 0.02
@@ -43,7 +43,7 @@ def configs():
 
 def run(with_reference: bool) -> dict:
     """{"<prefix>/<pass label>": plane}: reference-shader outputs (with_reference) or the oracle's outputs for the same passes."""
-    from refshader_driver import compare_frame, make_oracle
+    from oracle.refshader.driver import compare_frame, make_oracle
     out = {}
     for prefix, v, frames in configs():
         o = make_oracle(W, H, v)

@@ -46,4 +46,9 @@ def test_reference_arm_live(built):
     rec = json.loads(out[0])
     _check_common(rec)
     assert rec["impl"] == "reference" and rec["cpu_baseline"]["value"] == rec["value"]
+    # the reference's shaders compiled for the CPU where oracle/_ref exists ("reference"), else the oracle port; the port is always reported beside it
+    from oracle.refshader import refsh
+    assert rec["cpu_baseline"]["kind"] == ("reference" if refsh.available() else "port") and rec["port"]["value"] > 0
+    if rec["cpu_baseline"]["kind"] == "reference":
+        assert rec["value"] < rec["port"]["value"] * 1.5          # the checker-grade shader runner is not faster than the port by much, if at all
     assert rec["e2e"] == {"value": rec["value"], "unit": rec["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -18,7 +18,7 @@ import pytest
 from diligentfx_b200 import capi, synth
 from oracle.refshader import refsh
 
-from refshader_driver import Variant, compare_frame, make_oracle
+from oracle.refshader.driver import Variant, compare_frame, make_oracle
 
 W, H = 157, 89                                   # odd on both axes: the odd-size branches of every mip chain run
 TOLERATED = {"D8 dof_bokeh_first.near": (1e-3, 0.02), "D8 dof_bokeh_first.far": (1e-3, 0.02)}   # (max abs, max fraction of texels that differ)
