@@ -21,8 +21,9 @@ Lines of the JSON record (one line on stdout, rank 0):
                 (each pass alone on one stream), against MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s,
                 B200_PROFILING.md); `traffic` = DRAM bytes per launch from the committed ncu capture. `passes` lists every pass.
   cpu_baseline  the oracle (scalar C++ port of the Shaders/PostProcess math) on this box's host cores, bounded sample.
-  --impl reference: the same metric from the oracle alone (the reference has no CPU implementation and cannot be built
-                here: DiligentCore + HLSL compiler + graphics device are required — DESIGN.md).
+  --impl reference: the same metric from the reference's own pixel shaders compiled for the CPU (oracle/_ref, built from the HLSL
+                sources by oracle/refshader; time inside the shader calls, all host cores), with the oracle port's number beside it
+                in `port`; the port alone where oracle/_ref is absent. (The reference's C++ cannot be built here: DESIGN.md §2.)
 """
 from __future__ import annotations
 
