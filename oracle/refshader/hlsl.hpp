@@ -17,7 +17,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <ucontext.h>
 #include <vector>
@@ -470,18 +473,63 @@ template <class T = float4> struct TextureCube
 };
 
 // ---- the full-screen pass: one pixel-shader invocation per target pixel, rows split over host threads ----
+// A persistent pool (one per library: an inline function's static object is shared by all translation units of the .so), rows
+// handed out in small chunks, so that a pass costs no thread creation - with 128 host cores and ~80 passes per frame, creating
+// the threads per pass would cost more than shading the pixels.
+struct row_pool
+{
+    std::mutex                                m;
+    std::condition_variable                   cv_work, cv_done;
+    std::vector<std::thread>                  workers;
+    const std::function<void(int, int)>*      fn = nullptr;
+    std::atomic<int>                          next{0};
+    int                                       height = 0, chunk = 1, active = 0, pending = 0;
+    unsigned long long                        generation = 0;
+
+    explicit row_pool(int n)
+    {
+        for (int w = 0; w < n; ++w)
+            workers.emplace_back([this, w] {
+                unsigned long long seen = 0;
+                for (;;)
+                {
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv_work.wait(lk, [&] { return generation != seen; });
+                        seen = generation;
+                    }
+                    if (w < active)
+                        for (int y = next.fetch_add(chunk); y < height; y = next.fetch_add(chunk)) (*fn)(y, std::min(height, y + chunk));
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) cv_done.notify_one();
+                    }
+                }
+            });
+        for (auto& t : workers) t.detach();
+    }
+    void run(int h, int threads, const std::function<void(int, int)>& f)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        fn = &f, height = h, chunk = std::max(1, h / (4 * threads)), active = threads, pending = int(workers.size());
+        next = 0, ++generation;
+        cv_work.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+inline row_pool& the_row_pool()
+{
+    static row_pool* p = new row_pool(int(std::max(1u, std::thread::hardware_concurrency())));
+    return *p;
+}
 inline void for_rows(int height, int threads, const std::function<void(int, int)>& fn)
 {
-    if (threads <= 1 || height < 2 * threads) return fn(0, height);
-    std::vector<std::thread> pool;
-    const int                chunk = (height + threads - 1) / threads;
-    for (int t = 0; t < threads; ++t)
-    {
-        const int a = t * chunk, b = std::min(height, a + chunk);
-        if (a >= b) break;
-        pool.emplace_back(fn, a, b);
-    }
-    for (auto& th : pool) th.join();
+    static std::mutex           one_pass_at_a_time;
+    row_pool&                   pool = the_row_pool();
+    threads = std::min(threads, int(pool.workers.size()));
+    if (threads <= 1 || height < 8) return fn(0, height);
+    std::lock_guard<std::mutex> lk(one_pass_at_a_time);
+    pool.run(height, threads, fn);
 }
 
 // ---- 2x2 quads in lockstep, for ddx / ddy: each of the four lanes is a coroutine on its own stack. Lane l shades pixel
