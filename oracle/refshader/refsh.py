@@ -1,7 +1,8 @@
 """REFERENCE-SHADER RUNNER — TEST INFRASTRUCTURE ONLY. ctypes wrapper over oracle/_ref/librefshaders.so.
 
-The library holds the reference's own pixel shaders compiled for the CPU (build_ref.py). Importers: tests/ and
-tests/golden/make_reference_shader_golden.py. Never the product path, never bench.py's timed legs.
+The library holds the reference's own pixel shaders compiled for the CPU (build_ref.py). Importers: tests/,
+tests/golden/make_reference_shader_golden.py and bench.py's `--impl reference` arm (the CPU baseline: it times these shaders).
+Never the product path.
 """
 from __future__ import annotations
 
