@@ -148,6 +148,47 @@ def cpu_baseline(width: int, height: int, frames: int, threads: int) -> dict:
                       f"tests/test_reference_shaders.py), row-parallel std::thread"}
 
 
+def psnr_vs_oracle(seq, W: int, H: int, threads: int) -> dict:
+    """The metric's "PSNR vs ref" half: a FRESH chain and a fresh oracle both run the `len(seq)` consecutive frames of `seq`
+    (frame 0 resets every history) at the benchmarked size; the last frame's planes are compared. LDR and AO: peak 1; HDR
+    planes after Reinhard c/(1+c). Runs after the timed regions; the oracle here is the checker."""
+    import numpy as np
+    from diligentfx_b200.chain import PostProcessChain
+    from oracle import oracle_py as op
+
+    def psnr(a, b):
+        mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+        return 200.0 if mse == 0.0 else round(10.0 * np.log10(1.0 / mse), 2)
+
+    def rh(x):
+        x = np.maximum(np.nan_to_num(np.asarray(x, np.float64), nan=0.0, posinf=1e30), 0.0)
+        return x / (1.0 + x)
+
+    t0 = time.perf_counter()
+    chain = PostProcessChain(W, H)          # the benchmarked configuration: fused passes, async compute
+    o = op.Oracle(W, H, threads=threads)
+    for fr in seq:
+        ldr = chain.run_frame(fr)
+        o.set_inputs(fr)
+        o.frame()
+    cur = seq[-1]["frame"] & 1
+    got = ldr.cpu().numpy()
+    want = o.get("ldr")
+    out = {"ldr": psnr(np.clip(got[..., :3], 0, 1), np.clip(want[..., :3], 0, 1)),
+           "ssao": psnr(chain.fetch("ssao", 0), o.get("ssao_out")),
+           "ssr": psnr(rh(chain.fetch("ssr", 0)), rh(o.get("ssr_out"))),
+           "taa": psnr(rh(chain.fetch("taa", 0)), rh(o.get(f"taa_accum{cur}"))),
+           "bloom_up0": psnr(rh(chain.fetch("bloom", 30)[..., :3]), rh(o.get("bloom_up0")[..., :3])),
+           "ldr_max_abs_err": float(np.abs(np.clip(got[..., :3], 0, 1) - np.clip(want[..., :3], 0, 1)).max()),
+           "frames": len(seq), "size": [W, H], "floor_db": 49.0,
+           "against": "the CPU oracle (each pass bit-exact against the reference's own HLSL shader, tests/test_reference_shaders.py), fp32 storage",
+           "seconds": None}
+    out["pass"] = bool(out["ldr"] >= 49.0)
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    chain.close()
+    return out
+
+
 def _time_reference_shaders(seq, w: int, h: int, warmup: int, steps: int):
     """Seconds per frame spent inside the reference's own pixel shaders (oracle/_ref/librefshaders.so: the HLSL sources compiled
     for the CPU, every pass of the chain, all host cores), or None where that library is not available. The shaders are fed
@@ -244,6 +285,7 @@ def main() -> None:
     ap.add_argument("--ref-width", type=int, default=960)
     ap.add_argument("--ref-height", type=int, default=540)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-psnr", action="store_true", help="skip the PSNR-vs-oracle leg (4 frames of the CPU oracle at the benchmarked size)")
     ap.add_argument("--no-overlap", action="store_true", help="run every pass on one stream (no async compute)")
     ap.add_argument("--dof", action="store_true", help="add DepthOfField between TAA and Bloom (NOT the BASELINE.json workload; config.workload says so)")
     args = ap.parse_args()
@@ -409,6 +451,9 @@ def main() -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ref_width, args.ref_height, 3, os.cpu_count() or 1)
+    quality = None
+    if rank == 0 and not args.no_psnr:
+        quality = psnr_vs_oracle([{**fr, "frame": i} for i, fr in enumerate(seq)], W, H, os.cpu_count() or 1)
 
     if rank == 0:
         rec = {
@@ -429,7 +474,7 @@ def main() -> None:
                                "packed=True): copy-in / compute / copy-out pipelined on 3 streams",
                     "fp32_transfers": {"value": round(e2e32_value, 2), "ms_per_step": round(e2e32_ms, 4), "h2d_bytes_per_step": int(h2d_bytes_fp32),
                                        "d2h_bytes_per_step": int(d2h_bytes_fp32)}},
-            "roofline": roof, "cpu_baseline": cpu, "passes": passes,
+            "psnr": quality, "roofline": roof, "cpu_baseline": cpu, "passes": passes,
         }
         print(json.dumps(rec), flush=True)
     chain.close()
