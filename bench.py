@@ -62,12 +62,24 @@ PASS_BYTES_PER_PX = {
     "compose": 52.0, "taa": 64.0,
     "compose_taa": 84.0,                 # fused: colour 16 + ssr 16 + ao 4 + history 16 + motion 8 + depths 8 in, accumulation 16 out
     "bloom_composite_tonemap": 36.0,     # fused: colour 16 + up[0] 4 in, LDR 16 out
-    "bloom_prefilter": 20.0, "bloom_downsample": 6.67, "bloom_upsample": 12.0, "bloom_composite": 36.0,
+    "bloom_prefilter": 20.0, "bloom_downsample": 6.67, "bloom_upsample": 12.0, "bloom_composite": 36.0, "bloom_tail": 0.0,   # pyramid entries: see bloom_bytes()
     "tonemap": 32.0,
     # DepthOfField (--dof only): CoC planes 4 B/px, half-size colour planes 16 B per quarter pixel
     "dof_coc": 8.0, "dof_temporal_coc": 20.0, "dof_separated_coc": 8.0, "dof_dilation": 6.6, "dof_blur_coc": 0.25, "dof_prefilter": 28.0,
     "dof_bokeh_first": 16.0, "dof_bokeh_second": 16.0, "dof_postfilter": 16.0, "dof_combine": 40.0,
 }
+
+
+def bloom_bytes(W: int, H: int, mips: int, first: int) -> dict:
+    """Exact algorithmic bytes of the Bloom pyramid passes from the level sizes (16 B texels): B2 per-level launches cover the levels
+    1 .. first-1, the tail launch the levels first .. mips-1 down and mips-2 .. first-1 up, B3 per-level launches the levels first-2 .. 0."""
+    lv = [(max((W // 2) >> i, 1), max((H // 2) >> i, 1)) for i in range(mips)]
+    b = [16 * w * h for w, h in lv]
+    top = mips - 1
+    down = sum(b[i - 1] + b[i] for i in range(1, first))
+    tail = b[first - 1] + sum(b[first:mips]) + sum(b[first - 1:top]) if first < mips else 0
+    up = sum(2 * b[i - 1] + b[i] for i in range(min(top, first - 1), 0, -1))       # reads down[i-1] + coarser level, writes up[i-1]
+    return {"bloom_downsample": float(down), "bloom_tail": float(tail), "bloom_upsample": float(up)}
 
 
 def measured_hbm_peak() -> tuple[float, str]:
@@ -427,13 +439,16 @@ def main() -> None:
         lib.dfx_profile_enable(0)
         capi.check(lib.dfx_profile_collect())
         name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
+        bloom_mips = lib.dfx_bloom_mip_count(W // 2, H // 2, C.c_float(chain.cfg.bloom.Radius))
+        bloom_first = next((i for i in range(1, bloom_mips) if max((W // 2) >> i, 1) * max((H // 2) >> i, 1) <= 16384), bloom_mips)
+        pyramid_bytes = bloom_bytes(W, H, bloom_mips, bloom_first if lib.dfx_tune_get(b"bloom_tail", 1) else bloom_mips)
         step_sum = 0.0
         for i in range(lib.dfx_profile_count()):
             capi.check(lib.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls)))
             nm = name.value.decode()
             ms = tot.value / K                                  # per step (a pass may launch several kernels / levels)
             step_sum += ms
-            by = PASS_BYTES_PER_PX.get(nm, 0.0) * W * H
+            by = pyramid_bytes.get(nm, PASS_BYTES_PER_PX.get(nm, 0.0) * W * H)
             gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             passes.append({"pass": nm, "ms": round(ms, 4), "launch_groups_per_step": calls.value // K, "alg_bytes": int(by), "GBps": round(gbs, 1),
                            "frac": round(gbs / peak, 4)})
@@ -443,7 +458,7 @@ def main() -> None:
         traffic, traffic_src = ncu_traffic(top["pass"], W, H)
         roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
                 "traffic_source": traffic_src, "alg_bytes": top["alg_bytes"], "peak_source": peak_src, "share_of_step": top["share"],
-                "chain": {"alg_bytes_per_px": round(sum(PASS_BYTES_PER_PX.get(p["pass"], 0.0) for p in passes), 2),
+                "chain": {"alg_bytes_per_px": round(sum(p["alg_bytes"] for p in passes) / (W * H), 2),
                           "achieved": round(sum(p["alg_bytes"] for p in passes) / (ms_per_step * 1e-3) / 1e9, 1)}}
         roof["chain"]["frac"] = round(roof["chain"]["achieved"] / peak, 4)
 

@@ -7,6 +7,9 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <map>
+#include <mutex>
+#include <cstdlib>
 
 namespace dfx
 {
@@ -287,6 +290,44 @@ dfx_status dfx_profile_collect(void)
     g_records.clear();
     return DFX_OK;
 }
+// ---- implementation switches (A/B measurements) ----------------------------------------------------------------------
+static std::mutex                 g_tune_mutex;
+static std::map<std::string, int> g_tune;
+static bool                       g_tune_env_read = false;
+static void tune_read_env()
+{
+    if (g_tune_env_read) return;
+    g_tune_env_read = true;
+    const char* e = getenv("DFX_TUNE");
+    if (!e) return;
+    std::string s(e);
+    size_t      pos = 0;
+    while (pos < s.size())
+    {
+        size_t end = s.find(',', pos);
+        if (end == std::string::npos) end = s.size();
+        const std::string kv = s.substr(pos, end - pos);
+        const size_t      eq = kv.find('=');
+        if (eq != std::string::npos) g_tune.emplace(kv.substr(0, eq), atoi(kv.c_str() + eq + 1));
+        pos = end + 1;
+    }
+}
+void dfx_tune_set(const char* name, int32_t value)
+{
+    if (!name) return;
+    std::lock_guard<std::mutex> lk(g_tune_mutex);
+    tune_read_env();
+    g_tune[name] = value;
+}
+int32_t dfx_tune_get(const char* name, int32_t fallback)
+{
+    if (!name) return fallback;
+    std::lock_guard<std::mutex> lk(g_tune_mutex);
+    tune_read_env();
+    auto it = g_tune.find(name);
+    return it == g_tune.end() ? fallback : it->second;
+}
+
 void    dfx_profile_reset(void) { dfx_profile_collect(), g_entries.clear(); }
 int32_t dfx_profile_count(void) { return (int32_t)g_entries.size(); }
 dfx_status dfx_profile_entry(int32_t i, char* name, int32_t name_cap, double* total_ms, int32_t* calls)

@@ -548,13 +548,19 @@ static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attri
     DFX_REQUIRE(mips >= 2, "Bloom radius %.3f leaves fewer than two pyramid levels", A.Radius);
     auto rows = [](const dfx_plane& p) { return dfx_rows{0, p.height}; };
     dfx_status st;
-    if ((st = dfx_pass_bloom_prefilter(s, &A, a->color, &fx->down[0].p, rows(fx->down[0].p))) != DFX_OK) return st;
-    for (int i = 1; i < mips; ++i)
-        if ((st = dfx_pass_bloom_downsample(s, &fx->down[i - 1].p, &fx->down[i].p, rows(fx->down[i].p))) != DFX_OK) return st;
+    // The reference draws one level per pass (Bloom.cpp:324-337 down, :355-375 up). Here the large levels are one launch each
+    // and every level from `first` on (<= 16K texels) is handled, down and up again, by one cluster launch (dfx_pass_bloom_tail).
+    dfx_plane down[DFX_BLOOM_MAX_LEVELS], up[DFX_BLOOM_MAX_LEVELS];
+    DFX_REQUIRE(mips <= DFX_BLOOM_MAX_LEVELS, "too many Bloom levels");
+    for (int i = 0; i < mips; ++i) down[i] = fx->down[i].p, up[i] = fx->up[i].p;
+    const int first = dfx_bloom_tail_first_level(down, mips);
+    if ((st = dfx_pass_bloom_prefilter(s, &A, a->color, &down[0], rows(down[0]))) != DFX_OK) return st;
+    for (int i = 1; i < first; ++i)
+        if ((st = dfx_pass_bloom_downsample(s, &down[i - 1], &down[i], rows(down[i]))) != DFX_OK) return st;
+    if (first < mips && (st = dfx_pass_bloom_tail(s, down, up, first, mips)) != DFX_OK) return st;
     const int top = mips - 1;
-    for (int i = top; i > 0; --i)
-        if ((st = dfx_pass_bloom_upsample(s, &fx->down[i - 1].p, i != top ? &fx->up[i].p : &fx->down[i].p, &fx->up[i - 1].p, rows(fx->up[i - 1].p))) != DFX_OK)
-            return st;
+    for (int i = std::min(top, first - 1); i > 0; --i)
+        if ((st = dfx_pass_bloom_upsample(s, &down[i - 1], i != top ? &up[i] : &down[i], &up[i - 1], rows(up[i - 1]))) != DFX_OK) return st;
     if (tonemap)
     {
         const dfx_plane& u0 = fx->up[0].p;

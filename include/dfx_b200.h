@@ -427,6 +427,15 @@ DFX_API dfx_status dfx_pass_bloom_upsample(void* stream, const dfx_plane* same_l
 DFX_API dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_attribs* attribs,
                                             const dfx_plane* color, const dfx_plane* up0, const dfx_plane* out, dfx_rows rows);
 
+/* B2 for the levels first .. mips-1 followed by B3 for the levels mips-2 .. first-1, in ONE launch of one thread-block cluster
+ * (the reference issues one draw per level, Bloom.cpp:324-337 and :355-375; on the small levels of the pyramid those dependent
+ * launches cost more than the work). `down` / `up` are arrays of `mips` planes (level i = max(level0 >> i, 1)); reads
+ * down[first-1], writes down[first..mips-1] and up[first-1..mips-2]. Results are bit-identical to the per-level passes.
+ * dfx_bloom_tail_first_level: the level the effect object hands over to this pass (first one with <= 16384 texels; `mips` = none). */
+#define DFX_BLOOM_MAX_LEVELS 16
+DFX_API dfx_status dfx_pass_bloom_tail(void* stream, const dfx_plane* down, const dfx_plane* up, int32_t first, int32_t mips);
+DFX_API int32_t    dfx_bloom_tail_first_level(const dfx_plane* down, int32_t mips);
+
 /* T1 ComputeTemporalAccumulation (TemporalAntiAliasing.cpp:260-289; TAA_ComputeTemporalAccumulation.fx:229-261). */
 DFX_API dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs,
                                 uint32_t flags, const dfx_plane* curr_color, const dfx_plane* prev_accum,
@@ -511,6 +520,11 @@ DFX_API dfx_status dfx_pass_bloom_composite_tonemap(void* stream, const dfx_bloo
 DFX_API void dfx_taa_jitter_offset(uint32_t frame_index, uint32_t width, uint32_t height, float out_jitter[2]);
 /* Bloom::ComputeMipCount (Bloom.cpp:152-156) applied to the half-resolution level-0 size. */
 DFX_API int32_t dfx_bloom_mip_count(uint32_t width, uint32_t height, float radius);
+
+/* Implementation switches for A/B measurements (tools/, bench.py --tune): every value of a knob computes the same pass, through a
+ * different kernel. Unknown names read as `fallback`. Also settable at load time: DFX_TUNE="name=value,name=value". */
+DFX_API void    dfx_tune_set(const char* name, int32_t value);
+DFX_API int32_t dfx_tune_get(const char* name, int32_t fallback);
 
 /* ============================================================================================================ */
 /* 2. effect level                                                                                              */

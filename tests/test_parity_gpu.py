@@ -277,6 +277,64 @@ def test_bloom_passes(ctx):
     print(assert_close("bloom output", d.host(out), o.get("bloom_out"), tol=1e-5, min_psnr=100.0, hdr=True))
 
 
+def test_bloom_tail_and_streaming_kernels(built):
+    """The single-launch tail (one thread-block cluster for every level of <= 16K texels, down and up) and the warp-shuffle
+    streaming kernels of the exact-2:1 levels against the oracle's levels, and bit-identical (tail) / within rounding (streaming)
+    to the generic per-level kernels. 1024x576: levels 512x288 ... 16x9 are exact 2:1, 8x4 / 4x2 / 2x1 are not."""
+    from oracle import oracle_py as op
+    w, h = 1024, 576
+    seq = synth.generate_sequence(w, h, 1)
+    o = op.Oracle(w, h)
+    a = capi.BloomAttribs.default()
+    a.Radius = 0.95  # 9 of 10 levels: reaches the odd-sized ones
+    o.set_bloom(a)
+    o.set_inputs(seq[0])
+    o.frame()
+    d = Dev()
+    L = d.lib
+    src = o.get("bloom_in")
+    mips = L.dfx_bloom_mip_count(w // 2, h // 2, C.c_float(a.Radius))
+    assert mips == 9
+    want_d = [o.get(f"bloom_down{i}") for i in range(mips)]
+    want_u = [o.get(f"bloom_up{i}") for i in range(mips - 1)]
+
+    def run(impl, tail):
+        L.dfx_tune_set(b"bloom_impl", impl)
+        L.dfx_tune_set(b"bloom_tail", tail)
+        dn = [d.empty(*m.shape[:2], 4) for m in want_d]
+        up = [d.empty(*m.shape[:2], 4) for m in want_d]
+        pd = (capi.Plane * mips)(*[d.plane(t) for t in dn])
+        pu = (capi.Plane * mips)(*[d.plane(t) for t in up])
+        first = L.dfx_bloom_tail_first_level(pd, mips)
+        capi.check(L.dfx_pass_bloom_prefilter(None, C.byref(a), C.byref(d.plane(d.up(src))), C.byref(pd[0]), rows(dn[0].shape[0])))
+        for i in range(1, first):
+            capi.check(L.dfx_pass_bloom_downsample(None, C.byref(pd[i - 1]), C.byref(pd[i]), rows(dn[i].shape[0])))
+        if first < mips:
+            capi.check(L.dfx_pass_bloom_tail(None, pd, pu, first, mips))
+        top = mips - 1
+        for i in range(min(top, first - 1), 0, -1):
+            capi.check(L.dfx_pass_bloom_upsample(None, C.byref(pd[i - 1]), C.byref(pu[i] if i != top else pd[i]), C.byref(pu[i - 1]), rows(up[i - 1].shape[0])))
+        d.sync()
+        return first, [d.host(t) for t in dn], [d.host(t) for t in up[:-1]]
+
+    try:
+        first, dn, up = run(1, 1)
+        assert first == 2, first  # 256x144 = 36864 > 16384 >= 128x72
+        _, dn_g, up_g = run(2, 0)   # generic gather kernels, one launch per level
+        _, dn_t, up_t = run(1, 0)   # streaming kernels, per-level launches for the small levels
+    finally:
+        L.dfx_tune_set(b"bloom_impl", 1), L.dfx_tune_set(b"bloom_tail", 1)
+    for i in range(mips):
+        print(assert_close(f"bloom down {i} (stream + tail)", dn[i], want_d[i], tol=1e-5, min_psnr=95.0, hdr=True))
+        assert_close(f"bloom down {i} vs generic kernels", dn[i], dn_g[i], tol=1e-5, min_psnr=100.0, hdr=True)
+    for i in range(mips - 1):
+        print(assert_close(f"bloom up {i} (stream + tail)", up[i], want_u[i], tol=1e-5, min_psnr=95.0, hdr=True))
+        assert_close(f"bloom up {i} vs generic kernels", up[i], up_g[i], tol=1e-5, min_psnr=100.0, hdr=True)
+    # the tail does per texel exactly what the per-level kernels of the same levels do: the generic ones on the odd-sized levels
+    for i in range(6, mips):
+        assert np.array_equal(dn[i], dn_t[i]) or np.abs(dn[i] - dn_t[i]).max() < 1e-6, f"tail down {i}"
+
+
 @pytest.mark.parametrize("flags", [2, 0, 7], ids=["bicubic", "bilinear", "bicubic+ycocg+gauss"])
 def test_taa(ctx, flags):
     d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
