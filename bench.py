@@ -299,6 +299,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-psnr", action="store_true", help="skip the PSNR-vs-oracle leg (4 frames of the CPU oracle at the benchmarked size)")
     ap.add_argument("--no-overlap", action="store_true", help="run every pass on one stream (no async compute)")
+    ap.add_argument("--no-graph", action="store_true", help="issue every frame eagerly (no CUDA-graph replay)")
     ap.add_argument("--dof", action="store_true", help="add DepthOfField between TAA and Bloom (NOT the BASELINE.json workload; config.workload says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -351,7 +352,7 @@ def main() -> None:
         for cp in cams:
             for c in cp:
                 c.fFocusDistance, c.fFStop = 6.0, 1.4
-    chain = PostProcessChain(W, H, ChainConfig(overlap=not args.no_overlap, dof=dof, dof_flags=capi.DOF_FLAG_TEMPORAL_SMOOTHING if dof else 0), device=dev)
+    chain = PostProcessChain(W, H, ChainConfig(overlap=not args.no_overlap, graph=not args.no_graph, dof=dof, dof_flags=capi.DOF_FLAG_TEMPORAL_SMOOTHING if dof else 0), device=dev)
     ldr_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     ldr8_hosts = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
     d2h_bytes, d2h_bytes_fp32 = ldr8_hosts[0].numel(), ldr_host.numel() * 4
@@ -413,6 +414,7 @@ def main() -> None:
     launches0 = lib.dfx_launch_count()
     total_ms = timed(run_resident, K)
     launches = lib.dfx_launch_count() - launches0
+    issue = chain.stats()
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / K
     value = world * W * H / 1e6 / (ms_per_step / 1e3)
@@ -480,6 +482,9 @@ def main() -> None:
                        "width": W, "height": H, "parallelism": f"replicas x{world} (independent frame sequences, no data-path collective)",
                        "streams": ("3 per GPU: SSR chain + TAA | SSAO chain | Bloom + ToneMap (overlaps the next frame's front half); per-pass times in `passes` are "
                                    "measured serially on one stream" if chain.cfg.overlap else "1 per GPU"),
+                       "issue": {**issue, "what": "frames replayed from CUDA graphs (steady state) vs issued eagerly, since the chain was created; "
+                                                  "1 native call (dfx_chain_execute) per frame either way"},
+                       "tune": os.environ.get("DFX_TUNE", ""),
                        "cache": f"{args.frames} distinct resident G-buffers of {h2d_bytes_fp32 / 1e6:.0f} MB cycled: inputs larger than the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),

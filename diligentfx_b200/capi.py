@@ -169,6 +169,28 @@ class DOFRenderAttribs(C.Structure):
 
 
 assert C.sizeof(DOFAttribs) == 32
+
+
+class ChainConfigC(C.Structure):
+    """dfx_chain_config (include/dfx_b200.h, chain level)."""
+    _fields_ = [("ssao", SSAOAttribs), ("ssr", SSRAttribs), ("bloom", BloomAttribs), ("taa", TAAAttribs), ("tonemap", ToneMapAttribs), ("dof", DOFAttribs),
+                ("postfx_flags", C.c_uint32), ("ssao_flags", C.c_uint32), ("ssr_flags", C.c_uint32), ("taa_flags", C.c_uint32), ("dof_flags", C.c_uint32),
+                ("stages", C.c_uint32), ("enable_dof", C.c_int32), ("fuse", C.c_int32), ("overlap", C.c_int32), ("use_graph", C.c_int32), ("to_srgb", C.c_int32),
+                ("ave_log_lum", C.c_float), ("ssr_scale", C.c_float), ("ssao_scale", C.c_float), ("reserved", C.c_int32)]
+
+
+class ChainFrame(C.Structure):
+    """dfx_chain_frame."""
+    _fields_ = [("frame_index", C.c_uint32), ("defer_post", C.c_int32), ("curr_camera", C.POINTER(CameraAttribs)), ("prev_camera", C.POINTER(CameraAttribs)),
+                ("depth", C.POINTER(Plane)), ("prev_depth", C.POINTER(Plane)), ("motion", C.POINTER(Plane)), ("normal", C.POINTER(Plane)),
+                ("color", C.POINTER(Plane)), ("material", C.POINTER(Plane)), ("ldr_out", C.POINTER(Plane))]
+
+
+class ChainStats(C.Structure):
+    _fields_ = [("frames_eager", C.c_uint64), ("frames_replayed", C.c_uint64), ("graphs_built", C.c_uint64), ("graph_failures", C.c_uint64)]
+
+
+CHAIN_EFFECT = {"postfx": 0, "ssao": 1, "ssr": 2, "bloom": 3, "taa": 4, "dof": 5}
 assert C.sizeof(CameraAttribs) == 576 and C.sizeof(SSAOAttribs) == 48 and C.sizeof(SSRAttribs) == 48
 assert C.sizeof(BloomAttribs) == 32 and C.sizeof(TAAAttribs) == 16 and C.sizeof(ToneMapAttribs) == 48
 
@@ -199,6 +221,8 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.dfx_launch_count.restype = C.c_uint64
     lib.dfx_postfx_get_camera_attribs_dev.restype = C.c_void_p
     lib.dfx_bloom_mip_count.restype = C.c_int32
+    lib.dfx_chain_effect.restype = C.c_void_p
+    lib.dfx_chain_post_stream.restype = C.c_void_p
     for name in declared_symbols():
         if not hasattr(lib, name):
             raise DfxError(f"libdfx_b200.so does not export {name}")

@@ -1,9 +1,10 @@
-"""Host-side driver of the full PostProcess chain over the effect-level C-ABI.
+"""Python view of the chain-level C-ABI (`dfx_chain_*`): the full PostProcess chain of one view, one native call per frame.
 
-Mirrors the reference integration `HnPostProcessTask` (Hydrogent/src/Tasks/HnPostProcessTask.cpp): Prepare (:591-683)
-creates / prepares PostFXContext, SSR, SSAO, TAA, Bloom every frame; Execute (:743-947) runs
-PostFX -> SSR -> SSAO -> compose -> TAA -> Bloom -> ToneMap(+sRGB). All arithmetic happens in libdfx_b200.so; this
-module only sequences calls and owns the input/output device planes (torch is used for device memory and streams).
+The native executor mirrors the reference integration `HnPostProcessTask` (Hydrogent/src/Tasks/HnPostProcessTask.cpp): Prepare
+(:591-683) prepares PostFXContext, SSR, SSAO, TAA, Bloom every frame; Execute (:743-947) runs
+PostFX -> SSR -> SSAO -> compose -> TAA -> Bloom -> ToneMap(+sRGB). Sequencing, async-compute streams and CUDA-graph replay live
+in libdfx_b200.so (csrc/dfx_effects.cu); this module owns the input / output device planes (torch tensors) and the host <->
+device streaming pipeline of `stream_frames` (torch streams and events).
 """
 from __future__ import annotations
 
@@ -14,8 +15,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .capi import (BloomAttribs, BloomRenderAttribs, FrameDesc, Plane, PostFXRenderAttribs, Rows, SSAOAttribs, SSAORenderAttribs, SSRAttribs,
-                   SSRRenderAttribs, TAAAttribs, TAARenderAttribs, ToneMapAttribs, check, plane_of)
+from .capi import BloomAttribs, Plane, Rows, SSAOAttribs, SSRAttribs, TAAAttribs, ToneMapAttribs, check, plane_of
 
 STAGE_POSTFX, STAGE_SSR, STAGE_SSAO, STAGE_COMPOSE, STAGE_TAA, STAGE_BLOOM, STAGE_TONEMAP = 1, 2, 4, 8, 16, 32, 64
 STAGE_ALL = 127
@@ -91,10 +91,14 @@ class ChainConfig:
     stages: int = STAGE_ALL
     fuse: bool = True          # compose inside TAA, ToneMap inside the Bloom composite (same per-pixel arithmetic, two HBM round trips fewer)
     overlap: bool = True       # async compute: SSAO beside SSR on a second stream, Bloom + ToneMap beside the NEXT frame's front half on a third
+    graph: bool = True         # replay steady-state frames from CUDA graphs (dfx_chain_config.use_graph)
 
 
 class PostProcessChain:
-    """One view / one stream of consecutive frames on the current CUDA device."""
+    """One view / one stream of consecutive frames on the current CUDA device: a thin view of the C-ABI's chain executor
+    (`dfx_chain_*`, one call per frame). The executor sequences the effects like HnPostProcessTask, overlaps the SSAO passes
+    with the SSR passes and Bloom + ToneMap with the next frame's front half on its own streams, and replays steady-state
+    frames from CUDA graphs; this class only owns the input / output device planes (torch tensors)."""
 
     def __init__(self, width: int, height: int, config: ChainConfig | None = None, device: torch.device | None = None):
         self.lib = capi.load()
@@ -104,39 +108,43 @@ class PostProcessChain:
         if not torch.cuda.is_available():
             raise capi.DfxError("no CUDA device: the PostProcess chain has no CPU path")
         L = self.lib
-        self.postfx, self.ssao, self.ssr, self.bloom, self.taa, self.dof = (C.c_void_p() for _ in range(6))
-        check(L.dfx_postfx_create(C.byref(self.postfx)), "dfx_postfx_create")
-        check(L.dfx_ssao_create(C.byref(self.ssao)), "dfx_ssao_create")
-        check(L.dfx_ssr_create(C.byref(self.ssr)), "dfx_ssr_create")
-        check(L.dfx_bloom_create(C.byref(self.bloom)), "dfx_bloom_create")
-        check(L.dfx_taa_create(C.byref(self.taa)), "dfx_taa_create")
-        check(L.dfx_dof_create(C.byref(self.dof)), "dfx_dof_create")
+        self._cfg_c = self._config_struct()
+        self.chain = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(L.dfx_chain_create(width, height, C.byref(self._cfg_c), C.byref(self.chain)), "dfx_chain_create")
+        fx = {n: C.c_void_p(L.dfx_chain_effect(self.chain, i)) for n, i in capi.CHAIN_EFFECT.items()}
+        self.postfx, self.ssao, self.ssr, self.bloom, self.taa, self.dof = (fx[n] for n in ("postfx", "ssao", "ssr", "bloom", "taa", "dof"))
         dev = self.device
-        # device-resident inputs (filled by upload()) and chain-owned intermediates
+        # device-resident inputs (filled by upload()) and the LDR result
         self.inputs = {n: torch.empty((height, width) + ((c,) if c else ()), dtype=torch.float32, device=dev) for n, c in INPUT_SPECS.items()}
-        self.composed = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
         self.ldr = torch.empty((height, width, 4), dtype=torch.float32, device=dev)
         self.frame_index = None
-        # async-compute streams (cfg.overlap): the SSAO chain and the SSR chain only share read-only inputs, and Bloom + ToneMap
-        # of frame f only share the (ping-pong) TAA accumulator with frame f+1, so their small launches (pyramid levels) fill
-        # the gaps of the other branch instead of leaving the GPU idle.
-        self._ao_stream = torch.cuda.Stream(dev)
-        self._post_stream = torch.cuda.Stream(dev)
-        self._post_done: list = []   # events of the last two frames' Bloom + ToneMap (TAA of frame f+2 overwrites what Bloom of f read)
+        self._post_stream = torch.cuda.ExternalStream(L.dfx_chain_post_stream(self.chain), device=dev)  # Bloom + ToneMap under cfg.overlap
+        self._side_post = False
+
+    def _config_struct(self) -> capi.ChainConfigC:
+        cfg = self.cfg
+        c = capi.ChainConfigC()
+        c.ssao, c.ssr, c.bloom, c.taa, c.tonemap = cfg.ssao, cfg.ssr, cfg.bloom, cfg.taa, cfg.tonemap
+        c.dof = cfg.dof if cfg.dof is not None else capi.DOFAttribs.default()
+        c.postfx_flags, c.ssao_flags, c.ssr_flags, c.taa_flags, c.dof_flags = cfg.postfx_flags, cfg.ssao_flags, cfg.ssr_flags, cfg.taa_flags, cfg.dof_flags
+        c.stages, c.enable_dof, c.fuse, c.overlap, c.use_graph, c.to_srgb = cfg.stages, int(cfg.dof is not None), int(cfg.fuse), int(cfg.overlap), int(cfg.graph), int(cfg.to_srgb)
+        c.ave_log_lum, c.ssr_scale, c.ssao_scale = cfg.ave_log_lum, cfg.ssr_scale, cfg.ssao_scale
+        return c
 
     def join(self):
-        """Makes the current stream wait for everything execute(defer_post=True) left running on the side streams."""
-        main = torch.cuda.current_stream(self.device)
-        for e in self._post_done:
-            main.wait_event(e)
+        """Makes the current stream wait for everything execute(defer_post=True) left running on the executor's side stream."""
+        check(self.lib.dfx_chain_join(self.chain, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "dfx_chain_join")
+
+    def stats(self) -> dict:
+        s = capi.ChainStats()
+        check(self.lib.dfx_chain_get_stats(self.chain, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in s._fields_}
 
     def close(self):
-        L = self.lib
-        for h, fn in ((self.dof, L.dfx_dof_destroy), (self.taa, L.dfx_taa_destroy), (self.bloom, L.dfx_bloom_destroy), (self.ssr, L.dfx_ssr_destroy), (self.ssao, L.dfx_ssao_destroy),
-                      (self.postfx, L.dfx_postfx_destroy)):
-            if h:
-                fn(h)
-        self.postfx = self.ssao = self.ssr = self.bloom = self.taa = self.dof = None
+        if getattr(self, "chain", None):
+            self.lib.dfx_chain_destroy(self.chain)
+        self.chain = self.postfx = self.ssao = self.ssr = self.bloom = self.taa = self.dof = None
 
     def __del__(self):
         try:
@@ -161,115 +169,23 @@ class PostProcessChain:
         """Runs the chain on device-resident inputs (default: the planes filled by upload()); returns the final LDR plane
         (device tensor, rgba; `ldr_out` if given). Everything is ordered after the work already on the current stream. With
         cfg.overlap the LDR plane is produced on a side stream: by default the current stream waits for it before this call
-        returns; `defer_post=True` skips that wait so that the next frame's front half overlaps it (call join(), or wait
-        on `self.post_event`, before consuming the result)."""
-        if ldr_out is not None:
-            self.ldr, saved = ldr_out, self.ldr
-            try:
-                return self.execute(frame_index, curr_camera, prev_camera, inputs, defer_post=defer_post)
-            finally:
-                self.ldr = saved
+        returns; `defer_post=True` skips that wait so that the next frame's front half overlaps it (call join() before
+        consuming the result)."""
         L, cfg = self.lib, self.cfg
-        main = torch.cuda.current_stream(self.device)
-        stream = C.c_void_p(main.cuda_stream)
+        c = self._config_struct()
+        if bytes(c) != bytes(self._cfg_c):           # the caller edited self.cfg between frames
+            self._cfg_c = c
+            check(L.dfx_chain_set_config(self.chain, C.byref(c)), "dfx_chain_set_config")
         st = cfg.stages
-        side_ao = cfg.overlap and bool(st & STAGE_SSAO) and bool(st & STAGE_SSR)
-        side_post = self._side_post = cfg.overlap and bool(st & STAGE_BLOOM) and bool(st & STAGE_TAA) and cfg.dof is None
+        self._side_post = cfg.overlap and bool(st & STAGE_BLOOM) and bool(st & STAGE_TAA) and cfg.dof is None
+        out = self.ldr if ldr_out is None else ldr_out
         P = {n: plane_of(t) for n, t in (inputs or self.inputs).items()}
-
-        # Prepare (HnPostProcessTask.cpp:671-683)
-        desc = FrameDesc(frame_index, self.w, self.h, self.w, self.h)
-        check(L.dfx_postfx_prepare(self.postfx, C.byref(desc), cfg.postfx_flags), "dfx_postfx_prepare")
-        if st & STAGE_SSAO:
-            check(L.dfx_ssao_prepare(self.ssao, self.postfx, cfg.ssao_flags), "dfx_ssao_prepare")
-        if st & STAGE_SSR:
-            check(L.dfx_ssr_prepare(self.ssr, self.postfx, cfg.ssr_flags), "dfx_ssr_prepare")
-        if st & STAGE_TAA:
-            check(L.dfx_taa_prepare(self.taa, self.postfx, cfg.taa_flags, 0), "dfx_taa_prepare")
-        if st & STAGE_BLOOM:
-            check(L.dfx_bloom_prepare(self.bloom, self.postfx, 0), "dfx_bloom_prepare")
-        if cfg.dof is not None:
-            check(L.dfx_dof_prepare(self.dof, self.postfx, cfg.dof_flags), "dfx_dof_prepare")
-
-        # Execute (HnPostProcessTask.cpp:788-925)
-        if st & STAGE_POSTFX:
-            a = PostFXRenderAttribs(stream, C.pointer(P["depth"]), C.pointer(P["prev_depth"]), C.pointer(P["motion"]), C.pointer(curr_camera),
-                                    C.pointer(prev_camera))
-            check(L.dfx_postfx_execute(self.postfx, C.byref(a)), "dfx_postfx_execute")
-        if side_ao:
-            self._ao_stream.wait_stream(main)  # PostFX planes (and whatever produced the inputs) are ready
-        if st & STAGE_SSR:
-            a = SSRRenderAttribs(stream, self.postfx, C.pointer(P["color"]), C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(P["material"]),
-                                 C.pointer(P["motion"]), C.pointer(cfg.ssr))
-            check(L.dfx_ssr_execute(self.ssr, C.byref(a)), "dfx_ssr_execute")
-        if st & STAGE_SSAO:
-            ao_stream = C.c_void_p(self._ao_stream.cuda_stream) if side_ao else stream
-            a = SSAORenderAttribs(ao_stream, self.postfx, C.pointer(P["depth"]), C.pointer(P["normal"]), C.pointer(cfg.ssao))
-            check(L.dfx_ssao_execute(self.ssao, C.byref(a)), "dfx_ssao_execute")
-        if side_ao:
-            main.wait_stream(self._ao_stream)
-
-        color = P["color"]
-        fuse_compose = cfg.fuse and (st & STAGE_COMPOSE) and (st & STAGE_TAA)      # compose evaluated inside the TAA kernel
-        fuse_tonemap = cfg.fuse and (st & STAGE_BLOOM) and (st & STAGE_TONEMAP)    # tone map evaluated inside the Bloom composite
-        ssr_out, ao_out = Plane(), Plane()
-        pssr = pao = None
-        if st & STAGE_COMPOSE:
-            if st & STAGE_SSR:
-                check(L.dfx_ssr_get_plane(self.ssr, 0, C.byref(ssr_out)), "dfx_ssr_get_plane")
-                pssr = C.byref(ssr_out)
-            if st & STAGE_SSAO:
-                check(L.dfx_ssao_get_plane(self.ssao, 0, C.byref(ao_out)), "dfx_ssao_get_plane")
-                pao = C.byref(ao_out)
-            if not fuse_compose:
-                comp = plane_of(self.composed)
-                check(L.dfx_pass_compose(stream, C.byref(color), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale), C.byref(comp),
-                                         Rows(0, self.h)), "dfx_pass_compose")
-                color = comp
-        if st & STAGE_TAA:
-            while len(self._post_done) > 1:            # Bloom of frame f-2 read the accumulator this frame's TAA overwrites
-                main.wait_event(self._post_done.pop(0))
-            a = TAARenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.taa), 0)
-            if fuse_compose:
-                check(L.dfx_taa_execute_composed(self.taa, C.byref(a), pssr, pao, C.c_float(cfg.ssr_scale), C.c_float(cfg.ssao_scale)), "dfx_taa_execute_composed")
-            else:
-                check(L.dfx_taa_execute(self.taa, C.byref(a)), "dfx_taa_execute")
-            acc = Plane()
-            check(L.dfx_taa_get_plane(self.taa, 0, 0, C.byref(acc)), "dfx_taa_get_plane")
-            color = acc
-        if cfg.dof is not None:
-            # on the main stream: it reads the PostFX planes of this frame and its output feeds Bloom, so Bloom stays here too
-            a = capi.DOFRenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(P["depth"]), C.pointer(cfg.dof))
-            check(L.dfx_dof_execute(self.dof, C.byref(a)), "dfx_dof_execute")
-            dof_out = Plane()
-            check(L.dfx_dof_get_plane(self.dof, 0, C.byref(dof_out)), "dfx_dof_get_plane")
-            color = dof_out
-        if side_post:
-            self._post_stream.wait_stream(main)
-            stream = C.c_void_p(self._post_stream.cuda_stream)
-        if st & STAGE_BLOOM:
-            a = BloomRenderAttribs(stream, self.postfx, C.pointer(color), C.pointer(cfg.bloom))
-            if fuse_tonemap:
-                ldr = plane_of(self.ldr)
-                check(L.dfx_bloom_execute_tonemapped(self.bloom, C.byref(a), C.byref(cfg.tonemap), C.c_float(cfg.ave_log_lum), int(cfg.to_srgb), C.byref(ldr)),
-                      "dfx_bloom_execute_tonemapped")
-            else:
-                check(L.dfx_bloom_execute(self.bloom, C.byref(a)), "dfx_bloom_execute")
-                out = Plane()
-                check(L.dfx_bloom_get_plane(self.bloom, 0, C.byref(out)), "dfx_bloom_get_plane")
-                color = out
-        if (st & STAGE_TONEMAP) and not fuse_tonemap:
-            ldr = plane_of(self.ldr)
-            check(L.dfx_pass_tonemap(stream, C.byref(cfg.tonemap), C.c_float(cfg.ave_log_lum), int(cfg.to_srgb), C.byref(color), C.byref(ldr), Rows(0, self.h)),
-                  "dfx_pass_tonemap")
-        if side_post:
-            self.post_event = torch.cuda.Event()
-            self.post_event.record(self._post_stream)
-            self._post_done.append(self.post_event)
-            if not defer_post:
-                main.wait_event(self.post_event)
+        ldr = plane_of(out)
+        fr = capi.ChainFrame(frame_index, int(defer_post), C.pointer(curr_camera), C.pointer(prev_camera), C.pointer(P["depth"]), C.pointer(P["prev_depth"]),
+                             C.pointer(P["motion"]), C.pointer(P["normal"]), C.pointer(P["color"]), C.pointer(P["material"]), C.pointer(ldr))
+        check(L.dfx_chain_execute(self.chain, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), C.byref(fr)), "dfx_chain_execute")
         self.frame_index = frame_index
-        return self.ldr
+        return out
 
     def run_frame(self, frame: dict) -> torch.Tensor:
         """Public one-call API: host G-buffer in, LDR device plane out (upload + execute)."""

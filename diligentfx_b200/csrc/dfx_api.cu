@@ -1,5 +1,7 @@
 // dfx_api.cu — status / error plumbing, attribute defaults, host-side helpers and device-plane utilities of the C-ABI.
 #include "dfx_common.cuh"
+#include "dfx_tma.cuh"
+#include <tuple>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -107,6 +109,11 @@ void dfx_bloom_attribs_default(dfx_bloom_attribs* a)
 {
     // BloomStructures.fxh:12-34
     *a = dfx_bloom_attribs{0.15f, 1.0f, 0.125f, 0.75f, 1.0f, 0.0f, 0.0f, 0.0f};
+}
+void dfx_dof_attribs_default(dfx_dof_attribs* a)
+{
+    // DepthOfFieldStructures.fxh:31-56
+    *a = dfx_dof_attribs{0.01f, 0.9375f, 5, 7, 1.0f, 0.0f, 0.0f, 0.0f};
 }
 void dfx_taa_attribs_default(dfx_taa_attribs* a)
 {
@@ -328,6 +335,29 @@ int32_t dfx_tune_get(const char* name, int32_t fallback)
     return it == g_tune.end() ? fallback : it->second;
 }
 
+} // extern "C"
+namespace dfx
+{
+int  tune(const char* name, int fallback) { return dfx_tune_get(name, fallback); }
+bool profiling_enabled() { return g_profile_on; }
+
+// Tensor maps are encoded once per (plane, box) and cached: a frame touches a dozen planes, and encoding costs a driver call.
+const CUtensorMap* tensor_map_r32f(const View<float>& plane, int box_w, int box_h)
+{
+    static std::mutex                                                                  m;
+    static std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap>     cache;
+    std::lock_guard<std::mutex>                                                        lk(m);
+    const auto key = std::make_tuple(static_cast<const void*>(plane.p), plane.w, plane.h, plane.pitch, box_w, box_h);
+    auto       it  = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    CUtensorMap map;
+    if (!make_tensor_map_r32f(&map, plane.p, plane.w, plane.h, size_t(plane.pitch) * sizeof(float), box_w, box_h)) return nullptr;
+    if (cache.size() > 4096) cache.clear(); // planes come and go with their owners; the cache only ever saves the encode call
+    return &cache.emplace(key, map).first->second;
+}
+} // namespace dfx
+extern "C"
+{
 void    dfx_profile_reset(void) { dfx_profile_collect(), g_entries.clear(); }
 int32_t dfx_profile_count(void) { return (int32_t)g_entries.size(); }
 dfx_status dfx_profile_entry(int32_t i, char* name, int32_t name_cap, double* total_ms, int32_t* calls)

@@ -7,6 +7,8 @@
 //   TemporalAntiAliasing::Execute          …/TemporalAntiAliasing.cpp:169-201 (+ UpdateConstantBuffer :123-141)
 #include "dfx_common.cuh"
 #include <chrono>
+#include <cstring>
+#include <string>
 #include <map>
 #include <new>
 #include <vector>
@@ -61,7 +63,8 @@ struct dfx_postfx
     uint32_t            flags    = 0;
     bool                prepared = false, executed = false;
     uint8_t*            tables_dev = nullptr;
-    dfx_camera_attribs* cams_dev   = nullptr;
+    dfx_camera_attribs* cams_dev   = nullptr; // {curr, prev} followed by the frame index (uint32) the blue-noise pass reads
+    uint32_t*           frame_dev  = nullptr;
     PlaneOwner          bn_xy, bn_zw, reproj, prev_depth, closest;
     int                 w = 0, h = 0;
     ~dfx_postfx()
@@ -78,7 +81,8 @@ extern "C" dfx_status dfx_postfx_create(dfx_postfx** out)
     DFX_REQUIRE(c, "out of memory");
     cudaError_t e = cudaMalloc((void**)&c->tables_dev, sizeof(kBlueNoiseTables));
     if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, kBlueNoiseTables, sizeof(kBlueNoiseTables), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->cams_dev, 2 * sizeof(dfx_camera_attribs));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->cams_dev, 2 * sizeof(dfx_camera_attribs) + 16);
+    if (e == cudaSuccess) c->frame_dev = reinterpret_cast<uint32_t*>(c->cams_dev + 2);
     dfx_status st = DFX_OK;
     if (e != cudaSuccess) st = check_cuda(e, "dfx_postfx_create");
     if (st == DFX_OK) st = c->bn_xy.alloc(128, 128, DFX_FORMAT_RG32F);
@@ -120,6 +124,31 @@ extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* de
     return DFX_OK;
 }
 
+namespace dfx
+{
+dfx_status launch_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const uint32_t* frame_index_dev, const dfx_plane* xy, const dfx_plane* zw);
+}
+// upload {curr, prev} like the map-discard of PostFXContext.cpp:310-318 (pageable source: staged before returning), plus the frame index
+static dfx_status postfx_upload(dfx_postfx* c, cudaStream_t s, const dfx_camera_attribs* curr, const dfx_camera_attribs* prev)
+{
+    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[0], curr, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
+    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[1], prev, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
+    DFX_CUDA(cudaMemcpyAsync(c->frame_dev, &c->desc.Index, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    return DFX_OK;
+}
+// the kernels of PostFXContext::Execute (everything they read per frame comes from device memory: the launches can be replayed from a graph)
+static dfx_status postfx_launch(dfx_postfx* c, cudaStream_t s, const dfx_plane* curr_depth, const dfx_plane* prev_depth, const dfx_plane* motion)
+{
+    dfx_status st;
+    if ((st = launch_blue_noise(s, c->tables_dev, c->desc.Index, c->frame_dev, &c->bn_xy.p, &c->bn_zw.p)) != DFX_OK) return st;
+    dfx_rows  all{0, c->h};
+    dfx_plane depth = *curr_depth;
+    depth.flags |= c->reproj.p.flags;
+    if ((st = dfx_pass_postfx_prepare(s, c->cams_dev, &depth, prev_depth, motion, &c->reproj.p, &c->closest.p, &c->prev_depth.p, all)) != DFX_OK) return st;
+    c->executed = true;
+    return DFX_OK;
+}
+
 extern "C" dfx_status dfx_postfx_execute(dfx_postfx* c, const dfx_postfx_render_attribs* a)
 {
     DFX_REQUIRE(c && a, "null argument");
@@ -127,18 +156,9 @@ extern "C" dfx_status dfx_postfx_execute(dfx_postfx* c, const dfx_postfx_render_
     DFX_REQUIRE(a->curr_depth && a->prev_depth && a->motion_vectors, "depth / motion planes must not be null");
     DFX_REQUIRE(a->curr_camera && a->prev_camera, "camera attribs must not be null");
     cudaStream_t s = as_stream(a->stream);
-    // upload {curr, prev} like the map-discard of PostFXContext.cpp:310-318 (pageable source: staged before returning)
-    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[0], a->curr_camera, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
-    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[1], a->prev_camera, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
-    dfx_status st;
-    if ((st = dfx_pass_blue_noise(s, c->tables_dev, c->desc.Index, &c->bn_xy.p, &c->bn_zw.p)) != DFX_OK) return st;
-    dfx_rows all{0, c->h};
-    dfx_plane depth = *a->curr_depth;
-    depth.flags |= c->reproj.p.flags;
-    if ((st = dfx_pass_postfx_prepare(s, c->cams_dev, &depth, a->prev_depth, a->motion_vectors, &c->reproj.p, &c->closest.p, &c->prev_depth.p, all)) != DFX_OK)
-        return st;
-    c->executed = true;
-    return DFX_OK;
+    dfx_status   st;
+    if ((st = postfx_upload(c, s, a->curr_camera, a->prev_camera)) != DFX_OK) return st;
+    return postfx_launch(c, s, a->curr_depth, a->prev_depth, a->motion_vectors);
 }
 
 extern "C" dfx_status dfx_postfx_get_plane(const dfx_postfx* c, int32_t id, dfx_plane* out)
@@ -806,5 +826,432 @@ extern "C" dfx_status dfx_dof_get_plane(const dfx_dof* fx, int32_t id, dfx_plane
     else
         return set_error(DFX_ERR_INVALID_ARG, "unknown DepthOfField plane id %d", id);
     DFX_REQUIRE(out->ptr != nullptr, "plane %d is not available (temporal smoothing off?)", id);
+    return DFX_OK;
+}
+
+// =====================================================================================================================
+// Chain executor: the whole PostProcess chain of one view as ONE call per frame.
+//
+// Sequence and wiring follow the reference's only in-tree integration, Hydrogent's HnPostProcessTask (Prepare :591-683, Execute
+// :743-947): PostFXContext -> SSR -> SSAO -> compose -> TAA -> [DepthOfField] -> Bloom -> ToneMap(+sRGB). What is added here is
+// how the launches reach the GPU:
+//   * async compute: the SSAO passes run on a second stream beside the SSR passes (they share read-only inputs), and Bloom +
+//     ToneMap of frame f run on a third stream beside the front half of frame f+1 (they share only the ping-pong TAA accumulator);
+//   * CUDA graphs: in steady state (consecutive frame indices, no history reset, constant attributes) the ~25 launches of the
+//     front half and the ~8 of the back half are replayed from two instantiated graphs, cached per (input planes, ping-pong
+//     parity, attributes). Everything that changes from frame to frame - both cameras and the frame index - lives in device
+//     memory and is refreshed by one 1.2 KB copy from a pinned ring before the replay. A frame that resets a history, the first
+//     frames, or a profiling run take the eager path (same kernels, same streams).
+// =====================================================================================================================
+namespace dfx
+{
+bool profiling_enabled();
+}
+
+namespace
+{
+struct GraphPair
+{
+    cudaGraphExec_t front = nullptr, post = nullptr;
+    int             kernels = 0; // kernel nodes of the two graphs: what one replay adds to dfx_launch_count()
+};
+struct CameraSlot
+{
+    dfx_camera_attribs cams[2];
+    uint32_t           frame, pad[3];
+};
+constexpr int kCameraRing = 8;
+
+void append_bytes(std::string& k, const void* p, size_t n) { k.append(static_cast<const char*>(p), n); }
+void append_plane(std::string& k, const dfx_plane* p)
+{
+    static const dfx_plane none{};
+    append_bytes(k, p ? p : &none, sizeof(dfx_plane));
+}
+} // namespace
+
+static_assert(sizeof(dfx_chain_config) == 284, "dfx_chain_config layout (mirrored by diligentfx_b200/capi.py ChainConfigC)");
+struct dfx_chain
+{
+    dfx_chain_config cfg{};
+    int              w = 0, h = 0;
+    dfx_postfx*      pfx   = nullptr;
+    dfx_ssao*        ssao  = nullptr;
+    dfx_ssr*         ssr   = nullptr;
+    dfx_bloom*       bloom = nullptr;
+    dfx_taa*         taa   = nullptr;
+    dfx_dof*         dof   = nullptr;
+    cudaStream_t     ao_stream = nullptr, post_stream = nullptr, cap_stream = nullptr;
+    cudaEvent_t      ev_fork = nullptr, ev_ao_done = nullptr, ev_front_done = nullptr, post_done[2] = {nullptr, nullptr};
+    bool             post_pending[2] = {false, false};
+    PlaneOwner       composed;
+    CameraSlot*      ring = nullptr;
+    int              ring_pos = 0;
+    uint32_t         last_frame = ~0u;
+    bool             graphs_ok  = true;
+    std::map<std::string, GraphPair> graphs;
+    dfx_chain_stats  stats{};
+
+    void drop_graphs()
+    {
+        for (auto& g : graphs)
+        {
+            if (g.second.front) cudaGraphExecDestroy(g.second.front);
+            if (g.second.post) cudaGraphExecDestroy(g.second.post);
+        }
+        graphs.clear();
+    }
+    ~dfx_chain()
+    {
+        cudaDeviceSynchronize();
+        drop_graphs();
+        dfx_dof_destroy(dof), dfx_taa_destroy(taa), dfx_bloom_destroy(bloom), dfx_ssr_destroy(ssr), dfx_ssao_destroy(ssao), dfx_postfx_destroy(pfx);
+        for (cudaEvent_t e : {ev_fork, ev_ao_done, ev_front_done, post_done[0], post_done[1]})
+            if (e) cudaEventDestroy(e);
+        for (cudaStream_t s : {ao_stream, post_stream, cap_stream})
+            if (s) cudaStreamDestroy(s);
+        if (ring) cudaFreeHost(ring);
+    }
+};
+
+extern "C" void dfx_chain_config_default(dfx_chain_config* c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    dfx_ssao_attribs_default(&c->ssao), dfx_ssr_attribs_default(&c->ssr), dfx_bloom_attribs_default(&c->bloom), dfx_taa_attribs_default(&c->taa);
+    dfx_tonemap_attribs_default(&c->tonemap), dfx_dof_attribs_default(&c->dof);
+    c->taa_flags   = DFX_TAA_FEATURE_FLAG_BICUBIC_FILTER; // Hydrogent default (HnPostProcessTask.hpp:109)
+    c->stages      = DFX_CHAIN_STAGE_ALL;
+    c->fuse        = 1;
+    c->overlap     = 1;
+    c->use_graph   = 1;
+    c->to_srgb     = 1;
+    c->ave_log_lum = 0.3f; // HnPostProcessTask.hpp:88, fExposure 0
+    c->ssr_scale = c->ssao_scale = 1.0f;
+}
+
+extern "C" dfx_status dfx_chain_create(int32_t width, int32_t height, const dfx_chain_config* config, dfx_chain** out)
+{
+    DFX_REQUIRE(out && width > 0 && height > 0, "bad arguments");
+    dfx_chain* c = new (std::nothrow) dfx_chain;
+    DFX_REQUIRE(c, "out of memory");
+    c->w = width, c->h = height;
+    if (config)
+        c->cfg = *config;
+    else
+        dfx_chain_config_default(&c->cfg);
+    dfx_status st = DFX_OK;
+    if (st == DFX_OK) st = dfx_postfx_create(&c->pfx);
+    if (st == DFX_OK) st = dfx_ssao_create(&c->ssao);
+    if (st == DFX_OK) st = dfx_ssr_create(&c->ssr);
+    if (st == DFX_OK) st = dfx_bloom_create(&c->bloom);
+    if (st == DFX_OK) st = dfx_taa_create(&c->taa);
+    if (st == DFX_OK) st = dfx_dof_create(&c->dof);
+    cudaError_t e = cudaSuccess;
+    for (cudaStream_t* s : {&c->ao_stream, &c->post_stream, &c->cap_stream})
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_ao_done, &c->ev_front_done, &c->post_done[0], &c->post_done[1]})
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->ring, sizeof(CameraSlot) * kCameraRing);
+    if (st == DFX_OK && e != cudaSuccess) st = check_cuda(e, "dfx_chain_create");
+    if (st != DFX_OK)
+    {
+        delete c;
+        return st;
+    }
+    *out = c;
+    return DFX_OK;
+}
+extern "C" void dfx_chain_destroy(dfx_chain* c) { delete c; }
+
+extern "C" dfx_status dfx_chain_set_config(dfx_chain* c, const dfx_chain_config* config)
+{
+    DFX_REQUIRE(c && config, "null argument");
+    c->cfg = *config; // the graph cache is keyed by the configuration bytes: stale entries are simply never hit again
+    if (c->graphs.size() > 16) c->drop_graphs();
+    return DFX_OK;
+}
+extern "C" dfx_status dfx_chain_get_config(const dfx_chain* c, dfx_chain_config* out)
+{
+    DFX_REQUIRE(c && out, "null argument");
+    *out = c->cfg;
+    return DFX_OK;
+}
+extern "C" void* dfx_chain_effect(dfx_chain* c, int32_t which)
+{
+    if (!c) return nullptr;
+    switch (which)
+    {
+        case DFX_CHAIN_EFFECT_POSTFX: return c->pfx;
+        case DFX_CHAIN_EFFECT_SSAO: return c->ssao;
+        case DFX_CHAIN_EFFECT_SSR: return c->ssr;
+        case DFX_CHAIN_EFFECT_BLOOM: return c->bloom;
+        case DFX_CHAIN_EFFECT_TAA: return c->taa;
+        case DFX_CHAIN_EFFECT_DOF: return c->dof;
+        default: return nullptr;
+    }
+}
+extern "C" void* dfx_chain_post_stream(dfx_chain* c) { return c ? c->post_stream : nullptr; }
+extern "C" dfx_status dfx_chain_get_stats(const dfx_chain* c, dfx_chain_stats* out)
+{
+    DFX_REQUIRE(c && out, "null argument");
+    *out = c->stats;
+    return DFX_OK;
+}
+
+// Makes `stream` wait for the Bloom + ToneMap work that dfx_chain_execute(defer_post = 1) left running on the chain's own stream.
+extern "C" dfx_status dfx_chain_join(dfx_chain* c, void* stream)
+{
+    DFX_REQUIRE(c, "null argument");
+    for (int i = 0; i < 2; ++i)
+        if (c->post_pending[i]) DFX_CUDA(cudaStreamWaitEvent(as_stream(stream), c->post_done[i], 0));
+    return DFX_OK;
+}
+
+namespace
+{
+struct FrameCtx
+{
+    dfx_chain*             c;
+    const dfx_chain_frame* f;
+    uint32_t               st;
+    bool                   side_ao, side_post, fuse_compose, fuse_tonemap, with_dof;
+};
+
+// PostFX .. TAA [.. DoF] on `s` (the SSAO passes fork to the chain's second stream and join before the compose). `*color_out` = what Bloom reads.
+dfx_status record_front(const FrameCtx& x, cudaStream_t s, dfx_plane* color_out)
+{
+    dfx_chain*             c   = x.c;
+    const dfx_chain_frame* f   = x.f;
+    const dfx_chain_config& cfg = c->cfg;
+    dfx_status             st;
+    if (x.st & DFX_CHAIN_STAGE_POSTFX)
+        if ((st = postfx_launch(c->pfx, s, f->depth, f->prev_depth, f->motion)) != DFX_OK) return st;
+    if (x.side_ao)
+    {
+        DFX_CUDA(cudaEventRecord(c->ev_fork, s));
+        DFX_CUDA(cudaStreamWaitEvent(c->ao_stream, c->ev_fork, 0));
+    }
+    if (x.st & DFX_CHAIN_STAGE_SSR)
+    {
+        dfx_ssr_render_attribs a{s, c->pfx, f->color, f->depth, f->normal, f->material, f->motion, &cfg.ssr};
+        if ((st = dfx_ssr_execute(c->ssr, &a)) != DFX_OK) return st;
+    }
+    if (x.st & DFX_CHAIN_STAGE_SSAO)
+    {
+        dfx_ssao_render_attribs a{x.side_ao ? c->ao_stream : s, c->pfx, f->depth, f->normal, &cfg.ssao};
+        if ((st = dfx_ssao_execute(c->ssao, &a)) != DFX_OK) return st;
+    }
+    if (x.side_ao)
+    {
+        DFX_CUDA(cudaEventRecord(c->ev_ao_done, c->ao_stream));
+        DFX_CUDA(cudaStreamWaitEvent(s, c->ev_ao_done, 0));
+    }
+    dfx_plane        color = *f->color, ssr_out{}, ao_out{};
+    const dfx_plane *pssr = nullptr, *pao = nullptr;
+    if (x.st & DFX_CHAIN_STAGE_COMPOSE)
+    {
+        if (x.st & DFX_CHAIN_STAGE_SSR)
+        {
+            if ((st = dfx_ssr_get_plane(c->ssr, DFX_SSR_PLANE_OUTPUT, &ssr_out)) != DFX_OK) return st;
+            pssr = &ssr_out;
+        }
+        if (x.st & DFX_CHAIN_STAGE_SSAO)
+        {
+            if ((st = dfx_ssao_get_plane(c->ssao, DFX_SSAO_PLANE_OUTPUT, &ao_out)) != DFX_OK) return st;
+            pao = &ao_out;
+        }
+        if (!x.fuse_compose)
+        {
+            if ((st = dfx_pass_compose(s, &color, pssr, pao, cfg.ssr_scale, cfg.ssao_scale, &c->composed.p, dfx_rows{0, c->h})) != DFX_OK) return st;
+            color = c->composed.p;
+        }
+    }
+    if (x.st & DFX_CHAIN_STAGE_TAA)
+    {
+        dfx_taa_render_attribs a{s, c->pfx, &color, &cfg.taa, 0};
+        st = x.fuse_compose ? dfx_taa_execute_composed(c->taa, &a, pssr, pao, cfg.ssr_scale, cfg.ssao_scale) : dfx_taa_execute(c->taa, &a);
+        if (st != DFX_OK) return st;
+        if ((st = dfx_taa_get_plane(c->taa, DFX_TAA_PLANE_ACCUMULATED_CURR, 0, &color)) != DFX_OK) return st;
+    }
+    if (x.with_dof)
+    {
+        dfx_dof_render_attribs a{s, c->pfx, &color, f->depth, &cfg.dof};
+        if ((st = dfx_dof_execute(c->dof, &a)) != DFX_OK) return st;
+        if ((st = dfx_dof_get_plane(c->dof, DFX_DOF_PLANE_OUTPUT, &color)) != DFX_OK) return st;
+    }
+    *color_out = color;
+    return DFX_OK;
+}
+
+// Bloom + ToneMap(+sRGB) on `s`
+dfx_status record_post(const FrameCtx& x, cudaStream_t s, dfx_plane color)
+{
+    dfx_chain*              c   = x.c;
+    const dfx_chain_config& cfg = c->cfg;
+    dfx_status              st;
+    if (x.st & DFX_CHAIN_STAGE_BLOOM)
+    {
+        dfx_bloom_render_attribs a{s, c->pfx, &color, &cfg.bloom};
+        if (x.fuse_tonemap) return dfx_bloom_execute_tonemapped(c->bloom, &a, &cfg.tonemap, cfg.ave_log_lum, cfg.to_srgb, x.f->ldr_out);
+        if ((st = dfx_bloom_execute(c->bloom, &a)) != DFX_OK) return st;
+        if ((st = dfx_bloom_get_plane(c->bloom, DFX_BLOOM_PLANE_OUTPUT, &color)) != DFX_OK) return st;
+    }
+    if (x.st & DFX_CHAIN_STAGE_TONEMAP) return dfx_pass_tonemap(s, &cfg.tonemap, cfg.ave_log_lum, cfg.to_srgb, &color, x.f->ldr_out, dfx_rows{0, c->h});
+    return DFX_OK;
+}
+
+// what TAA's output plane will be for this frame (needed by the replay path, which never calls record_front)
+bool alpha_constant(AlphaTimer& a) { return a.pinned >= 0.0f || a.value() >= 1.0f; }
+} // namespace
+
+extern "C" dfx_status dfx_chain_execute(dfx_chain* c, void* stream, const dfx_chain_frame* f)
+{
+    DFX_REQUIRE(c && f, "null argument");
+    DFX_REQUIRE(f->curr_camera && f->prev_camera, "camera attribs must not be null");
+    DFX_REQUIRE(f->depth && f->prev_depth && f->motion && f->normal && f->color && f->material, "all six G-buffer planes must be given");
+    const dfx_chain_config& cfg = c->cfg;
+    const uint32_t          st  = cfg.stages;
+    DFX_REQUIRE(!(st & (DFX_CHAIN_STAGE_TONEMAP)) || f->ldr_out, "the tone-mapped output plane must be given");
+    cudaStream_t main = as_stream(stream);
+    FrameCtx     x{c, f, st, false, false, false, false, false};
+    x.with_dof     = cfg.enable_dof != 0;
+    x.side_ao      = cfg.overlap && (st & DFX_CHAIN_STAGE_SSAO) && (st & DFX_CHAIN_STAGE_SSR);
+    x.side_post    = cfg.overlap && (st & DFX_CHAIN_STAGE_BLOOM) && (st & DFX_CHAIN_STAGE_TAA) && !x.with_dof;
+    x.fuse_compose = cfg.fuse && (st & DFX_CHAIN_STAGE_COMPOSE) && (st & DFX_CHAIN_STAGE_TAA);
+    x.fuse_tonemap = cfg.fuse && (st & DFX_CHAIN_STAGE_BLOOM) && (st & DFX_CHAIN_STAGE_TONEMAP) && (c->w % 2 == 0) && (c->h % 2 == 0);
+
+    // ---- Prepare (HnPostProcessTask.cpp:671-683): host bookkeeping; allocates on the first frame / on a size change
+    dfx_status     s;
+    dfx_frame_desc desc{f->frame_index, (uint32_t)c->w, (uint32_t)c->h, (uint32_t)c->w, (uint32_t)c->h};
+    if ((s = dfx_postfx_prepare(c->pfx, &desc, cfg.postfx_flags)) != DFX_OK) return s;
+    if ((st & DFX_CHAIN_STAGE_SSAO) && (s = dfx_ssao_prepare(c->ssao, c->pfx, cfg.ssao_flags)) != DFX_OK) return s;
+    if ((st & DFX_CHAIN_STAGE_SSR) && (s = dfx_ssr_prepare(c->ssr, c->pfx, cfg.ssr_flags)) != DFX_OK) return s;
+    if ((st & DFX_CHAIN_STAGE_TAA) && (s = dfx_taa_prepare(c->taa, c->pfx, cfg.taa_flags, 0)) != DFX_OK) return s;
+    if ((st & DFX_CHAIN_STAGE_BLOOM) && (s = dfx_bloom_prepare(c->bloom, c->pfx, 0)) != DFX_OK) return s;
+    if (x.with_dof && (s = dfx_dof_prepare(c->dof, c->pfx, cfg.dof_flags)) != DFX_OK) return s;
+    if ((st & DFX_CHAIN_STAGE_COMPOSE) && !x.fuse_compose && !c->composed.p.ptr && (s = c->composed.alloc(c->w, c->h, DFX_FORMAT_RGBA32F)) != DFX_OK) return s;
+
+    // ---- can this frame be replayed from a graph?
+    const uint32_t par    = f->frame_index & 1u;
+    bool           steady = cfg.use_graph && c->graphs_ok && !profiling_enabled() && c->last_frame != ~0u && f->frame_index == c->last_frame + 1u;
+    if (steady && (st & DFX_CHAIN_STAGE_SSAO))
+        steady = c->ssao->last_frame != ~0u && c->ssao->curr_frame == c->ssao->last_frame + 1u && !cfg.ssao.ResetAccumulation && alpha_constant(c->ssao->alpha);
+    if (steady && (st & DFX_CHAIN_STAGE_SSR)) steady = alpha_constant(c->ssr->alpha);
+    if (steady && (st & DFX_CHAIN_STAGE_BLOOM)) steady = alpha_constant(c->bloom->alpha);
+    if (steady && x.with_dof) steady = alpha_constant(c->dof->alpha);
+    if (steady && (st & DFX_CHAIN_STAGE_TAA))
+    {
+        const TaaBuffer& b = c->taa->buffers[0];
+        steady             = b.last_frame != ~0u && b.curr_frame == b.last_frame + 1u && !cfg.taa.ResetAccumulation;
+    }
+
+    // ---- TAA of this frame overwrites the accumulator that Bloom of frame f-2 read on the chain's third stream
+    if (c->post_pending[par])
+    {
+        DFX_CUDA(cudaStreamWaitEvent(main, c->post_done[par], 0));
+        c->post_pending[par] = false;
+    }
+    // ---- cameras + frame index: one copy from the pinned ring (a slot is reused after kCameraRing frames)
+    if (st & DFX_CHAIN_STAGE_POSTFX)
+    {
+        CameraSlot& slot = c->ring[c->ring_pos];
+        c->ring_pos      = (c->ring_pos + 1) % kCameraRing;
+        slot.cams[0] = *f->curr_camera, slot.cams[1] = *f->prev_camera, slot.frame = f->frame_index;
+        DFX_CUDA(cudaMemcpyAsync(c->pfx->cams_dev, &slot, 2 * sizeof(dfx_camera_attribs) + sizeof(uint32_t), cudaMemcpyHostToDevice, main));
+    }
+
+    dfx_plane color{};
+    bool      replayed = false;
+    if (steady)
+    {
+        std::string key;
+        key.reserve(1024);
+        append_bytes(key, &par, sizeof(par));
+        append_bytes(key, &cfg, sizeof(cfg));
+        for (const dfx_plane* p : {f->depth, f->prev_depth, f->motion, f->normal, f->color, f->material, f->ldr_out}) append_plane(key, p);
+        const float alphas[4] = {c->ssao->alpha.value(), c->ssr->alpha.value(), c->bloom->alpha.value(), c->dof->alpha.value()};
+        append_bytes(key, alphas, sizeof(alphas));
+        GraphPair& g = c->graphs[key];
+        if (!g.front)
+        {
+            // capture on the chain's own stream (the caller's may be the legacy default stream, which cannot capture)
+            cudaGraph_t    graph    = nullptr;
+            const uint64_t counted0 = dfx_launch_count();
+            cudaError_t    e        = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
+            dfx_status  rs    = e == cudaSuccess ? record_front(x, c->cap_stream, &color) : check_cuda(e, "cudaStreamBeginCapture");
+            if (rs == DFX_OK && !x.side_post) rs = record_post(x, c->cap_stream, color);
+            if (e == cudaSuccess) e = cudaStreamEndCapture(c->cap_stream, &graph);
+            if (rs == DFX_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g.front, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rs == DFX_OK && e == cudaSuccess && x.side_post)
+            {
+                graph = nullptr;
+                e     = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
+                rs    = e == cudaSuccess ? record_post(x, c->cap_stream, color) : check_cuda(e, "cudaStreamBeginCapture");
+                if (e == cudaSuccess) e = cudaStreamEndCapture(c->cap_stream, &graph);
+                if (rs == DFX_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g.post, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (rs != DFX_OK || e != cudaSuccess)
+            {
+                // a capture that failed leaves nothing on the GPU: run this frame (and every later one) eagerly
+                (void)cudaGetLastError();
+                if (g.front) cudaGraphExecDestroy(g.front);
+                if (g.post) cudaGraphExecDestroy(g.post);
+                c->graphs.erase(key);
+                c->graphs_ok = false;
+                c->stats.graph_failures += 1;
+                steady = false;
+            }
+            else
+            {
+                c->stats.graphs_built += 1;
+                g.kernels = int(dfx_launch_count() - counted0);
+            }
+            count_launch(-int(dfx_launch_count() - counted0)); // recorded, not launched
+            if (c->graphs.size() > 64) c->drop_graphs(), steady = false; // runaway key churn (a caller that never reuses its planes): stay eager
+        }
+        if (steady)
+        {
+            GraphPair& gg = c->graphs[key];
+            DFX_CUDA(cudaGraphLaunch(gg.front, main));
+            if (x.side_post)
+            {
+                DFX_CUDA(cudaEventRecord(c->ev_front_done, main));
+                DFX_CUDA(cudaStreamWaitEvent(c->post_stream, c->ev_front_done, 0));
+                DFX_CUDA(cudaGraphLaunch(gg.post, c->post_stream));
+            }
+            // the host-side state the effects' Execute() would have advanced
+            c->pfx->executed = true;
+            if (st & DFX_CHAIN_STAGE_SSAO) c->ssao->last_frame = c->ssao->curr_frame;
+            if (st & DFX_CHAIN_STAGE_TAA) c->taa->buffers[0].last_frame = c->taa->buffers[0].curr_frame;
+            count_launch(gg.kernels);
+            c->stats.frames_replayed += 1;
+            replayed = true;
+        }
+    }
+    if (!replayed)
+    {
+        if ((s = record_front(x, main, &color)) != DFX_OK) return s;
+        if (x.side_post)
+        {
+            DFX_CUDA(cudaEventRecord(c->ev_front_done, main));
+            DFX_CUDA(cudaStreamWaitEvent(c->post_stream, c->ev_front_done, 0));
+        }
+        if ((s = record_post(x, x.side_post ? c->post_stream : main, color)) != DFX_OK) return s;
+        c->stats.frames_eager += 1;
+    }
+    if (x.side_post)
+    {
+        DFX_CUDA(cudaEventRecord(c->post_done[par], c->post_stream));
+        c->post_pending[par] = true;
+        if (!f->defer_post)
+        {
+            DFX_CUDA(cudaStreamWaitEvent(main, c->post_done[par], 0));
+            c->post_pending[par] = false;
+        }
+    }
+    c->last_frame = f->frame_index;
     return DFX_OK;
 }

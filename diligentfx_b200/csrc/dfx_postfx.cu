@@ -36,8 +36,11 @@ __device__ __forceinline__ uint32_t hilbert_index_128(uint32_t x, uint32_t y)
     return index;
 }
 
-__global__ void __launch_bounds__(128) blue_noise_kernel(const uint8_t* __restrict__ tables, uint32_t frame, View<float2> xy, View<float2> zw)
+// `frame_dev` (optional) overrides `frame`: a launch recorded into a CUDA graph reads the frame index of the frame being replayed
+__global__ void __launch_bounds__(128) blue_noise_kernel(const uint8_t* __restrict__ tables, uint32_t frame, const uint32_t* __restrict__ frame_dev, View<float2> xy,
+                                                         View<float2> zw)
 {
+    if (frame_dev) frame = *frame_dev;
     uint32_t x = threadIdx.x, y = blockIdx.x;
     // R1 sequence shift (golden ratio)
     float alpha = 0.5f + (1.0f / 1.61803398875f) * float(frame & 0xFFu);
@@ -107,16 +110,24 @@ __global__ void __launch_bounds__(256) postfx_prepare_kernel(const dfx_camera_at
 
 using namespace dfx;
 
-extern "C" dfx_status dfx_pass_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const dfx_plane* xy, const dfx_plane* zw)
+namespace dfx
+{
+dfx_status launch_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const uint32_t* frame_index_dev, const dfx_plane* xy, const dfx_plane* zw)
 {
     DFX_PROFILE(stream, "blue_noise");
     DFX_REQUIRE(tables != nullptr, "tables must not be null");
     DFX_VIEW(float2, vxy, xy, DFX_FORMAT_RG32F);
     DFX_VIEW(float2, vzw, zw, DFX_FORMAT_RG32F);
     DFX_REQUIRE(vxy.w == 128 && vxy.h == 128 && vzw.w == 128 && vzw.h == 128, "blue-noise planes must be 128x128");
-    blue_noise_kernel<<<128, 128, 0, as_stream(stream)>>>(tables, frame_index, vxy, vzw);
+    blue_noise_kernel<<<128, 128, 0, as_stream(stream)>>>(tables, frame_index, frame_index_dev, vxy, vzw);
     DFX_LAUNCHED("blue_noise_kernel");
     return DFX_OK;
+}
+} // namespace dfx
+
+extern "C" dfx_status dfx_pass_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const dfx_plane* xy, const dfx_plane* zw)
+{
+    return launch_blue_noise(stream, tables, frame_index, nullptr, xy, zw);
 }
 
 extern "C" dfx_status dfx_pass_postfx_prepare(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_plane* curr_depth,

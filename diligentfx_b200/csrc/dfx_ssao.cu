@@ -3,6 +3,7 @@
 // shaders: Shaders/PostProcess/ScreenSpaceAmbientOcclusion/private/SSAO_*.fx (cited per kernel).
 // Layout: depth / AO / history-length planes are fp32, normals float4 (xyz used); see DESIGN.md.
 #include "dfx_common.cuh"
+#include "dfx_pyramid.cuh"
 
 namespace dfx
 {
@@ -25,49 +26,7 @@ __device__ __forceinline__ void stage_cam(SsaoCam& s, const dfx_camera_attribs* 
 // level-m row range of a full-resolution strip [y0, y1)
 __host__ __device__ inline int mip_row(int y, int m, int full_h, int mip_h) { return y >= full_h ? mip_h : (y >> m); }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// A2: prefiltered depth mip m from mip m-1 (SSAO_ComputePrefilteredDepthBuffer.fx:79-122).
-// 2x2 footprint (+1 column / row when the source dimension is odd), taps converted to view-space Z, weighted average
-// that favours the closest tap within the falloff range, converted back to depth and saturated.
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ssao_prefilter_level_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
-                                                                   View<const float> src, View<float> dst, int r0, int r1)
-{
-    __shared__ CamS cam;
-    if (threadIdx.x == 0 && threadIdx.y == 0) load_cam(cam, &cams[0]);
-    __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dst.w || y >= r1) return;
-
-    const bool wodd = src.w & 1, hodd = src.h & 1;
-    float      z[9];
-    int        n = 0;
-    const int  rx = 2 * x, ry = 2 * y;
-    auto       tap = [&](int ox, int oy) { z[n++] = depth_to_camz(loadc(src, rx + ox, ry + oy), cam); };
-    tap(0, 0), tap(0, 1), tap(1, 0), tap(1, 1);
-    if (wodd) tap(2, 0), tap(2, 1);
-    if (hodd) tap(0, 2), tap(1, 2);
-    if (wodd && hodd) tap(2, 2);
-
-    float zmin = z[0];
-    for (int i = 1; i < n; ++i) zmin = fminf(zmin, z[i]);
-
-    const float radius       = 0.75f * A.EffectRadius * A.RadiusMultiplier;
-    const float falloffRange = A.EffectFalloffRange * radius;
-    const float falloffFrom  = radius - falloffRange;
-    const float falloffMul   = -1.0f / falloffRange;
-    const float falloffAdd   = falloffFrom / falloffRange + 1.0f;
-
-    float zsum = 0.0f, wsum = 0.0f;
-    for (int i = 0; i < n; ++i)
-    {
-        float w = saturate(fabsf(zmin - z[i]) * falloffMul + falloffAdd);
-        zsum += w * z[i];
-        wsum += w;
-    }
-    dst.at(x, y) = saturate(camz_to_depth(zsum / wsum, cam));
-}
+// A2 (prefiltered depth pyramid, SSAO_ComputePrefilteredDepthBuffer.fx:79-122): PrefilterOp in dfx_pyramid.cuh.
 
 // ---------------------------------------------------------------------------------------------------------------------
 // A3: ambient occlusion (SSAO_ComputeAmbientOcclusion.fx:132-231). One thread per pixel; the 18 depth taps per pixel are
@@ -416,32 +375,7 @@ __global__ void __launch_bounds__(256) ssao_temporal_kernel(const dfx_camera_att
     st_cs(&out_hist.at(x, y), rHist);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// A6: convoluted history / depth pyramids, level m from m-1, plain averages (SSAO_ComputeConvolutedDepthHistory.fx:93-109)
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float footprint_average(const View<const float>& src, int rx, int ry)
-{
-    const bool wodd = src.w & 1, hodd = src.h & 1;
-    // accumulation order of the reference's ArrayAppend sequence
-    float r = loadc(src, rx, ry);
-    r += loadc(src, rx, ry + 1);
-    r += loadc(src, rx + 1, ry);
-    r += loadc(src, rx + 1, ry + 1);
-    int n = 4;
-    if (wodd) r += loadc(src, rx + 2, ry), r += loadc(src, rx + 2, ry + 1), n += 2;
-    if (hodd) r += loadc(src, rx, ry + 2), r += loadc(src, rx + 1, ry + 2), n += 2;
-    if (wodd && hodd) r += loadc(src, rx + 2, ry + 2), n += 1;
-    return r / float(n);
-}
-__global__ void __launch_bounds__(256) ssao_convolute_level_kernel(View<const float> occ_src, View<const float> depth_src, View<float> occ_dst,
-                                                                   View<float> depth_dst, int r0, int r1)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= occ_dst.w || y >= r1) return;
-    occ_dst.at(x, y)   = footprint_average(occ_src, 2 * x, 2 * y);
-    depth_dst.at(x, y) = footprint_average(depth_src, 2 * x, 2 * y);
-}
+// A6 (convoluted AO-history and depth pyramids, SSAO_ComputeConvolutedDepthHistory.fx:93-109): ConvoluteOp in dfx_pyramid.cuh.
 
 // ---------------------------------------------------------------------------------------------------------------------
 // A7: resampled history (SSAO_ComputeResampledHistory.fx:56-115)
@@ -608,15 +542,10 @@ extern "C" dfx_status dfx_pass_ssao_prefilter_depth(void* stream, const dfx_came
     DFX_REQUIRE(make_pyr_rw(pyr, P, 1), "bad prefiltered-depth pyramid");
     const int H = P.lv[0].h;
     DFX_ROWS_ALIGNED(rows, H);
-    for (int m = 1; m < P.levels && m <= 4; ++m)
-    {
-        const int r0 = mip_row(rows.y0, m, H, P.lv[m].h), r1 = mip_row(rows.y1, m, H, P.lv[m].h);
-        if (r1 <= r0) continue;
-        dim3 block(32, 8), grid(div_up(P.lv[m].w, 32), div_up(r1 - r0, 8));
-        ssao_prefilter_level_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, ro(P.lv[m - 1]), P.lv[m], r0, r1);
-        DFX_LAUNCHED("ssao_prefilter_level_kernel");
-    }
-    return DFX_OK;
+    PyrPlanes<1> Q;
+    Q.levels = P.levels;
+    for (int i = 0; i < P.levels; ++i) Q.lv[0][i] = P.lv[i];
+    return build_pyramid(stream, make_prefilter_op(cameras_dev, *attribs), Q, 4, rows, "ssao_prefilter pyramid kernel");
 }
 
 extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssao_attribs* attribs,
@@ -727,15 +656,10 @@ extern "C" dfx_status dfx_pass_ssao_convolute(void* stream, const dfx_pyramid* o
     DFX_SAME_SIZE(O.lv[0], D.lv[0]);
     const int H = O.lv[0].h;
     DFX_ROWS_ALIGNED(rows, H);
-    for (int m = 1; m < O.levels && m <= 4; ++m)
-    {
-        const int r0 = mip_row(rows.y0, m, H, O.lv[m].h), r1 = mip_row(rows.y1, m, H, O.lv[m].h);
-        if (r1 <= r0) continue;
-        dim3 block(32, 8), grid(div_up(O.lv[m].w, 32), div_up(r1 - r0, 8));
-        ssao_convolute_level_kernel<<<grid, block, 0, as_stream(stream)>>>(ro(O.lv[m - 1]), ro(D.lv[m - 1]), O.lv[m], D.lv[m], r0, r1);
-        DFX_LAUNCHED("ssao_convolute_level_kernel");
-    }
-    return DFX_OK;
+    PyrPlanes<2> Q;
+    Q.levels = O.levels;
+    for (int i = 0; i < O.levels; ++i) Q.lv[0][i] = O.lv[i], Q.lv[1][i] = D.lv[i];
+    return build_pyramid(stream, ConvoluteOp{}, Q, 4, rows, "ssao_convolute pyramid kernel");
 }
 
 extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_pyramid* occlusion_pyr,

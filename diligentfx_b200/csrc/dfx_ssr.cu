@@ -4,6 +4,7 @@
 // The D16 stencil mask of the reference is an R8U plane here: 1 = reflection sample, 0 = masked out. Consumers that the
 // reference draws depth-tested against the mask simply skip masked pixels (their targets keep their previous content).
 #include "dfx_common.cuh"
+#include "dfx_pyramid.cuh"
 #ifndef DFX_INTERSECT_V2
 #    define DFX_INTERSECT_V2 0
 #endif
@@ -15,28 +16,7 @@ DFX_HD bool is_reflection_sample(float rough, float depth, float thr, int rev) {
 
 __host__ __device__ inline int ssr_mip_row(int y, int m, int full_h, int mip_h) { return y >= full_h ? mip_h : (y >> m); }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// S1: Hi-Z level m from m-1: closest (min) depth of the 2x2 footprint (+ odd row/column) — SSR_ComputeHierarchicalDepthBuffer.fx:30-73
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ssr_hiz_level_kernel(View<const float> src, View<float> dst, int r0, int r1, int rev)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = r0 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dst.w || y >= r1) return;
-    const bool wodd = src.w & 1, hodd = src.h & 1;
-    const int  rx = 2 * x, ry = 2 * y;
-    // ClosestDepth = min, DepthFarPlane = 1; reversed depth: max and 0 (SSR_Common.fxh:6-12)
-    float      m   = rev ? 0.0f : 1.0f;
-    const auto upd = [&](int ox, int oy) {
-        const float d = loadc(src, rx + ox, ry + oy);
-        m             = rev ? fmaxf(m, d) : fminf(m, d);
-    };
-    upd(0, 0), upd(0, 1), upd(1, 0), upd(1, 1);
-    if (wodd) upd(2, 0), upd(2, 1);
-    if (hodd) upd(0, 2), upd(1, 2);
-    if (wodd && hodd) upd(2, 2);
-    dst.at(x, y) = m;
-}
+// S1 (Hi-Z pyramid, SSR_ComputeHierarchicalDepthBuffer.fx:30-73): HizOp in dfx_pyramid.cuh — tile / tail / per-level kernels.
 
 // ---------------------------------------------------------------------------------------------------------------------
 // S2: reflection mask + roughness extraction — SSR_ComputeStencilMaskAndExtractRoughness.fx:13-40
@@ -725,24 +705,16 @@ extern "C" dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx
 {
     DFX_PROFILE(stream, "ssr_hiz");
     DFX_REQUIRE(pyr && pyr->levels >= 1 && pyr->levels <= DFX_MAX_MIPS, "bad Hi-Z pyramid");
-    View<float> lv[DFX_MAX_MIPS];
+    PyrPlanes<1> P;
+    P.levels = pyr->levels;
     for (int i = 0; i < pyr->levels; ++i)
     {
-        DFX_REQUIRE(make_view<float>(&pyr->level[i], DFX_FORMAT_R32F, lv[i]), "bad Hi-Z level %d", i);
-        DFX_REQUIRE(i == 0 || (lv[i].w == max(lv[0].w >> i, 1) && lv[i].h == max(lv[0].h >> i, 1)), "Hi-Z level %d has the wrong size", i);
+        DFX_REQUIRE(make_view<float>(&pyr->level[i], DFX_FORMAT_R32F, P.lv[0][i]), "bad Hi-Z level %d", i);
+        DFX_REQUIRE(i == 0 || (P.lv[0][i].w == max(P.lv[0][0].w >> i, 1) && P.lv[0][i].h == max(P.lv[0][0].h >> i, 1)), "Hi-Z level %d has the wrong size", i);
     }
-    const int H = lv[0].h;
+    const int H = P.lv[0][0].h;
     DFX_REQUIRE(rows_ok(rows, H) && rows.y0 % 64 == 0 && (rows.y1 % 64 == 0 || rows.y1 == H), "pyramid passes need 64-row aligned strips");
-    for (int m = 1; m < pyr->levels && m <= 6; ++m)
-    {
-        const int r0 = ssr_mip_row(rows.y0, m, H, lv[m].h), r1 = ssr_mip_row(rows.y1, m, H, lv[m].h);
-        if (r1 <= r0) continue;
-        dim3 block(32, 8), grid(div_up(lv[m].w, 32), div_up(r1 - r0, 8));
-        View<const float> src{lv[m - 1].p, lv[m - 1].pitch, lv[m - 1].w, lv[m - 1].h};
-        ssr_hiz_level_kernel<<<grid, block, 0, as_stream(stream)>>>(src, lv[m], r0, r1, reversed_depth(&pyr->level[0]));
-        DFX_LAUNCHED("ssr_hiz_level_kernel");
-    }
-    return DFX_OK;
+    return build_pyramid(stream, HizOp{reversed_depth(&pyr->level[0])}, P, 6, rows, "ssr_hiz pyramid kernel");
 }
 
 #define DFX_GRID(w, rows) dim3 block(32, 8), grid(div_up(w, 32), div_up(rows.y1 - rows.y0, 8))

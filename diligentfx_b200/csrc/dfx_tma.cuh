@@ -1,11 +1,8 @@
 // dfx_tma.cuh — the few TMA / mbarrier primitives the tile-staging kernels use (sm_100a), behind plain functions so that the
-// kernels read as ordinary code. Only compiled into the library when a TMA variant is enabled (-DDFX_BLOOM_TMA=1): round-1
-// builds do not contain it. The host-side helper builds a 2-D tensor map over a pitched RGBA32F plane through the driver
-// entry point, so the library keeps depending on libcudart only.
-//
-// A float4 texel is described to the TMA unit as two 64-bit elements (the widest element type a tensor map knows), which keeps
-// the 68-texel-wide Bloom tile inside the 256-element box limit. Out-of-range parts of a box are filled with zeros — the
-// border(0) addressing the Bloom down-sampling taps use (Bloom.cpp:185, :219).
+// kernels read as ordinary code. The host-side helpers build 2-D tensor maps over pitched planes through the driver entry
+// point, so the library keeps depending on libcudart only. Out-of-range parts of a box are filled with zeros.
+// (First run on a B200 in round 2: profiles/r2a — a Bloom variant staging its tile through these primitives produced the same
+// frames as the plain-load kernel.)
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -46,6 +43,26 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_addr(dst)),
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(x), "r"(y)
                  : "memory");
+}
+
+// Host: tensor map over a pitched plane of fp32 texels (width x height, pitch in bytes), box = box_w x box_h texels (each <= 256).
+inline bool make_tensor_map_r32f(CUtensorMap* map, const void* base, int width, int height, size_t pitch_bytes, int box_w, int box_h)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void*                           fn = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<encode_fn>(fn);
+    }();
+    if (!encode || (pitch_bytes % 16) != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0 || box_w > 256 || box_h > 256 || (box_w * 4) % 16 != 0) return false;
+    const cuuint64_t dims[2]    = {cuuint64_t(width), cuuint64_t(height)};
+    const cuuint64_t strides[1] = {cuuint64_t(pitch_bytes)};
+    const cuuint32_t box[2]     = {cuuint32_t(box_w), cuuint32_t(box_h)};
+    const cuuint32_t estr[2]    = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Host: tensor map over a pitched plane of 16-byte texels (width x height texels, pitch in bytes), box = box_w x box_h texels.

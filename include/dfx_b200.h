@@ -226,6 +226,7 @@ typedef struct dfx_tonemap_attribs
 DFX_API void dfx_ssao_attribs_default(dfx_ssao_attribs* a);
 DFX_API void dfx_ssr_attribs_default(dfx_ssr_attribs* a);
 DFX_API void dfx_bloom_attribs_default(dfx_bloom_attribs* a);
+DFX_API void dfx_dof_attribs_default(dfx_dof_attribs* a);
 DFX_API void dfx_taa_attribs_default(dfx_taa_attribs* a);
 DFX_API void dfx_tonemap_attribs_default(dfx_tonemap_attribs* a);
 
@@ -733,6 +734,86 @@ DFX_API dfx_status dfx_profile_collect(void);                 /* waits for the r
 DFX_API void       dfx_profile_reset(void);
 DFX_API int32_t    dfx_profile_count(void);
 DFX_API dfx_status dfx_profile_entry(int32_t i, char* name, int32_t name_cap, double* total_ms, int32_t* calls);
+
+/* ============================================================================================================ */
+/* 3. chain level: the whole PostProcess chain of one view, one call per frame                                    */
+/* ============================================================================================================ */
+/* Owns one PostFXContext, SSAO, SSR, TAA, DepthOfField and Bloom object and runs them in the order of the reference's only in-tree
+ * integration (Hydrogent/src/Tasks/HnPostProcessTask.cpp: Prepare :591-683, Execute :743-947):
+ *   PostFXContext -> SSR -> SSAO -> compose -> TAA -> [DepthOfField] -> Bloom -> ToneMap(+sRGB).
+ * The SSAO passes run beside the SSR passes on a second stream, Bloom + ToneMap of frame f beside the front half of frame f+1
+ * on a third; in steady state (consecutive frame indices, no history reset, constant attributes) the launches are replayed
+ * from CUDA graphs cached per (input planes, ping-pong parity, configuration). Results are bit-identical whichever way a frame
+ * is issued. Not thread-safe: one chain per view / stream of frames, like the reference's effect objects. */
+#define DFX_CHAIN_STAGE_POSTFX  1u
+#define DFX_CHAIN_STAGE_SSR     2u
+#define DFX_CHAIN_STAGE_SSAO    4u
+#define DFX_CHAIN_STAGE_COMPOSE 8u
+#define DFX_CHAIN_STAGE_TAA     16u
+#define DFX_CHAIN_STAGE_BLOOM   32u
+#define DFX_CHAIN_STAGE_TONEMAP 64u
+#define DFX_CHAIN_STAGE_ALL     127u
+
+typedef struct dfx_chain_config
+{
+    dfx_ssao_attribs    ssao;
+    dfx_ssr_attribs     ssr;
+    dfx_bloom_attribs   bloom;
+    dfx_taa_attribs     taa;
+    dfx_tonemap_attribs tonemap;
+    dfx_dof_attribs     dof;
+    uint32_t postfx_flags, ssao_flags, ssr_flags, taa_flags, dof_flags; /* DFX_*_FEATURE_FLAG_* */
+    uint32_t stages;      /* DFX_CHAIN_STAGE_* mask                                                                          */
+    int32_t  enable_dof;  /* DepthOfField between TAA and Bloom (HnPostProcessTask.cpp:899-909)                                */
+    int32_t  fuse;        /* compose inside TAA, ToneMap inside the Bloom composite (same arithmetic, two HBM round trips fewer) */
+    int32_t  overlap;     /* async compute on three streams                                                                  */
+    int32_t  use_graph;   /* replay steady-state frames from CUDA graphs                                                     */
+    int32_t  to_srgb;     /* LinearToSRGB after the tone map (HnCopyFrame.psh:60-62)                                         */
+    float    ave_log_lum; /* HnPostProcessTask.hpp:88                                                                        */
+    float    ssr_scale, ssao_scale; /* compose: rgb += ssr.rgb * ssr.a * ssr_scale; rgb *= lerp(1, ao, ssao_scale)           */
+    int32_t  reserved;
+} dfx_chain_config;
+
+typedef struct dfx_chain_frame
+{
+    uint32_t                  frame_index;  /* FrameDesc.Index: consecutive, or the histories reset                          */
+    int32_t                   defer_post;   /* 1: return without making `stream` wait for Bloom + ToneMap (dfx_chain_join)    */
+    const dfx_camera_attribs* curr_camera;  /* host pointers                                                                 */
+    const dfx_camera_attribs* prev_camera;
+    const dfx_plane*          depth;        /* R32F    */
+    const dfx_plane*          prev_depth;   /* R32F    */
+    const dfx_plane*          motion;       /* RG32F   */
+    const dfx_plane*          normal;       /* RGBA32F */
+    const dfx_plane*          color;        /* RGBA32F */
+    const dfx_plane*          material;     /* RGBA32F */
+    const dfx_plane*          ldr_out;      /* RGBA32F: the tone-mapped frame                                                */
+} dfx_chain_frame;
+
+typedef struct dfx_chain_stats
+{
+    uint64_t frames_eager, frames_replayed, graphs_built, graph_failures;
+} dfx_chain_stats;
+
+typedef enum dfx_chain_effect_id
+{
+    DFX_CHAIN_EFFECT_POSTFX = 0, DFX_CHAIN_EFFECT_SSAO = 1, DFX_CHAIN_EFFECT_SSR = 2, DFX_CHAIN_EFFECT_BLOOM = 3, DFX_CHAIN_EFFECT_TAA = 4, DFX_CHAIN_EFFECT_DOF = 5
+} dfx_chain_effect_id;
+
+typedef struct dfx_chain dfx_chain;
+DFX_API void       dfx_chain_config_default(dfx_chain_config* config); /* reference struct defaults, Hydrogent's TAA flags, every stage, fused, async, graphs */
+DFX_API dfx_status dfx_chain_create(int32_t width, int32_t height, const dfx_chain_config* config /* NULL = defaults */, dfx_chain** out);
+DFX_API void       dfx_chain_destroy(dfx_chain* chain);
+DFX_API dfx_status dfx_chain_set_config(dfx_chain* chain, const dfx_chain_config* config);
+DFX_API dfx_status dfx_chain_get_config(const dfx_chain* chain, dfx_chain_config* out);
+/* Runs one frame, ordered after the work already on `stream`; the frame's LDR plane is complete in stream order when the call
+ * returns (defer_post = 0) or after dfx_chain_join (defer_post = 1). */
+DFX_API dfx_status dfx_chain_execute(dfx_chain* chain, void* stream, const dfx_chain_frame* frame);
+DFX_API dfx_status dfx_chain_join(dfx_chain* chain, void* stream);
+/* The effect objects (dfx_postfx*, dfx_ssao*, ...) for dfx_*_get_plane / dfx_*_set_alpha_interpolation; owned by the chain. */
+DFX_API void*      dfx_chain_effect(dfx_chain* chain, int32_t which /* dfx_chain_effect_id */);
+/* The stream Bloom + ToneMap run on when `overlap` is set (to order a read-back after a deferred frame). */
+DFX_API void*      dfx_chain_post_stream(dfx_chain* chain);
+DFX_API dfx_status dfx_chain_get_stats(const dfx_chain* chain, dfx_chain_stats* out);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -98,3 +98,22 @@ def test_no_oracle_or_cpu_fallback_in_product_sources():
                     if re.search(r"oracle[_/]|liboracle|from oracle|import oracle", txt) and f not in ("capi.py",):
                         offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_chain_level_layouts_and_defaults():
+    """dfx_chain_config / dfx_chain_frame as seen from ctypes match the header (the library static_asserts the same size), and the
+    defaults are the reference's struct defaults with Hydrogent's TAA flags (HnPostProcessTask.hpp:109)."""
+    lib = capi.load()
+    assert C.sizeof(capi.ChainConfigC) == 284 and C.sizeof(capi.ChainFrame) == 80
+    c = capi.ChainConfigC()
+    lib.dfx_chain_config_default(C.byref(c))
+    assert bytes(c.ssao) == bytes(capi.SSAOAttribs.default()) and bytes(c.ssr) == bytes(capi.SSRAttribs.default())
+    assert bytes(c.bloom) == bytes(capi.BloomAttribs.default()) and bytes(c.taa) == bytes(capi.TAAAttribs.default())
+    assert bytes(c.tonemap) == bytes(capi.ToneMapAttribs.default()) and bytes(c.dof) == bytes(capi.DOFAttribs.default())
+    assert (c.stages, c.fuse, c.overlap, c.use_graph, c.to_srgb, c.taa_flags, c.enable_dof) == (127, 1, 1, 1, 1, capi.TAA_FLAG_BICUBIC, 0)
+    assert abs(c.ave_log_lum - 0.3) < 1e-7 and c.ssr_scale == 1.0 and c.ssao_scale == 1.0
+    assert lib.dfx_chain_execute(None, None, None) == capi.DFX_ERR_INVALID_ARG
+    # tuning knobs: unknown names read as the fallback, set values stick
+    assert lib.dfx_tune_get(b"no_such_knob", 7) == 7
+    lib.dfx_tune_set(b"unit_test_knob", 3)
+    assert lib.dfx_tune_get(b"unit_test_knob", 0) == 3
