@@ -967,8 +967,18 @@ extern "C" void dfx_chain_destroy(dfx_chain* c) { delete c; }
 extern "C" dfx_status dfx_chain_set_config(dfx_chain* c, const dfx_chain_config* config)
 {
     DFX_REQUIRE(c && config, "null argument");
-    c->cfg = *config; // the graph cache is keyed by the configuration bytes: stale entries are simply never hit again
-    if (c->graphs.size() > 16) c->drop_graphs();
+    // The graph cache is keyed by the configuration bytes, so a change of attribute values just stops hitting the old entries. A
+    // change of feature flags or stages, however, makes the effects re-create their planes: every recorded graph then points at
+    // freed memory and must go.
+    const dfx_chain_config& o = c->cfg;
+    const bool realloc = o.postfx_flags != config->postfx_flags || o.ssao_flags != config->ssao_flags || o.ssr_flags != config->ssr_flags || o.taa_flags != config->taa_flags ||
+                         o.dof_flags != config->dof_flags || o.enable_dof != config->enable_dof || o.stages != config->stages || o.fuse != config->fuse;
+    if (realloc || c->graphs.size() > 16)
+    {
+        DFX_CUDA(cudaDeviceSynchronize()); // a graph that is still executing must not be destroyed
+        c->drop_graphs();
+    }
+    c->cfg = *config;
     return DFX_OK;
 }
 extern "C" dfx_status dfx_chain_get_config(const dfx_chain* c, dfx_chain_config* out)
