@@ -456,6 +456,29 @@ def main() -> None:
                            "frac": round(gbs / peak, 4)})
         for p in passes:
             p["share"] = round(p["ms"] / step_sum, 4) if step_sum else 0.0
+        # The same, in the regime where the temporal filters are LIVE: the histories are reset every 4th frame (a jump of the frame
+        # index), so the SSAO resampling / spatial reconstruction run their taps instead of the long-history early-out they take in
+        # steady state (SSAO_ComputeSpatialReconstruction.fx:65-69, SSAO_ComputeResampledHistory.fx:67-71).
+        lib.dfx_profile_reset()
+        lib.dfx_profile_enable(1)
+        chain.cfg.overlap = False
+        base = step_id[0] + 1000
+        for i in range(K):
+            slot = i % len(seq)
+            chain.execute(base + (i // 4) * 10 + (i % 4), cams[slot][0], cams[slot][1], resident[slot])
+        torch.cuda.synchronize()
+        chain.cfg.overlap = overlap
+        lib.dfx_profile_enable(0)
+        capi.check(lib.dfx_profile_collect())
+        live = {}
+        for i in range(lib.dfx_profile_count()):
+            capi.check(lib.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls)))
+            live[name.value.decode()] = tot.value / K
+        step_id[0] = base + (K // 4 + 1) * 10
+        for p in passes:
+            if p["pass"] in live:
+                ms = live[p["pass"]]
+                p["live"] = {"ms": round(ms, 4), "frac": round(p["alg_bytes"] / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 else 0.0}
         top = max(passes, key=lambda p: p["ms"])
         traffic, traffic_src = ncu_traffic(top["pass"], W, H)
         roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,

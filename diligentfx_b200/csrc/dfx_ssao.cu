@@ -503,6 +503,90 @@ __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attr
     st_cs(&out.at(x, y), lerpf(1.0f, o, A.AlphaInterpolation));
 }
 
+// A8 with the tap window staged in shared memory. Every tap lands within +-4 pixels of its pixel (radius <= SpatialReconstructionRadius
+// = 4, |Poisson sample| < 1), so a 32x8 CTA needs the 40x16 window of the depth and of the resampled AO: two TMA 2-D tile loads
+// (cp.async.bulk.tensor; the parts of a box beyond the plane arrive as zeros and are never read - tap coordinates are clamped to
+// the plane first). The depth window is converted to view-space Z once per texel instead of once per tap, and the plane distance
+// dot(tapVS - centreVS, N) is evaluated as z_tap * dot(ray(tap), N) - dot(centreVS, N). CTAs in which no pixel needs the filter
+// (background, or a history long enough for the early-out of :65-69 - the steady state) never issue the loads.
+struct SpatialMaps
+{
+    CUtensorMap depth, occ;
+};
+constexpr int kSpTileW = 40, kSpTileH = 16;
+
+__global__ void __launch_bounds__(256) ssao_spatial_tile_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, const __grid_constant__ SpatialMaps maps,
+                                                                View<const float> occlusion, View<const float> history, View<const float> depth,
+                                                                View<const float4> normal, View<float> out, int y0, int y1, int rev)
+{
+    __shared__ SsaoCam                  S;
+    __shared__ __align__(128) float     tz[kSpTileH][kSpTileW];
+    __shared__ __align__(128) float     to[kSpTileH][kSpTileW];
+    __shared__ __align__(8) uint64_t    bar;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) mbar_init(&bar, 1);
+    stage_cam(S, cams); // __syncthreads inside
+    const CamS&   cam = S.c;
+    const PixelXY pix = cta_pixel(y0);
+    const int     x = pix.x, y = pix.y;
+    const bool    inside = x < out.w && y < y1;
+    float         hist = 0.f, d = 0.f, occC = 0.f, hq = 2.f;
+    bool          live = false;
+    if (inside)
+    {
+        hist = __ldg(&history.at(x, y)), d = __ldg(&depth.at(x, y)), occC = __ldg(&occlusion.at(x, y));
+        hq   = fabsf((hist - 1.0f) / 8.0f);
+        live = !(is_background(d, rev) || hq >= 1.0f);
+        if (!live) st_cs(&out.at(x, y), lerpf(1.0f, occC, A.AlphaInterpolation));
+    }
+    if (!__syncthreads_or(live)) return;
+    const int X0 = int(blockIdx.x) * 32 - 4, Y0 = y0 + int(blockIdx.y) * 8 - 4;
+    if (tid == 0)
+    {
+        mbar_arrive_expect_tx(&bar, uint32_t(sizeof(tz) + sizeof(to)));
+        tma_load_2d(&tz[0][0], &maps.depth, X0, Y0, &bar);
+        tma_load_2d(&to[0][0], &maps.occ, X0, Y0, &bar);
+    }
+    mbar_wait(&bar, 0);
+    for (int i = tid; i < kSpTileW * kSpTileH; i += 256) // depth -> view-space Z, once per staged texel
+    {
+        float* p = &tz[0][0] + i;
+        *p       = fdiv(cam.m32 - *p * cam.m33, *p * cam.m23 - cam.m22);
+    }
+    __syncthreads();
+    if (!live) return;
+    const float  acc = __powf(hq, 0.2f);
+    const int    W = (int)cam.vw, H = (int)cam.vh;
+    const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
+    const float  kx = 2.0f * frcp(cam.m00), ky = -2.0f * frcp(cam.m11);
+    const float  zc = tz[y - Y0][x - X0];
+    const float3 pvs = make_float3(zc * (posx * cam.ivw - 0.5f) * kx, zc * (posy * cam.ivh - 0.5f) * ky, zc);
+    const float3 nvs = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    const float  pn  = dot(pvs, nvs);
+    float        rs, rc;
+    __sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
+    const float radius    = lerpf(0.0f, A.SpatialReconstructionRadius, 1.0f - saturate(acc));
+    const float planeNorm = fdiv(10.0f, 1.0f + pvs.z);
+    // ray(tap) . N = ((sx + 0.5) * ivw - 0.5) * kx * N.x + ((sy + 0.5) * ivh - 0.5) * ky * N.y + N.z, linear in the integer tap position
+    const float gx = cam.ivw * kx * nvs.x, gy = cam.ivh * ky * nvs.y, g0 = (0.5f * cam.ivw - 0.5f) * kx * nvs.x + (0.5f * cam.ivh - 0.5f) * ky * nvs.y + nvs.z;
+    float       osum = 0.0f, wsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        const float3 P = kPoisson8[i];
+        const float  xi = P.x * rc + P.y * rs, yi = P.x * -rs + P.y * rc;
+        const int    sx = min(max((int)(posx + radius * xi), 0), W - 1), sy = min(max((int)(posy + radius * yi), 0), H - 1);
+        const float  sz = tz[sy - Y0][sx - X0], so = to[sy - Y0][sx - X0];
+        const float  dist = sz * (float(sx) * gx + float(sy) * gy + g0) - pn;
+        const float  wz   = saturate(1.0f - fabsf(dist) * planeNorm);
+        const float  ws   = kPoisson8Weight[i];
+        osum += ws * wz * so;
+        wsum += ws * wz;
+    }
+    const float o = wsum > 0.0f ? osum / wsum : occC;
+    st_cs(&out.at(x, y), lerpf(1.0f, o, A.AlphaInterpolation));
+}
+
 static bool make_pyr(const dfx_pyramid* p, PyrView& v, int min_levels)
 {
     if (!p || p->levels < min_levels || p->levels > DFX_MAX_MIPS) return false;
@@ -706,7 +790,17 @@ extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attri
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
-    ssao_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1, rev);
+    // dfx_tune("ssao_spatial_impl"): 1 (default) = tap window staged by TMA, 0 = taps gathered from HBM / L1
+    const CUtensorMap *md = nullptr, *mo = nullptr;
+    if (tune("ssao_spatial_impl", 1) == 1 && attribs->SpatialReconstructionRadius <= 4.0f)
+    {
+        md = tensor_map_r32f(View<float>{const_cast<float*>(d.p), d.pitch, d.w, d.h}, kSpTileW, kSpTileH);
+        mo = tensor_map_r32f(View<float>{const_cast<float*>(o.p), o.pitch, o.w, o.h}, kSpTileW, kSpTileH);
+    }
+    if (md && mo)
+        ssao_spatial_tile_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, SpatialMaps{*md, *mo}, o, h, d, n, out, rows.y0, rows.y1, rev);
+    else
+        ssao_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1, rev);
     DFX_LAUNCHED("ssao_spatial_kernel");
     return DFX_OK;
 }

@@ -8,6 +8,7 @@ run() { name=$1; shift; echo "== bench $name"; timeout 400 "$@" > gpurun_out/r2b
 run default python bench.py
 Q="--no-cpu-baseline --no-psnr --steps 40"
 DFX_TUNE=bloom_impl=0,bloom_tail=0 run bloom_r1 python bench.py $Q
+DFX_TUNE=ssao_spatial_impl=0 run spatial_gather python bench.py $Q
 DFX_TUNE=pyramid_impl=0 run pyr_levels python bench.py $Q
 DFX_TUNE=pyramid_impl=1 run pyr_ldg python bench.py $Q
 run nograph python bench.py $Q --no-graph
@@ -22,6 +23,8 @@ for f in sorted(glob.glob('gpurun_out/r2b_bench_*.json')):
     except Exception as e:
         print(f, 'unreadable', e); continue
     p = {x['pass']: x['ms'] for x in r['passes']}
+    live = {x['pass']: x.get('live', {}).get('ms', -1) for x in r['passes']}
+    print('   live: spatial %.4f resample %.4f temporal %.4f' % (live.get('ssao_spatial', -1), live.get('ssao_resample', -1), live.get('ssao_temporal', -1)))
     keys = ['ssr_hiz', 'ssao_prefilter_depth', 'ssao_convolute', 'bloom_prefilter', 'bloom_downsample', 'bloom_tail', 'bloom_upsample', 'bloom_composite_tonemap']
     print(f.split('r2b_bench_')[1][:-5].ljust(14), 'step %.4f e2e %.4f launches %d' % (r['ms_per_step'], r['e2e']['ms_per_step'], r['gpu_launches']), ' '.join('%s=%.4f' % (k.replace('bloom_', 'b_').replace('ssao_', 'a_'), p.get(k, -1)) for k in keys), r['config'].get('issue', {}).get('frames_replayed'), r.get('psnr', {}) and r['psnr'].get('ldr'))
 PY
