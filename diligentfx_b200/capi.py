@@ -137,6 +137,11 @@ class PeerSet(C.Structure):
                 ("normal", C.c_void_p * MAX_PEERS), ("hiz", (C.c_void_p * MAX_PEERS) * MAX_MIPS)]
 
 
+class PeerMap(C.Structure):
+    """dfx_peer_map: slab bases of the ranks sharing a frame + the 64-row aligned strip boundaries."""
+    _fields_ = [("count", C.c_int32), ("rank", C.c_int32), ("row_begin", C.c_int32 * (MAX_PEERS + 1)), ("base", C.c_void_p * MAX_PEERS)]
+
+
 class PostFXRenderAttribs(C.Structure):
     _fields_ = [("stream", C.c_void_p), ("curr_depth", C.POINTER(Plane)), ("prev_depth", C.POINTER(Plane)),
                 ("motion_vectors", C.POINTER(Plane)), ("curr_camera", C.POINTER(CameraAttribs)),

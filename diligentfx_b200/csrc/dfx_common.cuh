@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "../../include/dfx_b200.h"
 
 // Minimum resident CTAs per SM requested from ptxas for the latency-bound gather kernels (register budget = 65536 /
@@ -83,29 +84,70 @@ struct View
     int w, h;
     __device__ __forceinline__ T&       at(int x, int y) const { return p[(unsigned)(y * pitch + x)]; } // planes hold < 2^31 texels (host-checked): 32-bit index, one IMAD + one IMAD.WIDE
     __device__ __forceinline__ const T* row(int y) const { return p + (unsigned)(y * pitch); }
+    __device__ __forceinline__ typename std::remove_const<T>::type ld(int x, int y) const { return __ldg(p + (unsigned)(y * pitch + x)); } // read-only path
 };
+
+// A plane of a frame that is split into row strips over several GPUs (dfx_strips.cu): every GPU holds the plane at the same offset of
+// an identically laid-out slab, rows are owned in 64-row blocks, and a texel is loaded from the slab of the GPU that owns its row
+// (peer memory over NVLink; the own slab for own rows). `delta[g]` = byte distance from this GPU's slab to GPU g's mapping.
+constexpr int kPeerBlockShift = 6;
+constexpr int kPeerMaxBlocks  = 256; // 64-row blocks: heights up to 16384
+struct PeerMap
+{
+    long long delta[DFX_MAX_PEERS];
+    uint8_t   owner[kPeerMaxBlocks];
+};
+template <class T>
+struct PeerView
+{
+    const T*       p;
+    int            pitch, w, h;
+    const PeerMap* pm;
+    __device__ __forceinline__ T ld(int x, int y) const
+    {
+        const char* q = reinterpret_cast<const char*>(p + (unsigned)(y * pitch + x)) + pm->delta[pm->owner[y >> kPeerBlockShift]];
+        return __ldg(reinterpret_cast<const T*>(q));
+    }
+};
+
+// host: dfx_peer_map (C-ABI) -> the table the kernels index
+inline bool make_peer_map(const dfx_peer_map* m, int height, PeerMap& out)
+{
+    if (!m || m->count < 1 || m->count > DFX_MAX_PEERS || m->rank < 0 || m->rank >= m->count) return false;
+    if (m->row_begin[0] != 0 || m->row_begin[m->count] != height || ((height + 63) >> kPeerBlockShift) > kPeerMaxBlocks) return false;
+    for (int r = 0; r < m->count; ++r)
+    {
+        if (!m->base[r] || m->row_begin[r + 1] < m->row_begin[r] || (r > 0 && m->row_begin[r] % 64 != 0)) return false;
+        out.delta[r] = static_cast<long long>(reinterpret_cast<intptr_t>(m->base[r]) - reinterpret_cast<intptr_t>(m->base[m->rank]));
+    }
+    for (int r = m->count; r < DFX_MAX_PEERS; ++r) out.delta[r] = 0;
+    for (int b = 0, r = 0; b < kPeerMaxBlocks; ++b)
+    {
+        while (r + 1 < m->count && (b << kPeerBlockShift) >= m->row_begin[r + 1]) ++r;
+        out.owner[b] = (uint8_t)r;
+    }
+    return true;
+}
 
 template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
 
-// Texture.Load semantics: out of bounds -> 0
-__device__ __forceinline__ float load0(const View<const float>& v, int x, int y)
+// Texture.Load semantics: out of bounds -> 0. V = View<const T> or PeerView<T>.
+template <class T> __device__ __forceinline__ T zero_of();
+template <> __device__ __forceinline__ float  zero_of<float>() { return 0.0f; }
+template <> __device__ __forceinline__ float2 zero_of<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float4 zero_of<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <class V>
+__device__ __forceinline__ auto load0(const V& v, int x, int y) -> decltype(v.ld(0, 0))
 {
-    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (unsigned)(y * v.pitch + x)) : 0.0f;
+    using T = decltype(v.ld(0, 0));
+    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? v.ld(x, y) : zero_of<T>();
 }
-__device__ __forceinline__ float2 load0(const View<const float2>& v, int x, int y)
-{
-    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (unsigned)(y * v.pitch + x)) : make_float2(0.f, 0.f);
-}
-__device__ __forceinline__ float4 load0(const View<const float4>& v, int x, int y)
-{
-    return ((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h) ? __ldg(v.p + (unsigned)(y * v.pitch + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-template <class T>
-__device__ __forceinline__ T loadc(const View<const T>& v, int x, int y) // clamp addressing
+template <class V>
+__device__ __forceinline__ auto loadc(const V& v, int x, int y) -> decltype(v.ld(0, 0)) // clamp addressing
 {
     x = min(max(x, 0), v.w - 1);
     y = min(max(y, 0), v.h - 1);
-    return __ldg(v.p + (unsigned)(y * v.pitch + x));
+    return v.ld(x, y);
 }
 
 template <class T>
@@ -317,9 +359,10 @@ DFX_HD float3 fnormalize(float3 a) { return a * frsqrt(dot(a, a)); }
 DFX_HD float snap8(float p) { return floorf(p * 256.0f + 0.5f) * (1.0f / 256.0f); }
 
 // bilinear SampleLevel at normalised uv, clamp addressing
-template <class T>
-__device__ __forceinline__ T sample_linear_clamp(const View<const T>& t, float u, float v)
+template <class V>
+__device__ __forceinline__ auto sample_linear_clamp(const V& t, float u, float v) -> decltype(t.ld(0, 0))
 {
+    using T = decltype(t.ld(0, 0));
     float px = snap8(u * float(t.w) - 0.5f), py = snap8(v * float(t.h) - 0.5f);
     float fx0 = floorf(px), fy0 = floorf(py);
     int   x0 = (int)fx0, y0 = (int)fy0;
@@ -327,9 +370,10 @@ __device__ __forceinline__ T sample_linear_clamp(const View<const T>& t, float u
     T     a = loadc(t, x0, y0), b = loadc(t, x0 + 1, y0), c = loadc(t, x0, y0 + 1), d = loadc(t, x0 + 1, y0 + 1);
     return a * ((1.0f - fx) * (1.0f - fy)) + b * (fx * (1.0f - fy)) + c * ((1.0f - fx) * fy) + d * (fx * fy);
 }
-template <class T>
-__device__ __forceinline__ T sample_linear_border(const View<const T>& t, float u, float v)
+template <class V>
+__device__ __forceinline__ auto sample_linear_border(const V& t, float u, float v) -> decltype(t.ld(0, 0))
 {
+    using T = decltype(t.ld(0, 0));
     float px = snap8(u * float(t.w) - 0.5f), py = snap8(v * float(t.h) - 0.5f);
     float fx0 = floorf(px), fy0 = floorf(py);
     int   x0 = (int)fx0, y0 = (int)fy0;
@@ -338,8 +382,8 @@ __device__ __forceinline__ T sample_linear_border(const View<const T>& t, float 
     return a * ((1.0f - fx) * (1.0f - fy)) + b * (fx * (1.0f - fy)) + c * ((1.0f - fx) * fy) + d * (fx * fy);
 }
 // point SampleLevel at normalised uv, clamp addressing
-template <class T>
-__device__ __forceinline__ T sample_point_clamp(const View<const T>& t, float u, float v)
+template <class V>
+__device__ __forceinline__ auto sample_point_clamp(const V& t, float u, float v) -> decltype(t.ld(0, 0))
 {
     return loadc(t, (int)floorf(u * float(t.w)), (int)floorf(v * float(t.h)));
 }

@@ -132,8 +132,6 @@ DFX_HD float edge_vignette(float hx, float hy, float sw, float sh) // :192-197
 // Frame split into row strips over several GPUs (dfx_pass_ssr_intersect_peer): base pointers of the planes the march reads
 // beyond its own strip, per owning rank. Rank r owns the full-res rows [row_begin[r], row_begin[r+1]); boundaries are
 // multiples of 64 so row y of level k is owned by the owner of full-res row y << k.
-constexpr int kPeerBlockShift = 6;
-constexpr int kPeerMaxBlocks  = 256; // 64-row blocks: heights up to 16384
 struct PeerArgs
 {
     const float*  hiz[DFX_MAX_MIPS][DFX_MAX_PEERS];
@@ -502,12 +500,29 @@ DFX_HD float disocclusion_ratio(float cz, float pz)
 constexpr float kNegLn090 = 0.105360516f; // -ln(SSR_DISOCCLUSION_THRESHOLD)
 constexpr float kNegLn045 = 0.798507696f; // -ln(SSR_DISOCCLUSION_THRESHOLD / 2)
 
+// PEER: the three previous-frame planes (read at the reprojected position, which no fixed halo bounds) are loaded from the GPU that
+// owns the row (PeerView); everything else is read at the pixel or within +-1 row of it.
+struct NoPeerMap
+{
+};
+template <bool PEER>
 __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
                                                            View<const uint8_t> mask, View<const float2> motion, View<const float> hit_depth,
                                                            View<const float> curr_depth, View<const float4> curr_rad, View<const float> curr_var,
-                                                           View<const float> prev_depth, View<const float4> prev_rad, View<const float> prev_var,
-                                                           View<float4> out_rad, View<float> out_var, int y0, int y1)
+                                                           View<const float> prev_depth_, View<const float4> prev_rad_, View<const float> prev_var_,
+                                                           View<float4> out_rad, View<float> out_var, int y0, int y1,
+                                                           const __grid_constant__ typename std::conditional<PEER, PeerMap, NoPeerMap>::type peer_map)
 {
+    typename std::conditional<PEER, PeerView<float>, View<const float>>::type   prev_depth, prev_var;
+    typename std::conditional<PEER, PeerView<float4>, View<const float4>>::type prev_rad;
+    if constexpr (PEER)
+    {
+        prev_depth = PeerView<float>{prev_depth_.p, prev_depth_.pitch, prev_depth_.w, prev_depth_.h, &peer_map};
+        prev_var   = PeerView<float>{prev_var_.p, prev_var_.pitch, prev_var_.w, prev_var_.h, &peer_map};
+        prev_rad   = PeerView<float4>{prev_rad_.p, prev_rad_.pitch, prev_rad_.w, prev_rad_.h, &peer_map};
+    }
+    else
+        prev_depth = prev_depth_, prev_var = prev_var_, prev_rad = prev_rad_;
     __shared__ SsrTemporalCam S;
     if (threadIdx.x == 0 && threadIdx.y == 0)
     {
@@ -895,13 +910,13 @@ extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attrib
     return DFX_OK;
 }
 
-extern "C" dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_plane* mask,
+static dfx_status ssr_temporal_impl(const dfx_peer_map* peers, void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_plane* mask,
                                             const dfx_plane* motion, const dfx_plane* hit_depth, const dfx_plane* reprojected_depth,
                                             const dfx_plane* curr_radiance, const dfx_plane* curr_variance, const dfx_plane* previous_depth,
                                             const dfx_plane* prev_radiance, const dfx_plane* prev_variance, const dfx_plane* out_radiance,
                                             const dfx_plane* out_variance, dfx_rows rows)
 {
-    DFX_PROFILE(stream, "ssr_temporal");
+    DFX_PROFILE(stream, peers ? "ssr_temporal_peer" : "ssr_temporal");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
     DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
@@ -927,9 +942,36 @@ extern "C" dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attri
     DFX_REQUIRE(rows_ok(rows, cd.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(cd.w, rows);
-    ssr_temporal_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1);
+    if (peers)
+    {
+        PeerMap pm;
+        DFX_REQUIRE(make_peer_map(peers, cd.h, pm), "bad peer map (rank count, 64-row aligned strips, slab bases)");
+        ssr_temporal_kernel<true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1, pm);
+    }
+    else
+        ssr_temporal_kernel<false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1, NoPeerMap{});
     DFX_LAUNCHED("ssr_temporal_kernel");
     return DFX_OK;
+}
+
+extern "C" dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_plane* mask,
+                                            const dfx_plane* motion, const dfx_plane* hit_depth, const dfx_plane* reprojected_depth,
+                                            const dfx_plane* curr_radiance, const dfx_plane* curr_variance, const dfx_plane* previous_depth,
+                                            const dfx_plane* prev_radiance, const dfx_plane* prev_variance, const dfx_plane* out_radiance,
+                                            const dfx_plane* out_variance, dfx_rows rows)
+{
+    return ssr_temporal_impl(nullptr, stream, cameras_dev, attribs, mask, motion, hit_depth, reprojected_depth, curr_radiance, curr_variance, previous_depth, prev_radiance,
+                             prev_variance, out_radiance, out_variance, rows);
+}
+extern "C" dfx_status dfx_pass_ssr_temporal_peer(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_peer_map* peers,
+                                                 const dfx_plane* mask, const dfx_plane* motion, const dfx_plane* hit_depth, const dfx_plane* reprojected_depth,
+                                                 const dfx_plane* curr_radiance, const dfx_plane* curr_variance, const dfx_plane* previous_depth,
+                                                 const dfx_plane* prev_radiance, const dfx_plane* prev_variance, const dfx_plane* out_radiance,
+                                                 const dfx_plane* out_variance, dfx_rows rows)
+{
+    DFX_REQUIRE(peers, "null argument");
+    return ssr_temporal_impl(peers, stream, cameras_dev, attribs, mask, motion, hit_depth, reprojected_depth, curr_radiance, curr_variance, previous_depth, prev_radiance,
+                             prev_variance, out_radiance, out_variance, rows);
 }
 
 extern "C" dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs, const dfx_plane* mask,

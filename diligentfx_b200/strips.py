@@ -1,5 +1,11 @@
 """Row-strip sharding of one frame across the GPUs of a box (BASELINE.json config 4).
 
+`SsrStrips` (bottom of the file) is the product path: the native executor of csrc/dfx_strips.cu (peer stores + flags for halo rows, peer
+loads for the ray march and the temporal history, no NCCL call per frame). `strip_bounds` / `reflective_block_cost` decide who owns
+which rows; `PeerSlab` allocates and exchanges the CUDA-IPC slabs once at start-up. `exchange_halo` / `gather_rows` are the generic
+NCCL / gloo row exchanges of round 1 (torch.distributed P2P): kept as host-side utilities, no longer on the frame path.
+
+
 Every rank holds FULL-SIZE planes and owns the rows `[y0, y1)` of every plane; the pass-level C-ABI computes only the owned
 rows (`dfx_rows`). Between passes the host exchanges exactly the rows the next pass reads outside its strip:
 
@@ -213,170 +219,124 @@ class PeerSlab:
         self.base = None
 
 
-class SsrStripRunner:
-    """ScreenSpaceReflection (S1-S7) + the PostFX planes it needs, one frame split into row strips over the ranks of `group`.
+class SsrStrips:
+    """ScreenSpaceReflection (S1-S7 + the PostFX planes it reads) on one row strip of a frame whose other strips other ranks compute:
+    a thin view of the native executor `dfx_ssr_strips_*` (csrc/dfx_strips.cu). All planes live in one slab per rank that every other
+    rank has mapped; halo rows travel by peer stores + flags, the ray march and the temporal pass load from the owning GPU, and a frame
+    costs this class ONE native call (no NCCL, no host synchronisation).
 
-    Reach of every pass: P1-P3 +-1 row of depth / motion; S1, S2 none (64-row aligned strips); S4 unbounded
-    (Hi-Z, colour, normal gathered); S5 +-4 rows of the intersect outputs; S6 previous-frame planes at the reprojected
-    position (|motion| is capped at MAX_MOTION_ROWS by the caller) plus +-1 row of the resolved radiance; S7 +-2 rows.
+    Two ways to get the ranks together:
+      * `SsrStrips.distributed(w, h, bounds, group)` - one process per GPU (torchrun): slabs are CUDA-IPC allocations exchanged over
+        `torch.distributed` once at start-up;
+      * `SsrStrips.virtual(w, h, bounds)` - all ranks in this process on the current device, one stream each (functional tests on
+        a single GPU: the same kernels, flags and peer addressing, minus NVLink).
     """
 
-    MAX_MOTION_ROWS = 24  # reprojection reach (motion + 3x3 search + bilinear footprint) the temporal pass is given
+    PLANES = {"depth": 0, "prev_depth": 1, "motion": 2, "normal": 3, "color": 4, "material": 5, "reproj": 6, "closest": 7, "previous_depth": 8,
+              "roughness": 15, "mask": 16, "radiance": 17, "raydir": 18, "resolved_radiance": 19, "resolved_variance": 20, "resolved_depth": 21, "out": 26}
+    INPUTS = ("depth", "prev_depth", "motion", "normal", "color", "material")
 
-    def __init__(self, width: int, height: int, group=None, device: torch.device | None = None, peer: bool = False, poison: bool = False,
-                 input_sets: int = 1, bounds: list[tuple[int, int]] | None = None):
-        """`peer=True`: no gather before the ray march — the intersect kernel loads Hi-Z / colour / normal texels straight from
-        the GPU that owns their row over NVLink (dfx_pass_ssr_intersect_peer). The runner then owns the depth / colour /
-        normal planes the peers read: `self.shared_sets[i]` for i < input_sets (a renderer that double-buffers its G-buffer
-        asks for 2). Fill a set directly and name it in execute(input_set=i), or pass other tensors to execute() and pay a
-        device copy of the strip. `poison=True` fills those planes with NaN first (tests: a texel read from a row nobody
-        wrote shows up in the output). `bounds`: explicit strips (e.g. cost-balanced, `strip_bounds(weights=…)`)."""
+    def __init__(self, width: int, height: int, bounds, rank: int, bases: list[int], device=None):
         from . import capi
-        self.capi = capi
-        self.lib = capi.load()
-        self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.w, self.h = width, height
-        self.bounds = list(bounds) if bounds is not None else strip_bounds(height, self.world)  # identical on every rank
-        assert len(self.bounds) == self.world and self.bounds[0][0] == 0 and self.bounds[-1][1] == height
-        assert all(a % STRIP_ALIGN == 0 and a <= b for a, b in self.bounds), "strip boundaries must be multiples of 64 rows"
-        self.rows = capi.Rows(*self.bounds[self.rank])
-        dev = device or torch.device("cuda", torch.cuda.current_device())
-        self.dev = dev
-        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
-        H, W = height, width
-        self.hiz = [None] + [f(max(H >> i, 1), max(W >> i, 1)) for i in range(1, 7)]
-        self.roughness, self.mask = f(H, W), torch.zeros((H, W), dtype=torch.uint8, device=dev)
-        self.radiance, self.raydir = f(H, W, 4), f(H, W, 4)
-        self.res_rad, self.res_var, self.res_depth = f(H, W, 4), f(H, W), f(H, W)
-        self.radhist, self.varhist = [f(H, W, 4), f(H, W, 4)], [f(H, W), f(H, W)]
-        self.out = f(H, W, 4)
-        self.reproj, self.closest, self.prev_depth = f(H, W), f(H, W, 2), f(H, W)
-        self.bn_xy, self.bn_zw = f(128, 128, 2), f(128, 128, 2)
+        self.capi, self.lib = capi, capi.load()
+        self.w, self.h, self.rank, self.world, self.bounds = width, height, rank, len(bounds), list(bounds)
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        assert self.bounds[0][0] == 0 and self.bounds[-1][1] == height and all(a % STRIP_ALIGN == 0 and a <= b for a, b in self.bounds)
+        pm = capi.PeerMap()
+        pm.count, pm.rank = self.world, rank
+        for r, (a, _) in enumerate(self.bounds):
+            pm.row_begin[r] = a
+        pm.row_begin[self.world] = height
+        for r in range(self.world):
+            pm.base[r] = bases[r]
+        self.handle = C.c_void_p()
         blob = open(capi.REPO_ROOT + "/diligentfx_b200/data/blue_noise_tables.bin", "rb").read()
-        self.tables = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
-        self.cams = torch.zeros(2 * 576, dtype=torch.uint8, device=dev)
-        self.comm_bytes = 0
-        self.peer = bool(peer) and self.world > 1
-        if self.peer:
-            fill = float("nan") if poison else 0.0
-            specs = {f"hiz{k}": (tuple(self.hiz[k].shape), torch.float32) for k in range(1, 7)}
-            for i in range(max(1, input_sets)):
-                specs.update({f"depth{i}": ((H, W), torch.float32), f"color{i}": ((H, W, 4), torch.float32), f"normal{i}": ((H, W, 4), torch.float32)})
-            self.slab = PeerSlab(specs, group, dev, fill)
-            self.hiz = [None] + [self.slab.local[f"hiz{k}"] for k in range(1, 7)]
-            self.shared_sets = [{n: self.slab.local[f"{n}{i}"] for n in ("depth", "color", "normal")} for i in range(max(1, input_sets))]
-            self.peer_sets = []
-            for i in range(len(self.shared_sets)):
-                ps = capi.PeerSet()
-                ps.count = self.world
-                for r, (a, _) in enumerate(self.bounds):
-                    ps.row_begin[r] = a
-                ps.row_begin[self.world] = H
-                for r in range(self.world):
-                    ps.color[r], ps.normal[r] = self.slab.ptr(f"color{i}", r), self.slab.ptr(f"normal{i}", r)
-                    ps.hiz[0][r] = self.slab.ptr(f"depth{i}", r)
-                    for k in range(1, 7):
-                        ps.hiz[k][r] = self.slab.ptr(f"hiz{k}", r)
-                self.peer_sets.append(ps)
-            self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(self.dev):
+            capi.check(self.lib.dfx_ssr_strips_create(width, height, C.byref(pm), blob, C.byref(self.handle)), "dfx_ssr_strips_create")
+        self.y0, self.y1 = self.bounds[rank]
+        self._keep = None
+
+    # ---- construction -------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def slab_bytes(width: int, height: int) -> int:
+        from . import capi
+        L = capi.load()
+        L.dfx_ssr_strips_slab_bytes.restype = C.c_size_t
+        return int(L.dfx_ssr_strips_slab_bytes(width, height))
+
+    @classmethod
+    def virtual(cls, width: int, height: int, bounds, device=None) -> list["SsrStrips"]:
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        n = cls.slab_bytes(width, height)
+        slabs = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in bounds]
+        ranks = [cls(width, height, bounds, r, [t.data_ptr() for t in slabs], dev) for r in range(len(bounds))]
+        for r, x in enumerate(ranks):
+            x._keep = slabs
+            x.stream = torch.cuda.Stream(dev)
+        torch.cuda.synchronize(dev)
+        return ranks
+
+    @classmethod
+    def distributed(cls, width: int, height: int, bounds, group=None, device=None) -> "SsrStrips":
+        slab = PeerSlab({"slab": ((cls.slab_bytes(width, height),), torch.uint8)}, group, device)
+        x = cls(width, height, bounds, dist.get_rank(group), list(slab.base), device)
+        x._keep = slab
+        x.stream = torch.cuda.current_stream(x.dev)
+        torch.cuda.synchronize(x.dev)
+        if dist.get_world_size(group) > 1:
+            dist.barrier(group)  # every rank has zeroed its slab before anybody pushes into it
+        return x
 
     def close(self):
-        """Collective in peer mode (unmaps / frees the shared slab)."""
-        if self.peer:
-            self.slab.close()
-            self.peer = False
+        if self.handle:
+            torch.cuda.synchronize(self.dev)
+            self.lib.dfx_ssr_strips_destroy(self.handle)
+            self.handle = None
+        if isinstance(self._keep, PeerSlab):
+            self._keep.close()
+        self._keep = None
 
-    def _device_barrier(self):
-        """Stream-ordered barrier over the ranks (a 4-byte all-reduce): work enqueued after it on any rank starts only when
-        the work enqueued before it on every rank has finished. Does not block the host."""
-        dist.all_reduce(self.token, group=self.group)
+    # ---- planes -------------------------------------------------------------------------------------------------------------------
+    def plane(self, name_or_id) -> "object":
+        p = self.capi.Plane()
+        self.capi.check(self.lib.dfx_ssr_strips_plane(self.handle, self.PLANES.get(name_or_id, name_or_id), C.byref(p)), "dfx_ssr_strips_plane")
+        return p
 
-    def _count(self, planes, rows: int):
-        self.comm_bytes += sum(rows * p[0].numel() * p.element_size() for p in planes)
+    def _rows_of(self, p, y0: int, y1: int):
+        q = self.capi.Plane(p.ptr + y0 * p.pitch_bytes, p.pitch_bytes, p.width, y1 - y0, p.format, p.flags)
+        return q
 
-    def execute(self, frame_index: int, inputs: dict, curr_camera, prev_camera, attribs=None, flags: int = 0,
-                input_set: int = 0) -> torch.Tensor:
-        """`inputs`: full-size device planes depth, prev_depth, motion, normal, color, material of which this rank's strip is
-        valid (everything else is filled in by the exchanges). Returns the SSR output plane (valid on the owned rows).
-        Peer mode: depth / color / normal are taken from `self.shared_sets[input_set]`; entries of `inputs` under those
-        names that are other tensors are first copied into the set (owned rows)."""
-        capi, L, B, R, g = self.capi, self.lib, self.bounds, self.rows, self.group
-        P = capi.plane_of
-        a = attribs or capi.SSRAttribs.default()
-        s = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
-        cur, prv = frame_index & 1, (frame_index + 1) & 1
-        # cameras: pinned ring + async copy. A blocking copy here would make the host wait for the previous frame's kernels every
-        # frame, i.e. serialise launch overhead with execution (measured: the difference between 1.1x and real strong scaling).
-        if not hasattr(self, "_cam_ring"):
-            self._cam_ring = [(torch.empty(2 * 576, dtype=torch.uint8).pin_memory(), torch.cuda.Event()) for _ in range(4)]
-            self._cam_next = 0
-        buf, ev = self._cam_ring[self._cam_next]
-        self._cam_next = (self._cam_next + 1) % len(self._cam_ring)
-        ev.synchronize()  # the copy issued from this slot four frames ago has executed
-        buf.copy_(torch.frombuffer(bytearray(bytes(curr_camera) + bytes(prev_camera)), dtype=torch.uint8))
-        self.cams.copy_(buf, non_blocking=True)
-        ev.record(torch.cuda.current_stream(self.dev))
-        cams = C.c_void_p(self.cams.data_ptr())
-        ck = capi.check
-        depth, motion, normal, color = inputs.get("depth"), inputs["motion"], inputs.get("normal"), inputs.get("color")
-        if self.peer:
-            if flags & capi.SSR_FLAG_PREVIOUS_FRAME:
-                raise capi.DfxError("previous-frame SSR is not supported on peer-sharded frames")
-            shared = self.shared_sets[input_set]
-            for name in ("depth", "color", "normal"):
-                if inputs.get(name) is not None and inputs[name] is not shared[name]:
-                    shared[name][R.y0:R.y1].copy_(inputs[name][R.y0:R.y1])
-            depth, normal, color = shared["depth"], shared["normal"], shared["color"]
+    def write_inputs(self, frame: dict, rows: tuple[int, int] | None = None, stream=None):
+        """Host planes (numpy, full frame) -> this rank's slab, the owned rows only (what a renderer that shards its G-buffer pass the
+        same way would produce in place)."""
+        import numpy as np
+        y0, y1 = rows or (self.y0, self.y1)
+        s = C.c_void_p((stream or torch.cuda.current_stream(self.dev)).cuda_stream)
+        for name in self.INPUTS:
+            a = np.ascontiguousarray(frame[name][y0:y1], np.float32)
+            q = self._rows_of(self.plane(name), y0, y1)
+            self.capi.check(self.lib.dfx_plane_upload(s, C.byref(q), a.ctypes.data_as(C.c_void_p), 0), "dfx_plane_upload")
+        self.capi.check(self.lib.dfx_stream_synchronize(s))  # pageable source
 
-        # PostFX prep: 3x3 closest-depth search -> +-1 row of depth and motion; previous depth: reprojection reach
-        # (peer mode: S5 / S7 read depth and normal of up to 4 rows beyond the strip, which the gather would have provided)
-        if self.peer:
-            exchange_halo([depth, normal], B, 4, g)
-            exchange_halo([motion], B, 1, g)
-        else:
-            exchange_halo([depth, motion], B, 1, g)
-        exchange_halo([inputs["prev_depth"]], B, self.MAX_MOTION_ROWS, g)
-        ck(L.dfx_pass_blue_noise(s, C.c_void_p(self.tables.data_ptr()), frame_index, C.byref(P(self.bn_xy)), C.byref(P(self.bn_zw))))
-        # the copy of the previous depth has to cover the halo rows the temporal pass will read: widen the row range
-        y0w, y1w = max(R.y0 - self.MAX_MOTION_ROWS, 0), min(R.y1 + self.MAX_MOTION_ROWS, self.h)
-        ck(L.dfx_pass_postfx_prepare(s, cams, C.byref(P(depth)), C.byref(P(inputs["prev_depth"])), C.byref(P(motion)), C.byref(P(self.reproj)),
-                                     C.byref(P(self.closest)), C.byref(P(self.prev_depth)), R))
-        self.prev_depth[y0w:R.y0].copy_(inputs["prev_depth"][y0w:R.y0])
-        self.prev_depth[R.y1:y1w].copy_(inputs["prev_depth"][R.y1:y1w])
+    def read(self, name: str, rows: tuple[int, int] | None = None):
+        import numpy as np
+        y0, y1 = rows or (self.y0, self.y1)
+        p = self.plane(name)
+        ch = {self.capi.FORMAT_R32F: 1, self.capi.FORMAT_RG32F: 2, self.capi.FORMAT_RGBA32F: 4}[p.format]
+        out = np.empty((y1 - y0, p.width) if ch == 1 else (y1 - y0, p.width, ch), np.float32)
+        torch.cuda.synchronize(self.dev)
+        q = self._rows_of(p, y0, y1)
+        self.capi.check(self.lib.dfx_plane_download(None, C.byref(q), out.ctypes.data_as(C.c_void_p), 0), "dfx_plane_download")
+        self.capi.check(self.lib.dfx_stream_synchronize(None))
+        return out
 
-        # S1 + S2 on the owned rows, then make Hi-Z / colour / normal complete everywhere for the ray march
-        pyr = capi.pyramid_of([depth] + self.hiz[1:])
-        ck(L.dfx_pass_ssr_hiz(s, C.byref(pyr), R))
-        ck(L.dfx_pass_ssr_mask_roughness(s, C.byref(a), C.byref(P(inputs["material"])), C.byref(P(depth)), C.byref(P(self.roughness)), C.byref(P(self.mask)), R))
-        if self.peer:
-            # S4 with peer loads: every rank's Hi-Z / colour / normal strips must be complete before anybody marches, and
-            # every march must be over before anybody overwrites them (next frame) -> one device barrier on either side
-            self._device_barrier()
-            ck(L.dfx_pass_ssr_intersect_peer(s, cams, C.byref(a), flags, C.byref(self.peer_sets[input_set]), C.byref(P(color)), C.byref(P(normal)),
-                                             C.byref(P(self.roughness)), C.byref(P(self.mask)), C.byref(P(self.bn_xy)), C.byref(pyr),
-                                             C.byref(P(self.radiance)), C.byref(P(self.raydir)), R))
-            self._device_barrier()
-        else:
-            gather_rows([depth, color, normal] + ([motion] if flags & capi.SSR_FLAG_PREVIOUS_FRAME else []), B, g)
-            for k in range(1, 7):
-                gather_rows([self.hiz[k]], B, g, row_shift=k)
-            # S4
-            ck(L.dfx_pass_ssr_intersect(s, cams, C.byref(a), flags, C.byref(P(color)), C.byref(P(normal)), C.byref(P(self.roughness)), C.byref(P(self.mask)),
-                                        C.byref(P(self.bn_xy)), C.byref(pyr), C.byref(P(motion)), C.byref(P(self.radiance)), C.byref(P(self.raydir)), R))
-        # S5: 8-tap disk of radius <= 4 px
-        exchange_halo([self.radiance, self.raydir], B, 4, g)
-        ck(L.dfx_pass_ssr_spatial(s, cams, C.byref(a), C.byref(P(self.roughness)), C.byref(P(self.mask)), C.byref(P(normal)), C.byref(P(depth)),
-                                  C.byref(P(self.raydir)), C.byref(P(self.radiance)), C.byref(P(self.res_rad)), C.byref(P(self.res_var)),
-                                  C.byref(P(self.res_depth)), R))
-        # S6: 3x3 statistics of the resolved radiance; history of the previous frame at the reprojected position
-        exchange_halo([self.res_rad], B, 1, g)
-        exchange_halo([self.radhist[prv], self.varhist[prv]], B, self.MAX_MOTION_ROWS, g)
-        ck(L.dfx_pass_ssr_temporal(s, cams, C.byref(a), C.byref(P(self.mask)), C.byref(P(motion)), C.byref(P(self.res_depth)), C.byref(P(self.reproj)),
-                                   C.byref(P(self.res_rad)), C.byref(P(self.res_var)), C.byref(P(self.prev_depth)), C.byref(P(self.radhist[prv])),
-                                   C.byref(P(self.varhist[prv])), C.byref(P(self.radhist[cur])), C.byref(P(self.varhist[cur])), R))
-        # S7: (2r+1)^2 window, r <= 2, reads roughness / radiance of the neighbours (normal and depth are already complete)
-        exchange_halo([self.radhist[cur], self.roughness], B, 2, g)
-        ck(L.dfx_pass_ssr_bilateral(s, cams, C.byref(a), C.byref(P(self.mask)), C.byref(P(depth)), C.byref(P(normal)), C.byref(P(self.roughness)),
-                                    C.byref(P(self.radhist[cur])), C.byref(P(self.varhist[cur])), C.byref(P(self.out)), R))
-        return self.out
+    # ---- one frame ----------------------------------------------------------------------------------------------------------------
+    def execute(self, frame_index: int, curr_camera, prev_camera, attribs=None, stream=None):
+        a = attribs or self.capi.SSRAttribs.default()
+        s = C.c_void_p((stream or getattr(self, "stream", None) or torch.cuda.current_stream(self.dev)).cuda_stream)
+        self.capi.check(self.lib.dfx_ssr_strips_execute(self.handle, s, frame_index, C.byref(curr_camera), C.byref(prev_camera), C.byref(a)), "dfx_ssr_strips_execute")
+
+    def timed_out(self) -> bool:
+        t = C.c_int32()
+        self.capi.check(self.lib.dfx_ssr_strips_check(self.handle, C.byref(t)))
+        return bool(t.value)

@@ -372,6 +372,14 @@ typedef struct dfx_peer_set {
     const void* normal[DFX_MAX_PEERS];
     const void* hiz[DFX_MAX_MIPS][DFX_MAX_PEERS];       /* level 0 = the depth plane                                   */
 } dfx_peer_set;
+/* The same frame-sharding description in the form the strips executor (section 4) uses: every rank holds ALL planes at the same
+ * offsets of an identically laid-out slab; base[r] is rank r's slab as mapped into this process (dfx_ipc_open), so the copy of any
+ * plane on rank r is at (plane pointer - base[rank] + base[r]). Rows are owned in 64-row blocks: rank r owns [row_begin[r], row_begin[r+1]). */
+typedef struct dfx_peer_map {
+    int32_t     count, rank;
+    int32_t     row_begin[DFX_MAX_PEERS + 1];
+    const void* base[DFX_MAX_PEERS];
+} dfx_peer_map;
 DFX_API dfx_status dfx_pass_ssr_intersect_peer(void* stream, const dfx_camera_attribs* cameras_dev,
                                                const dfx_ssr_attribs* attribs, uint32_t flags, const dfx_peer_set* peers,
                                                const dfx_plane* color, const dfx_plane* normal, const dfx_plane* roughness,
@@ -406,6 +414,17 @@ DFX_API dfx_status dfx_pass_ssr_temporal(void* stream, const dfx_camera_attribs*
                                          const dfx_plane* curr_variance, const dfx_plane* previous_depth,
                                          const dfx_plane* prev_radiance, const dfx_plane* prev_variance,
                                          const dfx_plane* out_radiance, const dfx_plane* out_variance, dfx_rows rows);
+
+/* S6 on a row strip of a frame sharded over several GPUs: the previous-frame planes (previous depth, radiance and variance history),
+ * which the pass reads at reprojected positions that no fixed halo bounds, are loaded from the GPU that owns the row. The three planes
+ * must lie in the caller's slab (peers->base[peers->rank]). Bit-identical to dfx_pass_ssr_temporal on complete planes. */
+DFX_API dfx_status dfx_pass_ssr_temporal_peer(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_ssr_attribs* attribs,
+                                              const dfx_peer_map* peers, const dfx_plane* mask, const dfx_plane* motion,
+                                              const dfx_plane* hit_depth, const dfx_plane* reprojected_depth,
+                                              const dfx_plane* curr_radiance, const dfx_plane* curr_variance,
+                                              const dfx_plane* previous_depth, const dfx_plane* prev_radiance,
+                                              const dfx_plane* prev_variance, const dfx_plane* out_radiance,
+                                              const dfx_plane* out_variance, dfx_rows rows);
 
 /* S7 ComputeBilateralCleanup (…cpp:1071-1104; SSR_ComputeBilateralCleanup.fx:49-97). Includes the clear to 0. */
 DFX_API dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attribs* cameras_dev,
@@ -814,6 +833,48 @@ DFX_API void*      dfx_chain_effect(dfx_chain* chain, int32_t which /* dfx_chain
 /* The stream Bloom + ToneMap run on when `overlap` is set (to order a read-back after a deferred frame). */
 DFX_API void*      dfx_chain_post_stream(dfx_chain* chain);
 DFX_API dfx_status dfx_chain_get_stats(const dfx_chain* chain, dfx_chain_stats* out);
+
+/* ============================================================================================================ */
+/* 4. one frame split into row strips over the GPUs of a box (no reference counterpart)                          */
+/* ============================================================================================================ */
+/* ScreenSpaceReflection S1-S7 (+ the PostFXContext planes they read) on the strip [row_begin[rank], row_begin[rank+1]) of a frame
+ * whose other strips are computed by other GPUs (BASELINE.json config 4). Every rank allocates one slab of
+ * dfx_ssr_strips_slab_bytes() bytes (dfx_ipc_alloc), maps the other ranks' slabs (dfx_ipc_open) and hands all base addresses
+ * over in a dfx_peer_map; all planes live in the slab at offsets that depend on the frame size only. Halo rows of bounded taps are
+ * pushed into the neighbours' slabs by a copy kernel and announced through flags in peer memory; the ray march and the temporal
+ * pass load what they need beyond the strip from the owning GPU directly (NVLink peer loads); there is no host synchronisation and
+ * no NCCL call per frame. The sharded frame is bit-identical to the unsharded one. Several ranks may also live in one process on
+ * one device (plain cudaMalloc slabs, one stream per rank): that is how the single-GPU tests cover this path. */
+typedef enum dfx_ssr_strips_plane_id
+{
+    /* inputs: the caller writes its own rows */
+    DFX_SSR_STRIPS_PLANE_DEPTH = 0, DFX_SSR_STRIPS_PLANE_PREV_DEPTH_IN = 1, DFX_SSR_STRIPS_PLANE_MOTION = 2, DFX_SSR_STRIPS_PLANE_NORMAL = 3,
+    DFX_SSR_STRIPS_PLANE_COLOR = 4, DFX_SSR_STRIPS_PLANE_MATERIAL = 5,
+    /* PostFXContext */
+    DFX_SSR_STRIPS_PLANE_REPROJECTED_DEPTH = 6, DFX_SSR_STRIPS_PLANE_CLOSEST_MOTION = 7, DFX_SSR_STRIPS_PLANE_PREVIOUS_DEPTH = 8,
+    /* SSR */
+    DFX_SSR_STRIPS_PLANE_HIZ1 = 9, /* .. HIZ6 = 14 */
+    DFX_SSR_STRIPS_PLANE_ROUGHNESS = 15, DFX_SSR_STRIPS_PLANE_MASK = 16, DFX_SSR_STRIPS_PLANE_RADIANCE = 17, DFX_SSR_STRIPS_PLANE_RAYDIR = 18,
+    DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE = 19, DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE = 20, DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH = 21,
+    DFX_SSR_STRIPS_PLANE_RADIANCE_HISTORY0 = 22, DFX_SSR_STRIPS_PLANE_RADIANCE_HISTORY1 = 23, DFX_SSR_STRIPS_PLANE_VARIANCE_HISTORY0 = 24,
+    DFX_SSR_STRIPS_PLANE_VARIANCE_HISTORY1 = 25,
+    DFX_SSR_STRIPS_PLANE_OUTPUT = 26, /* == GetSSRRadianceSRV(), valid on the own rows */
+    DFX_SSR_STRIPS_PLANE_COUNT = 27
+} dfx_ssr_strips_plane_id;
+
+typedef struct dfx_ssr_strips dfx_ssr_strips;
+DFX_API size_t     dfx_ssr_strips_slab_bytes(int32_t width, int32_t height);
+/* peers->base[peers->rank] is this rank's slab (zeroed by this call: make sure no peer touches it before all ranks have returned);
+ * blue_noise_tables: the 131,328-byte Sobol + scrambling-tile blob (host memory). */
+DFX_API dfx_status dfx_ssr_strips_create(int32_t width, int32_t height, const dfx_peer_map* peers, const uint8_t* blue_noise_tables, dfx_ssr_strips** out);
+DFX_API void       dfx_ssr_strips_destroy(dfx_ssr_strips* strips);
+DFX_API dfx_status dfx_ssr_strips_plane(const dfx_ssr_strips* strips, int32_t id, dfx_plane* out);
+DFX_API dfx_status dfx_ssr_strips_rows(const dfx_ssr_strips* strips, dfx_rows* out);
+/* One frame on this rank's strip; every rank of the map calls it for every frame. Ends with an all-rank barrier in stream order. */
+DFX_API dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* strips, void* stream, uint32_t frame_index, const dfx_camera_attribs* curr_camera,
+                                          const dfx_camera_attribs* prev_camera, const dfx_ssr_attribs* attribs);
+/* *timed_out = 1 if a flag wait of an earlier frame gave up after ~2 s (a peer never signalled). Synchronises the device. */
+DFX_API dfx_status dfx_ssr_strips_check(const dfx_ssr_strips* strips, int32_t* timed_out);
 
 #ifdef __cplusplus
 } /* extern "C" */
