@@ -1,6 +1,7 @@
 // dfx_api.cu — status / error plumbing, attribute defaults, host-side helpers and device-plane utilities of the C-ABI.
 #include "dfx_common.cuh"
 #include "dfx_tma.cuh"
+#include <nvtx3/nvToolsExt.h> // header-only: resolves the tool's injection library at run time, no link dependency
 #include <tuple>
 #include <atomic>
 #include <cstdarg>
@@ -63,8 +64,32 @@ static cudaEvent_t take_event()
     return e;
 }
 
+// NVTX range per pass, named like the reference's ScopedDebugGroup of the draw(s) the pass stands for (e.g. Bloom.cpp:298, :320;
+// ScreenSpaceAmbientOcclusion.cpp:820 ff.), so that a timeline of this library reads like a capture of the reference.
+static const char* reference_group_name(const char* pass)
+{
+    static const struct { const char *pass, *group; } kNames[] = {
+        {"blue_noise", "ComputeBlueNoiseTexture"}, {"postfx_prepare", "ComputeReprojectedDepth+ComputeClosestMotion+ComputePreviousDepth"},
+        {"ssao_downsample_depth", "ComputeDownsampledDepth"}, {"ssao_prefilter_depth", "ComputePrefilteredDepth"}, {"ssao_ambient_occlusion", "ComputeAmbientOcclusion"},
+        {"ssao_upsample", "ComputeBilateralUpsampling"}, {"ssao_temporal", "ComputeTemporalAccumulation"}, {"ssao_convolute", "ComputeConvolutedDepthHistory"},
+        {"ssao_resample", "ComputeResampledHistory"}, {"ssao_spatial", "ComputeSpatialReconstruction"},
+        {"ssr_hiz", "ComputeHierarchicalDepthBuffer"}, {"ssr_mask_roughness", "ComputeStencilMaskAndExtractRoughness"}, {"ssr_downsample_mask", "ComputeDownsampledStencilMask"},
+        {"ssr_intersect", "ComputeIntersection"}, {"ssr_intersect_peer", "ComputeIntersection"}, {"ssr_spatial", "ComputeSpatialReconstruction"},
+        {"ssr_temporal", "ComputeTemporalAccumulation"}, {"ssr_temporal_peer", "ComputeTemporalAccumulation"}, {"ssr_bilateral", "ComputeBilateralCleanup"},
+        {"bloom_prefilter", "ComputePrefilteredTexture"}, {"bloom_downsample", "ComputeDownsampledTexture"}, {"bloom_tail", "ComputeDownsampledTexture+ComputeUpsampledTexture"},
+        {"bloom_upsample", "ComputeUpsampledTexture"}, {"bloom_composite", "ComputeUpsampledTexture"}, {"bloom_composite_tonemap", "ComputeUpsampledTexture+ToneMap"},
+        {"taa", "TemporalAccumulation"}, {"compose_taa", "HnPostProcess+TemporalAccumulation"}, {"compose", "HnPostProcess"}, {"tonemap", "ToneMap"},
+        {"dof_coc", "ComputeCircleOfConfusion"}, {"dof_temporal_coc", "ComputeTemporalCircleOfConfusion"}, {"dof_separated_coc", "ComputeSeparatedCircleOfConfusion"},
+        {"dof_dilation", "ComputeHierarchicalCoC"}, {"dof_blur_coc", "ComputeCircleOfConfusionBlur"}, {"dof_prefilter", "ComputePrefilteredTexture"},
+        {"dof_postfilter", "ComputePostFilteredTexture"}, {"dof_combine", "ComputeCombinedTexture"}};
+    for (const auto& n : kNames)
+        if (strcmp(n.pass, pass) == 0) return n.group;
+    return pass;
+}
+
 ProfileScope::ProfileScope(void* stream, const char* name) : s(static_cast<cudaStream_t>(stream)), slot(-1)
 {
+    nvtxRangePushA(reference_group_name(name));
     if (!g_profile_on) return;
     ProfileRecord r{name, take_event(), take_event()};
     cudaEventRecord(r.a, s);
@@ -74,7 +99,11 @@ ProfileScope::ProfileScope(void* stream, const char* name) : s(static_cast<cudaS
 ProfileScope::~ProfileScope()
 {
     if (slot >= 0) cudaEventRecord(g_records[slot].b, s);
+    nvtxRangePop();
 }
+
+EffectRange::EffectRange(const char* name) { nvtxRangePushA(name); }
+EffectRange::~EffectRange() { nvtxRangePop(); }
 
 __global__ void fill_kernel(float* p, int pitch_f, int wf, int h, int ch, float4 v)
 {

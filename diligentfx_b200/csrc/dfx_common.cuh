@@ -69,6 +69,12 @@ struct ProfileScope
     ~ProfileScope();
 };
 #define DFX_PROFILE(stream, name) ::dfx::ProfileScope profile_scope__(stream, name)
+// NVTX range around an effect's Execute(), named like the reference's outer ScopedDebugGroup ("ScreenSpaceAmbientOcclusion", "Bloom", ...)
+struct EffectRange
+{
+    explicit EffectRange(const char* name);
+    ~EffectRange();
+};
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 inline int          div_up(int a, int b) { return (a + b - 1) / b; }

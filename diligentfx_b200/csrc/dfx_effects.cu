@@ -139,6 +139,7 @@ static dfx_status postfx_upload(dfx_postfx* c, cudaStream_t s, const dfx_camera_
 // the kernels of PostFXContext::Execute (everything they read per frame comes from device memory: the launches can be replayed from a graph)
 static dfx_status postfx_launch(dfx_postfx* c, cudaStream_t s, const dfx_plane* curr_depth, const dfx_plane* prev_depth, const dfx_plane* motion)
 {
+    EffectRange nvtx_range("PreparePostFX");
     dfx_status st;
     if ((st = launch_blue_noise(s, c->tables_dev, c->desc.Index, c->frame_dev, &c->bn_xy.p, &c->bn_zw.p)) != DFX_OK) return st;
     dfx_rows  all{0, c->h};
@@ -271,6 +272,7 @@ extern "C" dfx_status dfx_ssao_prepare(dfx_ssao* fx, dfx_postfx* postfx, uint32_
 
 extern "C" dfx_status dfx_ssao_execute(dfx_ssao* fx, const dfx_ssao_render_attribs* a)
 {
+    EffectRange nvtx_range("ScreenSpaceAmbientOcclusion");
     DFX_REQUIRE(fx && a, "null argument");
     if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_ssao_prepare was not called");
     DFX_REQUIRE(a->postfx && a->depth && a->normal && a->attribs, "postfx / depth / normal / attribs must not be null");
@@ -415,6 +417,7 @@ extern "C" dfx_status dfx_ssr_prepare(dfx_ssr* fx, dfx_postfx* postfx, uint32_t 
 
 extern "C" dfx_status dfx_ssr_execute(dfx_ssr* fx, const dfx_ssr_render_attribs* a)
 {
+    EffectRange nvtx_range("ScreenSpaceReflection");
     DFX_REQUIRE(fx && a, "null argument");
     if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_ssr_prepare was not called");
     DFX_REQUIRE(a->postfx && a->color && a->depth && a->normal && a->material && a->motion && a->attribs, "all SSR inputs must not be null");
@@ -556,6 +559,7 @@ extern "C" dfx_status dfx_bloom_execute_tonemapped(dfx_bloom* fx, const dfx_bloo
 static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attribs* a, const dfx_tonemap_attribs* tonemap, float ave_log_lum,
                                      int32_t to_srgb, const dfx_plane* ldr_out)
 {
+    EffectRange nvtx_range("Bloom");
     DFX_REQUIRE(fx && a, "null argument");
     if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_bloom_prepare was not called");
     DFX_REQUIRE(a->color && a->attribs, "color / attribs must not be null");
@@ -775,6 +779,7 @@ extern "C" dfx_status dfx_dof_prepare(dfx_dof* fx, dfx_postfx* postfx, uint32_t 
 // DepthOfField::Execute (…cpp:292-331)
 extern "C" dfx_status dfx_dof_execute(dfx_dof* fx, const dfx_dof_render_attribs* a)
 {
+    EffectRange nvtx_range("DepthOfField");
     DFX_REQUIRE(fx && a, "null argument");
     if (!fx->prepared) return set_error(DFX_ERR_NOT_PREPARED, "dfx_dof_prepare was not called");
     DFX_REQUIRE(a->postfx && a->color && a->depth && a->attribs, "postfx / color / depth / attribs must not be null");
