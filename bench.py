@@ -179,10 +179,13 @@ def psnr_vs_oracle(seq, W: int, H: int, threads: int) -> dict:
     t0 = time.perf_counter()
     chain = PostProcessChain(W, H)          # the benchmarked configuration: fused passes, async compute
     o = op.Oracle(W, H, threads=threads)
+    of = op.Oracle(W, H, threads=threads)   # the same chain with every render target rounded to the reference's texture format
+    of.set_storage(True)
     for fr in seq:
         ldr = chain.run_frame(fr)
-        o.set_inputs(fr)
-        o.frame()
+        for orc in (o, of):
+            orc.set_inputs(fr)
+            orc.frame()
     cur = seq[-1]["frame"] & 1
     got = ldr.cpu().numpy()
     want = o.get("ldr")
@@ -192,6 +195,10 @@ def psnr_vs_oracle(seq, W: int, H: int, threads: int) -> dict:
            "taa": psnr(rh(chain.fetch("taa", 0)), rh(o.get(f"taa_accum{cur}"))),
            "bloom_up0": psnr(rh(chain.fetch("bloom", 30)[..., :3]), rh(o.get("bloom_up0")[..., :3])),
            "ldr_max_abs_err": float(np.abs(np.clip(got[..., :3], 0, 1) - np.clip(want[..., :3], 0, 1)).max()),
+           # sensitivity: how far the reference's own narrow render targets (R8 AO, RGBA16F SSR / TAA, R11G11B10F Bloom)
+           # move the same frame - the kernels (fp32 planes) sit closer to the fp32 oracle than the reference's storage does
+           "reference_storage_vs_fp32_ldr": psnr(np.clip(of.get("ldr")[..., :3], 0, 1), np.clip(want[..., :3], 0, 1)),
+           "kernels_vs_reference_storage_ldr": psnr(np.clip(got[..., :3], 0, 1), np.clip(of.get("ldr")[..., :3], 0, 1)),
            "frames": len(seq), "size": [W, H], "floor_db": 49.0,
            "against": "the CPU oracle (each pass bit-exact against the reference's own HLSL shader, tests/test_reference_shaders.py), fp32 storage",
            "seconds": None}

@@ -3,6 +3,7 @@
 // whole-frame driver that sequences them exactly as the reference's host code does
 // (Hydrogent/src/Tasks/HnPostProcessTask.cpp:743-947; per-effect Execute() methods).
 #include "oracle.h"
+#include "oracle_quant.h"
 #include <map>
 #include <string>
 #include <chrono>
@@ -41,6 +42,9 @@ struct Ctx
     uint   ssao_last = ~0u, taa_last = ~0u;
     double last_ms = 0.0;
     std::string err;
+    // 0 = fp32 planes (the gate); 1 = "faithful": every render target is rounded to the reference's texture format after the pass that
+    // writes it (oracle_quant.h) - a sensitivity figure, never the parity target
+    int faithful = 0;
 };
 
 std::string slot(const char* base, uint idx) { return std::string(base) + char('0' + (idx & 1u)); }
@@ -59,7 +63,59 @@ void ensure_persistent(Ctx& c)
     mk4("taa_accum0"), mk4("taa_accum1");
 }
 
+enum Fmt { F_UNORM8, F_UNORM16, F_HALF, F_R11G11B10 };
+void quant(TexF& t, Fmt f)
+{
+    for (float& v : t.d) v = f == F_UNORM8 ? q_unorm(v, 8) : f == F_UNORM16 ? q_unorm(v, 16) : q_half(v);
+}
+void quant(TexF2& t, Fmt f)
+{
+    for (auto& v : t.d) v.x = f == F_UNORM8 ? q_unorm(v.x, 8) : q_half(v.x), v.y = f == F_UNORM8 ? q_unorm(v.y, 8) : q_half(v.y);
+}
+void quant(TexF4& t, Fmt f)
+{
+    for (auto& v : t.d)
+    {
+        if (f == F_R11G11B10) v.x = q_float11(v.x), v.y = q_float11(v.y), v.z = q_float10(v.z); // no alpha channel: .w is never read
+        else v.x = q_half(v.x), v.y = q_half(v.y), v.z = q_half(v.z), v.w = q_half(v.w);
+    }
+}
+// the render targets pass `p` has just written, rounded to the formats the reference allocates them in
+void quantize_outputs(Ctx& c, const std::string& p)
+{
+    const uint cur = c.frame_index & 1u;
+    auto pyr = [&](const char* name, Fmt f, int from) {
+        auto it = c.pyr.find(name);
+        if (it != c.pyr.end())
+            for (int i = from; i < it->second.levels(); ++i) quant(it->second.mip[i], f);
+    };
+    if (p == "blue_noise") quant(c.f2["bn_xy"], F_UNORM8), quant(c.f2["bn_zw"], F_UNORM8);
+    else if (p == "closest_motion") quant(c.f2["closest_motion"], F_HALF);
+    else if (p == "ssao_prefilter") { if (c.ssao_flags & 1u) pyr("ssao_pre", F_UNORM16, 1); }
+    else if (p == "ssao_ao") quant(c.f1["ssao_occ"], F_UNORM8);
+    else if (p == "ssao_upsample") quant(c.f1["ssao_occ_up"], F_UNORM8);
+    else if (p == "ssao_temporal") quant(c.f1["ssao_acc"], F_UNORM8), quant(c.f1[slot("ssao_histlen", cur)], F_HALF);
+    else if (p == "ssao_convolute") { pyr("ssao_conv_occ", F_UNORM8, 0); if (c.ssao_flags & 1u) pyr("ssao_conv_depth", F_UNORM16, 1); }
+    else if (p == "ssao_resample") quant(c.f1["ssao_resampled"], F_UNORM8);
+    else if (p == "ssao_spatial") quant(c.f1["ssao_out"], F_UNORM8), quant(c.f1[slot("ssao_hist", cur)], F_UNORM8);
+    else if (p == "ssr_mask") quant(c.f1["ssr_roughness"], F_UNORM8);
+    else if (p == "ssr_intersect") quant(c.f4["ssr_radiance"], F_HALF), quant(c.f4["ssr_raydir"], F_HALF);
+    else if (p == "ssr_spatial") quant(c.f4["ssr_resolved_rad"], F_HALF), quant(c.f1["ssr_resolved_var"], F_HALF), quant(c.f1["ssr_resolved_depth"], F_HALF);
+    else if (p == "ssr_temporal") quant(c.f4[slot("ssr_radhist", cur)], F_HALF), quant(c.f1[slot("ssr_varhist", cur)], F_HALF);
+    else if (p == "ssr_bilateral") quant(c.f4["ssr_out"], F_HALF);
+    else if (p == "compose") quant(c.f4["composed"], F_HALF);
+    else if (p == "taa") quant(c.f4[slot("taa_accum", cur)], F_HALF);
+    // "bloom" rounds each level as soon as it is written (the next level reads the stored texels): see run_pass_impl
+}
+
+int run_pass_impl(Ctx& c, const std::string& p);
 int run_pass(Ctx& c, const std::string& p)
+{
+    const int r = run_pass_impl(c, p);
+    if (r == 0 && c.faithful) quantize_outputs(c, p);
+    return r;
+}
+int run_pass_impl(Ctx& c, const std::string& p)
 {
     const int  T   = c.threads;
     const uint cur = c.frame_index & 1u, prv = (c.frame_index + 1u) & 1u;
@@ -158,11 +214,12 @@ int run_pass(Ctx& c, const std::string& p)
         const int    mips = bloom_mip_count(std::max(in.w / 2, 1), std::max(in.h / 2, 1), c.bloom.Radius);
         auto dn = [&](int i) -> TexF4& { return c.f4["bloom_down" + std::to_string(i)]; };
         auto up = [&](int i) -> TexF4& { return c.f4["bloom_up" + std::to_string(i)]; };
-        bloom_prefilter(c.bloom, in, dn(0), T);
-        for (int i = 1; i < mips; ++i) bloom_downsample(dn(i - 1), dn(i), T);
+        auto store = [&](TexF4& t) { if (c.faithful) quant(t, F_R11G11B10); }; // every Bloom target is R11G11B10_FLOAT (Bloom.cpp:111, :125, :137)
+        bloom_prefilter(c.bloom, in, dn(0), T), store(dn(0));
+        for (int i = 1; i < mips; ++i) bloom_downsample(dn(i - 1), dn(i), T), store(dn(i));
         const int top = mips - 1;
-        for (int i = top; i > 0; --i) bloom_upsample(dn(i - 1), i != top ? up(i) : dn(i), up(i - 1), T);
-        bloom_composite(c.bloom, in, up(0), c.f4["bloom_out"], T);
+        for (int i = top; i > 0; --i) bloom_upsample(dn(i - 1), i != top ? up(i) : dn(i), up(i - 1), T), store(up(i - 1));
+        bloom_composite(c.bloom, in, up(0), c.f4["bloom_out"], T), store(c.f4["bloom_out"]);
     }
     else if (p == "tonemap") tonemap_pass(c.tm, c.ave_log_lum, c.to_srgb != 0, c.f4["tonemap_in"], c.f4["ldr"], T);
     else
@@ -309,6 +366,8 @@ ORC_API void orc_set_cameras(void* h, const dfx_camera_attribs* curr, const dfx_
     c.curr = to_camera(*curr);
     c.prev = to_camera(*prev);
 }
+ORC_API void orc_set_storage(void* h, int faithful) { static_cast<Ctx*>(h)->faithful = faithful; }
+ORC_API float orc_quantize(int fmt, float v) { return fmt == 0 ? q_unorm(v, 8) : fmt == 1 ? q_unorm(v, 16) : fmt == 2 ? q_half(v) : fmt == 3 ? q_float11(v) : q_float10(v); }
 ORC_API void orc_set_frame_index(void* h, uint32_t idx) { static_cast<Ctx*>(h)->frame_index = idx; }
 ORC_API void orc_set_ssao_attribs(void* h, const dfx_ssao_attribs* a) { static_cast<Ctx*>(h)->ssao = *a; }
 ORC_API void orc_set_ssao_flags(void* h, uint32_t flags) { static_cast<Ctx*>(h)->ssao_flags = flags; }

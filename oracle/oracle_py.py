@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
         L.orc_depth_to_camera_z.restype = C.c_float
         L.orc_camera_z_to_depth.restype = C.c_float
         L.orc_pcg_hash.restype = C.c_uint32
+        L.orc_quantize.restype = C.c_float
+        L.orc_quantize.argtypes = [C.c_int, C.c_float]
         for f in ("orc_destroy", "orc_set_threads", "orc_set_cameras", "orc_set_frame_index", "orc_set_ssao_attribs", "orc_set_ssr_attribs",
                   "orc_set_bloom_attribs", "orc_set_taa_attribs", "orc_set_tonemap_attribs", "orc_set_compose_scales", "orc_tone_map", "orc_taa_jitter"):
             getattr(L, f).restype = None
@@ -95,6 +97,11 @@ class Oracle:
         """PostFXContext::FEATURE_FLAG_REVERSED_DEPTH (process-wide switch, like the reference's shader macro)."""
         self.L.orc_set_reversed_depth(int(bool(on)))
 
+    def set_storage(self, faithful: bool):
+        """False (default): fp32 planes, the parity gate. True: every render target is rounded to the reference's texture format
+        (R8_UNORM AO, R16F / RGBA16F SSR and TAA, R11G11B10F Bloom, ...) right after the pass that writes it - SURVEY.md Appendix B.5."""
+        self.L.orc_set_storage(self.h_, int(bool(faithful)))
+
     def set_threads(self, t: int):
         self.L.orc_set_threads(self.h_, t)
 
@@ -137,6 +144,14 @@ class Oracle:
     def frame(self, stages: int = STAGE_ALL) -> float:
         self._chk(self.L.orc_frame(self.h_, C.c_uint32(stages)))
         return self.L.orc_last_ms(self.h_)
+
+
+QUANT_UNORM8, QUANT_UNORM16, QUANT_HALF, QUANT_FLOAT11, QUANT_FLOAT10 = range(5)
+
+
+def quantize(fmt: int, v: float) -> float:
+    """One value through a render-target format of the reference (oracle_quant.h)."""
+    return float(lib().orc_quantize(fmt, C.c_float(v)))
 
 
 def tone_map(attribs, ave_log_lum: float, rgb: np.ndarray) -> np.ndarray:
