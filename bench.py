@@ -104,6 +104,26 @@ def ncu_traffic(pass_name: str, width: int, height: int):
     return int(k["dram_bytes"]), "profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 
 
+def pin_to_gpu_numa_node(gpu_index: int) -> dict:
+    """One process per GPU: run this rank's host threads on the CPU cores NVML reports as local to its GPU (same socket / NUMA node as
+    the GPU's PCIe root), so that launches, pinned staging buffers and their first-touch pages do not cross the socket interconnect.
+    Without it eight ranks share whatever cores the scheduler picks and the replicas lose ~12 % to host-side contention (round 1)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * i + b for i, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus), "source": "nvmlDeviceGetCpuAffinity"}
+    except Exception as e:  # no NVML / restricted container: keep the inherited affinity
+        return {"cpus": len(os.sched_getaffinity(0)), "source": f"inherited ({type(e).__name__})"}
+    return {"cpus": len(os.sched_getaffinity(0)), "source": "inherited"}
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -395,6 +415,7 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device: the chain has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = pin_to_gpu_numa_node(local_rank)   # before any pinned host buffer is allocated: first touch places it on this node
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one (JSON) line
@@ -585,7 +606,7 @@ def main() -> None:
                                    "measured serially on one stream" if chain.cfg.overlap else "1 per GPU"),
                        "issue": {**issue, "what": "frames replayed from CUDA graphs (steady state) vs issued eagerly, since the chain was created; "
                                                   "1 native call (dfx_chain_execute) per frame either way"},
-                       "tune": os.environ.get("DFX_TUNE", ""),
+                       "tune": os.environ.get("DFX_TUNE", ""), "host_affinity": affinity,
                        "cache": f"{args.frames} distinct resident G-buffers of {h2d_bytes_fp32 / 1e6:.0f} MB cycled: inputs larger than the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),

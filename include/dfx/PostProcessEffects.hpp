@@ -49,6 +49,7 @@ public:
     {
         (void)pDevice, (void)CI;
         detail::Check(dfx_ssao_create(&m_Fx), "dfx_ssao_create");
+        if (m_Fx) dfx_ssao_set_alpha_interpolation(m_Fx, -1.0f); // reference behaviour: fade in over the first second (m_FrameTimer); SetAlphaInterpolation() pins it
     }
     ~ScreenSpaceAmbientOcclusion() { dfx_ssao_destroy(m_Fx); }
     ScreenSpaceAmbientOcclusion(const ScreenSpaceAmbientOcclusion&)            = delete;
@@ -85,7 +86,7 @@ public:
         return dfx_ssao_get_plane(m_Fx, DFX_SSAO_PLANE_OUTPUT, &p) == DFX_OK ? m_Out.Update(p) : nullptr;
     }
     // The reference fades the effect in over the first second of wall-clock time (AlphaInterpolation,
-    // ScreenSpaceAmbientOcclusion.cpp:793-795). This build pins it to 1 by default; pass a negative value to restore the fade.
+    // ScreenSpaceAmbientOcclusion.cpp:793-795), and so does this class. Tests pin it (>= 0); a negative value restores the fade.
     void SetAlphaInterpolation(float Alpha) { dfx_ssao_set_alpha_interpolation(m_Fx, Alpha); }
     dfx_ssao* GetHandle() const { return m_Fx; }
 
@@ -127,6 +128,7 @@ public:
     {
         (void)pDevice, (void)CI;
         detail::Check(dfx_ssr_create(&m_Fx), "dfx_ssr_create");
+        if (m_Fx) dfx_ssr_set_alpha_interpolation(m_Fx, -1.0f); // reference behaviour: fade in over the first second (m_FrameTimer); SetAlphaInterpolation() pins it
     }
     ~ScreenSpaceReflection() { dfx_ssr_destroy(m_Fx); }
     ScreenSpaceReflection(const ScreenSpaceReflection&)            = delete;
@@ -204,6 +206,7 @@ public:
     {
         (void)pDevice, (void)CI;
         detail::Check(dfx_bloom_create(&m_Fx), "dfx_bloom_create");
+        if (m_Fx) dfx_bloom_set_alpha_interpolation(m_Fx, -1.0f); // reference behaviour: fade in over the first second (m_FrameTimer); SetAlphaInterpolation() pins it
     }
     ~Bloom() { dfx_bloom_destroy(m_Fx); }
     Bloom(const Bloom&)            = delete;
@@ -275,6 +278,7 @@ public:
     {
         (void)pDevice, (void)CI;
         detail::Check(dfx_dof_create(&m_Fx), "dfx_dof_create");
+        if (m_Fx) dfx_dof_set_alpha_interpolation(m_Fx, -1.0f); // reference behaviour: fade in over the first second (m_FrameTimer); SetAlphaInterpolation() pins it
     }
     ~DepthOfField() { dfx_dof_destroy(m_Fx); }
     DepthOfField(const DepthOfField&)            = delete;

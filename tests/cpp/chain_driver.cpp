@@ -60,6 +60,8 @@ int main(int argc, char** argv)
     ScreenSpaceAmbientOcclusion SSAO{&Device, {}};
     TemporalAntiAliasing        TAA{&Device, {}};
     Bloom                       BloomFX{&Device, {}};
+    // the classes fade their effect in with wall-clock time like the reference (AlphaInterpolation); a test wants a fixed value
+    SSR.SetAlphaInterpolation(1.0f), SSAO.SetAlphaInterpolation(1.0f), BloomFX.SetAlphaInterpolation(1.0f);
 
     HLSL::ScreenSpaceAmbientOcclusionAttribs SSAOAttribs;
     HLSL::ScreenSpaceReflectionAttribs       SSRAttribs;
