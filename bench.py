@@ -9,12 +9,12 @@ frames: frames of a batch are independent sequences (r
 scaling is weak and `value` = pixels all ranks processed / max-over-ranks device time.
 
 Lines of the JSON record (one line on stdout, rank 0):
-  value         device-resident throughput: the G-buffers of the timed steps are already in HBM (4 distinct frames, 0.5 GB
-                each, cycled -> every step's inputs are cold in the 126 MB L2); timed with CUDA events, max over ranks.
+  value         device-resident throughput: the G-buffers of the timed steps are already in HBM in the renderer's formats (4 distinct
+                frames, 0.22 GB each, cycled -> every step's inputs are cold in the 126 MB L2); timed with CUDA events, max over ranks.
                 Async compute on three streams (ChainConfig.overlap; --no-overlap runs everything on one stream).
   e2e           the same K steps through the public streaming API (PostProcessChain.stream_frames) with HOST buffers: per
                 step the frame's G-buffer is copied from pinned host memory in the reference's render-target formats
-                (RGBA16F / RG16F / RG8 / D32F, widened on the device), the chain runs, and the frame is read back as RGBA8
+                (RGBA16F / RG16F / RG8 / D32F, which the passes read directly), the chain runs, and the frame is read back as RGBA8
                 into pinned host memory; copy-in, compute and copy-out of neighbouring frames overlap on three streams.
                 `e2e.fp32_transfers` is the same with every plane crossing PCIe as fp32.
   roofline      dominant pass of the chain (largest share of the step): algorithmic bytes / CUDA-event time inside this run
@@ -53,14 +53,15 @@ UNIT = "Mpix/s"
 
 # Algorithmic (compulsory) bytes per full-resolution pixel of each pass in this build's fp32 layout: every distinct plane the
 # pass reads or writes counted once at its full size, pyramids as geometric sums (derivation in DESIGN.md §4).
+# G-buffer inputs in the renderer's formats (HnBeginFrameTask.cpp:63-69): colour / normal RGBA16F 8 B, motion RG16F 4 B, material RG8 2 B, depth 4 B.
 PASS_BYTES_PER_PX = {
     "blue_noise": 0.0,
-    "postfx_prepare": 32.0,
-    "ssr_hiz": 5.33, "ssr_mask_roughness": 25.0, "ssr_intersect": 74.33, "ssr_spatial": 81.0, "ssr_temporal": 81.0, "ssr_bilateral": 61.0,
-    "ssao_prefilter_depth": 5.33, "ssao_ambient_occlusion": 25.33, "ssao_temporal": 36.0, "ssao_convolute": 10.67, "ssao_resample": 16.0,
-    "ssao_spatial": 32.0,
-    "compose": 52.0, "taa": 64.0,
-    "compose_taa": 84.0,                 # fused: colour 16 + ssr 16 + ao 4 + history 16 + motion 8 + depths 8 in, accumulation 16 out
+    "postfx_prepare": 28.0,              # depth 4 + previous depth 4 + motion 4 in; reprojected depth 4 + closest motion 8 + previous depth 4 out
+    "ssr_hiz": 5.33, "ssr_mask_roughness": 11.0, "ssr_intersect": 58.33, "ssr_spatial": 73.0, "ssr_temporal": 77.0, "ssr_bilateral": 53.0,
+    "ssao_prefilter_depth": 5.33, "ssao_ambient_occlusion": 17.33, "ssao_temporal": 36.0, "ssao_convolute": 10.67, "ssao_resample": 16.0,
+    "ssao_spatial": 24.0,
+    "compose": 44.0, "taa": 64.0,
+    "compose_taa": 76.0,                 # fused: colour 8 + ssr 16 + ao 4 + history 16 + motion 8 + depths 8 in, accumulation 16 out
     "bloom_composite_tonemap": 36.0,     # fused: colour 16 + up[0] 4 in, LDR 16 out
     "bloom_prefilter": 20.0, "bloom_downsample": 6.67, "bloom_upsample": 12.0, "bloom_composite": 36.0, "bloom_tail": 0.0,   # pyramid entries: see bloom_bytes()
     "tonemap": 32.0,
@@ -415,6 +416,7 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device: the chain has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
     affinity = pin_to_gpu_numa_node(local_rank)   # before any pinned host buffer is allocated: first touch places it on this node
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -432,7 +434,8 @@ def main() -> None:
     packed = [pack_frame(fr, pin=True) for fr in seq]
     seq = [widen_frame(p) for p in packed]
     host = [{n: torch.from_numpy(np.ascontiguousarray(fr[n])).pin_memory() for n in INPUT_SPECS} for fr in seq]
-    resident = [{n: t.to(dev) for n, t in hf.items()} for hf in host]
+    # device-resident arm: the G-buffer lies in HBM in the renderer's formats (what `packed` holds) and the passes read it as such
+    resident = [{n: (packed[i][PACKED_SPECS[n][0]].to(dev) if n in PACKED_SPECS else host[i][n].to(dev)) for n in INPUT_SPECS} for i in range(len(host))]
     cams = [(fr["curr_camera"], fr["prev_camera"]) for fr in seq]
     # consecutive frames: the previous depth is the depth of the frame before and stays on the device (stream_frames docstring)
     packed = [{k: v for k, v in p.items() if k != "prev_depth"} for p in packed]
@@ -536,7 +539,7 @@ def main() -> None:
         capi.check(lib.dfx_profile_collect())
         name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
         bloom_mips = lib.dfx_bloom_mip_count(W // 2, H // 2, C.c_float(chain.cfg.bloom.Radius))
-        bloom_first = next((i for i in range(1, bloom_mips) if max((W // 2) >> i, 1) * max((H // 2) >> i, 1) <= 16384), bloom_mips)
+        bloom_first = next((i for i in range(1, bloom_mips) if max((W // 2) >> i, 1) * max((H // 2) >> i, 1) <= 2048), bloom_mips)
         pyramid_bytes = bloom_bytes(W, H, bloom_mips, bloom_first if lib.dfx_tune_get(b"bloom_tail", 1) else bloom_mips)
         step_sum = 0.0
         for i in range(lib.dfx_profile_count()):
@@ -582,6 +585,7 @@ def main() -> None:
         roof["chain"]["frac"] = round(roof["chain"]["achieved"] / peak, 4)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
+    os.sched_setaffinity(0, all_cpus)   # the CPU legs (oracle baseline, PSNR check) may use every host core again
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ref_width, args.ref_height, 3, os.cpu_count() or 1)
@@ -612,7 +616,7 @@ def main() -> None:
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes),
                     "formats": "host G-buffer in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8 material, fp32 depth = "
-                               "26 B/px; the previous depth is the depth of the frame before and stays on the device), widened on the device; result read back as RGBA8 (4 B/px); PostProcessChain.stream_frames("
+                               "26 B/px; the previous depth is the depth of the frame before and stays on the device), read by the passes in those formats (no widening pass); result read back as RGBA8 (4 B/px); PostProcessChain.stream_frames("
                                "packed=True): copy-in / compute / copy-out pipelined on 3 streams",
                     "fp32_transfers": {"value": round(e2e32_value, 2), "ms_per_step": round(e2e32_ms, 4), "h2d_bytes_per_step": int(h2d_bytes_fp32),
                                        "d2h_bytes_per_step": int(d2h_bytes_fp32)}},

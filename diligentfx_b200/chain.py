@@ -203,8 +203,9 @@ class PostProcessChain:
 
         `packed=True`: the frames carry the G-buffer in the reference's render-target formats (`pack_frame`: colour and
         normal RGBA16F, motion RG16F, material RG8; depths stay fp32) and `ldr_host` holds (H, W, 4) uint8 tensors: 30 B/px
-        cross PCIe instead of 64, 4 B/px come back instead of 16. The device widens them (dfx_pass_unpack_plane) into the
-        same fp32 planes, so the chain computes exactly what it computes on `widen_frame(packed_frame)`.
+        cross PCIe instead of 64, 4 B/px come back instead of 16. The passes read those formats directly (every half / UNORM8
+        value is an fp32 value: the chain computes exactly what it computes on `widen_frame(packed_frame)`), so the narrow planes
+        are also what the kernels pull from HBM.
 
         A frame without a "prev_depth" entry takes the depth of the frame streamed before it (its own depth if it is the
         first one), which stays on the device: in the reference the previous depth is last frame's depth target, not
@@ -255,12 +256,10 @@ class PostProcessChain:
                 if last is not None:
                     P["depth_taken"][last].record(main)
             P["last_slot"] = s
-            if packed:                                               # widen the transfer formats into the fp32 planes the passes read
-                stream = C.c_void_p(main.cuda_stream)
-                for name in PACKED_SPECS:
-                    src, dst = plane_of(P["staging"][s][name]), plane_of(P["inputs"][s][name])
-                    check(L.dfx_pass_unpack_plane(stream, C.byref(src), C.byref(dst), full), "dfx_pass_unpack_plane")
-            self.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], P["inputs"][s], ldr_out=P["ldr"][s], defer_post=True)
+            ins = P["inputs"][s]
+            if packed:                                               # the passes read the render-target formats directly (Tex4 / Tex2 loaders): no widening pass
+                ins = {n: (P["staging"][s][n] if n in PACKED_SPECS else t) for n, t in P["inputs"][s].items()}
+            self.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], ins, ldr_out=P["ldr"][s], defer_post=True)
             # the frame is complete when its Bloom + ToneMap (side stream under cfg.overlap) is: the event goes on that stream
             post = self._post_stream if self._side_post else main
             if post is not main:

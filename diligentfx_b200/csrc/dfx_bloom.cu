@@ -7,11 +7,12 @@
 //   * streaming (exact 2:1 levels — every large level of the pyramid): a WARP walks down a column band; each lane loads its
 //     own texels with 128-bit coalesced loads exactly once and receives its horizontal neighbours' through warp shuffles, the
 //     vertical filter runs over a register sliding window. No shared memory, no barriers: the kernels are bound by HBM;
-//   * tail (levels of <= 16K texels, a dozen dependent launches in the reference): ONE thread-block cluster runs all of them,
+//   * tail (levels of <= 2K texels, a dozen dependent launches in the reference): ONE thread-block cluster runs all of them,
 //     down to the top of the pyramid and back up, with a cluster barrier between levels (the planes stay in L2).
 #include "dfx_common.cuh"
 #include "dfx_tonemap.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
 
 namespace dfx
 {
@@ -292,8 +293,10 @@ DFX_HD float3 shfl_dn3(float3 v) { return make_float3(__shfl_down_sync(0xfffffff
 DFX_HD float3 shfl3(float3 v, int src) { return make_float3(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src)); }
 
 constexpr int kDnCols = 30; // output columns per warp
-constexpr int kDnRows = 16; // output rows per warp (two source rows of warm-up above and below: 12.5 % re-read, served by L2)
 constexpr int kStreamWarps = 4;
+// Rows per warp are chosen per launch (stream_rows_per_warp): as few as keep the whole level in ONE wave of resident warps, so that a
+// large level streams at full bandwidth without a tail wave (measured: 1.05 waves cost 2x) and a small level is spread over as many
+// warps as the GPU has (a warp walks its rows sequentially: one memory latency per row pair).
 
 struct RowPair // texels (sx, sx + 1) of the source rows 2k and 2k + 1
 {
@@ -318,11 +321,11 @@ DFX_HD PairSums pair_sums(const RowPair& p)
 }
 
 template <bool PREFILTER>
-__global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1)
+__global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1, int rows_per_warp)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ox0 = (blockIdx.x * kStreamWarps + warp) * kDnCols;
-    const int oyb = y0 + blockIdx.y * kDnRows, oye = min(oyb + kDnRows, y1);
+    const int oyb = y0 + blockIdx.y * rows_per_warp, oye = min(oyb + rows_per_warp, y1);
     if (ox0 >= out.w || oyb >= oye) return; // warp-uniform
     const int  ox = ox0 + lane - 1, sx = 2 * ox;
     const bool col_ok = sx >= 0 && sx < in.w; // in.w == 2 * out.w: sx + 1 is inside whenever sx is
@@ -386,15 +389,14 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(
 // columns: lanes 0..19 load the 20 coarse texels of a coarse row that the 32 columns touch, every lane gathers its four by
 // shuffle, and the vertical filter slides over five coarse rows in registers, emitting two output rows per coarse row. The
 // fine-level texel (same-level down-sample for B3, the scene colour for B4) is read once, fully coalesced, and so is the store.
-constexpr int kUpCoarseRows = 8; // coarse rows per warp = 16 output rows
 
 template <bool COMPOSITE, bool TONEMAP>
 __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out,
-                                                                              int y0, int y1, ToneMapIn tm)
+                                                                              int y0, int y1, int coarse_rows_per_warp, ToneMapIn tm)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fx0 = (blockIdx.x * kStreamWarps + warp) * 32;
-    const int fyb = y0 + blockIdx.y * (2 * kUpCoarseRows), fye = min(fyb + 2 * kUpCoarseRows, y1); // y0 is even (checked by the caller)
+    const int fyb = y0 + blockIdx.y * (2 * coarse_rows_per_warp), fye = min(fyb + 2 * coarse_rows_per_warp, y1); // y0 is even (checked by the caller)
     if (fx0 >= out.w || fyb >= fye) return; // warp-uniform
     const int   x = fx0 + lane;
     const bool  xin = x < out.w;
@@ -439,12 +441,12 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
 }
 
 // =====================================================================================================================
-// Tail: every level with at most kTailTexels texels, down to the top of the pyramid and back up, in ONE launch of one
-// thread-block cluster (8 CTAs x 512 threads, co-scheduled on one GPC). Levels are separated by a cluster barrier
+// Tail: every level with at most kTailTexels texels (60x33 and below at 4K), down to the top of the pyramid and back up, in ONE launch
+// of one thread-block cluster (8 CTAs x 512 threads, co-scheduled on one GPC). Levels are separated by a cluster barrier
 // (release / acquire at cluster scope); planes written inside the kernel are re-read with ld.global.cg (L2, never a stale L1 line).
 // Per texel the arithmetic is the generic kernels' (same taps, same order): the tail is bit-identical to the per-level launches.
 // =====================================================================================================================
-constexpr int kTailTexels  = 16384;
+constexpr int kTailTexels  = 2048; // one cluster = 8 SMs: larger levels are faster as ordinary launches over the whole GPU (measured)
 constexpr int kTailThreads = 512;
 constexpr int kTailCluster = 8;
 
@@ -525,6 +527,23 @@ using namespace dfx;
 // (kept for A/B timing), 2 = generic gather kernels everywhere.
 static int bloom_impl() { return dfx_tune_get("bloom_impl", 1); }
 
+// Rows per warp of a streaming launch: the fewest that fit the level into one wave of resident warps (at least `min_rows`).
+template <class K>
+static int stream_rows_per_warp(K kernel, int warp_columns, int rows, int min_rows)
+{
+    static int slots = 0; // resident warps of this kernel on the current device (one static per kernel instantiation)
+    if (slots == 0)
+    {
+        int dev = 0, sms = 148, blocks = 4;
+        (void)cudaGetDevice(&dev);
+        (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, 32 * kStreamWarps, 0) != cudaSuccess || blocks < 1) blocks = 4;
+        slots = sms * blocks * kStreamWarps;
+    }
+    const int per_column = std::max(slots / std::max(warp_columns, 1), 1);
+    return std::max(div_up(rows, per_column), min_rows);
+}
+
 static dfx_status launch_down(void* stream, bool prefilter, const dfx_bloom_attribs& A, const View<const float4>& in, const View<float4>& out, dfx_rows rows)
 {
     cudaStream_t s     = as_stream(stream);
@@ -532,11 +551,13 @@ static dfx_status launch_down(void* stream, bool prefilter, const dfx_bloom_attr
     const int    impl  = bloom_impl();
     if (exact && impl == 1)
     {
-        const dim3 grid(div_up(out.w, kDnCols * kStreamWarps), div_up(rows.y1 - rows.y0, kDnRows));
+        const int  bx = div_up(out.w, kDnCols * kStreamWarps), n = rows.y1 - rows.y0;
+        const int  rpw = prefilter ? stream_rows_per_warp(bloom_down2x_stream_kernel<true>, bx * kStreamWarps, n, 2) : stream_rows_per_warp(bloom_down2x_stream_kernel<false>, bx * kStreamWarps, n, 2);
+        const dim3 grid(bx, div_up(n, rpw));
         if (prefilter)
-            bloom_down2x_stream_kernel<true><<<grid, 32 * kStreamWarps, 0, s>>>(A, in, out, rows.y0, rows.y1);
+            bloom_down2x_stream_kernel<true><<<grid, 32 * kStreamWarps, 0, s>>>(A, in, out, rows.y0, rows.y1, rpw);
         else
-            bloom_down2x_stream_kernel<false><<<grid, 32 * kStreamWarps, 0, s>>>(A, in, out, rows.y0, rows.y1);
+            bloom_down2x_stream_kernel<false><<<grid, 32 * kStreamWarps, 0, s>>>(A, in, out, rows.y0, rows.y1, rpw);
     }
     else
     {
@@ -590,10 +611,14 @@ static dfx_status launch_up(void* stream, int mode, const dfx_bloom_attribs& A, 
     if (mode == 2 && !exact) return set_error(DFX_ERR_UNSUPPORTED, "fused composite+tonemap needs an exact 2:1 level");
     if (exact && impl == 1)
     {
-        const dim3 grid(div_up(out.w, 32 * kStreamWarps), div_up(rows.y1 - rows.y0, 2 * kUpCoarseRows));
-        if (mode == 0) bloom_up2x_stream_kernel<false, false><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, tm);
-        if (mode == 1) bloom_up2x_stream_kernel<true, false><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, tm);
-        if (mode == 2) bloom_up2x_stream_kernel<true, true><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, tm);
+        const int bx = div_up(out.w, 32 * kStreamWarps), n = div_up(rows.y1 - rows.y0, 2); // coarse rows
+        const int cpw = mode == 0   ? stream_rows_per_warp(bloom_up2x_stream_kernel<false, false>, bx * kStreamWarps, n, 1)
+                        : mode == 1 ? stream_rows_per_warp(bloom_up2x_stream_kernel<true, false>, bx * kStreamWarps, n, 1)
+                                    : stream_rows_per_warp(bloom_up2x_stream_kernel<true, true>, bx * kStreamWarps, n, 1);
+        const dim3 grid(bx, div_up(n, cpw));
+        if (mode == 0) bloom_up2x_stream_kernel<false, false><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);
+        if (mode == 1) bloom_up2x_stream_kernel<true, false><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);
+        if (mode == 2) bloom_up2x_stream_kernel<true, true><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);
     }
     else if (exact && (impl == 0 || mode == 2))
     {

@@ -6,6 +6,7 @@
 // Planes are pitched fp32 arrays in HBM; all global loads of read-only planes go through the non-coherent path
 // (ld.global.nc) and are 64/128-bit wide where the element type allows.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -115,6 +116,67 @@ struct PeerView
         return __ldg(reinterpret_cast<const T*>(q));
     }
 };
+
+// G-buffer planes as the renderer stores them (Hydrogent/src/Tasks/HnBeginFrameTask.cpp:63-69: colour and normal RGBA16_FLOAT, motion
+// RG16_FLOAT, material RG8_UNORM) or widened to fp32: the kernels that read them take a Tex4 / Tex2, whose storage format is a
+// warp-uniform run-time field. Every half and every UNORM8 value is an fp32 value, so a pass computes bit for bit the same from
+// either representation; the narrow one halves (or better) the bytes the pass reads.
+struct Tex4
+{
+    const char* p;
+    int         pitch; // bytes
+    int         w, h, fmt; // DFX_FORMAT_RGBA32F | DFX_FORMAT_RGBA16F | DFX_FORMAT_RG8U (r, g, 0, 0)
+    __device__ __forceinline__ float4 ld(int x, int y) const
+    {
+        const char* row = p + (unsigned)(y * pitch); // planes are < 2^31 bytes (host-checked)
+        if (fmt == DFX_FORMAT_RGBA32F) return __ldg(reinterpret_cast<const float4*>(row) + x);
+        if (fmt == DFX_FORMAT_RGBA16F)
+        {
+            const uint2  v = __ldg(reinterpret_cast<const uint2*>(row) + x);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            return make_float4(a.x, a.y, b.x, b.y);
+        }
+        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(row) + x);
+        return make_float4(float(v.x) / 255.0f, float(v.y) / 255.0f, 0.0f, 0.0f); // UNORM -> float: c / 255, correctly rounded
+    }
+};
+struct Tex2
+{
+    const char* p;
+    int         pitch; // bytes
+    int         w, h, fmt; // DFX_FORMAT_RG32F | DFX_FORMAT_RG16F
+    __device__ __forceinline__ float2 ld(int x, int y) const
+    {
+        const char* row = p + (unsigned)(y * pitch);
+        if (fmt == DFX_FORMAT_RG32F) return __ldg(reinterpret_cast<const float2*>(row) + x);
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(row) + x);
+        return __half22float2(*reinterpret_cast<const __half2*>(&v));
+    }
+};
+inline bool make_tex4(const dfx_plane* pl, Tex4& t, bool allow_rg8 = false)
+{
+    if (!pl || !pl->ptr || pl->width <= 0 || pl->height <= 0) return false;
+    const size_t bpt = pl->format == DFX_FORMAT_RGBA32F ? 16 : pl->format == DFX_FORMAT_RGBA16F ? 8 : (pl->format == DFX_FORMAT_RG8U && allow_rg8) ? 2 : 0;
+    if (!bpt || pl->pitch_bytes % bpt != 0 || pl->pitch_bytes < size_t(pl->width) * bpt || reinterpret_cast<uintptr_t>(pl->ptr) % bpt != 0) return false;
+    if (pl->pitch_bytes * size_t(pl->height) >= (size_t(1) << 31)) return false;
+    t = Tex4{static_cast<const char*>(pl->ptr), int(pl->pitch_bytes), pl->width, pl->height, pl->format};
+    return true;
+}
+inline bool make_tex2(const dfx_plane* pl, Tex2& t)
+{
+    if (!pl || !pl->ptr || pl->width <= 0 || pl->height <= 0) return false;
+    const size_t bpt = pl->format == DFX_FORMAT_RG32F ? 8 : pl->format == DFX_FORMAT_RG16F ? 4 : 0;
+    if (!bpt || pl->pitch_bytes % bpt != 0 || pl->pitch_bytes < size_t(pl->width) * bpt || reinterpret_cast<uintptr_t>(pl->ptr) % bpt != 0) return false;
+    if (pl->pitch_bytes * size_t(pl->height) >= (size_t(1) << 31)) return false;
+    t = Tex2{static_cast<const char*>(pl->ptr), int(pl->pitch_bytes), pl->width, pl->height, pl->format};
+    return true;
+}
+#define DFX_TEX4(name, plane)                                                                                                      \
+    ::dfx::Tex4 name;                                                                                                              \
+    if (!::dfx::make_tex4(plane, name)) return ::dfx::set_error(DFX_ERR_INVALID_ARG, "bad plane '%s' (RGBA32F or RGBA16F expected; null, pitch or alignment)", #plane)
+#define DFX_TEX2(name, plane)                                                                                                      \
+    ::dfx::Tex2 name;                                                                                                              \
+    if (!::dfx::make_tex2(plane, name)) return ::dfx::set_error(DFX_ERR_INVALID_ARG, "bad plane '%s' (RG32F or RG16F expected; null, pitch or alignment)", #plane)
 
 // host: dfx_peer_map (C-ABI) -> the table the kernels index
 inline bool make_peer_map(const dfx_peer_map* m, int height, PeerMap& out)

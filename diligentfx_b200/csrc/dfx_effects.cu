@@ -127,14 +127,13 @@ extern "C" dfx_status dfx_postfx_prepare(dfx_postfx* c, const dfx_frame_desc* de
 namespace dfx
 {
 dfx_status launch_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const uint32_t* frame_index_dev, const dfx_plane* xy, const dfx_plane* zw);
+dfx_status launch_upload_cameras(void* stream, const dfx_camera_attribs* curr, const dfx_camera_attribs* prev, uint32_t frame_index, dfx_camera_attribs* dst_cams,
+                                 uint32_t* dst_frame);
 }
-// upload {curr, prev} like the map-discard of PostFXContext.cpp:310-318 (pageable source: staged before returning), plus the frame index
+// upload {curr, prev} like the map-discard of PostFXContext.cpp:310-318, plus the frame index (as kernel parameters: dfx_postfx.cu)
 static dfx_status postfx_upload(dfx_postfx* c, cudaStream_t s, const dfx_camera_attribs* curr, const dfx_camera_attribs* prev)
 {
-    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[0], curr, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
-    DFX_CUDA(cudaMemcpyAsync(&c->cams_dev[1], prev, sizeof(dfx_camera_attribs), cudaMemcpyHostToDevice, s));
-    DFX_CUDA(cudaMemcpyAsync(c->frame_dev, &c->desc.Index, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    return DFX_OK;
+    return launch_upload_cameras(s, curr, prev, c->desc.Index, c->cams_dev, c->frame_dev);
 }
 // the kernels of PostFXContext::Execute (everything they read per frame comes from device memory: the launches can be replayed from a graph)
 static dfx_status postfx_launch(dfx_postfx* c, cudaStream_t s, const dfx_plane* curr_depth, const dfx_plane* prev_depth, const dfx_plane* motion)
@@ -573,7 +572,7 @@ static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attri
     auto rows = [](const dfx_plane& p) { return dfx_rows{0, p.height}; };
     dfx_status st;
     // The reference draws one level per pass (Bloom.cpp:324-337 down, :355-375 up). Here the large levels are one launch each
-    // and every level from `first` on (<= 16K texels) is handled, down and up again, by one cluster launch (dfx_pass_bloom_tail).
+    // and every level from `first` on (<= 2K texels) is handled, down and up again, by one cluster launch (dfx_pass_bloom_tail).
     dfx_plane down[DFX_BLOOM_MAX_LEVELS], up[DFX_BLOOM_MAX_LEVELS];
     DFX_REQUIRE(mips <= DFX_BLOOM_MAX_LEVELS, "too many Bloom levels");
     for (int i = 0; i < mips; ++i) down[i] = fx->down[i].p, up[i] = fx->up[i].p;
@@ -845,7 +844,7 @@ extern "C" dfx_status dfx_dof_get_plane(const dfx_dof* fx, int32_t id, dfx_plane
 //   * CUDA graphs: in steady state (consecutive frame indices, no history reset, constant attributes) the ~25 launches of the
 //     front half and the ~8 of the back half are replayed from two instantiated graphs, cached per (input planes, ping-pong
 //     parity, attributes). Everything that changes from frame to frame - both cameras and the frame index - lives in device
-//     memory and is refreshed by one 1.2 KB copy from a pinned ring before the replay. A frame that resets a history, the first
+//     memory and is refreshed before the replay by a one-block kernel that receives them as launch parameters. A frame that resets a history, the first
 //     frames, or a profiling run take the eager path (same kernels, same streams).
 // =====================================================================================================================
 namespace dfx
@@ -860,13 +859,6 @@ struct GraphPair
     cudaGraphExec_t front = nullptr, post = nullptr;
     int             kernels = 0; // kernel nodes of the two graphs: what one replay adds to dfx_launch_count()
 };
-struct CameraSlot
-{
-    dfx_camera_attribs cams[2];
-    uint32_t           frame, pad[3];
-};
-constexpr int kCameraRing = 8;
-
 void append_bytes(std::string& k, const void* p, size_t n) { k.append(static_cast<const char*>(p), n); }
 void append_plane(std::string& k, const dfx_plane* p)
 {
@@ -890,8 +882,6 @@ struct dfx_chain
     cudaEvent_t      ev_fork = nullptr, ev_ao_done = nullptr, ev_front_done = nullptr, post_done[2] = {nullptr, nullptr};
     bool             post_pending[2] = {false, false};
     PlaneOwner       composed;
-    CameraSlot*      ring = nullptr;
-    int              ring_pos = 0;
     uint32_t         last_frame = ~0u;
     bool             graphs_ok  = true;
     std::map<std::string, GraphPair> graphs;
@@ -915,7 +905,6 @@ struct dfx_chain
             if (e) cudaEventDestroy(e);
         for (cudaStream_t s : {ao_stream, post_stream, cap_stream})
             if (s) cudaStreamDestroy(s);
-        if (ring) cudaFreeHost(ring);
     }
 };
 
@@ -957,7 +946,6 @@ extern "C" dfx_status dfx_chain_create(int32_t width, int32_t height, const dfx_
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_ao_done, &c->ev_front_done, &c->post_done[0], &c->post_done[1]})
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->ring, sizeof(CameraSlot) * kCameraRing);
     if (st == DFX_OK && e != cudaSuccess) st = check_cuda(e, "dfx_chain_create");
     if (st != DFX_OK)
     {
@@ -1167,14 +1155,8 @@ extern "C" dfx_status dfx_chain_execute(dfx_chain* c, void* stream, const dfx_ch
         DFX_CUDA(cudaStreamWaitEvent(main, c->post_done[par], 0));
         c->post_pending[par] = false;
     }
-    // ---- cameras + frame index: one copy from the pinned ring (a slot is reused after kCameraRing frames)
-    if (st & DFX_CHAIN_STAGE_POSTFX)
-    {
-        CameraSlot& slot = c->ring[c->ring_pos];
-        c->ring_pos      = (c->ring_pos + 1) % kCameraRing;
-        slot.cams[0] = *f->curr_camera, slot.cams[1] = *f->prev_camera, slot.frame = f->frame_index;
-        DFX_CUDA(cudaMemcpyAsync(c->pfx->cams_dev, &slot, 2 * sizeof(dfx_camera_attribs) + sizeof(uint32_t), cudaMemcpyHostToDevice, main));
-    }
+    // ---- cameras + frame index -> device memory (kernel parameters, no copy engine; outside the recorded graphs: they change every frame)
+    if ((st & DFX_CHAIN_STAGE_POSTFX) && (s = launch_upload_cameras(main, f->curr_camera, f->prev_camera, f->frame_index, c->pfx->cams_dev, c->pfx->frame_dev)) != DFX_OK) return s;
 
     dfx_plane color{};
     bool      replayed = false;

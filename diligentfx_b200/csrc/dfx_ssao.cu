@@ -68,7 +68,7 @@ struct __align__(16) AoLevel
 
 template <int ALGO>
 __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
-                                                      View<const float4> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half, float self_offset)
+                                                      Tex4 normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half, float self_offset)
 {
     __shared__ SsaoCam S;
     __shared__ AoLevel lvl[DFX_MAX_MIPS];
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_came
         const float z = fdiv(cam.m32 - d * cam.m33, d * cam.m23 - cam.m22);
         return make_float3(z * (su - 0.5f) * kx, z * (sv - 0.5f) * ky, z);
     };
-    const float3 nvs = mul_dir(xyz(half ? sample_point_clamp(normal, u, v) : __ldg(&normal.at(x, y))), S.view); // LoadNormalWS: point clamp
+    const float3 nvs = mul_dir(xyz(half ? sample_point_clamp(normal, u, v) : normal.ld(x, y)), S.view); // LoadNormalWS: point clamp
     float3       pvs = to_view(u, v, depth);
     pvs              = pvs + nvs * (self_offset * pvs.z); // 0.00001, or 0.005 with SSAO_OPTION_HALF_PRECISION_DEPTH (:145-150)
     const float3 view = -fnormalize(pvs);
@@ -386,7 +386,7 @@ DFX_HD float geometry_weight(float3 center, float3 tap, float3 n, float planeNor
 }
 
 __global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_attribs* __restrict__ cams, PyrView occ, PyrView dep,
-                                                            View<const float> history, View<const float4> normal, View<float> out, int y0, int y1, int rev)
+                                                            View<const float> history, Tex4 normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     stage_cam(S, cams);
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_att
     int          mip = min((int)(4.0f * (1.0f - saturate(acc))), occ.levels - 1);
     const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
     const float3 pvs  = screen_to_view(posx * cam.ivw, posy * cam.ivh, depth, cam);
-    const float3 nvs  = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    const float3 nvs  = mul_dir(xyz(normal.ld(x, y)), S.view);
     const float  planeNorm = 10.0f / (1.0f + depth_to_camz(depth, cam));
 
     float osum = 0.0f, wsum = 0.0f;
@@ -450,7 +450,7 @@ __constant__ float kPoisson8Weight[8] = {0.77283178f, 0.570022457f, 0.838854363f
 
 __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
                                                            View<const float> occlusion, View<const float> history, View<const float> depth,
-                                                           View<const float4> normal, View<float> out, int y0, int y1, int rev)
+                                                           Tex4 normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     stage_cam(S, cams);
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attr
         return make_float3(z * (su - 0.5f) * kx, z * (sv - 0.5f) * ky, z);
     };
     const float3 pvs  = to_view(posx * cam.ivw, posy * cam.ivh, d);
-    const float3 nvs  = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    const float3 nvs  = mul_dir(xyz(normal.ld(x, y)), S.view);
     float        rs, rc;
     __sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
     const float radius    = lerpf(0.0f, A.SpatialReconstructionRadius, 1.0f - saturate(acc));
@@ -517,7 +517,7 @@ constexpr int kSpTileW = 40, kSpTileH = 16;
 
 __global__ void __launch_bounds__(256) ssao_spatial_tile_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, const __grid_constant__ SpatialMaps maps,
                                                                 View<const float> occlusion, View<const float> history, View<const float> depth,
-                                                                View<const float4> normal, View<float> out, int y0, int y1, int rev)
+                                                                Tex4 normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam                  S;
     __shared__ __align__(128) float     tz[kSpTileH][kSpTileW];
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(256) ssao_spatial_tile_kernel(const dfx_camera
     const float  kx = 2.0f * frcp(cam.m00), ky = -2.0f * frcp(cam.m11);
     const float  zc = tz[y - Y0][x - X0];
     const float3 pvs = make_float3(zc * (posx * cam.ivw - 0.5f) * kx, zc * (posy * cam.ivh - 0.5f) * ky, zc);
-    const float3 nvs = mul_dir(xyz(__ldg(&normal.at(x, y))), S.view);
+    const float3 nvs = mul_dir(xyz(normal.ld(x, y)), S.view);
     const float  pn  = dot(pvs, nvs);
     float        rs, rc;
     __sincosf(2.0f * kPi * bayer4x4((uint32_t)x, (uint32_t)y, cam.frame_index), &rs, &rc);
@@ -642,7 +642,7 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     DFX_REQUIRE(make_pyr(prefiltered_depth, P, 1), "bad prefiltered-depth pyramid");
     const int   rev = reversed_depth(&prefiltered_depth->level[0]); // level 0 is the depth buffer
     const float self_offset = (prefiltered_depth->level[0].flags & DFX_PLANE_FLAG_HALF_PRECISION_DEPTH) ? 0.005f : 0.00001f;
-    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(n, normal);
     DFX_VIEW(const float2, bn, blue_noise_zw, DFX_FORMAT_RG32F);
     DFX_VIEW(float, out, occlusion, DFX_FORMAT_R32F);
     // A pyramid of half the normal plane's size means FEATURE_FLAG_HALF_RESOLUTION (the reference allocates W/2 x H/2, …cpp:109-110)
@@ -757,7 +757,7 @@ extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attr
     const int rev = reversed_depth(&depth_pyr->level[0]); // level 0 is the depth buffer
     DFX_REQUIRE(O.levels == D.levels, "pyramid level mismatch");
     DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);
-    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(n, normal);
     DFX_VIEW(float, out, out_occlusion, DFX_FORMAT_R32F);
     DFX_SAME_SIZE(O.lv[0], D.lv[0]);
     DFX_SAME_SIZE(O.lv[0], h);
@@ -781,7 +781,7 @@ extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attri
     DFX_VIEW(const float, h, history_length, DFX_FORMAT_R32F);
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
     const int rev = reversed_depth(depth);
-    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(n, normal);
     DFX_VIEW(float, out, out_occlusion, DFX_FORMAT_R32F);
     DFX_SAME_SIZE(o, h);
     DFX_SAME_SIZE(o, d);

@@ -21,13 +21,13 @@ __host__ __device__ inline int ssr_mip_row(int y, int m, int full_h, int mip_h) 
 // ---------------------------------------------------------------------------------------------------------------------
 // S2: reflection mask + roughness extraction — SSR_ComputeStencilMaskAndExtractRoughness.fx:13-40
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, View<const float4> material, View<const float> depth,
+__global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, Tex4 material, View<const float> depth,
                                                        View<float> roughness, View<uint8_t> mask, int y0, int y1, int rev)
 {
     const PixelXY pix = cta_pixel(y0);
     const int     x = pix.x, y = pix.y;
     if (x >= depth.w || y >= y1) return;
-    const float4 m = __ldg(&material.at(x, y));
+    const float4 m = material.ld(x, y);
     float r = A.RoughnessChannel == 0u ? m.x : A.RoughnessChannel == 1u ? m.y : A.RoughnessChannel == 2u ? m.z : A.RoughnessChannel == 3u ? m.w : 0.0f;
     if (!A.IsRoughnessPerceptual) r = sqrtf(r);
     const bool pass = is_reflection_sample(r, __ldg(&depth.at(x, y)), A.RoughnessThreshold, rev);
@@ -159,19 +159,19 @@ __device__ __forceinline__ float hiz_load(const HizLevel& L, const PeerTables& P
 }
 __device__ __forceinline__ float hiz_load(const HizLevel& L, const NoPeerTables&, int x, int y, int) { return hiz_load(L, x, y); }
 // Load of a full-res RGBA plane at the hit texel (0 out of bounds): from the owner of row y.
-template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const PeerTables& P, int x, int y)
+template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const Tex4& v, const PeerTables& P, int x, int y) // peer planes are RGBA32F (host-checked)
 {
     if (!((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* base = (NORMAL ? P.normal : P.color)[P.owner[y >> kPeerBlockShift]];
-    return __ldg(base + (unsigned)(y * v.pitch + x));
+    return __ldg(base + (unsigned)(y * (v.pitch >> 4) + x));
 }
-template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const View<const float4>& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
+template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const Tex4& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
 
 template <bool PREV_FRAME, bool PEER, bool REV>
 __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                            View<const float4> color, View<const float4> normal, View<const float> roughness,
+                                                            Tex4 color, Tex4 normal, View<const float> roughness,
                                                             View<const uint8_t> mask, View<const float2> noise, HizView hiz,
-                                                            View<const float2> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1, int half,
+                                                            Tex2 motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1, int half,
                                                             const __grid_constant__ typename std::conditional<PEER, PeerArgs, NoPeerTables>::type peer_args)
 {
     __shared__ IntersectCam S;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         px = 2 * x + (int)(idx & 1u), py = 2 * y + (int)(idx >> 1);
     }
     const float u = (float(px) + 0.5f) * cam.ivw, v = (float(py) + 0.5f) * cam.ivh;
-    const float3 nws = xyz(__ldg(&normal.at(px, py)));
+    const float3 nws = xyz(normal.ld(px, py));
     const float3 nvs = mul_dir(nws, S.view);
     const float  rough = __ldg(&roughness.at(px, py));
 
@@ -399,7 +399,7 @@ struct SpatialCam
 };
 
 __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                          View<const float> roughness, View<const uint8_t> mask, View<const float4> normal,
+                                                          View<const float> roughness, View<const uint8_t> mask, Tex4 normal,
                                                           View<const float> depth, View<const float4> raydir, View<const float4> radiance,
                                                           View<float4> out_rad, View<float> out_var, View<float> out_depth, int y0, int y1, int half)
 {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(c
     const float  posx = float(x) + 0.5f, posy = float(y) + 0.5f;
     const float3 camPos = make_float3(cam.px, cam.py, cam.pz);
     const float3 pws = inv_project_position(posx * cam.ivw, posy * cam.ivh, __ldg(&depth.at(x, y)), S.vp_inv);
-    const float3 nws = xyz(__ldg(&normal.at(x, y)));
+    const float3 nws = xyz(normal.ld(x, y));
     const float3 toCam = camPos - pws;
     const float  camDist2 = dot(toCam, toCam), invCamDist = frsqrt(camDist2);
     const float3 vws = toCam * invCamDist;
@@ -507,7 +507,7 @@ struct NoPeerMap
 };
 template <bool PEER>
 __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                           View<const uint8_t> mask, View<const float2> motion, View<const float> hit_depth,
+                                                           View<const uint8_t> mask, Tex2 motion, View<const float> hit_depth,
                                                            View<const float> curr_depth, View<const float4> curr_rad, View<const float> curr_var,
                                                            View<const float> prev_depth_, View<const float4> prev_rad_, View<const float> prev_var_,
                                                            View<float4> out_rad, View<float> out_var, int y0, int y1,
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel
 
     const float depth = __ldg(&curr_depth.at(x, y));
     const float hitD  = __ldg(&hit_depth.at(x, y));
-    float2      mv    = __ldg(&motion.at(x, y));
+    float2      mv    = motion.ld(x, y);
     mv.x *= 0.5f, mv.y *= -0.5f;
 
     const float ipx = posx - mv.x * cam.vw, ipy = posy - mv.y * cam.vh; // PrevIncidentPoint
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel
 // differences v(x|1) - v(x&~1), v(y|1) - v(y&~1) (coordinates clamped at odd image edges).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                            View<const uint8_t> mask, View<const float> depth, View<const float4> normal,
+                                                            View<const uint8_t> mask, View<const float> depth, Tex4 normal,
                                                             View<const float> roughness, View<const float4> radiance, View<const float> variance,
                                                             View<float4> out, int y0, int y1, int rev)
 {
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
     const int   W = (int)cam.vw, H = (int)cam.vh;
     const float rough = __ldg(&roughness.at(x, y));
     const float var   = __ldg(&variance.at(x, y));
-    const float3 nws  = xyz(__ldg(&normal.at(x, y)));
+    const float3 nws  = xyz(normal.ld(x, y));
     // The depth edge-stopping weight exp(-|dz| / (|grad . d| + 1e-6)) divides by a quantity that is ~0 on flat surfaces, so it
     // amplifies the last bits of the camera-space Z: this pass keeps the correctly-rounded division for Z.
     auto         camz_precise = [&](float dpt) { return (cam.m32 - dpt * cam.m33) / (dpt * cam.m23 - cam.m22); };
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_att
                 if (is_reflection_sample(sr, sd, A.RoughnessThreshold, rev))
                 {
                     const float4 srad = __ldg(&radiance.at(sx, sy));
-                    const float3 sn   = xyz(__ldg(&normal.at(sx, sy)));
+                    const float3 sn   = xyz(normal.ld(sx, sy));
                     const float  sz   = camz_precise(sd);
                     const float  fx = float(dx), fy = float(dy);
                     const float  ws = __expf(-0.5f * (fx * fx + fy * fy) * inv_sigma2);
@@ -716,6 +716,32 @@ static bool make_hiz(const dfx_pyramid* p, HizView& v)
 
 using namespace dfx;
 
+namespace dfx
+{
+void preload_postfx_kernels();
+// Everything a strip-sharded SSR frame launches, loaded up front: a kernel that is loaded lazily while a flag-wait kernel spins can
+// deadlock ranks that share a process (module loading may synchronise the device).
+void preload_ssr_strip_kernels()
+{
+    preload_postfx_kernels();
+    cudaFuncAttributes fa;
+    (void)cudaFuncGetAttributes(&fa, pyramid_level_kernel<HizOp>);
+    (void)cudaFuncGetAttributes(&fa, pyramid_tail_kernel<HizOp>);
+    (void)cudaFuncGetAttributes(&fa, pyramid_tile_kernel<HizOp, true>);
+    (void)cudaFuncGetAttributes(&fa, pyramid_tile_kernel<HizOp, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_mask_kernel);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, true, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, true, true>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, false, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, false, true>);
+    (void)cudaFuncGetAttributes(&fa, ssr_spatial_kernel);
+    (void)cudaFuncGetAttributes(&fa, ssr_temporal_kernel<true>);
+    (void)cudaFuncGetAttributes(&fa, ssr_temporal_kernel<false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_bilateral_kernel);
+    (void)cudaGetLastError();
+}
+} // namespace dfx
+
 extern "C" dfx_status dfx_pass_ssr_hiz(void* stream, const dfx_pyramid* pyr, dfx_rows rows)
 {
     DFX_PROFILE(stream, "ssr_hiz");
@@ -739,7 +765,8 @@ extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_at
 {
     DFX_PROFILE(stream, "ssr_mask_roughness");
     DFX_REQUIRE(attribs, "null argument");
-    DFX_VIEW(const float4, m, material, DFX_FORMAT_RGBA32F);
+    Tex4 m;
+    DFX_REQUIRE(make_tex4(material, m, true), "bad material plane (RGBA32F, RGBA16F or RG8U)");
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
     DFX_VIEW(float, r, roughness, DFX_FORMAT_R32F);
     DFX_VIEW(uint8_t, k, mask, DFX_FORMAT_R8U);
@@ -778,8 +805,8 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
                                      const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows)
 {
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
-    DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
-    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(c, color);
+    DFX_TEX4(n, normal);
     DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
     DFX_VIEW(const float2, bn, blue_noise_xy, DFX_FORMAT_RG32F);
@@ -807,6 +834,7 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
         DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) == 0, "previous-frame SSR is not supported on peer-sharded frames");
         DFX_REQUIRE(peers->count >= 1 && peers->count <= DFX_MAX_PEERS, "peer count out of range");
         DFX_REQUIRE(c.h <= (kPeerMaxBlocks << kPeerBlockShift), "frame too tall for the peer owner table");
+        DFX_REQUIRE(c.fmt == DFX_FORMAT_RGBA32F && n.fmt == DFX_FORMAT_RGBA32F, "peer-sharded planes must be RGBA32F");
         PeerArgs pa{};
         pa.count = peers->count;
         DFX_REQUIRE(peers->row_begin[0] == 0 && peers->row_begin[peers->count] == c.h, "peer strips must cover rows [0, height)");
@@ -829,7 +857,7 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
                 pa.hiz[m][i] = static_cast<const float*>(peers->hiz[m][i]);
             }
         }
-        View<const float2> mv{nullptr, 0, 0, 0};
+        Tex2 mv{nullptr, 0, 0, 0, DFX_FORMAT_RG32F};
         if (rev)
             ssr_intersect_kernel<false, true, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
         else
@@ -837,7 +865,7 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
     }
     else if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
     {
-        DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
+        DFX_TEX2(mv, motion);
         DFX_SAME_SIZE(c, mv);
         if (rev)
             ssr_intersect_kernel<true, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
@@ -846,7 +874,7 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
     }
     else
     {
-        View<const float2> mv{nullptr, 0, 0, 0};
+        Tex2 mv{nullptr, 0, 0, 0, DFX_FORMAT_RG32F};
         if (rev)
             ssr_intersect_kernel<false, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
         else
@@ -886,7 +914,7 @@ extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attrib
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
-    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(n, normal);
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
     DFX_VIEW(const float4, rd, raydir_pdf, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float4, ra, radiance, DFX_FORMAT_RGBA32F);
@@ -919,7 +947,7 @@ static dfx_status ssr_temporal_impl(const dfx_peer_map* peers, void* stream, con
     DFX_PROFILE(stream, peers ? "ssr_temporal_peer" : "ssr_temporal");
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
-    DFX_VIEW(const float2, mv, motion, DFX_FORMAT_RG32F);
+    DFX_TEX2(mv, motion);
     DFX_VIEW(const float, hd, hit_depth, DFX_FORMAT_R32F);
     DFX_VIEW(const float, cd, reprojected_depth, DFX_FORMAT_R32F);
     DFX_VIEW(const float4, cr, curr_radiance, DFX_FORMAT_RGBA32F);
@@ -982,7 +1010,7 @@ extern "C" dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attr
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
     DFX_VIEW(const uint8_t, k, mask, DFX_FORMAT_R8U);
     DFX_VIEW(const float, d, depth, DFX_FORMAT_R32F);
-    DFX_VIEW(const float4, n, normal, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(n, normal);
     DFX_VIEW(const float, r, roughness, DFX_FORMAT_R32F);
     DFX_VIEW(const float4, ra, radiance, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float, va, variance, DFX_FORMAT_R32F);

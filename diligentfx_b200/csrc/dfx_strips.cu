@@ -127,12 +127,13 @@ __global__ void barrier_kernel(const __grid_constant__ BarrierArgs a)
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 size_t texel_bytes(int fmt) { return fmt == DFX_FORMAT_R32F ? 4 : fmt == DFX_FORMAT_RG32F ? 8 : fmt == DFX_FORMAT_RGBA32F ? 16 : 1; }
 
-struct CameraSlot
-{
-    dfx_camera_attribs cams[2];
-};
-constexpr int kCameraRing = 8;
 } // namespace
+namespace dfx
+{
+dfx_status launch_upload_cameras(void* stream, const dfx_camera_attribs* curr, const dfx_camera_attribs* prev, uint32_t frame_index, dfx_camera_attribs* dst_cams,
+                                 uint32_t* dst_frame);
+void       preload_ssr_strip_kernels(); // dfx_ssr.cu
+}
 
 struct dfx_ssr_strips
 {
@@ -145,8 +146,6 @@ struct dfx_ssr_strips
     dfx_camera_attribs* cams_dev = nullptr;
     uint8_t*     tables_dev = nullptr;
     SyncBlock*   sync = nullptr;
-    CameraSlot*  ring = nullptr;
-    int          ring_pos = 0;
     unsigned     seq = 0;
     dfx_peer_set peer_set{};
 
@@ -156,7 +155,6 @@ struct dfx_ssr_strips
     }
     ~dfx_ssr_strips()
     {
-        if (ring) cudaFreeHost(ring);
         cudaFree(tables_dev);
     }
 };
@@ -229,7 +227,15 @@ extern "C" dfx_status dfx_ssr_strips_create(int32_t width, int32_t height, const
     cudaError_t e = cudaMemset(s->base, 0, L.total); // histories start from 0 (ScreenSpaceReflection.cpp:263-264, :279-280), flags from 0
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->tables_dev, 256 + 128 * 128 * 8);
     if (e == cudaSuccess) e = cudaMemcpy(s->tables_dev, blue_noise_tables, 256 + 128 * 128 * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->ring, sizeof(CameraSlot) * kCameraRing);
+    // CUDA loads kernels lazily, and loading one may synchronise the device: with a flag-wait kernel already spinning on a stream that
+    // would deadlock ranks sharing a process (and serialise the first frame otherwise). Everything a frame launches is loaded here.
+    preload_ssr_strip_kernels();
+    {
+        cudaFuncAttributes fa;
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, halo_push_kernel);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, flag_wait_kernel);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, barrier_kernel);
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess)
     {
@@ -338,10 +344,7 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
     const uint32_t cur = frame_index & 1u, prv = (frame_index + 1u) & 1u;
     dfx_status     rc;
 
-    CameraSlot& slot = s->ring[s->ring_pos];
-    s->ring_pos      = (s->ring_pos + 1) % kCameraRing;
-    slot.cams[0] = *curr_camera, slot.cams[1] = *prev_camera;
-    DFX_CUDA(cudaMemcpyAsync(s->cams_dev, &slot, sizeof(slot), cudaMemcpyHostToDevice, st));
+    if ((rc = launch_upload_cameras(st, curr_camera, prev_camera, frame_index, s->cams_dev, nullptr)) != DFX_OK) return rc;
 
     // E0: the inputs' halos. Depth: 64 rows from below (the Hi-Z rows of the strip's last block reach into the next block wherever a
     // level has an odd height: SSR_ComputeHierarchicalDepthBuffer.fx:52-70 reads row 2y+2), 4 rows from above and 4 more uses below

@@ -60,9 +60,9 @@ struct ComposeIn
     float              ssr_scale, ssao_scale;
 };
 template <bool COMPOSE>
-DFX_HD float3 load_scene_colour(const View<const float4>& color, const ComposeIn& ci, int gx, int gy)
+DFX_HD float3 load_scene_colour(const Tex4& color, const ComposeIn& ci, int gx, int gy)
 {
-    float3 c = xyz(__ldg(&color.at(gx, gy)));
+    float3 c = xyz(color.ld(gx, gy));
     if (COMPOSE)
     {
         if (ci.ssr.p && ci.ssr_scale > 0.0f)
@@ -76,7 +76,7 @@ DFX_HD float3 load_scene_colour(const View<const float4>& color, const ComposeIn
 }
 
 template <bool BICUBIC, bool YCOCG, bool GAUSS, bool COMPOSE>
-__global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, View<const float4> curr_color,
+__global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, Tex4 curr_color,
                                                   ComposeIn ci, View<const float4> prev_accum, View<const float2> motion, View<const float> curr_depth,
                                                   View<const float> prev_depth, View<float4> out, int y0, int y1)
 {
@@ -216,13 +216,13 @@ __global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_
 // =====================================================================================================================
 // compose (reduced form of HnPostProcess.psh:145-185): rgb += ssr.rgb*ssr.a*scale ; rgb *= lerp(1, ao, scale)
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) compose_kernel(View<const float4> color, View<const float4> ssr, View<const float> ao, float ssr_scale,
+__global__ void __launch_bounds__(256) compose_kernel(Tex4 color, View<const float4> ssr, View<const float> ao, float ssr_scale,
                                                       float ssao_scale, View<float4> out, int y0, int y1)
 {
     const PixelXY pix = cta_pixel(y0);
     const int     x = pix.x, y = pix.y;
     if (x >= out.w || y >= y1) return;
-    const float4 C = __ldg(&color.at(x, y));
+    const float4 C = color.ld(x, y);
     float3       c = xyz(C);
     if (ssr.p && ssr_scale > 0.0f)
     {
@@ -261,7 +261,7 @@ static dfx_status launch_taa(void* stream, const dfx_camera_attribs* cameras_dev
                              const dfx_plane* previous_depth, const dfx_plane* out_accum, dfx_rows rows)
 {
     DFX_REQUIRE(cameras_dev && attribs, "null argument");
-    DFX_VIEW(const float4, cc, curr_color, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(cc, curr_color);
     DFX_VIEW(const float4, pa, prev_accum, DFX_FORMAT_RGBA32F);
     DFX_VIEW(const float2, mv, closest_motion, DFX_FORMAT_RG32F);
     DFX_VIEW(const float, cd, reprojected_depth, DFX_FORMAT_R32F);
@@ -325,7 +325,7 @@ extern "C" dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, con
                                        float ssao_scale, const dfx_plane* out_, dfx_rows rows)
 {
     DFX_PROFILE(stream, "compose");
-    DFX_VIEW(const float4, c, color, DFX_FORMAT_RGBA32F);
+    DFX_TEX4(c, color);
     DFX_VIEW(float4, out, out_, DFX_FORMAT_RGBA32F);
     DFX_SAME_SIZE(c, out);
     View<const float4> s{nullptr, 0, 0, 0};

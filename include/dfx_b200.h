@@ -451,7 +451,7 @@ DFX_API dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_attrib
  * (the reference issues one draw per level, Bloom.cpp:324-337 and :355-375; on the small levels of the pyramid those dependent
  * launches cost more than the work). `down` / `up` are arrays of `mips` planes (level i = max(level0 >> i, 1)); reads
  * down[first-1], writes down[first..mips-1] and up[first-1..mips-2]. Results are bit-identical to the per-level passes.
- * dfx_bloom_tail_first_level: the level the effect object hands over to this pass (first one with <= 16384 texels; `mips` = none). */
+ * dfx_bloom_tail_first_level: the level the effect object hands over to this pass (first one with <= 2048 texels; `mips` = none). */
 #define DFX_BLOOM_MAX_LEVELS 16
 DFX_API dfx_status dfx_pass_bloom_tail(void* stream, const dfx_plane* down, const dfx_plane* up, int32_t first, int32_t mips);
 DFX_API int32_t    dfx_bloom_tail_first_level(const dfx_plane* down, int32_t mips);

@@ -278,7 +278,7 @@ def test_bloom_passes(ctx):
 
 
 def test_bloom_tail_and_streaming_kernels(built):
-    """The single-launch tail (one thread-block cluster for every level of <= 16K texels, down and up) and the warp-shuffle
+    """The single-launch tail (one thread-block cluster for every level of <= 2K texels, down and up) and the warp-shuffle
     streaming kernels of the exact-2:1 levels against the oracle's levels, and bit-identical (tail) / within rounding (streaming)
     to the generic per-level kernels. 1024x576: levels 512x288 ... 16x9 are exact 2:1, 8x4 / 4x2 / 2x1 are not."""
     from oracle import oracle_py as op
@@ -319,7 +319,7 @@ def test_bloom_tail_and_streaming_kernels(built):
 
     try:
         first, dn, up = run(1, 1)
-        assert first == 2, first  # 256x144 = 36864 > 16384 >= 128x72
+        assert first == 4, first  # 64x36 = 2304 > 2048 >= 32x18
         _, dn_g, up_g = run(2, 0)   # generic gather kernels, one launch per level
         _, dn_t, up_t = run(1, 0)   # streaming kernels, per-level launches for the small levels
     finally:
@@ -461,6 +461,23 @@ def test_packed_streaming_equals_widened_frames(ctx):
     for k, wnt in enumerate(want):
         assert np.array_equal(hosts2[k].numpy(), wnt), f"device-kept previous depth, frame {k}"
     a.close(), b.close(), c.close()
+
+
+def test_native_gbuffer_formats_equal_widened_planes(ctx):
+    """The passes read colour / normal as RGBA16F, motion as RG16F and material as RG8 directly (Tex4 / Tex2 loaders): every frame of the
+    chain must be bit-identical to the one computed from the same values widened to fp32 planes."""
+    import torch
+    from diligentfx_b200.chain import PACKED_SPECS, PostProcessChain, pack_frame, widen_frame
+    seq, h, w = ctx["seq"], ctx["h"], ctx["w"]
+    a, b = PostProcessChain(w, h), PostProcessChain(w, h)
+    for k, fr in enumerate(seq):
+        p = pack_frame(fr)
+        wide = widen_frame(p)
+        want = a.run_frame(wide).cpu().numpy()
+        ins = {n: (p[PACKED_SPECS[n][0]].cuda() if n in PACKED_SPECS else torch.from_numpy(np.ascontiguousarray(wide[n], np.float32)).cuda()) for n in a.inputs}
+        got = b.execute(fr["frame"], fr["curr_camera"], fr["prev_camera"], ins).cpu().numpy()
+        assert np.array_equal(got, want), f"frame {k}: {np.count_nonzero(got != want)} values differ, max abs {np.abs(got - want).max()}"
+    a.close(), b.close()
 
 
 # =====================================================================================================================
