@@ -102,6 +102,19 @@ ProfileScope::~ProfileScope()
     nvtxRangePop();
 }
 
+// fill of a plane in one of the renderer's narrow formats: `bpc` bytes per channel (2 = half, 1 = UNORM8), `ch` channels
+__global__ void fill_narrow_kernel(unsigned char* p, size_t pitch, int w, int h, int ch, int bpc, float4 v)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w * ch || y >= h) return;
+    const int   c = x % ch;
+    const float s = c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+    if (bpc == 2)
+        reinterpret_cast<__half*>(p + size_t(y) * pitch)[x] = __float2half_rn(s);
+    else
+        (p + size_t(y) * pitch)[x] = (unsigned char)__fmaf_rn(fminf(fmaxf(s, 0.0f), 1.0f), 255.0f, 0.5f);
+}
+
 EffectRange::EffectRange(const char* name) { nvtxRangePushA(name); }
 EffectRange::~EffectRange() { nvtxRangePop(); }
 
@@ -234,6 +247,14 @@ dfx_status dfx_plane_fill(void* stream, const dfx_plane* dst, const float value[
     if (dst->format == DFX_FORMAT_R8U)
     {
         DFX_CUDA(cudaMemset2DAsync(dst->ptr, dst->pitch_bytes, value[0] != 0.0f ? 1 : 0, dst->width, dst->height, as_stream(stream)));
+        return DFX_OK;
+    }
+    if (dst->format == DFX_FORMAT_RGBA16F || dst->format == DFX_FORMAT_RG16F || dst->format == DFX_FORMAT_RG8U || dst->format == DFX_FORMAT_RGBA8U)
+    {
+        const int nch = (dst->format == DFX_FORMAT_RGBA16F || dst->format == DFX_FORMAT_RGBA8U) ? 4 : 2, bpc = (dst->format == DFX_FORMAT_RGBA16F || dst->format == DFX_FORMAT_RG16F) ? 2 : 1;
+        fill_narrow_kernel<<<dim3(div_up(dst->width * nch, 256), dst->height), 256, 0, as_stream(stream)>>>(static_cast<unsigned char*>(dst->ptr), dst->pitch_bytes, dst->width, dst->height,
+                                                                                                         nch, bpc, make_float4(value[0], value[1], value[2], value[3]));
+        DFX_LAUNCHED("fill_narrow_kernel");
         return DFX_OK;
     }
     int ch = dst->format == DFX_FORMAT_R32F ? 1 : dst->format == DFX_FORMAT_RG32F ? 2 : 4;

@@ -60,7 +60,13 @@ enum TEXTURE_FORMAT : Uint32
     TEX_FORMAT_R32_FLOAT    = DFX_FORMAT_R32F,
     TEX_FORMAT_RG32_FLOAT   = DFX_FORMAT_RG32F,
     TEX_FORMAT_RGBA32_FLOAT = DFX_FORMAT_RGBA32F,
-    TEX_FORMAT_R8_UINT      = DFX_FORMAT_R8U
+    TEX_FORMAT_R8_UINT      = DFX_FORMAT_R8U,
+    // the G-buffer's own formats (Hydrogent/src/Tasks/HnBeginFrameTask.cpp:63-69): read by the passes as they are
+    TEX_FORMAT_RGBA16_FLOAT = DFX_FORMAT_RGBA16F,
+    TEX_FORMAT_RG16_FLOAT   = DFX_FORMAT_RG16F,
+    TEX_FORMAT_RG8_UNORM    = DFX_FORMAT_RG8U,
+    TEX_FORMAT_RGBA8_UNORM  = DFX_FORMAT_RGBA8U,
+    TEX_FORMAT_D32_FLOAT    = DFX_FORMAT_R32F // depth is an R32F plane here
 };
 
 class IRenderDevice

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "dfx/GBuffer.hpp"
 #include "dfx/PostProcessEffects.hpp"
 
 using namespace Diligent;
@@ -49,9 +50,14 @@ int main(int argc, char** argv)
     IDeviceContext Context; // default stream
 
     // G-buffer planes (what the renderer would hand over)
-    ITexture     Depth{W, H, TEX_FORMAT_R32_FLOAT}, PrevDepth{W, H, TEX_FORMAT_R32_FLOAT}, Motion{W, H, TEX_FORMAT_RG32_FLOAT};
-    ITexture     Normal{W, H, TEX_FORMAT_RGBA32_FLOAT}, Color{W, H, TEX_FORMAT_RGBA32_FLOAT}, Material{W, H, TEX_FORMAT_RGBA32_FLOAT};
-    ITexture     Composed{W, H, TEX_FORMAT_RGBA32_FLOAT}, LDR{W, H, TEX_FORMAT_RGBA32_FLOAT};
+    // ... held in a Diligent::GBuffer (Components/interface/GBuffer.hpp), like Hydrogent's HnBeginFrameTask does
+    GBuffer::ElementDesc Elems[6];
+    Elems[0].Format = TEX_FORMAT_D32_FLOAT, Elems[0].BindFlags = BIND_DEPTH_STENCIL | BIND_SHADER_RESOURCE, Elems[1] = Elems[0];
+    Elems[2].Format = TEX_FORMAT_RG32_FLOAT, Elems[3].Format = Elems[4].Format = Elems[5].Format = TEX_FORMAT_RGBA32_FLOAT;
+    GBuffer   GB{Elems, 6, &Device, W, H};
+    GB.Bind(&Context, 0x3Fu, nullptr, 0x3Fu); // clears every buffer to its ClearValue (depth 1, colours 0) before the frame's data arrives
+    ITexture &Depth = *GB.GetBuffer(0), &PrevDepth = *GB.GetBuffer(1), &Motion = *GB.GetBuffer(2), &Normal = *GB.GetBuffer(3), &Color = *GB.GetBuffer(4), &Material = *GB.GetBuffer(5);
+    ITexture  Composed{W, H, TEX_FORMAT_RGBA32_FLOAT}, LDR{W, H, TEX_FORMAT_RGBA32_FLOAT};
     ITextureView DepthSRV{&Depth}, PrevDepthSRV{&PrevDepth}, MotionSRV{&Motion}, NormalSRV{&Normal}, ColorSRV{&Color}, MaterialSRV{&Material};
     ITextureView ComposedView{&Composed}, LDRView{&LDR};
 

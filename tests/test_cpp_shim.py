@@ -13,7 +13,7 @@ INC = os.path.join(ROOT, "include")
 OUT = os.path.join(ROOT, "tests", "cpp", "_build")
 
 
-@pytest.mark.parametrize("header", ["dfx/DiligentShim.hpp", "dfx/PostFXContext.hpp", "dfx/PostProcessEffects.hpp", "dfx_b200.h"])
+@pytest.mark.parametrize("header", ["dfx/DiligentShim.hpp", "dfx/GBuffer.hpp", "dfx/PostFXContext.hpp", "dfx/PostProcessEffects.hpp", "dfx_b200.h"])
 def test_header_is_self_contained(header):
     src = f'#include "{header}"\nint main() {{ return 0; }}\n'
     r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-", "-I", INC], input=src.encode(), capture_output=True)
