@@ -71,6 +71,11 @@ PASS_BYTES_PER_PX = {
 }
 
 
+# extra bytes per pixel when the G-buffer planes are widened to fp32 (--gbuffer fp32): colour / normal +8, motion +4, material +14
+FP32_GBUFFER_EXTRA = {"postfx_prepare": 4.0, "ssr_mask_roughness": 14.0, "ssr_intersect": 16.0, "ssr_spatial": 8.0, "ssr_temporal": 4.0, "ssr_bilateral": 8.0,
+                      "ssao_ambient_occlusion": 8.0, "ssao_spatial": 8.0, "compose": 8.0, "compose_taa": 8.0}
+
+
 def bloom_bytes(W: int, H: int, mips: int, first: int) -> dict:
     """Exact algorithmic bytes of the Bloom pyramid passes from the level sizes (16 B texels): B2 per-level launches cover the levels
     1 .. first-1, the tail launch the levels first .. mips-1 down and mips-2 .. first-1 up, B3 per-level launches the levels first-2 .. 0."""
@@ -393,6 +398,8 @@ def main() -> None:
     ap.add_argument("--strips-width", type=int, default=7680)
     ap.add_argument("--strips-height", type=int, default=4320)
     ap.add_argument("--strips-steps", type=int, default=20)
+    ap.add_argument("--gbuffer", default="native", choices=["native", "fp32"],
+                    help="device-resident arm: G-buffer planes in the renderer's formats (RGBA16F / RG16F / RG8, what the passes read directly) or widened to fp32")
     ap.add_argument("--no-graph", action="store_true", help="issue every frame eagerly (no CUDA-graph replay)")
     ap.add_argument("--dof", action="store_true", help="add DepthOfField between TAA and Bloom (NOT the BASELINE.json workload; config.workload says so)")
     args = ap.parse_args()
@@ -435,7 +442,8 @@ def main() -> None:
     seq = [widen_frame(p) for p in packed]
     host = [{n: torch.from_numpy(np.ascontiguousarray(fr[n])).pin_memory() for n in INPUT_SPECS} for fr in seq]
     # device-resident arm: the G-buffer lies in HBM in the renderer's formats (what `packed` holds) and the passes read it as such
-    resident = [{n: (packed[i][PACKED_SPECS[n][0]].to(dev) if n in PACKED_SPECS else host[i][n].to(dev)) for n in INPUT_SPECS} for i in range(len(host))]
+    native = args.gbuffer == "native"
+    resident = [{n: (packed[i][PACKED_SPECS[n][0]].to(dev) if (native and n in PACKED_SPECS) else host[i][n].to(dev)) for n in INPUT_SPECS} for i in range(len(host))]
     cams = [(fr["curr_camera"], fr["prev_camera"]) for fr in seq]
     # consecutive frames: the previous depth is the depth of the frame before and stays on the device (stream_frames docstring)
     packed = [{k: v for k, v in p.items() if k != "prev_depth"} for p in packed]
@@ -547,7 +555,7 @@ def main() -> None:
             nm = name.value.decode()
             ms = tot.value / K                                  # per step (a pass may launch several kernels / levels)
             step_sum += ms
-            by = pyramid_bytes.get(nm, PASS_BYTES_PER_PX.get(nm, 0.0) * W * H)
+            by = pyramid_bytes.get(nm, (PASS_BYTES_PER_PX.get(nm, 0.0) + (0.0 if native else FP32_GBUFFER_EXTRA.get(nm, 0.0))) * W * H)
             gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             passes.append({"pass": nm, "ms": round(ms, 4), "launch_groups_per_step": calls.value // K, "alg_bytes": int(by), "GBps": round(gbs, 1),
                            "frac": round(gbs / peak, 4)})
@@ -611,10 +619,13 @@ def main() -> None:
                        "issue": {**issue, "what": "frames replayed from CUDA graphs (steady state) vs issued eagerly, since the chain was created; "
                                                   "1 native call (dfx_chain_execute) per frame either way"},
                        "tune": os.environ.get("DFX_TUNE", ""), "host_affinity": affinity,
+                       "gbuffer": ("renderer formats (colour / normal RGBA16F, motion RG16F, material RG8, depth R32F), read directly by the passes" if native
+                                   else "widened to fp32 planes"),
                        "cache": f"{args.frames} distinct resident G-buffers of {h2d_bytes_fp32 / 1e6:.0f} MB cycled: inputs larger than the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4), "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes),
+                    "h2d_GBps": round(h2d_bytes / (e2e_ms * 1e-3) / 1e9, 1),   # what bounds this number: the host link (PCIe 5 x16, ~55 GB/s achievable), not a kernel
                     "formats": "host G-buffer in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8 material, fp32 depth = "
                                "26 B/px; the previous depth is the depth of the frame before and stays on the device), read by the passes in those formats (no widening pass); result read back as RGBA8 (4 B/px); PostProcessChain.stream_frames("
                                "packed=True): copy-in / compute / copy-out pipelined on 3 streams",

@@ -404,11 +404,11 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
     const int   s0 = (lane >> 1) + (lane & 1);
     const bool  odd = lane & 1;
     const float w0 = odd ? 3.f / 16 : 1.f / 16, w1 = odd ? 7.f / 16 : 5.f / 16, w2 = odd ? 5.f / 16 : 7.f / 16, w3 = odd ? 1.f / 16 : 3.f / 16;
-    auto hrow = [&](int j) { // horizontal 4-tap of the coarse row j (clamped)
-        const int    cj = min(max(j, 0), coarser.h - 1);
-        const float3 c = lane < 20 ? xyz(__ldg(&coarser.at(ck, cj))) : make_float3(0.f, 0.f, 0.f);
-        return shfl3(c, s0) * w0 + shfl3(c, s0 + 1) * w1 + shfl3(c, s0 + 2) * w2 + shfl3(c, s0 + 3) * w3;
+    auto load_coarse = [&](int j) { // this lane's texel of the coarse row j (clamped); lanes 20..31 hold nothing
+        const int cj = min(max(j, 0), coarser.h - 1);
+        return lane < 20 ? xyz(__ldg(&coarser.at(ck, cj))) : make_float3(0.f, 0.f, 0.f);
     };
+    auto hfilter = [&](float3 c) { return shfl3(c, s0) * w0 + shfl3(c, s0 + 1) * w1 + shfl3(c, s0 + 2) * w2 + shfl3(c, s0 + 3) * w3; }; // horizontal 4-tap
     auto load_fine = [&](int y) { return (xin && y < y1) ? __ldg(&fine.at(x, y)) : make_float4(0.f, 0.f, 0.f, 0.f); };
     auto emit = [&](int y, float3 s, float4 f) {
         if (!xin || y >= y1) return;
@@ -426,14 +426,20 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
         else
             out.at(x, y) = f4(c + s, 0.0f);
     };
+    // Software pipeline: the fine texels of the next TWO steps and the coarse row of the next step are always in flight, so a step
+    // never waits for a load it has just issued (one warp keeps 4 x 512 B + 320 B outstanding).
     const int jb = fyb >> 1;
-    float4    f0 = load_fine(fyb), f1 = load_fine(fyb + 1);
-    float3    H0 = hrow(jb - 2), H1 = hrow(jb - 1), H2 = hrow(jb), H3 = hrow(jb + 1);
+    float4    f0 = load_fine(fyb), f1 = load_fine(fyb + 1), g0 = load_fine(fyb + 2), g1 = load_fine(fyb + 3);
+    float3    cnext = load_coarse(jb + 2);
+    float3    H0 = hfilter(load_coarse(jb - 2)), H1 = hfilter(load_coarse(jb - 1)), H2 = hfilter(load_coarse(jb)), H3 = hfilter(load_coarse(jb + 1));
     for (int j = jb; 2 * j < fye; ++j)
     {
         const float4 c0 = f0, c1 = f1;
-        f0 = load_fine(2 * j + 2), f1 = load_fine(2 * j + 3); // next iteration's fine texels: in flight during this one
-        const float3 H4 = hrow(j + 2);
+        const float3 ccur = cnext;
+        f0 = g0, f1 = g1;
+        g0 = load_fine(2 * j + 4), g1 = load_fine(2 * j + 5);
+        cnext = load_coarse(j + 3);
+        const float3 H4 = hfilter(ccur);
         emit(2 * j, H0 * (1.f / 16) + H1 * (5.f / 16) + H2 * (7.f / 16) + H3 * (3.f / 16), c0);
         emit(2 * j + 1, H1 * (3.f / 16) + H2 * (7.f / 16) + H3 * (5.f / 16) + H4 * (1.f / 16), c1);
         H0 = H1, H1 = H2, H2 = H3, H3 = H4;

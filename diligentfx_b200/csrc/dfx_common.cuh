@@ -153,6 +153,70 @@ struct Tex2
         return __half22float2(*reinterpret_cast<const __half2*>(&v));
     }
 };
+// The same with the format as a COMPILE-TIME parameter: what the kernels take. The run-time form above costs the issue-bound kernels
+// registers (a fifth field per plane, both load paths live: measured +10 % on the ray march, spills under its 40-register cap);
+// the host picks the instantiation from the plane's format (DFX_FMT16 below).
+template <int FMT>
+struct Tex4T
+{
+    const char* p;
+    int         pitch, w, h;
+    __host__ __device__ Tex4T() = default;
+    __host__ __device__ Tex4T(const Tex4& t) : p(t.p), pitch(t.pitch), w(t.w), h(t.h) {}
+    __device__ __forceinline__ float4 ld(int x, int y) const
+    {
+        const char* row = p + (unsigned)(y * pitch);
+        if constexpr (FMT == DFX_FORMAT_RGBA32F) return __ldg(reinterpret_cast<const float4*>(row) + x);
+        else if constexpr (FMT == DFX_FORMAT_RGBA16F)
+        {
+            const uint2  v = __ldg(reinterpret_cast<const uint2*>(row) + x);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            return make_float4(a.x, a.y, b.x, b.y);
+        }
+        else
+        {
+            const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(row) + x);
+            return make_float4(float(v.x) / 255.0f, float(v.y) / 255.0f, 0.0f, 0.0f);
+        }
+    }
+};
+template <int FMT>
+struct Tex2T
+{
+    const char* p;
+    int         pitch, w, h;
+    __host__ __device__ Tex2T() = default;
+    __host__ __device__ Tex2T(const Tex2& t) : p(t.p), pitch(t.pitch), w(t.w), h(t.h) {}
+    __device__ __forceinline__ float2 ld(int x, int y) const
+    {
+        const char* row = p + (unsigned)(y * pitch);
+        if constexpr (FMT == DFX_FORMAT_RG32F) return __ldg(reinterpret_cast<const float2*>(row) + x);
+        else
+        {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(row) + x);
+            return __half22float2(*reinterpret_cast<const __half2*>(&v));
+        }
+    }
+};
+template <bool H16> using TexRGBA = Tex4T<H16 ? DFX_FORMAT_RGBA16F : DFX_FORMAT_RGBA32F>;
+template <bool H16> using TexRG   = Tex2T<H16 ? DFX_FORMAT_RG16F : DFX_FORMAT_RG32F>;
+inline bool is16(const Tex4& t) { return t.fmt == DFX_FORMAT_RGBA16F; }
+inline bool is16(const Tex2& t) { return t.fmt == DFX_FORMAT_RG16F; }
+// DFX_FMT16(cond, H, statement): runs `statement` with `constexpr bool H` = cond
+#define DFX_FMT16(cond, H, ...)          \
+    do {                                 \
+        if (cond)                        \
+        {                                \
+            constexpr bool H = true;     \
+            __VA_ARGS__;                 \
+        }                                \
+        else                             \
+        {                                \
+            constexpr bool H = false;    \
+            __VA_ARGS__;                 \
+        }                                \
+    } while (0)
+
 inline bool make_tex4(const dfx_plane* pl, Tex4& t, bool allow_rg8 = false)
 {
     if (!pl || !pl->ptr || pl->width <= 0 || pl->height <= 0) return false;

@@ -65,8 +65,9 @@ struct PrepCam
     Mat4  curr_vp_inv, prev_vp;
 };
 
+template <bool M16>
 __global__ void __launch_bounds__(256) postfx_prepare_kernel(const dfx_camera_attribs* __restrict__ cams, View<const float> depth,
-                                                             View<const float> prev_in, Tex2 motion, View<float> reproj,
+                                                             View<const float> prev_in, TexRG<M16> motion, View<float> reproj,
                                                              View<float2> closest, View<float> prev_out, int y0, int y1, int rev)
 {
     __shared__ PrepCam cam;
@@ -143,7 +144,7 @@ void preload_postfx_kernels() // force the lazily-loaded kernels of this file in
     cudaFuncAttributes fa;
     (void)cudaFuncGetAttributes(&fa, upload_cameras_kernel);
     (void)cudaFuncGetAttributes(&fa, blue_noise_kernel);
-    (void)cudaFuncGetAttributes(&fa, postfx_prepare_kernel);
+    (void)cudaFuncGetAttributes(&fa, postfx_prepare_kernel<false>);
 }
 
 dfx_status launch_blue_noise(void* stream, const uint8_t* tables, uint32_t frame_index, const uint32_t* frame_index_dev, const dfx_plane* xy, const dfx_plane* zw)
@@ -184,7 +185,7 @@ extern "C" dfx_status dfx_pass_postfx_prepare(void* stream, const dfx_camera_att
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(d.w, 32), div_up(rows.y1 - rows.y0, 8));
-    postfx_prepare_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, d, pin, m, rp, cm, pout, rows.y0, rows.y1, reversed_depth(curr_depth));
+    DFX_FMT16(is16(m), M16, postfx_prepare_kernel<M16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, d, pin, m, rp, cm, pout, rows.y0, rows.y1, reversed_depth(curr_depth)));
     DFX_LAUNCHED("postfx_prepare_kernel");
     return DFX_OK;
 }

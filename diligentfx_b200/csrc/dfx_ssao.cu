@@ -66,9 +66,9 @@ struct __align__(16) AoLevel
     int          h, pad0;
 };
 
-template <int ALGO>
+template <int ALGO, bool N16>
 __global__ void __launch_bounds__(256, DFX_OCC_AO) ssao_ao_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, PyrView pyr,
-                                                      Tex4 normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half, float self_offset)
+                                                      TexRGBA<N16> normal, View<const float2> noise, View<float> out, int y0, int y1, int rev, int half, float self_offset)
 {
     __shared__ SsaoCam S;
     __shared__ AoLevel lvl[DFX_MAX_MIPS];
@@ -385,8 +385,9 @@ DFX_HD float geometry_weight(float3 center, float3 tap, float3 n, float planeNor
     return saturate(1.0f - fabsf(dot(tap - center, n)) * planeNorm);
 }
 
+template <bool N16>
 __global__ void __launch_bounds__(256) ssao_resample_kernel(const dfx_camera_attribs* __restrict__ cams, PyrView occ, PyrView dep,
-                                                            View<const float> history, Tex4 normal, View<float> out, int y0, int y1, int rev)
+                                                            View<const float> history, TexRGBA<N16> normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     stage_cam(S, cams);
@@ -448,9 +449,10 @@ __constant__ float3 kPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0
 // exp(-z^2 / (2 * 0.9^2)) for the eight disk samples (the shader evaluates this constant expression per tap)
 __constant__ float kPoisson8Weight[8] = {0.77283178f, 0.570022457f, 0.838854363f, 0.769187387f, 0.758268871f, 0.940613337f, 0.613583686f, 0.650469323f};
 
+template <bool N16>
 __global__ void __launch_bounds__(256) ssao_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A,
                                                            View<const float> occlusion, View<const float> history, View<const float> depth,
-                                                           Tex4 normal, View<float> out, int y0, int y1, int rev)
+                                                           TexRGBA<N16> normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam S;
     stage_cam(S, cams);
@@ -515,9 +517,10 @@ struct SpatialMaps
 };
 constexpr int kSpTileW = 40, kSpTileH = 16;
 
+template <bool N16>
 __global__ void __launch_bounds__(256) ssao_spatial_tile_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssao_attribs A, const __grid_constant__ SpatialMaps maps,
                                                                 View<const float> occlusion, View<const float> history, View<const float> depth,
-                                                                Tex4 normal, View<float> out, int y0, int y1, int rev)
+                                                                TexRGBA<N16> normal, View<float> out, int y0, int y1, int rev)
 {
     __shared__ SsaoCam                  S;
     __shared__ __align__(128) float     tz[kSpTileH][kSpTileW];
@@ -655,9 +658,9 @@ extern "C" dfx_status dfx_pass_ssao_ambient_occlusion(void* stream, const dfx_ca
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
     switch (attribs->Algorithm)
     {
-        case DFX_SSAO_ALGORITHM_GTAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset); break;
-        case DFX_SSAO_ALGORITHM_HBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset); break;
-        case DFX_SSAO_ALGORITHM_VBAO: ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset); break;
+        case DFX_SSAO_ALGORITHM_GTAO: DFX_FMT16(is16(n), N16, ssao_ao_kernel<DFX_SSAO_ALGORITHM_GTAO, N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset)); break;
+        case DFX_SSAO_ALGORITHM_HBAO: DFX_FMT16(is16(n), N16, ssao_ao_kernel<DFX_SSAO_ALGORITHM_HBAO, N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset)); break;
+        case DFX_SSAO_ALGORITHM_VBAO: DFX_FMT16(is16(n), N16, ssao_ao_kernel<DFX_SSAO_ALGORITHM_VBAO, N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, P, n, bn, out, rows.y0, rows.y1, rev, half, self_offset)); break;
         default: return set_error(DFX_ERR_INVALID_ARG, "unknown SSAO algorithm %u", attribs->Algorithm);
     }
     DFX_LAUNCHED("ssao_ao_kernel");
@@ -766,7 +769,7 @@ extern "C" dfx_status dfx_pass_ssao_resample(void* stream, const dfx_camera_attr
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     dim3 block(32, 8), grid(div_up(out.w, 32), div_up(rows.y1 - rows.y0, 8));
-    ssao_resample_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, O, D, h, n, out, rows.y0, rows.y1, rev);
+    DFX_FMT16(is16(n), N16, ssao_resample_kernel<N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, O, D, h, n, out, rows.y0, rows.y1, rev));
     DFX_LAUNCHED("ssao_resample_kernel");
     return DFX_OK;
 }
@@ -798,9 +801,9 @@ extern "C" dfx_status dfx_pass_ssao_spatial(void* stream, const dfx_camera_attri
         mo = tensor_map_r32f(View<float>{const_cast<float*>(o.p), o.pitch, o.w, o.h}, kSpTileW, kSpTileH);
     }
     if (md && mo)
-        ssao_spatial_tile_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, SpatialMaps{*md, *mo}, o, h, d, n, out, rows.y0, rows.y1, rev);
+        DFX_FMT16(is16(n), N16, ssao_spatial_tile_kernel<N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, SpatialMaps{*md, *mo}, o, h, d, n, out, rows.y0, rows.y1, rev));
     else
-        ssao_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1, rev);
+        DFX_FMT16(is16(n), N16, ssao_spatial_kernel<N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, o, h, d, n, out, rows.y0, rows.y1, rev));
     DFX_LAUNCHED("ssao_spatial_kernel");
     return DFX_OK;
 }

@@ -21,7 +21,8 @@ __host__ __device__ inline int ssr_mip_row(int y, int m, int full_h, int mip_h) 
 // ---------------------------------------------------------------------------------------------------------------------
 // S2: reflection mask + roughness extraction — SSR_ComputeStencilMaskAndExtractRoughness.fx:13-40
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, Tex4 material, View<const float> depth,
+template <int MFMT>
+__global__ void __launch_bounds__(256) ssr_mask_kernel(dfx_ssr_attribs A, Tex4T<MFMT> material, View<const float> depth,
                                                        View<float> roughness, View<uint8_t> mask, int y0, int y1, int rev)
 {
     const PixelXY pix = cta_pixel(y0);
@@ -159,19 +160,19 @@ __device__ __forceinline__ float hiz_load(const HizLevel& L, const PeerTables& P
 }
 __device__ __forceinline__ float hiz_load(const HizLevel& L, const NoPeerTables&, int x, int y, int) { return hiz_load(L, x, y); }
 // Load of a full-res RGBA plane at the hit texel (0 out of bounds): from the owner of row y.
-template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const Tex4& v, const PeerTables& P, int x, int y) // peer planes are RGBA32F (host-checked)
+template <bool NORMAL, class V> __device__ __forceinline__ float4 hit_load0(const V& v, const PeerTables& P, int x, int y) // peer planes are RGBA32F (host-checked)
 {
     if (!((unsigned)x < (unsigned)v.w && (unsigned)y < (unsigned)v.h)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* base = (NORMAL ? P.normal : P.color)[P.owner[y >> kPeerBlockShift]];
     return __ldg(base + (unsigned)(y * (v.pitch >> 4) + x));
 }
-template <bool NORMAL> __device__ __forceinline__ float4 hit_load0(const Tex4& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
+template <bool NORMAL, class V> __device__ __forceinline__ float4 hit_load0(const V& v, const NoPeerTables&, int x, int y) { return load0(v, x, y); }
 
-template <bool PREV_FRAME, bool PEER, bool REV>
+template <bool PREV_FRAME, bool PEER, bool REV, bool G16>
 __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                            Tex4 color, Tex4 normal, View<const float> roughness,
+                                                            TexRGBA<G16> color, TexRGBA<G16> normal, View<const float> roughness,
                                                             View<const uint8_t> mask, View<const float2> noise, HizView hiz,
-                                                            Tex2 motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1, int half,
+                                                            TexRG<G16> motion, View<float4> out_rad, View<float4> out_dir, int y0, int y1, int half,
                                                             const __grid_constant__ typename std::conditional<PEER, PeerArgs, NoPeerTables>::type peer_args)
 {
     __shared__ IntersectCam S;
@@ -398,8 +399,9 @@ struct SpatialCam
     Mat4 vp_inv;
 };
 
+template <bool N16>
 __global__ void __launch_bounds__(256, DFX_OCC_SSR_SPATIAL) ssr_spatial_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                          View<const float> roughness, View<const uint8_t> mask, Tex4 normal,
+                                                          View<const float> roughness, View<const uint8_t> mask, TexRGBA<N16> normal,
                                                           View<const float> depth, View<const float4> raydir, View<const float4> radiance,
                                                           View<float4> out_rad, View<float> out_var, View<float> out_depth, int y0, int y1, int half)
 {
@@ -505,9 +507,9 @@ constexpr float kNegLn045 = 0.798507696f; // -ln(SSR_DISOCCLUSION_THRESHOLD / 2)
 struct NoPeerMap
 {
 };
-template <bool PEER>
+template <bool PEER, bool M16>
 __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                           View<const uint8_t> mask, Tex2 motion, View<const float> hit_depth,
+                                                           View<const uint8_t> mask, TexRG<M16> motion, View<const float> hit_depth,
                                                            View<const float> curr_depth, View<const float4> curr_rad, View<const float> curr_var,
                                                            View<const float> prev_depth_, View<const float4> prev_rad_, View<const float> prev_var_,
                                                            View<float4> out_rad, View<float> out_var, int y0, int y1,
@@ -636,8 +638,9 @@ __global__ void __launch_bounds__(256, DFX_OCC_SSR_TEMPORAL) ssr_temporal_kernel
 // S7: bilateral cleanup — SSR_ComputeBilateralCleanup.fx:49-97. ddx/ddy(CameraZ) are the 2x2 pixel-quad finite
 // differences v(x|1) - v(x&~1), v(y|1) - v(y&~1) (coordinates clamped at odd image edges).
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool N16>
 __global__ void __launch_bounds__(256) ssr_bilateral_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_ssr_attribs A,
-                                                            View<const uint8_t> mask, View<const float> depth, Tex4 normal,
+                                                            View<const uint8_t> mask, View<const float> depth, TexRGBA<N16> normal,
                                                             View<const float> roughness, View<const float4> radiance, View<const float> variance,
                                                             View<float4> out, int y0, int y1, int rev)
 {
@@ -729,15 +732,15 @@ void preload_ssr_strip_kernels()
     (void)cudaFuncGetAttributes(&fa, pyramid_tail_kernel<HizOp>);
     (void)cudaFuncGetAttributes(&fa, pyramid_tile_kernel<HizOp, true>);
     (void)cudaFuncGetAttributes(&fa, pyramid_tile_kernel<HizOp, false>);
-    (void)cudaFuncGetAttributes(&fa, ssr_mask_kernel);
-    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, true, false>);
-    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, true, true>);
-    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, false, false>);
-    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, false, true>);
-    (void)cudaFuncGetAttributes(&fa, ssr_spatial_kernel);
-    (void)cudaFuncGetAttributes(&fa, ssr_temporal_kernel<true>);
-    (void)cudaFuncGetAttributes(&fa, ssr_temporal_kernel<false>);
-    (void)cudaFuncGetAttributes(&fa, ssr_bilateral_kernel);
+    (void)cudaFuncGetAttributes(&fa, ssr_mask_kernel<DFX_FORMAT_RGBA32F>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, true, false, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, true, true, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, false, false, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_intersect_kernel<false, false, true, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_spatial_kernel<false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_temporal_kernel<true, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_temporal_kernel<false, false>);
+    (void)cudaFuncGetAttributes(&fa, ssr_bilateral_kernel<false>);
     (void)cudaGetLastError();
 }
 } // namespace dfx
@@ -776,7 +779,9 @@ extern "C" dfx_status dfx_pass_ssr_mask_roughness(void* stream, const dfx_ssr_at
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(d.w, rows);
-    ssr_mask_kernel<<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1, reversed_depth(depth));
+    if (m.fmt == DFX_FORMAT_RGBA32F) ssr_mask_kernel<DFX_FORMAT_RGBA32F><<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1, reversed_depth(depth));
+    else if (m.fmt == DFX_FORMAT_RGBA16F) ssr_mask_kernel<DFX_FORMAT_RGBA16F><<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1, reversed_depth(depth));
+    else ssr_mask_kernel<DFX_FORMAT_RG8U><<<grid, block, 0, as_stream(stream)>>>(*attribs, m, d, r, k, rows.y0, rows.y1, reversed_depth(depth));
     DFX_LAUNCHED("ssr_mask_kernel");
     return DFX_OK;
 }
@@ -829,6 +834,8 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
     DFX_REQUIRE(rows_ok(rows, orad.h), "bad row range (rows of the intersect targets)");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(orad.w, rows);
+    const bool g16 = is16(c);
+    DFX_REQUIRE(is16(n) == g16, "colour and normal must both be RGBA16F or both RGBA32F");
     if (peers)
     {
         DFX_REQUIRE((flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME) == 0, "previous-frame SSR is not supported on peer-sharded frames");
@@ -857,28 +864,29 @@ static dfx_status ssr_intersect_impl(void* stream, const dfx_camera_attribs* cam
                 pa.hiz[m][i] = static_cast<const float*>(peers->hiz[m][i]);
             }
         }
-        Tex2 mv{nullptr, 0, 0, 0, DFX_FORMAT_RG32F};
+        Tex2 mv{nullptr, 0, 0, 0, g16 ? DFX_FORMAT_RG16F : DFX_FORMAT_RG32F};
         if (rev)
-            ssr_intersect_kernel<false, true, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
+            ssr_intersect_kernel<false, true, true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
         else
-            ssr_intersect_kernel<false, true, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
+            ssr_intersect_kernel<false, true, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, 0, pa);
     }
     else if (flags & DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME)
     {
         DFX_TEX2(mv, motion);
         DFX_SAME_SIZE(c, mv);
+        DFX_REQUIRE(is16(mv) == g16, "motion must be RG16F with an RGBA16F G-buffer and RG32F with an RGBA32F one");
         if (rev)
-            ssr_intersect_kernel<true, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
+            DFX_FMT16(g16, G16, ssr_intersect_kernel<true, false, true, G16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{}));
         else
-            ssr_intersect_kernel<true, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
+            DFX_FMT16(g16, G16, ssr_intersect_kernel<true, false, false, G16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{}));
     }
     else
     {
-        Tex2 mv{nullptr, 0, 0, 0, DFX_FORMAT_RG32F};
+        Tex2 mv{nullptr, 0, 0, 0, g16 ? DFX_FORMAT_RG16F : DFX_FORMAT_RG32F};
         if (rev)
-            ssr_intersect_kernel<false, false, true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
+            DFX_FMT16(g16, G16, ssr_intersect_kernel<false, false, true, G16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{}));
         else
-            ssr_intersect_kernel<false, false, false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{});
+            DFX_FMT16(g16, G16, ssr_intersect_kernel<false, false, false, G16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, c, n, r, k, bn, H, mv, orad, odir, rows.y0, rows.y1, half, NoPeerTables{}));
     }
     DFX_LAUNCHED("ssr_intersect_kernel");
     return DFX_OK;
@@ -933,7 +941,7 @@ extern "C" dfx_status dfx_pass_ssr_spatial(void* stream, const dfx_camera_attrib
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(d.w, rows);
-    ssr_spatial_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, r, k, n, d, rd, ra, orad, ovar, odep, rows.y0, rows.y1, half);
+    DFX_FMT16(is16(n), N16, ssr_spatial_kernel<N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, r, k, n, d, rd, ra, orad, ovar, odep, rows.y0, rows.y1, half));
     DFX_LAUNCHED("ssr_spatial_kernel");
     return DFX_OK;
 }
@@ -974,10 +982,10 @@ static dfx_status ssr_temporal_impl(const dfx_peer_map* peers, void* stream, con
     {
         PeerMap pm;
         DFX_REQUIRE(make_peer_map(peers, cd.h, pm), "bad peer map (rank count, 64-row aligned strips, slab bases)");
-        ssr_temporal_kernel<true><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1, pm);
+        DFX_FMT16(is16(mv), M16, ssr_temporal_kernel<true, M16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1, pm));
     }
     else
-        ssr_temporal_kernel<false><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1, NoPeerMap{});
+        DFX_FMT16(is16(mv), M16, ssr_temporal_kernel<false, M16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, mv, hd, cd, cr, cv, pd, pr, pv, orad, ovar, rows.y0, rows.y1, NoPeerMap{}));
     DFX_LAUNCHED("ssr_temporal_kernel");
     return DFX_OK;
 }
@@ -1024,7 +1032,7 @@ extern "C" dfx_status dfx_pass_ssr_bilateral(void* stream, const dfx_camera_attr
     DFX_REQUIRE(rows_ok(rows, d.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(d.w, rows);
-    ssr_bilateral_kernel<<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, d, n, r, ra, va, o, rows.y0, rows.y1, reversed_depth(depth));
+    DFX_FMT16(is16(n), N16, ssr_bilateral_kernel<N16><<<grid, block, 0, as_stream(stream)>>>(cameras_dev, *attribs, k, d, n, r, ra, va, o, rows.y0, rows.y1, reversed_depth(depth)));
     DFX_LAUNCHED("ssr_bilateral_kernel");
     return DFX_OK;
 }

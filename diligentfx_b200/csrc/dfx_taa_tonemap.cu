@@ -59,8 +59,8 @@ struct ComposeIn
     View<const float>  ao;
     float              ssr_scale, ssao_scale;
 };
-template <bool COMPOSE>
-DFX_HD float3 load_scene_colour(const Tex4& color, const ComposeIn& ci, int gx, int gy)
+template <bool COMPOSE, class TexC>
+DFX_HD float3 load_scene_colour(const TexC& color, const ComposeIn& ci, int gx, int gy)
 {
     float3 c = xyz(color.ld(gx, gy));
     if (COMPOSE)
@@ -75,8 +75,8 @@ DFX_HD float3 load_scene_colour(const Tex4& color, const ComposeIn& ci, int gx, 
     return c;
 }
 
-template <bool BICUBIC, bool YCOCG, bool GAUSS, bool COMPOSE>
-__global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, Tex4 curr_color,
+template <bool BICUBIC, bool YCOCG, bool GAUSS, bool COMPOSE, bool C16>
+__global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_attribs* __restrict__ cams, dfx_taa_attribs A, TexRGBA<C16> curr_color,
                                                   ComposeIn ci, View<const float4> prev_accum, View<const float2> motion, View<const float> curr_depth,
                                                   View<const float> prev_depth, View<float4> out, int y0, int y1)
 {
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256, DFX_OCC_TAA) taa_kernel(const dfx_camera_
 // =====================================================================================================================
 // compose (reduced form of HnPostProcess.psh:145-185): rgb += ssr.rgb*ssr.a*scale ; rgb *= lerp(1, ao, scale)
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) compose_kernel(Tex4 color, View<const float4> ssr, View<const float> ao, float ssr_scale,
+template <bool C16>
+__global__ void __launch_bounds__(256) compose_kernel(TexRGBA<C16> color, View<const float4> ssr, View<const float> ao, float ssr_scale,
                                                       float ssao_scale, View<float4> out, int y0, int y1)
 {
     const PixelXY pix = cta_pixel(y0);
@@ -282,9 +283,9 @@ static dfx_status launch_taa(void* stream, const dfx_camera_attribs* cameras_dev
 #define TAA_LAUNCH(B, Y, G)                                                                                                            \
     do {                                                                                                                               \
         if (compose)                                                                                                                   \
-            taa_kernel<B, Y, G, true><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, ci, pa, mv, cd, pd, out, rows.y0, rows.y1);    \
+            DFX_FMT16(is16(cc), C16, taa_kernel<B, Y, G, true, C16><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, ci, pa, mv, cd, pd, out, rows.y0, rows.y1));    \
         else                                                                                                                           \
-            taa_kernel<B, Y, G, false><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, ci, pa, mv, cd, pd, out, rows.y0, rows.y1);   \
+            DFX_FMT16(is16(cc), C16, taa_kernel<B, Y, G, false, C16><<<grid, block, 0, s>>>(cameras_dev, *attribs, cc, ci, pa, mv, cd, pd, out, rows.y0, rows.y1));   \
     } while (0)
     switch (flags & 7u)
     {
@@ -341,7 +342,7 @@ extern "C" dfx_status dfx_pass_compose(void* stream, const dfx_plane* color, con
     DFX_REQUIRE(rows_ok(rows, out.h), "bad row range");
     if (rows.y1 == rows.y0) return DFX_OK;
     DFX_GRID(out.w, rows);
-    compose_kernel<<<grid, block, 0, as_stream(stream)>>>(c, s, a, ssr_scale, ssao_scale, out, rows.y0, rows.y1);
+    DFX_FMT16(is16(c), C16, compose_kernel<C16><<<grid, block, 0, as_stream(stream)>>>(c, s, a, ssr_scale, ssao_scale, out, rows.y0, rows.y1));
     DFX_LAUNCHED("compose_kernel");
     return DFX_OK;
 }
