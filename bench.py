@@ -391,6 +391,7 @@ def main() -> None:
     ap.add_argument("--ref-width", type=int, default=960)
     ap.add_argument("--ref-height", type=int, default=540)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--psnr", action="store_true", help="run the PSNR-vs-oracle leg at N > 1 too (default: N = 1 only)")
     ap.add_argument("--no-psnr", action="store_true", help="skip the PSNR-vs-oracle leg (4 frames of the CPU oracle at the benchmarked size)")
     ap.add_argument("--no-overlap", action="store_true", help="run every pass on one stream (no async compute)")
     ap.add_argument("--no-strips", action="store_true", help="skip the row-strip leg (config 4: one 8K SSR frame split over the ranks)")
@@ -598,7 +599,7 @@ def main() -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ref_width, args.ref_height, 3, os.cpu_count() or 1)
     quality = None
-    if rank == 0 and not args.no_psnr:
+    if rank == 0 and not args.no_psnr and (world == 1 or args.psnr):   # one check per build: the N = 1 line carries it (N > 1 would idle N - 1 GPUs meanwhile)
         quality = psnr_vs_oracle([{**fr, "frame": i} for i, fr in enumerate(seq)], W, H, os.cpu_count() or 1)
 
     strips = None
