@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(
 // shuffle, and the vertical filter slides over five coarse rows in registers, emitting two output rows per coarse row. The
 // fine-level texel (same-level down-sample for B3, the scene colour for B4) is read once, fully coalesced, and so is the store.
 
-template <bool COMPOSITE, bool TONEMAP>
+// TM: -1 = no tone map, otherwise the tone-mapping operator (a compile-time parameter: one operator's code per instantiation, and its
+// per-frame constants - exposure scale, white-point normalisation - are hoisted out of the row loop by the compiler)
+template <bool COMPOSITE, int TM>
 __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out,
                                                                               int y0, int y1, int coarse_rows_per_warp, ToneMapIn tm)
 {
@@ -416,9 +418,9 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
         if (COMPOSITE)
         {
             float3 o = lerp3(c, c + A.Intensity * s, A.AlphaInterpolation);
-            if (TONEMAP)
+            if (TM >= 0)
             {
-                o = tone_map_rt(tm.attribs.iToneMappingMode, o, tm.attribs, tm.ave_log_lum);
+                o = tone_map<TM>(o, tm.attribs, tm.ave_log_lum);
                 if (tm.to_srgb) o = linear_to_srgb(o);
             }
             st_cs(&out.at(x, y), f4(o, 0.0f));
@@ -618,13 +620,31 @@ static dfx_status launch_up(void* stream, int mode, const dfx_bloom_attribs& A, 
     if (exact && impl == 1)
     {
         const int bx = div_up(out.w, 32 * kStreamWarps), n = div_up(rows.y1 - rows.y0, 2); // coarse rows
-        const int cpw = mode == 0   ? stream_rows_per_warp(bloom_up2x_stream_kernel<false, false>, bx * kStreamWarps, n, 1)
-                        : mode == 1 ? stream_rows_per_warp(bloom_up2x_stream_kernel<true, false>, bx * kStreamWarps, n, 1)
-                                    : stream_rows_per_warp(bloom_up2x_stream_kernel<true, true>, bx * kStreamWarps, n, 1);
-        const dim3 grid(bx, div_up(n, cpw));
-        if (mode == 0) bloom_up2x_stream_kernel<false, false><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);
-        if (mode == 1) bloom_up2x_stream_kernel<true, false><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);
-        if (mode == 2) bloom_up2x_stream_kernel<true, true><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);
+#define DFX_UP_LAUNCH(COMP, TMODE)                                                                                                                   \
+    do {                                                                                                                                             \
+        const int  cpw = stream_rows_per_warp(bloom_up2x_stream_kernel<COMP, TMODE>, bx * kStreamWarps, n, 1);                                       \
+        const dim3 grid(bx, div_up(n, cpw));                                                                                                         \
+        bloom_up2x_stream_kernel<COMP, TMODE><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);                       \
+    } while (0)
+        if (mode == 0) DFX_UP_LAUNCH(false, -1);
+        else if (mode == 1) DFX_UP_LAUNCH(true, -1);
+        else
+            switch (tm.attribs.iToneMappingMode)
+            {
+                case DFX_TONE_MAPPING_MODE_NONE: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_NONE); break;
+                case DFX_TONE_MAPPING_MODE_EXP: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_EXP); break;
+                case DFX_TONE_MAPPING_MODE_REINHARD: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_REINHARD); break;
+                case DFX_TONE_MAPPING_MODE_REINHARD_MOD: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_REINHARD_MOD); break;
+                case DFX_TONE_MAPPING_MODE_UNCHARTED2: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_UNCHARTED2); break;
+                case DFX_TONE_MAPPING_MODE_FILMIC_ALU: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_FILMIC_ALU); break;
+                case DFX_TONE_MAPPING_MODE_LOGARITHMIC: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_LOGARITHMIC); break;
+                case DFX_TONE_MAPPING_MODE_ADAPTIVE_LOG: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_ADAPTIVE_LOG); break;
+                case DFX_TONE_MAPPING_MODE_AGX: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_AGX); break;
+                case DFX_TONE_MAPPING_MODE_AGX_CUSTOM: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_AGX_CUSTOM); break;
+                case DFX_TONE_MAPPING_MODE_PBR_NEUTRAL: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_PBR_NEUTRAL); break;
+                default: DFX_UP_LAUNCH(true, DFX_TONE_MAPPING_MODE_COMMERCE); break;
+            }
+#undef DFX_UP_LAUNCH
     }
     else if (exact && (impl == 0 || mode == 2))
     {
