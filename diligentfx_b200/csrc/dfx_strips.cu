@@ -59,9 +59,10 @@ struct PushSeg
     long long   pitch;  // bytes between rows
     int         rows, row_chunks; // 16-byte chunks per row
 };
+constexpr int kMaxPushSegs = 48; // halo pushes use up to 2 x kMaxPushPlanes; the Hi-Z all-gather 6 levels x 7 peers
 struct PushArgs
 {
-    PushSeg   seg[2 * kMaxPushPlanes];
+    PushSeg   seg[kMaxPushSegs];
     int       nseg;
     unsigned* flag_up;   // in the upper neighbour's slab (nullptr: no such neighbour)
     unsigned* flag_down; // in the lower neighbour's slab
@@ -251,7 +252,7 @@ extern "C" dfx_status dfx_ssr_strips_create(int32_t width, int32_t height, const
         ps.color[r]  = s->remote(static_cast<char*>(s->plane[DFX_SSR_STRIPS_PLANE_COLOR].ptr), r);
         ps.normal[r] = s->remote(static_cast<char*>(s->plane[DFX_SSR_STRIPS_PLANE_NORMAL].ptr), r);
         ps.hiz[0][r] = s->remote(static_cast<char*>(s->plane[DFX_SSR_STRIPS_PLANE_DEPTH].ptr), r);
-        for (int k = 1; k <= 6; ++k) ps.hiz[k][r] = s->remote(static_cast<char*>(s->plane[DFX_SSR_STRIPS_PLANE_HIZ1 + k - 1].ptr), r);
+        for (int k = 1; k <= 6; ++k) ps.hiz[k][r] = s->plane[DFX_SSR_STRIPS_PLANE_HIZ1 + k - 1].ptr; // gathered before the march: every row is local
     }
     *out = s;
     return DFX_OK;
@@ -317,6 +318,32 @@ dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const Pus
     DFX_LAUNCHED("flag_wait_kernel");
     return DFX_OK;
 }
+// The Hi-Z levels 1..6 of this rank's strip, copied into EVERY peer's slab (an all-gather by peer stores; the all-rank barrier that
+// follows is its completion). The march descends and climbs the pyramid in a dependent chain of ~36 loads per ray, and reflection
+// rays run mostly vertically - out of a row strip: served from the owner over NVLink every one of those loads would pay the link's
+// latency (measured: 2 GPUs no faster than 1). The coarse levels are 1/3 of a depth plane in total, so replicating them costs little;
+// level 0 (touched a few times per ray, at its ends) and the colour / normal at the hit stay peer loads.
+dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int levels)
+{
+    if (s->world == 1 || s->rows.y1 <= s->rows.y0) return DFX_OK;
+    PushArgs a{};
+    for (int m = 1; m < levels; ++m)
+    {
+        const dfx_plane& p  = s->plane[DFX_SSR_STRIPS_PLANE_HIZ1 + m - 1];
+        const int        r0 = s->rows.y0 >> m, r1 = s->rows.y1 >= s->h ? p.height : (s->rows.y1 >> m);
+        if (r1 <= r0) continue;
+        const int   chunks = int(align_up(size_t(p.width) * 4, 16) / 16);
+        const char* b      = static_cast<const char*>(p.ptr);
+        for (int r = 0; r < s->world; ++r)
+            if (r != s->rank && a.nseg < kMaxPushSegs) a.seg[a.nseg++] = PushSeg{b + size_t(r0) * p.pitch_bytes, s->remote(const_cast<char*>(b), r) - b, (long long)p.pitch_bytes, r1 - r0, chunks};
+    }
+    a.tickets = &s->sync->push_tickets[kFlagSlots - 1];
+    a.value   = 0; // no flags: the all-rank barrier orders it
+    halo_push_kernel<<<148, 256, 0, st>>>(a);
+    DFX_LAUNCHED("halo_push_kernel (Hi-Z all-gather)");
+    return DFX_OK;
+}
+
 dfx_status all_rank_barrier(dfx_ssr_strips* s, cudaStream_t st, int which)
 {
     if (s->world == 1) return DFX_OK;
@@ -373,7 +400,9 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
                                                          P(DFX_SSR_STRIPS_PLANE_MASK), wide)) != DFX_OK)
         return rc;
 
-    // S4 loads Hi-Z / colour / normal texels from whichever rank owns their row, S6 last frame's history: everybody's are complete
+    // S4 marches on a complete local copy of the Hi-Z levels >= 1 and loads depth / colour / normal texels from whichever rank owns
+    // their row, S6 last frame's history: after the barrier everybody's are complete
+    if ((rc = gather_hiz_levels(s, st, hz.levels)) != DFX_OK) return rc;
     if ((rc = all_rank_barrier(s, st, 0)) != DFX_OK) return rc;
     if (s->world > 1)
         rc = dfx_pass_ssr_intersect_peer(st, s->cams_dev, attribs, 0, &s->peer_set, P(DFX_SSR_STRIPS_PLANE_COLOR), P(DFX_SSR_STRIPS_PLANE_NORMAL), P(DFX_SSR_STRIPS_PLANE_ROUGHNESS),
