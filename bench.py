@@ -283,10 +283,27 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         msn = float(t.item())
         same = bool(np.array_equal(x.read("out"), one.read("out", rows=(x.y0, x.y1)))) and not x.timed_out()
+        # where the time goes, per rank: CUDA events around every pass and every exchange of 8 more frames (after the timed ones)
+        L = x.lib
+        L.dfx_profile_reset()
+        L.dfx_profile_enable(1)
+        for i in range(8):
+            x.execute(Wm + K + i, fr["curr_camera"], fr["prev_camera"])
+        torch.cuda.synchronize()
+        L.dfx_profile_enable(0)
+        L.dfx_profile_collect()
+        name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
+        mine = {}
+        for i in range(L.dfx_profile_count()):
+            L.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls))
+            mine[name.value.decode()] = round(tot.value / 8, 4)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
         ok = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         out.update({"n_gpus": world, "ms": round(msn, 4), "Mpix_s": round(W8 * H8 / 1e6 / (msn / 1e3), 1), "speedup": round(ms1 / msn, 3),
                     "efficiency": round(ms1 / msn / world, 3), "strips_bit_identical": bool(ok.item()), "bounds": bounds, "scaling": "strong",
+                    "per_rank_pass_ms": per_rank,
                     "exchange": "halo rows (64/4 depth, 4 normal + material, 1 motion; 4 ray planes; 1 resolved radiance; 2 radiance history) pushed into the neighbours' "
                                 "slabs by a copy kernel + flags in peer memory; Hi-Z / colour / normal at ray hits and last frame's history loaded from the owning GPU "
                                 "over NVLink; two all-rank flag barriers per frame; no NCCL call per frame"})
@@ -395,6 +412,7 @@ def main() -> None:
     ap.add_argument("--no-psnr", action="store_true", help="skip the PSNR-vs-oracle leg (4 frames of the CPU oracle at the benchmarked size)")
     ap.add_argument("--no-overlap", action="store_true", help="run every pass on one stream (no async compute)")
     ap.add_argument("--no-strips", action="store_true", help="skip the row-strip leg (config 4: one 8K SSR frame split over the ranks)")
+    ap.add_argument("--strips-only", action="store_true", help="only the row-strip leg (development: not the contract line)")
     ap.add_argument("--strips-n1", action="store_true", help="run the (unsharded) strips executor at N = 1 too")
     ap.add_argument("--strips-width", type=int, default=7680)
     ap.add_argument("--strips-height", type=int, default=4320)
@@ -433,12 +451,20 @@ def main() -> None:
 
     W, H, K, Wm = args.width, args.height, args.steps, args.warmup
     lib = capi.load()
+    if args.strips_only:
+        out = strips_leg(args, rank, world, dev)
+        if rank == 0:
+            print(json.dumps({"strips": out}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    # ---- synthetic data: `frames` consecutive frames of one camera path per rank (rank-specific seed) ----
+    # ---- synthetic data: `frames` consecutive frames of one camera path per rank ----
     # The renderer hands the G-buffer over in the reference's render-target formats (RGBA16F colour / normal, RG16F motion, RG8
     # material, D32F depths: Hydrogent/src/Tasks/HnBeginFrameTask.cpp:63-69); the fp32 planes the passes read are the exact
     # widening of those, on the device-resident arm as well, so both arms process the same values.
-    seq = synth.generate_sequence(W, H, args.frames, seed=7 + rank)
+    seq = synth.generate_sequence(W, H, args.frames, seed=7)   # the same sequence on every rank: weak scaling means equal work per GPU (a seed per rank
+    # made the ranks' frames differ in cost - reflective area - by several per cent, which the max-over-ranks time then read as a scaling loss)
     packed = [pack_frame(fr, pin=True) for fr in seq]
     seq = [widen_frame(p) for p in packed]
     host = [{n: torch.from_numpy(np.ascontiguousarray(fr[n])).pin_memory() for n in INPUT_SPECS} for fr in seq]

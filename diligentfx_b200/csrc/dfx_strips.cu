@@ -290,6 +290,7 @@ struct PushSpec
 dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const PushSpec* specs, int n)
 {
     if (s->world == 1 || (s->up < 0 && s->down < 0) || s->rows.y1 <= s->rows.y0) return DFX_OK;
+    DFX_PROFILE(st, "strips_halo_exchange"); // push + the wait for the neighbours' pushes (i.e. including their lateness)
     PushArgs a{};
     const int strip = s->rows.y1 - s->rows.y0;
     for (int i = 0; i < n; ++i)
@@ -326,6 +327,7 @@ dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const Pus
 dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int levels)
 {
     if (s->world == 1 || s->rows.y1 <= s->rows.y0) return DFX_OK;
+    DFX_PROFILE(st, "strips_gather_hiz");
     PushArgs a{};
     for (int m = 1; m < levels; ++m)
     {
@@ -347,6 +349,7 @@ dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int levels)
 dfx_status all_rank_barrier(dfx_ssr_strips* s, cudaStream_t st, int which)
 {
     if (s->world == 1) return DFX_OK;
+    DFX_PROFILE(st, which == 0 ? "strips_barrier_before_march" : "strips_barrier_frame_end");
     BarrierArgs a{};
     for (int r = 0; r < s->world; ++r) a.remote[r] = &s->remote(s->sync, r)->barrier[s->rank];
     a.local = s->sync->barrier, a.error = &s->sync->error, a.count = s->world, a.me = s->rank, a.value = s->seq * 2 + unsigned(which);

@@ -14,7 +14,7 @@ import json
 try:
     r = json.loads(open('gpurun_out/r2e_bench_n$N.json').read().strip().splitlines()[-1])
     print('N=$N value %.1f ms %.4f e2e %.1f (%.4f ms)' % (r['value'], r['ms_per_step'], r['e2e']['value'], r['e2e']['ms_per_step']))
-    print('strips', json.dumps(r.get('strips'))[:900])
+    print("strips", json.dumps(r.get("strips"))[:3000])
     print('issue', r['config'].get('issue'), r['config'].get('host_affinity'))
 except Exception as e:
     print('unreadable', e)
