@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         {
             const HizLevel L  = lvl[mip];
             const float    mx = L.resx * pos.x, my = L.resy * pos.y;
-            const float    surf = hiz_load(L, PT, (int)mx, (int)my, mip);
+            const float    surf = hiz_load(L, (int)mx, (int)my); // sharded frames too: the pyramid is complete on every GPU (gathered before the march)
             const float px = (floorf(mx) + fox) * L.irx + uox, py = (floorf(my) + foy) * L.iry + uoy;
             const float tx = px * invD.x - oxi, ty = py * invD.y - oyi;
             const float tz = surf * rz - oz;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         {
             const HizLevel L  = lvl[mip];
             const float    mx = L.resx * pos.x, my = L.resy * pos.y;
-            const float    surf = hiz_load(L, PT, (int)mx, (int)my, mip);
+            const float    surf = hiz_load(L, (int)mx, (int)my);
             // AdvanceRay :88-136
             const float px = (floorf(mx) + fox) * L.irx + uox, py = (floorf(my) + foy) * L.iry + uoy;
             const float tx = px * invD.x - oxi, ty = py * invD.y - oyi;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         if (!(mdx < (2.0f / sw) && mdy < (2.0f / sh)))
         {
             const int   tx = (int)(sw * pos.x), ty = (int)(sh * pos.y);
-            const float surfD = hiz_load(lvl[0], PT, tx, ty, 0);
+            const float surfD = hiz_load(lvl[0], tx, ty);
             if (!is_background(surfD, REV))
             {
                 const float3 hitN = xyz(hit_load0<true>(normal, PT, tx, ty));

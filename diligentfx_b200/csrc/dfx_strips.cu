@@ -319,19 +319,20 @@ dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const Pus
     DFX_LAUNCHED("flag_wait_kernel");
     return DFX_OK;
 }
-// The Hi-Z levels 1..6 of this rank's strip, copied into EVERY peer's slab (an all-gather by peer stores; the all-rank barrier that
-// follows is its completion). The march descends and climbs the pyramid in a dependent chain of ~36 loads per ray, and reflection
-// rays run mostly vertically - out of a row strip: served from the owner over NVLink every one of those loads would pay the link's
-// latency (measured: 2 GPUs no faster than 1). The coarse levels are 1/3 of a depth plane in total, so replicating them costs little;
-// level 0 (touched a few times per ray, at its ends) and the colour / normal at the hit stay peer loads.
+// The whole Hi-Z pyramid (depth = level 0 included) of this rank's strip, copied into EVERY peer's slab (an all-gather by peer stores;
+// the all-rank barrier that follows is its completion). The march descends and climbs the pyramid in a dependent chain of ~36 loads
+// per ray, and reflection rays run mostly vertically - out of a row strip: served from the owner over NVLink every one of those loads
+// pays the link's latency (measured on 2 GPUs: 1.006x with all levels remote, 1.41x with only level 0 remote - the bottom strip's march
+// alone then took longer than the unsharded frame's). 5.33 B/px replicated once per frame; the colour and the normal at the hit (two
+// independent loads per ray, after the loop) stay peer loads.
 dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int levels)
 {
     if (s->world == 1 || s->rows.y1 <= s->rows.y0) return DFX_OK;
     DFX_PROFILE(st, "strips_gather_hiz");
     PushArgs a{};
-    for (int m = 1; m < levels; ++m)
+    for (int m = 0; m < levels; ++m)
     {
-        const dfx_plane& p  = s->plane[DFX_SSR_STRIPS_PLANE_HIZ1 + m - 1];
+        const dfx_plane& p  = m == 0 ? s->plane[DFX_SSR_STRIPS_PLANE_DEPTH] : s->plane[DFX_SSR_STRIPS_PLANE_HIZ1 + m - 1];
         const int        r0 = s->rows.y0 >> m, r1 = s->rows.y1 >= s->h ? p.height : (s->rows.y1 >> m);
         if (r1 <= r0) continue;
         const int   chunks = int(align_up(size_t(p.width) * 4, 16) / 16);
@@ -403,8 +404,8 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
                                                          P(DFX_SSR_STRIPS_PLANE_MASK), wide)) != DFX_OK)
         return rc;
 
-    // S4 marches on a complete local copy of the Hi-Z levels >= 1 and loads depth / colour / normal texels from whichever rank owns
-    // their row, S6 last frame's history: after the barrier everybody's are complete
+    // S4 marches on a complete local copy of the Hi-Z pyramid and loads the colour / normal at the hit from whichever rank owns the
+    // row, S6 last frame's history: after the barrier everybody's are complete
     if ((rc = gather_hiz_levels(s, st, hz.levels)) != DFX_OK) return rc;
     if ((rc = all_rank_barrier(s, st, 0)) != DFX_OK) return rc;
     if (s->world > 1)

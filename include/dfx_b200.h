@@ -354,16 +354,17 @@ DFX_API dfx_status dfx_pass_ssr_intersect(void* stream, const dfx_camera_attribs
                                           const dfx_pyramid* hiz, const dfx_plane* motion,
                                           const dfx_plane* out_radiance, const dfx_plane* out_raydir_pdf, dfx_rows rows);
 
-/* S4 for one frame split into row strips over several GPUs of an NVLink / NVSwitch box. The march of a ray
- * may cross the whole screen, so instead of gathering Hi-Z / colour / normal onto every GPU before the pass, the kernel
- * loads each texel straight from the GPU that OWNS its row (peer loads; every GPU holds full-size planes at the same pitch,
- * valid on its own rows only). `color`, `normal`, `hiz` describe the local planes (sizes and pitches); `peers` gives, per
- * rank, the base pointer of the same plane as mapped into this process (cudaIpcOpenMemHandle, or a plain pointer when one
- * process drives all GPUs; base[own rank] = the local pointer). row_begin[r] .. row_begin[r+1] are the rows of full-res
- * planes rank r owns; every boundary but the last is a multiple of 64 so that every Hi-Z level splits at a row boundary.
- * Output is bit-identical to dfx_pass_ssr_intersect on complete planes. DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME is not
- * supported. The caller orders the producers on all GPUs before this launch (stream-ordered barrier) and this launch
- * before the next frame's writers. No reference counterpart: the reference renders a frame on one device.          */
+/* S4 for one frame split into row strips over several GPUs of an NVLink / NVSwitch box. The march of a ray may
+ * cross the whole screen. The Hi-Z pyramid `hiz` (depth included) must be COMPLETE on this GPU - the march walks it in a dependent
+ * chain of ~36 loads per ray, which must not cross the link (measured; the strips executor all-gathers it by peer stores) - while
+ * the colour and the normal at the hit, two independent loads per ray, are loaded straight from the GPU that OWNS the row (peer
+ * loads; every GPU holds full-size RGBA32F planes at the same pitch, valid on its own rows only). `color`, `normal` describe the
+ * local planes; `peers` gives, per rank, the base pointer of the same plane as mapped into this process (cudaIpcOpenMemHandle, or a
+ * plain pointer when one process drives all GPUs; base[own rank] = the local pointer; the `hiz` entries are not used).
+ * row_begin[r] .. row_begin[r+1] are the rows rank r owns; every boundary but the last is a multiple of 64. Output is bit-identical
+ * to dfx_pass_ssr_intersect on complete planes. DFX_SSR_FEATURE_FLAG_PREVIOUS_FRAME is not supported. The caller orders the
+ * producers on all GPUs before this launch (stream-ordered barrier) and this launch before the next frame's writers. No reference
+ * counterpart: the reference renders a frame on one device.                                                        */
 #define DFX_MAX_PEERS 8
 typedef struct dfx_peer_set {
     int32_t     count;                                  /* GPUs sharing the frame, 1..DFX_MAX_PEERS                    */
