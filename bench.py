@@ -250,7 +250,7 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
     # cost-balanced strips: rays are only marched for reflective pixels, which a frame concentrates where its glossy surfaces are
     small = synth.generate_sequence(W8 // 8, H8 // 8, 2, seed=11)[1]
     refl = (small["material"][..., 0] <= 0.2) & (small["depth"] < 1.0 - 1e-6)
-    bounds = strip_bounds(H8, world, weights=reflective_block_cost(refl.mean(axis=1), H8)) if world > 1 else [(0, H8)]
+    bounds = strip_bounds(H8, world, weights=reflective_block_cost(refl.mean(axis=1), H8, march_cost=args.strips_march_cost)) if world > 1 else [(0, H8)]
 
     def run(x, frames: int, timed_from: int) -> float:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -414,6 +414,7 @@ def main() -> None:
     ap.add_argument("--no-strips", action="store_true", help="skip the row-strip leg (config 4: one 8K SSR frame split over the ranks)")
     ap.add_argument("--strips-only", action="store_true", help="only the row-strip leg (development: not the contract line)")
     ap.add_argument("--strips-n1", action="store_true", help="run the (unsharded) strips executor at N = 1 too")
+    ap.add_argument("--strips-march-cost", type=float, default=13.0, help="cost of a reflective pixel relative to a plain one when the strips are balanced")
     ap.add_argument("--strips-width", type=int, default=7680)
     ap.add_argument("--strips-height", type=int, default=4320)
     ap.add_argument("--strips-steps", type=int, default=20)

@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
     }
 
     // ValidateHit :201-242
-    float confidence = 0.0f;
+    float  confidence = 0.0f;
+    float4 peer_colour = make_float4(0.f, 0.f, 0.f, 0.f);
     if (validHit && !(pos.x < 0.0f || pos.y < 0.0f || pos.x > 1.0f || pos.y > 1.0f))
     {
         const float mdx = fabsf(pos.x - u), mdy = fabsf(pos.y - v);
@@ -364,6 +365,9 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
             if (!is_background(surfD, REV))
             {
                 const float3 hitN = xyz(hit_load0<true>(normal, PT, tx, ty));
+                // sharded frame: both texels at the hit may live on another GPU. The colour is requested together with the normal (it is
+                // only needed if the hit survives the tests below) so that a ray pays ONE trip over the link, not two in a chain.
+                if (PEER) peer_colour = hit_load0<false>(color, PT, tx, ty);
                 if (!(dot(hitN, dirWS) > 0.0f))
                 {
                     const float3 surfVS = screen_to_view(pos.x, pos.y, surfD, cam);
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(256, DFX_OCC_INTERSECT) ssr_intersect_kernel(c
         }
     }
     float3 radiance = make_float3(0.f, 0.f, 0.f);
-    if (confidence > 0.0f) radiance = xyz(hit_load0<false>(color, PT, (int)(sw * hpx), (int)(sh * hpy)));
+    if (confidence > 0.0f) radiance = PEER ? xyz(peer_colour) : xyz(hit_load0<false>(color, PT, (int)(sw * hpx), (int)(sh * hpy))); // PEER implies !PREV_FRAME: same texel
     const float3 dv = hitVS - originVS;
     st_cs(&out_rad.at(x, y), f4(radiance, confidence));
     st_cs(&out_dir.at(x, y), f4(dirWS * length(dv), pdf));
