@@ -272,6 +272,23 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms1 = float(t.item())
+    def profile(x, first: int) -> dict:
+        """CUDA events around every pass and every exchange of 8 more frames (after the timed ones): ms per frame."""
+        L = x.lib
+        L.dfx_profile_reset()
+        L.dfx_profile_enable(1)
+        for i in range(8):
+            x.execute(first + i, fr["curr_camera"], fr["prev_camera"])
+        torch.cuda.synchronize()
+        L.dfx_profile_enable(0)
+        L.dfx_profile_collect()
+        name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
+        res = {}
+        for i in range(L.dfx_profile_count()):
+            L.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls))
+            res[name.value.decode()] = round(tot.value / 8, 4)
+        return res
+
     out = {"config": f"SSR S1-S7 + PostFX prep on one {W8}x{H8} frame (BASELINE.json configs[3]), inputs resident, {K} timed frames", "ms_1gpu": round(ms1, 4),
            "Mpix_s_1gpu": round(W8 * H8 / 1e6 / (ms1 / 1e3), 1)}
     if world > 1:
@@ -283,30 +300,18 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         msn = float(t.item())
         same = bool(np.array_equal(x.read("out"), one.read("out", rows=(x.y0, x.y1)))) and not x.timed_out()
-        # where the time goes, per rank: CUDA events around every pass and every exchange of 8 more frames (after the timed ones)
-        L = x.lib
-        L.dfx_profile_reset()
-        L.dfx_profile_enable(1)
-        for i in range(8):
-            x.execute(Wm + K + i, fr["curr_camera"], fr["prev_camera"])
-        torch.cuda.synchronize()
-        L.dfx_profile_enable(0)
-        L.dfx_profile_collect()
-        name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
-        mine = {}
-        for i in range(L.dfx_profile_count()):
-            L.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls))
-            mine[name.value.decode()] = round(tot.value / 8, 4)
+        mine = profile(x, Wm + K)     # where the time goes, per rank (after the comparison: both executors have run the same frames until here)
+        one_passes = profile(one, Wm + K)
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
         ok = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         out.update({"n_gpus": world, "ms": round(msn, 4), "Mpix_s": round(W8 * H8 / 1e6 / (msn / 1e3), 1), "speedup": round(ms1 / msn, 3),
                     "efficiency": round(ms1 / msn / world, 3), "strips_bit_identical": bool(ok.item()), "bounds": bounds, "scaling": "strong",
-                    "per_rank_pass_ms": per_rank,
+                    "per_rank_pass_ms": per_rank, "one_gpu_pass_ms": one_passes,
                     "exchange": "halo rows (64/4 depth, 4 normal + material, 1 motion; 4 ray planes; 1 resolved radiance; 2 radiance history) pushed into the neighbours' "
-                                "slabs by a copy kernel + flags in peer memory; Hi-Z / colour / normal at ray hits and last frame's history loaded from the owning GPU "
-                                "over NVLink; two all-rank flag barriers per frame; no NCCL call per frame"})
+                                "slabs by a copy kernel + flags in peer memory; the Hi-Z pyramid all-gathered by peer stores before the march; colour / normal at ray hits and "
+                                "last frame's history loaded from the owning GPU over NVLink; two all-rank flag barriers per frame; no NCCL call per frame"})
         x.close()
     one.close()
     return out
