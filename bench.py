@@ -244,7 +244,7 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
     import torch.distributed as dist
 
     from diligentfx_b200 import synth
-    from diligentfx_b200.strips import SsrStrips, reflective_block_cost, strip_bounds
+    from diligentfx_b200.strips import SsrStrips, rebalance_bounds, reflective_block_cost, strip_bounds
     W8, H8, K, Wm = args.strips_width, args.strips_height, args.strips_steps, 3
     fr = synth.generate_sequence(W8, H8, 2, seed=11)[1]            # the same frame on every rank (second of a sequence: motion, previous camera)
     # cost-balanced strips: rays are only marched for reflective pixels, which a frame concentrates where its glossy surfaces are
@@ -292,7 +292,21 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
     out = {"config": f"SSR S1-S7 + PostFX prep on one {W8}x{H8} frame (BASELINE.json configs[3]), inputs resident, {K} timed frames", "ms_1gpu": round(ms1, 4),
            "Mpix_s_1gpu": round(W8 * H8 / 1e6 / (ms1 / 1e3), 1)}
     if world > 1:
-        x = SsrStrips.distributed(W8, H8, bounds, device=dev)
+        # strips balanced by measurement: two rounds of (8 profiled frames -> per-rank compute time -> new cuts)
+        sync_passes = ("strips_halo_exchange", "strips_barrier_before_march", "strips_barrier_frame_end")
+        slab, history = None, []
+        for _ in range(args.strips_balance_rounds):
+            x = SsrStrips.distributed(W8, H8, bounds, device=dev, slab=slab)
+            x.write_inputs(fr)
+            dist.barrier()
+            run(x, 3, 3)
+            p = profile(x, 3)
+            mine_ms = [None] * world
+            dist.all_gather_object(mine_ms, sum(v for k, v in p.items() if k not in sync_passes))
+            history.append({"bounds": bounds, "compute_ms": [round(v, 3) for v in mine_ms]})
+            bounds = rebalance_bounds(bounds, mine_ms, H8)
+            slab = x.close(keep_slab=True)
+        x = SsrStrips.distributed(W8, H8, bounds, device=dev, slab=slab)
         x.write_inputs(fr)
         dist.barrier()
         msn = run(x, Wm + K, Wm)
@@ -308,7 +322,7 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         out.update({"n_gpus": world, "ms": round(msn, 4), "Mpix_s": round(W8 * H8 / 1e6 / (msn / 1e3), 1), "speedup": round(ms1 / msn, 3),
                     "efficiency": round(ms1 / msn / world, 3), "strips_bit_identical": bool(ok.item()), "bounds": bounds, "scaling": "strong",
-                    "per_rank_pass_ms": per_rank, "one_gpu_pass_ms": one_passes,
+                    "per_rank_pass_ms": per_rank, "one_gpu_pass_ms": one_passes, "balancing": history,
                     "exchange": "halo rows (64/4 depth, 4 normal + material, 1 motion; 4 ray planes; 1 resolved radiance; 2 radiance history) pushed into the neighbours' "
                                 "slabs by a copy kernel + flags in peer memory; the Hi-Z pyramid all-gathered by peer stores before the march; colour / normal at ray hits and "
                                 "last frame's history loaded from the owning GPU over NVLink; two all-rank flag barriers per frame; no NCCL call per frame"})
@@ -420,6 +434,7 @@ def main() -> None:
     ap.add_argument("--strips-only", action="store_true", help="only the row-strip leg (development: not the contract line)")
     ap.add_argument("--strips-n1", action="store_true", help="run the (unsharded) strips executor at N = 1 too")
     ap.add_argument("--strips-march-cost", type=float, default=13.0, help="cost of a reflective pixel relative to a plain one when the strips are balanced")
+    ap.add_argument("--strips-balance-rounds", type=int, default=2, help="rounds of measured re-balancing of the strip boundaries before the timed run")
     ap.add_argument("--strips-width", type=int, default=7680)
     ap.add_argument("--strips-height", type=int, default=4320)
     ap.add_argument("--strips-steps", type=int, default=20)

@@ -80,6 +80,23 @@ def reflective_block_cost(reflective_fraction_per_row, height: int, align: int =
     return [float(cost[b * align:min((b + 1) * align, height)].sum()) for b in range(blocks)]
 
 
+def rebalance_bounds(bounds: list[tuple[int, int]], rank_ms: list[float], height: int, align: int = STRIP_ALIGN) -> list[tuple[int, int]]:
+    """New strips from MEASURED per-rank compute times of the current ones: the time of a rank is spread evenly over its rows (a
+    piecewise-constant cost density over the frame) and the cuts go where the cumulative cost crosses k / world of the total, at
+    `align`-row granularity. A static model (`reflective_block_cost`) cannot know that rays starting on the ground plane march
+    longer than rays starting on an object; two rounds of this feedback bring the ranks within a block of each other."""
+    dens = [ms / max(b - a, 1) for ms, (a, b) in zip(rank_ms, bounds)]
+    blocks = -(-height // align)
+    weights = []
+    for k in range(blocks):
+        y0, y1 = k * align, min((k + 1) * align, height)
+        w = 0.0
+        for d, (a, b) in zip(dens, bounds):
+            w += d * max(0, min(b, y1) - max(a, y0))
+        weights.append(w)
+    return strip_bounds(height, len(bounds), align, weights)
+
+
 def exchange_halo(planes: list[torch.Tensor], bounds: list[tuple[int, int]], halo: int, group=None) -> None:
     """In place: after the call rows [y0 - halo, y0) and [y1, y1 + halo) of every plane hold the neighbours' owned rows.
 
@@ -277,8 +294,11 @@ class SsrStrips:
         return ranks
 
     @classmethod
-    def distributed(cls, width: int, height: int, bounds, group=None, device=None) -> "SsrStrips":
-        slab = PeerSlab({"slab": ((cls.slab_bytes(width, height),), torch.uint8)}, group, device)
+    def distributed(cls, width: int, height: int, bounds, group=None, device=None, slab: "PeerSlab | None" = None) -> "SsrStrips":
+        """`slab`: reuse the CUDA-IPC slab of an executor that was closed with `close(keep_slab=True)` (new strips, same memory)."""
+        if dist.get_world_size(group) > 1:
+            dist.barrier(group)  # nobody is still pushing into a slab that is about to be zeroed
+        slab = slab or PeerSlab({"slab": ((cls.slab_bytes(width, height),), torch.uint8)}, group, device)
         x = cls(width, height, bounds, dist.get_rank(group), list(slab.base), device)
         x._keep = slab
         x.stream = torch.cuda.current_stream(x.dev)
@@ -287,14 +307,18 @@ class SsrStrips:
             dist.barrier(group)  # every rank has zeroed its slab before anybody pushes into it
         return x
 
-    def close(self):
+    def close(self, keep_slab: bool = False):
+        """Collective when the slab is a CUDA-IPC one. `keep_slab=True` returns it instead of freeing it (see `distributed(slab=...)`)."""
         if self.handle:
             torch.cuda.synchronize(self.dev)
             self.lib.dfx_ssr_strips_destroy(self.handle)
             self.handle = None
-        if isinstance(self._keep, PeerSlab):
-            self._keep.close()
+        kept = self._keep
         self._keep = None
+        if isinstance(kept, PeerSlab) and not keep_slab:
+            kept.close()
+            kept = None
+        return kept
 
     # ---- planes -------------------------------------------------------------------------------------------------------------------
     def plane(self, name_or_id) -> "object":

@@ -93,3 +93,19 @@ def _worker(rank: int, world: int, port: int, h: int, w: int):
 @pytest.mark.parametrize("world,h", [(2, 256), (3, 448), (2, 187)])
 def test_exchange_over_gloo(world, h):
     mp.spawn(_worker, args=(world, _free_port(), h, 7), nprocs=world, join=True)
+
+
+def test_rebalance_bounds_from_measured_times():
+    """Measured feedback: the cuts move towards the rank that took longer, stay 64-row aligned, cover the frame, and a balanced
+    measurement is a fixed point."""
+    from diligentfx_b200.strips import rebalance_bounds
+    b = [(0, 2624), (2624, 4320)]
+    nb = rebalance_bounds(b, [3.08, 3.39], 4320)
+    assert nb[0][0] == 0 and nb[-1][1] == 4320 and nb[0][1] == nb[1][0] and nb[0][1] % 64 == 0
+    assert nb[0][1] > 2624                      # rank 1 was slower: it gives rows away
+    assert rebalance_bounds(b, [3.2, 3.2 * 1696 / 2624 * 2624 / 1696], 4320)[0][1] in (2624, 2560, 2688)
+    even = [(0, 1088), (1088, 2176), (2176, 3264), (3264, 4320)]
+    assert rebalance_bounds(even, [1.0, 1.0, 1.0, 1.0 * 1056 / 1088], 4320) == even
+    # an empty strip contributes nothing and may get rows back
+    out = rebalance_bounds([(0, 64), (64, 64), (64, 432)], [1.0, 0.0, 5.0], 432)
+    assert out[0][0] == 0 and out[-1][1] == 432 and all(a % 64 == 0 for a, _ in out)
