@@ -299,7 +299,8 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
             x = SsrStrips.distributed(W8, H8, bounds, device=dev, slab=slab)
             x.write_inputs(fr)
             dist.barrier()
-            run(x, 3, 3)
+            for i in range(3):
+                x.execute(i, fr["curr_camera"], fr["prev_camera"])
             p = profile(x, 3)
             mine_ms = [None] * world
             dist.all_gather_object(mine_ms, sum(v for k, v in p.items() if k not in sync_passes))
