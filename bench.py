@@ -293,7 +293,7 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
            "Mpix_s_1gpu": round(W8 * H8 / 1e6 / (ms1 / 1e3), 1)}
     if world > 1:
         # strips balanced by measurement: two rounds of (8 profiled frames -> per-rank compute time -> new cuts)
-        sync_passes = ("strips_halo_exchange", "strips_barrier_before_march", "strips_barrier_frame_end")
+        sync_passes = ("strips_halo_wait", "strips_barrier_before_march", "strips_barrier_frame_end")
         slab, history = None, []
         for _ in range(args.strips_balance_rounds):
             x = SsrStrips.distributed(W8, H8, bounds, device=dev, slab=slab)

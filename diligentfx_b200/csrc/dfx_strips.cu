@@ -287,10 +287,14 @@ struct PushSpec
 {
     int id, up_rows, down_rows; // rows of the strip's top pushed to the upper neighbour / of its bottom pushed to the lower one
 };
-dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const PushSpec* specs, int n)
+bool has_neighbours(const dfx_ssr_strips* s) { return s->world > 1 && (s->up >= 0 || s->down >= 0) && s->rows.y1 > s->rows.y0; }
+unsigned flag_value(const dfx_ssr_strips* s, int slot) { return s->seq * kFlagSlots + unsigned(slot); }
+
+// my halo rows -> the neighbours' slabs, then their flags
+dfx_status push_halos(dfx_ssr_strips* s, cudaStream_t st, int slot, const PushSpec* specs, int n)
 {
-    if (s->world == 1 || (s->up < 0 && s->down < 0) || s->rows.y1 <= s->rows.y0) return DFX_OK;
-    DFX_PROFILE(st, "strips_halo_exchange"); // push + the wait for the neighbours' pushes (i.e. including their lateness)
+    if (!has_neighbours(s)) return DFX_OK;
+    DFX_PROFILE(st, "strips_halo_push");
     PushArgs a{};
     const int strip = s->rows.y1 - s->rows.y0;
     for (int i = 0; i < n; ++i)
@@ -309,14 +313,45 @@ dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const Pus
             a.seg[a.nseg++] = PushSeg{b + size_t(s->rows.y1 - rows) * p.pitch_bytes, s->remote(const_cast<char*>(b), s->down) - b, (long long)p.pitch_bytes, rows, chunks};
         }
     }
-    a.value     = s->seq * kFlagSlots + unsigned(slot);
+    a.value     = flag_value(s, slot);
     a.flag_up   = s->up >= 0 ? &s->remote(s->sync, s->up)->from_down[slot] : nullptr;     // I am my upper neighbour's lower neighbour
     a.flag_down = s->down >= 0 ? &s->remote(s->sync, s->down)->from_up[slot] : nullptr;
     a.tickets   = &s->sync->push_tickets[slot];
     halo_push_kernel<<<32, 256, 0, st>>>(a);
     DFX_LAUNCHED("halo_push_kernel");
-    flag_wait_kernel<<<1, 1, 0, st>>>(s->up >= 0 ? &s->sync->from_up[slot] : nullptr, s->down >= 0 ? &s->sync->from_down[slot] : nullptr, a.value, &s->sync->error);
+    return DFX_OK;
+}
+// the neighbours' halo rows of exchange `slot` have arrived in my slab (the wait includes their lateness)
+dfx_status wait_halos(dfx_ssr_strips* s, cudaStream_t st, int slot)
+{
+    if (!has_neighbours(s)) return DFX_OK;
+    DFX_PROFILE(st, "strips_halo_wait");
+    flag_wait_kernel<<<1, 1, 0, st>>>(s->up >= 0 ? &s->sync->from_up[slot] : nullptr, s->down >= 0 ? &s->sync->from_down[slot] : nullptr, flag_value(s, slot), &s->sync->error);
     DFX_LAUNCHED("flag_wait_kernel");
+    return DFX_OK;
+}
+dfx_status push_and_wait(dfx_ssr_strips* s, cudaStream_t st, int slot, const PushSpec* specs, int n)
+{
+    dfx_status rc = push_halos(s, st, slot, specs, n);
+    return rc != DFX_OK ? rc : wait_halos(s, st, slot);
+}
+// A pass whose taps reach `halo` rows beyond the strip, issued so that the neighbours' lateness hides behind useful work: the interior
+// rows (which read nothing of the neighbours') first, then the wait for exchange `slot`, then the `halo` rows next to each neighbour.
+template <class F>
+dfx_status run_with_halo(dfx_ssr_strips* s, cudaStream_t st, int slot, int halo, F&& pass)
+{
+    const dfx_rows R = s->rows;
+    dfx_status     rc;
+    if (!has_neighbours(s) || R.y1 - R.y0 <= 2 * halo) // nothing to hide behind
+    {
+        if ((rc = wait_halos(s, st, slot)) != DFX_OK) return rc;
+        return pass(R);
+    }
+    const int a = s->up >= 0 ? R.y0 + halo : R.y0, b = s->down >= 0 ? R.y1 - halo : R.y1;
+    if ((rc = pass(dfx_rows{a, b})) != DFX_OK) return rc;
+    if ((rc = wait_halos(s, st, slot)) != DFX_OK) return rc;
+    if (a > R.y0 && (rc = pass(dfx_rows{R.y0, a})) != DFX_OK) return rc;
+    if (b < R.y1 && (rc = pass(dfx_rows{b, R.y1})) != DFX_OK) return rc;
     return DFX_OK;
 }
 // The whole Hi-Z pyramid (depth = level 0 included) of this rank's strip, copied into EVERY peer's slab (an all-gather by peer stores;
@@ -418,32 +453,37 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
 
     // S5: 8-tap disk of radius <= 4 px over the ray planes
     const PushSpec e1[] = {{DFX_SSR_STRIPS_PLANE_RADIANCE, 4, 4}, {DFX_SSR_STRIPS_PLANE_RAYDIR, 4, 4}};
-    if ((rc = push_and_wait(s, st, 1, e1, 2)) != DFX_OK) return rc;
-    if ((rc = dfx_pass_ssr_spatial(st, s->cams_dev, attribs, P(DFX_SSR_STRIPS_PLANE_ROUGHNESS), P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_NORMAL), P(DFX_SSR_STRIPS_PLANE_DEPTH),
-                                   P(DFX_SSR_STRIPS_PLANE_RAYDIR), P(DFX_SSR_STRIPS_PLANE_RADIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE),
-                                   P(DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH), R)) != DFX_OK)
+    if ((rc = push_halos(s, st, 1, e1, 2)) != DFX_OK) return rc;
+    if ((rc = run_with_halo(s, st, 1, 4, [&](dfx_rows rows) {
+             return dfx_pass_ssr_spatial(st, s->cams_dev, attribs, P(DFX_SSR_STRIPS_PLANE_ROUGHNESS), P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_NORMAL), P(DFX_SSR_STRIPS_PLANE_DEPTH),
+                                         P(DFX_SSR_STRIPS_PLANE_RAYDIR), P(DFX_SSR_STRIPS_PLANE_RADIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE),
+                                         P(DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH), rows);
+         })) != DFX_OK)
         return rc;
 
     // S6: 3x3 statistics of the resolved radiance (halo +-1); last frame's planes through peer loads
     const PushSpec e2[] = {{DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE, 1, 1}};
-    if ((rc = push_and_wait(s, st, 2, e2, 1)) != DFX_OK) return rc;
+    if ((rc = push_halos(s, st, 2, e2, 1)) != DFX_OK) return rc;
     const int rh_prv = prv ? DFX_SSR_STRIPS_PLANE_RADIANCE_HISTORY1 : DFX_SSR_STRIPS_PLANE_RADIANCE_HISTORY0, rh_cur = cur ? DFX_SSR_STRIPS_PLANE_RADIANCE_HISTORY1 : DFX_SSR_STRIPS_PLANE_RADIANCE_HISTORY0;
     const int vh_prv = prv ? DFX_SSR_STRIPS_PLANE_VARIANCE_HISTORY1 : DFX_SSR_STRIPS_PLANE_VARIANCE_HISTORY0, vh_cur = cur ? DFX_SSR_STRIPS_PLANE_VARIANCE_HISTORY1 : DFX_SSR_STRIPS_PLANE_VARIANCE_HISTORY0;
-    if (s->world > 1)
-        rc = dfx_pass_ssr_temporal_peer(st, s->cams_dev, attribs, &s->peers, P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_MOTION), P(DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH),
-                                        P(DFX_SSR_STRIPS_PLANE_REPROJECTED_DEPTH), P(DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE),
-                                        P(DFX_SSR_STRIPS_PLANE_PREVIOUS_DEPTH), P(rh_prv), P(vh_prv), P(rh_cur), P(vh_cur), R);
-    else
-        rc = dfx_pass_ssr_temporal(st, s->cams_dev, attribs, P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_MOTION), P(DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH),
-                                   P(DFX_SSR_STRIPS_PLANE_REPROJECTED_DEPTH), P(DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE),
-                                   P(DFX_SSR_STRIPS_PLANE_PREVIOUS_DEPTH), P(rh_prv), P(vh_prv), P(rh_cur), P(vh_cur), R);
-    if (rc != DFX_OK) return rc;
+    if ((rc = run_with_halo(s, st, 2, 1, [&](dfx_rows rows) {
+             if (s->world > 1)
+                 return dfx_pass_ssr_temporal_peer(st, s->cams_dev, attribs, &s->peers, P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_MOTION), P(DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH),
+                                                   P(DFX_SSR_STRIPS_PLANE_REPROJECTED_DEPTH), P(DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE),
+                                                   P(DFX_SSR_STRIPS_PLANE_PREVIOUS_DEPTH), P(rh_prv), P(vh_prv), P(rh_cur), P(vh_cur), rows);
+             return dfx_pass_ssr_temporal(st, s->cams_dev, attribs, P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_MOTION), P(DFX_SSR_STRIPS_PLANE_RESOLVED_DEPTH),
+                                          P(DFX_SSR_STRIPS_PLANE_REPROJECTED_DEPTH), P(DFX_SSR_STRIPS_PLANE_RESOLVED_RADIANCE), P(DFX_SSR_STRIPS_PLANE_RESOLVED_VARIANCE),
+                                          P(DFX_SSR_STRIPS_PLANE_PREVIOUS_DEPTH), P(rh_prv), P(vh_prv), P(rh_cur), P(vh_cur), rows);
+         })) != DFX_OK)
+        return rc;
 
     // S7: (2r+1)^2 window, r <= 2, over this frame's radiance history
     const PushSpec e3[] = {{rh_cur, 2, 2}};
-    if ((rc = push_and_wait(s, st, 3, e3, 1)) != DFX_OK) return rc;
-    if ((rc = dfx_pass_ssr_bilateral(st, s->cams_dev, attribs, P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_DEPTH), P(DFX_SSR_STRIPS_PLANE_NORMAL), P(DFX_SSR_STRIPS_PLANE_ROUGHNESS),
-                                     P(rh_cur), P(vh_cur), P(DFX_SSR_STRIPS_PLANE_OUTPUT), R)) != DFX_OK)
+    if ((rc = push_halos(s, st, 3, e3, 1)) != DFX_OK) return rc;
+    if ((rc = run_with_halo(s, st, 3, 2, [&](dfx_rows rows) {
+             return dfx_pass_ssr_bilateral(st, s->cams_dev, attribs, P(DFX_SSR_STRIPS_PLANE_MASK), P(DFX_SSR_STRIPS_PLANE_DEPTH), P(DFX_SSR_STRIPS_PLANE_NORMAL), P(DFX_SSR_STRIPS_PLANE_ROUGHNESS),
+                                           P(rh_cur), P(vh_cur), P(DFX_SSR_STRIPS_PLANE_OUTPUT), rows);
+         })) != DFX_OK)
         return rc;
     // nobody overwrites an input, a Hi-Z level or a history slot that a peer may still be loading from
     return all_rank_barrier(s, st, 1);
