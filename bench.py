@@ -303,7 +303,9 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
                 x.execute(i, fr["curr_camera"], fr["prev_camera"])
             p = profile(x, 3)
             mine_ms = [None] * world
-            dist.all_gather_object(mine_ms, sum(v for k, v in p.items() if k not in sync_passes))
+            # what is balanced is the work AFTER the all-rank barrier (ray march .. bilateral cleanup): everything before it is levelled
+            # by the barrier itself, so a rank with fewer rows gains nothing from finishing its part of it early
+            dist.all_gather_object(mine_ms, sum(v for k, v in p.items() if k in ("ssr_intersect_peer", "ssr_spatial", "ssr_temporal_peer", "ssr_bilateral", "strips_halo_push")))
             history.append({"bounds": bounds, "compute_ms": [round(v, 3) for v in mine_ms]})
             bounds = rebalance_bounds(bounds, mine_ms, H8)
             slab = x.close(keep_slab=True)
