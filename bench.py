@@ -437,7 +437,7 @@ def main() -> None:
     ap.add_argument("--strips-only", action="store_true", help="only the row-strip leg (development: not the contract line)")
     ap.add_argument("--strips-n1", action="store_true", help="run the (unsharded) strips executor at N = 1 too")
     ap.add_argument("--strips-march-cost", type=float, default=13.0, help="cost of a reflective pixel relative to a plain one when the strips are balanced")
-    ap.add_argument("--strips-balance-rounds", type=int, default=2, help="rounds of measured re-balancing of the strip boundaries before the timed run")
+    ap.add_argument("--strips-balance-rounds", type=int, default=3, help="rounds of measured re-balancing of the strip boundaries before the timed run")
     ap.add_argument("--strips-width", type=int, default=7680)
     ap.add_argument("--strips-height", type=int, default=4320)
     ap.add_argument("--strips-steps", type=int, default=20)

@@ -149,6 +149,8 @@ struct dfx_ssr_strips
     SyncBlock*   sync = nullptr;
     unsigned     seq = 0;
     dfx_peer_set peer_set{};
+    cudaStream_t side = nullptr;                 // the depth plane's all-gather runs beside the pre-march passes
+    cudaEvent_t  ev_begin = nullptr, ev_side = nullptr;
 
     template <class T> T* remote(T* local_ptr, int r) const
     {
@@ -156,6 +158,9 @@ struct dfx_ssr_strips
     }
     ~dfx_ssr_strips()
     {
+        if (side) cudaStreamDestroy(side);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_side) cudaEventDestroy(ev_side);
         cudaFree(tables_dev);
     }
 };
@@ -237,6 +242,9 @@ extern "C" dfx_status dfx_ssr_strips_create(int32_t width, int32_t height, const
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, flag_wait_kernel);
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, barrier_kernel);
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess)
     {
@@ -360,12 +368,12 @@ dfx_status run_with_halo(dfx_ssr_strips* s, cudaStream_t st, int slot, int halo,
 // pays the link's latency (measured on 2 GPUs: 1.006x with all levels remote, 1.41x with only level 0 remote - the bottom strip's march
 // alone then took longer than the unsharded frame's). 5.33 B/px replicated once per frame; the colour and the normal at the hit (two
 // independent loads per ray, after the loop) stay peer loads.
-dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int levels)
+dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int first_level, int levels)
 {
     if (s->world == 1 || s->rows.y1 <= s->rows.y0) return DFX_OK;
-    DFX_PROFILE(st, "strips_gather_hiz");
+    DFX_PROFILE(st, first_level == 0 ? "strips_gather_depth" : "strips_gather_hiz");
     PushArgs a{};
-    for (int m = 0; m < levels; ++m)
+    for (int m = first_level; m < levels; ++m)
     {
         const dfx_plane& p  = m == 0 ? s->plane[DFX_SSR_STRIPS_PLANE_DEPTH] : s->plane[DFX_SSR_STRIPS_PLANE_HIZ1 + m - 1];
         const int        r0 = s->rows.y0 >> m, r1 = s->rows.y1 >= s->h ? p.height : (s->rows.y1 >> m);
@@ -375,7 +383,7 @@ dfx_status gather_hiz_levels(dfx_ssr_strips* s, cudaStream_t st, int levels)
         for (int r = 0; r < s->world; ++r)
             if (r != s->rank && a.nseg < kMaxPushSegs) a.seg[a.nseg++] = PushSeg{b + size_t(r0) * p.pitch_bytes, s->remote(const_cast<char*>(b), r) - b, (long long)p.pitch_bytes, r1 - r0, chunks};
     }
-    a.tickets = &s->sync->push_tickets[kFlagSlots - 1];
+    a.tickets = &s->sync->push_tickets[kFlagSlots - 1 - (first_level == 0 ? 1 : 0)]; // the two gathers may be in flight together
     a.value   = 0; // no flags: the all-rank barrier orders it
     halo_push_kernel<<<148, 256, 0, st>>>(a);
     DFX_LAUNCHED("halo_push_kernel (Hi-Z all-gather)");
@@ -416,6 +424,15 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
     // level has an odd height: SSR_ComputeHierarchicalDepthBuffer.fx:52-70 reads row 2y+2), 4 rows from above and 4 more uses below
     // (S5 / S7 taps, S7's quad partner, the 3x3 closest-depth search). Normal, material: +-4 (S5 / S7 taps; S2 is evaluated on the
     // halo rows too instead of exchanging its outputs). Motion: +-1 (closest motion).
+    // The depth plane (level 0 of the Hi-Z pyramid, 3/4 of its bytes) is an INPUT: its all-gather starts now, on a second stream, and
+    // runs beside the exchange of the input halos and the pre-march passes; the march waits for it through the barrier below.
+    if (s->world > 1)
+    {
+        DFX_CUDA(cudaEventRecord(s->ev_begin, st));
+        DFX_CUDA(cudaStreamWaitEvent(s->side, s->ev_begin, 0));
+        if ((rc = gather_hiz_levels(s, s->side, 0, 1)) != DFX_OK) return rc;
+        DFX_CUDA(cudaEventRecord(s->ev_side, s->side));
+    }
     const PushSpec e0[] = {{DFX_SSR_STRIPS_PLANE_DEPTH, 64, 4}, {DFX_SSR_STRIPS_PLANE_NORMAL, 4, 4}, {DFX_SSR_STRIPS_PLANE_MATERIAL, 4, 4}, {DFX_SSR_STRIPS_PLANE_MOTION, 1, 1}};
     if ((rc = push_and_wait(s, st, 0, e0, 4)) != DFX_OK) return rc;
 
@@ -441,7 +458,8 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
 
     // S4 marches on a complete local copy of the Hi-Z pyramid and loads the colour / normal at the hit from whichever rank owns the
     // row, S6 last frame's history: after the barrier everybody's are complete
-    if ((rc = gather_hiz_levels(s, st, hz.levels)) != DFX_OK) return rc;
+    if ((rc = gather_hiz_levels(s, st, 1, hz.levels)) != DFX_OK) return rc;
+    if (s->world > 1) DFX_CUDA(cudaStreamWaitEvent(st, s->ev_side, 0));
     if ((rc = all_rank_barrier(s, st, 0)) != DFX_OK) return rc;
     if (s->world > 1)
         rc = dfx_pass_ssr_intersect_peer(st, s->cams_dev, attribs, 0, &s->peer_set, P(DFX_SSR_STRIPS_PLANE_COLOR), P(DFX_SSR_STRIPS_PLANE_NORMAL), P(DFX_SSR_STRIPS_PLANE_ROUGHNESS),
