@@ -77,11 +77,24 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const __grid_constant__ 
     {
         const PushSeg& g = a.seg[s];
         const int      n = g.rows * g.row_chunks;
-        for (int i = tid; i < n; i += nth)
+        for (int i0 = tid; i0 < n; i0 += 4 * nth) // four 16-byte chunks in flight per thread: the link's latency is long
         {
-            const int   r = i / g.row_chunks, c = i - r * g.row_chunks;
-            const char* p = g.src + r * g.pitch + (long long)c * 16;
-            *reinterpret_cast<float4*>(const_cast<char*>(p) + g.delta) = __ldg(reinterpret_cast<const float4*>(p));
+            float4      v[4];
+            const char* p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const int i = i0 + k * nth;
+                if (i < n)
+                {
+                    const int r = i / g.row_chunks, c = i - r * g.row_chunks;
+                    p[k]        = g.src + r * g.pitch + (long long)c * 16;
+                    v[k]        = __ldg(reinterpret_cast<const float4*>(p[k]));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k * nth < n) *reinterpret_cast<float4*>(const_cast<char*>(p[k]) + g.delta) = v[k];
         }
     }
     __threadfence_system(); // this thread's stores are visible system-wide before the ticket below
@@ -430,7 +443,18 @@ extern "C" dfx_status dfx_ssr_strips_execute(dfx_ssr_strips* s, void* stream, ui
     {
         DFX_CUDA(cudaEventRecord(s->ev_begin, st));
         DFX_CUDA(cudaStreamWaitEvent(s->side, s->ev_begin, 0));
-        if ((rc = gather_hiz_levels(s, s->side, 0, 1)) != DFX_OK) return rc;
+        {
+            // one contiguous block of rows per peer, moved by the copy engines (no SM is spent on the 3/4 of the pyramid's bytes)
+            DFX_PROFILE(s->side, "strips_gather_depth");
+            const dfx_plane& d = s->plane[DFX_SSR_STRIPS_PLANE_DEPTH];
+            char*            b = static_cast<char*>(d.ptr) + size_t(R.y0) * d.pitch_bytes;
+            const size_t     n = size_t(R.y1 - R.y0) * d.pitch_bytes;
+            for (int k = 1; k < s->world && n > 0; ++k)
+            {
+                const int r = (s->rank + k) % s->world; // every rank starts with a different peer: no link is hit by all at once
+                DFX_CUDA(cudaMemcpyAsync(s->remote(b, r), b, n, cudaMemcpyDefault, s->side));
+            }
+        }
         DFX_CUDA(cudaEventRecord(s->ev_side, s->side));
     }
     const PushSpec e0[] = {{DFX_SSR_STRIPS_PLANE_DEPTH, 64, 4}, {DFX_SSR_STRIPS_PLANE_NORMAL, 4, 4}, {DFX_SSR_STRIPS_PLANE_MATERIAL, 4, 4}, {DFX_SSR_STRIPS_PLANE_MOTION, 1, 1}};
