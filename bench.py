@@ -305,7 +305,12 @@ def strips_leg(args, rank: int, world: int, dev) -> dict:
             mine_ms = [None] * world
             # what is balanced is the work AFTER the all-rank barrier (ray march .. bilateral cleanup): everything before it is levelled
             # by the barrier itself, so a rank with fewer rows gains nothing from finishing its part of it early
-            dist.all_gather_object(mine_ms, sum(v for k, v in p.items() if k in ("ssr_intersect_peer", "ssr_spatial", "ssr_temporal_peer", "ssr_bilateral", "strips_halo_push")))
+            # With many ranks the work BEFORE the barrier matters as well: it grows with a strip's rows (the top strip of this frame
+            # is three times as tall as the others when only the post-barrier work is balanced, and everybody then waits for its PostFX /
+            # Hi-Z / mask passes at the barrier: measured at N = 8), so from 4 ranks on the pre-march kernels count too.
+            post = ("ssr_intersect_peer", "ssr_spatial", "ssr_temporal_peer", "ssr_bilateral", "strips_halo_push")
+            pre = ("postfx_prepare", "ssr_hiz", "ssr_mask_roughness", "strips_gather_hiz") if world >= 4 else ()
+            dist.all_gather_object(mine_ms, sum(v for k, v in p.items() if k in post + pre))
             history.append({"bounds": bounds, "compute_ms": [round(v, 3) for v in mine_ms]})
             bounds = rebalance_bounds(bounds, mine_ms, H8)
             slab = x.close(keep_slab=True)
