@@ -97,9 +97,10 @@ def measured_hbm_peak() -> tuple[float, str]:
 
 
 def ncu_traffic(pass_name: str, width: int, height: int):
-    """DRAM bytes per launch of the pass's kernel from the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json),
+    """DRAM bytes per launch of the pass's kernel from the committed `ncu --set full` capture (profiles/r2d_ncu_traffic.json, made
+    by tools/ncu_traffic_json.py from the raw page of the round-2 capture; G-buffer in the renderer formats),
     or None when the capture has no entry for it or was taken at another frame size (3840x2160)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2d_ncu_traffic.json")
     try:
         d = json.load(open(path))
         k = d["kernels"][d["pass_to_kernel"][pass_name]]
@@ -107,7 +108,7 @@ def ncu_traffic(pass_name: str, width: int, height: int):
         return None, "no ncu capture for this kernel"
     if (width, height) != (3840, 2160):
         return None, "ncu capture is for 3840x2160"
-    return int(k["dram_bytes"]), "profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    return int(k["dram_bytes"]), "profiles/r2d_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 
 
 def pin_to_gpu_numa_node(gpu_index: int) -> dict:
@@ -641,7 +642,7 @@ def main() -> None:
                 ms = live[p["pass"]]
                 p["live"] = {"ms": round(ms, 4), "frac": round(p["alg_bytes"] / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 else 0.0}
         top = max(passes, key=lambda p: p["ms"])
-        traffic, traffic_src = ncu_traffic(top["pass"], W, H)
+        traffic, traffic_src = ncu_traffic(top["pass"], W, H) if native else (None, "ncu capture is for the renderer-format G-buffer")
         roof = {"bound": "hbm", "kernel": top["pass"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
                 "traffic_source": traffic_src, "alg_bytes": top["alg_bytes"], "peak_source": peak_src, "share_of_step": top["share"],
                 "chain": {"alg_bytes_per_px": round(sum(p["alg_bytes"] for p in passes) / (W * H), 2),

@@ -320,22 +320,21 @@ DFX_HD PairSums pair_sums(const RowPair& p)
     return s;
 }
 
-template <bool PREFILTER>
-__global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1, int rows_per_warp)
+// One warp's share of a streaming down-sample: output columns [ox0, ox0 + kDnCols) x rows [oyb, oye). CG: loads bypass L1 (ld.global.cg), for
+// source levels written earlier in the SAME launch by other SMs (bloom_levels_kernel).
+template <bool PREFILTER, bool CG>
+__device__ __forceinline__ void down2x_stream_item(const dfx_bloom_attribs& A, const View<const float4>& in, const View<float4>& out, int ox0, int oyb, int oye, int lane)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ox0 = (blockIdx.x * kStreamWarps + warp) * kDnCols;
-    const int oyb = y0 + blockIdx.y * rows_per_warp, oye = min(oyb + rows_per_warp, y1);
-    if (ox0 >= out.w || oyb >= oye) return; // warp-uniform
     const int  ox = ox0 + lane - 1, sx = 2 * ox;
     const bool col_ok = sx >= 0 && sx < in.w; // in.w == 2 * out.w: sx + 1 is inside whenever sx is
+    auto ld = [&](const float4* q) { return CG ? __ldcg(q) : __ldg(q); };
     auto load_pair = [&](int k) {
         RowPair   p;
         const int r = 2 * k; // in.h == 2 * out.h: rows 2k and 2k + 1 are inside or outside together
         if (col_ok && r >= 0 && r < in.h)
         {
             const float4* q = in.row(r) + sx;
-            p.a0 = __ldg(q), p.a1 = __ldg(q + 1), p.b0 = __ldg(q + in.pitch), p.b1 = __ldg(q + in.pitch + 1);
+            p.a0 = ld(q), p.a1 = ld(q + 1), p.b0 = ld(q + in.pitch), p.b1 = ld(q + in.pitch + 1);
         }
         else
             p.a0 = p.a1 = p.b0 = p.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -382,6 +381,16 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(
     }
 }
 
+template <bool PREFILTER>
+__global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(dfx_bloom_attribs A, View<const float4> in, View<float4> out, int y0, int y1, int rows_per_warp)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ox0 = (blockIdx.x * kStreamWarps + warp) * kDnCols;
+    const int oyb = y0 + blockIdx.y * rows_per_warp, oye = min(oyb + rows_per_warp, y1);
+    if (ox0 >= out.w || oyb >= oye) return; // warp-uniform
+    down2x_stream_item<PREFILTER, false>(A, in, out, ox0, oyb, oye, lane);
+}
+
 // Up (B3 / B4). With out = 2 x coarser the 3x3 tent of bilinear taps (Bloom_ComputeUpsampledTexture.fx:27-43) collapses to a
 // separable 4-tap filter whose weights depend only on the parity of the output coordinate:
 //   even x = 2k : coarse texels k-2..k+1 weigh (1, 5, 7, 3)/16      odd x = 2k+1 : k-1..k+2 weigh (3, 7, 5, 1)/16
@@ -391,27 +400,25 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_down2x_stream_kernel(
 // fine-level texel (same-level down-sample for B3, the scene colour for B4) is read once, fully coalesced, and so is the store.
 
 // TM: -1 = no tone map, otherwise the tone-mapping operator (a compile-time parameter: one operator's code per instantiation, and its
-// per-frame constants - exposure scale, white-point normalisation - are hoisted out of the row loop by the compiler)
-template <bool COMPOSITE, int TM>
-__global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out,
-                                                                              int y0, int y1, int coarse_rows_per_warp, ToneMapIn tm)
+// per-frame constants - exposure scale, white-point normalisation - are hoisted out of the row loop by the compiler).
+// One warp's share: output columns [fx0, fx0 + 32) x rows [fyb, fye), fyb even; y1 = end of the caller's row range.
+template <bool COMPOSITE, int TM, bool CG>
+__device__ __forceinline__ void up2x_stream_item(const dfx_bloom_attribs& A, const View<const float4>& fine, const View<const float4>& coarser, const View<float4>& out,
+                                                 int fx0, int fyb, int fye, int y1, int lane, const ToneMapIn& tm)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int fx0 = (blockIdx.x * kStreamWarps + warp) * 32;
-    const int fyb = y0 + blockIdx.y * (2 * coarse_rows_per_warp), fye = min(fyb + 2 * coarse_rows_per_warp, y1); // y0 is even (checked by the caller)
-    if (fx0 >= out.w || fyb >= fye) return; // warp-uniform
     const int   x = fx0 + lane;
     const bool  xin = x < out.w;
     const int   ck = min(max((fx0 >> 1) - 2 + lane, 0), coarser.w - 1);
     const int   s0 = (lane >> 1) + (lane & 1);
     const bool  odd = lane & 1;
     const float w0 = odd ? 3.f / 16 : 1.f / 16, w1 = odd ? 7.f / 16 : 5.f / 16, w2 = odd ? 5.f / 16 : 7.f / 16, w3 = odd ? 1.f / 16 : 3.f / 16;
+    auto ld = [&](const float4* q) { return CG ? __ldcg(q) : __ldg(q); };
     auto load_coarse = [&](int j) { // this lane's texel of the coarse row j (clamped); lanes 20..31 hold nothing
         const int cj = min(max(j, 0), coarser.h - 1);
-        return lane < 20 ? xyz(__ldg(&coarser.at(ck, cj))) : make_float3(0.f, 0.f, 0.f);
+        return lane < 20 ? xyz(ld(&coarser.at(ck, cj))) : make_float3(0.f, 0.f, 0.f);
     };
     auto hfilter = [&](float3 c) { return shfl3(c, s0) * w0 + shfl3(c, s0 + 1) * w1 + shfl3(c, s0 + 2) * w2 + shfl3(c, s0 + 3) * w3; }; // horizontal 4-tap
-    auto load_fine = [&](int y) { return (xin && y < y1) ? __ldg(&fine.at(x, y)) : make_float4(0.f, 0.f, 0.f, 0.f); };
+    auto load_fine = [&](int y) { return (xin && y < y1) ? ld(&fine.at(x, y)) : make_float4(0.f, 0.f, 0.f, 0.f); };
     auto emit = [&](int y, float3 s, float4 f) {
         if (!xin || y >= y1) return;
         const float3 c = xyz(f); // linear sampler at the texel centre == the texel
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
             float3 o = lerp3(c, c + A.Intensity * s, A.AlphaInterpolation);
             if (TM >= 0)
             {
-                o = tone_map<TM>(o, tm.attribs, tm.ave_log_lum);
+                o = tone_map<(TM < 0 ? 0 : TM)>(o, tm.attribs, tm.ave_log_lum);
                 if (tm.to_srgb) o = linear_to_srgb(o);
             }
             st_cs(&out.at(x, y), f4(o, 0.0f));
@@ -428,24 +435,34 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
         else
             out.at(x, y) = f4(c + s, 0.0f);
     };
-    // Software pipeline: the fine texels of the next TWO steps and the coarse row of the next step are always in flight, so a step
-    // never waits for a load it has just issued (one warp keeps 4 x 512 B + 320 B outstanding).
+    // Software pipeline: the fine texels and the coarse row of the NEXT step are in flight while this step computes. (Two steps ahead
+    // was measured slower: 0.079 vs 0.064 ms for the 4K composite, profiles/r2i.)
     const int jb = fyb >> 1;
-    float4    f0 = load_fine(fyb), f1 = load_fine(fyb + 1), g0 = load_fine(fyb + 2), g1 = load_fine(fyb + 3);
+    float4    f0 = load_fine(fyb), f1 = load_fine(fyb + 1);
     float3    cnext = load_coarse(jb + 2);
     float3    H0 = hfilter(load_coarse(jb - 2)), H1 = hfilter(load_coarse(jb - 1)), H2 = hfilter(load_coarse(jb)), H3 = hfilter(load_coarse(jb + 1));
     for (int j = jb; 2 * j < fye; ++j)
     {
         const float4 c0 = f0, c1 = f1;
         const float3 ccur = cnext;
-        f0 = g0, f1 = g1;
-        g0 = load_fine(2 * j + 4), g1 = load_fine(2 * j + 5);
+        f0 = load_fine(2 * j + 2), f1 = load_fine(2 * j + 3);
         cnext = load_coarse(j + 3);
         const float3 H4 = hfilter(ccur);
         emit(2 * j, H0 * (1.f / 16) + H1 * (5.f / 16) + H2 * (7.f / 16) + H3 * (3.f / 16), c0);
         emit(2 * j + 1, H1 * (3.f / 16) + H2 * (7.f / 16) + H3 * (5.f / 16) + H4 * (1.f / 16), c1);
         H0 = H1, H1 = H2, H2 = H3, H3 = H4;
     }
+}
+
+template <bool COMPOSITE, int TM>
+__global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(dfx_bloom_attribs A, View<const float4> fine, View<const float4> coarser, View<float4> out,
+                                                                              int y0, int y1, int coarse_rows_per_warp, ToneMapIn tm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fx0 = (blockIdx.x * kStreamWarps + warp) * 32;
+    const int fyb = y0 + blockIdx.y * (2 * coarse_rows_per_warp), fye = min(fyb + 2 * coarse_rows_per_warp, y1); // y0 is even (checked by the caller)
+    if (fx0 >= out.w || fyb >= fye) return; // warp-uniform
+    up2x_stream_item<COMPOSITE, TM, false>(A, fine, coarser, out, fx0, fyb, fye, y1, lane, tm);
 }
 
 // =====================================================================================================================
@@ -620,9 +637,12 @@ static dfx_status launch_up(void* stream, int mode, const dfx_bloom_attribs& A, 
     if (exact && impl == 1)
     {
         const int bx = div_up(out.w, 32 * kStreamWarps), n = div_up(rows.y1 - rows.y0, 2); // coarse rows
+        // coarse rows per warp: dfx_tune("bloom_up_rows"), 0 = as few as fill one wave. Measured at 4K (profiles/r2i): 4 rows 0.062 ms for the
+        // composite, 8 rows 0.064, 16 rows 0.066, one wave (25 rows) 0.070 - unlike the down-sampling, short warps win here.
+        const int fixed_rows = dfx_tune_get("bloom_up_rows", 4);
 #define DFX_UP_LAUNCH(COMP, TMODE)                                                                                                                   \
     do {                                                                                                                                             \
-        const int  cpw = stream_rows_per_warp(bloom_up2x_stream_kernel<COMP, TMODE>, bx * kStreamWarps, n, 1);                                       \
+        const int  cpw = fixed_rows > 0 ? fixed_rows : stream_rows_per_warp(bloom_up2x_stream_kernel<COMP, TMODE>, bx * kStreamWarps, n, 1);         \
         const dim3 grid(bx, div_up(n, cpw));                                                                                                         \
         bloom_up2x_stream_kernel<COMP, TMODE><<<grid, 32 * kStreamWarps, 0, s>>>(A, fine, lo, out, rows.y0, rows.y1, cpw, tm);                       \
     } while (0)

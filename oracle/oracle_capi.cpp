@@ -232,6 +232,8 @@ namespace orc
 {
 float oracle_fast_acos(float v);
 extern std::atomic<unsigned long long> g_march_rays, g_march_iterations;
+extern unsigned short* g_march_iteration_plane;
+extern int             g_march_iteration_pitch;
 bool g_reversed_depth = false;
 } // namespace orc
 
@@ -497,6 +499,12 @@ ORC_API void orc_march_stats(unsigned long long* rays, unsigned long long* itera
     *rays       = orc::g_march_rays.load();
     *iterations = orc::g_march_iterations.load();
     if (reset) orc::g_march_rays = 0, orc::g_march_iterations = 0;
+}
+// per-pixel trip counts of the next intersection passes into plane[h][pitch] (zero it first; nullptr switches the record off)
+ORC_API void orc_march_iteration_plane(unsigned short* plane, int pitch)
+{
+    orc::g_march_iteration_plane = plane;
+    orc::g_march_iteration_pitch = pitch;
 }
 // kernel textures of DepthOfField (DepthOfField.cpp:49-91): points as x,y pairs; returns the count (writes at most max_count entries)
 ORC_API int orc_dof_kernel_points(int ring_count, int ring_density, float* out_xy, int max_count)

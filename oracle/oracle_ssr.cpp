@@ -107,6 +107,11 @@ void ssr_downsample_mask(const dfx_ssr_attribs& A, const TexF& roughness, const 
 // S4  SSR_ComputeIntersection.fx
 // workload statistics of the Hi-Z march (rays traced, loop iterations), for DESIGN.md / the bench report
 std::atomic<unsigned long long> g_march_rays{0}, g_march_iterations{0};
+// optional per-pixel record of the loop's trip count (0 where no ray is traced), W x H uint16: what a SIMD implementation needs to
+// know about the divergence of neighbouring rays (orc_march_iteration_plane)
+unsigned short* g_march_iteration_plane = nullptr;
+int             g_march_iteration_pitch = 0;
+static thread_local unsigned t_last_march_iterations = 0;
 
 namespace
 {
@@ -180,6 +185,7 @@ inline float3 HierarchicalRaymarch(const MipTex<float>& hiz, float3 Origin, floa
     ValidHit = (Idx <= MaxTraversalIntersections);
     g_march_rays.fetch_add(1, std::memory_order_relaxed);
     g_march_iterations.fetch_add(Idx, std::memory_order_relaxed);
+    t_last_march_iterations = Idx;
     return Position;
 }
 
@@ -259,6 +265,7 @@ void ssr_intersect(const Camera& cam, const dfx_ssr_attribs& A, uint flags, cons
 
                 bool   ValidHit = false;
                 float3 SurfaceHitSS = HierarchicalRaymarch(hiz, RayOriginSS, RayDirectionSS, ScreenSize, MostDetailedMip, A.MaxTraversalIntersections, ValidHit);
+                if (g_march_iteration_plane) g_march_iteration_plane[size_t(py) * g_march_iteration_pitch + px] = (unsigned short)std::min(t_last_march_iterations, 65535u);
                 float3 SurfaceHitVS = ScreenXYDepthToViewSpace(SurfaceHitSS, cam.mProj);
 
                 float2 HitPrev = SurfaceHitSS.xy();
