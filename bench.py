@@ -85,7 +85,8 @@ def bloom_bytes(W: int, H: int, mips: int, first: int) -> dict:
     down = sum(b[i - 1] + b[i] for i in range(1, first))
     tail = b[first - 1] + sum(b[first:mips]) + sum(b[first - 1:top]) if first < mips else 0
     up = sum(2 * b[i - 1] + b[i] for i in range(min(top, first - 1), 0, -1))       # reads down[i-1] + coarser level, writes up[i-1]
-    return {"bloom_downsample": float(down), "bloom_tail": float(tail), "bloom_upsample": float(up)}
+    levels = sum(b[i - 1] + b[i] for i in range(1, mips)) + sum(2 * b[i - 1] + b[i] for i in range(top, 0, -1))   # dfx_pass_bloom_levels: all of B2 + B3
+    return {"bloom_downsample": float(down), "bloom_tail": float(tail), "bloom_upsample": float(up), "bloom_levels": float(levels)}
 
 
 def measured_hbm_peak() -> tuple[float, str]:

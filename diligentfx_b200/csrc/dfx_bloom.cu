@@ -497,6 +497,41 @@ DFX_HD float3 tap3_cg(const View<float4>& t, float u, float v)
     return xyz(a * ((1.0f - fx) * (1.0f - fy)) + b * (fx * (1.0f - fy)) + c * ((1.0f - fx) * fy) + d * (fx * fy));
 }
 
+// B2 (generic level) and B3 (generic level) over a flat range of threads; every load is ld.global.cg
+__device__ __forceinline__ void generic_down_level(const View<float4>& in, const View<float4>& out, int tid, int nth)
+{
+    for (int idx = tid; idx < out.w * out.h; idx += nth)
+    {
+        const int   y = idx / out.w, x = idx - y * out.w;
+        const float u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
+        const float tx = 1.0f / float(in.w), ty = 1.0f / float(in.h);
+        auto        T = [&](float i_, float j_) { return tap3_cg<true>(in, u + tx * i_, v + ty * j_); };
+        const float3 tA = T(-2, +2), tB = T(0, +2), tC = T(+2, +2), tD = T(-2, 0), tE = T(0, 0), tF = T(+2, 0), tG = T(-2, -2), tH = T(0, -2), tI = T(+2, -2);
+        const float3 tJ = T(-1, +1), tK = T(+1, +1), tL = T(-1, -1), tM = T(+1, -1);
+        float3 o = make_float3(0.f, 0.f, 0.f);
+        o = o + (tA + tC + tG + tI) * 0.03125f;
+        o = o + (tB + tD + tF + tH) * 0.0625f;
+        o = o + (tE + tJ + tK + tL + tM) * 0.125f;
+        out.at(x, y) = f4(o, 0.0f);
+    }
+}
+__device__ __forceinline__ void generic_up_level(const View<float4>& same, const View<float4>& lo, const View<float4>& out, int tid, int nth)
+{
+    for (int idx = tid; idx < out.w * out.h; idx += nth)
+    {
+        const int   y = idx / out.w, x = idx - y * out.w;
+        const float u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
+        const float tx = 1.0f / float(lo.w), ty = 1.0f / float(lo.h);
+        const float3 tA = tap3_cg<false>(lo, u - tx, v + ty), tB = tap3_cg<false>(lo, u, v + ty), tC = tap3_cg<false>(lo, u + tx, v + ty);
+        const float3 tD = tap3_cg<false>(lo, u - tx, v), tE = tap3_cg<false>(lo, u, v), tF = tap3_cg<false>(lo, u + tx, v);
+        const float3 tG = tap3_cg<false>(lo, u - tx, v - ty), tH = tap3_cg<false>(lo, u, v - ty), tI = tap3_cg<false>(lo, u + tx, v - ty);
+        float3 s = tE * 0.25f;
+        s = s + (tB + tD + tF + tH) * 0.125f;
+        s = s + (tA + tC + tG + tI) * 0.0625f;
+        out.at(x, y) = f4(tap3_cg<false>(same, u, v) + s, 0.0f);
+    }
+}
+
 __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThreads) bloom_tail_kernel(TailArgs a)
 {
     namespace cg = cooperative_groups;
@@ -504,41 +539,117 @@ __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailThre
     const int tid = int(cluster.block_rank()) * kTailThreads + int(threadIdx.x), nth = kTailCluster * kTailThreads;
     for (int i = a.first; i < a.mips; ++i) // B2
     {
-        const View<float4> in = a.down[i - 1], out = a.down[i];
-        for (int idx = tid; idx < out.w * out.h; idx += nth)
-        {
-            const int   y = idx / out.w, x = idx - y * out.w;
-            const float u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
-            const float tx = 1.0f / float(in.w), ty = 1.0f / float(in.h);
-            auto        T = [&](float i_, float j_) { return tap3_cg<true>(in, u + tx * i_, v + ty * j_); };
-            const float3 tA = T(-2, +2), tB = T(0, +2), tC = T(+2, +2), tD = T(-2, 0), tE = T(0, 0), tF = T(+2, 0), tG = T(-2, -2), tH = T(0, -2), tI = T(+2, -2);
-            const float3 tJ = T(-1, +1), tK = T(+1, +1), tL = T(-1, -1), tM = T(+1, -1);
-            float3 o = make_float3(0.f, 0.f, 0.f);
-            o = o + (tA + tC + tG + tI) * 0.03125f;
-            o = o + (tB + tD + tF + tH) * 0.0625f;
-            o = o + (tE + tJ + tK + tL + tM) * 0.125f;
-            out.at(x, y) = f4(o, 0.0f);
-        }
+        generic_down_level(a.down[i - 1], a.down[i], tid, nth);
         cluster.sync();
     }
     const int top = a.mips - 1;
     for (int i = top; i >= a.first; --i) // B3: up[i-1] = down[i-1] + tent(i == top ? down[i] : up[i])
     {
-        const View<float4> same = a.down[i - 1], lo = i == top ? a.down[i] : a.up[i], out = a.up[i - 1];
-        for (int idx = tid; idx < out.w * out.h; idx += nth)
-        {
-            const int   y = idx / out.w, x = idx - y * out.w;
-            const float u = (float(x) + 0.5f) / float(out.w), v = (float(y) + 0.5f) / float(out.h);
-            const float tx = 1.0f / float(lo.w), ty = 1.0f / float(lo.h);
-            const float3 tA = tap3_cg<false>(lo, u - tx, v + ty), tB = tap3_cg<false>(lo, u, v + ty), tC = tap3_cg<false>(lo, u + tx, v + ty);
-            const float3 tD = tap3_cg<false>(lo, u - tx, v), tE = tap3_cg<false>(lo, u, v), tF = tap3_cg<false>(lo, u + tx, v);
-            const float3 tG = tap3_cg<false>(lo, u - tx, v - ty), tH = tap3_cg<false>(lo, u, v - ty), tI = tap3_cg<false>(lo, u + tx, v - ty);
-            float3 s = tE * 0.25f;
-            s = s + (tB + tD + tF + tH) * 0.125f;
-            s = s + (tA + tC + tG + tI) * 0.0625f;
-            out.at(x, y) = f4(tap3_cg<false>(same, u, v) + s, 0.0f);
-        }
+        generic_up_level(a.down[i - 1], i == top ? a.down[i] : a.up[i], a.up[i - 1], tid, nth);
         if (i > a.first) cluster.sync();
+    }
+}
+
+// =====================================================================================================================
+// Levels: EVERY level after the prefilter - down to the top of the pyramid and back up to level 0 - in ONE cooperative launch over the
+// whole GPU (dfx_pass_bloom_levels). The per-level launches of B2 / B3 are a chain of 9-11 dependent kernels of 5-15 us each on planes
+// that fit in L2: launch gaps and the 8-SM cluster of the tail were half of their time. Here a level is a phase of a persistent grid
+// (as many CTAs as are co-resident), phases are separated by a grid-wide barrier (arrive counter in global memory, release / acquire at
+// GPU scope), and a phase is either the streaming shuffle code of an exact 2:1 level (work items = warp column x row chunk, dealt
+// round-robin to the grid's warps) or the generic gather code. Planes written inside the launch are read with ld.global.cg. Per texel
+// the arithmetic is that of the per-level kernels (same taps, same order; the compiler's FMA contraction may differ in the last bit).
+// Measured at 4K (profiles/r2j): 0.104 ms against 0.118 ms for the nine per-level launches and 20 instead of 28 launches per frame,
+// but the whole frame is SLOWER under async compute (2.34 vs 2.28 ms): a cooperative grid needs every SM at once, so it cannot
+// slip into the gaps of the next frame's front half the way the small per-level launches do. Opt-in: dfx_tune("bloom_levels") = 1.
+// The launch is cooperative (all CTAs co-resident or the launch fails), so two such kernels on two streams cannot starve each other at
+// the barrier; a barrier that is not reached within ~2 s raises the error word of the workspace instead of hanging the GPU.
+// =====================================================================================================================
+constexpr int                kLevelsThreads = 256;
+constexpr unsigned long long kLevelsSpinLimit = 4000000000ull; // cycles
+struct LevelsArgs
+{
+    TailArgs  t;
+    unsigned* ws; // [0] barrier arrivals, [1] exit tickets, [2] error; all zero between launches
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* ws, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        atomicAdd(&ws[0], 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(&ws[0]) < target)
+        {
+            if (ld_acquire_gpu(&ws[2]) != 0u) break; // another CTA gave up: do not wait for it
+            if ((unsigned long long)(clock64() - t0) > kLevelsSpinLimit)
+            {
+                atomicExch(&ws[2], 1u);
+                break;
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ View<const float4> as_const(const View<float4>& v) { return View<const float4>{v.p, v.pitch, v.w, v.h}; }
+__device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__global__ void __launch_bounds__(kLevelsThreads, 3) bloom_levels_kernel(const __grid_constant__ LevelsArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * kLevelsThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kLevelsThreads) >> 5;
+    const int tid = blockIdx.x * kLevelsThreads + threadIdx.x, nth = gridDim.x * kLevelsThreads;
+    unsigned  phase = 0;
+    const dfx_bloom_attribs A{};
+    const ToneMapIn         tm{};
+    for (int i = a.t.first; i < a.t.mips; ++i) // B2
+    {
+        const View<float4>&in = a.t.down[i - 1], &out = a.t.down[i];
+        if (in.w == 2 * out.w && in.h == 2 * out.h)
+        {
+            // rows per item: as few as give every warp of the grid at most one item (at least 2: each item re-reads two source row pairs)
+            const int cols = cdiv(out.w, kDnCols), per_col = max(nwarps / cols, 1), rpw = max(cdiv(out.h, per_col), 2), chunks = cdiv(out.h, rpw);
+            for (int item = gwarp; item < cols * chunks; item += nwarps)
+            {
+                const int c = item % cols, r = item / cols;
+                down2x_stream_item<false, true>(A, as_const(in), out, c * kDnCols, r * rpw, min((r + 1) * rpw, out.h), lane);
+            }
+        }
+        else
+            generic_down_level(in, out, tid, nth);
+        grid_barrier(a.ws, ++phase * gridDim.x);
+    }
+    const int top = a.t.mips - 1;
+    for (int i = top; i >= a.t.first; --i) // B3: up[i-1] = down[i-1] + tent(i == top ? down[i] : up[i])
+    {
+        const View<float4>&same = a.t.down[i - 1], &lo = i == top ? a.t.down[i] : a.t.up[i], &out = a.t.up[i - 1];
+        if (out.w == 2 * lo.w && out.h == 2 * lo.h)
+        {
+            const int cols = cdiv(out.w, 32), per_col = max(nwarps / cols, 1), cpw = min(max(cdiv(lo.h, per_col), 1), 4), chunks = cdiv(lo.h, cpw);
+            for (int item = gwarp; item < cols * chunks; item += nwarps)
+            {
+                const int c = item % cols, r = item / cols;
+                up2x_stream_item<false, -1, true>(A, as_const(same), as_const(lo), out, c * 32, 2 * r * cpw, min(2 * (r + 1) * cpw, out.h), out.h, lane, tm);
+            }
+        }
+        else
+            generic_up_level(same, lo, out, tid, nth);
+        if (i > a.t.first) grid_barrier(a.ws, ++phase * gridDim.x);
+    }
+    // leave the workspace zeroed for the next launch: the last CTA out knows that every other CTA is past the last barrier
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&a.ws[1], 1u) == gridDim.x - 1)
+    {
+        a.ws[0] = 0u, a.ws[1] = 0u;
+        __threadfence();
     }
 }
 
@@ -731,8 +842,9 @@ extern "C" dfx_status dfx_pass_bloom_composite_tonemap(void* stream, const dfx_b
 extern "C" int32_t dfx_bloom_tail_first_level(const dfx_plane* down, int32_t mips)
 {
     if (!down || mips < 2 || dfx_tune_get("bloom_tail", 1) == 0) return mips;
+    const long long limit = dfx_tune_get("bloom_tail_texels", kTailTexels);
     for (int i = 1; i < mips; ++i)
-        if ((long long)down[i].width * down[i].height <= kTailTexels) return i;
+        if ((long long)down[i].width * down[i].height <= limit) return i;
     return mips;
 }
 
@@ -756,5 +868,56 @@ extern "C" dfx_status dfx_pass_bloom_tail(void* stream, const dfx_plane* down, c
     }
     bloom_tail_kernel<<<kTailCluster, kTailThreads, 0, as_stream(stream)>>>(a);
     DFX_LAUNCHED("bloom_tail_kernel");
+    return DFX_OK;
+}
+
+// B2 for the levels first .. mips-1 and B3 for the levels mips-2 .. first-1 in one cooperative launch over the whole GPU (bloom_levels_kernel).
+extern "C" dfx_status dfx_pass_bloom_levels(void* stream, const dfx_plane* down, const dfx_plane* up, int32_t first, int32_t mips, void* workspace)
+{
+    DFX_PROFILE(stream, "bloom_levels");
+    DFX_REQUIRE(down && up && workspace, "null argument");
+    DFX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+    DFX_REQUIRE(mips >= 2 && mips <= DFX_BLOOM_MAX_LEVELS && first >= 1 && first < mips, "bad level range: first %d of %d levels", first, mips);
+    LevelsArgs a;
+    a.t.first = first, a.t.mips = mips, a.ws = static_cast<unsigned*>(workspace);
+    for (int i = first - 1; i < mips; ++i)
+    {
+        DFX_REQUIRE(make_view<float4>(&down[i], DFX_FORMAT_RGBA32F, a.t.down[i]), "bad down-sampled level %d", i);
+        if (i > first - 1) DFX_REQUIRE(a.t.down[i].w == max(a.t.down[i - 1].w / 2, 1) && a.t.down[i].h == max(a.t.down[i - 1].h / 2, 1), "level %d must be half of level %d", i, i - 1);
+        if (i < mips - 1)
+        {
+            DFX_REQUIRE(make_view<float4>(&up[i], DFX_FORMAT_RGBA32F, a.t.up[i]), "bad up-sampled level %d", i);
+            DFX_REQUIRE(a.t.up[i].w == a.t.down[i].w && a.t.up[i].h == a.t.down[i].h, "up-sampled level %d must have the size of the down-sampled one", i);
+        }
+    }
+    static int grid = 0; // co-resident CTAs of the kernel on the current device
+    if (grid == 0)
+    {
+        int dev = 0, sms = 0, blocks = 0, coop = 0;
+        DFX_CUDA(cudaGetDevice(&dev));
+        DFX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        DFX_REQUIRE(coop, "the device does not support cooperative launches");
+        DFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, bloom_levels_kernel, kLevelsThreads, 0));
+        DFX_REQUIRE(blocks >= 1, "bloom_levels_kernel does not fit on an SM");
+        grid = sms * blocks;
+    }
+    cudaLaunchConfig_t   cfg{};
+    cudaLaunchAttribute  attr{};
+    attr.id              = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kLevelsThreads), cfg.dynamicSmemBytes = 0, cfg.stream = as_stream(stream), cfg.attrs = &attr, cfg.numAttrs = 1;
+    DFX_CUDA(cudaLaunchKernelEx(&cfg, bloom_levels_kernel, a));
+    DFX_LAUNCHED("bloom_levels_kernel");
+    return DFX_OK;
+}
+
+// 1 if a launch of dfx_pass_bloom_levels on this workspace gave up at a barrier (synchronises with the device)
+extern "C" dfx_status dfx_bloom_levels_check(const void* workspace, int32_t* timed_out)
+{
+    DFX_REQUIRE(workspace && timed_out, "null argument");
+    unsigned w[4] = {0, 0, 0, 0};
+    DFX_CUDA(cudaMemcpy(w, workspace, sizeof(w), cudaMemcpyDeviceToHost));
+    *timed_out = w[2] != 0u;
     return DFX_OK;
 }

@@ -490,6 +490,9 @@ extern "C" dfx_status dfx_ssr_get_plane(const dfx_ssr* fx, int32_t id, dfx_plane
 // =====================================================================================================================
 // Bloom
 // =====================================================================================================================
+#ifndef DFX_BLOOM_LEVELS_DEFAULT
+#define DFX_BLOOM_LEVELS_DEFAULT 0
+#endif
 struct dfx_bloom
 {
     int                     w = 0, h = 0;
@@ -497,6 +500,7 @@ struct dfx_bloom
     AlphaTimer              alpha;
     std::vector<PlaneOwner> down, up;
     PlaneOwner              out;
+    PlaneOwner              levels_ws; // barrier words of dfx_pass_bloom_levels (zero between launches)
 };
 
 extern "C" dfx_status dfx_bloom_create(dfx_bloom** out)
@@ -537,6 +541,8 @@ extern "C" dfx_status dfx_bloom_prepare(dfx_bloom* fx, dfx_postfx* postfx, uint3
         if ((st = fx->up[i].alloc(std::max(hw >> i, 1), std::max(hh >> i, 1), DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
     }
     if ((st = fx->out.alloc(fx->w, fx->h, DFX_FORMAT_RGBA32F)) != DFX_OK) return st;
+    if ((st = fx->levels_ws.alloc(16, 1, DFX_FORMAT_R32F)) != DFX_OK) return st;
+    DFX_CUDA(cudaMemset(fx->levels_ws.p.ptr, 0, 64));
     fx->prepared = true;
     return DFX_OK;
 }
@@ -571,19 +577,27 @@ static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attri
     DFX_REQUIRE(mips >= 2, "Bloom radius %.3f leaves fewer than two pyramid levels", A.Radius);
     auto rows = [](const dfx_plane& p) { return dfx_rows{0, p.height}; };
     dfx_status st;
-    // The reference draws one level per pass (Bloom.cpp:324-337 down, :355-375 up). Here the large levels are one launch each
-    // and every level from `first` on (<= 2K texels) is handled, down and up again, by one cluster launch (dfx_pass_bloom_tail).
+    // The reference draws one level per pass (Bloom.cpp:324-337 down, :355-375 up). Here every level after the prefilter, down and up
+    // again, is ONE cooperative launch over the whole GPU (dfx_pass_bloom_levels; dfx_tune "bloom_levels" = 0: the large levels one
+    // launch each and the levels of <= 2K texels in one cluster launch, dfx_pass_bloom_tail).
     dfx_plane down[DFX_BLOOM_MAX_LEVELS], up[DFX_BLOOM_MAX_LEVELS];
     DFX_REQUIRE(mips <= DFX_BLOOM_MAX_LEVELS, "too many Bloom levels");
     for (int i = 0; i < mips; ++i) down[i] = fx->down[i].p, up[i] = fx->up[i].p;
-    const int first = dfx_bloom_tail_first_level(down, mips);
     if ((st = dfx_pass_bloom_prefilter(s, &A, a->color, &down[0], rows(down[0]))) != DFX_OK) return st;
-    for (int i = 1; i < first; ++i)
-        if ((st = dfx_pass_bloom_downsample(s, &down[i - 1], &down[i], rows(down[i]))) != DFX_OK) return st;
-    if (first < mips && (st = dfx_pass_bloom_tail(s, down, up, first, mips)) != DFX_OK) return st;
-    const int top = mips - 1;
-    for (int i = std::min(top, first - 1); i > 0; --i)
-        if ((st = dfx_pass_bloom_upsample(s, &down[i - 1], i != top ? &up[i] : &down[i], &up[i - 1], rows(up[i - 1]))) != DFX_OK) return st;
+    if (dfx_tune_get("bloom_levels", DFX_BLOOM_LEVELS_DEFAULT))
+    {
+        if ((st = dfx_pass_bloom_levels(s, down, up, 1, mips, fx->levels_ws.p.ptr)) != DFX_OK) return st;
+    }
+    else
+    {
+        const int first = dfx_bloom_tail_first_level(down, mips);
+        for (int i = 1; i < first; ++i)
+            if ((st = dfx_pass_bloom_downsample(s, &down[i - 1], &down[i], rows(down[i]))) != DFX_OK) return st;
+        if (first < mips && (st = dfx_pass_bloom_tail(s, down, up, first, mips)) != DFX_OK) return st;
+        const int top = mips - 1;
+        for (int i = std::min(top, first - 1); i > 0; --i)
+            if ((st = dfx_pass_bloom_upsample(s, &down[i - 1], i != top ? &up[i] : &down[i], &up[i - 1], rows(up[i - 1]))) != DFX_OK) return st;
+    }
     if (tonemap)
     {
         const dfx_plane& u0 = fx->up[0].p;

@@ -456,6 +456,15 @@ DFX_API dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_attrib
 #define DFX_BLOOM_MAX_LEVELS 16
 DFX_API dfx_status dfx_pass_bloom_tail(void* stream, const dfx_plane* down, const dfx_plane* up, int32_t first, int32_t mips);
 DFX_API int32_t    dfx_bloom_tail_first_level(const dfx_plane* down, int32_t mips);
+/* The same contract as dfx_pass_bloom_tail for levels of ANY size, in one cooperative launch over the whole GPU: a level is a phase
+ * of a persistent grid, phases are separated by a grid-wide barrier (replaces the 5 + 5 draws of Bloom.cpp:324-337 / :355-375 at 4K).
+ * `workspace`: 64 bytes of device memory, 16-byte aligned, zeroed once by the caller and used by one launch at a time (the kernel
+ * leaves it zeroed). A barrier that is not reached within ~2 s raises an error word in the workspace instead of hanging the GPU:
+ * dfx_bloom_levels_check reads it back (synchronises). Same taps in the same order as the per-level passes (results agree to the last
+ * bit or two: FMA contraction). The effect object uses it when dfx_tune "bloom_levels" is 1; default 0 - under async compute the per-level
+ * launches overlap the next frame better than a grid that needs the whole GPU (profiles/r2j). */
+DFX_API dfx_status dfx_pass_bloom_levels(void* stream, const dfx_plane* down, const dfx_plane* up, int32_t first, int32_t mips, void* workspace);
+DFX_API dfx_status dfx_bloom_levels_check(const void* workspace, int32_t* timed_out);
 
 /* T1 ComputeTemporalAccumulation (TemporalAntiAliasing.cpp:260-289; TAA_ComputeTemporalAccumulation.fx:229-261). */
 DFX_API dfx_status dfx_pass_taa(void* stream, const dfx_camera_attribs* cameras_dev, const dfx_taa_attribs* attribs,

@@ -13,6 +13,10 @@
 #include <vector>
 #include <thread>
 #include <functional>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
+#include <algorithm>
 
 namespace orc
 {
@@ -119,24 +123,103 @@ inline T sample_linear(const Tex<T>& t, float2 uv, Address addr)
 // Nearest-mip selection for a point-mip sampler given a fractional LOD.
 inline int nearest_mip(float lod, int levels) { return clampi(int(std::floor(lod + 0.5f)), 0, levels - 1); }
 
-// Row-parallel helper: the oracle's "all host cores" mode for the cpu_baseline leg. threads<=1 -> serial.
-inline void parallel_rows(int y0, int y1, int threads, const std::function<void(int, int)>& fn)
+// Row-parallel helper: the oracle's "all host cores" mode for the cpu_baseline leg. threads <= 1 -> serial.
+// A persistent pool (no thread creation per pass) deals rows in small dynamic chunks: per-row cost varies by an order of magnitude
+// (sky rows vs reflective rows of the SSR march), and the small pyramid levels are too short for one static chunk per thread.
+// Rows are independent in every pass, so the results do not depend on the schedule.
+class RowPool
 {
-    int rows = y1 - y0;
-    if (threads <= 1 || rows < 2 * threads)
+public:
+    static RowPool& get()
     {
-        fn(y0, y1);
-        return;
+        static RowPool pool;
+        return pool;
     }
-    std::vector<std::thread> pool;
-    int                      chunk = (rows + threads - 1) / threads;
-    for (int t = 0; t < threads; ++t)
+    void run(int y0, int y1, int threads, const std::function<void(int, int)>& fn)
     {
-        int a = y0 + t * chunk, b = std::min(y1, a + chunk);
-        if (a >= b) break;
-        pool.emplace_back(fn, a, b);
+        const int rows = y1 - y0;
+        if (threads <= 1 || rows < 2 || in_job())
+        {
+            fn(y0, y1);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mutex_); // one job at a time (two oracles in one process take turns)
+        ensure_workers(threads - 1);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_     = &fn;
+            end_    = y1;
+            chunk_  = std::max(1, rows / (threads * 8));
+            wanted_ = threads - 1;
+            next_.store(y0, std::memory_order_relaxed);
+            pending_ = int(workers_.size());
+            ++generation_;
+        }
+        cv_work_.notify_all();
+        in_job() = true;
+        drain();
+        in_job() = false;
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
     }
-    for (auto& th : pool) th.join();
-}
+    ~RowPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+
+private:
+    static bool& in_job()
+    {
+        static thread_local bool flag = false;
+        return flag;
+    }
+    void drain()
+    {
+        for (;;)
+        {
+            const int a = next_.fetch_add(chunk_, std::memory_order_relaxed);
+            if (a >= end_) break;
+            (*fn_)(a, std::min(a + chunk_, end_));
+        }
+    }
+    void ensure_workers(int n)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        while (int(workers_.size()) < n)
+        {
+            const int id = int(workers_.size());
+            workers_.emplace_back([this, id, seen = generation_]() mutable {
+                in_job() = true;
+                std::unique_lock<std::mutex> lk2(m_);
+                for (;;)
+                {
+                    cv_work_.wait(lk2, [&] { return stop_ || generation_ != seen; });
+                    if (stop_) return;
+                    seen = generation_;
+                    const bool take = id < wanted_;
+                    lk2.unlock();
+                    if (take) drain();
+                    lk2.lock();
+                    if (--pending_ == 0) cv_done_.notify_one();
+                }
+            });
+        }
+    }
+    std::mutex                             run_mutex_, m_;
+    std::condition_variable                cv_work_, cv_done_;
+    std::vector<std::thread>               workers_;
+    const std::function<void(int, int)>*   fn_ = nullptr;
+    std::atomic<int>                       next_{0};
+    int                                    end_ = 0, chunk_ = 1, wanted_ = 0, pending_ = 0;
+    unsigned                               generation_ = 0;
+    bool                                   stop_ = false;
+};
+inline void parallel_rows(int y0, int y1, int threads, const std::function<void(int, int)>& fn) { RowPool::get().run(y0, y1, threads, fn); }
 
 } // namespace orc

@@ -335,6 +335,65 @@ def test_bloom_tail_and_streaming_kernels(built):
         assert np.array_equal(dn[i], dn_t[i]) or np.abs(dn[i] - dn_t[i]).max() < 1e-6, f"tail down {i}"
 
 
+def test_bloom_levels_kernel(built):
+    """dfx_pass_bloom_levels - every level after the prefilter, down and up, as phases of ONE cooperative launch with grid-wide
+    barriers - against the per-level launches of the same code (streaming on the exact 2:1 levels, generic on the odd-sized ones):
+    same taps in the same order, so the planes agree to the last bit or two (the compiler contracts a*b + c*d into an FMA on one side
+    or the other depending on the surrounding code: 1 ulp differences were observed in the up-sampled levels). The kernel leaves its
+    workspace zeroed (repeated launches on the same workspace give the same planes) and works on a side stream.
+    1024x576 / radius 0.95: levels 1..5 exact, 6..8 generic; 1000x562: nothing exact after level 0."""
+    import torch
+    d = Dev()
+    L = d.lib
+    a = capi.BloomAttribs.default()
+    a.Radius = 0.95
+    for (w, h) in ((1024, 576), (1000, 562)):
+        src = d.up(synth.generate_sequence(w, h, 1)[0]["color"])
+        mips = L.dfx_bloom_mip_count(w // 2, h // 2, C.c_float(a.Radius))
+        shapes = [(max((h // 2) >> i, 1), max((w // 2) >> i, 1)) for i in range(mips)]
+
+        def planes():
+            dn, up = [d.empty(*s_, 4, fill=-7.0) for s_ in shapes], [d.empty(*s_, 4, fill=-7.0) for s_ in shapes]
+            return dn, up, (capi.Plane * mips)(*[d.plane(t) for t in dn]), (capi.Plane * mips)(*[d.plane(t) for t in up])
+
+        L.dfx_tune_set(b"bloom_tail", 0)
+        try:
+            dn, up, pd, pu = planes()
+            capi.check(L.dfx_pass_bloom_prefilter(None, C.byref(a), C.byref(d.plane(src)), C.byref(pd[0]), rows(shapes[0][0])))
+            for i in range(1, mips):
+                capi.check(L.dfx_pass_bloom_downsample(None, C.byref(pd[i - 1]), C.byref(pd[i]), rows(shapes[i][0])))
+            top = mips - 1
+            for i in range(top, 0, -1):
+                capi.check(L.dfx_pass_bloom_upsample(None, C.byref(pd[i - 1]), C.byref(pu[i] if i != top else pd[i]), C.byref(pu[i - 1]), rows(shapes[i - 1][0])))
+            d.sync()
+            want_d, want_u = [d.host(t) for t in dn], [d.host(t) for t in up[:-1]]
+        finally:
+            L.dfx_tune_set(b"bloom_tail", 1)
+
+        ws = torch.zeros(16, dtype=torch.int32, device="cuda")
+        side = torch.cuda.Stream()
+        for attempt, stream in enumerate((None, None, side)):
+            dn, up, pd, pu = planes()
+            sp = C.c_void_p(stream.cuda_stream) if stream is not None else None
+            if stream is not None:
+                stream.wait_stream(torch.cuda.current_stream())
+            capi.check(L.dfx_pass_bloom_prefilter(sp, C.byref(a), C.byref(d.plane(src)), C.byref(pd[0]), rows(shapes[0][0])))
+            capi.check(L.dfx_pass_bloom_levels(sp, pd, pu, 1, mips, C.c_void_p(ws.data_ptr())))
+            d.sync()
+            timed_out = C.c_int32(-1)
+            capi.check(L.dfx_bloom_levels_check(C.c_void_p(ws.data_ptr()), C.byref(timed_out)))
+            assert timed_out.value == 0
+            assert ws.cpu().tolist() == [0] * 16, f"workspace not left zeroed: {ws.cpu().tolist()}"
+            got_d, got_u = [d.host(t) for t in dn], [d.host(t) for t in up[:-1]]
+            for name, got, want in [(f"down {i}", got_d[i], want_d[i]) for i in range(mips)] + [(f"up {i}", got_u[i], want_u[i]) for i in range(mips - 1)]:
+                err = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
+                assert err.max() <= 4e-7, f"{w}x{h} attempt {attempt}: level {name} differs from the per-level launch by {err.max():.2e} (relative)"
+            if attempt == 0:
+                first_d, first_u = got_d, got_u
+            else:   # the same launch repeated: identical bits
+                assert all(np.array_equal(a_, b_) for a_, b_ in zip(got_d + got_u, first_d + first_u)), f"{w}x{h} attempt {attempt}: not reproducible"
+
+
 @pytest.mark.parametrize("flags", [2, 0, 7], ids=["bicubic", "bilinear", "bicubic+ycocg+gauss"])
 def test_taa(ctx, flags):
     d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
