@@ -606,7 +606,7 @@ def main() -> None:
         name, tot, calls = C.create_string_buffer(64), C.c_double(), C.c_int32()
         bloom_mips = lib.dfx_bloom_mip_count(W // 2, H // 2, C.c_float(chain.cfg.bloom.Radius))
         bloom_first = next((i for i in range(1, bloom_mips) if max((W // 2) >> i, 1) * max((H // 2) >> i, 1) <= 2048), bloom_mips)
-        pyramid_bytes = bloom_bytes(W, H, bloom_mips, bloom_first if lib.dfx_tune_get(b"bloom_tail", 1) else bloom_mips)
+        pyramid_bytes = bloom_bytes(W, H, bloom_mips, bloom_first if lib.dfx_tune_get(b"bloom_tail", 0) else bloom_mips)
         step_sum = 0.0
         for i in range(lib.dfx_profile_count()):
             capi.check(lib.dfx_profile_entry(i, name, 64, C.byref(tot), C.byref(calls)))
@@ -673,7 +673,9 @@ def main() -> None:
                                    f"ToneMap Uncharted2 + sRGB) on a {W}x{H} synthetic G-buffer + history, consecutive frames, one sequence per GPU",
                        "width": W, "height": H, "parallelism": f"replicas x{world} (independent frame sequences, no data-path collective)",
                        "streams": ("3 per GPU: SSR chain + TAA | SSAO chain | Bloom + ToneMap (overlaps the next frame's front half); per-pass times in `passes` are "
-                                   "measured serially on one stream" if chain.cfg.overlap else "1 per GPU"),
+                                   "measured serially on one stream, where the depth / AO pyramids use their single-launch TMA tile kernels; with the two halves "
+                                   "side by side the executor issues them one launch per level (the frame is 1.7 % faster that way, profiles/r2k1b)"
+                                   if chain.cfg.overlap else "1 per GPU"),
                        "issue": {**issue, "what": "frames replayed from CUDA graphs (steady state) vs issued eagerly, since the chain was created; "
                                                   "1 native call (dfx_chain_execute) per frame either way"},
                        "tune": os.environ.get("DFX_TUNE", ""), "host_affinity": affinity,

@@ -376,6 +376,15 @@ void dfx_tune_set(const char* name, int32_t value)
     tune_read_env();
     g_tune[name] = value;
 }
+void dfx_tune_unset(const char* name)
+{
+    std::lock_guard<std::mutex> lk(g_tune_mutex);
+    tune_read_env();
+    if (name)
+        g_tune.erase(name);
+    else
+        g_tune.clear();
+}
 int32_t dfx_tune_get(const char* name, int32_t fallback)
 {
     if (!name) return fallback;
@@ -389,6 +398,10 @@ int32_t dfx_tune_get(const char* name, int32_t fallback)
 namespace dfx
 {
 int  tune(const char* name, int fallback) { return dfx_tune_get(name, fallback); }
+// Set by the chain executor while it issues (or records) a frame whose SSR and SSAO halves run side by side on two streams.
+static thread_local bool t_async_compute = false;
+bool async_compute_hint() { return t_async_compute; }
+void set_async_compute_hint(bool on) { t_async_compute = on; }
 bool profiling_enabled() { return g_profile_on; }
 
 // Tensor maps are encoded once per (plane, box) and cached: a frame touches a dozen planes, and encoding costs a driver call.

@@ -472,6 +472,9 @@ __global__ void __launch_bounds__(32 * kStreamWarps) bloom_up2x_stream_kernel(df
 // Per texel the arithmetic is the generic kernels' (same taps, same order): the tail is bit-identical to the per-level launches.
 // =====================================================================================================================
 constexpr int kTailTexels  = 2048; // one cluster = 8 SMs: larger levels are faster as ordinary launches over the whole GPU (measured)
+constexpr int kTailDefault = 0;    // dfx_tune("bloom_tail"): measured at 4K (profiles/r2k1) the tail wins as a pass (0.035 ms against 0.049 ms for the two
+                                   // launches it replaces) and loses as a frame (2.30 vs 2.24 ms): the cluster holds 8 SMs of one GPC for 35 us of
+                                   // dependent latency on the Bloom stream, the per-level launches interleave with the next frame's front half
 constexpr int kTailThreads = 512;
 constexpr int kTailCluster = 8;
 
@@ -841,7 +844,7 @@ extern "C" dfx_status dfx_pass_bloom_composite_tonemap(void* stream, const dfx_b
 // First level the tail kernel takes over: the first one with at most kTailTexels texels (never level 0: it needs a source level).
 extern "C" int32_t dfx_bloom_tail_first_level(const dfx_plane* down, int32_t mips)
 {
-    if (!down || mips < 2 || dfx_tune_get("bloom_tail", 1) == 0) return mips;
+    if (!down || mips < 2 || dfx_tune_get("bloom_tail", kTailDefault) == 0) return mips;
     const long long limit = dfx_tune_get("bloom_tail_texels", kTailTexels);
     for (int i = 1; i < mips; ++i)
         if ((long long)down[i].width * down[i].height <= limit) return i;

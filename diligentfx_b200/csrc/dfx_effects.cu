@@ -577,9 +577,10 @@ static dfx_status bloom_execute_impl(dfx_bloom* fx, const dfx_bloom_render_attri
     DFX_REQUIRE(mips >= 2, "Bloom radius %.3f leaves fewer than two pyramid levels", A.Radius);
     auto rows = [](const dfx_plane& p) { return dfx_rows{0, p.height}; };
     dfx_status st;
-    // The reference draws one level per pass (Bloom.cpp:324-337 down, :355-375 up). Here every level after the prefilter, down and up
-    // again, is ONE cooperative launch over the whole GPU (dfx_pass_bloom_levels; dfx_tune "bloom_levels" = 0: the large levels one
-    // launch each and the levels of <= 2K texels in one cluster launch, dfx_pass_bloom_tail).
+    // The reference draws one level per pass (Bloom.cpp:324-337 down, :355-375 up), and by default so does this: under async compute
+    // the small per-level launches interleave with the next frame's front half, and the frame is fastest that way (profiles/r2k1,
+    // r2j). Two fused forms exist and win as isolated passes: dfx_tune "bloom_tail" = 1 (the levels of <= 2K texels, down and up, in one
+    // thread-block-cluster launch) and "bloom_levels" = 1 (every level after the prefilter in one cooperative launch over the GPU).
     dfx_plane down[DFX_BLOOM_MAX_LEVELS], up[DFX_BLOOM_MAX_LEVELS];
     DFX_REQUIRE(mips <= DFX_BLOOM_MAX_LEVELS, "too many Bloom levels");
     for (int i = 0; i < mips; ++i) down[i] = fx->down[i].p, up[i] = fx->up[i].p;
@@ -864,6 +865,7 @@ extern "C" dfx_status dfx_dof_get_plane(const dfx_dof* fx, int32_t id, dfx_plane
 namespace dfx
 {
 bool profiling_enabled();
+void set_async_compute_hint(bool on);
 }
 
 namespace
@@ -1137,6 +1139,13 @@ extern "C" dfx_status dfx_chain_execute(dfx_chain* c, void* stream, const dfx_ch
     x.side_post    = cfg.overlap && (st & DFX_CHAIN_STAGE_BLOOM) && (st & DFX_CHAIN_STAGE_TAA) && !x.with_dof;
     x.fuse_compose = cfg.fuse && (st & DFX_CHAIN_STAGE_COMPOSE) && (st & DFX_CHAIN_STAGE_TAA);
     x.fuse_tonemap = cfg.fuse && (st & DFX_CHAIN_STAGE_BLOOM) && (st & DFX_CHAIN_STAGE_TONEMAP) && (c->w % 2 == 0) && (c->h % 2 == 0);
+    // launch shapes that depend on whether the two halves of the frame share the GPU (dfx_pyramid.cuh: build_pyramid) read this while
+    // the frame is issued or recorded; it is part of the graph key through cfg.overlap
+    struct AsyncHint
+    {
+        explicit AsyncHint(bool on) { set_async_compute_hint(on); }
+        ~AsyncHint() { set_async_compute_hint(false); }
+    } async_hint(x.side_ao);
 
     // ---- Prepare (HnPostProcessTask.cpp:671-683): host bookkeeping; allocates on the first frame / on a size change
     dfx_status     s;

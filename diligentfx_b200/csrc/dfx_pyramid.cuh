@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(256) pyramid_tile_kernel(Op op, const __grid_c
 // ---- host side ----------------------------------------------------------------------------------------------------------------------
 const CUtensorMap* tensor_map_r32f(const View<float>& plane, int box_w, int box_h); // cached per (pointer, size, pitch, box); nullptr if the plane cannot be described
 int                tune(const char* name, int fallback);
+bool               async_compute_hint(); // the chain executor is issuing a frame whose SSR and SSAO halves share the GPU (dfx_api.cu)
 
 inline int trailing_zeros(int v)
 {
@@ -327,7 +328,12 @@ dfx_status build_pyramid(void* stream, const Op& op, const PyrPlanes<Op::N>& P, 
     max_m           = min(max_m, P.levels - 1);
     const bool full = rows.y0 == 0 && rows.y1 == H;
     int        m    = 1;
-    const int  mode = tune("pyramid_impl", 2); // 2 = TMA tile + cluster tail, 1 = tile staged with plain loads + tail, 0 = one launch per level
+    // 2 = TMA tile + cluster tail, 1 = tile staged with plain loads + tail, 0 = one launch per level. As an isolated pass the tile kernel is
+    // twice as fast as the per-level launches (0.019 vs 0.040 ms for the 4K Hi-Z), but with the SSR and SSAO halves of the frame side by
+    // side on two streams the FRAME is 1.7 % faster with per-level launches (2.218 vs 2.255 ms, profiles/r2k1b): a tile CTA holds 256
+    // threads and 16-32 KB of shared memory while ever fewer of its threads reduce the upper levels, and that residency is taken from
+    // the issue-bound kernel of the other stream; small CTAs that come and go share the SMs better. So the default follows the issuer.
+    const int  mode = tune("pyramid_impl", async_compute_hint() ? 0 : 2);
     if (full && mode != 0 && max_m >= 1)
     {
         const int K = min(min(trailing_zeros(W), trailing_zeros(H)), min(max_m, 6));
@@ -355,7 +361,7 @@ dfx_status build_pyramid(void* stream, const Op& op, const PyrPlanes<Op::N>& P, 
     for (; m <= max_m; ++m)
     {
         const int lw = P.lv[0][m].w, lh = P.lv[0][m].h;
-        if (full && mode != 0 && (long long)lw * lh <= kPyrTailTexels)
+        if (full && mode != 0 && tune("pyramid_tail", 1) && (long long)lw * lh <= kPyrTailTexels)
         {
             pyramid_tail_kernel<Op><<<kPyrTailCluster, kPyrTailThreads, 0, s>>>(op, P, m, max_m);
             DFX_LAUNCHED(what);

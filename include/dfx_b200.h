@@ -452,7 +452,10 @@ DFX_API dfx_status dfx_pass_bloom_composite(void* stream, const dfx_bloom_attrib
  * (the reference issues one draw per level, Bloom.cpp:324-337 and :355-375; on the small levels of the pyramid those dependent
  * launches cost more than the work). `down` / `up` are arrays of `mips` planes (level i = max(level0 >> i, 1)); reads
  * down[first-1], writes down[first..mips-1] and up[first-1..mips-2]. Results are bit-identical to the per-level passes.
- * dfx_bloom_tail_first_level: the level the effect object hands over to this pass (first one with <= 2048 texels; `mips` = none). */
+ * dfx_bloom_tail_first_level: the level the effect object hands over to this pass (`mips` = none). Off by default (dfx_tune "bloom_tail" =
+ * 1 switches it on: first level with <= "bloom_tail_texels" = 2048 texels): as a pass the cluster launch beats the per-level launches of the
+ * same levels, but a cluster occupies 8 SMs of one GPC for 35 us, and under async compute the whole frame is 2 % faster without it
+ * (profiles/r2k1). */
 #define DFX_BLOOM_MAX_LEVELS 16
 DFX_API dfx_status dfx_pass_bloom_tail(void* stream, const dfx_plane* down, const dfx_plane* up, int32_t first, int32_t mips);
 DFX_API int32_t    dfx_bloom_tail_first_level(const dfx_plane* down, int32_t mips);
@@ -555,6 +558,7 @@ DFX_API int32_t dfx_bloom_mip_count(uint32_t width, uint32_t height, float radiu
  * different kernel. Unknown names read as `fallback`. Also settable at load time: DFX_TUNE="name=value,name=value". */
 DFX_API void    dfx_tune_set(const char* name, int32_t value);
 DFX_API int32_t dfx_tune_get(const char* name, int32_t fallback);
+DFX_API void    dfx_tune_unset(const char* name); /* back to the built-in default (NULL: every knob) */
 
 /* ============================================================================================================ */
 /* 2. effect level                                                                                              */

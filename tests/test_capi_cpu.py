@@ -117,3 +117,5 @@ def test_chain_level_layouts_and_defaults():
     assert lib.dfx_tune_get(b"no_such_knob", 7) == 7
     lib.dfx_tune_set(b"unit_test_knob", 3)
     assert lib.dfx_tune_get(b"unit_test_knob", 0) == 3
+    lib.dfx_tune_unset(b"unit_test_knob")
+    assert lib.dfx_tune_get(b"unit_test_knob", 5) == 5

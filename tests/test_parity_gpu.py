@@ -159,6 +159,43 @@ def test_ssao_convolute_resample_spatial(ctx):
     print(assert_close("ssao spatial (output)", d.host(out), o.get("ssao_out"), tol=2e-4, max_outliers=2e-3, min_psnr=60.0))
 
 
+def test_pyramid_launch_shapes_agree(built):
+    """The three depth / AO pyramids through their three launch shapes (dfx_tune "pyramid_impl": 2 = one TMA-staged tile kernel for the
+    even levels + cluster tail, 1 = the same with plain loads, 0 = one launch per level - what the chain executor uses when the SSR and
+    SSAO halves of the frame share the GPU): the same reduction per texel, so Hi-Z (a min) is bit-identical and the two averaging pyramids
+    agree to rounding. 512x288: levels 1-5 from the tile kernel; 320x432: level 4 onward odd-sized."""
+    d = Dev()
+    L = d.lib
+    a = capi.SSAOAttribs.default()
+    for (w, h) in ((512, 288), (320, 432)):
+        fr = synth.generate_sequence(w, h, 1)[0]
+        cams = d.cameras(fr["curr_camera"], fr["prev_camera"])
+        shapes = [(max(h >> i, 1), max(w >> i, 1)) for i in range(7)]
+        ao0 = np.random.default_rng(3).random((h, w), dtype=np.float32)
+        got = {}
+        try:
+            for impl in (2, 1, 0):
+                L.dfx_tune_set(b"pyramid_impl", impl)
+                hiz = [d.up(fr["depth"])] + [d.empty(*s_, fill=-3.0) for s_ in shapes[1:]]
+                pre = [d.up(fr["depth"])] + [d.empty(*s_, fill=-3.0) for s_ in shapes[1:5]]
+                occ = [d.up(ao0)] + [d.empty(*s_, fill=-3.0) for s_ in shapes[1:5]]
+                dep = [d.up(fr["depth"])] + [d.empty(*s_, fill=-3.0) for s_ in shapes[1:5]]
+                capi.check(L.dfx_pass_ssr_hiz(None, C.byref(d.pyr(hiz)), rows(h)))
+                capi.check(L.dfx_pass_ssao_prefilter_depth(None, cams, C.byref(a), C.byref(d.pyr(pre)), rows(h)))
+                capi.check(L.dfx_pass_ssao_convolute(None, C.byref(d.pyr(occ)), C.byref(d.pyr(dep)), rows(h)))
+                d.sync()
+                got[impl] = dict(hiz=[d.host(t) for t in hiz[1:]], pre=[d.host(t) for t in pre[1:]], occ=[d.host(t) for t in occ[1:]], dep=[d.host(t) for t in dep[1:]])
+        finally:
+            L.dfx_tune_unset(b"pyramid_impl")
+        for impl in (2, 1):
+            for i, (x, y) in enumerate(zip(got[impl]["hiz"], got[0]["hiz"])):
+                assert np.array_equal(x, y), f"{w}x{h} Hi-Z level {i + 1}: impl {impl} differs from the per-level launches"
+            for name in ("pre", "occ", "dep"):
+                for i, (x, y) in enumerate(zip(got[impl][name], got[0][name])):
+                    err = np.abs(x - y).max()   # depth near 1.0: one ulp is 6e-8; the prefilter's view-space average amplifies it through 1/z
+                    assert err <= (1e-6 if name == "pre" else 2.5e-7), f"{w}x{h} {name} level {i + 1}: impl {impl} differs from the per-level launches by {err:.2e}"
+
+
 def test_ssr_hiz_and_mask(ctx):
     d, o, fr, h, w = Dev(), ctx["o"], ctx["fr"], ctx["h"], ctx["w"]
     want = _pyr_names(o, "ssr_hiz", 7)
@@ -323,7 +360,7 @@ def test_bloom_tail_and_streaming_kernels(built):
         _, dn_g, up_g = run(2, 0)   # generic gather kernels, one launch per level
         _, dn_t, up_t = run(1, 0)   # streaming kernels, per-level launches for the small levels
     finally:
-        L.dfx_tune_set(b"bloom_impl", 1), L.dfx_tune_set(b"bloom_tail", 1)
+        L.dfx_tune_unset(b"bloom_impl"), L.dfx_tune_unset(b"bloom_tail")
     for i in range(mips):
         print(assert_close(f"bloom down {i} (stream + tail)", dn[i], want_d[i], tol=1e-5, min_psnr=95.0, hdr=True))
         assert_close(f"bloom down {i} vs generic kernels", dn[i], dn_g[i], tol=1e-5, min_psnr=100.0, hdr=True)
@@ -368,7 +405,7 @@ def test_bloom_levels_kernel(built):
             d.sync()
             want_d, want_u = [d.host(t) for t in dn], [d.host(t) for t in up[:-1]]
         finally:
-            L.dfx_tune_set(b"bloom_tail", 1)
+            L.dfx_tune_unset(b"bloom_tail")
 
         ws = torch.zeros(16, dtype=torch.int32, device="cuda")
         side = torch.cuda.Stream()
@@ -562,22 +599,30 @@ def test_async_compute_equals_single_stream(ctx):
 
     from diligentfx_b200.chain import ChainConfig, PostProcessChain
     seq, h, w = ctx["seq"], ctx["h"], ctx["w"]
-    a, b, c = (PostProcessChain(w, h, ChainConfig(overlap=o)) for o in (True, False, True))
-    deferred = []
-    for rep in range(3):  # 12 frames: long enough for the ping-pong planes to be reused several times
-        for k, fr in enumerate(seq):
-            idx = rep * len(seq) + k
-            f2 = {**fr, "frame": idx}
-            la, lb = a.run_frame(f2).cpu().numpy(), b.run_frame(f2).cpu().numpy()
-            assert np.array_equal(la, lb), f"frame {idx}: max abs diff {np.abs(la - lb).max()}"
-            c.upload(f2)
-            out = torch.empty_like(c.ldr)
-            c.execute(idx, f2["curr_camera"], f2["prev_camera"], ldr_out=out, defer_post=True)
-            deferred.append((out, lb))
-    c.join()
-    for idx, (out, want) in enumerate(deferred):
-        assert np.array_equal(out.cpu().numpy(), want), f"deferred frame {idx} differs"
-    a.close(), b.close(), c.close()
+    from diligentfx_b200 import capi as _capi
+    lib = _capi.load()
+    # the executor picks the pyramids' launch shape by whether the two halves share the GPU (build_pyramid); pin it, so that this test
+    # compares the issue ORDER only (the shapes against each other: test_pyramid_launch_shapes_agree)
+    lib.dfx_tune_set(b"pyramid_impl", 2)
+    try:
+        a, b, c = (PostProcessChain(w, h, ChainConfig(overlap=o)) for o in (True, False, True))
+        deferred = []
+        for rep in range(3):  # 12 frames: long enough for the ping-pong planes to be reused several times
+            for k, fr in enumerate(seq):
+                idx = rep * len(seq) + k
+                f2 = {**fr, "frame": idx}
+                la, lb = a.run_frame(f2).cpu().numpy(), b.run_frame(f2).cpu().numpy()
+                assert np.array_equal(la, lb), f"frame {idx}: max abs diff {np.abs(la - lb).max()}"
+                c.upload(f2)
+                out = torch.empty_like(c.ldr)
+                c.execute(idx, f2["curr_camera"], f2["prev_camera"], ldr_out=out, defer_post=True)
+                deferred.append((out, lb))
+        c.join()
+        for idx, (out, want) in enumerate(deferred):
+            assert np.array_equal(out.cpu().numpy(), want), f"deferred frame {idx} differs"
+        a.close(), b.close(), c.close()
+    finally:
+        lib.dfx_tune_unset(b"pyramid_impl")
 
 
 def test_full_chain_four_frames(ctx):
