@@ -17,6 +17,7 @@
 #include <condition_variable>
 #include <atomic>
 #include <algorithm>
+#include <memory>
 
 namespace orc
 {
@@ -144,18 +145,19 @@ public:
             return;
         }
         std::lock_guard<std::mutex> serial(run_mutex_); // one job at a time (two oracles in one process take turns)
-        ensure_workers(threads - 1);
+        const int helpers = std::min(threads - 1, rows - 1); // never more threads than rows
+        ensure_workers(helpers);
         {
             std::lock_guard<std::mutex> lk(m_);
-            fn_     = &fn;
-            end_    = y1;
-            chunk_  = std::max(1, rows / (threads * 8));
-            wanted_ = threads - 1;
+            fn_      = &fn;
+            end_     = y1;
+            chunk_   = std::max(1, rows / ((helpers + 1) * 8));
             next_.store(y0, std::memory_order_relaxed);
-            pending_ = int(workers_.size());
+            pending_ = helpers;
             ++generation_;
+            for (int i = 0; i < helpers; ++i) workers_[i]->wanted = generation_;
         }
-        cv_work_.notify_all();
+        for (int i = 0; i < helpers; ++i) workers_[i]->cv.notify_one(); // only the workers this job uses wake up
         in_job() = true;
         drain();
         in_job() = false;
@@ -169,11 +171,17 @@ public:
             std::lock_guard<std::mutex> lk(m_);
             stop_ = true;
         }
-        cv_work_.notify_all();
-        for (auto& t : workers_) t.join();
+        for (auto& w : workers_) w->cv.notify_one();
+        for (auto& w : workers_) w->th.join();
     }
 
 private:
+    struct Worker
+    {
+        std::thread             th;
+        std::condition_variable cv;
+        unsigned                wanted = 0, seen = 0; // generation this worker is asked to join / has joined (guarded by m_)
+    };
     static bool& in_job()
     {
         static thread_local bool flag = false;
@@ -193,32 +201,32 @@ private:
         std::lock_guard<std::mutex> lk(m_);
         while (int(workers_.size()) < n)
         {
-            const int id = int(workers_.size());
-            workers_.emplace_back([this, id, seen = generation_]() mutable {
+            workers_.emplace_back(new Worker);
+            Worker* w = workers_.back().get();
+            w->th     = std::thread([this, w] {
                 in_job() = true;
                 std::unique_lock<std::mutex> lk2(m_);
                 for (;;)
                 {
-                    cv_work_.wait(lk2, [&] { return stop_ || generation_ != seen; });
+                    w->cv.wait(lk2, [&] { return stop_ || w->wanted != w->seen; });
                     if (stop_) return;
-                    seen = generation_;
-                    const bool take = id < wanted_;
+                    w->seen = w->wanted;
                     lk2.unlock();
-                    if (take) drain();
+                    drain();
                     lk2.lock();
                     if (--pending_ == 0) cv_done_.notify_one();
                 }
             });
         }
     }
-    std::mutex                             run_mutex_, m_;
-    std::condition_variable                cv_work_, cv_done_;
-    std::vector<std::thread>               workers_;
-    const std::function<void(int, int)>*   fn_ = nullptr;
-    std::atomic<int>                       next_{0};
-    int                                    end_ = 0, chunk_ = 1, wanted_ = 0, pending_ = 0;
-    unsigned                               generation_ = 0;
-    bool                                   stop_ = false;
+    std::mutex                           run_mutex_, m_;
+    std::condition_variable              cv_done_;
+    std::vector<std::unique_ptr<Worker>> workers_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    std::atomic<int>                     next_{0};
+    int                                  end_ = 0, chunk_ = 1, pending_ = 0;
+    unsigned                             generation_ = 0;
+    bool                                 stop_ = false;
 };
 inline void parallel_rows(int y0, int y1, int threads, const std::function<void(int, int)>& fn) { RowPool::get().run(y0, y1, threads, fn); }
 
