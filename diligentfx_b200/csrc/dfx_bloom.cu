@@ -13,6 +13,7 @@
 #include "dfx_tonemap.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <atomic>
 
 namespace dfx
 {
@@ -670,7 +671,10 @@ static int bloom_impl() { return dfx_tune_get("bloom_impl", 1); }
 template <class K>
 static int stream_rows_per_warp(K kernel, int warp_columns, int rows, int min_rows)
 {
-    static int slots = 0; // resident warps of this kernel on the current device (one static per kernel instantiation)
+    // resident warps of this kernel (one static per kernel instantiation). Cached once per process: the GPUs of a node are identical, and
+    // two threads racing here store the same value.
+    static std::atomic<int> cached{0};
+    int                     slots = cached.load(std::memory_order_relaxed);
     if (slots == 0)
     {
         int dev = 0, sms = 148, blocks = 4;
@@ -678,6 +682,7 @@ static int stream_rows_per_warp(K kernel, int warp_columns, int rows, int min_ro
         (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, 32 * kStreamWarps, 0) != cudaSuccess || blocks < 1) blocks = 4;
         slots = sms * blocks * kStreamWarps;
+        cached.store(slots, std::memory_order_relaxed);
     }
     const int per_column = std::max(slots / std::max(warp_columns, 1), 1);
     return std::max(div_up(rows, per_column), min_rows);
@@ -893,7 +898,8 @@ extern "C" dfx_status dfx_pass_bloom_levels(void* stream, const dfx_plane* down,
             DFX_REQUIRE(a.t.up[i].w == a.t.down[i].w && a.t.up[i].h == a.t.down[i].h, "up-sampled level %d must have the size of the down-sampled one", i);
         }
     }
-    static int grid = 0; // co-resident CTAs of the kernel on the current device
+    static std::atomic<int> cached_grid{0}; // co-resident CTAs of the kernel (identical GPUs: see stream_rows_per_warp)
+    int                     grid = cached_grid.load(std::memory_order_relaxed);
     if (grid == 0)
     {
         int dev = 0, sms = 0, blocks = 0, coop = 0;
@@ -904,6 +910,7 @@ extern "C" dfx_status dfx_pass_bloom_levels(void* stream, const dfx_plane* down,
         DFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, bloom_levels_kernel, kLevelsThreads, 0));
         DFX_REQUIRE(blocks >= 1, "bloom_levels_kernel does not fit on an SM");
         grid = sms * blocks;
+        cached_grid.store(grid, std::memory_order_relaxed);
     }
     cudaLaunchConfig_t   cfg{};
     cudaLaunchAttribute  attr{};
