@@ -22,6 +22,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <memory>
 #include <ucontext.h>
 #include <vector>
 
@@ -478,42 +479,57 @@ template <class T = float4> struct TextureCube
 // the threads per pass would cost more than shading the pixels.
 struct row_pool
 {
+    struct worker
+    {
+        std::condition_variable cv;
+        unsigned long long      wanted = 0, seen = 0; // generation this worker is asked to join / has joined (guarded by m)
+    };
     std::mutex                                m;
-    std::condition_variable                   cv_work, cv_done;
-    std::vector<std::thread>                  workers;
+    std::condition_variable                   cv_done;
+    std::vector<std::unique_ptr<worker>>      workers;
     const std::function<void(int, int)>*      fn = nullptr;
     std::atomic<int>                          next{0};
-    int                                       height = 0, chunk = 1, active = 0, pending = 0;
+    int                                       height = 0, chunk = 1, pending = 0;
     unsigned long long                        generation = 0;
 
     explicit row_pool(int n)
     {
-        for (int w = 0; w < n; ++w)
-            workers.emplace_back([this, w] {
-                unsigned long long seen = 0;
+        for (int i = 0; i < n; ++i)
+        {
+            workers.emplace_back(new worker);
+            worker* w = workers.back().get();
+            std::thread([this, w] {
+                std::unique_lock<std::mutex> lk(m);
                 for (;;)
                 {
-                    {
-                        std::unique_lock<std::mutex> lk(m);
-                        cv_work.wait(lk, [&] { return generation != seen; });
-                        seen = generation;
-                    }
-                    if (w < active)
-                        for (int y = next.fetch_add(chunk); y < height; y = next.fetch_add(chunk)) (*fn)(y, std::min(height, y + chunk));
-                    {
-                        std::lock_guard<std::mutex> lk(m);
-                        if (--pending == 0) cv_done.notify_one();
-                    }
+                    w->cv.wait(lk, [&] { return w->wanted != w->seen; });
+                    w->seen = w->wanted;
+                    lk.unlock();
+                    drain();
+                    lk.lock();
+                    if (--pending == 0) cv_done.notify_one();
                 }
-            });
-        for (auto& t : workers) t.detach();
+            }).detach();
+        }
     }
+    void drain()
+    {
+        for (int y = next.fetch_add(chunk); y < height; y = next.fetch_add(chunk)) (*fn)(y, std::min(height, y + chunk));
+    }
+    // `threads` row workers in total: the caller is one of them, and only the helpers this pass uses are woken (waking all 128 workers
+    // of a big host for every one of the ~80 passes of a frame costs more than a small pass's pixels)
     void run(int h, int threads, const std::function<void(int, int)>& f)
     {
+        const int helpers = std::min(threads - 1, int(workers.size()));
+        {
+            std::lock_guard<std::mutex> lk(m);
+            fn = &f, height = h, chunk = std::max(1, h / (8 * threads)), pending = helpers;
+            next = 0, ++generation;
+            for (int i = 0; i < helpers; ++i) workers[i]->wanted = generation;
+        }
+        for (int i = 0; i < helpers; ++i) workers[i]->cv.notify_one();
+        drain();
         std::unique_lock<std::mutex> lk(m);
-        fn = &f, height = h, chunk = std::max(1, h / (4 * threads)), active = threads, pending = int(workers.size());
-        next = 0, ++generation;
-        cv_work.notify_all();
         cv_done.wait(lk, [&] { return pending == 0; });
     }
 };
@@ -526,7 +542,7 @@ inline void for_rows(int height, int threads, const std::function<void(int, int)
 {
     static std::mutex           one_pass_at_a_time;
     row_pool&                   pool = the_row_pool();
-    threads = std::min(threads, int(pool.workers.size()));
+    threads = std::min(std::min(threads, int(pool.workers.size())), height / 2);
     if (threads <= 1 || height < 8) return fn(0, height);
     std::lock_guard<std::mutex> lk(one_pass_at_a_time);
     pool.run(height, threads, fn);
