@@ -185,7 +185,7 @@ def cpu_baseline(width: int, height: int, frames: int, threads: int) -> dict:
     return {"value": round(mpix, 3), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{len(steady)} consecutive {width}x{height} frames of the full chain (1/{(3840 * 2160) // (width * height)} of a 4K frame each), "
                       f"median; scalar C++ oracle (each pass bit-exact against the reference's own HLSL shader run on the CPU, "
-                      f"tests/test_reference_shaders.py), row-parallel std::thread"}
+                      f"tests/test_reference_shaders.py), rows dealt to a persistent std::thread pool"}
 
 
 def psnr_vs_oracle(seq, W: int, H: int, threads: int) -> dict:
@@ -406,7 +406,7 @@ def run_reference(args) -> None:
     port_value = w * h / 1e6 / (port_ms / 1e3)
     frame = f"each step = one {w}x{h} frame of the full chain (1/{(args.width * args.height) // (w * h)} of the {args.width}x{args.height} workload)"
     port = {"value": round(port_value, 3), "unit": UNIT, "ms_per_step": round(port_ms, 3), "cores": threads,
-            "what": "the scalar C++ oracle port, each pass bit-exact against the reference's shaders (tests/test_reference_shaders.py), row-parallel std::thread"}
+            "what": "the scalar C++ oracle port, each pass bit-exact against the reference's shaders (tests/test_reference_shaders.py), rows dealt to a persistent std::thread pool"}
     shader_s = _time_reference_shaders(seq, w, h, args.warmup, args.steps)
     if shader_s is not None:
         ms, kind = shader_s * 1e3, "reference"
@@ -654,7 +654,9 @@ def main() -> None:
     os.sched_setaffinity(0, all_cpus)   # the CPU legs (oracle baseline, PSNR check) may use every host core again
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.ref_width, args.ref_height, 3, os.cpu_count() or 1)
+        # a quarter of the workload's frame, 4 consecutive frames (median of the last 3): ~5-10 s on the GPU boxes' hosts. Larger than the
+        # --impl reference arm's per-step sample on purpose: with 128 cores a 540-row frame leaves 4 rows per thread and times the pool.
+        cpu = cpu_baseline(max(args.ref_width, 1920), max(args.ref_height, 1080), 4, os.cpu_count() or 1)
     quality = None
     if rank == 0 and not args.no_psnr and (world == 1 or args.psnr):   # one check per build: the N = 1 line carries it (N > 1 would idle N - 1 GPUs meanwhile)
         quality = psnr_vs_oracle([{**fr, "frame": i} for i, fr in enumerate(seq)], W, H, os.cpu_count() or 1)
